@@ -1,0 +1,145 @@
+"""CPU: the oracle restatement (oracle/harp_oracle.py) against golden vectors produced by the reference's own Python
+(tests/golden/make_golden.py), plus self-checks of the restated PyTorch3D primitives."""
+import math
+
+import pytest
+import torch
+
+import harp_oracle as O
+from pytorch3d import _core as p3d, _raster
+from util import load_golden, golden_case, rel_l2
+
+
+@pytest.mark.parametrize("name", ["c1_sil_256_coarse", "c2_full_128_sub"])
+def test_oracle_matches_reference_golden(name):
+    g = load_golden(name)
+    model, topo, params, batch, cfg = golden_case(g)
+    losses, img, grads = O.step(model, topo, params, batch, cfg)
+    for k, v in losses.items():
+        assert math.isclose(float(v), float(g["loss_" + k]), rel_tol=1e-6, abs_tol=1e-9), k
+    assert (img["sil"] - torch.tensor(g["img_sil"])).abs().max() <= 1e-6
+    # shadow taps are `.round()`-selected and sharpened x1000 (renderer_helper.py:385,406): a 1-ulp change in the
+    # centroid reduction order (thread-count dependent) can move a handful of pixels by ~1e-4
+    drgb = (img["rgb"] - torch.tensor(g["img_rgb"])).abs()
+    assert float((drgb <= 1e-6).double().mean()) >= 0.9995 and float(drgb.max()) < 5e-3
+    assert (img["verts"] - torch.tensor(g["verts"])).abs().max() <= 1e-7
+    assert int(img["sil_overflow"]) == int(g["sil_overflow"])
+    for k, v in grads.items():
+        gg = torch.tensor(g["grad_" + ("light_positions" if k == "light_position" else k)])
+        if k == "light_position":
+            gg = gg[0]  # share_light_position: only row 0 is used (optimize_sequence.py:453-454)
+        if float(gg.abs().max()) == 0.0:
+            assert float(v.abs().max()) == 0.0, k
+        else:
+            assert rel_l2(v, gg) < 1e-5, (k, rel_l2(v, gg))
+
+
+def _brute_force_raster(verts, faces, S, blur, K, clip):
+    """Literal per-pixel / per-face double loop of SURVEY.md A.3 (python floats via float64 tensors)."""
+    import numpy as np
+    v = verts.double().numpy(); f = faces.numpy()
+    p2f = -np.ones((S, S, K), np.int64); zb = -np.ones((S, S, K)); ds = -np.ones((S, S, K))
+    r = math.sqrt(blur)
+    edge = lambda p, a, b: (p[0] - a[0]) * (b[1] - a[1]) - (p[1] - a[1]) * (b[0] - a[0])
+
+    def pld(p, a, b):
+        ba = b - a; l2 = ba @ ba
+        if l2 <= 1e-8:
+            return (p - b) @ (p - b)
+        t = min(max(ba @ (p - a) / l2, 0.0), 1.0)
+        d = a + t * ba - p
+        return d @ d
+    for yi in range(S):
+        for xi in range(S):
+            p = np.array([-1 + (2 * (S - 1 - xi) + 1) / S, -1 + (2 * (S - 1 - yi) + 1) / S])
+            q = []
+            for fi, (a, b, c) in enumerate(f):
+                v0, v1, v2 = v[a], v[b], v[c]
+                xs, ys = (v0[0], v1[0], v2[0]), (v0[1], v1[1], v2[1])
+                if p[0] > max(xs) + r or p[0] < min(xs) - r or p[1] > max(ys) + r or p[1] < min(ys) - r:
+                    continue
+                area_f = edge(v0[:2], v1[:2], v2[:2])
+                if max(v0[2], v1[2], v2[2]) < 0 or abs(area_f) <= 1e-8:
+                    continue
+                area = edge(v2[:2], v0[:2], v1[:2]) + 1e-8
+                w = np.array([edge(p, v1[:2], v2[:2]), edge(p, v2[:2], v0[:2]), edge(p, v0[:2], v1[:2])]) / area
+                top = np.array([w[0] * v1[2] * v2[2], v0[2] * w[1] * v2[2], v0[2] * v1[2] * w[2]])
+                b_ = top / max(top.sum(), 1e-8)
+                bc = b_
+                if clip:
+                    bc = np.maximum(b_, 0); bc = bc / max(bc.sum(), 1e-5)
+                pz = bc @ np.array([v0[2], v1[2], v2[2]])
+                if pz < 0:
+                    continue
+                dist = min(pld(p, v0[:2], v1[:2]), pld(p, v0[:2], v2[:2]), pld(p, v1[:2], v2[:2]))
+                inside = (b_ > 0).all()
+                if not inside and dist >= blur:
+                    continue
+                q.append((pz, fi, -dist if inside else dist))
+            q.sort(key=lambda t: t[0])
+            for k, (pz, fi, sd) in enumerate(q[:K]):
+                p2f[yi, xi, k], zb[yi, xi, k], ds[yi, xi, k] = fi, pz, sd
+    return p2f, zb, ds
+
+
+def test_rasteriser_vs_brute_force():
+    torch.manual_seed(0)
+    V, Fn, S = 12, 16, 12
+    verts = torch.cat([torch.rand(V, 2) * 1.6 - 0.8, 0.5 + torch.rand(V, 1)], 1).double()
+    faces = torch.stack([torch.randperm(V)[:3] for _ in range(Fn)], 0)
+    for blur, K, clip in ((0.0, 1, False), (2e-3, 4, True)):
+        p2f, zb, ba, ds, _ = _raster.rasterize_one(verts, faces, S, blur, K, True, clip)
+        bp, bz, bd = _brute_force_raster(verts, faces, S, blur, K, clip)
+        assert (p2f.numpy() == bp).all()
+        assert torch.allclose(zb, torch.tensor(bz), atol=1e-12)
+        assert torch.allclose(ds, torch.tensor(bd), atol=1e-12)
+
+
+def test_mesh_primitives_flat_grid():
+    n = 5
+    ys, xs = torch.meshgrid(torch.arange(n), torch.arange(n), indexing="ij")
+    v = torch.stack([xs.flatten().float(), ys.flatten().float(), torch.zeros(n * n)], 1)
+    idx = lambda i, j: i * n + j
+    f = []
+    for i in range(n - 1):
+        for j in range(n - 1):
+            f += [[idx(i, j), idx(i, j + 1), idx(i + 1, j)], [idx(i + 1, j), idx(i, j + 1), idx(i + 1, j + 1)]]
+    m = p3d.Meshes(v[None], torch.tensor(f)[None])
+    assert float(p3d.mesh_normal_consistency(m)) < 1e-6           # flat => all dihedral cosines are 1
+    assert torch.allclose(m.verts_normals_packed().abs(), torch.tensor([0.0, 0.0, 1.0]).expand(n * n, 3), atol=1e-6)
+    e = m.edges_packed()
+    assert e.shape[0] == (n - 1) * n * 2 + (n - 1) ** 2 and bool((e[:, 0] < e[:, 1]).all())
+    sub = p3d.SubdivideMeshes(m)(m)
+    assert sub.verts_padded().shape[1] == n * n + e.shape[0] and sub.faces_padded().shape[1] == 4 * len(f)
+
+
+def test_rodrigues_matches_closed_form():
+    a = torch.randn(64, 3, dtype=torch.float64) * 0.7
+    R = O.batch_rodrigues(a).view(-1, 3, 3)
+    th = a.norm(dim=1).view(-1, 1, 1)
+    k = a / th.view(-1, 1)
+    Kx = torch.zeros(64, 3, 3, dtype=torch.float64)
+    Kx[:, 0, 1], Kx[:, 0, 2], Kx[:, 1, 0], Kx[:, 1, 2], Kx[:, 2, 0], Kx[:, 2, 1] = -k[:, 2], k[:, 1], k[:, 2], -k[:, 0], -k[:, 1], k[:, 0]
+    Rc = torch.eye(3, dtype=torch.float64) + torch.sin(th) * Kx + (1 - torch.cos(th)) * Kx @ Kx
+    assert (R - Rc).abs().max() < 1e-7
+
+
+def test_oracle_silhouette_gradient_finite_difference():
+    """float64 central differences on the soft-silhouette loss w.r.t. cam (visibility-flip free at this step size)."""
+    g = load_golden("c1_sil_256_coarse")
+    model, topo, params, batch, cfg = golden_case(g, dtype=torch.float64)
+    cfg = dict(cfg, img_size=64, focal_length=1000.0 * 64 / 224.0, render_rgb=False, mesh_losses=False)
+    batch = dict(batch, y_sil=torch.zeros(1, 64, 64, dtype=torch.float64))
+    batch.pop("init_joints")
+
+    def loss(cam):
+        p = dict(params, cam=cam)
+        l, _ = O.forward_losses(model, topo, p, batch, cfg)
+        return l["silhouette"]
+    cam = params["cam"].clone().requires_grad_(True)
+    ga, = torch.autograd.grad(loss(cam), cam)
+    h = 1e-7
+    for i in range(3):
+        d = torch.zeros_like(cam); d[0, i] = h
+        fd = (loss(cam.detach() + d) - loss(cam.detach() - d)) / (2 * h)
+        assert abs(float(fd) - float(ga[0, i])) <= 2e-2 * max(1e-3, abs(float(ga[0, i]))), (i, float(fd), float(ga[0, i]))
