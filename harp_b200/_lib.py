@@ -1,0 +1,92 @@
+"""ctypes binding of libharpb200.so (the C ABI declared in include/harp_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or cannot be loaded, importing the CUDA-backed ops
+raises.  (The oracle under `oracle/` is test infrastructure and is never imported from here.)
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libharpb200.so")
+
+c_float_p = C.POINTER(C.c_float)
+c_int32_p = C.POINTER(C.c_int32)
+
+
+class HarpTopology(C.Structure):
+    _fields_ = [("V0", C.c_int32), ("F0", C.c_int32), ("faces0", c_int32_p), ("subdivide", C.c_int32),
+                ("Vt", C.c_int32), ("faces_uvs", c_int32_p), ("verts_uvs", c_float_p)]
+
+
+class HarpManoModel(C.Structure):
+    _fields_ = [("shapedirs", c_float_p), ("posedirs", c_float_p), ("v_template", c_float_p),
+                ("J_regressor", c_float_p), ("weights", c_float_p), ("hands_mean", c_float_p), ("tips", c_int32_p)]
+
+
+class HarpShadeGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d_verts", "d_normals", "d_cam_R", "d_cam_T", "d_light_R", "d_light_T",
+                                          "d_light_pos", "d_amb", "d_texture", "d_normal_map")]
+
+
+class HarpError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# every symbol include/harp_b200.h declares (tests/test_abi.py checks the library exports exactly these)
+SYMBOLS = ["harp_last_error", "harp_version", "harp_ctx_create", "harp_ctx_destroy", "harp_ctx_reserve", "harp_ctx_dims",
+           "harp_ctx_faces", "harp_ctx_read_counters", "harp_lbs_mano_fwd", "harp_lbs_mano_bwd", "harp_mesh_build_fwd",
+           "harp_mesh_build_bwd", "harp_mesh_losses", "harp_silhouette", "harp_shade", "harp_texture_reg", "harp_adam"]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise HarpError(f"{LIB_PATH} not built: run `python -m harp_b200.build` (needs nvcc). "
+                            "harp_b200 has no CPU or PyTorch fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.harp_last_error.restype = C.c_char_p
+        L.harp_ctx_destroy.restype = None
+        vp, i, f = C.c_void_p, C.c_int, C.c_float
+        L.harp_ctx_create.argtypes = [C.POINTER(vp), C.POINTER(HarpTopology), C.POINTER(HarpManoModel)]
+        L.harp_ctx_destroy.argtypes = [vp]
+        L.harp_ctx_reserve.argtypes = [vp, i, i]
+        L.harp_ctx_dims.argtypes = [vp, c_int32_p, c_int32_p, c_int32_p, c_int32_p]
+        L.harp_ctx_faces.argtypes = [vp, c_int32_p]
+        L.harp_ctx_read_counters.argtypes = [vp, C.POINTER(C.c_int64), vp]
+        L.harp_lbs_mano_fwd.argtypes = [vp, i, vp, vp, i, vp, vp, vp, vp]
+        L.harp_lbs_mano_bwd.argtypes = [vp, i, vp, vp, i, vp, vp, vp, vp, vp, vp, vp]
+        L.harp_mesh_build_fwd.argtypes = [vp, i, vp, vp, vp, vp, vp]
+        L.harp_mesh_build_bwd.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp]
+        L.harp_mesh_losses.argtypes = [vp, i, vp, vp, vp, vp, vp, c_float_p, vp, vp, vp, vp, vp]
+        L.harp_silhouette.argtypes = [vp, i, i, i, f, f, vp, vp, vp, vp, vp, f, vp, vp, vp, vp, vp]
+        L.harp_shade.argtypes = [vp, i, i, i, f, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, f, vp,
+                                 C.POINTER(HarpShadeGrads), vp]
+        L.harp_texture_reg.argtypes = [vp, i, vp, i, i, vp, vp, f, vp, vp, vp]
+        L.harp_adam.argtypes = [vp, vp, vp, vp, C.c_int64, f, f, f, f, i, vp]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise HarpError(f"libharpb200 error {rc}: {lib().harp_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA fp32/int32 tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise HarpError("harp_b200 ops need CUDA tensors (there is no CPU path)")
+    if not t.is_contiguous():
+        raise HarpError("harp_b200 ops need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,266 @@
+// Context: static topology tables (PyTorch3D Meshes/SubdivideMeshes layouts), folded MANO
+// constants, and scratch buffers.  Host-side construction runs once per (model, topology).
+#include <algorithm>
+#include <map>
+#include <mutex>
+
+#include "common.cuh"
+
+static thread_local std::string g_last_error;
+void harp_set_error(const std::string& msg) { g_last_error = msg; }
+extern "C" const char* harp_last_error(void) { return g_last_error.c_str(); }
+extern "C" int harp_version(void) { return 100; }
+
+namespace {
+
+struct EdgeTables {
+  std::vector<int32_t> edges;  // (E,2) sorted unique (min,max), ascending key min*V+max  == Meshes.edges_packed
+  std::vector<int32_t> f2e;    // (F,3) edge opposite v0 | v1 | v2  == faces_packed_to_edges_packed
+};
+
+EdgeTables build_edges(const std::vector<int32_t>& faces, int V) {
+  int F = (int)faces.size() / 3;
+  std::map<int64_t, int32_t> ids;
+  auto key = [&](int a, int b) { return (int64_t)std::min(a, b) * V + std::max(a, b); };
+  for (int f = 0; f < F; ++f) {
+    int a = faces[3 * f], b = faces[3 * f + 1], c = faces[3 * f + 2];
+    ids[key(b, c)] = 0;
+    ids[key(c, a)] = 0;
+    ids[key(a, b)] = 0;
+  }
+  EdgeTables t;
+  int32_t n = 0;
+  for (auto& kv : ids) {
+    kv.second = n++;
+    t.edges.push_back((int32_t)(kv.first / V));
+    t.edges.push_back((int32_t)(kv.first % V));
+  }
+  t.f2e.resize(3 * F);
+  for (int f = 0; f < F; ++f) {
+    int a = faces[3 * f], b = faces[3 * f + 1], c = faces[3 * f + 2];
+    t.f2e[3 * f + 0] = ids[key(b, c)];
+    t.f2e[3 * f + 1] = ids[key(c, a)];
+    t.f2e[3 * f + 2] = ids[key(a, b)];
+  }
+  return t;
+}
+
+template <typename T>
+int upload(T** dst, const std::vector<T>& src) {
+  size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+  HARP_CHECK_CUDA(cudaMalloc((void**)dst, bytes));
+  if (!src.empty()) HARP_CHECK_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return HARP_OK;
+}
+
+void csr_from_lists(const std::vector<std::vector<int32_t>>& lists, std::vector<int32_t>& off, std::vector<int32_t>& idx) {
+  off.assign(lists.size() + 1, 0);
+  for (size_t i = 0; i < lists.size(); ++i) off[i + 1] = off[i] + (int32_t)lists[i].size();
+  idx.clear();
+  for (auto& l : lists) idx.insert(idx.end(), l.begin(), l.end());
+}
+
+}  // namespace
+
+extern "C" int harp_ctx_create(harp_ctx** out, const harp_topology* topo, const harp_mano_model* model) {
+  HARP_REQUIRE(out && topo && topo->faces0 && topo->V0 > 0 && topo->F0 > 0, HARP_ERR_INVALID, "harp_ctx_create: bad topology");
+  harp_ctx* c = new harp_ctx();
+  c->V0 = topo->V0;
+  c->F0 = topo->F0;
+  c->subdivide = topo->subdivide != 0;
+  std::vector<int32_t> faces0(topo->faces0, topo->faces0 + 3 * topo->F0);
+  for (int32_t v : faces0) HARP_REQUIRE(v >= 0 && v < c->V0, HARP_ERR_INVALID, "harp_ctx_create: face index out of range");
+  EdgeTables e0 = build_edges(faces0, c->V0);
+  c->E0 = (int)e0.edges.size() / 2;
+  std::vector<int32_t> faces;
+  if (c->subdivide) {  // SubdivideMeshes.subdivide_faces
+    c->V = c->V0 + c->E0;
+    c->F = 4 * c->F0;
+    faces.resize(3 * c->F);
+    for (int f = 0; f < c->F0; ++f) {
+      int v0 = faces0[3 * f], v1 = faces0[3 * f + 1], v2 = faces0[3 * f + 2];
+      int a = e0.f2e[3 * f] + c->V0, b = e0.f2e[3 * f + 1] + c->V0, d = e0.f2e[3 * f + 2] + c->V0;  // e0,e1,e2
+      int32_t* f0 = &faces[3 * f];
+      int32_t* f1 = &faces[3 * (f + c->F0)];
+      int32_t* f2 = &faces[3 * (f + 2 * c->F0)];
+      int32_t* f3 = &faces[3 * (f + 3 * c->F0)];
+      f0[0] = v0; f0[1] = d; f0[2] = b;
+      f1[0] = v1; f1[1] = a; f1[2] = d;
+      f2[0] = v2; f2[1] = b; f2[2] = a;
+      f3[0] = a;  f3[1] = b; f3[2] = d;
+    }
+  } else {
+    c->V = c->V0;
+    c->F = c->F0;
+    faces = faces0;
+  }
+  EdgeTables e = build_edges(faces, c->V);
+  c->E = (int)e.edges.size() / 2;
+  // vertex -> (face, corner)
+  std::vector<std::vector<int32_t>> vf(c->V), vn(c->V), v0e(c->V0);
+  for (int f = 0; f < c->F; ++f)
+    for (int k = 0; k < 3; ++k) vf[faces[3 * f + k]].push_back(f * 4 + k);
+  for (int i = 0; i < c->E; ++i) {
+    vn[e.edges[2 * i]].push_back(e.edges[2 * i + 1]);
+    vn[e.edges[2 * i + 1]].push_back(e.edges[2 * i]);
+  }
+  for (int i = 0; i < c->E0; ++i) {
+    v0e[e0.edges[2 * i]].push_back(i);
+    v0e[e0.edges[2 * i + 1]].push_back(i);
+  }
+  // normal-consistency pairs: every pair of faces sharing an edge (mesh_normal_consistency.py)
+  std::vector<std::vector<int32_t>> opp(c->E);
+  for (int f = 0; f < c->F; ++f)
+    for (int k = 0; k < 3; ++k) opp[e.f2e[3 * f + k]].push_back(faces[3 * f + k]);
+  std::vector<int32_t> pairs;
+  for (int i = 0; i < c->E; ++i)
+    for (size_t p = 0; p < opp[i].size(); ++p)
+      for (size_t q = p + 1; q < opp[i].size(); ++q) {
+        pairs.push_back(e.edges[2 * i]);
+        pairs.push_back(e.edges[2 * i + 1]);
+        pairs.push_back(opp[i][p]);
+        pairs.push_back(opp[i][q]);
+      }
+  c->NP = (int)pairs.size() / 4;
+  std::vector<int32_t> off, idx;
+  int rc;
+#define UP(dst, vec) if ((rc = upload(&c->dst, vec)) != HARP_OK) { harp_ctx_destroy(c); return rc; }
+  UP(faces, faces);
+  UP(edges0, e0.edges);
+  UP(edges, e.edges);
+  UP(nc_pairs, pairs);
+  csr_from_lists(vf, off, idx);  UP(vf_off, off);  UP(vf_idx, idx);
+  csr_from_lists(vn, off, idx);  UP(vn_off, off);  UP(vn_idx, idx);
+  csr_from_lists(v0e, off, idx); UP(v0e_off, off); UP(v0e_idx, idx);
+  if (topo->faces_uvs && topo->verts_uvs && topo->Vt > 0) {
+    c->Vt = topo->Vt;
+    std::vector<float> fuv(6 * (size_t)c->F);
+    for (int f = 0; f < c->F; ++f)
+      for (int k = 0; k < 3; ++k) {
+        int t = topo->faces_uvs[3 * f + k];
+        if (t < 0 || t >= c->Vt) { harp_ctx_destroy(c); harp_set_error("harp_ctx_create: faces_uvs out of range"); return HARP_ERR_INVALID; }
+        fuv[6 * f + 2 * k] = topo->verts_uvs[2 * t];
+        fuv[6 * f + 2 * k + 1] = topo->verts_uvs[2 * t + 1];
+      }
+    UP(face_uvs, fuv);
+    c->has_uv = true;
+  }
+  if (model) {
+    int V0 = c->V0;
+    std::vector<float> sd(model->shapedirs, model->shapedirs + (size_t)V0 * 30);
+    std::vector<float> pd(model->posedirs, model->posedirs + (size_t)V0 * 405);
+    std::vector<float> vt(model->v_template, model->v_template + (size_t)V0 * 3);
+    std::vector<float> w(model->weights, model->weights + (size_t)V0 * 16);
+    std::vector<float> hm(model->hands_mean, model->hands_mean + 45);
+    std::vector<int32_t> tips(model->tips, model->tips + 5);
+    // fold the joint regressor: J(beta) = Jreg v_template + (Jreg shapedirs) beta   (manolayer.py:185-188)
+    std::vector<float> Jt(48, 0.f), Js(480, 0.f);
+    for (int j = 0; j < 16; ++j)
+      for (int v = 0; v < V0; ++v) {
+        double r = model->J_regressor[(size_t)j * V0 + v];
+        if (r == 0.0) continue;
+        for (int k = 0; k < 3; ++k) {
+          Jt[j * 3 + k] += (float)(r * vt[v * 3 + k]);
+          for (int b = 0; b < 10; ++b) Js[(j * 3 + k) * 10 + b] += (float)(r * sd[(v * 3 + k) * 10 + b]);
+        }
+      }
+    // (the float accumulation above runs in double per term; tiny vs the fp32 reference's own summation order)
+    // blendshape tables are stored transposed, (k, V0*3), so that a thread-per-vertex loop reads coalesced
+    std::vector<float> sdT((size_t)V0 * 30), pdT((size_t)V0 * 405);
+    for (int i = 0; i < V0 * 3; ++i) {
+      for (int b = 0; b < 10; ++b) sdT[(size_t)b * V0 * 3 + i] = sd[(size_t)i * 10 + b];
+      for (int k = 0; k < 135; ++k) pdT[(size_t)k * V0 * 3 + i] = pd[(size_t)i * 135 + k];
+    }
+    sd.swap(sdT);
+    pd.swap(pdT);
+    UP(shapedirs, sd); UP(posedirs, pd); UP(v_template, vt); UP(weights, w); UP(hands_mean, hm); UP(tips, tips);
+    UP(J_template, Jt); UP(J_shapedirs, Js);
+    c->has_model = true;
+  }
+#undef UP
+  if (cudaMalloc((void**)&c->counters, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemset(c->counters, 0, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+    harp_ctx_destroy(c);
+    harp_set_error("harp_ctx_create: counters alloc failed");
+    return HARP_ERR_CUDA;
+  }
+  *out = c;
+  return HARP_OK;
+}
+
+static void free_scratch(harp_ctx* c) {
+  void* ptrs[] = {c->ndc_cam, c->ndc_light, c->d_ndc_cam, c->d_ndc_light, c->bin_count, c->bin_start, c->bin_fill,
+                  c->bin_list, c->light_zbuf, c->light_face, c->d_light_zbuf, c->vN, c->vtmp, c->vtmp2};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  c->ndc_cam = c->ndc_light = c->d_ndc_cam = c->d_ndc_light = c->light_zbuf = c->d_light_zbuf = c->vN = c->vtmp = c->vtmp2 = nullptr;
+  c->bin_count = c->bin_start = c->bin_fill = c->bin_list = c->light_face = nullptr;
+  c->maxB = 0;
+}
+
+extern "C" void harp_ctx_destroy(harp_ctx* c) {
+  if (!c) return;
+  free_scratch(c);
+  void* ptrs[] = {c->faces, c->edges0, c->v0e_off, c->v0e_idx, c->vf_off, c->vf_idx, c->vn_off, c->vn_idx, c->edges,
+                  c->nc_pairs, c->face_uvs, c->shapedirs, c->posedirs, c->v_template, c->weights, c->hands_mean,
+                  c->J_template, c->J_shapedirs, c->tips, c->counters};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete c;
+}
+
+extern "C" int harp_ctx_reserve(harp_ctx* c, int max_batch, int img_size) {
+  HARP_REQUIRE(c && max_batch > 0 && img_size > 0 && img_size % 8 == 0, HARP_ERR_INVALID,
+               "harp_ctx_reserve: need max_batch>0 and img_size a positive multiple of 8");
+  if (max_batch <= c->maxB && img_size == c->S) return HARP_OK;
+  free_scratch(c);
+  int B = max_batch, S = img_size;
+  int tiles = (S / 8) * (S / 8);
+  size_t nv = (size_t)B * c->V * 3 * sizeof(float);
+  size_t npx = (size_t)B * S * S;
+  // a face overlaps ~1-4 8x8 tiles at the reference's scales; 24 per face leaves a wide margin (checked: counters[1])
+  c->bin_cap = (int64_t)c->F * 24;
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->ndc_cam, nv));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->ndc_light, nv));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->d_ndc_cam, nv));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->d_ndc_light, nv));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->vN, nv));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->vtmp, nv));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->vtmp2, nv));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->bin_count, 2 * (size_t)B * tiles * sizeof(int32_t)));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->bin_start, 2 * (size_t)B * tiles * sizeof(int32_t)));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->bin_fill, 2 * (size_t)B * tiles * sizeof(int32_t)));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->bin_list, 2 * (size_t)B * c->bin_cap * sizeof(int32_t)));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->light_zbuf, npx * sizeof(float)));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->light_face, npx * sizeof(int32_t)));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->d_light_zbuf, npx * sizeof(float)));
+  c->maxB = B;
+  c->S = S;
+  c->tiles = tiles;
+  return HARP_OK;
+}
+
+extern "C" int harp_ctx_dims(const harp_ctx* c, int32_t* V0, int32_t* V, int32_t* F, int32_t* E) {
+  HARP_REQUIRE(c, HARP_ERR_INVALID, "harp_ctx_dims: null ctx");
+  if (V0) *V0 = c->V0;
+  if (V) *V = c->V;
+  if (F) *F = c->F;
+  if (E) *E = c->E;
+  return HARP_OK;
+}
+
+extern "C" int harp_ctx_faces(const harp_ctx* c, int32_t* out) {
+  HARP_REQUIRE(c && out, HARP_ERR_INVALID, "harp_ctx_faces: null");
+  HARP_CHECK_CUDA(cudaMemcpy(out, c->faces, (size_t)c->F * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return HARP_OK;
+}
+
+extern "C" int harp_ctx_read_counters(harp_ctx* c, int64_t out[2], void* stream) {
+  HARP_REQUIRE(c && out, HARP_ERR_INVALID, "harp_ctx_read_counters: null");
+  unsigned long long h[2];
+  cudaStream_t st = (cudaStream_t)stream;
+  HARP_CHECK_CUDA(cudaMemcpyAsync(h, c->counters, sizeof(h), cudaMemcpyDeviceToHost, st));
+  HARP_CHECK_CUDA(cudaMemsetAsync(c->counters, 0, sizeof(h), st));
+  HARP_CHECK_CUDA(cudaStreamSynchronize(st));
+  out[0] = (int64_t)h[0];
+  out[1] = (int64_t)h[1];
+  return HARP_OK;
+}

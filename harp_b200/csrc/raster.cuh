@@ -1,0 +1,118 @@
+// Shared rasterisation machinery: projection, 8x8-pixel tile binning, and the per-(pixel, face) evaluation that restates
+// PyTorch3D v0.6.2's CheckPixelInsideFace operation by operation.
+//
+// Numerics: the silhouette's sigmoid has sigma = 1e-7 in squared-NDC units, so alpha in the +-1/3 px band around every
+// edge is sensitive to single-ulp differences in the distance computation.  The per-pair arithmetic therefore uses
+// explicitly rounded, *unfused* fp32 operations in the oracle's operation order (the reference's ATen/CUDA kernels do not
+// contract across these statements either); everything else may use FMA.
+#pragma once
+#include "common.cuh"
+
+#define HARP_TILE 8
+#define HARP_K_EPS 1e-8f
+
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// pixel index (0 = left/top) -> NDC coordinate of its centre; PyTorch3D reverses both axes (+X left, +Y up)
+__device__ __forceinline__ float pix_to_ndc(int idx, int S) {
+  float i = (float)(S - 1 - idx);
+  return fadd(-1.0f, fdiv(fadd(fmul(2.0f, i), 1.0f), (float)S));
+}
+
+// EdgeFunctionForward(p, a, b) = (p.x-a.x)*(b.y-a.y) - (p.y-a.y)*(b.x-a.x)
+__device__ __forceinline__ float edge_fn(float px, float py, float ax, float ay, float bx, float by) {
+  return fsub(fmul(fsub(px, ax), fsub(by, ay)), fmul(fsub(py, ay), fsub(bx, ax)));
+}
+
+// PointLineDistanceForward: squared distance from p to the segment (a,b); also returns the clamped parameter
+__device__ __forceinline__ float point_seg_dist(float px, float py, float ax, float ay, float bx, float by, float* t_out) {
+  float bax = fsub(bx, ax), bay = fsub(by, ay);
+  float l2 = fadd(fmul(bax, bax), fmul(bay, bay));
+  if (l2 <= HARP_K_EPS) {
+    float ex = fsub(px, bx), ey = fsub(py, by);
+    *t_out = -1.f;  // degenerate marker
+    return fadd(fmul(ex, ex), fmul(ey, ey));
+  }
+  float t = fdiv(fadd(fmul(bax, fsub(px, ax)), fmul(bay, fsub(py, ay))), l2);
+  t = fminf(fmaxf(t, 0.f), 1.f);
+  float qx = fadd(ax, fmul(t, bax)), qy = fadd(ay, fmul(t, bay));
+  float dx = fsub(qx, px), dy = fsub(qy, py);
+  *t_out = t;
+  return fadd(fmul(dx, dx), fmul(dy, dy));
+}
+
+struct FaceRec {  // staged in shared memory, one per face of the current chunk (struct-of-arrays)
+  float x0, y0, z0, x1, y1, z1, x2, y2, z2;
+  float xmin, xmax, ymin, ymax;  // bbox inflated by sqrt(blur)
+  float area;                    // EdgeFunction(v2, v0, v1) + kEpsilon
+  int v0, v1, v2, fid;
+};
+
+struct PairEval {
+  bool pass, inside;
+  float pz, dist;      // dist = unsigned squared distance to the triangle boundary
+  float b0, b1, b2;    // perspective-correct (and, for the silhouette, clipped) barycentrics
+  float w0, w1, w2;    // screen-space barycentrics
+  int edge;            // 0: (v0,v1)  1: (v0,v2)  2: (v1,v2)  closest edge
+  float t;             // clamped parameter on that edge (-1: degenerate edge)
+};
+
+// One (pixel, face) pair.  CLIP: clip_barycentric_coords (silhouette); blur: blur_radius (squared NDC).
+template <bool CLIP, bool NEED_DIST>
+__device__ __forceinline__ void eval_pair(const FaceRec& f, float px, float py, float blur, PairEval& r) {
+  r.pass = false;
+  if (px > f.xmax || px < f.xmin || py > f.ymax || py < f.ymin) return;
+  float w0 = fdiv(edge_fn(px, py, f.x1, f.y1, f.x2, f.y2), f.area);
+  float w1 = fdiv(edge_fn(px, py, f.x2, f.y2, f.x0, f.y0), f.area);
+  float w2 = fdiv(edge_fn(px, py, f.x0, f.y0, f.x1, f.y1), f.area);
+  // BarycentricPerspectiveCorrectionForward
+  float t0 = fmul(fmul(w0, f.z1), f.z2), t1 = fmul(fmul(f.z0, w1), f.z2), t2 = fmul(fmul(f.z0, f.z1), w2);
+  float den = fmaxf(fadd(fadd(t0, t1), t2), HARP_K_EPS);
+  float b0 = fdiv(t0, den), b1 = fdiv(t1, den), b2 = fdiv(t2, den);
+  bool inside = b0 > 0.f && b1 > 0.f && b2 > 0.f;
+  float c0 = b0, c1 = b1, c2 = b2;
+  if (CLIP) {  // BarycentricClipForward
+    c0 = fmaxf(b0, 0.f); c1 = fmaxf(b1, 0.f); c2 = fmaxf(b2, 0.f);
+    float s = fmaxf(fadd(fadd(c0, c1), c2), 1e-5f);
+    c0 = fdiv(c0, s); c1 = fdiv(c1, s); c2 = fdiv(c2, s);
+  }
+  float pz = fadd(fadd(fmul(c0, f.z0), fmul(c1, f.z1)), fmul(c2, f.z2));
+  if (pz < 0.f) return;
+  r.inside = inside;
+  r.pz = pz;
+  r.b0 = c0; r.b1 = c1; r.b2 = c2;
+  r.w0 = w0; r.w1 = w1; r.w2 = w2;
+  if (NEED_DIST) {
+    float ta, tb, tc;
+    float d01 = point_seg_dist(px, py, f.x0, f.y0, f.x1, f.y1, &ta);
+    float d02 = point_seg_dist(px, py, f.x0, f.y0, f.x2, f.y2, &tb);
+    float d12 = point_seg_dist(px, py, f.x1, f.y1, f.x2, f.y2, &tc);
+    // torch.min over the stacked [d01, d02, d12]: first minimal index (matches PointTriangleDistanceBackward's order)
+    float d = d01; int e = 0; float t = ta;
+    if (d02 < d) { d = d02; e = 1; t = tb; }
+    if (d12 < d) { d = d12; e = 2; t = tc; }
+    r.dist = d; r.edge = e; r.t = t;
+    if (!inside && d >= blur) return;
+  } else {
+    if (!inside) return;
+  }
+  r.pass = true;
+}
+
+// Load face `fid` of frame-local projected verts into a FaceRec.  Returns false for faces PyTorch3D skips outright.
+__device__ __forceinline__ void load_face(const harp_ctx& c, const float* ndc, int fid, float radius, FaceRec& f) {
+  const int32_t* fv = c.faces + (size_t)fid * 3;
+  f.v0 = fv[0]; f.v1 = fv[1]; f.v2 = fv[2]; f.fid = fid;
+  const float *a = ndc + (size_t)f.v0 * 3, *b = ndc + (size_t)f.v1 * 3, *d = ndc + (size_t)f.v2 * 3;
+  f.x0 = a[0]; f.y0 = a[1]; f.z0 = a[2];
+  f.x1 = b[0]; f.y1 = b[1]; f.z1 = b[2];
+  f.x2 = d[0]; f.y2 = d[1]; f.z2 = d[2];
+  f.xmin = fsub(fminf(fminf(f.x0, f.x1), f.x2), radius);
+  f.xmax = fadd(fmaxf(fmaxf(f.x0, f.x1), f.x2), radius);
+  f.ymin = fsub(fminf(fminf(f.y0, f.y1), f.y2), radius);
+  f.ymax = fadd(fmaxf(fmaxf(f.y0, f.y1), f.y2), radius);
+  f.area = fadd(edge_fn(f.x2, f.y2, f.x0, f.y0, f.x1, f.y1), HARP_K_EPS);
+}

@@ -1,0 +1,116 @@
+// Per-step (not per-frame) pieces: texture regularisers and fused Adam.
+// Replaces loss/texture_reg.py:5-66 and torch.optim.Adam.step on the CPU-resident texture / normal map
+// (optimize_sequence.py:253-310,567-573).
+#include "common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+
+// smooth_texture_reg / albedo_reg: mean_{ij} mask_ij * ||t_ij - t_{clamp(ij + off_ij)}||_1 / 3
+__global__ void __launch_bounds__(TPB) tex_smooth_kernel(const float* __restrict__ map, int H, int W,
+                                                          const int32_t* __restrict__ off, const float* __restrict__ mask,
+                                                          float w, float* __restrict__ loss, float* __restrict__ d_map) {
+  __shared__ float red[32];
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  float val = 0.f;
+  if (idx < H * W) {
+    int i = idx / W, j = idx % W;
+    int ti = min(max(i + off[2 * idx], 0), H - 1), tj = min(max(j + off[2 * idx + 1], 0), W - 1);
+    int tidx = ti * W + tj;
+    float m = mask ? mask[idx] : 1.f;
+    float inv = 1.f / ((float)H * (float)W);
+    float s = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float d = map[idx * 3 + ch] - map[tidx * 3 + ch];
+      s += fabsf(d);
+      if (d_map && d != 0.f && m != 0.f && tidx != idx) {
+        float g = w * inv * m / 3.f * (d > 0.f ? 1.f : -1.f);
+        atomicAdd(d_map + idx * 3 + ch, g);
+        atomicAdd(d_map + tidx * 3 + ch, -g);
+      }
+    }
+    val = s / 3.f * m * inv;
+  }
+  float tot = block_sum(val, red);
+  if (threadIdx.x == 0 && tot != 0.f) atomicAdd(loss, tot);
+}
+
+// close_to_z_reg (loss/texture_reg.py:40-45): torch.norm(normal_map - [0,0,1], p=2, dim=2) on the 4-D (1,H,W,3) tensor,
+// i.e. the L2 norm runs along the W axis per (row, channel) — reproduced as written.  One CTA per row.
+__global__ void __launch_bounds__(TPB) close_to_z_kernel(const float* __restrict__ map, int H, int W, float w,
+                                                          float* __restrict__ loss, float* __restrict__ d_map) {
+  __shared__ float red[32];
+  __shared__ float nrm[3];
+  int i = blockIdx.x;
+  const float* row = map + (size_t)i * W * 3;
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int j = threadIdx.x; j < W; j += blockDim.x) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float d = row[j * 3 + ch] - (ch == 2 ? 1.f : 0.f);
+      acc[ch] += d * d;
+    }
+  }
+  for (int ch = 0; ch < 3; ++ch) {
+    float s = block_sum(acc[ch], red);
+    if (threadIdx.x == 0) nrm[ch] = sqrtf(s);
+  }
+  __syncthreads();
+  float inv = 1.f / (3.f * (float)H * 3.f);  // (/3.0).mean() over (1,H,3)
+  if (threadIdx.x == 0) atomicAdd(loss, 0.2f * (nrm[0] + nrm[1] + nrm[2]) * inv);
+  if (d_map) {
+    float* drow = d_map + (size_t)i * W * 3;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) {
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        if (nrm[ch] > 0.f) {
+          float d = row[j * 3 + ch] - (ch == 2 ? 1.f : 0.f);
+          atomicAdd(drow + j * 3 + ch, w * 0.2f * inv * d / nrm[ch]);
+        }
+      }
+    }
+  }
+}
+
+// torch.optim.Adam (amsgrad=False, weight_decay=0): one thread per element
+__global__ void __launch_bounds__(TPB) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                                    float bc1, float bc2_sqrt) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i];
+  float mi = m[i] + (1.f - b1) * (gi - m[i]);  // lerp, as torch._single_tensor_adam
+  float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+
+}  // namespace
+
+extern "C" int harp_texture_reg(harp_ctx* c, int kind, const float* map, int H, int W, const int32_t* offsets,
+                                const float* uv_mask, float weight, float* loss, float* d_map, void* stream) {
+  (void)c;
+  HARP_REQUIRE(map && offsets && loss && H > 0 && W > 0, HARP_ERR_INVALID, "harp_texture_reg: null argument");
+  HARP_REQUIRE(kind == 0 || kind == 1, HARP_ERR_INVALID, "harp_texture_reg: kind must be 0 (albedo) or 1 (normal)");
+  cudaStream_t st = (cudaStream_t)stream;
+  tex_smooth_kernel<<<(H * W + TPB - 1) / TPB, TPB, 0, st>>>(map, H, W, offsets, uv_mask, weight, loss, d_map);
+  if (kind == 1) close_to_z_kernel<<<H, TPB, 0, st>>>(map, H, W, weight, loss, d_map);
+  HARP_LAUNCH_CHECK();
+  return HARP_OK;
+}
+
+extern "C" int harp_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                         float beta1, float beta2, float eps, int step, void* stream) {
+  HARP_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, HARP_ERR_INVALID, "harp_adam: bad argument");
+  if (n == 0) return HARP_OK;
+  float bc1 = 1.f - powf(beta1, (float)step);
+  float bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<(int)((n + TPB - 1) / TPB), TPB, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
+                                                                             beta2, eps, bc1, sqrtf(bc2));
+  HARP_LAUNCH_CHECK();
+  return HARP_OK;
+}

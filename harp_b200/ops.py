@@ -1,0 +1,298 @@
+"""torch.autograd wrappers over the C ABI: one Function per forward/backward kernel pair.
+
+These are the building blocks the reference-signature shims (`manolayer.py`, `renderer_helper.py`, `visualize.py`,
+`loss.py`) and the fused optimiser step (`step.py`) are made of.  Everything runs on the current CUDA stream.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import HarpManoModel, HarpShadeGrads, HarpTopology, check, ptr, stream
+
+
+def _np_f32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def _np_i32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+
+
+def _fp(a):
+    return a.ctypes.data_as(_lib.c_float_p)
+
+
+def _ip(a):
+    return a.ctypes.data_as(_lib.c_int32_p)
+
+
+class HarpContext:
+    """Owns a `harp_ctx*`: static topology (+ optional MANO model) on one CUDA device.
+
+    faces0: (F0,3) coarse faces (`ManoLayer.th_faces`); subdivide: apply one SubdivideMeshes step
+    (`optimize_sequence.py:67-89`); faces_uvs/verts_uvs: template UV tables (`utils/hand_model_utils.py:59-61`);
+    mano: dict with the buffers registered at `manopth/manolayer.py:70-97` (+ 'tips')."""
+
+    def __init__(self, faces0, subdivide=True, faces_uvs=None, verts_uvs=None, mano=None, device="cuda:0"):
+        self.device = torch.device(device)
+        L = _lib.lib()
+        faces0 = _np_i32(faces0)
+        topo = HarpTopology()
+        topo.V0 = int(faces0.max()) + 1 if mano is None else int(np.asarray(mano["th_v_template"]).reshape(-1, 3).shape[0])
+        topo.F0 = faces0.shape[0]
+        topo.faces0 = _ip(faces0)
+        topo.subdivide = int(bool(subdivide))
+        keep = [faces0]
+        if faces_uvs is not None:
+            nf = faces0.shape[0] * (4 if subdivide else 1)  # TexturesUV pairs faces_uvs with faces by index
+            fu, vu = _np_i32(np.asarray(faces_uvs)[:nf]), _np_f32(verts_uvs)
+            topo.Vt, topo.faces_uvs, topo.verts_uvs = vu.shape[0], _ip(fu), _fp(vu)
+            keep += [fu, vu]
+        model_p = None
+        if mano is not None:
+            arrs = {k: _np_f32(np.asarray(mano[k])) for k in ("th_shapedirs", "th_posedirs", "th_v_template",
+                                                               "th_J_regressor", "th_weights", "th_hands_mean")}
+            tips = _np_i32(np.asarray(mano["tips"]))
+            m = HarpManoModel(_fp(arrs["th_shapedirs"]), _fp(arrs["th_posedirs"]), _fp(arrs["th_v_template"]),
+                              _fp(arrs["th_J_regressor"]), _fp(arrs["th_weights"]), _fp(arrs["th_hands_mean"]), _ip(tips))
+            model_p = C.byref(m)
+            keep += list(arrs.values()) + [tips]
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(L.harp_ctx_create(C.byref(h), C.byref(topo), model_p))
+        self.h = h
+        dims = [C.c_int32() for _ in range(4)]
+        check(L.harp_ctx_dims(self.h, *[C.byref(d) for d in dims]))
+        self.V0, self.V, self.F, self.E = [d.value for d in dims]
+        self.has_model = mano is not None
+        self._reserved = (0, 0)
+        self._faces = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                _lib.lib().harp_ctx_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def reserve(self, B, S):
+        """Size the ctx scratch for <= B frames of S x S (harp_ctx_reserve); grows monotonically for a fixed S."""
+        rb, rs = self._reserved
+        if B > rb or S != rs:
+            nb = max(B, rb) if S == rs else B
+            with torch.cuda.device(self.device):
+                check(_lib.lib().harp_ctx_reserve(self.h, int(nb), int(S)))
+            self._reserved = (nb, S)
+
+    def faces(self):
+        """(F,3) int64 face list of the (subdivided) mesh, as `Meshes.faces_padded()[0]`."""
+        if self._faces is None:
+            host = np.empty((self.F, 3), dtype=np.int32)
+            check(_lib.lib().harp_ctx_faces(self.h, _ip(host)))
+            self._faces = torch.from_numpy(host).long().to(self.device)
+        return self._faces
+
+    def counters(self):
+        out = (C.c_int64 * 2)()
+        check(_lib.lib().harp_ctx_read_counters(self.h, out, stream()))
+        return {"sil_k_overflow_pixels": int(out[0]), "bin_overflow": int(out[1])}
+
+
+def _c(t):
+    return t.contiguous().float()
+
+
+class LbsMano(torch.autograd.Function):
+    """ManoLayer.forward (manopth/manolayer.py:108-296) -> (verts0 m, joints m)."""
+
+    @staticmethod
+    def forward(ctx, hc, pose48, betas, trans):
+        pose48, betas, trans = _c(pose48), _c(betas), _c(trans)
+        B = pose48.shape[0]
+        shared = betas.dim() == 1 or betas.shape[0] == 1
+        verts0 = torch.empty(B, hc.V0, 3, device=pose48.device)
+        joints = torch.empty(B, 21, 3, device=pose48.device)
+        check(_lib.lib().harp_lbs_mano_fwd(hc.h, B, ptr(pose48), ptr(betas), int(shared), ptr(trans), ptr(verts0), ptr(joints), stream()))
+        ctx.hc, ctx.shared, ctx.betas_shape = hc, shared, betas.shape
+        ctx.save_for_backward(pose48, betas, trans)
+        return verts0, joints
+
+    @staticmethod
+    def backward(ctx, g_verts0, g_joints):
+        pose48, betas, trans = ctx.saved_tensors
+        B = pose48.shape[0]
+        g_verts0 = _c(g_verts0) if g_verts0 is not None else torch.zeros(B, ctx.hc.V0, 3, device=pose48.device)
+        g_joints = _c(g_joints) if g_joints is not None else None
+        d_pose = torch.empty_like(pose48)
+        d_betas = torch.empty(B, 10, device=pose48.device)
+        d_trans = torch.empty(B, 3, device=pose48.device)
+        check(_lib.lib().harp_lbs_mano_bwd(ctx.hc.h, B, ptr(pose48), ptr(betas), int(ctx.shared), ptr(trans), ptr(g_verts0),
+                                           ptr(g_joints), ptr(d_pose), ptr(d_betas), ptr(d_trans), stream()))
+        if ctx.shared:
+            d_betas = d_betas.sum(0).view(ctx.betas_shape)
+        return None, d_pose, d_betas, d_trans
+
+
+class MeshBuild(torch.autograd.Function):
+    """SubdivideMeshes + displacement along vertex normals + final vertex normals (utils/visualize.py:48-64)."""
+
+    @staticmethod
+    def forward(ctx, hc, verts0, disps):
+        verts0 = _c(verts0)
+        disps_c = _c(disps).view(-1) if disps is not None else None
+        B = verts0.shape[0]
+        hc.reserve(B, hc._reserved[1] or 8)
+        verts = torch.empty(B, hc.V, 3, device=verts0.device)
+        normals = torch.empty(B, hc.V, 3, device=verts0.device)
+        check(_lib.lib().harp_mesh_build_fwd(hc.h, B, ptr(verts0), ptr(disps_c), ptr(verts), ptr(normals), stream()))
+        ctx.hc, ctx.disps_shape = hc, (disps.shape if disps is not None else None)
+        ctx.save_for_backward(verts0, disps_c)
+        return verts, normals
+
+    @staticmethod
+    def backward(ctx, g_verts, g_normals):
+        verts0, disps = ctx.saved_tensors
+        hc, B = ctx.hc, verts0.shape[0]
+        g_verts = _c(g_verts) if g_verts is not None else torch.zeros(B, hc.V, 3, device=verts0.device)
+        g_normals = _c(g_normals) if g_normals is not None else None
+        d_verts0 = torch.empty_like(verts0)
+        d_disps = torch.zeros(hc.V, device=verts0.device) if disps is not None else None
+        check(_lib.lib().harp_mesh_build_bwd(hc.h, B, ptr(verts0), ptr(disps), ptr(g_verts), ptr(g_normals), ptr(d_verts0),
+                                             ptr(d_disps), stream()))
+        return None, d_verts0, (d_disps.view(ctx.disps_shape) if disps is not None else None)
+
+
+class MeshLosses(torch.autograd.Function):
+    """-> (5,) unweighted [laplacian, normal consistency, arap, kps, sum disp^2]; gradients are precomputed at unit
+    weight per term in forward and scaled by the upstream gradient in backward (no host sync)."""
+
+    @staticmethod
+    def forward(ctx, hc, verts, ref_verts, joints, init_joints_mm, disps):
+        verts = _c(verts)
+        B, dev = verts.shape[0], verts.device
+        ref = _c(ref_verts).view(-1, 3) if ref_verts is not None else None
+        joints_c = _c(joints) if joints is not None else None
+        init_c = _c(init_joints_mm) if init_joints_mm is not None else None
+        disps_c = _c(disps).view(-1) if disps is not None else None
+        losses = torch.zeros(5, device=dev)
+        gv = torch.zeros(5, B, hc.V, 3, device=dev)
+        gj = torch.zeros(B, 21, 3, device=dev) if joints_c is not None else None
+        gd = torch.zeros(hc.V, device=dev) if disps_c is not None else None
+        L = _lib.lib()
+        scratch = torch.zeros(5, device=dev)
+        f5 = lambda *w: (C.c_float * 5)(*w)
+        # call 0: every loss value + unit-weight gradients of laplacian (verts), kps (joints), disp^2 (disps)
+        check(L.harp_mesh_losses(hc.h, B, ptr(verts), ptr(ref), ptr(joints_c), ptr(init_c), ptr(disps_c), f5(1, 0, 0, 1, 1),
+                                 ptr(losses), ptr(gv[0]), ptr(gj), ptr(gd), stream()))
+        # calls 1, 2: separate unit-weight vertex gradients for normal consistency and arap (values go to scratch)
+        check(L.harp_mesh_losses(hc.h, B, ptr(verts), None, None, None, None, f5(0, 1, 0, 0, 0), ptr(scratch), ptr(gv[1]),
+                                 None, None, stream()))
+        if ref is not None:
+            check(L.harp_mesh_losses(hc.h, B, ptr(verts), ptr(ref), None, None, None, f5(0, 0, 1, 0, 0), ptr(scratch),
+                                     ptr(gv[2]), None, None, stream()))
+        ctx.save_for_backward(gv, gj, gd)
+        ctx.disps_shape = disps.shape if disps is not None else None
+        return losses
+
+    @staticmethod
+    def backward(ctx, g):
+        gv, gj, gd = ctx.saved_tensors
+        d_verts = g[0] * gv[0] + g[1] * gv[1] + g[2] * gv[2]
+        d_joints = g[3] * gj if gj is not None else None
+        d_disps = (g[4] * gd).view(ctx.disps_shape) if gd is not None else None
+        return None, d_verts, None, d_joints, None, d_disps
+
+
+class Silhouette(torch.autograd.Function):
+    """MeshRasterizer(K=50) + SoftSilhouetteShader alpha channel (renderer_helper.py:37-58)."""
+
+    @staticmethod
+    def forward(ctx, hc, verts, R, T, focal, S, sigma):
+        verts, R, T = _c(verts), _c(R), _c(T)
+        B = verts.shape[0]
+        hc.reserve(B, S)
+        alpha = torch.empty(B, S, S, device=verts.device)
+        check(_lib.lib().harp_silhouette(hc.h, 0, B, S, float(focal), float(sigma), ptr(verts), ptr(R), ptr(T), ptr(alpha),
+                                         None, 0.0, None, None, None, None, stream()))
+        ctx.hc, ctx.args = hc, (float(focal), int(S), float(sigma))
+        ctx.save_for_backward(verts, R, T)
+        return alpha
+
+    @staticmethod
+    def backward(ctx, g_alpha):
+        verts, R, T = ctx.saved_tensors
+        focal, S, sigma = ctx.args
+        B = verts.shape[0]
+        d_verts, d_R, d_T = torch.zeros_like(verts), torch.zeros_like(R), torch.zeros_like(T)
+        check(_lib.lib().harp_silhouette(ctx.hc.h, 1, B, S, focal, sigma, ptr(verts), ptr(R), ptr(T), None, ptr(_c(g_alpha)),
+                                         0.0, None, ptr(d_verts), ptr(d_R), ptr(d_T), stream()))
+        return None, d_verts, d_R, d_T, None, None, None
+
+
+class Shade(torch.autograd.Function):
+    """MeshRendererShadow + SoftPhongShaderShadow + PBR normal map, RGB channels (renderer_helper.py:331-412,472-592)."""
+
+    @staticmethod
+    def forward(ctx, hc, verts, normals, cam_R, cam_T, light_R, light_T, light_pos, amb, texture, normal_map, focal, S,
+                self_shadow):
+        ts = [_c(t) for t in (verts, normals, cam_R, cam_T, light_R, light_T, light_pos, amb.view(1), texture, normal_map)]
+        verts, normals, cam_R, cam_T, light_R, light_T, light_pos, amb1, tex, nm = ts
+        B = verts.shape[0]
+        hc.reserve(B, S)
+        H, W = tex.shape[-3], tex.shape[-2]
+        rgb = torch.empty(B, S, S, 3, device=verts.device)
+        check(_lib.lib().harp_shade(hc.h, 0, B, S, float(focal), int(self_shadow), ptr(verts), ptr(normals), ptr(cam_R),
+                                    ptr(cam_T), ptr(light_R), ptr(light_T), ptr(light_pos), ptr(amb1), ptr(tex), ptr(nm), H, W,
+                                    ptr(rgb), None, None, 0.0, None, None, stream()))
+        ctx.hc, ctx.args = hc, (float(focal), int(S), int(self_shadow), H, W)
+        ctx.shapes = (amb.shape, texture.shape, normal_map.shape)
+        ctx.save_for_backward(*ts)
+        return rgb
+
+    @staticmethod
+    def backward(ctx, g_rgb):
+        verts, normals, cam_R, cam_T, light_R, light_T, light_pos, amb1, tex, nm = ctx.saved_tensors
+        focal, S, self_shadow, H, W = ctx.args
+        B = verts.shape[0]
+        z = torch.zeros_like
+        g = dict(d_verts=z(verts), d_normals=z(normals), d_cam_R=z(cam_R), d_cam_T=z(cam_T), d_light_R=z(light_R),
+                 d_light_T=z(light_T), d_light_pos=z(light_pos), d_amb=z(amb1), d_texture=z(tex), d_normal_map=z(nm))
+        gs = HarpShadeGrads(**{k: ptr(v) for k, v in g.items()})
+        check(_lib.lib().harp_shade(ctx.hc.h, 1, B, S, focal, self_shadow, ptr(verts), ptr(normals), ptr(cam_R), ptr(cam_T),
+                                    ptr(light_R), ptr(light_T), ptr(light_pos), ptr(amb1), ptr(tex), ptr(nm), H, W, None,
+                                    ptr(_c(g_rgb)), None, 0.0, None, C.byref(gs), stream()))
+        sa, st, sn = ctx.shapes
+        return (None, g["d_verts"], g["d_normals"], g["d_cam_R"], g["d_cam_T"], g["d_light_R"], g["d_light_T"],
+                g["d_light_pos"], g["d_amb"].view(sa), g["d_texture"].view(st), g["d_normal_map"].view(sn), None, None, None)
+
+
+class TextureReg(torch.autograd.Function):
+    """albedo_reg (kind 0) / normal_reg (kind 1) with explicit neighbour offsets (loss/texture_reg.py:5-66)."""
+
+    @staticmethod
+    def forward(ctx, hc, kind, tex, offsets, uv_mask):
+        t = _c(tex)
+        H, W = t.shape[-3], t.shape[-2]
+        off = offsets.to(device=t.device, dtype=torch.int32).contiguous()
+        m = _c(uv_mask) if uv_mask is not None else None
+        loss = torch.zeros(1, device=t.device)
+        d = torch.zeros_like(t)
+        check(_lib.lib().harp_texture_reg(hc.h if hc is not None else None, int(kind), ptr(t), H, W, ptr(off), ptr(m), 1.0,
+                                          ptr(loss), ptr(d), stream()))
+        ctx.save_for_backward(d)
+        ctx.shape = tex.shape
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        return None, None, (g * d).view(ctx.shape), None, None
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
+    """In-place fused Adam on flat fp32 CUDA tensors (torch.optim.Adam defaults; optimize_sequence.py:253-310)."""
+    check(_lib.lib().harp_adam(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), float(lr), float(beta1),
+                               float(beta2), float(eps), int(step), stream()))

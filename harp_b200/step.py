@@ -1,0 +1,237 @@
+"""Fused optimiser step: the body of `optimize_sequence.py:446-579` as one asynchronous launch sequence.
+
+`HarpFitter` keeps every parameter, image and optimiser state resident in HBM (the reference keeps parameters on the CPU
+and copies them every iteration: `utils/visualize.py:37-44,81,94`) and runs, per minibatch,
+
+    LBS -> mesh build -> [silhouette fwd+L1+bwd] -> [light depth -> shade fwd+L1+bwd -> light depth bwd]
+        -> mesh regularisers -> texture regularisers -> mesh build bwd -> LBS bwd -> (allreduce) -> Adam x2
+
+with no host synchronisation: loss scalars stay on the device until the caller asks for them.
+Loss weights, stage gating and optimiser grouping follow `optimize_sequence.py:253-310,411-422,507-515,567-573`.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib, camera
+from ._lib import HarpShadeGrads, check, ptr, stream
+
+# slots 1..5 are contiguous in harp_mesh_losses' output order
+LOSS_NAMES = ("silhouette", "laplacian", "normal", "arap", "kps_anchor", "vert_disp_reg", "photo", "albedo", "normal_reg")
+LOSS_WEIGHTS = {"silhouette": 7.0, "kps_anchor": 10.0, "vert_disp_reg": 2.0, "normal": 0.1, "laplacian": 4.0, "arap": 0.2,
+                "photo": 1.0, "albedo": 0.5, "normal_reg": 0.1}  # optimize_sequence.py:411-422 (vgg excluded)
+_SLOT = {n: i for i, n in enumerate(LOSS_NAMES)}
+
+
+class _Flat:
+    """Several named parameters as views of one flat fp32 buffer (+ grad, Adam moments) so that one fused Adam launch
+    updates the whole optimiser group."""
+
+    def __init__(self, named, device):
+        self.names = [n for n, _ in named]
+        sizes = [t.numel() for _, t in named]
+        self.offsets = [0]
+        for s in sizes:
+            self.offsets.append(self.offsets[-1] + s)
+        n = self.offsets[-1]
+        self.data = torch.empty(n, device=device)
+        self.grad = torch.zeros(n, device=device)
+        self.m = torch.zeros(n, device=device)
+        self.v = torch.zeros(n, device=device)
+        self.p, self.g = {}, {}
+        for (name, t), a, b in zip(named, self.offsets[:-1], self.offsets[1:]):
+            self.data[a:b].copy_(t.detach().reshape(-1).to(device))
+            self.p[name] = self.data[a:b].view(t.shape)
+            self.g[name] = self.grad[a:b].view(t.shape)
+        self.steps = 0
+
+    def adam(self, lr):
+        self.steps += 1
+        check(_lib.lib().harp_adam(ptr(self.data), ptr(self.grad), ptr(self.m), ptr(self.v), self.data.numel(), float(lr),
+                                   0.9, 0.999, 1e-8, self.steps, stream()))
+
+
+class HarpFitter:
+    """params: dict with the reference's keys (`optimize_sequence.py:181-250`): pose (T,45), rot (T,3), trans (T,3),
+    cam (T,3), shape (10,), verts_disps (V,1), texture / normal_map (1,H,W,3), light_positions (T,3), amb_ratio ().
+    frames: y_true (T,S,S,3), y_sil (T,S,S), y_sil_eroded (T,S,S), init_joints (T,21,3) [mm] — device resident.
+    ref_verts: (1,V,3) ARAP reference (`optimize_sequence.py:429-435`); uv_mask (H,W)."""
+
+    def __init__(self, hc, params, frames, ref_verts, uv_mask, img_size, focal_length, self_shadow=True,
+                 lr_coarse=1e-3, lr_app=1e-2, world_size=1, process_group=None):
+        dev = hc.device
+        self.hc, self.S, self.focal, self.self_shadow = hc, int(img_size), float(focal_length), bool(self_shadow)
+        self.lr_coarse, self.lr_app = lr_coarse, lr_app
+        self.world_size, self.pg = int(world_size), process_group
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        # optimiser groups (get_optimizers, optimize_sequence.py:253-310, default `harp` branch)
+        self.coarse = _Flat([("pose", f32(params["pose"])), ("cam", f32(params["cam"])),
+                             ("verts_disps", f32(params["verts_disps"])), ("shape", f32(params["shape"]))], dev)
+        self.app = _Flat([("light_positions", f32(params["light_positions"])), ("amb_ratio", f32(params["amb_ratio"]).view(1)),
+                          ("texture", f32(params["texture"])), ("normal_map", f32(params["normal_map"]))], dev)
+        self.rot, self.trans = f32(params["rot"]), f32(params["trans"])
+        self.frames = {k: f32(v) for k, v in frames.items()}
+        self.ref_verts = f32(ref_verts).view(-1, 3)
+        self.uv_mask = f32(uv_mask)
+        self.T = self.rot.shape[0]
+        self.losses = torch.zeros(len(LOSS_NAMES), device=dev)
+        self._scratch = {}
+        self.last = {}
+
+    # -- helpers --------------------------------------------------------------------------------------------------------
+    def params(self):
+        out = dict(self.coarse.p)
+        out.update(self.app.p)
+        out["amb_ratio"] = self.app.p["amb_ratio"].view(())
+        out["rot"], out["trans"] = self.rot, self.trans
+        return out
+
+    def _buf(self, name, shape, zero=True):
+        t = self._scratch.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, device=self.hc.device)
+            self._scratch[name] = t
+        if zero:
+            t.zero_()
+        return t
+
+    # -- one minibatch ----------------------------------------------------------------------------------------------------
+    def step(self, fid, off_albedo, off_normal, stage="both", update=True, batch=None, frame_range=None):
+        """fid: (B,) long device tensor of frame ids owned by this rank.  stage: 'coarse' | 'both' | 'app'
+        (`optimize_sequence.py:507-515`).  batch: optional dict overriding self.frames rows (host->device ingest path).
+        frame_range=(a,b): promise that fid == arange(a,b), so image rows are used in place instead of gathered.
+        Returns the device tensor of unweighted losses (LOSS_NAMES order); gradients are in self.coarse.grad / self.app.grad."""
+        hc, L, S, focal = self.hc, _lib.lib(), self.S, self.focal
+        dev, st = hc.device, stream()
+        B = int(fid.shape[0])
+        R = self.world_size
+        fscale = 1.0 / R  # frame losses are means over the GLOBAL batch; frame-independent terms are split over ranks
+        hc.reserve(B, S)
+        P, A = self.coarse.p, self.app.p
+        coarse_on, app_on = stage in ("coarse", "both"), stage in ("both", "app")
+        if batch is not None:
+            fr = batch
+        elif frame_range is not None:
+            fr = {k: v[frame_range[0]:frame_range[1]] for k, v in self.frames.items()}
+        else:
+            fr = {k: v.index_select(0, fid) for k, v in self.frames.items()}
+        self.losses.zero_()
+        self.coarse.grad.zero_()
+        self.app.grad.zero_()
+        # ---- forward geometry
+        pose48 = torch.cat((self.rot.index_select(0, fid), P["pose"].index_select(0, fid)), 1)
+        trans = self.trans.index_select(0, fid)
+        verts0 = self._buf("verts0", (B, hc.V0, 3), zero=False)
+        joints = self._buf("joints", (B, 21, 3), zero=False)
+        check(L.harp_lbs_mano_fwd(hc.h, B, ptr(pose48), ptr(P["shape"]), 1, ptr(trans), ptr(verts0), ptr(joints), st))
+        disps = P["verts_disps"].view(-1)
+        verts = self._buf("verts", (B, hc.V, 3), zero=False)
+        normals = self._buf("normals", (B, hc.V, 3), zero=False)
+        check(L.harp_mesh_build_fwd(hc.h, B, ptr(verts0), ptr(disps), ptr(verts), ptr(normals), st))
+        # ---- per-frame camera / light glue (tiny tensors; torch autograd carries their chain)
+        cam_b = P["cam"].index_select(0, fid).requires_grad_(True)
+        light_l = A["light_positions"][0].detach().clone().requires_grad_(True)  # share_light_position (453-454)
+        centroid = verts.mean(1).requires_grad_(True)
+        amb_leaf = A["amb_ratio"].detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            cT = camera.cam_to_T(cam_b, focal, S)
+            light_b = light_l[None].expand(B, 3)
+            lR, lT = camera.light_camera(light_b, centroid)
+            amb = torch.sigmoid(amb_leaf)
+        cR = camera.flip_xy_R(B, dev)
+        cTc, lRc, lTc, light_bc = cT.detach().contiguous(), lR.detach().contiguous(), lT.detach().contiguous(), light_b.detach().contiguous()
+        # ---- gradient accumulators
+        d_verts = self._buf("d_verts", (B, hc.V, 3))
+        d_normals = self._buf("d_normals", (B, hc.V, 3))
+        d_joints = self._buf("d_joints", (B, 21, 3))
+        d_cT = self._buf("d_cT", (B, 3))
+        d_lR, d_lT, d_lpos, d_amb = self._buf("d_lR", (B, 3, 3)), self._buf("d_lT", (B, 3)), self._buf("d_lpos", (B, 3)), self._buf("d_amb", (1,))
+        W = LOSS_WEIGHTS
+        # ---- silhouette (rendered in every stage, loss only while COARSE_OPT: 469-471, 517-519)
+        alpha = self._buf("alpha", (B, S, S), zero=False)
+        if coarse_on:
+            check(L.harp_silhouette(hc.h, 2, B, S, focal, 1e-7, ptr(verts), ptr(cR), ptr(cTc), ptr(alpha), ptr(fr["y_sil"]),
+                                    W["silhouette"] * fscale, ptr(self.losses[_SLOT["silhouette"]:]), ptr(d_verts), None,
+                                    ptr(d_cT), st))
+        else:
+            check(L.harp_silhouette(hc.h, 0, B, S, focal, 1e-7, ptr(verts), ptr(cR), ptr(cTc), ptr(alpha), None, 0.0, None,
+                                    None, None, None, st))
+        # ---- colour render (474-488), photometric loss only while APP_OPT (541-543)
+        rgb = self._buf("rgb", (B, S, S, 3), zero=False)
+        tex, nm = A["texture"], A["normal_map"]
+        H, Wd = tex.shape[-3], tex.shape[-2]
+        ambc = amb.detach().contiguous()
+        if app_on:
+            gs = HarpShadeGrads(d_verts=ptr(d_verts), d_normals=ptr(d_normals), d_cam_R=None, d_cam_T=ptr(d_cT), d_light_R=ptr(d_lR),
+                                d_light_T=ptr(d_lT), d_light_pos=ptr(d_lpos), d_amb=ptr(d_amb),
+                                d_texture=ptr(self.app.g["texture"]), d_normal_map=ptr(self.app.g["normal_map"]))
+            check(L.harp_shade(hc.h, 2, B, S, focal, int(self.self_shadow), ptr(verts), ptr(normals), ptr(cR), ptr(cTc), ptr(lRc),
+                               ptr(lTc), ptr(light_bc), ptr(ambc), ptr(tex), ptr(nm), H, Wd, ptr(rgb), ptr(fr["y_true"]),
+                               ptr(fr["y_sil_eroded"]), W["photo"] * fscale, ptr(self.losses[_SLOT["photo"]:]), C.byref(gs), st))
+            check(L.harp_texture_reg(hc.h, 0, ptr(tex), H, Wd, ptr(off_albedo), ptr(self.uv_mask), W["albedo"] * fscale,
+                                     ptr(self.losses[_SLOT["albedo"]:]), ptr(self.app.g["texture"]), st))
+            check(L.harp_texture_reg(hc.h, 1, ptr(nm), H, Wd, ptr(off_normal), ptr(self.uv_mask), W["normal_reg"] * fscale,
+                                     ptr(self.losses[_SLOT["normal_reg"]:]), ptr(self.app.g["normal_map"]), st))
+        else:
+            check(L.harp_shade(hc.h, 0, B, S, focal, int(self.self_shadow), ptr(verts), ptr(normals), ptr(cR), ptr(cTc), ptr(lRc),
+                               ptr(lTc), ptr(light_bc), ptr(ambc), ptr(tex), ptr(nm), H, Wd, ptr(rgb), None, None, 0.0, None, None, st))
+        # ---- mesh regularisers + keypoint anchor (521-539)
+        if coarse_on:
+            w5 = (C.c_float * 5)(W["laplacian"] * fscale, W["normal"] * fscale, W["arap"] * fscale, W["kps_anchor"] * fscale,
+                                 W["vert_disp_reg"] * fscale)
+            check(L.harp_mesh_losses(hc.h, B, ptr(verts), ptr(self.ref_verts), ptr(joints), ptr(fr["init_joints"]), ptr(disps), w5,
+                                     ptr(self.losses[_SLOT["laplacian"]:]), ptr(d_verts), ptr(d_joints),
+                                     ptr(self.coarse.g["verts_disps"].view(-1)), st))
+        # ---- backward through the small per-frame chain, then geometry
+        if coarse_on or app_on:
+            g_cam, g_light, g_centroid, g_ambr = torch.autograd.grad(
+                [cT, lR, lT, light_b, amb], [cam_b, light_l, centroid, amb_leaf],
+                grad_outputs=[d_cT, d_lR, d_lT, d_lpos, d_amb.view(amb.shape)], allow_unused=True)
+            d_verts += (g_centroid / hc.V)[:, None, :]
+            d_verts0 = self._buf("d_verts0", (B, hc.V0, 3), zero=False)
+            check(L.harp_mesh_build_bwd(hc.h, B, ptr(verts0), ptr(disps), ptr(d_verts), ptr(d_normals), ptr(d_verts0),
+                                        ptr(self.coarse.g["verts_disps"].view(-1)), st))
+            d_pose48 = self._buf("d_pose48", (B, 48), zero=False)
+            d_betas = self._buf("d_betas", (B, 10), zero=False)
+            d_trans = self._buf("d_trans", (B, 3), zero=False)
+            check(L.harp_lbs_mano_bwd(hc.h, B, ptr(pose48), ptr(P["shape"]), 1, ptr(trans), ptr(d_verts0), ptr(d_joints),
+                                      ptr(d_pose48), ptr(d_betas), ptr(d_trans), st))
+            self.coarse.g["pose"].index_add_(0, fid, d_pose48[:, 3:])
+            self.coarse.g["cam"].index_add_(0, fid, g_cam)
+            self.coarse.g["shape"] += d_betas.sum(0)
+            self.app.g["light_positions"][0] += g_light
+            self.app.g["amb_ratio"] += g_ambr.view(1)
+            self.last = dict(d_rot=d_pose48[:, :3], d_trans=d_trans, alpha=alpha, rgb=rgb, verts=verts, joints=joints)
+        # ---- data-parallel exchange: ONE allreduce of the shared-parameter gradients
+        if R > 1:
+            self._allreduce_shared()
+        if update:
+            if coarse_on:
+                self.coarse.adam(self.lr_coarse)
+            if app_on:
+                self.app.adam(self.lr_app)
+        return self.losses
+
+    def _allreduce_shared(self):
+        """Per-frame rows (pose, cam) are rank-local under static frame sharding; everything else is shared and summed.
+        One flat buffer: [verts_disps | shape | light row 0 | amb | texture | normal_map | losses]."""
+        import torch.distributed as dist
+        cg, ag = self.coarse, self.app
+        a0 = cg.offsets[cg.names.index("verts_disps")]
+        parts = [cg.grad[a0:], ag.grad[:3], ag.grad[ag.offsets[ag.names.index("amb_ratio")]:], self.losses]
+        flat = torch.cat([p.reshape(-1) for p in parts])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
+        o = 0
+        for p in parts:
+            n = p.numel()
+            p.copy_(flat[o:o + n].view(p.shape))
+            o += n
+        # losses were frame means over the local batch (x 1/R applied to gradients only): average them
+        self.losses /= self.world_size
+
+    def loss_dict(self):
+        """One device->host read of the loss vector (the reference does >= 10 `.cpu()` syncs per iteration, 556-561)."""
+        vals = self.losses.detach().cpu().tolist()
+        d = dict(zip(LOSS_NAMES, vals))
+        d["total"] = sum(LOSS_WEIGHTS[k] * v for k, v in d.items())
+        return d

@@ -1,0 +1,156 @@
+/* harp_b200.h — C ABI of libharpb200.so: the B200-native (sm_100a) replacement for the PyTorch3D / manopth hot path of
+ * korrawe/harp (per-minibatch body of optimize_sequence.py:446-579).
+ *
+ * The reference has no FFI of its own: its seam is a set of Python call signatures.  Each entry
+ * point below names the reference call it replaces; the Python modules under `harp_b200/` bind them with ctypes and re-exposes the
+ * reference's Python signatures (INTEGRATION.md shows the binding a maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (enum below); harp_last_error() gives the message (thread local)
+ *   - all tensor arguments are DEVICE pointers to dense row-major fp32 / int32 unless marked [host]
+ *   - the caller (PyTorch) owns every tensor; the library owns only the opaque harp_ctx (static topology, model
+ *     constants, scratch sized by harp_ctx_reserve); no allocation happens inside hot calls
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it; one ctx per device+stream
+ *   - gradient outputs named d_* are ACCUMULATED INTO (+=) unless the comment says "overwritten"
+ *   - units: metres (the reference's mm scaling at manolayer.py:291-292 is undone at visualize.py:45-46)
+ */
+#ifndef HARP_B200_H
+#define HARP_B200_H
+
+#if defined(__GNUC__)
+#define HARP_API __attribute__((visibility("default")))
+#else
+#define HARP_API
+#endif
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct harp_ctx harp_ctx;
+
+enum {
+  HARP_OK = 0,
+  HARP_ERR_INVALID = -1,   /* bad argument / shape */
+  HARP_ERR_CUDA = -2,      /* CUDA runtime error (message has the string) */
+  HARP_ERR_CAPACITY = -3,  /* harp_ctx_reserve too small for this call */
+  HARP_ERR_NO_MODEL = -4   /* LBS called on a ctx created without a MANO model */
+};
+
+/* Static mesh topology + UV tables.  [host] pointers, copied at create time.
+ * faces0: coarse triangle list (manolayer th_faces, manolayer.py:82-83).  If `subdivide` != 0 the ctx applies one
+ * PyTorch3D SubdivideMeshes step (optimize_sequence.py:67-89): V = V0 + E0, F = 4*F0, face order f0|f1|f2|f3.
+ * faces_uvs (F,3) / verts_uvs (Vt,2): TexturesUV tables (utils/hand_model_utils.py:59-61); may be NULL (no shading). */
+typedef struct {
+  int32_t V0, F0;
+  const int32_t* faces0;
+  int32_t subdivide;
+  int32_t Vt;
+  const int32_t* faces_uvs;
+  const float* verts_uvs;
+} harp_topology;
+
+/* MANO constants, names as registered at manopth/manolayer.py:70-97.  [host] pointers, fp32, copied. */
+typedef struct {
+  const float* shapedirs;   /* (V0,3,10) */
+  const float* posedirs;    /* (V0,3,135) */
+  const float* v_template;  /* (V0,3) metres */
+  const float* J_regressor; /* (16,V0) */
+  const float* weights;     /* (V0,16) */
+  const float* hands_mean;  /* (45) */
+  const int32_t* tips;      /* (5) fingertip vertex ids, manolayer.py:272 */
+} harp_mano_model;
+
+HARP_API const char* harp_last_error(void);
+HARP_API int harp_version(void);
+
+HARP_API int harp_ctx_create(harp_ctx** out, const harp_topology* topo, const harp_mano_model* model /* nullable */);
+HARP_API void harp_ctx_destroy(harp_ctx* ctx);
+/* Size all scratch (bin lists, projected verts, light depth, per-frame Jacobians) for <= max_batch frames of
+ * img_size x img_size.  Allocates; call outside the hot loop. */
+HARP_API int harp_ctx_reserve(harp_ctx* ctx, int max_batch, int img_size);
+HARP_API int harp_ctx_dims(const harp_ctx* ctx, int32_t* V0, int32_t* V, int32_t* F, int32_t* E);
+/* Copy the (F,3) int32 (subdivided) face list to [host] memory, for callers that need Meshes.faces_padded(). */
+HARP_API int harp_ctx_faces(const harp_ctx* ctx, int32_t* faces_out);
+/* counters written by the kernels since the last call: [0] pixels with more than K=50 silhouette candidates
+ * (PyTorch3D would have kept only the 50 nearest), [1] bin-list capacity overflows.  [host] out. Synchronises. */
+HARP_API int harp_ctx_read_counters(harp_ctx* ctx, int64_t out[2], void* stream);
+
+/* ---- MANO linear blend skinning: ManoLayer.forward (manopth/manolayer.py:108-296), use_pca=False, axis-angle -------
+ * pose48 (B,48) = [rot3 | pose45]; betas (B,10) or one shared row if betas_shared; trans (B,3).
+ * verts0 (B,V0,3) m; joints (B,21,3) m. */
+HARP_API int harp_lbs_mano_fwd(harp_ctx*, int B, const float* pose48, const float* betas, int betas_shared, const float* trans,
+                      float* verts0, float* joints, void* stream);
+/* d_pose48 (B,48), d_betas (B,10) [per frame, caller sums for a shared shape], d_trans (B,3): overwritten. */
+HARP_API int harp_lbs_mano_bwd(harp_ctx*, int B, const float* pose48, const float* betas, int betas_shared, const float* trans,
+                      const float* d_verts0, const float* d_joints, float* d_pose48, float* d_betas, float* d_trans,
+                      void* stream);
+
+/* ---- mesh build: SubdivideMeshes + normal displacement + vertex normals (utils/visualize.py:48-64) -------------------
+ * verts0 (B,V0,3); disps (V) or NULL.  verts (B,V,3), normals (B,V,3) = Meshes.verts_normals_padded() of `verts`. */
+HARP_API int harp_mesh_build_fwd(harp_ctx*, int B, const float* verts0, const float* disps, float* verts, float* normals,
+                        void* stream);
+/* d_verts / d_normals (B,V,3) in (d_normals may be NULL).  d_verts0 (B,V0,3) overwritten; d_disps (V) accumulated. */
+HARP_API int harp_mesh_build_bwd(harp_ctx*, int B, const float* verts0, const float* disps, const float* d_verts,
+                        const float* d_normals, float* d_verts0, float* d_disps, void* stream);
+
+/* ---- mesh regularisers + keypoint anchor, value and gradient in one pass --------------------------------------------
+ * mesh_laplacian_smoothing / mesh_normal_consistency (optimize_sequence.py:536-537), arap_loss (loss/arap.py:4-57),
+ * kps_loss (loss/kps_loss.py:4-17), sum(disp^2) (optimize_sequence.py:533).
+ * w[5] = upstream weights for {laplacian, normal, arap, kps, disp}; losses[5] (device) receives the UNWEIGHTED values
+ * (accumulated, zero it first); gradients are weighted.  ref_verts (V,3); joints/init_joints (B,21,3) m / mm. */
+HARP_API int harp_mesh_losses(harp_ctx*, int B, const float* verts, const float* ref_verts, const float* joints,
+                     const float* init_joints_mm, const float* disps, const float w[5], float* losses,
+                     float* d_verts, float* d_joints, float* d_disps, void* stream);
+
+/* ---- cameras --------------------------------------------------------------------------------------------------------
+ * Per-frame world->view transform in PyTorch3D's row-vector convention X_view = X_world R + T.  R (B,3,3), T (B,3). */
+
+/* ---- soft silhouette: MeshRasterizer(K=50, blur=ln(1/1e-4-1)*sigma) + SoftSilhouetteShader ---------------------------
+ * (renderer/renderer_helper.py:37-58, utils/visualize.py:258-285).  alpha (B,S,S).
+ * mode 0: forward only.
+ * mode 1: backward with upstream gradient g_alpha (B,S,S): d_verts (B,V,3), d_R (B,9), d_T (B,3) accumulated.
+ * mode 2: fused L1 loss: target (B,S,S); loss (device scalar, accumulated, unweighted mean|target-alpha|);
+ *         gradients of weight*loss accumulated. */
+HARP_API int harp_silhouette(harp_ctx*, int mode, int B, int S, float focal, float sigma, const float* verts, const float* R,
+                    const float* T, float* alpha, const float* g_alpha_or_target, float weight, float* loss,
+                    float* d_verts, float* d_R, float* d_T, void* stream);
+
+/* ---- shadowed PBR colour render: MeshRendererShadow + SoftPhongShaderShadow + PBRMaterials.apply_normal_map ----------
+ * (renderer/renderer_helper.py:331-412,472-592; renderer/pbr_materials.py:58-124).
+ * verts, normals (B,V,3); cam R,T and light R,T (B,3,3)/(B,3) (process_info_for_shadow, renderer_helper.py:454-468);
+ * light_pos (B,3); amb (1) = sigmoid(amb_ratio) already applied; texture, normal_map (H,W,3) shared maps, normal_map RAW
+ * (normalised per texel inside, visualize.py:98).  self_shadow=0 renders with vis=1.  rgb (B,S,S,3).
+ * mode as above; for mode 1 g = g_rgb (B,S,S,3); for mode 2 g = y_true (B,S,S,3) and `mask` = eroded mask (B,S,S):
+ * loss = mean|y*m - rgb*m| (optimize_sequence.py:543). */
+typedef struct {
+  float *d_verts, *d_normals;        /* (B,V,3) */
+  float *d_cam_R, *d_cam_T;          /* (B,9),(B,3) */
+  float *d_light_R, *d_light_T;      /* (B,9),(B,3) */
+  float *d_light_pos;                /* (B,3) */
+  float *d_amb;                      /* (1) w.r.t. the post-sigmoid ambient */
+  float *d_texture, *d_normal_map;   /* (H,W,3) */
+} harp_shade_grads;
+
+HARP_API int harp_shade(harp_ctx*, int mode, int B, int S, float focal, int self_shadow, const float* verts,
+               const float* normals, const float* cam_R, const float* cam_T, const float* light_R, const float* light_T,
+               const float* light_pos, const float* amb, const float* texture, const float* normal_map, int texH,
+               int texW, float* rgb, const float* g_or_target, const float* mask, float weight, float* loss,
+               const harp_shade_grads* grads, void* stream);
+
+/* ---- texture regularisers: albedo_reg / normal_reg (loss/texture_reg.py:5-66) ----------------------------------------
+ * offsets (H,W,2) int32 = the reference's CPU-RNG neighbour offsets, passed in.  kind 0: albedo_reg; 1: normal_reg
+ * (adds 0.2*close_to_z with the reference's dim=2 norm).  loss accumulated (unweighted); d_map accumulated. */
+HARP_API int harp_texture_reg(harp_ctx*, int kind, const float* map, int H, int W, const int32_t* offsets, const float* uv_mask,
+                     float weight, float* loss, float* d_map, void* stream);
+
+/* ---- Adam (torch.optim.Adam defaults, optimize_sequence.py:253-310,567-573), fused over a flat buffer ----------------*/
+HARP_API int harp_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+              float beta2, float eps, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HARP_B200_H */

@@ -1,0 +1,246 @@
+"""GPU parity: every CUDA kernel pair, called through the C ABI (ctypes), against the CPU oracle on identical inputs."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import harp_oracle as O
+from util import load_golden, golden_case, rel_l2, frac_within
+
+
+def _ctx(model, topo_sub, tmpl=None, with_uv=True):
+    from harp_b200 import synth
+    from harp_b200.ops import HarpContext
+    tmpl = tmpl or synth.load_template("hand")
+    pack = synth.make_mano_pack(seed=0, template=tmpl)
+    return HarpContext(pack["th_faces"], subdivide=topo_sub, faces_uvs=tmpl["faces_uvs"] if with_uv else None,
+                       verts_uvs=tmpl["verts_uvs"] if with_uv else None, mano=pack)
+
+
+@pytest.fixture(scope="module")
+def case():
+    g = load_golden("c2_full_128_sub")
+    return golden_case(g)
+
+
+def test_lbs_forward_backward(case):
+    from harp_b200.ops import LbsMano
+    model, topo, params, batch, cfg = case
+    hc = _ctx(model, True)
+    B = params["pose"].shape[0]
+    pose48 = torch.cat((params["rot"], params["pose"]), 1)
+    p_o = pose48.clone().requires_grad_(True); b_o = params["shape"].clone().requires_grad_(True); t_o = params["trans"].clone().requires_grad_(True)
+    v_o, j_o = O.mano_forward(model, p_o, b_o.repeat(B, 1), t_o)
+    v_o, j_o = v_o / 1000, j_o / 1000
+    gv, gj = torch.randn_like(v_o), torch.randn_like(j_o)
+    (v_o * gv).sum().add((j_o * gj).sum()).backward()
+    p_c = pose48.cuda().requires_grad_(True); b_c = params["shape"].cuda().requires_grad_(True); t_c = params["trans"].cuda().requires_grad_(True)
+    v_c, j_c = LbsMano.apply(hc, p_c, b_c, t_c)
+    ((v_c * gv.cuda()).sum() + (j_c * gj.cuda()).sum()).backward()
+    assert (v_c.cpu() - v_o).abs().max() < 2e-6      # metres
+    assert (j_c.cpu() - j_o).abs().max() < 2e-6
+    assert rel_l2(p_c.grad.cpu(), p_o.grad) < 1e-4
+    assert rel_l2(b_c.grad.cpu(), b_o.grad) < 1e-4
+    assert rel_l2(t_c.grad.cpu(), t_o.grad) < 1e-4
+
+
+@pytest.mark.parametrize("sub", [True, False])
+def test_mesh_build_forward_backward(case, sub):
+    from harp_b200.ops import MeshBuild
+    import pytorch3d._core as p3d
+    model, topo, params, batch, cfg = case
+    hc = _ctx(model, sub)
+    topo_o = O.Topology(model["th_faces"], subdivide=sub)
+    torch.manual_seed(0)
+    B = 3
+    v0 = model["th_v_template"].repeat(B, 1, 1) + 0.002 * torch.randn(B, 778, 3)
+    disps = 0.001 * torch.randn(topo_o.V, 1)
+    v0_o, d_o = v0.clone().requires_grad_(True), disps.clone().requires_grad_(True)
+    verts_o = O.build_mesh(v0_o, topo_o, d_o)
+    n_o = p3d.Meshes(verts_o, topo_o.faces[None].expand(B, -1, -1)).verts_normals_padded()
+    gv, gn = torch.randn_like(verts_o), torch.randn_like(n_o)
+    ((verts_o * gv).sum() + (n_o * gn).sum()).backward()
+    v0_c, d_c = v0.cuda().requires_grad_(True), disps.cuda().requires_grad_(True)
+    verts_c, n_c = MeshBuild.apply(hc, v0_c, d_c)
+    ((verts_c * gv.cuda()).sum() + (n_c * gn.cuda()).sum()).backward()
+    assert (hc.faces().cpu() == topo_o.faces).all()
+    assert (verts_c.cpu() - verts_o).abs().max() < 1e-6
+    assert (n_c.cpu() - n_o).abs().max() < 2e-4
+    assert rel_l2(v0_c.grad.cpu(), v0_o.grad) < 2e-4
+    assert rel_l2(d_c.grad.cpu(), d_o.grad) < 2e-4
+
+
+def test_mesh_losses(case):
+    from harp_b200.ops import MeshLosses
+    model, topo, params, batch, cfg = case
+    hc = _ctx(model, True)
+    torch.manual_seed(1)
+    B = 2
+    verts = batch["ref_verts"].repeat(B, 1, 1) + 0.0005 * torch.randn(B, topo.V, 3)
+    joints = 0.05 * torch.randn(B, 21, 3)
+    init = 50 * torch.randn(B, 21, 3)
+    disps = 0.001 * torch.randn(topo.V, 1)
+    w = torch.tensor([4.0, 0.1, 0.2, 10.0, 2.0])
+    v_o, j_o, d_o = verts.clone().requires_grad_(True), joints.clone().requires_grad_(True), disps.clone().requires_grad_(True)
+    lap, nc = O.mesh_reg_losses(v_o, topo)
+    lo = torch.stack([lap, nc, O.arap_loss(v_o, batch["ref_verts"], topo), O.kps_loss(init, j_o), torch.sum(d_o ** 2.0)])
+    (lo * w).sum().backward()
+    v_c, j_c, d_c = verts.cuda().requires_grad_(True), joints.cuda().requires_grad_(True), disps.cuda().requires_grad_(True)
+    lc = MeshLosses.apply(hc, v_c, batch["ref_verts"].cuda(), j_c, init.cuda(), d_c)
+    (lc * w.cuda()).sum().backward()
+    for i in range(5):
+        assert math.isclose(float(lc[i]), float(lo[i]), rel_tol=2e-4), (i, float(lc[i]), float(lo[i]))
+    assert rel_l2(v_c.grad.cpu(), v_o.grad) < 5e-4
+    assert rel_l2(j_c.grad.cpu(), j_o.grad) < 1e-4
+    assert rel_l2(d_c.grad.cpu(), d_o.grad) < 1e-5
+
+
+@pytest.mark.parametrize("S,sub", [(128, True), (256, False), (64, True)])
+def test_silhouette_forward_backward(case, S, sub):
+    """Same world-space verts into both paths.  alpha is hard 0/1 except in the +-1/3 px bands, where the sigma=1e-7
+    sigmoid amplifies 1-ulp differences of the projected coordinates; both tolerances are stated."""
+    from harp_b200.ops import Silhouette
+    model, topo, params, batch, cfg = case
+    hc = _ctx(model, sub)
+    topo_o = O.Topology(model["th_faces"], subdivide=sub)
+    B = 2
+    focal = 1000.0 * S / 224.0
+    pose48 = torch.cat((params["rot"], params["pose"]), 1)
+    vm, _ = O.mano_forward(model, pose48, params["shape"].repeat(B, 1), params["trans"])
+    verts = O.build_mesh(vm / 1000.0, topo_o, None).detach()
+    cam = params["cam"]
+    v_o, cam_o = verts.clone().requires_grad_(True), cam.clone().requires_grad_(True)
+    a_o, ov = O.render_silhouette(v_o, topo_o, cam_o, focal, S, return_overflow=True)
+    torch.manual_seed(3)
+    g = torch.randn_like(a_o)
+    (a_o * g).sum().backward()
+    v_c, cam_c = verts.cuda().requires_grad_(True), cam.cuda().requires_grad_(True)
+    R = O.cam_R(B, torch.float32).cuda()
+    T = O.cam_to_T(cam_c, focal, S)
+    a_c = Silhouette.apply(hc, v_c, R, T, focal, S, 1e-7)
+    (a_c * g.cuda()).sum().backward()
+    cnt = hc.counters()
+    assert cnt["bin_overflow"] == 0
+    if not ov:
+        assert cnt["sil_k_overflow_pixels"] == 0
+        d = (a_c.cpu() - a_o.detach()).abs()
+        assert float((d <= 1e-4).double().mean()) >= 0.999, float((d <= 1e-4).double().mean())
+        assert float((d <= 5e-3).double().mean()) >= 0.9999
+        assert rel_l2(v_c.grad.cpu(), v_o.grad) < 2e-2
+        assert rel_l2(cam_c.grad.cpu(), cam_o.grad) < 2e-2
+    else:
+        assert cnt["sil_k_overflow_pixels"] > 0
+
+
+@pytest.mark.parametrize("S,shadow", [(128, True), (64, True), (128, False)])
+def test_shade_forward_backward(case, S, shadow):
+    """Colour render: hard visibility (a 1-ulp vertex move can flip a pixel's face) => image tolerance on a pixel
+    fraction; gradients are sums over ~1e4 pixels and must agree to 1e-3 in relative L2."""
+    import pytorch3d._core as p3d
+    from harp_b200.ops import Shade
+    from harp_b200 import camera
+    model, topo, params, batch, cfg = case
+    hc = _ctx(model, True)
+    B = 2
+    focal = 1000.0 * S / 224.0
+    pose48 = torch.cat((params["rot"], params["pose"]), 1)
+    vm, _ = O.mano_forward(model, pose48, params["shape"].repeat(B, 1), params["trans"])
+    verts = O.build_mesh(vm / 1000.0, topo, params["verts_disps"]).detach()
+    names = ("verts", "cam", "light", "amb", "tex", "nm")
+    base = dict(verts=verts, cam=params["cam"], light=params["light_position"][None].repeat(B, 1).clone(),
+                amb=params["amb_ratio"], tex=params["texture"], nm=params["normal_map"])
+    o = {k: v.clone().requires_grad_(True) for k, v in base.items()}
+    rgb_o = O.render_rgb_shadow(o["verts"], topo, o["cam"], o["light"], o["amb"], o["tex"], o["nm"], focal, S, shadow)
+    torch.manual_seed(5)
+    g = torch.randn_like(rgb_o)
+    (rgb_o * g).sum().backward()
+    c = {k: v.clone().cuda().requires_grad_(True) for k, v in base.items()}
+    faces = topo.faces.cuda()[None].expand(B, -1, -1)
+    normals = p3d.Meshes(c["verts"], faces).verts_normals_padded()
+    cR = camera.flip_xy_R(B, "cuda")
+    cT = camera.cam_to_T(c["cam"], focal, S)
+    lR, lT = camera.light_camera(c["light"], c["verts"].mean(1))
+    rgb_c = Shade.apply(hc, c["verts"], normals, cR, cT, lR, lT, c["light"], torch.sigmoid(c["amb"]), c["tex"], c["nm"],
+                        focal, S, int(shadow))
+    (rgb_c * g.cuda()).sum().backward()
+    assert hc.counters()["bin_overflow"] == 0
+    d = (rgb_c.detach().cpu() - rgb_o.detach()).abs().amax(-1)
+    assert float((d <= 1e-4).double().mean()) >= 0.995, float((d <= 1e-4).double().mean())
+    assert float((d <= 2e-2).double().mean()) >= 0.9995
+    for k in names:
+        r = rel_l2(c[k].grad.cpu(), o[k].grad)
+        assert r < (5e-3 if k in ("verts",) else 2e-3), (k, r)
+
+
+def test_texture_reg_and_adam():
+    from harp_b200 import synth
+    from harp_b200.ops import TextureReg, adam_step
+    app = synth.make_appearance(seed=2)
+    mask = torch.tensor(synth.load_template("hand")["uv_mask"])
+    off = synth.make_reg_offsets(seed=3, std=1.0)
+    for kind, key in ((0, "texture"), (1, "normal_map")):
+        t_o = app[key].clone().requires_grad_(True)
+        lo = O.smooth_texture_reg(t_o, off, mask) if kind == 0 else O.normal_reg(t_o, off, mask)
+        lo.backward()
+        t_c = app[key].clone().cuda().requires_grad_(True)
+        lc = TextureReg.apply(None, kind, t_c, off.cuda(), mask.cuda())
+        lc.backward()
+        assert math.isclose(float(lc), float(lo), rel_tol=1e-4)
+        assert rel_l2(t_c.grad.cpu(), t_o.grad) < 1e-4
+    torch.manual_seed(0)
+    p = torch.randn(1000, requires_grad=True)
+    opt = torch.optim.Adam([p], lr=1e-2)
+    pc, m, v = p.detach().clone().cuda(), torch.zeros(1000).cuda(), torch.zeros(1000).cuda()
+    for step in range(1, 6):
+        gr = torch.randn(1000)
+        p.grad = gr.clone()
+        opt.step()
+        adam_step(pc, gr.cuda(), m, v, 1e-2, step)
+    assert (pc.cpu() - p.detach()).abs().max() < 1e-6
+
+
+def _fitter_from_case(case, S=None):
+    from harp_b200 import synth
+    from harp_b200.step import HarpFitter
+    model, topo, params, batch, cfg = case
+    hc = _ctx(model, topo.edges0 is not None)
+    B = params["pose"].shape[0]
+    p = dict(params)
+    p["light_positions"] = params["light_position"][None].repeat(B, 1)
+    frames = dict(y_true=batch["y_true"], y_sil=batch["y_sil"], y_sil_eroded=batch["y_sil_eroded"], init_joints=batch["init_joints"])
+    return HarpFitter(hc, p, frames, batch["ref_verts"], batch["uv_mask"], cfg["img_size"], cfg["focal_length"]), hc
+
+
+@pytest.mark.parametrize("name", ["c2_full_128_sub", "c1_sil_256_coarse"])
+def test_fused_step_matches_reference_golden(name):
+    """The whole fused step against vectors produced by the reference's own Python (tests/golden/make_golden.py)."""
+    from harp_b200.step import LOSS_NAMES
+    g = load_golden(name)
+    case = golden_case(g)
+    model, topo, params, batch, cfg = case
+    ft, hc = _fitter_from_case(case)
+    B = params["pose"].shape[0]
+    fid = torch.arange(B, device="cuda")
+    ft.step(fid, batch["off_albedo"].cuda().int().contiguous(), batch["off_normal"].cuda().int().contiguous(),
+            stage=cfg["stage"], update=False)
+    ld = ft.loss_dict()
+    cnt = hc.counters()
+    assert cnt["bin_overflow"] == 0 and cnt["sil_k_overflow_pixels"] == 0
+    for k in LOSS_NAMES:
+        if "loss_" + k in g:
+            assert math.isclose(ld[k], float(g["loss_" + k]), rel_tol=2e-3, abs_tol=1e-7), (k, ld[k], float(g["loss_" + k]))
+    assert math.isclose(ld["total"], float(g["loss_total"]), rel_tol=1e-3)
+    d = (ft.last["alpha"].cpu() - torch.tensor(g["img_sil"])).abs()
+    assert float((d <= 1e-4).double().mean()) >= 0.998
+    grads = dict(ft.coarse.g); grads.update(ft.app.g)
+    grads["rot"], grads["trans"] = ft.last["d_rot"], ft.last["d_trans"]
+    tol = dict(pose=1e-2, rot=1e-2, cam=1e-2, shape=1e-2, verts_disps=2e-2, texture=1e-2, normal_map=1e-2,
+               light_positions=2e-2, amb_ratio=1e-2, trans=1e-2)
+    for k, t in tol.items():
+        gg = torch.tensor(g["grad_" + k])
+        if float(gg.abs().max()) == 0.0:
+            continue
+        r = rel_l2(grads[k].cpu().view(gg.shape), gg)
+        assert r < t, (k, r)
