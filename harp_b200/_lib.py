@@ -37,7 +37,7 @@ class HarpError(RuntimeError):
 _lib = None
 
 # every symbol include/harp_b200.h declares (tests/test_abi.py checks the library exports exactly these)
-SYMBOLS = ["harp_last_error", "harp_version", "harp_ctx_create", "harp_ctx_destroy", "harp_ctx_reserve", "harp_ctx_dims",
+SYMBOLS = ["harp_last_error", "harp_version", "harp_launch_count", "harp_ctx_profile", "harp_ctx_profile_read", "harp_ctx_create", "harp_ctx_destroy", "harp_ctx_reserve", "harp_ctx_dims",
            "harp_ctx_faces", "harp_ctx_read_counters", "harp_lbs_mano_fwd", "harp_lbs_mano_bwd", "harp_mesh_build_fwd",
            "harp_mesh_build_bwd", "harp_mesh_losses", "harp_silhouette", "harp_shade", "harp_texture_reg", "harp_adam"]
 
@@ -51,6 +51,10 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.harp_last_error.restype = C.c_char_p
         L.harp_ctx_destroy.restype = None
+        L.harp_launch_count.restype = C.c_int64
+        L.harp_launch_count.argtypes = []
+        L.harp_ctx_profile.argtypes = [C.c_void_p, C.c_int]
+        L.harp_ctx_profile_read.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         vp, i, f = C.c_void_p, C.c_int, C.c_float
         L.harp_ctx_create.argtypes = [C.POINTER(vp), C.POINTER(HarpTopology), C.POINTER(HarpManoModel)]
         L.harp_ctx_destroy.argtypes = [vp]

@@ -11,6 +11,10 @@
 #define HARP_SM_COUNT 148  // B200: 2 dies x 74 SMs
 
 void harp_set_error(const std::string& msg);
+void harp_count_launches(int n);
+struct harp_ctx;
+void harp_prof_begin(harp_ctx* c, int kernel_id, cudaStream_t st);
+void harp_prof_end(harp_ctx* c, int kernel_id, cudaStream_t st);
 
 #define HARP_CHECK_CUDA(expr)                                                                       \
   do {                                                                                              \
@@ -29,14 +33,16 @@ void harp_set_error(const std::string& msg);
     }                                                                                               \
   } while (0)
 
-#define HARP_LAUNCH_CHECK()                                                                         \
+#define HARP_LAUNCH_CHECK_N(n)                                                                      \
   do {                                                                                              \
+    harp_count_launches(n);                                                                         \
     cudaError_t _e = cudaGetLastError();                                                            \
     if (_e != cudaSuccess) {                                                                        \
       harp_set_error(std::string("kernel launch: ") + cudaGetErrorString(_e));                      \
       return HARP_ERR_CUDA;                                                                         \
     }                                                                                               \
   } while (0)
+#define HARP_LAUNCH_CHECK() HARP_LAUNCH_CHECK_N(1)
 
 // Topology tables + model constants + scratch, all device resident.
 struct harp_ctx {
@@ -76,6 +82,7 @@ struct harp_ctx {
   float* vtmp = nullptr;          // (B,V,3) scratch
   float* vtmp2 = nullptr;         // (B,V,3) scratch
   unsigned long long* counters = nullptr;  // [0] K overflow pixels, [1] bin overflow
+  struct harp_prof* prof = nullptr;        // host-side event lists (harp_ctx_profile)
 };
 
 // ---------------------------------------------------------------------------------------------- small vector math

@@ -11,6 +11,42 @@ void harp_set_error(const std::string& msg) { g_last_error = msg; }
 extern "C" const char* harp_last_error(void) { return g_last_error.c_str(); }
 extern "C" int harp_version(void) { return 100; }
 
+#include <atomic>
+static std::atomic<int64_t> g_launches{0};
+void harp_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" int64_t harp_launch_count(void) { return g_launches.load(); }
+
+struct harp_prof {
+  bool enabled = false;
+  std::vector<cudaEvent_t> ev[2];  // start/stop pairs per kernel id
+};
+void harp_prof_begin(harp_ctx* c, int id, cudaStream_t st) {
+  if (!c->prof || !c->prof->enabled) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); c->prof->ev[id].push_back(e); }
+}
+void harp_prof_end(harp_ctx* c, int id, cudaStream_t st) { harp_prof_begin(c, id, st); }
+extern "C" int harp_ctx_profile(harp_ctx* c, int enable) {
+  HARP_REQUIRE(c, HARP_ERR_INVALID, "harp_ctx_profile: null ctx");
+  if (!c->prof) c->prof = new harp_prof();
+  c->prof->enabled = enable != 0;
+  return HARP_OK;
+}
+extern "C" int harp_ctx_profile_read(harp_ctx* c, int id, float* total_ms, int* launches) {
+  HARP_REQUIRE(c && id >= 0 && id < 2 && total_ms && launches, HARP_ERR_INVALID, "harp_ctx_profile_read: bad argument");
+  *total_ms = 0.f; *launches = 0;
+  if (!c->prof) return HARP_OK;
+  auto& v = c->prof->ev[id];
+  HARP_CHECK_CUDA(cudaDeviceSynchronize());
+  for (size_t i = 0; i + 1 < v.size(); i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, v[i], v[i + 1]) == cudaSuccess) { *total_ms += ms; ++*launches; }
+  }
+  for (cudaEvent_t e : v) cudaEventDestroy(e);
+  v.clear();
+  return HARP_OK;
+}
+
 namespace {
 
 struct EdgeTables {
@@ -204,6 +240,10 @@ extern "C" void harp_ctx_destroy(harp_ctx* c) {
                   c->nc_pairs, c->face_uvs, c->shapedirs, c->posedirs, c->v_template, c->weights, c->hands_mean,
                   c->J_template, c->J_shapedirs, c->tips, c->counters};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (c->prof) {
+    for (auto& v : c->prof->ev) for (cudaEvent_t e : v) cudaEventDestroy(e);
+    delete c->prof;
+  }
   delete c;
 }
 

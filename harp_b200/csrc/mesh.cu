@@ -305,7 +305,7 @@ extern "C" int harp_mesh_build_fwd(harp_ctx* c, int B, const float* verts0, cons
   cudaStream_t st = (cudaStream_t)stream;
   build_displace_kernel<<<nblk((size_t)B * c->V), TPB, 0, st>>>(*c, B, verts0, disps, verts);
   if (normals) vertex_normals_kernel<<<nblk((size_t)B * c->V), TPB, 0, st>>>(*c, B, verts, normals);
-  HARP_LAUNCH_CHECK();
+  HARP_LAUNCH_CHECK_N(normals ? 2 : 1);
   return HARP_OK;
 }
 
@@ -328,7 +328,7 @@ extern "C" int harp_mesh_build_bwd(harp_ctx* c, int B, const float* verts0, cons
     g = c->vtmp;
   }
   subdivide_bwd_kernel<<<nblk((size_t)B * c->V0), TPB, 0, st>>>(*c, B, g, d_verts0);
-  HARP_LAUNCH_CHECK();
+  HARP_LAUNCH_CHECK_N(1 + (d_normals ? 3 : 0) + (disps ? 2 : 0));
   return HARP_OK;
 }
 
@@ -342,6 +342,6 @@ extern "C" int harp_mesh_losses(harp_ctx* c, int B, const float* verts, const fl
   if (ref_verts) arap_kernel<<<nblk((size_t)B * c->E), TPB, 0, st>>>(*c, B, verts, ref_verts, w[2], losses + 2, d_verts);
   if (joints && init_joints_mm) kps_kernel<<<B, 32, 0, st>>>(B, joints, init_joints_mm, w[3], losses + 3, d_joints);
   if (disps) disp_reg_kernel<<<nblk(c->V), TPB, 0, st>>>(c->V, disps, w[4], losses + 4, d_disps);
-  HARP_LAUNCH_CHECK();
+  HARP_LAUNCH_CHECK_N(1 + (c->NP > 0) + (ref_verts != nullptr) + (joints && init_joints_mm) + (disps != nullptr));
   return HARP_OK;
 }

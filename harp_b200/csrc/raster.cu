@@ -271,7 +271,7 @@ int harp_build_bins(harp_ctx* c, int view, int B, int S, float radius, const flo
   bin_kernel<false><<<nblk((size_t)B * c->F), TPB, 0, st>>>(*c, B, S, radius, ndc, count, start, fill, list);
   bin_scan_kernel<<<B, 1024, 0, st>>>(*c, c->tiles, count, start);
   bin_kernel<true><<<nblk((size_t)B * c->F), TPB, 0, st>>>(*c, B, S, radius, ndc, count, start, fill, list);
-  HARP_LAUNCH_CHECK();
+  HARP_LAUNCH_CHECK_N(3);
   return HARP_OK;
 }
 
@@ -311,12 +311,14 @@ extern "C" int harp_silhouette(harp_ctx* c, int mode, int B, int S, float focal,
   float inv_n = 1.f / ((float)B * (float)S * (float)S);
   float gscale = weight * inv_n;
   const int32_t *cnt = c->bin_count, *bst = c->bin_start, *lst = c->bin_list;
+  harp_prof_begin(c, 0, st);
   if (mode == 0)
     sil_kernel<0><<<grid, HARP_TILE * HARP_TILE, 0, st>>>(*c, S, sigma, blur, radius, c->ndc_cam, cnt, bst, lst, alpha, nullptr, 0.f, 0.f, nullptr, nullptr);
   else if (mode == 1)
     sil_kernel<1><<<grid, HARP_TILE * HARP_TILE, 0, st>>>(*c, S, sigma, blur, radius, c->ndc_cam, cnt, bst, lst, alpha, gin, 0.f, 0.f, nullptr, c->d_ndc_cam);
   else
     sil_kernel<2><<<grid, HARP_TILE * HARP_TILE, 0, st>>>(*c, S, sigma, blur, radius, c->ndc_cam, cnt, bst, lst, alpha, gin, gscale, inv_n, loss, c->d_ndc_cam);
+  harp_prof_end(c, 0, st);
   HARP_LAUNCH_CHECK();
   if (mode != 0) {
     if ((rc = harp_project_bwd(c, B, S, focal, verts, R, T, c->d_ndc_cam, d_verts, d_R, d_T, st)) != HARP_OK) return rc;

@@ -428,9 +428,11 @@ extern "C" int harp_shade(harp_ctx* c, int mode, int B, int S, float focal, int 
     a.d_amb = grads->d_amb; a.d_texture = grads->d_texture; a.d_normal_map = grads->d_normal_map;
     a.d_light_zbuf = c->d_light_zbuf;
   }
+  harp_prof_begin(c, 1, st);
   if (mode == 0) shade_kernel<0><<<grid, NT, 0, st>>>(*c, a);
   else if (mode == 1) shade_kernel<1><<<grid, NT, 0, st>>>(*c, a);
   else shade_kernel<2><<<grid, NT, 0, st>>>(*c, a);
+  harp_prof_end(c, 1, st);
   HARP_LAUNCH_CHECK();
   if (mode != 0) {
     if (self_shadow) {

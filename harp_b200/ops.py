@@ -95,6 +95,19 @@ class HarpContext:
             self._faces = torch.from_numpy(host).long().to(self.device)
         return self._faces
 
+    def profile(self, enable=True):
+        """Bracket the silhouette / shade pixel kernels with CUDA events on the launch stream (bench roofline timing)."""
+        check(_lib.lib().harp_ctx_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        """-> {'silhouette': (total_ms, launches), 'shade': (total_ms, launches)} since the last read; synchronises."""
+        out = {}
+        for i, n in enumerate(("silhouette", "shade")):
+            ms, k = C.c_float(), C.c_int()
+            check(_lib.lib().harp_ctx_profile_read(self.h, i, C.byref(ms), C.byref(k)))
+            out[n] = (ms.value, k.value)
+        return out
+
     def counters(self):
         out = (C.c_int64 * 2)()
         check(_lib.lib().harp_ctx_read_counters(self.h, out, stream()))

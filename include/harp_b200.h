@@ -78,6 +78,14 @@ HARP_API int harp_ctx_faces(const harp_ctx* ctx, int32_t* faces_out);
  * (PyTorch3D would have kept only the 50 nearest), [1] bin-list capacity overflows.  [host] out. Synchronises. */
 HARP_API int harp_ctx_read_counters(harp_ctx* ctx, int64_t out[2], void* stream);
 
+/* Number of CUDA kernels this library has launched in this process (all contexts), for launch accounting. */
+HARP_API int64_t harp_launch_count(void);
+/* Per-kernel device timing.  enable != 0: the two pixel kernels (id 0 = silhouette, 1 = shade) are bracketed by CUDA
+ * events on the launch stream.  harp_ctx_profile_read synchronises, returns the summed elapsed ms and launch count since
+ * the last read, and clears. */
+HARP_API int harp_ctx_profile(harp_ctx* ctx, int enable);
+HARP_API int harp_ctx_profile_read(harp_ctx* ctx, int kernel_id, float* total_ms, int* launches);
+
 /* ---- MANO linear blend skinning: ManoLayer.forward (manopth/manolayer.py:108-296), use_pca=False, axis-angle -------
  * pose48 (B,48) = [rot3 | pose45]; betas (B,10) or one shared row if betas_shared; trans (B,3).
  * verts0 (B,V0,3) m; joints (B,21,3) m. */

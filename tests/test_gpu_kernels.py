@@ -236,11 +236,18 @@ def test_fused_step_matches_reference_golden(name):
     assert float((d <= 1e-4).double().mean()) >= 0.998
     grads = dict(ft.coarse.g); grads.update(ft.app.g)
     grads["rot"], grads["trans"] = ft.last["d_rot"], ft.last["d_trans"]
-    tol = dict(pose=1e-2, rot=1e-2, cam=1e-2, shape=1e-2, verts_disps=2e-2, texture=1e-2, normal_map=1e-2,
+    # Dense parameters: relative L2.  Texture / normal map: each hit pixel deposits +-w/(3 B S^2) on its own 4 texels
+    # (sign of an L1 residual), so ONE pixel whose nearest face or residual sign differs moves the L2 norm by ~2/sqrt(N_hit)
+    # (N_hit ~ 5e3 at 128^2); the faithful statement is element-wise agreement on all but a handful of texels.
+    tol = dict(pose=1e-2, rot=1e-2, cam=1e-2, shape=1e-2, verts_disps=2e-2, texture=6e-2, normal_map=6e-2,
                light_positions=2e-2, amb_ratio=1e-2, trans=1e-2)
     for k, t in tol.items():
         gg = torch.tensor(g["grad_" + k])
         if float(gg.abs().max()) == 0.0:
             continue
-        r = rel_l2(grads[k].cpu().view(gg.shape), gg)
+        mine = grads[k].cpu().view(gg.shape)
+        r = rel_l2(mine, gg)
         assert r < t, (k, r)
+        if k in ("texture", "normal_map"):
+            frac = frac_within(mine, gg, 1e-3 * float(gg.abs().max()))
+            assert frac >= 0.9995, (k, frac)
