@@ -131,6 +131,7 @@ def main():
     ap.add_argument("--frames", type=int, default=FRAMES)
     ap.add_argument("--size", type=int, default=SIZE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -139,7 +140,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        k, w = max(1, min(args.steps, 3)), min(args.warmup, 1)
+        # one frame per step (~1.5 s on 8 cores): honour K and W, bounded so the arm ends within a few minutes
+        k, w = max(1, min(args.steps, 60)), max(0, min(args.warmup, 5))
         r = cpu_reference(k, w, frames=1, size=args.size)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": k,
                 "warmup": w, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -187,8 +189,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
     e0.record()
+    torch.cuda.nvtx.range_push("harp_timed")  # ncu --nvtx --nvtx-include "harp_timed/" isolates the timed region
     for _ in range(args.steps):
         run_step()
+    torch.cuda.nvtx.range_pop()
     e1.record()
     sync()
     launches = _lib.lib().harp_launch_count() - n0
@@ -216,13 +220,16 @@ def main():
         ft.step(fid, oa, on, stage="both", update=True, batch=stage)
         return ft.loss_dict()
 
-    e2e_step()
+    if args.no_e2e:
+        k_e2e = 0
+    else:
+        e2e_step()
     sync()
     t0 = time.perf_counter()
     for _ in range(k_e2e):
         e2e_step()
     sync()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    e2e_s = torch.tensor([max(time.perf_counter() - t0, 1e-9)], device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
 

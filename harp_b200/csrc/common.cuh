@@ -62,6 +62,7 @@ struct harp_ctx {
   float* face_uvs = nullptr;     // (F,3,2)
   // MANO model
   float *shapedirs = nullptr, *posedirs = nullptr, *v_template = nullptr, *weights = nullptr, *hands_mean = nullptr;
+  float* weightsT = nullptr;      // (16,V0) transposed skinning weights
   float *J_template = nullptr, *J_shapedirs = nullptr;  // (16,3), (16,3,10) = J_regressor folded
   int32_t* tips = nullptr;
   // scratch (harp_ctx_reserve)
@@ -69,8 +70,12 @@ struct harp_ctx {
   int64_t bin_cap = 0;            // bin list capacity per frame
   float* ndc_cam = nullptr;       // (B,V,3)
   float* ndc_light = nullptr;     // (B,V,3)
-  float* d_ndc_cam = nullptr;     // (B,V,3)
-  float* d_ndc_light = nullptr;   // (B,V,3)
+  float* d_ndc_cam = nullptr;     // (B,V,4) xyz + pad: 16-byte rows so one vector atomic covers a vertex
+  float* d_ndc_light = nullptr;   // (B,V,4)
+  float* d_verts4 = nullptr;      // (B,V,4) shade-backward accumulators, folded into the caller's (B,V,3) tensors
+  float* d_normals4 = nullptr;    // (B,V,4)
+  float* d_tex4 = nullptr;        // (2,texcap,4) texture / normal-map gradient accumulators
+  int64_t texcap = 0;
   int32_t* bin_count = nullptr;   // (2,B,tiles)  [0]=camera view, [1]=light view
   int32_t* bin_start = nullptr;   // (2,B,tiles)
   int32_t* bin_fill = nullptr;    // (2,B,tiles)
@@ -108,6 +113,11 @@ __device__ inline void atomic_add3(float* p, f3 v) {
   atomicAdd(p + 0, v.x);
   atomicAdd(p + 1, v.y);
   atomicAdd(p + 2, v.z);
+}
+
+// one 16-byte vector reduction (sm_90+): 3x fewer L2 atomic operations than three scalar REDs
+__device__ inline void atomic_add4(float* p, float x, float y, float z) {
+  atomicAdd(reinterpret_cast<float4*>(p), make_float4(x, y, z, 0.f));
 }
 
 __device__ inline float warp_sum(float v) {

@@ -209,6 +209,10 @@ extern "C" int harp_ctx_create(harp_ctx** out, const harp_topology* topo, const 
     }
     sd.swap(sdT);
     pd.swap(pdT);
+    std::vector<float> wT((size_t)V0 * 16);
+    for (int v = 0; v < V0; ++v)
+      for (int j = 0; j < 16; ++j) wT[(size_t)j * V0 + v] = w[(size_t)v * 16 + j];
+    UP(weightsT, wT);
     UP(shapedirs, sd); UP(posedirs, pd); UP(v_template, vt); UP(weights, w); UP(hands_mean, hm); UP(tips, tips);
     UP(J_template, Jt); UP(J_shapedirs, Js);
     c->has_model = true;
@@ -226,7 +230,9 @@ extern "C" int harp_ctx_create(harp_ctx** out, const harp_topology* topo, const 
 
 static void free_scratch(harp_ctx* c) {
   void* ptrs[] = {c->ndc_cam, c->ndc_light, c->d_ndc_cam, c->d_ndc_light, c->bin_count, c->bin_start, c->bin_fill,
-                  c->bin_list, c->light_zbuf, c->light_face, c->d_light_zbuf, c->vN, c->vtmp, c->vtmp2};
+                  c->bin_list, c->light_zbuf, c->light_face, c->d_light_zbuf, c->vN, c->vtmp, c->vtmp2, c->d_verts4,
+                  c->d_normals4};
+  c->d_verts4 = c->d_normals4 = nullptr;
   for (void* p : ptrs) if (p) cudaFree(p);
   c->ndc_cam = c->ndc_light = c->d_ndc_cam = c->d_ndc_light = c->light_zbuf = c->d_light_zbuf = c->vN = c->vtmp = c->vtmp2 = nullptr;
   c->bin_count = c->bin_start = c->bin_fill = c->bin_list = c->light_face = nullptr;
@@ -238,7 +244,7 @@ extern "C" void harp_ctx_destroy(harp_ctx* c) {
   free_scratch(c);
   void* ptrs[] = {c->faces, c->edges0, c->v0e_off, c->v0e_idx, c->vf_off, c->vf_idx, c->vn_off, c->vn_idx, c->edges,
                   c->nc_pairs, c->face_uvs, c->shapedirs, c->posedirs, c->v_template, c->weights, c->hands_mean,
-                  c->J_template, c->J_shapedirs, c->tips, c->counters};
+                  c->J_template, c->J_shapedirs, c->tips, c->counters, c->d_tex4, c->weightsT};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->prof) {
     for (auto& v : c->prof->ev) for (cudaEvent_t e : v) cudaEventDestroy(e);
@@ -260,8 +266,11 @@ extern "C" int harp_ctx_reserve(harp_ctx* c, int max_batch, int img_size) {
   c->bin_cap = (int64_t)c->F * 24;
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->ndc_cam, nv));
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->ndc_light, nv));
-  HARP_CHECK_CUDA(cudaMalloc((void**)&c->d_ndc_cam, nv));
-  HARP_CHECK_CUDA(cudaMalloc((void**)&c->d_ndc_light, nv));
+  size_t nv4 = (size_t)B * c->V * 4 * sizeof(float);
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->d_ndc_cam, nv4));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->d_ndc_light, nv4));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->d_verts4, nv4));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->d_normals4, nv4));
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->vN, nv));
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->vtmp, nv));
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->vtmp2, nv));

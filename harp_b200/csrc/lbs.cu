@@ -7,7 +7,7 @@
 
 namespace {
 
-constexpr int LBS_THREADS = 256;
+constexpr int LBS_THREADS = 512;
 constexpr int NJ = 16;
 
 // joint order of the returned 21 joints (manolayer.py:279) indexing [16 chain joints | 5 tips]
@@ -158,10 +158,11 @@ __global__ void __launch_bounds__(LBS_THREADS) lbs_mano_bwd_kernel(harp_ctx c, c
                                                                      float* __restrict__ d_trans) {
   __shared__ LbsShared s;
   __shared__ LbsBwdShared g;
-  extern __shared__ float dvp[];  // (V0*3) gradient w.r.t. v_posed
+  extern __shared__ float dyn[];
+  float* dvp = dyn;                 // (V0*3) gradient w.r.t. v_posed
+  float* dTs = dyn + c.V0 * 3;      // (12, V0) per-vertex dT = g (x) [v_posed;1], k-major (bank-conflict free)
   int b = blockIdx.x, t = threadIdx.x;
   lbs_prologue(c, pose48 + (size_t)b * 48, betas + (betas_shared ? 0 : (size_t)b * 10), s);
-  for (int i = t; i < NJ * 12; i += blockDim.x) (&g.dA[0][0])[i] = 0.f;
   const float* dj = d_joints ? d_joints + (size_t)b * 63 : nullptr;
   if (t < NJ * 3) (&g.djtr[0][0])[t] = 0.f;
   __syncthreads();
@@ -195,14 +196,8 @@ __global__ void __launch_bounds__(LBS_THREADS) lbs_mano_bwd_kernel(harp_ctx c, c
     // dT = g (x) [vp;1]  ->  dA_j += w_j dT
     float dT[12] = {gg.x * vp.x, gg.x * vp.y, gg.x * vp.z, gg.x, gg.y * vp.x, gg.y * vp.y, gg.y * vp.z, gg.y,
                     gg.z * vp.x, gg.z * vp.y, gg.z * vp.z, gg.z};
-    const float* w = c.weights + (size_t)v * NJ;
-    for (int j = 0; j < NJ; ++j) {
-      float wj = w[j];
-      if (wj != 0.f) {
 #pragma unroll
-        for (int k = 0; k < 12; ++k) atomicAdd(&g.dA[j][k], wj * dT[k]);
-      }
-    }
+    for (int k = 0; k < 12; ++k) dTs[k * c.V0 + v] = dT[k];
   }
   // d_trans = sum_v g_v + sum of chain-joint grads (tips were folded into g_v)
   float tx = block_sum(tsum.x, g.red), ty = block_sum(tsum.y, g.red), tz = block_sum(tsum.z, g.red);
@@ -211,8 +206,19 @@ __global__ void __launch_bounds__(LBS_THREADS) lbs_mano_bwd_kernel(harp_ctx c, c
     for (int j = 0; j < NJ; ++j) { tx += g.djtr[j][0]; ty += g.djtr[j][1]; tz += g.djtr[j][2]; }
     if (d_trans) { d_trans[b * 3] = tx; d_trans[b * 3 + 1] = ty; d_trans[b * 3 + 2] = tz; }
   }
-  // d pose_map (135) and the direct d beta (10): transposed-table mat-vec, one warp per output
   int warp = t >> 5, lane = t & 31, nw = blockDim.x >> 5, n3 = c.V0 * 3;
+  // dA (16x12) = W^T (16 x V0) . dT (V0 x 12): one warp per output, lanes over vertices (no shared-memory float atomics:
+  // those compile to CAS spin loops)
+  for (int o = warp; o < NJ * 12; o += nw) {
+    int j = o / 12, k = o % 12;
+    const float* wrow = c.weightsT + (size_t)j * c.V0;
+    const float* drow = dTs + k * c.V0;
+    float a = 0.f;
+    for (int v = lane; v < c.V0; v += 32) a += wrow[v] * drow[v];
+    a = warp_sum(a);
+    if (lane == 0) g.dA[j][k] = a;
+  }
+  // d pose_map (135) and the direct d beta (10): transposed-table mat-vec, one warp per output
   for (int o = warp; o < 145; o += nw) {
     const float* row = o < 135 ? c.posedirs + (size_t)o * n3 : c.shapedirs + (size_t)(o - 135) * n3;
     float a = 0.f;
@@ -302,7 +308,12 @@ extern "C" int harp_lbs_mano_bwd(harp_ctx* c, int B, const float* pose48, const 
   (void)trans;
   HARP_REQUIRE(c && B > 0 && pose48 && betas && d_verts0 && d_pose48 && d_betas, HARP_ERR_INVALID, "harp_lbs_mano_bwd: null argument");
   HARP_REQUIRE(c->has_model, HARP_ERR_NO_MODEL, "harp_lbs_mano_bwd: ctx has no MANO model");
-  size_t dyn = (size_t)c->V0 * 3 * sizeof(float);
+  size_t dyn = (size_t)c->V0 * 15 * sizeof(float);
+  static size_t configured = 0;
+  if (dyn > configured) {
+    HARP_CHECK_CUDA(cudaFuncSetAttribute(lbs_mano_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    configured = dyn;
+  }
   lbs_mano_bwd_kernel<<<B, LBS_THREADS, dyn, (cudaStream_t)stream>>>(*c, pose48, betas, betas_shared, d_verts0, d_joints,
                                                                      d_pose48, d_betas, d_trans);
   HARP_LAUNCH_CHECK();

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(TPB) project_kernel(int B, int V, const float*
   st3(ndc + (size_t)idx * 3, mk3((focal * X / Z) / half_s, (focal * Y / Z) / half_s, Z));
 }
 
-// backward of project_kernel: d_ndc (B,V,3) -> d_verts += , d_R += , d_T +=
+// backward of project_kernel: d_ndc (B,V,4: xyz + pad) -> d_verts += , d_R += , d_T +=
 __global__ void __launch_bounds__(TPB) project_bwd_kernel(int B, int V, const float* __restrict__ verts, const float* __restrict__ R,
                                                            const float* __restrict__ T, float focal, float half_s,
                                                            const float* __restrict__ d_ndc, float* __restrict__ d_verts,
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(TPB) project_bwd_kernel(int B, int V, const fl
   for (int i = 0; i < 12; ++i) acc[i] = 0.f;
   if (v < V) {
     size_t idx = (size_t)b * V + v;
-    f3 g = ld3(d_ndc + idx * 3);
+    f3 g = ld3(d_ndc + idx * 4);
     if (g.x != 0.f || g.y != 0.f || g.z != 0.f) {
       f3 p = ld3(verts + idx * 3);
       float X = p.x * r[0] + p.y * r[3] + p.z * r[6] + t[0];
@@ -157,6 +157,33 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(harp_ctx c, int tiles, c
 
 // ---- soft silhouette -------------------------------------------------------------------------------------------------
 // MODE 0 forward; 1 backward with upstream g_alpha; 2 fused L1(target, alpha) loss (forward + backward in one pass).
+// The +-1/3 px band pairs that need the full distance computation are a few percent of all (pixel, face) candidates but
+// sit in nearly every face a warp visits, so evaluating them in the pixel loop leaves ~6 of 32 lanes active.  Instead the
+// convergent classification pass queues them per tile in shared memory and all 64 threads drain the queue.
+constexpr int QCAP = 512;
+
+__device__ __forceinline__ void sil_pair_gradient(const FaceRec& f, float px, float py, float sd, int edge, float t, float g,
+                                                  float prod, float sigma, float* d_ndc) {
+  float prob = 1.f / (1.f + expf(fdiv(sd, sigma)));
+  // alpha = 1 - prod_k(1-p_k):  d alpha / d sd_k = -(prod) * p_k / sigma   (no exact-zero factor on this path)
+  float gsd = g * (-prod * prob / sigma);
+  float gd = sd < 0.f ? -gsd : gsd;  // w.r.t. the unsigned squared distance (inside <=> signed distance negative)
+  if (gd == 0.f) return;
+  float ax, ay, bx, by; int va, vb;
+  if (edge == 0) { ax = f.x0; ay = f.y0; bx = f.x1; by = f.y1; va = f.v0; vb = f.v1; }
+  else if (edge == 1) { ax = f.x0; ay = f.y0; bx = f.x2; by = f.y2; va = f.v0; vb = f.v2; }
+  else { ax = f.x1; ay = f.y1; bx = f.x2; by = f.y2; va = f.v1; vb = f.v2; }
+  if (t < 0.f) {  // degenerate edge: dist = |p - b|^2
+    atomicAdd(reinterpret_cast<float2*>(d_ndc + (size_t)vb * 4), make_float2(gd * 2.f * (bx - px), gd * 2.f * (by - py)));
+    return;
+  }
+  // PointLineDistanceBackward: q = a + t (b - a), d = q - p ; grad_a = g (1-t) 2 d ; grad_b = g t 2 d
+  float qx = ax + t * (bx - ax), qy = ay + t * (by - ay);
+  float dx = 2.f * gd * (qx - px), dy = 2.f * gd * (qy - py);
+  atomicAdd(reinterpret_cast<float2*>(d_ndc + (size_t)va * 4), make_float2((1.f - t) * dx, (1.f - t) * dy));
+  atomicAdd(reinterpret_cast<float2*>(d_ndc + (size_t)vb * 4), make_float2(t * dx, t * dy));
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(HARP_TILE* HARP_TILE) sil_kernel(harp_ctx c, int S, float sigma, float blur, float radius,
                                                                    const float* __restrict__ ndc_all,
@@ -165,12 +192,17 @@ __global__ void __launch_bounds__(HARP_TILE* HARP_TILE) sil_kernel(harp_ctx c, i
                                                                    const int32_t* __restrict__ bin_list, float* __restrict__ alpha,
                                                                    const float* __restrict__ gin, float gscale, float inv_n,
                                                                    float* __restrict__ loss, float* __restrict__ d_ndc_all) {
+  constexpr int NT = HARP_TILE * HARP_TILE;
   __shared__ FaceRec faces[CHUNK];
   __shared__ float red[32];
-  __shared__ int any_bwd;
-  int b = blockIdx.z, tw = S / HARP_TILE;
+  __shared__ unsigned char q_pix[QCAP], q_face[QCAP], q_edge[QCAP];  // q_edge == 255: pair did not pass
+  __shared__ float q_sd[QCAP], q_t[QCAP];
+  __shared__ int q_n, any_bwd;
+  __shared__ float s_g[NT], s_prod[NT];
+  __shared__ unsigned char s_need[NT];
+  int b = blockIdx.z, tw = S / HARP_TILE, tid = threadIdx.x;
   int tile = blockIdx.y * tw + blockIdx.x;
-  int lx = threadIdx.x % HARP_TILE, ly = threadIdx.x / HARP_TILE;
+  int lx = tid % HARP_TILE, ly = tid / HARP_TILE;
   int col = blockIdx.x * HARP_TILE + lx, row = blockIdx.y * HARP_TILE + ly;
   size_t pix = ((size_t)b * S + row) * S + col;
   size_t tglob = (size_t)b * tw * tw + tile;
@@ -182,22 +214,59 @@ __global__ void __launch_bounds__(HARP_TILE* HARP_TILE) sil_kernel(harp_ctx c, i
   float px = pix_to_ndc(col, S), py = pix_to_ndc(row, S);
   float prod = 1.f;
   int nzero = 0, npass = 0;
-  if (threadIdx.x == 0) any_bwd = 0;
+  bool q_overflow = false;
+  const float sat = 17.5f * sigma;
+  if (tid == 0) { any_bwd = 0; q_n = 0; }
   for (int base = 0; base < n; base += CHUNK) {
     int m = min(CHUNK, n - base);
     __syncthreads();
-    if (threadIdx.x < m) load_face(c, ndc, list[base + threadIdx.x], radius, faces[threadIdx.x]);
+    if (tid < m) load_face(c, ndc, list[base + tid], radius, faces[tid]);
+    if (tid == 0) q_n = 0;
     __syncthreads();
-    for (int i = 0; i < m; ++i) {
-      PairEval e;
-      eval_pair<true, true>(faces[i], px, py, blur, e);
-      if (!e.pass) continue;
-      ++npass;
-      float sd = e.inside ? -e.dist : e.dist;
-      float prob = 1.f / (1.f + expf(fdiv(sd, sigma)));  // sigmoid(-sd/sigma)
-      float om = 1.f - prob;
-      if (om == 0.f) ++nzero; else prod *= om;
+    // A: convergent classification; a pixel with one exactly-zero factor is final (alpha = 1, zero gradient)
+    if (nzero == 0) {
+      for (int i = 0; i < m; ++i) {
+        int cls = classify_pair<true>(faces[i], px, py, blur, sat);
+        if (cls == PAIR_REJECT) continue;
+        if (cls == PAIR_SATURATED) { ++npass; ++nzero; break; }
+        int slot = atomicAdd(&q_n, 1);
+        if (slot < QCAP) {
+          q_pix[slot] = (unsigned char)tid; q_face[slot] = (unsigned char)i;
+        } else {  // queue full (never seen at the reference's scales): evaluate in place
+          q_overflow = true;
+          PairEval e;
+          eval_pair_full<true, true>(faces[i], px, py, blur, e);
+          if (!e.pass) continue;
+          ++npass;
+          float om = 1.f - 1.f / (1.f + expf(fdiv(e.inside ? -e.dist : e.dist, sigma)));
+          if (om == 0.f) { ++nzero; break; }
+          prod *= om;
+        }
+      }
     }
+    __syncthreads();
+    // B: drain the queue with every thread busy
+    int qn = min(q_n, QCAP);
+    for (int s = tid; s < qn; s += NT) {
+      int p = q_pix[s];
+      float ppx = pix_to_ndc(blockIdx.x * HARP_TILE + (p % HARP_TILE), S), ppy = pix_to_ndc(blockIdx.y * HARP_TILE + (p / HARP_TILE), S);
+      PairEval e;
+      eval_pair_full<true, true>(faces[q_face[s]], ppx, ppy, blur, e);
+      if (e.pass) { q_sd[s] = e.inside ? -e.dist : e.dist; q_edge[s] = (unsigned char)e.edge; q_t[s] = e.t; }
+      else q_edge[s] = 255;
+    }
+    __syncthreads();
+    // C: every pixel folds its own results in queue (= face list) order
+    if (nzero == 0) {
+      for (int s = 0; s < qn; ++s) {
+        if (q_pix[s] != tid || q_edge[s] == 255) continue;
+        ++npass;
+        float om = 1.f - 1.f / (1.f + expf(fdiv(q_sd[s], sigma)));  // 1 - sigmoid(-sd/sigma)
+        if (om == 0.f) { ++nzero; break; }
+        prod *= om;
+      }
+    }
+    if (__syncthreads_and(nzero > 0)) break;  // whole tile saturated
   }
   float a = nzero > 0 ? 1.f : 1.f - prod;
   if (npass > 50) atomicAdd(c.counters, 1ULL);
@@ -211,53 +280,59 @@ __global__ void __launch_bounds__(HARP_TILE* HARP_TILE) sil_kernel(harp_ctx c, i
     float diff = a - tgt;
     g = diff > 0.f ? gscale : (diff < 0.f ? -gscale : 0.f);
     float s = block_sum(fabsf(diff), red);
-    if (threadIdx.x == 0 && s != 0.f) atomicAdd(loss, s * inv_n);
+    if (tid == 0 && s != 0.f) atomicAdd(loss, s * inv_n);
   }
   bool need = (g != 0.f) && nzero == 0 && prod > 0.f && npass > 0;
   if (need) any_bwd = 1;
-  __syncthreads();
+  s_g[tid] = g; s_prod[tid] = prod; s_need[tid] = need ? 1 : 0;
+  int any_overflow = __syncthreads_or(q_overflow ? 1 : 0);
   if (!any_bwd) return;
-  float* d_ndc = d_ndc_all + (size_t)b * c.V * 3;
-  for (int base = 0; base < n; base += CHUNK) {
+  float* d_ndc = d_ndc_all + (size_t)b * c.V * 4;
+  if (n <= CHUNK && !any_overflow) {
+    // single-chunk tile (the common case): the queue and the staged faces of pass 1 are still valid
+    int qn = min(q_n, QCAP);
+    for (int s = tid; s < qn; s += NT) {
+      int p = q_pix[s];
+      if (!s_need[p] || q_edge[s] == 255) continue;
+      float ppx = pix_to_ndc(blockIdx.x * HARP_TILE + (p % HARP_TILE), S), ppy = pix_to_ndc(blockIdx.y * HARP_TILE + (p / HARP_TILE), S);
+      sil_pair_gradient(faces[q_face[s]], ppx, ppy, q_sd[s], q_edge[s], q_t[s], s_g[p], s_prod[p], sigma, d_ndc);
+    }
+    return;
+  }
+  for (int base = 0; base < n; base += CHUNK) {  // generic path: re-stage every chunk, pixel-parallel
     int m = min(CHUNK, n - base);
     __syncthreads();
-    if (threadIdx.x < m) load_face(c, ndc, list[base + threadIdx.x], radius, faces[threadIdx.x]);
+    if (tid < m) load_face(c, ndc, list[base + tid], radius, faces[tid]);
     __syncthreads();
     if (!need) continue;
     for (int i = 0; i < m; ++i) {
-      const FaceRec& f = faces[i];
       PairEval e;
-      eval_pair<true, true>(f, px, py, blur, e);
-      if (!e.pass) continue;
-      float sd = e.inside ? -e.dist : e.dist;
-      float prob = 1.f / (1.f + expf(fdiv(sd, sigma)));
-      // alpha = 1 - prod_k(1-p_k):  d alpha / d sd_k = -(prod) * p_k / sigma   (no exact-zero factor on this path)
-      float gsd = g * (-prod * prob / sigma);
-      float gd = e.inside ? -gsd : gsd;  // w.r.t. the unsigned squared distance
-      if (gd == 0.f) continue;
-      float ax, ay, bx, by; int va, vb;
-      if (e.edge == 0) { ax = f.x0; ay = f.y0; bx = f.x1; by = f.y1; va = f.v0; vb = f.v1; }
-      else if (e.edge == 1) { ax = f.x0; ay = f.y0; bx = f.x2; by = f.y2; va = f.v0; vb = f.v2; }
-      else { ax = f.x1; ay = f.y1; bx = f.x2; by = f.y2; va = f.v1; vb = f.v2; }
-      if (e.t < 0.f) {  // degenerate edge: dist = |p - b|^2
-        atomicAdd(d_ndc + (size_t)vb * 3 + 0, gd * 2.f * (bx - px));
-        atomicAdd(d_ndc + (size_t)vb * 3 + 1, gd * 2.f * (by - py));
-        continue;
-      }
-      // PointLineDistanceBackward: q = a + t (b - a), d = q - p ; grad_a = g (1-t) 2 d ; grad_b = g t 2 d
-      float qx = ax + e.t * (bx - ax), qy = ay + e.t * (by - ay);
-      float dx = 2.f * gd * (qx - px), dy = 2.f * gd * (qy - py);
-      atomicAdd(d_ndc + (size_t)va * 3 + 0, (1.f - e.t) * dx);
-      atomicAdd(d_ndc + (size_t)va * 3 + 1, (1.f - e.t) * dy);
-      atomicAdd(d_ndc + (size_t)vb * 3 + 0, e.t * dx);
-      atomicAdd(d_ndc + (size_t)vb * 3 + 1, e.t * dy);
+      eval_pair<true, true>(faces[i], px, py, blur, sat, e);
+      if (!e.pass || e.saturated) continue;
+      sil_pair_gradient(faces[i], px, py, e.inside ? -e.dist : e.dist, e.edge, e.t, g, prod, sigma, d_ndc);
     }
+  }
+}
+
+// dst (n,3) += src (n,4).xyz
+__global__ void __launch_bounds__(TPB) fold4_kernel(size_t n, const float4* __restrict__ src, float* __restrict__ dst) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 v = src[i];
+  if (v.x != 0.f || v.y != 0.f || v.z != 0.f) {
+    dst[i * 3] += v.x; dst[i * 3 + 1] += v.y; dst[i * 3 + 2] += v.z;
   }
 }
 
 inline int nblk(size_t n) { return (int)((n + TPB - 1) / TPB); }
 
 }  // namespace
+
+int harp_fold4(size_t n, const float* src4, float* dst3, cudaStream_t st) {
+  fold4_kernel<<<nblk(n), TPB, 0, st>>>(n, reinterpret_cast<const float4*>(src4), dst3);
+  HARP_LAUNCH_CHECK();
+  return HARP_OK;
+}
 
 // Build the bin lists of one view (0 = camera, 1 = light) for B frames from already-projected verts.
 int harp_build_bins(harp_ctx* c, int view, int B, int S, float radius, const float* ndc, cudaStream_t st) {
@@ -306,7 +381,7 @@ extern "C" int harp_silhouette(harp_ctx* c, int mode, int B, int S, float focal,
   int rc;
   if ((rc = harp_project(c, B, S, focal, verts, R, T, c->ndc_cam, st)) != HARP_OK) return rc;
   if ((rc = harp_build_bins(c, 0, B, S, radius, c->ndc_cam, st)) != HARP_OK) return rc;
-  if (mode != 0) HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_cam, 0, (size_t)B * c->V * 3 * sizeof(float), st));
+  if (mode != 0) HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_cam, 0, (size_t)B * c->V * 4 * sizeof(float), st));
   dim3 grid(S / HARP_TILE, S / HARP_TILE, B);
   float inv_n = 1.f / ((float)B * (float)S * (float)S);
   float gscale = weight * inv_n;

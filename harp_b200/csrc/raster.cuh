@@ -48,11 +48,13 @@ struct FaceRec {  // staged in shared memory, one per face of the current chunk 
   float x0, y0, z0, x1, y1, z1, x2, y2, z2;
   float xmin, xmax, ymin, ymax;  // bbox inflated by sqrt(blur)
   float area;                    // EdgeFunction(v2, v0, v1) + kEpsilon
+  float l12, l20, l01;           // squared lengths of the edges opposite v0, v1, v2
+  float zmin;
   int v0, v1, v2, fid;
 };
 
 struct PairEval {
-  bool pass, inside;
+  bool pass, inside, saturated;
   float pz, dist;      // dist = unsigned squared distance to the triangle boundary
   float b0, b1, b2;    // perspective-correct (and, for the silhouette, clipped) barycentrics
   float w0, w1, w2;    // screen-space barycentrics
@@ -60,11 +62,42 @@ struct PairEval {
   float t;             // clamped parameter on that edge (-1: degenerate edge)
 };
 
-// One (pixel, face) pair.  CLIP: clip_barycentric_coords (silhouette); blur: blur_radius (squared NDC).
+// One (pixel, face) pair, in two stages.
+//
+// classify_pair — cheap, fully convergent (exactness argued in DESIGN.md section 4): with all three view depths > 0 the sign
+// of every perspective-correct barycentric equals the sign of e_i / area, so strict-inside is decided by the edge functions
+// alone.  A point's distance to the triangle boundary is >= its distance to any edge LINE, |e_i| / |edge_i|, hence
+//   * inside and min_i e_i^2/l_i >= sat  (sat = 17.5 sigma; 1 - sigmoid(x) == 0 in fp32 for x >= 16.64)
+//       => the silhouette factor is exactly 0: PAIR_SATURATED, no distance computation needed;
+//   * outside and e_i^2/l_i >= 1.001 blur for a violated edge => dist >= blur_radius => PyTorch3D skips the pair.
+// eval_pair_full — everything in between, operation by operation as PyTorch3D's CheckPixelInsideFace.
+enum { PAIR_REJECT = 0, PAIR_SATURATED = 1, PAIR_FULL = 2 };
+
+template <bool NEED_DIST>
+__device__ __forceinline__ int classify_pair(const FaceRec& f, float px, float py, float blur, float sat) {
+  if (px > f.xmax || px < f.xmin || py > f.ymax || py < f.ymin) return PAIR_REJECT;
+  if (f.zmin > 0.f) {
+    float e0 = edge_fn(px, py, f.x1, f.y1, f.x2, f.y2);
+    float e1 = edge_fn(px, py, f.x2, f.y2, f.x0, f.y0);
+    float e2 = edge_fn(px, py, f.x0, f.y0, f.x1, f.y1);
+    bool pos = f.area > 0.f;
+    bool i0 = pos ? e0 > 0.f : e0 < 0.f, i1 = pos ? e1 > 0.f : e1 < 0.f, i2 = pos ? e2 > 0.f : e2 < 0.f;
+    if (i0 && i1 && i2) {
+      if (NEED_DIST && e0 * e0 >= sat * f.l12 && e1 * e1 >= sat * f.l20 && e2 * e2 >= sat * f.l01) return PAIR_SATURATED;
+    } else {
+      if (!NEED_DIST) return PAIR_REJECT;
+      float far = 1.001f * blur;
+      if ((!i0 && e0 * e0 >= far * f.l12) || (!i1 && e1 * e1 >= far * f.l20) || (!i2 && e2 * e2 >= far * f.l01)) return PAIR_REJECT;
+    }
+  }
+  return PAIR_FULL;
+}
+
+// CLIP: clip_barycentric_coords (silhouette); blur: blur_radius (squared NDC).  The bounding-box test is classify_pair's.
 template <bool CLIP, bool NEED_DIST>
-__device__ __forceinline__ void eval_pair(const FaceRec& f, float px, float py, float blur, PairEval& r) {
+__device__ __forceinline__ void eval_pair_full(const FaceRec& f, float px, float py, float blur, PairEval& r) {
   r.pass = false;
-  if (px > f.xmax || px < f.xmin || py > f.ymax || py < f.ymin) return;
+  r.saturated = false;
   float w0 = fdiv(edge_fn(px, py, f.x1, f.y1, f.x2, f.y2), f.area);
   float w1 = fdiv(edge_fn(px, py, f.x2, f.y2, f.x0, f.y0), f.area);
   float w2 = fdiv(edge_fn(px, py, f.x0, f.y0, f.x1, f.y1), f.area);
@@ -102,6 +135,16 @@ __device__ __forceinline__ void eval_pair(const FaceRec& f, float px, float py, 
   r.pass = true;
 }
 
+template <bool CLIP, bool NEED_DIST>
+__device__ __forceinline__ void eval_pair(const FaceRec& f, float px, float py, float blur, float sat, PairEval& r) {
+  r.pass = false;
+  r.saturated = false;
+  int cls = classify_pair<NEED_DIST>(f, px, py, blur, sat);
+  if (cls == PAIR_REJECT) return;
+  if (cls == PAIR_SATURATED) { r.pass = true; r.inside = true; r.saturated = true; return; }
+  eval_pair_full<CLIP, NEED_DIST>(f, px, py, blur, r);
+}
+
 // Load face `fid` of frame-local projected verts into a FaceRec.  Returns false for faces PyTorch3D skips outright.
 __device__ __forceinline__ void load_face(const harp_ctx& c, const float* ndc, int fid, float radius, FaceRec& f) {
   const int32_t* fv = c.faces + (size_t)fid * 3;
@@ -115,4 +158,8 @@ __device__ __forceinline__ void load_face(const harp_ctx& c, const float* ndc, i
   f.ymin = fsub(fminf(fminf(f.y0, f.y1), f.y2), radius);
   f.ymax = fadd(fmaxf(fmaxf(f.y0, f.y1), f.y2), radius);
   f.area = fadd(edge_fn(f.x2, f.y2, f.x0, f.y0, f.x1, f.y1), HARP_K_EPS);
+  f.l12 = (f.x2 - f.x1) * (f.x2 - f.x1) + (f.y2 - f.y1) * (f.y2 - f.y1);
+  f.l20 = (f.x0 - f.x2) * (f.x0 - f.x2) + (f.y0 - f.y2) * (f.y0 - f.y2);
+  f.l01 = (f.x1 - f.x0) * (f.x1 - f.x0) + (f.y1 - f.y0) * (f.y1 - f.y0);
+  f.zmin = fminf(fminf(f.z0, f.z1), f.z2);
 }

@@ -11,6 +11,7 @@ int harp_project(harp_ctx* c, int B, int S, float focal, const float* verts, con
                  cudaStream_t st);
 int harp_project_bwd(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R, const float* T,
                      const float* d_ndc, float* d_verts, float* d_R, float* d_T, cudaStream_t st);
+int harp_fold4(size_t n, const float* src4, float* dst3, cudaStream_t st);
 
 namespace {
 
@@ -47,7 +48,7 @@ __device__ __forceinline__ void nearest_face(const harp_ctx& c, const float* ndc
     __syncthreads();
     for (int i = 0; i < m; ++i) {
       PairEval e;
-      eval_pair<false, false>(faces[i], px, py, 0.f, e);
+      eval_pair<false, false>(faces[i], px, py, 0.f, 0.f, e);
       if (!e.pass) continue;
       int fid = faces[i].fid;
       if (e.pz < h.pz || (e.pz == h.pz && fid < h.fid)) {
@@ -106,10 +107,9 @@ __device__ __forceinline__ void bary_backward(const float* ndc, int v0, int v1, 
   float gy1 = ge0 * (x2 - px) + ge2 * (px - x0) + gA * (x2 - x0);
   float gx2 = ge0 * (y1 - py) + ge1 * (py - y0) + gA * (y1 - y0);
   float gy2 = ge0 * (px - x1) + ge1 * (x0 - px) + gA * (x0 - x1);
-  float* D0 = d_ndc + (size_t)v0 * 3; float* D1 = d_ndc + (size_t)v1 * 3; float* D2 = d_ndc + (size_t)v2 * 3;
-  atomicAdd(D0, gx0); atomicAdd(D0 + 1, gy0); atomicAdd(D0 + 2, gz0);
-  atomicAdd(D1, gx1); atomicAdd(D1 + 1, gy1); atomicAdd(D1 + 2, gz1);
-  atomicAdd(D2, gx2); atomicAdd(D2 + 1, gy2); atomicAdd(D2 + 2, gz2);
+  atomic_add4(d_ndc + (size_t)v0 * 4, gx0, gy0, gz0);
+  atomic_add4(d_ndc + (size_t)v1 * 4, gx1, gy1, gz1);
+  atomic_add4(d_ndc + (size_t)v2 * 4, gx2, gy2, gz2);
 }
 
 // backward of the light-view depth buffer: zbuf = sum_i b_i z_i at the stored face
@@ -129,12 +129,12 @@ __global__ void __launch_bounds__(256) light_depth_bwd_kernel(harp_ctx c, int B,
   load_face(c, ndc, fid, 0.f, f);
   float px = pix_to_ndc(col, S), py = pix_to_ndc(row, S);
   PairEval e;
-  eval_pair<false, false>(f, px, py, 0.f, e);
+  eval_pair<false, false>(f, px, py, 0.f, 0.f, e);
   if (!e.pass) return;
   Hit h; h.fid = fid; h.pz = e.pz; h.b0 = e.b0; h.b1 = e.b1; h.b2 = e.b2; h.w0 = e.w0; h.w1 = e.w1; h.w2 = e.w2;
   float gb[3] = {g * f.z0, g * f.z1, g * f.z2};
   float gz[3] = {g * e.b0, g * e.b1, g * e.b2};
-  bary_backward(ndc, f.v0, f.v1, f.v2, px, py, h, gb, gz, d_ndc_all + (size_t)b * c.V * 3);
+  bary_backward(ndc, f.v0, f.v1, f.v2, px, py, h, gb, gz, d_ndc_all + (size_t)b * c.V * 4);
 }
 
 // ---- texture fetch: F.grid_sample(bilinear, align_corners=True, border) on the H-flipped map ------------
@@ -175,7 +175,7 @@ __device__ __forceinline__ f3 normalize_bwd_eps(f3 x, f3 gy, float eps) {
 
 // MODE 0 forward; 1 backward with upstream g_rgb; 2 fused photometric L1 on the eroded mask
 template <int MODE>
-__global__ void __launch_bounds__(NT) shade_kernel(harp_ctx c, ShadeArgs a) {
+__global__ void __launch_bounds__(NT, (MODE == 0 ? 16 : 10)) shade_kernel(harp_ctx c, ShadeArgs a) {
   __shared__ FaceRec faces[CHUNK];
   __shared__ float red[32];
   int b = blockIdx.z, S = a.S, tw = S / HARP_TILE;
@@ -339,8 +339,9 @@ __global__ void __launch_bounds__(NT) shade_kernel(harp_ctx c, ShadeArgs a) {
         mraw[k] = ld3(a.normal_map + (size_t)tp.idx[k] * 3);
         m4[k] = normalize12(mraw[k]);
         if (tp.w[k] != 0.f) {
-          if (a.d_texture) atomic_add3(a.d_texture + (size_t)tp.idx[k] * 3, tp.w[k] * g_tex);
-          if (a.d_normal_map) atomic_add3(a.d_normal_map + (size_t)tp.idx[k] * 3, normalize_bwd_eps(mraw[k], tp.w[k] * g_m, 1e-12f));
+          f3 gt = tp.w[k] * g_tex, gm = normalize_bwd_eps(mraw[k], tp.w[k] * g_m, 1e-12f);
+          atomic_add4(a.d_texture + (size_t)tp.idx[k] * 4, gt.x, gt.y, gt.z);
+          atomic_add4(a.d_normal_map + (size_t)tp.idx[k] * 4, gm.x, gm.y, gm.z);
         }
       }
       // d out / d ix = (ne - nw)(1-fy) + (se - sw) fy ;  d out / d iy = (sw - nw)(1-fx) + (se - ne) fx
@@ -355,12 +356,16 @@ __global__ void __launch_bounds__(NT) shade_kernel(harp_ctx c, ShadeArgs a) {
     float gb[3] = {dot(P0, gP) + dot(N0, gN) + uvx[0] * g_u_tex + uvy[0] * g_v_tex,
                    dot(P1, gP) + dot(N1, gN) + uvx[1] * g_u_tex + uvy[1] * g_v_tex,
                    dot(P2, gP) + dot(N2, gN) + uvx[2] * g_u_tex + uvy[2] * g_v_tex};
-    float* dvb = a.d_verts + (size_t)b * c.V * 3;
-    float* dnb = a.d_normals + (size_t)b * c.V * 3;
-    atomic_add3(dvb + (size_t)v0 * 3, h.b0 * gP); atomic_add3(dvb + (size_t)v1 * 3, h.b1 * gP); atomic_add3(dvb + (size_t)v2 * 3, h.b2 * gP);
-    atomic_add3(dnb + (size_t)v0 * 3, h.b0 * gN); atomic_add3(dnb + (size_t)v1 * 3, h.b1 * gN); atomic_add3(dnb + (size_t)v2 * 3, h.b2 * gN);
+    float* dvb = a.d_verts + (size_t)b * c.V * 4;   // padded (B,V,4) accumulators, folded after the kernel
+    float* dnb = a.d_normals + (size_t)b * c.V * 4;
+    atomic_add4(dvb + (size_t)v0 * 4, h.b0 * gP.x, h.b0 * gP.y, h.b0 * gP.z);
+    atomic_add4(dvb + (size_t)v1 * 4, h.b1 * gP.x, h.b1 * gP.y, h.b1 * gP.z);
+    atomic_add4(dvb + (size_t)v2 * 4, h.b2 * gP.x, h.b2 * gP.y, h.b2 * gP.z);
+    atomic_add4(dnb + (size_t)v0 * 4, h.b0 * gN.x, h.b0 * gN.y, h.b0 * gN.z);
+    atomic_add4(dnb + (size_t)v1 * 4, h.b1 * gN.x, h.b1 * gN.y, h.b1 * gN.z);
+    atomic_add4(dnb + (size_t)v2 * 4, h.b2 * gN.x, h.b2 * gN.y, h.b2 * gN.z);
     float gz[3] = {0.f, 0.f, 0.f};
-    bary_backward(ndc, v0, v1, v2, px, py, h, gb, gz, a.d_ndc_cam + (size_t)b * c.V * 3);
+    bary_backward(ndc, v0, v1, v2, px, py, h, gb, gz, a.d_ndc_cam + (size_t)b * c.V * 4);
   }
   // per-frame scalars: warp-reduce, one atomic per warp
   int any = __syncthreads_or(active ? 1 : 0);
@@ -397,7 +402,7 @@ extern "C" int harp_shade(harp_ctx* c, int mode, int B, int S, float focal, int 
   HARP_REQUIRE(mode != 2 || (mask && loss), HARP_ERR_INVALID, "harp_shade: mask and loss required in fused mode");
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  size_t nv = (size_t)B * c->V * 3 * sizeof(float), npx = (size_t)B * S * S;
+  size_t npx = (size_t)B * S * S;
   if ((rc = harp_project(c, B, S, focal, verts, cam_R, cam_T, c->ndc_cam, st)) != HARP_OK) return rc;
   if ((rc = harp_build_bins(c, 0, B, S, 0.f, c->ndc_cam, st)) != HARP_OK) return rc;
   dim3 grid(S / HARP_TILE, S / HARP_TILE, B);
@@ -417,15 +422,26 @@ extern "C" int harp_shade(harp_ctx* c, int mode, int B, int S, float focal, int 
   a.light_T = light_T ? light_T : cam_T; a.light_pos = light_pos; a.amb = amb; a.texture = texture; a.normal_map = normal_map;
   a.light_zbuf = c->light_zbuf; a.bin_count = c->bin_count; a.bin_start = c->bin_start; a.bin_list = c->bin_list;
   a.rgb = rgb; a.gin = gin; a.mask = mask; a.loss = loss;
+  size_t ntex = (size_t)texH * texW;
   if (mode != 0) {
-    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_cam, 0, nv, st));
+    if ((int64_t)ntex > c->texcap) {  // one-time (re)allocation of the padded texel accumulators
+      if (c->d_tex4) cudaFree(c->d_tex4);
+      c->d_tex4 = nullptr; c->texcap = 0;
+      HARP_CHECK_CUDA(cudaMalloc((void**)&c->d_tex4, 2 * ntex * 4 * sizeof(float)));
+      c->texcap = (int64_t)ntex;
+    }
+    size_t nv4 = (size_t)B * c->V * 4 * sizeof(float);
+    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_cam, 0, nv4, st));
+    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_verts4, 0, nv4, st));
+    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_normals4, 0, nv4, st));
+    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_tex4, 0, 2 * ntex * 4 * sizeof(float), st));
     if (self_shadow) {
-      HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_light, 0, nv, st));
+      HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_light, 0, nv4, st));
       HARP_CHECK_CUDA(cudaMemsetAsync(c->d_light_zbuf, 0, npx * sizeof(float), st));
     }
-    a.d_ndc_cam = c->d_ndc_cam; a.d_verts = grads->d_verts; a.d_normals = grads->d_normals;
+    a.d_ndc_cam = c->d_ndc_cam; a.d_verts = c->d_verts4; a.d_normals = c->d_normals4;
     a.d_light_R = grads->d_light_R; a.d_light_T = grads->d_light_T; a.d_light_pos = grads->d_light_pos;
-    a.d_amb = grads->d_amb; a.d_texture = grads->d_texture; a.d_normal_map = grads->d_normal_map;
+    a.d_amb = grads->d_amb; a.d_texture = c->d_tex4; a.d_normal_map = c->d_tex4 + ntex * 4;
     a.d_light_zbuf = c->d_light_zbuf;
   }
   harp_prof_begin(c, 1, st);
@@ -435,6 +451,10 @@ extern "C" int harp_shade(harp_ctx* c, int mode, int B, int S, float focal, int 
   harp_prof_end(c, 1, st);
   HARP_LAUNCH_CHECK();
   if (mode != 0) {
+    if ((rc = harp_fold4((size_t)B * c->V, c->d_verts4, grads->d_verts, st)) != HARP_OK) return rc;
+    if ((rc = harp_fold4((size_t)B * c->V, c->d_normals4, grads->d_normals, st)) != HARP_OK) return rc;
+    if (grads->d_texture && (rc = harp_fold4(ntex, c->d_tex4, grads->d_texture, st)) != HARP_OK) return rc;
+    if (grads->d_normal_map && (rc = harp_fold4(ntex, c->d_tex4 + ntex * 4, grads->d_normal_map, st)) != HARP_OK) return rc;
     if (self_shadow) {
       light_depth_bwd_kernel<<<(int)((npx + 255) / 256), 256, 0, st>>>(*c, B, S, c->ndc_light, c->light_face, c->d_light_zbuf,
                                                                        c->d_ndc_light);

@@ -1,0 +1,66 @@
+"""CPU: the C-ABI shared library loads without a GPU and exports exactly the symbols include/harp_b200.h declares;
+the product has no CPU / oracle fallback."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    from harp_b200 import build
+    return build.build()
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "harp_b200.h")).read()
+    return sorted(set(re.findall(r"HARP_API[^;(]*?\b(harp_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(libpath):
+    L = ctypes.CDLL(libpath)
+    declared = _header_symbols()
+    assert len(declared) >= 19
+    for s in declared:
+        assert hasattr(L, s), s
+    out = subprocess.run(["nm", "-D", "--defined-only", libpath], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (harp_\w+)", out)))
+    assert exported == declared, (set(exported) ^ set(declared))
+    from harp_b200._lib import SYMBOLS
+    assert sorted(SYMBOLS) == declared
+
+
+def test_version_and_error_string_without_gpu(libpath):
+    L = ctypes.CDLL(libpath)
+    L.harp_last_error.restype = ctypes.c_char_p
+    assert L.harp_version() == 100
+    assert L.harp_ctx_dims(None, None, None, None, None) == -1       # HARP_ERR_INVALID, no CUDA call made
+    assert b"null ctx" in L.harp_last_error()
+
+
+def test_library_is_sm100a_only(libpath):
+    out = subprocess.run(["cuobjdump", "--list-elf", libpath], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\w+)\.", out))
+    assert archs == {"100a"}, archs
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "harp_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "harp_oracle" not in src and "p3d_shim" not in src and "import pytorch3d" not in src, f
+
+
+def test_ops_fail_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    from harp_b200 import _lib
+    with pytest.raises(_lib.HarpError):
+        _lib.ptr(torch.zeros(3))
