@@ -39,7 +39,7 @@ _lib = None
 # every symbol include/harp_b200.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = ["harp_last_error", "harp_version", "harp_launch_count", "harp_ctx_profile", "harp_ctx_profile_read", "harp_ctx_create", "harp_ctx_destroy", "harp_ctx_reserve", "harp_ctx_dims",
            "harp_ctx_faces", "harp_ctx_read_counters", "harp_lbs_mano_fwd", "harp_lbs_mano_bwd", "harp_mesh_build_fwd",
-           "harp_mesh_build_bwd", "harp_mesh_losses", "harp_silhouette", "harp_shade", "harp_texture_reg", "harp_adam"]
+           "harp_mesh_build_bwd", "harp_mesh_losses", "harp_silhouette", "harp_shade", "harp_texture_reg", "harp_adam", "harp_adam_dev"]
 
 
 def lib():
@@ -72,6 +72,7 @@ def lib():
                                  C.POINTER(HarpShadeGrads), vp]
         L.harp_texture_reg.argtypes = [vp, i, vp, i, i, vp, vp, f, vp, vp, vp]
         L.harp_adam.argtypes = [vp, vp, vp, vp, C.c_int64, f, f, f, f, i, vp]
+        L.harp_adam_dev.argtypes = [vp, vp, vp, vp, C.c_int64, f, f, f, f, vp, vp]
         _lib = L
     return _lib
 

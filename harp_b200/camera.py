@@ -15,19 +15,30 @@ def cam_to_T(cam, focal_length, img_size):
     return torch.stack([-cam[:, 1], -cam[:, 2], tz], dim=1)
 
 
+_CONST = {}
+
+
+def _const(name, values, device, dtype):
+    """Small constants cached per device so that no host->device copy happens inside a hot (graph-captured) step."""
+    key = (name, str(device), dtype)
+    if key not in _CONST:
+        _CONST[key] = torch.tensor(values, device=device, dtype=dtype)
+    return _CONST[key]
+
+
 def flip_xy_R(batch_size, device, dtype=torch.float32):
     """OpenCV -> PyTorch3D axis flip, diag(-1,-1,1), repeated per frame."""
-    R = torch.diag(torch.tensor([-1.0, -1.0, 1.0], device=device, dtype=dtype))
+    R = _const("flip", [[-1.0, 0.0, 0.0], [0.0, -1.0, 0.0], [0.0, 0.0, 1.0]], device, dtype)
     return R.expand(batch_size, 3, 3).contiguous()
 
 
 def look_at_rotation(camera_position, at, up=(0.0, 1.0, 0.0)):
     """PyTorch3D look_at_rotation: columns of R are the camera x, y, z axes in world space."""
-    up_t = torch.as_tensor(up, dtype=camera_position.dtype, device=camera_position.device).expand_as(camera_position)
+    up_t = _const("up" + repr(tuple(up)), list(up), camera_position.device, camera_position.dtype).expand_as(camera_position)
     z = F.normalize(at - camera_position, eps=1e-5)
     x = F.normalize(torch.cross(up_t, z, dim=1), eps=1e-5)
     y = F.normalize(torch.cross(z, x, dim=1), eps=1e-5)
-    degenerate = torch.isclose(x, torch.zeros_like(x), atol=5e-3).all(dim=1, keepdim=True)
+    degenerate = (x.abs() <= 5e-3).all(dim=1, keepdim=True)
     x = torch.where(degenerate, F.normalize(torch.cross(y, z, dim=1), eps=1e-5), x)
     return torch.stack((x, y, z), dim=2)
 

@@ -18,12 +18,22 @@ extern "C" int64_t harp_launch_count(void) { return g_launches.load(); }
 
 struct harp_prof {
   bool enabled = false;
+  bool in_graph = false;  // events belong to a captured graph: keep them across reads
   std::vector<cudaEvent_t> ev[2];  // start/stop pairs per kernel id
 };
 void harp_prof_begin(harp_ctx* c, int id, cudaStream_t st) {
   if (!c->prof || !c->prof->enabled) return;
   cudaEvent_t e;
-  if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); c->prof->ev[id].push_back(e); }
+  if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return; }
+  // inside a stream capture the record must become an EXTERNAL event node: it is re-recorded on every graph replay and
+  // stays usable with cudaEventElapsedTime
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  if (cap == cudaStreamCaptureStatusActive) c->prof->in_graph = true;
+  cudaError_t rc = cap == cudaStreamCaptureStatusActive ? cudaEventRecordWithFlags(e, st, cudaEventRecordExternal)
+                                                        : cudaEventRecord(e, st);
+  if (rc != cudaSuccess) { cudaGetLastError(); cudaEventDestroy(e); return; }
+  c->prof->ev[id].push_back(e);
 }
 void harp_prof_end(harp_ctx* c, int id, cudaStream_t st) { harp_prof_begin(c, id, st); }
 extern "C" int harp_ctx_profile(harp_ctx* c, int enable) {
@@ -42,8 +52,10 @@ extern "C" int harp_ctx_profile_read(harp_ctx* c, int id, float* total_ms, int* 
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, v[i], v[i + 1]) == cudaSuccess) { *total_ms += ms; ++*launches; }
   }
-  for (cudaEvent_t e : v) cudaEventDestroy(e);
-  v.clear();
+  if (!c->prof->in_graph) {
+    for (cudaEvent_t e : v) cudaEventDestroy(e);
+    v.clear();
+  }
   return HARP_OK;
 }
 

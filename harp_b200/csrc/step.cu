@@ -89,7 +89,45 @@ __global__ void __launch_bounds__(TPB) adam_kernel(float* __restrict__ p, const 
   p[i] -= (lr / bc1) * (mi / denom);
 }
 
+struct AdamState {
+  int step;
+  float bc1, bc2_sqrt;
+};
+
+__global__ void adam_tick_kernel(AdamState* st, float b1, float b2) {
+  int s = st->step + 1;
+  st->step = s;
+  st->bc1 = 1.f - powf(b1, (float)s);
+  st->bc2_sqrt = sqrtf(1.f - powf(b2, (float)s));
+}
+
+__global__ void __launch_bounds__(TPB) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                                        const AdamState* __restrict__ st) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float bc1 = st->bc1, bc2s = st->bc2_sqrt;
+  float gi = g[i];
+  float mi = m[i] + (1.f - b1) * (gi - m[i]);
+  float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= (lr / bc1) * (mi / (sqrtf(vi) / bc2s + eps));
+}
+
 }  // namespace
+
+extern "C" int harp_adam_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                             float beta1, float beta2, float eps, void* state, void* stream) {
+  HARP_REQUIRE(param && grad && exp_avg && exp_avg_sq && state && n >= 0, HARP_ERR_INVALID, "harp_adam_dev: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  adam_tick_kernel<<<1, 1, 0, st>>>((AdamState*)state, beta1, beta2);
+  if (n > 0)
+    adam_dev_kernel<<<(int)((n + TPB - 1) / TPB), TPB, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                                (const AdamState*)state);
+  HARP_LAUNCH_CHECK_N(2);
+  return HARP_OK;
+}
 
 extern "C" int harp_texture_reg(harp_ctx* c, int kind, const float* map, int H, int W, const int32_t* offsets,
                                 const float* uv_mask, float weight, float* loss, float* d_map, void* stream) {

@@ -43,12 +43,16 @@ class _Flat:
             self.data[a:b].copy_(t.detach().reshape(-1).to(device))
             self.p[name] = self.data[a:b].view(t.shape)
             self.g[name] = self.grad[a:b].view(t.shape)
-        self.steps = 0
+        # {int32 step, float bias_correction1, float sqrt(bias_correction2)} on the device: the update is graph-capturable
+        self.state = torch.zeros(3, dtype=torch.int32, device=device)
+
+    @property
+    def steps(self):
+        return int(self.state[0].item())
 
     def adam(self, lr):
-        self.steps += 1
-        check(_lib.lib().harp_adam(ptr(self.data), ptr(self.grad), ptr(self.m), ptr(self.v), self.data.numel(), float(lr),
-                                   0.9, 0.999, 1e-8, self.steps, stream()))
+        check(_lib.lib().harp_adam_dev(ptr(self.data), ptr(self.grad), ptr(self.m), ptr(self.v), self.data.numel(), float(lr),
+                                       0.9, 0.999, 1e-8, self.state.data_ptr(), stream()))
 
 
 class HarpFitter:
@@ -211,6 +215,29 @@ class HarpFitter:
             if app_on:
                 self.app.adam(self.lr_app)
         return self.losses
+
+    # -- CUDA-graph replay ------------------------------------------------------------------------------------------------
+    def capture(self, fid, off_albedo, off_normal, stage="both", frame_range=None, batch=None, warmup=2, keep_profile=False):
+        """Record one optimiser step (all C-ABI launches + the small torch glue) into a CUDA graph.  The ~120 launches of
+        a step then replay back to back; inputs are read from the same device buffers every replay (fid, offsets, the
+        resident frames or the staging `batch`).  Returns a callable; each call runs one step (update=True)."""
+        assert self.world_size == 1, "graph capture covers the single-GPU step (NCCL allreduce is launched eagerly)"
+        if not keep_profile:
+            self.hc.profile(False)
+        side = torch.cuda.Stream(device=self.hc.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(fid, off_albedo, off_normal, stage=stage, update=True, frame_range=frame_range, batch=batch)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        if keep_profile:
+            self.hc.profile_read()  # drop the warm-up event pairs; the captured step re-creates one pair per kernel
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.step(fid, off_albedo, off_normal, stage=stage, update=True, frame_range=frame_range, batch=batch)
+        self._graph = graph
+        return graph.replay
 
     def _allreduce_shared(self):
         """Per-frame rows (pose, cam) are rank-local under static frame sharding; everything else is shared and summed.

@@ -158,6 +158,12 @@ HARP_API int harp_texture_reg(harp_ctx*, int kind, const float* map, int H, int 
 HARP_API int harp_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
               float beta2, float eps, int step, void* stream);
 
+/* Same update with the step counter on the device, so the launch can be captured in a CUDA graph and replayed:
+ * state = {int32 step, float bias_correction1, float sqrt(bias_correction2)} (3 x 4 bytes, zero-initialised by the
+ * caller); each call increments state.step first. */
+HARP_API int harp_adam_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                           float beta2, float eps, void* state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
