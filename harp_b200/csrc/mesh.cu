@@ -109,8 +109,7 @@ __global__ void __launch_bounds__(TPB) normals_bwd_dN_kernel(harp_ctx c, int B, 
 
 // out = d_verts + gather(dN)   on the final mesh
 __global__ void __launch_bounds__(TPB) normals_bwd_gather_kernel(harp_ctx c, int B, const float* __restrict__ verts,
-                                                                  const float* __restrict__ dN, const float* __restrict__ d_verts,
-                                                                  float* __restrict__ out) {
+                                                                  const float* __restrict__ dN, const float* d_verts, float* out) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * c.V) return;
   int b = idx / c.V, v = idx % c.V;
@@ -306,6 +305,25 @@ extern "C" int harp_mesh_build_fwd(harp_ctx* c, int B, const float* verts0, cons
   build_displace_kernel<<<nblk((size_t)B * c->V), TPB, 0, st>>>(*c, B, verts0, disps, verts);
   if (normals) vertex_normals_kernel<<<nblk((size_t)B * c->V), TPB, 0, st>>>(*c, B, verts, normals);
   HARP_LAUNCH_CHECK_N(normals ? 2 : 1);
+  return HARP_OK;
+}
+
+extern "C" int harp_vertex_normals_fwd(harp_ctx* c, int B, const float* verts, float* normals, void* stream) {
+  HARP_REQUIRE(c && B > 0 && verts && normals, HARP_ERR_INVALID, "harp_vertex_normals_fwd: null argument");
+  vertex_normals_kernel<<<nblk((size_t)B * c->V), TPB, 0, (cudaStream_t)stream>>>(*c, B, verts, normals);
+  HARP_LAUNCH_CHECK();
+  return HARP_OK;
+}
+
+extern "C" int harp_vertex_normals_bwd(harp_ctx* c, int B, const float* verts, const float* d_normals, float* d_verts,
+                                       void* stream) {
+  HARP_REQUIRE(c && B > 0 && verts && d_normals && d_verts, HARP_ERR_INVALID, "harp_vertex_normals_bwd: null argument");
+  HARP_REQUIRE(B <= c->maxB, HARP_ERR_CAPACITY, "harp_vertex_normals_bwd: batch exceeds harp_ctx_reserve");
+  cudaStream_t st = (cudaStream_t)stream;
+  int nb = nblk((size_t)B * c->V);
+  normals_bwd_dN_kernel<<<nb, TPB, 0, st>>>(*c, B, verts, d_normals, c->vtmp2);
+  normals_bwd_gather_kernel<<<nb, TPB, 0, st>>>(*c, B, verts, c->vtmp2, d_verts, d_verts);  // in place: each thread owns its row
+  HARP_LAUNCH_CHECK_N(2);
   return HARP_OK;
 }
 

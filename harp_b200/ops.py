@@ -178,6 +178,28 @@ class MeshBuild(torch.autograd.Function):
         return None, d_verts0, (d_disps.view(ctx.disps_shape) if disps is not None else None)
 
 
+class VertexNormals(torch.autograd.Function):
+    """Meshes.verts_normals_padded() (PyTorch3D `_compute_vertex_normals`) on the context's topology."""
+
+    @staticmethod
+    def forward(ctx, hc, verts):
+        verts = _c(verts)
+        B = verts.shape[0]
+        hc.reserve(B, hc._reserved[1] or 8)
+        normals = torch.empty_like(verts)
+        check(_lib.lib().harp_vertex_normals_fwd(hc.h, B, ptr(verts), ptr(normals), stream()))
+        ctx.hc = hc
+        ctx.save_for_backward(verts)
+        return normals
+
+    @staticmethod
+    def backward(ctx, g):
+        (verts,) = ctx.saved_tensors
+        d_verts = torch.zeros_like(verts)
+        check(_lib.lib().harp_vertex_normals_bwd(ctx.hc.h, verts.shape[0], ptr(verts), ptr(_c(g)), ptr(d_verts), stream()))
+        return None, d_verts
+
+
 class MeshLosses(torch.autograd.Function):
     """-> (5,) unweighted [laplacian, normal consistency, arap, kps, sum disp^2]; gradients are precomputed at unit
     weight per term in forward and scaled by the upstream gradient in backward (no host sync)."""

@@ -104,6 +104,11 @@ HARP_API int harp_mesh_build_fwd(harp_ctx*, int B, const float* verts0, const fl
 HARP_API int harp_mesh_build_bwd(harp_ctx*, int B, const float* verts0, const float* disps, const float* d_verts,
                         const float* d_normals, float* d_verts0, float* d_disps, void* stream);
 
+/* Meshes.verts_normals_padded() of arbitrary verts on the ctx topology (area-weighted, F.normalize eps 1e-6). */
+HARP_API int harp_vertex_normals_fwd(harp_ctx*, int B, const float* verts, float* normals, void* stream);
+/* d_verts (B,V,3) accumulated. */
+HARP_API int harp_vertex_normals_bwd(harp_ctx*, int B, const float* verts, const float* d_normals, float* d_verts, void* stream);
+
 /* ---- mesh regularisers + keypoint anchor, value and gradient in one pass --------------------------------------------
  * mesh_laplacian_smoothing / mesh_normal_consistency (optimize_sequence.py:536-537), arap_loss (loss/arap.py:4-57),
  * kps_loss (loss/kps_loss.py:4-17), sum(disp^2) (optimize_sequence.py:533).
