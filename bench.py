@@ -175,7 +175,7 @@ def main():
     n_before = _lib.lib().harp_launch_count()
     run_step()
     launches_per_step = _lib.lib().harp_launch_count() - n_before
-    use_graph = world == 1 and not args.eager
+    use_graph = not args.eager
     if use_graph:
         # the step is captured with the event brackets of the two pixel kernels inside (event-record graph nodes), so every
         # replay re-records them and the kernel durations are read from the timed region itself

@@ -55,6 +55,31 @@ class _Flat:
                                        0.9, 0.999, 1e-8, self.state.data_ptr(), stream()))
 
 
+def shard_frames(total_frames, rank, world_size):
+    """Static contiguous frame sharding: rank r owns [r T/R, (r+1) T/R); remainder to the first ranks."""
+    base, rem = divmod(total_frames, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def allreduce_shared(coarse, app, losses, world_size, group=None):
+    """The step's ONE collective.  Per-frame rows (pose, cam) are rank-local under static frame sharding and are not
+    exchanged; everything else is shared and summed: [verts_disps | shape | light row 0 | amb | texture | normal_map | losses]
+    as a single flat fp32 buffer (about 6.3 MB).  Loss values come back averaged over ranks."""
+    import torch.distributed as dist
+    a0 = coarse.offsets[coarse.names.index("verts_disps")]
+    a1 = app.offsets[app.names.index("amb_ratio")]
+    parts = [coarse.grad[a0:], app.grad[:3], app.grad[a1:], losses]
+    flat = torch.cat([p.reshape(-1) for p in parts])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    o = 0
+    for p in parts:
+        n = p.numel()
+        p.copy_(flat[o:o + n].view(p.shape))
+        o += n
+    losses /= world_size
+
+
 class HarpFitter:
     """params: dict with the reference's keys (`optimize_sequence.py:181-250`): pose (T,45), rot (T,3), trans (T,3),
     cam (T,3), shape (10,), verts_disps (V,1), texture / normal_map (1,H,W,3), light_positions (T,3), amb_ratio ().
@@ -100,7 +125,7 @@ class HarpFitter:
         return t
 
     # -- one minibatch ----------------------------------------------------------------------------------------------------
-    def step(self, fid, off_albedo, off_normal, stage="both", update=True, batch=None, frame_range=None):
+    def step(self, fid, off_albedo, off_normal, stage="both", update=True, batch=None, frame_range=None, exchange=True):
         """fid: (B,) long device tensor of frame ids owned by this rank.  stage: 'coarse' | 'both' | 'app'
         (`optimize_sequence.py:507-515`).  batch: optional dict overriding self.frames rows (host->device ingest path).
         frame_range=(a,b): promise that fid == arange(a,b), so image rows are used in place instead of gathered.
@@ -207,54 +232,51 @@ class HarpFitter:
             self.app.g["amb_ratio"] += g_ambr.view(1)
             self.last = dict(d_rot=d_pose48[:, :3], d_trans=d_trans, alpha=alpha, rgb=rgb, verts=verts, joints=joints)
         # ---- data-parallel exchange: ONE allreduce of the shared-parameter gradients
-        if R > 1:
+        if R > 1 and exchange:
             self._allreduce_shared()
         if update:
-            if coarse_on:
-                self.coarse.adam(self.lr_coarse)
-            if app_on:
-                self.app.adam(self.lr_app)
+            self._update(stage)
         return self.losses
+
+    def _update(self, stage):
+        if stage in ("coarse", "both"):
+            self.coarse.adam(self.lr_coarse)
+        if stage in ("both", "app"):
+            self.app.adam(self.lr_app)
 
     # -- CUDA-graph replay ------------------------------------------------------------------------------------------------
     def capture(self, fid, off_albedo, off_normal, stage="both", frame_range=None, batch=None, warmup=2, keep_profile=False):
         """Record one optimiser step (all C-ABI launches + the small torch glue) into a CUDA graph.  The ~120 launches of
         a step then replay back to back; inputs are read from the same device buffers every replay (fid, offsets, the
         resident frames or the staging `batch`).  Returns a callable; each call runs one step (update=True)."""
-        assert self.world_size == 1, "graph capture covers the single-GPU step (NCCL allreduce is launched eagerly)"
+        multi = self.world_size > 1  # the NCCL allreduce and the two Adam launches stay outside the graph
+        kw = dict(stage=stage, frame_range=frame_range, batch=batch)
         if not keep_profile:
             self.hc.profile(False)
         side = torch.cuda.Stream(device=self.hc.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self.step(fid, off_albedo, off_normal, stage=stage, update=True, frame_range=frame_range, batch=batch)
+                self.step(fid, off_albedo, off_normal, update=True, **kw)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         if keep_profile:
             self.hc.profile_read()  # drop the warm-up event pairs; the captured step re-creates one pair per kernel
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self.step(fid, off_albedo, off_normal, stage=stage, update=True, frame_range=frame_range, batch=batch)
+            self.step(fid, off_albedo, off_normal, update=not multi, exchange=False, **kw)
         self._graph = graph
-        return graph.replay
+        if not multi:
+            return graph.replay
+
+        def replay_and_exchange():
+            graph.replay()
+            self._allreduce_shared()
+            self._update(stage)
+        return replay_and_exchange
 
     def _allreduce_shared(self):
-        """Per-frame rows (pose, cam) are rank-local under static frame sharding; everything else is shared and summed.
-        One flat buffer: [verts_disps | shape | light row 0 | amb | texture | normal_map | losses]."""
-        import torch.distributed as dist
-        cg, ag = self.coarse, self.app
-        a0 = cg.offsets[cg.names.index("verts_disps")]
-        parts = [cg.grad[a0:], ag.grad[:3], ag.grad[ag.offsets[ag.names.index("amb_ratio")]:], self.losses]
-        flat = torch.cat([p.reshape(-1) for p in parts])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
-        o = 0
-        for p in parts:
-            n = p.numel()
-            p.copy_(flat[o:o + n].view(p.shape))
-            o += n
-        # losses were frame means over the local batch (x 1/R applied to gradients only): average them
-        self.losses /= self.world_size
+        allreduce_shared(self.coarse, self.app, self.losses, self.world_size, self.pg)
 
     def loss_dict(self):
         """One device->host read of the loss vector (the reference does >= 10 `.cpu()` syncs per iteration, 556-561)."""
