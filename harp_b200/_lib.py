@@ -30,6 +30,14 @@ class HarpShadeGrads(C.Structure):
                                           "d_light_pos", "d_amb", "d_texture", "d_normal_map")]
 
 
+class HarpRenderArgs(C.Structure):
+    _fields_ = ([(n, C.c_void_p) for n in ("verts", "normals", "cam_R", "cam_T", "light_R", "light_T", "light_pos", "amb",
+                                            "texture", "normal_map")] +
+                [("texH", C.c_int32), ("texW", C.c_int32), ("self_shadow", C.c_int32), ("sigma", C.c_float)] +
+                [(n, C.c_void_p) for n in ("y_sil", "y_true", "y_mask")] + [("w_sil", C.c_float), ("w_photo", C.c_float)] +
+                [(n, C.c_void_p) for n in ("alpha", "rgb", "loss_sil", "loss_photo")] + [("grads", HarpShadeGrads)])
+
+
 class HarpError(RuntimeError):
     pass
 
@@ -39,7 +47,7 @@ _lib = None
 # every symbol include/harp_b200.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = ["harp_last_error", "harp_version", "harp_launch_count", "harp_ctx_profile", "harp_ctx_profile_read", "harp_ctx_create", "harp_ctx_destroy", "harp_ctx_reserve", "harp_ctx_dims",
            "harp_ctx_faces", "harp_ctx_read_counters", "harp_lbs_mano_fwd", "harp_lbs_mano_bwd", "harp_mesh_build_fwd",
-           "harp_mesh_build_bwd", "harp_vertex_normals_fwd", "harp_vertex_normals_bwd", "harp_mesh_losses", "harp_silhouette", "harp_shade", "harp_texture_reg", "harp_adam", "harp_adam_dev"]
+           "harp_mesh_build_bwd", "harp_vertex_normals_fwd", "harp_vertex_normals_bwd", "harp_mesh_losses", "harp_silhouette", "harp_shade", "harp_render_fused", "harp_texture_reg", "harp_adam", "harp_adam_dev"]
 
 
 def lib():
@@ -72,6 +80,7 @@ def lib():
         L.harp_silhouette.argtypes = [vp, i, i, i, f, f, vp, vp, vp, vp, vp, f, vp, vp, vp, vp, vp]
         L.harp_shade.argtypes = [vp, i, i, i, f, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, f, vp,
                                  C.POINTER(HarpShadeGrads), vp]
+        L.harp_render_fused.argtypes = [vp, i, i, f, C.POINTER(HarpRenderArgs), vp]
         L.harp_texture_reg.argtypes = [vp, i, vp, i, i, vp, vp, f, vp, vp, vp]
         L.harp_adam.argtypes = [vp, vp, vp, vp, C.c_int64, f, f, f, f, i, vp]
         L.harp_adam_dev.argtypes = [vp, vp, vp, vp, C.c_int64, f, f, f, f, vp, vp]

@@ -83,6 +83,9 @@ struct harp_ctx {
   float* light_zbuf = nullptr;    // (B,S,S)
   int32_t* light_face = nullptr;  // (B,S,S)
   float* d_light_zbuf = nullptr;  // (B,S,S)
+  int32_t* vis_fid = nullptr;     // (B,S,S) nearest camera-view face per pixel (fused pixel pass)
+  int32_t* hit_list = nullptr;    // (B,S*S) compacted row*S+col of hit pixels, per frame
+  int32_t* hit_count = nullptr;   // (B)
   float* vN = nullptr;            // (B,V,3) unnormalised vertex normals (mesh build scratch)
   float* vtmp = nullptr;          // (B,V,3) scratch
   float* vtmp2 = nullptr;         // (B,V,3) scratch

@@ -243,8 +243,9 @@ extern "C" int harp_ctx_create(harp_ctx** out, const harp_topology* topo, const 
 static void free_scratch(harp_ctx* c) {
   void* ptrs[] = {c->ndc_cam, c->ndc_light, c->d_ndc_cam, c->d_ndc_light, c->bin_count, c->bin_start, c->bin_fill,
                   c->bin_list, c->light_zbuf, c->light_face, c->d_light_zbuf, c->vN, c->vtmp, c->vtmp2, c->d_verts4,
-                  c->d_normals4};
+                  c->d_normals4, c->vis_fid, c->hit_list, c->hit_count};
   c->d_verts4 = c->d_normals4 = nullptr;
+  c->vis_fid = c->hit_list = c->hit_count = nullptr;
   for (void* p : ptrs) if (p) cudaFree(p);
   c->ndc_cam = c->ndc_light = c->d_ndc_cam = c->d_ndc_light = c->light_zbuf = c->d_light_zbuf = c->vN = c->vtmp = c->vtmp2 = nullptr;
   c->bin_count = c->bin_start = c->bin_fill = c->bin_list = c->light_face = nullptr;
@@ -293,6 +294,9 @@ extern "C" int harp_ctx_reserve(harp_ctx* c, int max_batch, int img_size) {
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->light_zbuf, npx * sizeof(float)));
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->light_face, npx * sizeof(int32_t)));
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->d_light_zbuf, npx * sizeof(float)));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->vis_fid, npx * sizeof(int32_t)));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->hit_list, npx * sizeof(int32_t)));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->hit_count, (size_t)B * sizeof(int32_t)));
   c->maxB = B;
   c->S = S;
   c->tiles = tiles;

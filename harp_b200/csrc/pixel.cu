@@ -1,0 +1,353 @@
+// The fused pixel pass of the optimiser step: ONE walk over each tile's face list yields the soft silhouette (value, L1
+// loss, gradient) AND the nearest covering face of every pixel; hit pixels are compacted per frame and shaded (forward,
+// photometric L1, backward) by a second kernel whose warps are full and barrier-free.
+// Replaces, per minibatch: the K=50 and the K=1 camera-view rasterisations (renderer_helper.py:44-58,353), both shaders
+// and blends, both image losses (optimize_sequence.py:519,543) and their autograd.
+#include "shade_pixel.cuh"
+
+int harp_build_bins(harp_ctx* c, int view, int B, int S, float radius, const float* ndc, cudaStream_t st);
+int harp_project(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R, const float* T, float* ndc,
+                 cudaStream_t st);
+int harp_project_bwd(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R, const float* T,
+                     const float* d_ndc, float* d_verts, float* d_R, float* d_T, cudaStream_t st);
+int harp_fold4(size_t n, const float* src4, float* dst3, cudaStream_t st);
+int harp_light_depth(harp_ctx* c, int B, int S, cudaStream_t st);
+int harp_light_depth_bwd(harp_ctx* c, int B, int S, cudaStream_t st);
+
+namespace {
+
+constexpr int CHUNK = 64;
+constexpr int NT = HARP_TILE * HARP_TILE;
+constexpr int QCAP = 512;
+
+struct VisArgs {
+  int S;
+  float sigma, blur, radius;
+  const float* ndc;
+  const int32_t *bin_count, *bin_start, *bin_list;
+  // silhouette
+  float* alpha;
+  const float* y_sil;
+  float sil_gscale, sil_inv_n;
+  float* sil_loss;
+  float* d_ndc;
+  // visibility
+  int32_t *vis_fid, *hit_list, *hit_count;
+  // background pixels of the colour image
+  float* rgb;
+  const float *y_true, *y_mask;
+  float photo_inv_n;
+  float* photo_loss;
+};
+
+__device__ __forceinline__ void sil_pair_gradient2(const FaceRec& f, float px, float py, float sd, int edge, float t, float g,
+                                                   float prod, float sigma, float* d_ndc) {
+  float prob = 1.f / (1.f + expf(fdiv(sd, sigma)));
+  float gsd = g * (-prod * prob / sigma);
+  float gd = sd < 0.f ? -gsd : gsd;
+  if (gd == 0.f) return;
+  float ax, ay, bx, by; int va, vb;
+  if (edge == 0) { ax = f.x0; ay = f.y0; bx = f.x1; by = f.y1; va = f.v0; vb = f.v1; }
+  else if (edge == 1) { ax = f.x0; ay = f.y0; bx = f.x2; by = f.y2; va = f.v0; vb = f.v2; }
+  else { ax = f.x1; ay = f.y1; bx = f.x2; by = f.y2; va = f.v1; vb = f.v2; }
+  if (t < 0.f) {
+    atomicAdd(reinterpret_cast<float2*>(d_ndc + (size_t)vb * 4), make_float2(gd * 2.f * (bx - px), gd * 2.f * (by - py)));
+    return;
+  }
+  float qx = ax + t * (bx - ax), qy = ay + t * (by - ay);
+  float dx = 2.f * gd * (qx - px), dy = 2.f * gd * (qy - py);
+  atomicAdd(reinterpret_cast<float2*>(d_ndc + (size_t)va * 4), make_float2((1.f - t) * dx, (1.f - t) * dy));
+  atomicAdd(reinterpret_cast<float2*>(d_ndc + (size_t)vb * 4), make_float2(t * dx, t * dy));
+}
+
+// SIL_BWD: accumulate the silhouette L1 loss and its gradient (COARSE_OPT stages); PHOTO: accumulate the photometric loss
+// of background pixels (APP_OPT stages; hit pixels are handled by the deferred shading kernel).
+template <bool SIL_BWD, bool PHOTO>
+__global__ void __launch_bounds__(NT) pixel_vis_kernel(harp_ctx c, VisArgs a) {
+  __shared__ FaceRec faces[CHUNK];
+  __shared__ float red[32];
+  __shared__ unsigned char q_pix[QCAP], q_face[QCAP], q_edge[QCAP];
+  __shared__ float q_sd[QCAP], q_t[QCAP];
+  __shared__ int q_n, any_bwd;
+  __shared__ float s_g[NT], s_prod[NT];
+  __shared__ unsigned char s_need[NT];
+  const int S = a.S;
+  int b = blockIdx.z, tw = S / HARP_TILE, tid = threadIdx.x;
+  int lx = tid % HARP_TILE, ly = tid / HARP_TILE;
+  int col = blockIdx.x * HARP_TILE + lx, row = blockIdx.y * HARP_TILE + ly;
+  size_t pix = ((size_t)b * S + row) * S + col;
+  size_t tglob = (size_t)b * tw * tw + blockIdx.y * tw + blockIdx.x;
+  int n = a.bin_count[tglob], start = a.bin_start[tglob];
+  if (start + n > c.bin_cap) n = max(0, (int)c.bin_cap - start);
+  const int32_t* list = a.bin_list + (size_t)b * c.bin_cap + start;
+  const float* ndc = a.ndc + (size_t)b * c.V * 3;
+  const float sigma = a.sigma, blur = a.blur;
+  float px = pix_to_ndc(col, S), py = pix_to_ndc(row, S);
+  float prod = 1.f;
+  int nzero = 0, npass = 0;
+  int best_fid = -1;
+  float best_q = 0.f;
+  bool q_overflow = false;
+  const float sat = 17.5f * sigma;
+  if (tid == 0) { any_bwd = 0; q_n = 0; }
+  for (int base = 0; base < n; base += CHUNK) {
+    int m = min(CHUNK, n - base);
+    __syncthreads();
+    if (tid < m) load_face(c, ndc, list[base + tid], a.radius, faces[tid]);
+    if (tid == 0) q_n = 0;
+    __syncthreads();
+    // A: convergent classification of every (pixel, face) pair: visibility (nearest inside face by 1/depth) for all
+    //    pixels; silhouette factors until the pixel saturates (one exactly-zero factor => alpha = 1, zero gradient)
+    for (int i = 0; i < m; ++i) {
+      const FaceRec& f = faces[i];
+      bool inside, exact;
+      float q;
+      int cls = classify_pair_vis<true>(f, px, py, blur, sat, inside, q, exact);
+      if (cls == PAIR_REJECT) continue;
+      if (exact) {  // a vertex behind the camera: decide visibility with the exact operation sequence
+        PairEval e;
+        eval_pair_full<false, false>(f, px, py, 0.f, e);
+        inside = e.pass;
+        q = e.pass ? 1.f / e.pz : 0.f;
+      }
+      if (inside && (q > best_q || (q == best_q && (best_fid < 0 || f.fid < best_fid)))) { best_q = q; best_fid = f.fid; }
+      if (nzero > 0) continue;
+      if (cls == PAIR_SATURATED) { ++npass; ++nzero; continue; }
+      int slot = atomicAdd(&q_n, 1);
+      if (slot < QCAP) {
+        q_pix[slot] = (unsigned char)tid; q_face[slot] = (unsigned char)i;
+      } else {
+        q_overflow = true;
+        PairEval e;
+        eval_pair_full<true, true>(f, px, py, blur, e);
+        if (!e.pass) continue;
+        ++npass;
+        float om = 1.f - 1.f / (1.f + expf(fdiv(e.inside ? -e.dist : e.dist, sigma)));
+        if (om == 0.f) ++nzero; else prod *= om;
+      }
+    }
+    __syncthreads();
+    // B: drain the queue of band pairs with every thread busy
+    int qn = min(q_n, QCAP);
+    for (int s = tid; s < qn; s += NT) {
+      int p = q_pix[s];
+      float ppx = pix_to_ndc(blockIdx.x * HARP_TILE + (p % HARP_TILE), S), ppy = pix_to_ndc(blockIdx.y * HARP_TILE + (p / HARP_TILE), S);
+      PairEval e;
+      eval_pair_full<true, true>(faces[q_face[s]], ppx, ppy, blur, e);
+      if (e.pass) { q_sd[s] = e.inside ? -e.dist : e.dist; q_edge[s] = (unsigned char)e.edge; q_t[s] = e.t; }
+      else q_edge[s] = 255;
+    }
+    __syncthreads();
+    // C: every pixel folds its own results in face-list order
+    if (nzero == 0) {
+      for (int s = 0; s < qn; ++s) {
+        if (q_pix[s] != tid || q_edge[s] == 255) continue;
+        ++npass;
+        float om = 1.f - 1.f / (1.f + expf(fdiv(q_sd[s], sigma)));
+        if (om == 0.f) { ++nzero; break; }
+        prod *= om;
+      }
+    }
+  }
+  // ---- visibility outputs: face id image + per-frame compacted hit list (warp-aggregated append)
+  a.vis_fid[pix] = best_fid;
+  bool hit = best_fid >= 0;
+  {
+    unsigned mask = __ballot_sync(0xffffffffu, hit);
+    int lane = tid & 31, base = 0;
+    if (mask) {
+      if (lane == 0) base = atomicAdd(a.hit_count + b, __popc(mask));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (hit) a.hit_list[(size_t)b * S * S + base + __popc(mask & ((1u << lane) - 1u))] = row * S + col;
+    }
+  }
+  float photo_abs = 0.f;
+  if (!hit) {
+    st3(a.rgb + pix * 3, mk3(1.f, 1.f, 1.f));  // background colour (renderer_helper.py:430)
+    if (PHOTO) {
+      float mk = a.y_mask[pix];
+      f3 y = ld3(a.y_true + pix * 3);
+      photo_abs = fabsf(mk - y.x * mk) + fabsf(mk - y.y * mk) + fabsf(mk - y.z * mk);
+    }
+  }
+  if (PHOTO) {
+    float s = block_sum(photo_abs, red);
+    if (tid == 0 && s != 0.f) atomicAdd(a.photo_loss, s * a.photo_inv_n);
+  }
+  // ---- silhouette value, loss and gradient
+  float al = nzero > 0 ? 1.f : 1.f - prod;
+  if (npass > 50) atomicAdd(c.counters, 1ULL);
+  a.alpha[pix] = al;
+  if (!SIL_BWD) return;
+  float diff = al - a.y_sil[pix];
+  float g = diff > 0.f ? a.sil_gscale : (diff < 0.f ? -a.sil_gscale : 0.f);
+  {
+    float s = block_sum(fabsf(diff), red);
+    if (tid == 0 && s != 0.f) atomicAdd(a.sil_loss, s * a.sil_inv_n);
+  }
+  bool need = (g != 0.f) && nzero == 0 && prod > 0.f && npass > 0;
+  if (need) any_bwd = 1;
+  s_g[tid] = g; s_prod[tid] = prod; s_need[tid] = need ? 1 : 0;
+  int any_overflow = __syncthreads_or(q_overflow ? 1 : 0);
+  if (!any_bwd) return;
+  float* d_ndc = a.d_ndc + (size_t)b * c.V * 4;
+  if (n <= CHUNK && !any_overflow) {
+    int qn = min(q_n, QCAP);
+    for (int s = tid; s < qn; s += NT) {
+      int p = q_pix[s];
+      if (!s_need[p] || q_edge[s] == 255) continue;
+      float ppx = pix_to_ndc(blockIdx.x * HARP_TILE + (p % HARP_TILE), S), ppy = pix_to_ndc(blockIdx.y * HARP_TILE + (p / HARP_TILE), S);
+      sil_pair_gradient2(faces[q_face[s]], ppx, ppy, q_sd[s], q_edge[s], q_t[s], s_g[p], s_prod[p], sigma, d_ndc);
+    }
+    return;
+  }
+  for (int base = 0; base < n; base += CHUNK) {  // generic path (multi-chunk tiles): re-stage and evaluate per pixel
+    int m = min(CHUNK, n - base);
+    __syncthreads();
+    if (tid < m) load_face(c, ndc, list[base + tid], a.radius, faces[tid]);
+    __syncthreads();
+    if (!need) continue;
+    for (int i = 0; i < m; ++i) {
+      PairEval e;
+      eval_pair<true, true>(faces[i], px, py, blur, sat, e);
+      if (!e.pass || e.saturated) continue;
+      sil_pair_gradient2(faces[i], px, py, e.inside ? -e.dist : e.dist, e.edge, e.t, g, prod, sigma, d_ndc);
+    }
+  }
+}
+
+// Shade the compacted hit pixels of one frame per blockIdx.y; grid-stride over the frame's hit list.
+template <int MODE>
+__global__ void __launch_bounds__(128, 4) shade_deferred_kernel(harp_ctx c, ShadeArgs a, const int32_t* __restrict__ vis_fid,
+                                                             const int32_t* __restrict__ hit_list,
+                                                             const int32_t* __restrict__ hit_count) {
+  const int S = a.S;
+  int b = blockIdx.y;
+  int n = hit_count[b];
+  int n_pad = (n + 31) & ~31;  // keep warps whole for the warp reductions
+  const float* ndc = a.ndc_cam + (size_t)b * c.V * 3;
+  const int32_t* list = hit_list + (size_t)b * S * S;
+  float loss_acc = 0.f, fr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_pad; idx += gridDim.x * blockDim.x) {
+    if (idx >= n) continue;
+    int rc = list[idx];
+    int row = rc / S, col = rc % S;
+    size_t pix = (size_t)b * S * S + rc;
+    float px = pix_to_ndc(col, S), py = pix_to_ndc(row, S);
+    Hit h;
+    h.fid = vis_fid[pix];
+    FaceRec f;
+    load_face(c, ndc, h.fid, 0.f, f);
+    PairEval e;
+    eval_pair_full<false, false>(f, px, py, 0.f, e);
+    if (e.pass) { h.pz = e.pz; h.b0 = e.b0; h.b1 = e.b1; h.b2 = e.b2; h.w0 = e.w0; h.w1 = e.w1; h.w2 = e.w2; }
+    else h.fid = -1;  // the exact test disagrees with the fast classification on a boundary pixel: background
+    ShadeOut o;
+    shade_pixel<MODE>(c, a, b, pix, px, py, h, o);
+    if (MODE != 1) st3(a.rgb + pix * 3, o.rgb);
+    loss_acc += o.loss_abs;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) fr[k] += o.frame[k];
+  }
+  if (MODE == 0) return;
+  if (MODE == 2) {
+    float s = warp_sum(loss_acc);
+    if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(a.loss, s * a.inv_n);
+  }
+  shade_flush_frame_scalars(a, b, fr);
+}
+
+}  // namespace
+
+extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const harp_render_args* r, void* stream) {
+  HARP_REQUIRE(c && r && B > 0, HARP_ERR_INVALID, "harp_render_fused: null argument");
+  HARP_REQUIRE(r->verts && r->normals && r->cam_R && r->cam_T && r->light_pos && r->amb && r->texture && r->normal_map &&
+                   r->alpha && r->rgb, HARP_ERR_INVALID, "harp_render_fused: missing input / output tensor");
+  HARP_REQUIRE(c->has_uv, HARP_ERR_INVALID, "harp_render_fused: ctx was created without UV tables");
+  HARP_REQUIRE(B <= c->maxB && S == c->S, HARP_ERR_CAPACITY, "harp_render_fused: call harp_ctx_reserve(B, S) first");
+  HARP_REQUIRE(!r->self_shadow || (r->light_R && r->light_T), HARP_ERR_INVALID, "harp_render_fused: light camera required");
+  const bool sil_bwd = r->w_sil != 0.f, photo_bwd = r->w_photo != 0.f;
+  HARP_REQUIRE(!sil_bwd || (r->y_sil && r->loss_sil && r->grads.d_verts && r->grads.d_cam_T), HARP_ERR_INVALID,
+               "harp_render_fused: silhouette loss needs y_sil, loss_sil, d_verts, d_cam_T");
+  HARP_REQUIRE(!photo_bwd || (r->y_true && r->y_mask && r->loss_photo && r->grads.d_verts && r->grads.d_normals), HARP_ERR_INVALID,
+               "harp_render_fused: photometric loss needs y_true, y_mask, loss_photo, d_verts, d_normals");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  const size_t npx = (size_t)B * S * S, nv4 = (size_t)B * c->V * 4 * sizeof(float), ntex = (size_t)r->texH * r->texW;
+  double blur_d = 9.210240366975849 * (double)r->sigma;  // ln(1/1e-4 - 1) sigma (renderer_helper.py:46)
+  float blur = (float)blur_d, radius = (float)sqrt(blur_d);
+  if ((rc = harp_project(c, B, S, focal, r->verts, r->cam_R, r->cam_T, c->ndc_cam, st)) != HARP_OK) return rc;
+  if ((rc = harp_build_bins(c, 0, B, S, radius, c->ndc_cam, st)) != HARP_OK) return rc;
+  if (r->self_shadow) {
+    if ((rc = harp_project(c, B, S, focal, r->verts, r->light_R, r->light_T, c->ndc_light, st)) != HARP_OK) return rc;
+    if ((rc = harp_build_bins(c, 1, B, S, 0.f, c->ndc_light, st)) != HARP_OK) return rc;
+    if ((rc = harp_light_depth(c, B, S, st)) != HARP_OK) return rc;
+  }
+  if (sil_bwd || photo_bwd) HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_cam, 0, nv4, st));
+  if (photo_bwd) {
+    if ((int64_t)ntex > c->texcap) {
+      if (c->d_tex4) cudaFree(c->d_tex4);
+      c->d_tex4 = nullptr; c->texcap = 0;
+      HARP_CHECK_CUDA(cudaMalloc((void**)&c->d_tex4, 2 * ntex * 4 * sizeof(float)));
+      c->texcap = (int64_t)ntex;
+    }
+    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_verts4, 0, nv4, st));
+    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_normals4, 0, nv4, st));
+    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_tex4, 0, 2 * ntex * 4 * sizeof(float), st));
+    if (r->self_shadow) {
+      HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_light, 0, nv4, st));
+      HARP_CHECK_CUDA(cudaMemsetAsync(c->d_light_zbuf, 0, npx * sizeof(float), st));
+    }
+  }
+  HARP_CHECK_CUDA(cudaMemsetAsync(c->hit_count, 0, (size_t)B * sizeof(int32_t), st));
+  VisArgs v{};
+  v.S = S; v.sigma = r->sigma; v.blur = blur; v.radius = radius; v.ndc = c->ndc_cam;
+  v.bin_count = c->bin_count; v.bin_start = c->bin_start; v.bin_list = c->bin_list;
+  v.alpha = r->alpha; v.y_sil = r->y_sil; v.sil_inv_n = 1.f / ((float)B * S * S); v.sil_gscale = r->w_sil * v.sil_inv_n;
+  v.sil_loss = r->loss_sil; v.d_ndc = c->d_ndc_cam;
+  v.vis_fid = c->vis_fid; v.hit_list = c->hit_list; v.hit_count = c->hit_count;
+  v.rgb = r->rgb; v.y_true = r->y_true; v.y_mask = r->y_mask; v.photo_inv_n = 1.f / ((float)B * S * S * 3.f);
+  v.photo_loss = r->loss_photo;
+  dim3 grid(S / HARP_TILE, S / HARP_TILE, B);
+  harp_prof_begin(c, 0, st);
+  if (sil_bwd && photo_bwd) pixel_vis_kernel<true, true><<<grid, NT, 0, st>>>(*c, v);
+  else if (sil_bwd) pixel_vis_kernel<true, false><<<grid, NT, 0, st>>>(*c, v);
+  else if (photo_bwd) pixel_vis_kernel<false, true><<<grid, NT, 0, st>>>(*c, v);
+  else pixel_vis_kernel<false, false><<<grid, NT, 0, st>>>(*c, v);
+  harp_prof_end(c, 0, st);
+  HARP_LAUNCH_CHECK();
+  ShadeArgs a{};
+  a.B = B; a.S = S; a.self_shadow = r->self_shadow; a.texH = r->texH; a.texW = r->texW; a.focal = focal;
+  a.inv_n = v.photo_inv_n; a.gscale = r->w_photo * a.inv_n;
+  a.verts = r->verts; a.normals = r->normals; a.ndc_cam = c->ndc_cam;
+  a.light_R = r->light_R ? r->light_R : r->cam_R; a.light_T = r->light_T ? r->light_T : r->cam_T;
+  a.light_pos = r->light_pos; a.amb = r->amb; a.texture = r->texture; a.normal_map = r->normal_map;
+  a.light_zbuf = c->light_zbuf; a.rgb = r->rgb; a.gin = r->y_true; a.mask = r->y_mask; a.loss = r->loss_photo;
+  if (photo_bwd) {
+    a.d_ndc_cam = c->d_ndc_cam; a.d_verts = c->d_verts4; a.d_normals = c->d_normals4;
+    a.d_light_R = r->grads.d_light_R; a.d_light_T = r->grads.d_light_T; a.d_light_pos = r->grads.d_light_pos;
+    a.d_amb = r->grads.d_amb; a.d_texture = c->d_tex4; a.d_normal_map = c->d_tex4 + ntex * 4; a.d_light_zbuf = c->d_light_zbuf;
+  }
+  dim3 sgrid(96, B);
+  harp_prof_begin(c, 1, st);
+  if (photo_bwd) shade_deferred_kernel<2><<<sgrid, 128, 0, st>>>(*c, a, c->vis_fid, c->hit_list, c->hit_count);
+  else shade_deferred_kernel<0><<<sgrid, 128, 0, st>>>(*c, a, c->vis_fid, c->hit_list, c->hit_count);
+  harp_prof_end(c, 1, st);
+  HARP_LAUNCH_CHECK();
+  if (photo_bwd) {
+    if ((rc = harp_fold4((size_t)B * c->V, c->d_verts4, r->grads.d_verts, st)) != HARP_OK) return rc;
+    if ((rc = harp_fold4((size_t)B * c->V, c->d_normals4, r->grads.d_normals, st)) != HARP_OK) return rc;
+    if (r->grads.d_texture && (rc = harp_fold4(ntex, c->d_tex4, r->grads.d_texture, st)) != HARP_OK) return rc;
+    if (r->grads.d_normal_map && (rc = harp_fold4(ntex, c->d_tex4 + ntex * 4, r->grads.d_normal_map, st)) != HARP_OK) return rc;
+    if (r->self_shadow) {
+      if ((rc = harp_light_depth_bwd(c, B, S, st)) != HARP_OK) return rc;
+      if ((rc = harp_project_bwd(c, B, S, focal, r->verts, r->light_R, r->light_T, c->d_ndc_light, r->grads.d_verts,
+                                 r->grads.d_light_R, r->grads.d_light_T, st)) != HARP_OK) return rc;
+    }
+  }
+  if (sil_bwd || photo_bwd) {
+    if ((rc = harp_project_bwd(c, B, S, focal, r->verts, r->cam_R, r->cam_T, c->d_ndc_cam, r->grads.d_verts, r->grads.d_cam_R,
+                               r->grads.d_cam_T, st)) != HARP_OK) return rc;
+  }
+  return HARP_OK;
+}

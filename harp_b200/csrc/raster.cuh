@@ -50,6 +50,7 @@ struct FaceRec {  // staged in shared memory, one per face of the current chunk 
   float area;                    // EdgeFunction(v2, v0, v1) + kEpsilon
   float l12, l20, l01;           // squared lengths of the edges opposite v0, v1, v2
   float zmin;
+  float inv_area, iz0, iz1, iz2;  // reciprocals for the fast 1/depth ordering (visibility only; never for output values)
   int v0, v1, v2, fid;
 };
 
@@ -90,6 +91,34 @@ __device__ __forceinline__ int classify_pair(const FaceRec& f, float px, float p
       if ((!i0 && e0 * e0 >= far * f.l12) || (!i1 && e1 * e1 >= far * f.l20) || (!i2 && e2 * e2 >= far * f.l01)) return PAIR_REJECT;
     }
   }
+  return PAIR_FULL;
+}
+
+// Same classification, additionally reporting strict-inside and q = 1 / (perspective-correct depth) for inside pairs:
+// with w_i = e_i / area and b_i ~ w_i / z_i, pz = sum b_i z_i = 1 / sum(w_i / z_i).  q orders the faces covering a pixel
+// (nearest = largest q); the winner's barycentrics and depth are then recomputed with the exact operation sequence.
+// `exact_needed` is set for faces with a vertex behind the camera, where the sign argument does not hold.
+template <bool NEED_DIST>
+__device__ __forceinline__ int classify_pair_vis(const FaceRec& f, float px, float py, float blur, float sat, bool& inside,
+                                                 float& q, bool& exact_needed) {
+  inside = false;
+  exact_needed = false;
+  if (px > f.xmax || px < f.xmin || py > f.ymax || py < f.ymin) return PAIR_REJECT;
+  if (!(f.zmin > 0.f)) { exact_needed = true; return PAIR_FULL; }
+  float e0 = edge_fn(px, py, f.x1, f.y1, f.x2, f.y2);
+  float e1 = edge_fn(px, py, f.x2, f.y2, f.x0, f.y0);
+  float e2 = edge_fn(px, py, f.x0, f.y0, f.x1, f.y1);
+  bool pos = f.area > 0.f;
+  bool i0 = pos ? e0 > 0.f : e0 < 0.f, i1 = pos ? e1 > 0.f : e1 < 0.f, i2 = pos ? e2 > 0.f : e2 < 0.f;
+  if (i0 && i1 && i2) {
+    inside = true;
+    q = f.inv_area * (e0 * f.iz0 + e1 * f.iz1 + e2 * f.iz2);
+    if (NEED_DIST && e0 * e0 >= sat * f.l12 && e1 * e1 >= sat * f.l20 && e2 * e2 >= sat * f.l01) return PAIR_SATURATED;
+    return NEED_DIST ? PAIR_FULL : PAIR_SATURATED;
+  }
+  if (!NEED_DIST) return PAIR_REJECT;
+  float far = 1.001f * blur;
+  if ((!i0 && e0 * e0 >= far * f.l12) || (!i1 && e1 * e1 >= far * f.l20) || (!i2 && e2 * e2 >= far * f.l01)) return PAIR_REJECT;
   return PAIR_FULL;
 }
 
@@ -162,4 +191,6 @@ __device__ __forceinline__ void load_face(const harp_ctx& c, const float* ndc, i
   f.l20 = (f.x0 - f.x2) * (f.x0 - f.x2) + (f.y0 - f.y2) * (f.y0 - f.y2);
   f.l01 = (f.x1 - f.x0) * (f.x1 - f.x0) + (f.y1 - f.y0) * (f.y1 - f.y0);
   f.zmin = fminf(fminf(f.z0, f.z1), f.z2);
+  f.inv_area = 1.f / f.area;
+  f.iz0 = 1.f / f.z0; f.iz1 = 1.f / f.z1; f.iz2 = 1.f / f.z2;
 }

@@ -4,7 +4,7 @@
 // + normal-map bilinear fetches (TexturesUV), PBRMaterials.apply_normal_map (pbr_materials.py:58-124),
 // Lambert lighting (A.7), softmax_rgb_blend at K=1 (A.4); and their autograd graph.
 // One pass per pixel, nothing staged in HBM except the light-view depth/face buffers the PCF taps must read.
-#include "raster.cuh"
+#include "shade_pixel.cuh"
 
 int harp_build_bins(harp_ctx* c, int view, int B, int S, float radius, const float* ndc, cudaStream_t st);
 int harp_project(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R, const float* T, float* ndc,
@@ -17,25 +17,6 @@ namespace {
 
 constexpr int CHUNK = 64;
 constexpr int NT = HARP_TILE * HARP_TILE;
-
-struct ShadeArgs {
-  int B, S, self_shadow, texH, texW;
-  float focal, gscale, inv_n;
-  const float *verts, *normals, *ndc_cam, *light_R, *light_T, *light_pos, *amb, *texture, *normal_map;
-  const float* light_zbuf;
-  const int32_t *bin_count, *bin_start, *bin_list;
-  float* rgb;
-  const float *gin, *mask;
-  float* loss;
-  float *d_ndc_cam, *d_verts, *d_normals, *d_light_R, *d_light_T, *d_light_pos, *d_amb, *d_texture, *d_normal_map;
-  float* d_light_zbuf;
-};
-
-// nearest face covering the pixel centre: strict inside, smallest perspective-correct depth, ties -> lower face id
-struct Hit {
-  int fid;
-  float pz, b0, b1, b2, w0, w1, w2;
-};
 
 __device__ __forceinline__ void nearest_face(const harp_ctx& c, const float* ndc, const int32_t* list, int n, float px,
                                              float py, FaceRec* faces, Hit& h) {
@@ -80,38 +61,6 @@ __global__ void __launch_bounds__(NT) light_depth_kernel(harp_ctx c, int S, cons
   face[pix] = h.fid;
 }
 
-// ---- barycentric backward: grads of the perspective-correct barycentrics -> NDC xy and view z of the 3 face verts ------
-// b_i = t_i / sum(t), t_0 = w0 z1 z2 ..., w_i = e_i / A  (BarycentricPerspectiveCorrection / BarycentricCoords backward)
-__device__ __forceinline__ void bary_backward(const float* ndc, int v0, int v1, int v2, float px, float py, const Hit& h,
-                                              const float gb[3], float gz_direct[3], float* d_ndc) {
-  const float *A0 = ndc + (size_t)v0 * 3, *A1 = ndc + (size_t)v1 * 3, *A2 = ndc + (size_t)v2 * 3;
-  float x0 = A0[0], y0 = A0[1], z0 = A0[2], x1 = A1[0], y1 = A1[1], z1 = A1[2], x2 = A2[0], y2 = A2[1], z2 = A2[2];
-  float den = h.w0 * z1 * z2 + z0 * h.w1 * z2 + z0 * z1 * h.w2;
-  float gz0 = gz_direct[0], gz1 = gz_direct[1], gz2 = gz_direct[2];
-  float gw0 = 0.f, gw1 = 0.f, gw2 = 0.f;
-  if (den > HARP_K_EPS) {
-    float dotgb = gb[0] * h.b0 + gb[1] * h.b1 + gb[2] * h.b2;
-    float gt0 = (gb[0] - dotgb) / den, gt1 = (gb[1] - dotgb) / den, gt2 = (gb[2] - dotgb) / den;
-    gw0 = gt0 * z1 * z2; gz1 += gt0 * h.w0 * z2; gz2 += gt0 * h.w0 * z1;
-    gw1 = gt1 * z0 * z2; gz0 += gt1 * h.w1 * z2; gz2 += gt1 * z0 * h.w1;
-    gw2 = gt2 * z0 * z1; gz0 += gt2 * z1 * h.w2; gz1 += gt2 * z0 * h.w2;
-  }
-  float area = (x2 - x0) * (y1 - y0) - (y2 - y0) * (x1 - x0) + HARP_K_EPS;
-  float ge0 = gw0 / area, ge1 = gw1 / area, ge2 = gw2 / area;
-  float gA = -(gw0 * h.w0 + gw1 * h.w1 + gw2 * h.w2) / area;
-  // E(p,a,b) = (px-ax)(by-ay) - (py-ay)(bx-ax):  dE/da = (py-by, bx-px),  dE/db = (ay-py, px-ax)
-  // e0 = E(p,v1,v2), e1 = E(p,v2,v0), e2 = E(p,v0,v1);  A = E(v2,v0,v1) + eps
-  float gx0 = ge1 * (y2 - py) + ge2 * (py - y1) + gA * (y2 - y1);
-  float gy0 = ge1 * (px - x2) + ge2 * (x1 - px) + gA * (x1 - x2);
-  float gx1 = ge0 * (py - y2) + ge2 * (y0 - py) + gA * (y0 - y2);
-  float gy1 = ge0 * (x2 - px) + ge2 * (px - x0) + gA * (x2 - x0);
-  float gx2 = ge0 * (y1 - py) + ge1 * (py - y0) + gA * (y1 - y0);
-  float gy2 = ge0 * (px - x1) + ge1 * (x0 - px) + gA * (x0 - x1);
-  atomic_add4(d_ndc + (size_t)v0 * 4, gx0, gy0, gz0);
-  atomic_add4(d_ndc + (size_t)v1 * 4, gx1, gy1, gz1);
-  atomic_add4(d_ndc + (size_t)v2 * 4, gx2, gy2, gz2);
-}
-
 // backward of the light-view depth buffer: zbuf = sum_i b_i z_i at the stored face
 __global__ void __launch_bounds__(256) light_depth_bwd_kernel(harp_ctx c, int B, int S, const float* __restrict__ ndc_all,
                                                               const int32_t* __restrict__ face, const float* __restrict__ d_zbuf,
@@ -137,42 +86,6 @@ __global__ void __launch_bounds__(256) light_depth_bwd_kernel(harp_ctx c, int B,
   bary_backward(ndc, f.v0, f.v1, f.v2, px, py, h, gb, gz, d_ndc_all + (size_t)b * c.V * 4);
 }
 
-// ---- texture fetch: F.grid_sample(bilinear, align_corners=True, border) on the H-flipped map ------------
-struct Taps {
-  int idx[4];     // texel linear indices (row*W + col) in the ORIGINAL (unflipped) map: nw, ne, sw, se
-  float w[4];
-  float fx, fy;
-  float gmx, gmy; // d(ix)/du , d(iy)/dv including the border-clip mask
-};
-
-__device__ __forceinline__ void make_taps(float u, float v, int H, int W, Taps& t) {
-  float gx = u * 2.f - 1.f, gy = v * 2.f - 1.f;
-  float ix = ((gx + 1.f) / 2.f) * (float)(W - 1), iy = ((gy + 1.f) / 2.f) * (float)(H - 1);
-  t.gmx = (float)(W - 1); t.gmy = (float)(H - 1);
-  if (ix <= 0.f) { ix = 0.f; t.gmx = 0.f; } else if (ix >= (float)(W - 1)) { ix = (float)(W - 1); t.gmx = 0.f; }
-  if (iy <= 0.f) { iy = 0.f; t.gmy = 0.f; } else if (iy >= (float)(H - 1)) { iy = (float)(H - 1); t.gmy = 0.f; }
-  float x0 = floorf(ix), y0 = floorf(iy);
-  t.fx = ix - x0; t.fy = iy - y0;
-  int c0 = (int)x0, r0 = (int)y0;
-  int c1 = min(c0 + 1, W - 1), r1 = min(r0 + 1, H - 1);  // out-of-range taps carry zero weight
-  int R0 = H - 1 - r0, R1 = H - 1 - r1;                  // undo the flip
-  t.idx[0] = R0 * W + c0; t.idx[1] = R0 * W + c1; t.idx[2] = R1 * W + c0; t.idx[3] = R1 * W + c1;
-  t.w[0] = (1.f - t.fx) * (1.f - t.fy); t.w[1] = t.fx * (1.f - t.fy); t.w[2] = (1.f - t.fx) * t.fy; t.w[3] = t.fx * t.fy;
-}
-
-__device__ __forceinline__ f3 normalize12(f3 x) {  // F.normalize default eps = 1e-12
-  float l = fmaxf(sqrtf(dot(x, x)), 1e-12f);
-  return mk3(x.x / l, x.y / l, x.z / l);
-}
-__device__ __forceinline__ f3 normalize_bwd_eps(f3 x, f3 gy, float eps) {
-  float l = sqrtf(dot(x, x));
-  if (l > eps) {
-    f3 y = (1.f / l) * x;
-    return (1.f / l) * (gy - dot(y, gy) * y);
-  }
-  return (1.f / eps) * gy;
-}
-
 // MODE 0 forward; 1 backward with upstream g_rgb; 2 fused photometric L1 on the eroded mask
 template <int MODE>
 __global__ void __launch_bounds__(NT, (MODE == 0 ? 16 : 10)) shade_kernel(harp_ctx c, ShadeArgs a) {
@@ -190,200 +103,37 @@ __global__ void __launch_bounds__(NT, (MODE == 0 ? 16 : 10)) shade_kernel(harp_c
   Hit h;
   nearest_face(c, ndc, a.bin_list + (size_t)b * c.bin_cap + start, n, px, py, faces, h);
 
-  f3 rgb = mk3(1.f, 1.f, 1.f);  // background (renderer_helper.py:430)
-  // forward state kept for the backward half
-  int v0 = 0, v1 = 0, v2 = 0;
-  f3 P0, P1, P2, N0, N1, N2, P, N, tex, m, npre, n1, dvec, dh, n2;
-  float uvx[3], uvy[3];
-  Taps tp;
-  float amb = a.amb[0], cosang = 0.f, vis = 1.f, sh = 0.f, zL = 0.f, s_sign = 1.f, aa = 0.f;
-  f3 uvec, vvec;
-  int tapidx[9];
-  float tapsig[9];
-  const float* lR = a.light_R + (size_t)b * 9;
-  const float* lT = a.light_T + (size_t)b * 3;
-  f3 L = ld3(a.light_pos + (size_t)b * 3);
-  bool hit = h.fid >= 0;
-  if (hit) {
-    const int32_t* fv = c.faces + (size_t)h.fid * 3;
-    v0 = fv[0]; v1 = fv[1]; v2 = fv[2];
-    const float* vb = a.verts + (size_t)b * c.V * 3;
-    const float* nb = a.normals + (size_t)b * c.V * 3;
-    P0 = ld3(vb + (size_t)v0 * 3); P1 = ld3(vb + (size_t)v1 * 3); P2 = ld3(vb + (size_t)v2 * 3);
-    N0 = ld3(nb + (size_t)v0 * 3); N1 = ld3(nb + (size_t)v1 * 3); N2 = ld3(nb + (size_t)v2 * 3);
-    const float* fu = c.face_uvs + (size_t)h.fid * 6;
-    uvx[0] = fu[0]; uvy[0] = fu[1]; uvx[1] = fu[2]; uvy[1] = fu[3]; uvx[2] = fu[4]; uvy[2] = fu[5];
-    P = h.b0 * P0 + h.b1 * P1 + h.b2 * P2;
-    N = h.b0 * N0 + h.b1 * N1 + h.b2 * N2;
-    float u = h.b0 * uvx[0] + h.b1 * uvx[1] + h.b2 * uvx[2];
-    float v = h.b0 * uvy[0] + h.b1 * uvy[1] + h.b2 * uvy[2];
-    make_taps(u, v, a.texH, a.texW, tp);
-    tex = mk3(0.f, 0.f, 0.f);
-    m = mk3(0.f, 0.f, 0.f);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      tex = tex + tp.w[k] * ld3(a.texture + (size_t)tp.idx[k] * 3);
-      m = m + tp.w[k] * normalize12(ld3(a.normal_map + (size_t)tp.idx[k] * 3));
-    }
-    // PBRMaterials.compute_tangent / apply_normal_map on the (un-normalised) interpolated normal
-    s_sign = N.z >= 0.f ? 1.f : -1.f;
-    aa = -1.f / (s_sign + N.z);
-    float bb = N.x * N.y * aa;
-    uvec = mk3(1.f + s_sign * N.x * N.x * aa, s_sign * bb, -s_sign * N.x);
-    vvec = mk3(bb, s_sign + N.y * N.y * aa, -N.y);
-    npre = (-m.x) * uvec + (-m.y) * vvec + m.z * N;
-    n1 = normalize12(npre);
-    // lighting: F.normalize(eps=1e-6) on both, relu(dot)
-    float l1 = fmaxf(sqrtf(dot(n1, n1)), 1e-6f);
-    n2 = (1.f / l1) * n1;
-    dvec = L - P;
-    float ld = fmaxf(sqrtf(dot(dvec, dvec)), 1e-6f);
-    dh = (1.f / ld) * dvec;
-    cosang = fmaxf(dot(n2, dh), 0.f);
-    if (a.self_shadow) {
-      // hit point in light view space (row-vector: p R + T), its light-screen pixel, 3x3 clamped taps
-      float xl = P.x * lR[0] + P.y * lR[3] + P.z * lR[6] + lT[0];
-      float yl = P.x * lR[1] + P.y * lR[4] + P.z * lR[7] + lT[1];
-      zL = P.x * lR[2] + P.y * lR[5] + P.z * lR[8] + lT[2];
-      float hs = 0.5f * (float)S;
-      float xs = hs - hs * ((a.focal * xl / zL) / hs), ys = hs - hs * ((a.focal * yl / zL) / hs);
-      // .round().long(): round-half-even, then saturate like a float->int64 cast would never need to here
-      float xr = rintf(xs), yr = rintf(ys);
-      xr = fminf(fmaxf(xr, -2.f), (float)S + 1.f); yr = fminf(fmaxf(yr, -2.f), (float)S + 1.f);
-      int xk = (int)xr, yk = (int)yr;
-      const float* zb = a.light_zbuf + (size_t)b * S * S;
-      float acc = 0.f;
-#pragma unroll
-      for (int ii = -1; ii <= 1; ++ii)
-#pragma unroll
-        for (int jj = -1; jj <= 1; ++jj) {
-          int ry = min(max(yk + ii, 0), S - 1), rx = min(max(xk + jj, 0), S - 1);
-          int t = (ii + 1) * 3 + (jj + 1);
-          tapidx[t] = ry * S + rx;
-          float x = (zb[tapidx[t]] - (zL - 0.008f)) * 1000.f;
-          float sg = 1.f / (1.f + expf(-x));
-          tapsig[t] = sg;
-          acc += sg;
-        }
-      vis = acc / 9.f;
-    }
-    sh = amb + (1.f - amb) * cosang * vis;
-    rgb = sh * tex;
-    // softmax_rgb_blend with K=1: (prob c + delta bg)/(prob + delta), delta = 1e-10 -> equals c to < 1 ulp; kept implicit
-  }
-  if (MODE != 1) st3(a.rgb + pix * 3, rgb);
+  ShadeOut o;
+  shade_pixel<MODE>(c, a, b, pix, px, py, h, o);
+  if (MODE != 1) st3(a.rgb + pix * 3, o.rgb);
   if (MODE == 0) return;
-
-  f3 g;  // dL/d rgb
-  if (MODE == 1) {
-    g = ld3(a.gin + pix * 3);
-  } else {
-    float mk = a.mask[pix];
-    f3 y = ld3(a.gin + pix * 3);
-    f3 d = mk3(rgb.x * mk - y.x * mk, rgb.y * mk - y.y * mk, rgb.z * mk - y.z * mk);
-    float s = block_sum(fabsf(d.x) + fabsf(d.y) + fabsf(d.z), red);
+  if (MODE == 2) {
+    float s = block_sum(o.loss_abs, red);
     if (threadIdx.x == 0 && s != 0.f) atomicAdd(a.loss, s * a.inv_n);
-    auto sgn = [](float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); };
-    g = mk3(a.gscale * mk * sgn(d.x), a.gscale * mk * sgn(d.y), a.gscale * mk * sgn(d.z));
   }
-  float r_light[3] = {0.f, 0.f, 0.f}, r_amb = 0.f, r_lR[3] = {0.f, 0.f, 0.f}, r_lT = 0.f;
-  bool active = hit && (g.x != 0.f || g.y != 0.f || g.z != 0.f);
-  if (active) {
-    f3 g_tex = sh * g;
-    float g_sh = g.x * tex.x + g.y * tex.y + g.z * tex.z;
-    r_amb = g_sh * (1.f - cosang * vis);
-    float g_cos = cosang > 0.f ? g_sh * (1.f - amb) * vis : 0.f;
-    float g_vis = g_sh * (1.f - amb) * cosang;
-    f3 gP = mk3(0.f, 0.f, 0.f), gN = mk3(0.f, 0.f, 0.f);
-    // --- lighting ---
-    f3 g_n2 = g_cos * dh, g_dh = g_cos * n2;
-    f3 g_n1 = normalize_bwd_eps(n1, g_n2, 1e-6f);
-    f3 g_npre = normalize_bwd_eps(npre, g_n1, 1e-12f);
-    f3 g_d = normalize_bwd_eps(dvec, g_dh, 1e-6f);
-    r_light[0] = g_d.x; r_light[1] = g_d.y; r_light[2] = g_d.z;
-    gP = gP - g_d;
-    // --- normal map / TBN ---
-    f3 g_m = mk3(-dot(uvec, g_npre), -dot(vvec, g_npre), dot(N, g_npre));
-    gN = gN + m.z * g_npre;
-    f3 g_u = (-m.x) * g_npre, g_v = (-m.y) * g_npre;
-    {
-      float s = s_sign, x = N.x, y = N.y, a2 = aa * aa;
-      // u = (1 + s x^2 a, s x y a, -s x), v = (x y a, s + y^2 a, -y), a = -1/(s+z), da/dz = a^2
-      gN.x += g_u.x * (2.f * s * x * aa) + g_u.y * (s * y * aa) + g_u.z * (-s) + g_v.x * (y * aa);
-      gN.y += g_u.y * (s * x * aa) + g_v.x * (x * aa) + g_v.y * (2.f * y * aa) + g_v.z * (-1.f);
-      gN.z += g_u.x * (s * x * x * a2) + g_u.y * (s * x * y * a2) + g_v.x * (x * y * a2) + g_v.y * (y * y * a2);
-    }
-    // --- shadow ---
-    if (a.self_shadow && g_vis != 0.f) {
-      float gz = 0.f;
-      float* dzb = a.d_light_zbuf + (size_t)b * S * S;
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        float ga = g_vis / 9.f * tapsig[t] * (1.f - tapsig[t]) * 1000.f;
-        if (ga != 0.f) {
-          atomicAdd(dzb + tapidx[t], ga);
-          gz -= ga;
-        }
-      }
-      gP = gP + mk3(gz * lR[2], gz * lR[5], gz * lR[8]);
-      r_lR[0] = gz * P.x; r_lR[1] = gz * P.y; r_lR[2] = gz * P.z;
-      r_lT = gz;
-    }
-    // --- textures: value grads to the 4 taps, coordinate grads to uv ---
-    float g_u_tex = 0.f, g_v_tex = 0.f;
-    {
-      f3 t4[4], m4[4], mraw[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        t4[k] = ld3(a.texture + (size_t)tp.idx[k] * 3);
-        mraw[k] = ld3(a.normal_map + (size_t)tp.idx[k] * 3);
-        m4[k] = normalize12(mraw[k]);
-        if (tp.w[k] != 0.f) {
-          f3 gt = tp.w[k] * g_tex, gm = normalize_bwd_eps(mraw[k], tp.w[k] * g_m, 1e-12f);
-          atomic_add4(a.d_texture + (size_t)tp.idx[k] * 4, gt.x, gt.y, gt.z);
-          atomic_add4(a.d_normal_map + (size_t)tp.idx[k] * 4, gm.x, gm.y, gm.z);
-        }
-      }
-      // d out / d ix = (ne - nw)(1-fy) + (se - sw) fy ;  d out / d iy = (sw - nw)(1-fx) + (se - ne) fx
-      f3 dtx = (1.f - tp.fy) * (t4[1] - t4[0]) + tp.fy * (t4[3] - t4[2]);
-      f3 dty = (1.f - tp.fx) * (t4[2] - t4[0]) + tp.fx * (t4[3] - t4[1]);
-      f3 dmx = (1.f - tp.fy) * (m4[1] - m4[0]) + tp.fy * (m4[3] - m4[2]);
-      f3 dmy = (1.f - tp.fx) * (m4[2] - m4[0]) + tp.fx * (m4[3] - m4[1]);
-      g_u_tex = tp.gmx * (dot(g_tex, dtx) + dot(g_m, dmx));
-      g_v_tex = tp.gmy * (dot(g_tex, dty) + dot(g_m, dmy));
-    }
-    // --- interpolation: P, N, uv = sum_i b_i attr_i ---
-    float gb[3] = {dot(P0, gP) + dot(N0, gN) + uvx[0] * g_u_tex + uvy[0] * g_v_tex,
-                   dot(P1, gP) + dot(N1, gN) + uvx[1] * g_u_tex + uvy[1] * g_v_tex,
-                   dot(P2, gP) + dot(N2, gN) + uvx[2] * g_u_tex + uvy[2] * g_v_tex};
-    float* dvb = a.d_verts + (size_t)b * c.V * 4;   // padded (B,V,4) accumulators, folded after the kernel
-    float* dnb = a.d_normals + (size_t)b * c.V * 4;
-    atomic_add4(dvb + (size_t)v0 * 4, h.b0 * gP.x, h.b0 * gP.y, h.b0 * gP.z);
-    atomic_add4(dvb + (size_t)v1 * 4, h.b1 * gP.x, h.b1 * gP.y, h.b1 * gP.z);
-    atomic_add4(dvb + (size_t)v2 * 4, h.b2 * gP.x, h.b2 * gP.y, h.b2 * gP.z);
-    atomic_add4(dnb + (size_t)v0 * 4, h.b0 * gN.x, h.b0 * gN.y, h.b0 * gN.z);
-    atomic_add4(dnb + (size_t)v1 * 4, h.b1 * gN.x, h.b1 * gN.y, h.b1 * gN.z);
-    atomic_add4(dnb + (size_t)v2 * 4, h.b2 * gN.x, h.b2 * gN.y, h.b2 * gN.z);
-    float gz[3] = {0.f, 0.f, 0.f};
-    bary_backward(ndc, v0, v1, v2, px, py, h, gb, gz, a.d_ndc_cam + (size_t)b * c.V * 4);
-  }
-  // per-frame scalars: warp-reduce, one atomic per warp
-  int any = __syncthreads_or(active ? 1 : 0);
+  int any = __syncthreads_or(o.active ? 1 : 0);
   if (!any) return;
-  float vals[8] = {r_light[0], r_light[1], r_light[2], r_amb, r_lR[0], r_lR[1], r_lR[2], r_lT};
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    float s = warp_sum(vals[k]);
-    if ((threadIdx.x & 31) == 0 && s != 0.f) {
-      if (k < 3) { if (a.d_light_pos) atomicAdd(a.d_light_pos + (size_t)b * 3 + k, s); }
-      else if (k == 3) { if (a.d_amb) atomicAdd(a.d_amb, s); }
-      else if (k < 7) { if (a.d_light_R) atomicAdd(a.d_light_R + (size_t)b * 9 + (k - 4) * 3 + 2, s); }
-      else { if (a.d_light_T) atomicAdd(a.d_light_T + (size_t)b * 3 + 2, s); }
-    }
-  }
+  shade_flush_frame_scalars(a, b, o.frame);
 }
 
 }  // namespace
+// light-view depth pass / its backward on the ctx scratch (projected light-view verts and bins must be current)
+int harp_light_depth(harp_ctx* c, int B, int S, cudaStream_t st) {
+  dim3 grid(S / HARP_TILE, S / HARP_TILE, B);
+  size_t voff = (size_t)c->maxB * c->tiles;
+  light_depth_kernel<<<grid, NT, 0, st>>>(*c, S, c->ndc_light, c->bin_count + voff, c->bin_start + voff,
+                                          c->bin_list + (size_t)c->maxB * c->bin_cap, c->light_zbuf, c->light_face);
+  HARP_LAUNCH_CHECK();
+  return HARP_OK;
+}
+
+int harp_light_depth_bwd(harp_ctx* c, int B, int S, cudaStream_t st) {
+  size_t npx = (size_t)B * S * S;
+  light_depth_bwd_kernel<<<(int)((npx + 255) / 256), 256, 0, st>>>(*c, B, S, c->ndc_light, c->light_face, c->d_light_zbuf,
+                                                                   c->d_ndc_light);
+  HARP_LAUNCH_CHECK();
+  return HARP_OK;
+}
 
 extern "C" int harp_shade(harp_ctx* c, int mode, int B, int S, float focal, int self_shadow, const float* verts,
                           const float* normals, const float* cam_R, const float* cam_T, const float* light_R,

@@ -14,7 +14,7 @@ import ctypes as C
 import torch
 
 from . import _lib, camera
-from ._lib import HarpShadeGrads, check, ptr, stream
+from ._lib import HarpRenderArgs, HarpShadeGrads, check, ptr, stream
 
 # slots 1..5 are contiguous in harp_mesh_losses' output order
 LOSS_NAMES = ("silhouette", "laplacian", "normal", "arap", "kps_anchor", "vert_disp_reg", "photo", "albedo", "normal_reg")
@@ -176,34 +176,28 @@ class HarpFitter:
         d_cT = self._buf("d_cT", (B, 3))
         d_lR, d_lT, d_lpos, d_amb = self._buf("d_lR", (B, 3, 3)), self._buf("d_lT", (B, 3)), self._buf("d_lpos", (B, 3)), self._buf("d_amb", (1,))
         W = LOSS_WEIGHTS
-        # ---- silhouette (rendered in every stage, loss only while COARSE_OPT: 469-471, 517-519)
+        # ---- both renders (silhouette 469-471 and shadowed colour 474-488 run in every stage; their losses are gated by
+        #      COARSE_OPT / APP_OPT, 517-519 and 541-543) in one fused pixel pass
         alpha = self._buf("alpha", (B, S, S), zero=False)
-        if coarse_on:
-            check(L.harp_silhouette(hc.h, 2, B, S, focal, 1e-7, ptr(verts), ptr(cR), ptr(cTc), ptr(alpha), ptr(fr["y_sil"]),
-                                    W["silhouette"] * fscale, ptr(self.losses[_SLOT["silhouette"]:]), ptr(d_verts), None,
-                                    ptr(d_cT), st))
-        else:
-            check(L.harp_silhouette(hc.h, 0, B, S, focal, 1e-7, ptr(verts), ptr(cR), ptr(cTc), ptr(alpha), None, 0.0, None,
-                                    None, None, None, st))
-        # ---- colour render (474-488), photometric loss only while APP_OPT (541-543)
         rgb = self._buf("rgb", (B, S, S, 3), zero=False)
         tex, nm = A["texture"], A["normal_map"]
         H, Wd = tex.shape[-3], tex.shape[-2]
         ambc = amb.detach().contiguous()
+        gs = HarpShadeGrads(d_verts=ptr(d_verts), d_normals=ptr(d_normals), d_cam_R=None, d_cam_T=ptr(d_cT), d_light_R=ptr(d_lR),
+                            d_light_T=ptr(d_lT), d_light_pos=ptr(d_lpos), d_amb=ptr(d_amb),
+                            d_texture=ptr(self.app.g["texture"]), d_normal_map=ptr(self.app.g["normal_map"]))
+        ra = HarpRenderArgs(verts=ptr(verts), normals=ptr(normals), cam_R=ptr(cR), cam_T=ptr(cTc), light_R=ptr(lRc), light_T=ptr(lTc),
+                            light_pos=ptr(light_bc), amb=ptr(ambc), texture=ptr(tex), normal_map=ptr(nm), texH=H, texW=Wd,
+                            self_shadow=int(self.self_shadow), sigma=1e-7, y_sil=ptr(fr["y_sil"]), y_true=ptr(fr["y_true"]),
+                            y_mask=ptr(fr["y_sil_eroded"]), w_sil=W["silhouette"] * fscale if coarse_on else 0.0,
+                            w_photo=W["photo"] * fscale if app_on else 0.0, alpha=ptr(alpha), rgb=ptr(rgb),
+                            loss_sil=ptr(self.losses[_SLOT["silhouette"]:]), loss_photo=ptr(self.losses[_SLOT["photo"]:]), grads=gs)
+        check(L.harp_render_fused(hc.h, B, S, focal, C.byref(ra), st))
         if app_on:
-            gs = HarpShadeGrads(d_verts=ptr(d_verts), d_normals=ptr(d_normals), d_cam_R=None, d_cam_T=ptr(d_cT), d_light_R=ptr(d_lR),
-                                d_light_T=ptr(d_lT), d_light_pos=ptr(d_lpos), d_amb=ptr(d_amb),
-                                d_texture=ptr(self.app.g["texture"]), d_normal_map=ptr(self.app.g["normal_map"]))
-            check(L.harp_shade(hc.h, 2, B, S, focal, int(self.self_shadow), ptr(verts), ptr(normals), ptr(cR), ptr(cTc), ptr(lRc),
-                               ptr(lTc), ptr(light_bc), ptr(ambc), ptr(tex), ptr(nm), H, Wd, ptr(rgb), ptr(fr["y_true"]),
-                               ptr(fr["y_sil_eroded"]), W["photo"] * fscale, ptr(self.losses[_SLOT["photo"]:]), C.byref(gs), st))
             check(L.harp_texture_reg(hc.h, 0, ptr(tex), H, Wd, ptr(off_albedo), ptr(self.uv_mask), W["albedo"] * fscale,
                                      ptr(self.losses[_SLOT["albedo"]:]), ptr(self.app.g["texture"]), st))
             check(L.harp_texture_reg(hc.h, 1, ptr(nm), H, Wd, ptr(off_normal), ptr(self.uv_mask), W["normal_reg"] * fscale,
                                      ptr(self.losses[_SLOT["normal_reg"]:]), ptr(self.app.g["normal_map"]), st))
-        else:
-            check(L.harp_shade(hc.h, 0, B, S, focal, int(self.self_shadow), ptr(verts), ptr(normals), ptr(cR), ptr(cTc), ptr(lRc),
-                               ptr(lTc), ptr(light_bc), ptr(ambc), ptr(tex), ptr(nm), H, Wd, ptr(rgb), None, None, 0.0, None, None, st))
         # ---- mesh regularisers + keypoint anchor (521-539)
         if coarse_on:
             w5 = (C.c_float * 5)(W["laplacian"] * fscale, W["normal"] * fscale, W["arap"] * fscale, W["kps_anchor"] * fscale,

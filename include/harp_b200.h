@@ -153,6 +153,27 @@ HARP_API int harp_shade(harp_ctx*, int mode, int B, int S, float focal, int self
                int texW, float* rgb, const float* g_or_target, const float* mask, float weight, float* loss,
                const harp_shade_grads* grads, void* stream);
 
+/* ---- fused pixel pass of the optimiser step --------------------------------------------------------------------------
+ * harp_silhouette(mode 2) + harp_shade(mode 2) in one launch sequence that walks every tile's face list ONCE (silhouette
+ * factors and nearest-face visibility together), compacts hit pixels per frame and shades them with full warps.
+ * w_sil / w_photo: loss weights; 0 renders that image forward-only (the reference renders both in every stage,
+ * optimize_sequence.py:469-488).  Losses (device scalars) receive the unweighted means; gradients are accumulated. */
+typedef struct {
+  const float *verts, *normals;                       /* (B,V,3) */
+  const float *cam_R, *cam_T, *light_R, *light_T;     /* (B,3,3), (B,3) */
+  const float *light_pos, *amb;                       /* (B,3), (1) post-sigmoid */
+  const float *texture, *normal_map;                  /* (H,W,3) shared maps, normal_map raw */
+  int32_t texH, texW, self_shadow;
+  float sigma;                                        /* silhouette blend sigma (1e-7) */
+  const float *y_sil, *y_true, *y_mask;               /* targets: (B,S,S), (B,S,S,3), eroded mask (B,S,S) */
+  float w_sil, w_photo;
+  float *alpha, *rgb;                                 /* (B,S,S), (B,S,S,3) */
+  float *loss_sil, *loss_photo;
+  harp_shade_grads grads;
+} harp_render_args;
+
+HARP_API int harp_render_fused(harp_ctx*, int B, int S, float focal, const harp_render_args* args, void* stream);
+
 /* ---- texture regularisers: albedo_reg / normal_reg (loss/texture_reg.py:5-66) ----------------------------------------
  * offsets (H,W,2) int32 = the reference's CPU-RNG neighbour offsets, passed in.  kind 0: albedo_reg; 1: normal_reg
  * (adds 0.2*close_to_z with the reference's dim=2 norm).  loss accumulated (unweighted); d_map accumulated. */
