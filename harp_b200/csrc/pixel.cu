@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(NT) pixel_vis_kernel(harp_ctx c, VisArgs a) {
         inside = e.pass;
         q = e.pass ? 1.f / e.pz : 0.f;
       }
-      if (inside && (q > best_q || (q == best_q && (best_fid < 0 || f.fid < best_fid)))) { best_q = q; best_fid = f.fid; }
+      if (inside) vis_update(c, ndc, px, py, f.fid, q, best_fid, best_q);
       if (nzero > 0) continue;
       if (cls == PAIR_SATURATED) { ++npass; ++nzero; continue; }
       int slot = atomicAdd(&q_n, 1);

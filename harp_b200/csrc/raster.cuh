@@ -95,7 +95,8 @@ __device__ __forceinline__ int classify_pair(const FaceRec& f, float px, float p
 }
 
 // Same classification, additionally reporting strict-inside and q = 1 / (perspective-correct depth) for inside pairs:
-// with w_i = e_i / area and b_i ~ w_i / z_i, pz = sum b_i z_i = 1 / sum(w_i / z_i).  q orders the faces covering a pixel
+// with w_i = e_i / area and b_i ~ w_i / z_i, pz = sum b_i z_i = sum(w_i) / sum(w_i / z_i) = sum(e_i) / sum(e_i / z_i) (the
+// screen-space weights of a sliver face need not sum to 1 in fp32, hence the normalisation).  q orders the faces covering a pixel
 // (nearest = largest q); the winner's barycentrics and depth are then recomputed with the exact operation sequence.
 // `exact_needed` is set for faces with a vertex behind the camera, where the sign argument does not hold.
 template <bool NEED_DIST>
@@ -112,7 +113,7 @@ __device__ __forceinline__ int classify_pair_vis(const FaceRec& f, float px, flo
   bool i0 = pos ? e0 > 0.f : e0 < 0.f, i1 = pos ? e1 > 0.f : e1 < 0.f, i2 = pos ? e2 > 0.f : e2 < 0.f;
   if (i0 && i1 && i2) {
     inside = true;
-    q = f.inv_area * (e0 * f.iz0 + e1 * f.iz1 + e2 * f.iz2);
+    q = __fdividef(e0 * f.iz0 + e1 * f.iz1 + e2 * f.iz2, e0 + e1 + e2);  // = sum(w_i/z_i) / sum(w_i): independent of the area
     if (NEED_DIST && e0 * e0 >= sat * f.l12 && e1 * e1 >= sat * f.l20 && e2 * e2 >= sat * f.l01) return PAIR_SATURATED;
     return NEED_DIST ? PAIR_FULL : PAIR_SATURATED;
   }
@@ -193,4 +194,25 @@ __device__ __forceinline__ void load_face(const harp_ctx& c, const float* ndc, i
   f.zmin = fminf(fminf(f.z0, f.z1), f.z2);
   f.inv_area = 1.f / f.area;
   f.iz0 = 1.f / f.z0; f.iz1 = 1.f / f.z1; f.iz2 = 1.f / f.z2;
+}
+
+// Visibility candidate update.  The fast inverse depth q orders candidates; when two are within 1e-5 relative (touching
+// or interpenetrating surfaces) the decision is taken with the exact perspective-correct depth, ties to the lower face
+// id — the order PyTorch3D's K=1 insertion produces.
+__device__ __forceinline__ float exact_pz(const harp_ctx& c, const float* ndc, int fid, float px, float py) {
+  FaceRec g;
+  load_face(c, ndc, fid, 0.f, g);
+  PairEval e;
+  eval_pair_full<false, false>(g, px, py, 0.f, e);
+  return e.pass ? e.pz : 3.4e38f;
+}
+
+__device__ __forceinline__ void vis_update(const harp_ctx& c, const float* ndc, float px, float py, int fid, float q, int& best,
+                                           float& best_q) {
+  if (best < 0) { best = fid; best_q = q; return; }
+  float tol = 1e-5f * fmaxf(q, best_q);
+  if (q > best_q + tol) { best = fid; best_q = q; return; }
+  if (q < best_q - tol) return;
+  float pz_new = exact_pz(c, ndc, fid, px, py), pz_old = exact_pz(c, ndc, best, px, py);
+  if (pz_new < pz_old || (pz_new == pz_old && fid < best)) { best = fid; best_q = q; }
 }

@@ -20,24 +20,37 @@ constexpr int NT = HARP_TILE * HARP_TILE;
 
 __device__ __forceinline__ void nearest_face(const harp_ctx& c, const float* ndc, const int32_t* list, int n, float px,
                                              float py, FaceRec* faces, Hit& h) {
-  h.fid = -1;
-  h.pz = 3.4e38f;
+  // ordering by the fast inverse depth q (raster.cuh: classify_pair_vis); the winner is re-evaluated exactly below
+  int best = -1;
+  float best_q = 0.f;
   for (int base = 0; base < n; base += CHUNK) {
     int m = min(CHUNK, n - base);
     __syncthreads();
     if (threadIdx.x < m) load_face(c, ndc, list[base + threadIdx.x], 0.f, faces[threadIdx.x]);
     __syncthreads();
     for (int i = 0; i < m; ++i) {
-      PairEval e;
-      eval_pair<false, false>(faces[i], px, py, 0.f, 0.f, e);
-      if (!e.pass) continue;
-      int fid = faces[i].fid;
-      if (e.pz < h.pz || (e.pz == h.pz && fid < h.fid)) {
-        h.fid = fid; h.pz = e.pz;
-        h.b0 = e.b0; h.b1 = e.b1; h.b2 = e.b2;
-        h.w0 = e.w0; h.w1 = e.w1; h.w2 = e.w2;
+      const FaceRec& f = faces[i];
+      bool inside, exact;
+      float q;
+      if (classify_pair_vis<false>(f, px, py, 0.f, 0.f, inside, q, exact) == PAIR_REJECT) continue;
+      if (exact) {
+        PairEval e;
+        eval_pair_full<false, false>(f, px, py, 0.f, e);
+        inside = e.pass;
+        q = e.pass ? 1.f / e.pz : 0.f;
       }
+      if (inside) vis_update(c, ndc, px, py, f.fid, q, best, best_q);
     }
+  }
+  h.fid = best;
+  h.pz = 3.4e38f;
+  if (best >= 0) {
+    FaceRec f;
+    load_face(c, ndc, best, 0.f, f);
+    PairEval e;
+    eval_pair_full<false, false>(f, px, py, 0.f, e);
+    if (e.pass) { h.pz = e.pz; h.b0 = e.b0; h.b1 = e.b1; h.b2 = e.b2; h.w0 = e.w0; h.w1 = e.w1; h.w2 = e.w2; }
+    else h.fid = -1;
   }
 }
 
