@@ -25,6 +25,13 @@ class HarpManoModel(C.Structure):
                 ("J_regressor", c_float_p), ("weights", c_float_p), ("hands_mean", c_float_p), ("tips", c_int32_p)]
 
 
+class HarpLbsModel(C.Structure):
+    _fields_ = [("J", C.c_int32), ("n_shape", C.c_int32), ("parents", c_int32_p), ("shapedirs", c_float_p),
+                ("posedirs", c_float_p), ("v_template", c_float_p), ("J_template", c_float_p), ("J_shapedirs", c_float_p),
+                ("weights", c_float_p), ("pose_mean", c_float_p), ("rodrigues_kind", C.c_int32), ("center_joint", C.c_int32),
+                ("n_joints_out", C.c_int32), ("joint_out_src", c_int32_p), ("n_tips", C.c_int32), ("tips", c_int32_p)]
+
+
 class HarpShadeGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("d_verts", "d_normals", "d_cam_R", "d_cam_T", "d_light_R", "d_light_T",
                                           "d_light_pos", "d_amb", "d_texture", "d_normal_map")]
@@ -45,7 +52,7 @@ class HarpError(RuntimeError):
 _lib = None
 
 # every symbol include/harp_b200.h declares (tests/test_abi.py checks the library exports exactly these)
-SYMBOLS = ["harp_last_error", "harp_version", "harp_launch_count", "harp_ctx_profile", "harp_ctx_profile_read", "harp_ctx_create", "harp_ctx_destroy", "harp_ctx_reserve", "harp_ctx_dims",
+SYMBOLS = ["harp_last_error", "harp_version", "harp_launch_count", "harp_ctx_profile", "harp_ctx_profile_read", "harp_ctx_create", "harp_ctx_create_lbs", "harp_ctx_destroy", "harp_lbs_fwd", "harp_lbs_bwd", "harp_ctx_reserve", "harp_ctx_dims",
            "harp_ctx_faces", "harp_ctx_read_counters", "harp_lbs_mano_fwd", "harp_lbs_mano_bwd", "harp_mesh_build_fwd",
            "harp_mesh_build_bwd", "harp_vertex_normals_fwd", "harp_vertex_normals_bwd", "harp_mesh_losses", "harp_silhouette", "harp_shade", "harp_render_fused", "harp_texture_reg", "harp_adam", "harp_adam_dev"]
 
@@ -66,6 +73,9 @@ def lib():
         vp, i, f = C.c_void_p, C.c_int, C.c_float
         L.harp_ctx_create.argtypes = [C.POINTER(vp), C.POINTER(HarpTopology), C.POINTER(HarpManoModel)]
         L.harp_ctx_destroy.argtypes = [vp]
+        L.harp_ctx_create_lbs.argtypes = [C.POINTER(vp), C.POINTER(HarpTopology), C.POINTER(HarpLbsModel)]
+        L.harp_lbs_fwd.argtypes = [vp, i, vp, vp, i, vp, vp, vp, vp]
+        L.harp_lbs_bwd.argtypes = [vp, i, vp, vp, i, vp, vp, vp, vp, vp, vp, vp]
         L.harp_ctx_reserve.argtypes = [vp, i, i]
         L.harp_ctx_dims.argtypes = [vp, c_int32_p, c_int32_p, c_int32_p, c_int32_p]
         L.harp_ctx_faces.argtypes = [vp, c_int32_p]

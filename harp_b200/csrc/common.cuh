@@ -60,11 +60,13 @@ struct harp_ctx {
   int32_t* edges = nullptr;      // (E,2) final edges, PyTorch3D edges_packed order
   int32_t* nc_pairs = nullptr;   // (NP,4): v0, v1 of the shared edge, opposite verts a, b
   float* face_uvs = nullptr;     // (F,3,2)
-  // MANO model
-  float *shapedirs = nullptr, *posedirs = nullptr, *v_template = nullptr, *weights = nullptr, *hands_mean = nullptr;
-  float* weightsT = nullptr;      // (16,V0) transposed skinning weights
-  float *J_template = nullptr, *J_shapedirs = nullptr;  // (16,3), (16,3,10) = J_regressor folded
-  int32_t* tips = nullptr;
+  // skinning model (MANO: J=16, n_shape=10; SMPL-X arm: J=55, n_shape=10)
+  int J = 0, n_shape = 0, rodrigues_kind = 0, center_joint = -1, n_joints_out = 0, n_tips = 0;
+  float *shapedirs = nullptr, *posedirs = nullptr;      // transposed: (n_shape, 3 V0), ((J-1)*9, 3 V0)
+  float *v_template = nullptr, *weights = nullptr, *pose_mean = nullptr;
+  float* weightsT = nullptr;      // (J,V0) transposed skinning weights
+  float *J_template = nullptr, *J_shapedirs = nullptr;  // (J,3), (J,3,n_shape) = J_regressor folded
+  int32_t *tips = nullptr, *parents = nullptr, *joint_out_src = nullptr;
   // scratch (harp_ctx_reserve)
   int maxB = 0, S = 0, tiles = 0;
   int64_t bin_cap = 0;            // bin list capacity per frame

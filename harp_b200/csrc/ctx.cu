@@ -110,7 +110,7 @@ void csr_from_lists(const std::vector<std::vector<int32_t>>& lists, std::vector<
 
 }  // namespace
 
-extern "C" int harp_ctx_create(harp_ctx** out, const harp_topology* topo, const harp_mano_model* model) {
+extern "C" int harp_ctx_create_lbs(harp_ctx** out, const harp_topology* topo, const harp_lbs_model* model) {
   HARP_REQUIRE(out && topo && topo->faces0 && topo->V0 > 0 && topo->F0 > 0, HARP_ERR_INVALID, "harp_ctx_create: bad topology");
   harp_ctx* c = new harp_ctx();
   c->V0 = topo->V0;
@@ -194,39 +194,33 @@ extern "C" int harp_ctx_create(harp_ctx** out, const harp_topology* topo, const 
     c->has_uv = true;
   }
   if (model) {
-    int V0 = c->V0;
-    std::vector<float> sd(model->shapedirs, model->shapedirs + (size_t)V0 * 30);
-    std::vector<float> pd(model->posedirs, model->posedirs + (size_t)V0 * 405);
+    int V0 = c->V0, J = model->J, NS = model->n_shape, NP = (J - 1) * 9;
+    bool ok = J >= 1 && J <= HARP_MAX_JOINTS && NS >= 0 && NS <= HARP_MAX_SHAPE && model->parents && model->shapedirs &&
+              model->posedirs && model->v_template && model->J_template && model->J_shapedirs && model->weights &&
+              model->pose_mean && model->n_joints_out >= 0 && model->n_joints_out <= 512 && (model->n_tips == 0 || model->tips);
+    for (int j = 1; ok && j < J; ++j) ok = model->parents[j] >= 0 && model->parents[j] < j;
+    for (int i = 0; ok && i < model->n_tips; ++i) ok = model->tips[i] >= 0 && model->tips[i] < V0;
+    for (int i = 0; ok && i < model->n_joints_out; ++i) ok = model->joint_out_src[i] >= 0 && model->joint_out_src[i] < J + model->n_tips;
+    if (!ok) { harp_ctx_destroy(c); harp_set_error("harp_ctx_create: invalid skinning model"); return HARP_ERR_INVALID; }
+    c->J = J; c->n_shape = NS; c->rodrigues_kind = model->rodrigues_kind; c->center_joint = model->center_joint;
+    c->n_joints_out = model->n_joints_out; c->n_tips = model->n_tips;
     std::vector<float> vt(model->v_template, model->v_template + (size_t)V0 * 3);
-    std::vector<float> w(model->weights, model->weights + (size_t)V0 * 16);
-    std::vector<float> hm(model->hands_mean, model->hands_mean + 45);
-    std::vector<int32_t> tips(model->tips, model->tips + 5);
-    // fold the joint regressor: J(beta) = Jreg v_template + (Jreg shapedirs) beta   (manolayer.py:185-188)
-    std::vector<float> Jt(48, 0.f), Js(480, 0.f);
-    for (int j = 0; j < 16; ++j)
-      for (int v = 0; v < V0; ++v) {
-        double r = model->J_regressor[(size_t)j * V0 + v];
-        if (r == 0.0) continue;
-        for (int k = 0; k < 3; ++k) {
-          Jt[j * 3 + k] += (float)(r * vt[v * 3 + k]);
-          for (int b = 0; b < 10; ++b) Js[(j * 3 + k) * 10 + b] += (float)(r * sd[(v * 3 + k) * 10 + b]);
-        }
-      }
-    // (the float accumulation above runs in double per term; tiny vs the fp32 reference's own summation order)
+    std::vector<float> w(model->weights, model->weights + (size_t)V0 * J);
+    std::vector<float> pm(model->pose_mean, model->pose_mean + (size_t)J * 3);
+    std::vector<float> Jt(model->J_template, model->J_template + (size_t)J * 3);
+    std::vector<float> Js(model->J_shapedirs, model->J_shapedirs + (size_t)J * 3 * NS);
+    std::vector<int32_t> tips(model->tips, model->tips + model->n_tips), par(model->parents, model->parents + J);
+    std::vector<int32_t> jsrc(model->joint_out_src, model->joint_out_src + model->n_joints_out);
     // blendshape tables are stored transposed, (k, V0*3), so that a thread-per-vertex loop reads coalesced
-    std::vector<float> sdT((size_t)V0 * 30), pdT((size_t)V0 * 405);
+    std::vector<float> sdT((size_t)V0 * 3 * NS), pdT((size_t)V0 * 3 * NP), wT((size_t)V0 * J);
     for (int i = 0; i < V0 * 3; ++i) {
-      for (int b = 0; b < 10; ++b) sdT[(size_t)b * V0 * 3 + i] = sd[(size_t)i * 10 + b];
-      for (int k = 0; k < 135; ++k) pdT[(size_t)k * V0 * 3 + i] = pd[(size_t)i * 135 + k];
+      for (int b = 0; b < NS; ++b) sdT[(size_t)b * V0 * 3 + i] = model->shapedirs[(size_t)i * NS + b];
+      for (int k = 0; k < NP; ++k) pdT[(size_t)k * V0 * 3 + i] = model->posedirs[(size_t)i * NP + k];
     }
-    sd.swap(sdT);
-    pd.swap(pdT);
-    std::vector<float> wT((size_t)V0 * 16);
     for (int v = 0; v < V0; ++v)
-      for (int j = 0; j < 16; ++j) wT[(size_t)j * V0 + v] = w[(size_t)v * 16 + j];
-    UP(weightsT, wT);
-    UP(shapedirs, sd); UP(posedirs, pd); UP(v_template, vt); UP(weights, w); UP(hands_mean, hm); UP(tips, tips);
-    UP(J_template, Jt); UP(J_shapedirs, Js);
+      for (int j = 0; j < J; ++j) wT[(size_t)j * V0 + v] = w[(size_t)v * J + j];
+    UP(weightsT, wT); UP(shapedirs, sdT); UP(posedirs, pdT); UP(v_template, vt); UP(weights, w); UP(pose_mean, pm);
+    UP(tips, tips); UP(parents, par); UP(joint_out_src, jsrc); UP(J_template, Jt); UP(J_shapedirs, Js);
     c->has_model = true;
   }
 #undef UP
@@ -256,8 +250,9 @@ extern "C" void harp_ctx_destroy(harp_ctx* c) {
   if (!c) return;
   free_scratch(c);
   void* ptrs[] = {c->faces, c->edges0, c->v0e_off, c->v0e_idx, c->vf_off, c->vf_idx, c->vn_off, c->vn_idx, c->edges,
-                  c->nc_pairs, c->face_uvs, c->shapedirs, c->posedirs, c->v_template, c->weights, c->hands_mean,
-                  c->J_template, c->J_shapedirs, c->tips, c->counters, c->d_tex4, c->weightsT};
+                  c->nc_pairs, c->face_uvs, c->shapedirs, c->posedirs, c->v_template, c->weights,
+                  c->J_template, c->J_shapedirs, c->tips, c->counters, c->d_tex4, c->weightsT, c->pose_mean, c->parents,
+                  c->joint_out_src};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->prof) {
     for (auto& v : c->prof->ev) for (cudaEvent_t e : v) cudaEventDestroy(e);
@@ -328,4 +323,35 @@ extern "C" int harp_ctx_read_counters(harp_ctx* c, int64_t out[2], void* stream)
   out[0] = (int64_t)h[0];
   out[1] = (int64_t)h[1];
   return HARP_OK;
+}
+
+// MANO (manopth/manolayer.py:70-97) as an instance of the generic model: fold the joint regressor,
+// J(beta) = Jreg v_template + (Jreg shapedirs) beta (manolayer.py:185-188), kinematic tree of manolayer.py:209-242,
+// 21 output joints = 16 chain joints + 5 fingertip vertices in the order of manolayer.py:279.
+extern "C" int harp_ctx_create(harp_ctx** out, const harp_topology* topo, const harp_mano_model* m) {
+  if (!m) return harp_ctx_create_lbs(out, topo, nullptr);
+  HARP_REQUIRE(out && topo && topo->V0 > 0, HARP_ERR_INVALID, "harp_ctx_create: bad topology");
+  HARP_REQUIRE(m->shapedirs && m->posedirs && m->v_template && m->J_regressor && m->weights && m->hands_mean && m->tips,
+               HARP_ERR_INVALID, "harp_ctx_create: incomplete MANO model");
+  int V0 = topo->V0;
+  std::vector<double> Jt(48, 0.0), Js(480, 0.0);
+  for (int j = 0; j < 16; ++j)
+    for (int v = 0; v < V0; ++v) {
+      double r = m->J_regressor[(size_t)j * V0 + v];
+      if (r == 0.0) continue;
+      for (int k = 0; k < 3; ++k) {
+        Jt[j * 3 + k] += r * m->v_template[v * 3 + k];
+        for (int b = 0; b < 10; ++b) Js[(j * 3 + k) * 10 + b] += r * m->shapedirs[((size_t)v * 3 + k) * 10 + b];
+      }
+    }
+  std::vector<float> Jtf(Jt.begin(), Jt.end()), Jsf(Js.begin(), Js.end()), pm(48, 0.f);
+  for (int i = 0; i < 45; ++i) pm[3 + i] = m->hands_mean[i];
+  const int32_t parents[16] = {-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 0, 10, 11, 0, 13, 14};
+  const int32_t jsrc[21] = {0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20};
+  harp_lbs_model g{};
+  g.J = 16; g.n_shape = 10; g.parents = parents; g.shapedirs = m->shapedirs; g.posedirs = m->posedirs;
+  g.v_template = m->v_template; g.J_template = Jtf.data(); g.J_shapedirs = Jsf.data(); g.weights = m->weights;
+  g.pose_mean = pm.data(); g.rodrigues_kind = 0; g.center_joint = -1; g.n_joints_out = 21; g.joint_out_src = jsrc;
+  g.n_tips = 5; g.tips = m->tips;
+  return harp_ctx_create_lbs(out, topo, &g);
 }

@@ -254,12 +254,14 @@ __global__ void __launch_bounds__(TPB) normal_consistency_kernel(harp_ctx c, int
 }
 
 // root-aligned keypoint anchor, (mm/100)^2 (loss/kps_loss.py:4-17): one warp per frame
-__global__ void kps_kernel(int B, const float* __restrict__ joints_m, const float* __restrict__ init_mm, float w,
+// `nj`: joints per frame in joints_m / d_joints (21 for MANO; 22 for the SMPL-X arm, whose first 21 are compared:
+// kps_loss(use_arm=True) slices pred_kps[:, :21], loss/kps_loss.py:7-8)
+__global__ void kps_kernel(int B, int nj, const float* __restrict__ joints_m, const float* __restrict__ init_mm, float w,
                            float* __restrict__ loss, float* __restrict__ d_joints) {
   int b = blockIdx.x, j = threadIdx.x;
   float val = 0.f;
   f3 g = mk3(0.f, 0.f, 0.f);
-  const float* J = joints_m + (size_t)b * 63;
+  const float* J = joints_m + (size_t)b * nj * 3;
   const float* G = init_mm + (size_t)b * 63;
   float scale = 1.f / (21.f * (float)B);
   if (j < 21) {
@@ -274,7 +276,7 @@ __global__ void kps_kernel(int B, const float* __restrict__ joints_m, const floa
   val = warp_sum(val);
   if (d_joints && j < 21) {
     f3 o = j == 0 ? g - mk3(gx, gy, gz) : g;
-    float* dj = d_joints + ((size_t)b * 21 + j) * 3;
+    float* dj = d_joints + ((size_t)b * nj + j) * 3;
     dj[0] += o.x; dj[1] += o.y; dj[2] += o.z;
   }
   if (j == 0) atomicAdd(loss, val);
@@ -358,7 +360,8 @@ extern "C" int harp_mesh_losses(harp_ctx* c, int B, const float* verts, const fl
   laplacian_kernel<<<nblk((size_t)B * c->V), TPB, 0, st>>>(*c, B, verts, w[0], losses + 0, d_verts);
   if (c->NP > 0) normal_consistency_kernel<<<nblk((size_t)B * c->NP), TPB, 0, st>>>(*c, B, verts, w[1], losses + 1, d_verts);
   if (ref_verts) arap_kernel<<<nblk((size_t)B * c->E), TPB, 0, st>>>(*c, B, verts, ref_verts, w[2], losses + 2, d_verts);
-  if (joints && init_joints_mm) kps_kernel<<<B, 32, 0, st>>>(B, joints, init_joints_mm, w[3], losses + 3, d_joints);
+  if (joints && init_joints_mm)
+    kps_kernel<<<B, 32, 0, st>>>(B, c->n_joints_out >= 21 ? c->n_joints_out : 21, joints, init_joints_mm, w[3], losses + 3, d_joints);
   if (disps) disp_reg_kernel<<<nblk(c->V), TPB, 0, st>>>(c->V, disps, w[4], losses + 4, d_disps);
   HARP_LAUNCH_CHECK_N(1 + (c->NP > 0) + (ref_verts != nullptr) + (joints && init_joints_mm) + (disps != nullptr));
   return HARP_OK;

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import HarpManoModel, HarpShadeGrads, HarpTopology, check, ptr, stream
+from ._lib import HarpLbsModel, HarpManoModel, HarpShadeGrads, HarpTopology, check, ptr, stream
 
 
 def _np_f32(a):
@@ -33,14 +33,21 @@ class HarpContext:
 
     faces0: (F0,3) coarse faces (`ManoLayer.th_faces`); subdivide: apply one SubdivideMeshes step
     (`optimize_sequence.py:67-89`); faces_uvs/verts_uvs: template UV tables (`utils/hand_model_utils.py:59-61`);
-    mano: dict with the buffers registered at `manopth/manolayer.py:70-97` (+ 'tips')."""
+    mano: dict with the buffers registered at `manopth/manolayer.py:70-97` (+ 'tips');
+    lbs: generic skinning model dict (`harp_lbs_model` of include/harp_b200.h, e.g. `synth.reduce_smplx_arm`) for the
+    SMPL-X arm of `hand_models_harp/body_models.py:SMPLXARM`."""
 
-    def __init__(self, faces0, subdivide=True, faces_uvs=None, verts_uvs=None, mano=None, device="cuda:0"):
+    def __init__(self, faces0, subdivide=True, faces_uvs=None, verts_uvs=None, mano=None, lbs=None, device="cuda:0"):
         self.device = torch.device(device)
         L = _lib.lib()
         faces0 = _np_i32(faces0)
         topo = HarpTopology()
-        topo.V0 = int(faces0.max()) + 1 if mano is None else int(np.asarray(mano["th_v_template"]).reshape(-1, 3).shape[0])
+        if mano is not None:
+            topo.V0 = int(np.asarray(mano["th_v_template"]).reshape(-1, 3).shape[0])
+        elif lbs is not None:
+            topo.V0 = int(np.asarray(lbs["v_template"]).shape[0])
+        else:
+            topo.V0 = int(faces0.max()) + 1
         topo.F0 = faces0.shape[0]
         topo.faces0 = _ip(faces0)
         topo.subdivide = int(bool(subdivide))
@@ -60,13 +67,28 @@ class HarpContext:
             model_p = C.byref(m)
             keep += list(arrs.values()) + [tips]
         h = C.c_void_p()
-        with torch.cuda.device(self.device):
-            check(L.harp_ctx_create(C.byref(h), C.byref(topo), model_p))
+        if lbs is not None:
+            a = {k: _np_f32(lbs[k]) for k in ("shapedirs", "posedirs", "v_template", "J_template", "J_shapedirs", "weights", "pose_mean")}
+            ia = {k: _np_i32(lbs[k]) for k in ("parents", "joint_out_src", "tips")}
+            g = HarpLbsModel(J=int(lbs["J"]), n_shape=int(lbs["n_shape"]), parents=_ip(ia["parents"]), shapedirs=_fp(a["shapedirs"]),
+                             posedirs=_fp(a["posedirs"]), v_template=_fp(a["v_template"]), J_template=_fp(a["J_template"]),
+                             J_shapedirs=_fp(a["J_shapedirs"]), weights=_fp(a["weights"]), pose_mean=_fp(a["pose_mean"]),
+                             rodrigues_kind=int(lbs["rodrigues_kind"]), center_joint=int(lbs["center_joint"]),
+                             n_joints_out=int(ia["joint_out_src"].shape[0]), joint_out_src=_ip(ia["joint_out_src"]),
+                             n_tips=int(ia["tips"].shape[0]), tips=_ip(ia["tips"]))
+            keep += list(a.values()) + list(ia.values())
+            with torch.cuda.device(self.device):
+                check(L.harp_ctx_create_lbs(C.byref(h), C.byref(topo), C.byref(g)))
+            self.J, self.n_shape, self.n_joints_out = int(lbs["J"]), int(lbs["n_shape"]), int(ia["joint_out_src"].shape[0])
+        else:
+            with torch.cuda.device(self.device):
+                check(L.harp_ctx_create(C.byref(h), C.byref(topo), model_p))
+            self.J, self.n_shape, self.n_joints_out = (16, 10, 21) if mano is not None else (0, 0, 0)
         self.h = h
         dims = [C.c_int32() for _ in range(4)]
         check(L.harp_ctx_dims(self.h, *[C.byref(d) for d in dims]))
         self.V0, self.V, self.F, self.E = [d.value for d in dims]
-        self.has_model = mano is not None
+        self.has_model = mano is not None or lbs is not None
         self._reserved = (0, 0)
         self._faces = None
 
@@ -149,6 +171,38 @@ class LbsMano(torch.autograd.Function):
         return None, d_pose, d_betas, d_trans
 
 
+class Lbs(torch.autograd.Function):
+    """Generic kinematic-tree LBS (SMPLXARM.forward -> smplx.lbs.lbs, hand_models_harp/body_models.py:2163-2390):
+    full_pose (B,3J), shape (n_shape,) or (B,n_shape), trans (B,3) -> (verts0 m (B,V0,3), joints m (B,n_joints_out,3))."""
+
+    @staticmethod
+    def forward(ctx, hc, full_pose, shape, trans):
+        full_pose, shape, trans = _c(full_pose), _c(shape), _c(trans)
+        B = full_pose.shape[0]
+        shared = shape.dim() == 1 or shape.shape[0] == 1
+        verts0 = torch.empty(B, hc.V0, 3, device=full_pose.device)
+        joints = torch.empty(B, hc.n_joints_out, 3, device=full_pose.device)
+        check(_lib.lib().harp_lbs_fwd(hc.h, B, ptr(full_pose), ptr(shape), int(shared), ptr(trans), ptr(verts0), ptr(joints), stream()))
+        ctx.hc, ctx.shared, ctx.shape_shape = hc, shared, shape.shape
+        ctx.save_for_backward(full_pose, shape, trans)
+        return verts0, joints
+
+    @staticmethod
+    def backward(ctx, g_verts0, g_joints):
+        full_pose, shape, trans = ctx.saved_tensors
+        hc, B = ctx.hc, full_pose.shape[0]
+        g_verts0 = _c(g_verts0) if g_verts0 is not None else torch.zeros(B, hc.V0, 3, device=full_pose.device)
+        g_joints = _c(g_joints) if g_joints is not None else None
+        d_pose = torch.empty_like(full_pose)
+        d_shape = torch.empty(B, hc.n_shape, device=full_pose.device)
+        d_trans = torch.empty(B, 3, device=full_pose.device)
+        check(_lib.lib().harp_lbs_bwd(hc.h, B, ptr(full_pose), ptr(shape), int(ctx.shared), ptr(trans), ptr(g_verts0), ptr(g_joints),
+                                      ptr(d_pose), ptr(d_shape), ptr(d_trans), stream()))
+        if ctx.shared:
+            d_shape = d_shape.sum(0).view(ctx.shape_shape)
+        return None, d_pose, d_shape, d_trans
+
+
 class MeshBuild(torch.autograd.Function):
     """SubdivideMeshes + displacement along vertex normals + final vertex normals (utils/visualize.py:48-64)."""
 
@@ -214,7 +268,7 @@ class MeshLosses(torch.autograd.Function):
         disps_c = _c(disps).view(-1) if disps is not None else None
         losses = torch.zeros(5, device=dev)
         gv = torch.zeros(5, B, hc.V, 3, device=dev)
-        gj = torch.zeros(B, 21, 3, device=dev) if joints_c is not None else None
+        gj = torch.zeros_like(joints_c) if joints_c is not None else None
         gd = torch.zeros(hc.V, device=dev) if disps_c is not None else None
         L = _lib.lib()
         scratch = torch.zeros(5, device=dev)

@@ -87,18 +87,29 @@ class HarpFitter:
     ref_verts: (1,V,3) ARAP reference (`optimize_sequence.py:429-435`); uv_mask (H,W)."""
 
     def __init__(self, hc, params, frames, ref_verts, uv_mask, img_size, focal_length, self_shadow=True,
-                 lr_coarse=1e-3, lr_app=1e-2, world_size=1, process_group=None):
+                 lr_coarse=1e-3, lr_app=1e-2, world_size=1, process_group=None, opt_arm_pose=False):
         dev = hc.device
         self.hc, self.S, self.focal, self.self_shadow = hc, int(img_size), float(focal_length), bool(self_shadow)
         self.lr_coarse, self.lr_app = lr_coarse, lr_app
         self.world_size, self.pg = int(world_size), process_group
         f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
-        # optimiser groups (get_optimizers, optimize_sequence.py:253-310, default `harp` branch)
-        self.coarse = _Flat([("pose", f32(params["pose"])), ("cam", f32(params["cam"])),
-                             ("verts_disps", f32(params["verts_disps"])), ("shape", f32(params["shape"]))], dev)
+        # optimiser groups (get_optimizers, optimize_sequence.py:253-310, default `harp` branch).  With the SMPL-X arm model
+        # (`use_arm`) and `opt_arm_pose`, wrist_pose and rot join the coarse group at the same lr (279-283); they are
+        # placed BEFORE verts_disps so that everything from verts_disps on is the shared (all-reduced) block.
+        self.arm = hc.J == 55
+        T_ = params["pose"].shape[0]
+        self.wrist = f32(params["wrist_pose"]) if self.arm and "wrist_pose" in params else torch.zeros(T_, 3, device=dev)
+        groups = [("pose", f32(params["pose"])), ("cam", f32(params["cam"]))]
+        self.opt_arm_pose = bool(opt_arm_pose and self.arm)
+        if self.opt_arm_pose:
+            groups += [("wrist_pose", self.wrist), ("rot", f32(params["rot"]))]
+        groups += [("verts_disps", f32(params["verts_disps"])), ("shape", f32(params["shape"]))]
+        self.coarse = _Flat(groups, dev)
         self.app = _Flat([("light_positions", f32(params["light_positions"])), ("amb_ratio", f32(params["amb_ratio"]).view(1)),
                           ("texture", f32(params["texture"])), ("normal_map", f32(params["normal_map"]))], dev)
         self.rot, self.trans = f32(params["rot"]), f32(params["trans"])
+        if self.opt_arm_pose:
+            self.rot, self.wrist = self.coarse.p["rot"], self.coarse.p["wrist_pose"]
         self.frames = {k: f32(v) for k, v in frames.items()}
         self.ref_verts = f32(ref_verts).view(-1, 3)
         self.uv_mask = f32(uv_mask)
@@ -148,11 +159,17 @@ class HarpFitter:
         self.coarse.grad.zero_()
         self.app.grad.zero_()
         # ---- forward geometry
-        pose48 = torch.cat((self.rot.index_select(0, fid), P["pose"].index_select(0, fid)), 1)
+        rot_b, pose_b = self.rot.index_select(0, fid), P["pose"].index_select(0, fid)
+        if self.arm:  # SMPL-X joint order: global | 20 body joints | right wrist (joint 21) | jaw, eyes | left hand | right hand
+            z = self._buf("zeros", (B, 60))
+            pose48 = torch.cat((rot_b, z, self.wrist.index_select(0, fid), z[:, :54], pose_b), 1)
+        else:
+            pose48 = torch.cat((rot_b, pose_b), 1)
         trans = self.trans.index_select(0, fid)
+        NJ = hc.n_joints_out
         verts0 = self._buf("verts0", (B, hc.V0, 3), zero=False)
-        joints = self._buf("joints", (B, 21, 3), zero=False)
-        check(L.harp_lbs_mano_fwd(hc.h, B, ptr(pose48), ptr(P["shape"]), 1, ptr(trans), ptr(verts0), ptr(joints), st))
+        joints = self._buf("joints", (B, NJ, 3), zero=False)
+        check(L.harp_lbs_fwd(hc.h, B, ptr(pose48), ptr(P["shape"]), 1, ptr(trans), ptr(verts0), ptr(joints), st))
         disps = P["verts_disps"].view(-1)
         verts = self._buf("verts", (B, hc.V, 3), zero=False)
         normals = self._buf("normals", (B, hc.V, 3), zero=False)
@@ -172,7 +189,7 @@ class HarpFitter:
         # ---- gradient accumulators
         d_verts = self._buf("d_verts", (B, hc.V, 3))
         d_normals = self._buf("d_normals", (B, hc.V, 3))
-        d_joints = self._buf("d_joints", (B, 21, 3))
+        d_joints = self._buf("d_joints", (B, NJ, 3))
         d_cT = self._buf("d_cT", (B, 3))
         d_lR, d_lT, d_lpos, d_amb = self._buf("d_lR", (B, 3, 3)), self._buf("d_lT", (B, 3)), self._buf("d_lpos", (B, 3)), self._buf("d_amb", (1,))
         W = LOSS_WEIGHTS
@@ -214,17 +231,21 @@ class HarpFitter:
             d_verts0 = self._buf("d_verts0", (B, hc.V0, 3), zero=False)
             check(L.harp_mesh_build_bwd(hc.h, B, ptr(verts0), ptr(disps), ptr(d_verts), ptr(d_normals), ptr(d_verts0),
                                         ptr(self.coarse.g["verts_disps"].view(-1)), st))
-            d_pose48 = self._buf("d_pose48", (B, 48), zero=False)
+            d_pose48 = self._buf("d_pose48", (B, pose48.shape[1]), zero=False)
             d_betas = self._buf("d_betas", (B, 10), zero=False)
             d_trans = self._buf("d_trans", (B, 3), zero=False)
-            check(L.harp_lbs_mano_bwd(hc.h, B, ptr(pose48), ptr(P["shape"]), 1, ptr(trans), ptr(d_verts0), ptr(d_joints),
-                                      ptr(d_pose48), ptr(d_betas), ptr(d_trans), st))
-            self.coarse.g["pose"].index_add_(0, fid, d_pose48[:, 3:])
+            check(L.harp_lbs_bwd(hc.h, B, ptr(pose48), ptr(P["shape"]), 1, ptr(trans), ptr(d_verts0), ptr(d_joints),
+                                 ptr(d_pose48), ptr(d_betas), ptr(d_trans), st))
+            self.coarse.g["pose"].index_add_(0, fid, d_pose48[:, -45:])
+            if self.opt_arm_pose:
+                self.coarse.g["rot"].index_add_(0, fid, d_pose48[:, :3])
+                self.coarse.g["wrist_pose"].index_add_(0, fid, d_pose48[:, 63:66])
             self.coarse.g["cam"].index_add_(0, fid, g_cam)
             self.coarse.g["shape"] += d_betas.sum(0)
             self.app.g["light_positions"][0] += g_light
             self.app.g["amb_ratio"] += g_ambr.view(1)
-            self.last = dict(d_rot=d_pose48[:, :3], d_trans=d_trans, alpha=alpha, rgb=rgb, verts=verts, joints=joints)
+            self.last = dict(d_rot=d_pose48[:, :3], d_trans=d_trans, alpha=alpha, rgb=rgb, verts=verts, joints=joints,
+                             d_wrist=d_pose48[:, 63:66] if self.arm else None)
         # ---- data-parallel exchange: ONE allreduce of the shared-parameter gradients
         if R > 1 and exchange:
             self._allreduce_shared()

@@ -126,3 +126,109 @@ def make_reg_offsets(seed=3, std=1.0, size=TEX_SIZE):
     them from the CPU RNG each call; for parity they are an explicit input. Returns int32 (size,size,2)."""
     g = torch.Generator().manual_seed(seed)
     return torch.normal(mean=0.0, std=std, size=(size, size, 2), generator=g).to(torch.int32)
+
+
+# ----------------------------------------------------------------------------------------------------- SMPL-X arm
+# standard SMPL-X kinematic tree (55 joints: 22 body, jaw, 2 eyes, 15 + 15 hand joints)
+SMPLX_PARENTS = [-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 15, 15, 15,
+                 20, 25, 26, 20, 28, 29, 20, 31, 32, 20, 34, 35, 20, 37, 38,
+                 21, 40, 41, 21, 43, 44, 21, 46, 47, 21, 49, 50, 21, 52, 53]
+SMPLX_NUM_VERTS = 10475
+# VertexJointSelector extra joints (smplx/vertex_ids.py, 'smplx' table): face 5, feet 6, left tips 5, right tips 5
+SMPLX_VERTEX_IDS = dict(nose=9120, reye=9929, leye=9448, rear=616, lear=6, rthumb=8079, rindex=7669, rmiddle=7794, rring=7905,
+                        rpinky=8022, lthumb=5361, lindex=4933, lmiddle=5058, lring=5169, lpinky=5286, LBigToe=5770,
+                        LSmallToe=5780, LHeel=8846, RBigToe=8463, RSmallToe=8474, RHeel=8635)
+SMPLX_RIGHT_TIPS = ["rthumb", "rindex", "rmiddle", "rring", "rpinky"]  # extra joints 71..75
+
+
+def make_smplx_pack(seed=0, template=None):
+    """SMPL-X-shaped model dict (field names of SMPLX_NEUTRAL.npz as read at hand_models_harp/body_models.py:143-260,
+    602-623,2013-2067) that is anatomically meaningful only on the right arm: the 1026 arm vertices sit at the real
+    `template/arm` positions (via `smplx_arm_corr.pkl`), everything else is filler.  float32."""
+    t = template if template is not None else load_template("arm")
+    rng = np.random.RandomState(seed)
+    V, J = SMPLX_NUM_VERTS, 55
+    arm_ids = t["arm_vert"].astype(np.int64)
+    va = t["verts0"].astype(np.float64)                     # (1026,3) arm verts in arm numbering
+    hand_local = t["mano_vert_from_arm"].astype(np.int64)
+    v = rng.normal(0, 0.15, size=(V, 3)) + np.array([0.2, 0.0, 0.0])
+    v[arm_ids] = va
+    # joints: wrist / elbow from the geometry, fingers by farthest-point sampling on the hand part (as make_mano_pack)
+    hand = va[hand_local]
+    forearm = np.setdiff1d(np.arange(va.shape[0]), hand_local)
+    wrist = hand[np.argsort(hand[:, 0])[-40:]].mean(0)     # the hand's proximal rim (largest x)
+    elbow = va[forearm][np.argsort(va[forearm][:, 0])[-40:]].mean(0)
+    d = np.linalg.norm(hand - wrist, axis=1)
+    tips = []
+    for _ in range(5):
+        i = int(np.argmax(d)); tips.append(i)
+        d = np.minimum(d, np.linalg.norm(hand - hand[i], axis=1) * 1.5)
+    Jpos = rng.normal(0, 0.15, size=(J, 3)) + np.array([0.2, 0.0, 0.0])
+    Jpos[19], Jpos[21] = elbow, wrist
+    Jpos[17] = elbow + (elbow - wrist)                      # shoulder continues the forearm axis
+    Jpos[14] = Jpos[17] + np.array([0.15, 0.0, 0.0])
+    # right-hand joints 40..54 in SMPL-X order: index, middle, pinky, ring, thumb (3 each)
+    for f in range(5):
+        for k, a in enumerate((0.45, 0.65, 0.82)):
+            Jpos[40 + 3 * f + k] = wrist + a * (hand[tips[f]] - wrist)
+    # regressor rows: softmax over the nearest vertices (arm verts for arm joints), rows sum to 1
+    Jreg = np.zeros((J, V))
+    for j in range(J):
+        d2 = ((v - Jpos[j]) ** 2).sum(1)
+        nn_ = np.argsort(d2)[:24]
+        w = np.exp(-d2[nn_] / (2 * 0.012 ** 2) + d2[nn_].min() / (2 * 0.012 ** 2)); w /= w.sum()
+        Jreg[j, nn_] = w
+    # skinning weights: arm verts over {elbow, wrist, right-hand joints}; everything else rigid to the pelvis
+    W = np.zeros((V, J)); W[:, 0] = 1.0
+    cand = np.array([19, 21] + list(range(40, 55)))
+    Jtrue = Jreg @ v
+    d2 = ((va[:, None, :] - Jtrue[cand][None]) ** 2).sum(-1)
+    w = np.exp(-d2 / (2 * 0.025 ** 2))
+    kth = np.sort(w, axis=1)[:, -4][:, None]
+    w = np.where(w >= kth, w, 0.0); w /= w.sum(1, keepdims=True)
+    W[arm_ids] = 0.0
+    W[np.repeat(arm_ids, cand.size), np.tile(cand, arm_ids.size)] = w.reshape(-1)
+    nb = _one_ring(va.shape[0], t["faces0"])
+
+    def smooth(x, it=2):
+        for _ in range(it):
+            x = np.stack([(x[i] + sum(x[j] for j in nb[i])) / (1 + len(nb[i])) for i in range(x.shape[0])], 0)
+        return x
+
+    shapedirs = np.zeros((V, 3, 20), np.float32)
+    shapedirs[arm_ids] = (smooth(rng.normal(0, 2e-3, size=(va.shape[0], 60))) * 3.0).reshape(-1, 3, 20)
+    posedirs = np.zeros((V, 3, 486), np.float32)
+    posedirs[arm_ids] = (smooth(rng.normal(0, 0.5e-3, size=(va.shape[0], 1458)), it=1) * 2.0).reshape(-1, 3, 486)
+    faces = arm_ids[t["faces0"].astype(np.int64)]
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    return dict(v_template=f32(v), shapedirs=shapedirs, posedirs=posedirs, J_regressor=f32(Jreg), weights=f32(W),
+                kintree_table=np.stack([np.asarray(SMPLX_PARENTS, np.int64), np.arange(J)], 0), f=faces.astype(np.int64),
+                hands_componentsl=np.eye(45, dtype=np.float32), hands_componentsr=np.eye(45, dtype=np.float32),
+                hands_meanl=f32(rng.normal(0, 0.1, size=45)), hands_meanr=f32(rng.normal(0, 0.1, size=45)),
+                lmk_faces_idx=np.zeros(51, np.int64), lmk_bary_coords=np.full((51, 3), 1.0 / 3.0, np.float32),
+                dynamic_lmk_faces_idx=np.zeros((79, 17), np.int64), dynamic_lmk_bary_coords=np.full((79, 17, 3), 1.0 / 3.0, np.float32))
+
+
+def reduce_smplx_arm(pack, template=None):
+    """Restrict a SMPL-X model dict to what SMPLXARM returns (hand_models_harp/body_models.py:2383-2390): the 1026 arm
+    vertices and the 22 `mano_joint` joints; fold the joint regressor; express fingertip vertex-joints in arm numbering.
+    -> kwargs of `harp_b200.ops.HarpContext(..., lbs=...)` (the generic skinning model of include/harp_b200.h)."""
+    t = template if template is not None else load_template("arm")
+    arm_ids = t["arm_vert"].astype(np.int64)
+    inv = -np.ones(SMPLX_NUM_VERTS, np.int64); inv[arm_ids] = np.arange(arm_ids.size)
+    n_shape = 10  # betas; the 10 expression coefficients are the layer's zero default (body_models.py:2248, 2323)
+    Jreg = pack["J_regressor"].astype(np.float64)
+    J_template = Jreg @ pack["v_template"].astype(np.float64)
+    J_shapedirs = np.einsum("jv,vkb->jkb", Jreg, pack["shapedirs"][:, :, :n_shape].astype(np.float64))
+    tips_smplx = [SMPLX_VERTEX_IDS[n] for n in SMPLX_RIGHT_TIPS]
+    tips = inv[tips_smplx]
+    assert (tips >= 0).all(), "right-hand fingertip vertices must belong to the arm sub-mesh"
+    pose_mean = np.concatenate([np.zeros(3 * 25), pack["hands_meanl"], pack["hands_meanr"]])  # create_mean_pose, 2129-2147
+    src = []
+    for j in t["mano_joint"].tolist():  # 55 chain joints, then VertexJointSelector extras: right tips are 71..75
+        src.append(j if j < 55 else 55 + (j - 71))
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    return dict(J=55, n_shape=n_shape, parents=np.asarray(SMPLX_PARENTS, np.int32), shapedirs=f32(pack["shapedirs"][arm_ids][:, :, :n_shape]),
+                posedirs=f32(pack["posedirs"][arm_ids]), v_template=f32(pack["v_template"][arm_ids]), J_template=f32(J_template),
+                J_shapedirs=f32(J_shapedirs), weights=f32(pack["weights"][arm_ids]), pose_mean=f32(pose_mean), rodrigues_kind=1,
+                center_joint=21, joint_out_src=np.asarray(src, np.int32), tips=tips.astype(np.int32), faces0=t["faces0"].astype(np.int32))

@@ -12,14 +12,19 @@ def prepare_mesh(params, fid, mano_layer, verts_textures, mesh_subdivider, globa
     """-> (hand_joints (B,21,3) m, hand_verts (B,V,3) m, faces (B,F,3), textures).
     `mesh_subdivider`: None for the coarse mesh, anything truthy for one SubdivideMeshes step (the subdivision tables live
     in `mano_layer.hc`)."""
-    if use_arm or configs.get("model_type", "harp") != "harp":
-        raise NotImplementedError("SMPLXARM / html / nimble branches: SURVEY.md 8(f) 'next' rows")
+    if configs.get("model_type", "harp") != "harp":
+        raise NotImplementedError("html / nimble hand models need third-party code and assets (SURVEY.md section 2 row 23)")
     B = fid.shape[0]
     fid = fid.to(params["pose"].device)
-    pose48 = torch.cat((params["rot"][fid], params["pose"][fid]), 1).to(device)
     betas = params["shape"].to(device)
     hc = mano_layer.hc if mesh_subdivider is not None else mano_layer.hc_coarse
-    verts0, joints = ops.LbsMano.apply(hc, pose48, betas, params["trans"][fid].to(device))  # metres (visualize.py:45-46)
+    if use_arm:  # visualize.py:36-40
+        full_pose = mano_layer.assemble_full_pose(params["rot"][fid].to(device), params["pose"][fid].to(device),
+                                                  params["wrist_pose"][fid].to(device))
+        verts0, joints = ops.Lbs.apply(hc, full_pose, betas, params["trans"][fid].to(device))
+    else:
+        pose48 = torch.cat((params["rot"][fid], params["pose"][fid]), 1).to(device)
+        verts0, joints = ops.LbsMano.apply(hc, pose48, betas, params["trans"][fid].to(device))  # metres (visualize.py:45-46)
     disps = params.get("verts_disps")
     if disps is not None and disps.shape[1] != 1:
         raise NotImplementedError("free 3-D vertex offsets (VERT_DISPS_NORMALS=False) are not used by HARP's config")

@@ -63,10 +63,37 @@ typedef struct {
   const int32_t* tips;      /* (5) fingertip vertex ids, manolayer.py:272 */
 } harp_mano_model;
 
+/* Generic linear-blend-skinning model of the SMPL family restricted to the vertices the caller keeps (the 1026 arm verts
+ * of SMPLXARM, hand_models_harp/body_models.py:2100-2127,2383).  [host] pointers, fp32 / int32, copied.
+ * The joint regressor is passed FOLDED: J(shape) = J_template + J_shapedirs . shape  (= J_regressor (v_template + S shape)).
+ * Output joints: joint_out_src[k] < J selects chain joint k's posed location, J + i selects vertex tips[i] (the
+ * VertexJointSelector fingertips).  center_joint >= 0 subtracts that joint from every output (body_models.py:2342-2343). */
+#define HARP_MAX_JOINTS 64
+#define HARP_MAX_SHAPE 32
+typedef struct {
+  int32_t J, n_shape;            /* V0 comes from the topology */
+  const int32_t* parents;        /* (J) parents[0] = -1, parents precede children */
+  const float* shapedirs;        /* (V0,3,n_shape) */
+  const float* posedirs;         /* (V0,3,(J-1)*9) */
+  const float* v_template;       /* (V0,3) metres */
+  const float* J_template;       /* (J,3) */
+  const float* J_shapedirs;      /* (J,3,n_shape) */
+  const float* weights;          /* (V0,J) */
+  const float* pose_mean;        /* (3J) added to the axis-angle pose */
+  int32_t rodrigues_kind;        /* 0: manopth quaternion form (rodrigues_layer.py:15-54); 1: smplx.lbs.batch_rodrigues */
+  int32_t center_joint;          /* -1: none */
+  int32_t n_joints_out;
+  const int32_t* joint_out_src;  /* (n_joints_out) */
+  int32_t n_tips;
+  const int32_t* tips;           /* (n_tips) vertex ids in [0,V0) */
+} harp_lbs_model;
+
 HARP_API const char* harp_last_error(void);
 HARP_API int harp_version(void);
 
 HARP_API int harp_ctx_create(harp_ctx** out, const harp_topology* topo, const harp_mano_model* model /* nullable */);
+/* Same, with a generic skinning model (SMPL-X arm).  harp_ctx_create(topo, mano) is the MANO special case. */
+HARP_API int harp_ctx_create_lbs(harp_ctx** out, const harp_topology* topo, const harp_lbs_model* model);
 HARP_API void harp_ctx_destroy(harp_ctx* ctx);
 /* Size all scratch (bin lists, projected verts, light depth, per-frame Jacobians) for <= max_batch frames of
  * img_size x img_size.  Allocates; call outside the hot loop. */
@@ -96,6 +123,15 @@ HARP_API int harp_lbs_mano_bwd(harp_ctx*, int B, const float* pose48, const floa
                       const float* d_verts0, const float* d_joints, float* d_pose48, float* d_betas, float* d_trans,
                       void* stream);
 
+/* ---- generic LBS (SMPLXARM.forward -> smplx.lbs.lbs, hand_models_harp/body_models.py:2163-2390) ----------------------
+ * pose (B,3J) full axis-angle pose (pose_mean is added inside); shape (B,n_shape) or one shared row; trans (B,3).
+ * verts0 (B,V0,3) m, joints (B,n_joints_out,3) m.  bwd: d_pose (B,3J), d_shape (B,n_shape), d_trans (B,3) overwritten. */
+HARP_API int harp_lbs_fwd(harp_ctx*, int B, const float* pose, const float* shape, int shape_shared, const float* trans,
+                          float* verts0, float* joints, void* stream);
+HARP_API int harp_lbs_bwd(harp_ctx*, int B, const float* pose, const float* shape, int shape_shared, const float* trans,
+                          const float* d_verts0, const float* d_joints, float* d_pose, float* d_shape, float* d_trans,
+                          void* stream);
+
 /* ---- mesh build: SubdivideMeshes + normal displacement + vertex normals (utils/visualize.py:48-64) -------------------
  * verts0 (B,V0,3); disps (V) or NULL.  verts (B,V,3), normals (B,V,3) = Meshes.verts_normals_padded() of `verts`. */
 HARP_API int harp_mesh_build_fwd(harp_ctx*, int B, const float* verts0, const float* disps, float* verts, float* normals,
@@ -113,7 +149,8 @@ HARP_API int harp_vertex_normals_bwd(harp_ctx*, int B, const float* verts, const
  * mesh_laplacian_smoothing / mesh_normal_consistency (optimize_sequence.py:536-537), arap_loss (loss/arap.py:4-57),
  * kps_loss (loss/kps_loss.py:4-17), sum(disp^2) (optimize_sequence.py:533).
  * w[5] = upstream weights for {laplacian, normal, arap, kps, disp}; losses[5] (device) receives the UNWEIGHTED values
- * (accumulated, zero it first); gradients are weighted.  ref_verts (V,3); joints/init_joints (B,21,3) m / mm. */
+ * (accumulated, zero it first); gradients are weighted.  ref_verts (V,3); joints (B,n_joints_out,3) m of the ctx's model
+ * (21 for MANO / no model, 22 for the arm: the first 21 are used); init_joints (B,21,3) mm. */
 HARP_API int harp_mesh_losses(harp_ctx*, int B, const float* verts, const float* ref_verts, const float* joints,
                      const float* init_joints_mm, const float* disps, const float w[5], float* losses,
                      float* d_verts, float* d_joints, float* d_disps, void* stream);

@@ -112,6 +112,36 @@ def mano_forward(m, pose_coeffs, betas, trans):
     return verts * 1000, jtr * 1000  # 291-292
 
 
+# ------------------------------------------------------------------------------------------------- SMPL-X arm LBS
+def smplxarm_forward(m, betas, global_orient, right_hand_pose, right_wrist_pose, transl):
+    """hand_models_harp/body_models.py:2163-2390 (SMPLXARM.forward, return_type='mano_w_arm') for the arguments
+    utils/visualize.py:37-40 passes; every other pose input is the layer's zero default (SMPL.__init__ 180-215, SMPLH
+    638-660, SMPLXARM 2036-2098).  m: dict of tensors with the SMPLX npz field names + 'arm_vert', 'mano_joint',
+    'extra_joints_idxs'.  Returns (verts_mm (B,1026,3), joints_mm (B,22,3))."""
+    from smplx_shim import lbs as slbs
+    B, dt = global_orient.shape[0], betas.dtype
+    body_pose = torch.zeros(B, 63, dtype=dt)
+    body_pose[:, 60:63] = right_wrist_pose  # 2299-2301
+    z3, z45 = torch.zeros(B, 3, dtype=dt), torch.zeros(B, 45, dtype=dt)
+    full_pose = torch.cat([global_orient.reshape(-1, 1, 3), body_pose.reshape(-1, 21, 3), z3.reshape(-1, 1, 3),
+                           z3.reshape(-1, 1, 3), z3.reshape(-1, 1, 3), z45.reshape(-1, 15, 3),
+                           right_hand_pose.reshape(-1, 15, 3)], dim=1).reshape(-1, 165)  # 2304-2311
+    pose_mean = torch.cat([torch.zeros(75, dtype=dt), m["hands_meanl"], m["hands_meanr"]])  # create_mean_pose 2129-2147
+    full_pose = full_pose + pose_mean  # 2315
+    shape_components = torch.cat([betas, torch.zeros(B, 10, dtype=dt)], dim=-1)  # expression default zeros, 2323
+    posedirs = m["posedirs"].reshape(-1, m["posedirs"].shape[-1]).T  # SMPL.__init__ 249-253
+    parents = m["kintree_table"][0].long().clone(); parents[0] = -1
+    vertices, joints = slbs.lbs(shape_components, full_pose, m["v_template"], m["shapedirs"], posedirs, m["J_regressor"],
+                                parents, m["weights"])  # 2335-2339
+    vertices = vertices - joints[:, None, 21, :]  # 2342
+    joints = joints - joints[:, None, 21, :]
+    joints = torch.cat([joints, torch.index_select(vertices, 1, m["extra_joints_idxs"])], dim=1)  # 2365 (landmarks are appended
+    # after index 75 and never selected by joint_idx_tensor)
+    joints = joints + transl.unsqueeze(1)  # 2378-2380
+    vertices = vertices + transl.unsqueeze(1)
+    return vertices[:, m["arm_vert"]] * 1000.0, joints[:, m["mano_joint"]] * 1000.0  # 2383-2385
+
+
 # ------------------------------------------------------------------------------------------------- topology
 class Topology:
     """Static tables: coarse faces -> PyTorch3D SubdivideMeshes layout (optimize_sequence.py:67-89), UVs."""
@@ -336,8 +366,12 @@ def forward_losses(model, topo, params, batch, cfg):
     S, focal = cfg["img_size"], cfg["focal_length"]
     B = params["pose"].shape[0]
     stage = cfg.get("stage", "both")
-    verts_mm, joints_mm = mano_forward(model, torch.cat((params["rot"], params["pose"]), 1),
-                                       params["shape"].repeat([B, 1]), params["trans"])  # visualize.py:42-44
+    if cfg.get("use_arm", False):  # visualize.py:36-40
+        verts_mm, joints_mm = smplxarm_forward(model, params["shape"].repeat([B, 1]), params["rot"], params["pose"],
+                                               params["wrist_pose"], params["trans"])
+    else:
+        verts_mm, joints_mm = mano_forward(model, torch.cat((params["rot"], params["pose"]), 1),
+                                           params["shape"].repeat([B, 1]), params["trans"])  # visualize.py:42-44
     verts0, joints = verts_mm / 1000.0, joints_mm / 1000.0
     verts = build_mesh(verts0, topo, params.get("verts_disps"))
     light = params["light_position"][None].repeat(B, 1)  # share_light_position (453-454)
@@ -350,7 +384,7 @@ def forward_losses(model, topo, params, batch, cfg):
     if stage in ("coarse", "both"):
         out["silhouette"] = F.l1_loss(batch["y_sil"], sil)
         if "init_joints" in batch:
-            out["kps_anchor"] = kps_loss(batch["init_joints"], joints)
+            out["kps_anchor"] = kps_loss(batch["init_joints"], joints[:, :21] if cfg.get("use_arm", False) else joints)
         if params.get("verts_disps") is not None and cfg.get("mesh_losses", True):
             out["vert_disp_reg"] = torch.sum(params["verts_disps"] ** 2.0)
             out["laplacian"], out["normal"] = mesh_reg_losses(verts, topo)
@@ -371,7 +405,8 @@ def total_loss(losses):
     return s
 
 
-GRAD_KEYS = ("pose", "rot", "trans", "cam", "shape", "verts_disps", "texture", "normal_map", "light_position", "amb_ratio")
+GRAD_KEYS = ("pose", "rot", "trans", "wrist_pose", "cam", "shape", "verts_disps", "texture", "normal_map", "light_position",
+             "amb_ratio")
 
 
 def step(model, topo, params, batch, cfg):

@@ -63,7 +63,26 @@ def ref_mano_layer(pack):
     return layer
 
 
-def reference_step(pack, tmpl, p, batch, S, focal, subdivide, stage, seed_albedo, seed_normal):
+_ARM_LAYER = {}
+
+
+def ref_arm_layer(pack):
+    """The reference's SMPLXARM (hand_models_harp/body_models.py) on the restated smplx modules, fed a synthetic
+    SMPLX_NEUTRAL.npz; built as utils/hand_model_utils.py:65-70 does.  cwd must be /root/reference (body_models.py:2101)."""
+    if "layer" not in _ARM_LAYER:
+        import tempfile
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import smplx_shim
+        bm = smplx_shim.load_reference_body_models(REF)
+        d = tempfile.mkdtemp()
+        os.makedirs(os.path.join(d, "smplx"))
+        np.savez(os.path.join(d, "smplx", "SMPLX_NEUTRAL.npz"), **pack)
+        _ARM_LAYER["layer"] = bm.create(d, model_type="smplxarm", gender="neutral", use_face_contour=False, num_betas=10,
+                                        use_pca=False, num_expression_coeffs=10, ext="npz")
+    return _ARM_LAYER["layer"]
+
+
+def reference_step(pack, tmpl, p, batch, S, focal, subdivide, stage, seed_albedo, seed_normal, arm=False):
     """optimize_sequence.py:446-569 with the reference's functions, device='cpu'."""
     import renderer.renderer_helper as renderer_helper
     from utils.visualize import prepare_mesh, prepare_materials, render_image, render_image_with_RT
@@ -75,15 +94,19 @@ def reference_step(pack, tmpl, p, batch, S, focal, subdivide, stage, seed_albedo
     from pytorch3d.loss import mesh_laplacian_smoothing, mesh_normal_consistency
 
     dev = "cpu"
-    layer = ref_mano_layer(pack)
-    configs = {"model_type": "harp", "img_size": S, "focal_length": focal, "use_arm": False,
+    layer = ref_arm_layer(pack) if arm else ref_mano_layer(pack)
+    configs = {"model_type": "harp", "img_size": S, "focal_length": focal, "use_arm": arm,
                "share_light_position": True, "self_shadow": True, "known_appearance": False}
     mesh_subdivider = None
-    if subdivide:  # optimize_sequence.py:67-89
+    if subdivide and arm:  # optimize_sequence.py:67-72
+        hv, _ = layer(betas=torch.zeros([1, 10]), global_orient=torch.zeros([1, 3]), transl=torch.zeros([1, 3]),
+                      right_hand_pose=torch.zeros([1, 45]), return_type="mano_w_arm")
+        mesh_subdivider = SubdivideMeshes(meshes=Meshes(hv, layer.right_arm_faces_tensor.repeat(1, 1, 1)))
+    elif subdivide:  # optimize_sequence.py:73-81
         hv, _ = layer(torch.zeros([1, 48]), torch.zeros([1, 10]), torch.zeros([1, 3]))
         mesh_subdivider = SubdivideMeshes(meshes=Meshes(hv, layer.th_faces.repeat(1, 1, 1)))
     params = dict(p)
-    params["mesh_faces"] = layer.th_faces
+    params["mesh_faces"] = layer.right_arm_faces_tensor if arm else layer.th_faces
     params["verts_uvs"] = torch.tensor(tmpl["verts_uvs"])[None]
     params["faces_uvs"] = torch.tensor(tmpl["faces_uvs"]).long()[None]
     B = p["pose"].shape[0]
@@ -94,7 +117,7 @@ def reference_step(pack, tmpl, p, batch, S, focal, subdivide, stage, seed_albedo
         image_size=S, light_posi=light_positions, silh_sigma=1e-7, silh_gamma=1e-1, silh_faces_per_pixel=50, device=dev)
     hand_joints, hand_verts, faces, textures = prepare_mesh(params, fid, layer, False, mesh_subdivider,
                                                             global_pose=False, configs=configs, shared_texture=True,
-                                                            device=dev, use_arm=False)
+                                                            device=dev, use_arm=arm)
     meshes = Meshes(hand_verts, faces, textures)
     cam = params["cam"][fid]
     materials_properties = prepare_materials(params, B, device=dev)
@@ -111,7 +134,7 @@ def reference_step(pack, tmpl, p, batch, S, focal, subdivide, stage, seed_albedo
     loss = {}
     if stage in ("coarse", "both"):
         loss["silhouette"] = l1_loss(batch["y_sil"], y_sil_pred)
-        loss["kps_anchor"] = kps_loss(batch["init_joints"], hand_joints, use_arm=False, device=dev)
+        loss["kps_anchor"] = kps_loss(batch["init_joints"], hand_joints, use_arm=arm, device=dev)
         loss["vert_disp_reg"] = torch.sum(params["verts_disps"] ** 2.0)
         loss["laplacian"] = mesh_laplacian_smoothing(meshes)
         loss["normal"] = mesh_normal_consistency(meshes)
@@ -126,21 +149,26 @@ def reference_step(pack, tmpl, p, batch, S, focal, subdivide, stage, seed_albedo
     return loss, dict(sil=y_sil_pred, rgb=y_pred, verts=hand_verts, joints=hand_joints, sil_overflow=sil_overflow)
 
 
-def scenario(name, S, B, subdivide, stage, dtype=torch.float32, trans_amp=0.0):
+def scenario(name, S, B, subdivide, stage, dtype=torch.float32, trans_amp=0.0, arm=False):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import harp_oracle as O
-    tmpl = synth.load_template("hand")
-    pack = synth.make_mano_pack(seed=0, template=tmpl)
+    tmpl = synth.load_template("arm" if arm else "hand")
+    pack = synth.make_smplx_pack(seed=0, template=tmpl) if arm else synth.make_mano_pack(seed=0, template=tmpl)
     focal = 1000.0 * S / 224.0
     seq = synth.make_sequence(max(B, 2), seed=1, img_size=S)
     app = synth.make_appearance(seed=2)
-    V = 3093 if subdivide else 778
+    V = (4083 if subdivide else 1026) if arm else (3093 if subdivide else 778)
     g = torch.Generator().manual_seed(7)
     trans = seq["trans"][:B] + trans_amp * torch.randn(B, 3, generator=g)
     P = dict(pose=seq["pose"][:B], rot=seq["rot"][:B], trans=trans, cam=seq["cam"][:B],
              shape=seq["shape"], verts_disps=0.0008 * torch.randn(V, 1, generator=g),
              texture=app["texture"], normal_map=app["normal_map"],
              light_positions=app["light_position"][None].repeat(B, 1), amb_ratio=app["amb_ratio"])
+    if arm:
+        # the arm template lies along -x with the wrist at the origin after centring (body_models.py:2342): a smaller
+        # weak-perspective scale keeps the ~0.45 m arm inside the frame
+        P["wrist_pose"] = 0.1 * torch.randn(B, 3, generator=g)
+        P["cam"] = P["cam"] * torch.tensor([0.35, 1.0, 1.0]) + torch.tensor([0.0, 0.15, 0.0])
     uv_mask = torch.tensor(tmpl["uv_mask"])
     leaf = {k: torch.nn.Parameter(v.clone().to(dtype)) for k, v in P.items()}
     # targets: render a perturbed parameter set with the reference path, no grad
@@ -152,21 +180,21 @@ def scenario(name, S, B, subdivide, stage, dtype=torch.float32, trans_amp=0.0):
         Pp["texture"], Pp["normal_map"] = app2["texture"], app2["normal_map"]
         dummy = dict(y_sil=torch.zeros(B, S, S), y_sil_eroded=torch.zeros(B, S, S), y_true=torch.zeros(B, S, S, 3),
                      init_joints=torch.zeros(B, 21, 3), ref_verts=torch.zeros(1, V, 3), uv_mask=uv_mask)
-        _, im = reference_step(pack, tmpl, Pp, dummy, S, focal, subdivide, "both", 11, 12)
+        _, im = reference_step(pack, tmpl, Pp, dummy, S, focal, subdivide, "both", 11, 12, arm=arm)
         y_sil = (im["sil"] >= 0.5).float()
         y_er = synth.erode_mask(y_sil)
         y_true = im["rgb"].clamp(0, 1)
-        init_joints = im["joints"] * 1000.0
+        init_joints = im["joints"][:, :21] * 1000.0
         d1 = {k: (v[:1] if k != "uv_mask" else v) for k, v in dummy.items()}
-        _, im0 = reference_step(pack, tmpl, {k: v[:1] if k in ("pose", "rot", "trans", "cam", "light_positions") else v
-                                             for k, v in P.items()}, d1, S, focal, subdivide, "both", 11, 12)
+        _, im0 = reference_step(pack, tmpl, {k: v[:1] if k in ("pose", "rot", "trans", "cam", "light_positions", "wrist_pose") else v
+                                             for k, v in P.items()}, d1, S, focal, subdivide, "both", 11, 12, arm=arm)
         ref_verts = im0["verts"][:1].clone()
     batch = dict(y_sil=y_sil, y_sil_eroded=y_er, y_true=y_true, init_joints=init_joints, ref_verts=ref_verts, uv_mask=uv_mask)
-    loss, im = reference_step(pack, tmpl, leaf, batch, S, focal, subdivide, stage, 11, 12)
+    loss, im = reference_step(pack, tmpl, leaf, batch, S, focal, subdivide, stage, 11, 12, arm=arm)
     total = sum(v * O.LOSS_WEIGHTS[k] for k, v in loss.items())
     names = list(leaf.keys())
     gs = torch.autograd.grad(total, [leaf[k] for k in names], allow_unused=True)
-    out = {"S": S, "B": B, "subdivide": int(subdivide), "stage": stage, "focal": focal,
+    out = {"S": S, "B": B, "subdivide": int(subdivide), "stage": stage, "focal": focal, "arm": int(arm),
            "seed_albedo": 11, "seed_normal": 12}
     for k, v in P.items():
         if k in ("texture", "normal_map"):  # regenerated from synth.make_appearance(seed=2); keep a checksum only
@@ -195,3 +223,4 @@ if __name__ == "__main__":
     os.chdir(REF)
     scenario("c1_sil_256_coarse", S=256, B=1, subdivide=False, stage="coarse")
     scenario("c2_full_128_sub", S=128, B=2, subdivide=True, stage="both", trans_amp=0.004)
+    scenario("c4_arm_128_sub", S=128, B=2, subdivide=True, stage="both", trans_amp=0.004, arm=True)

@@ -10,7 +10,7 @@ from pytorch3d import _core as p3d, _raster
 from util import load_golden, golden_case, rel_l2
 
 
-@pytest.mark.parametrize("name", ["c1_sil_256_coarse", "c2_full_128_sub"])
+@pytest.mark.parametrize("name", ["c1_sil_256_coarse", "c2_full_128_sub", "c4_arm_128_sub"])
 def test_oracle_matches_reference_golden(name):
     g = load_golden(name)
     model, topo, params, batch, cfg = golden_case(g)

@@ -62,7 +62,7 @@ def subdivide_faces(faces, V):
     return edges, np.concatenate([f0, f1, f2, f3], 0)
 
 
-def process(name, obj, mask_png, scale_to_m):
+def process(name, obj, mask_png, scale_to_m, corr_pkl=None):
     v, vt, fv, ft = parse_obj(obj)
     F = fv.shape[0]
     F0 = F // 4
@@ -86,6 +86,26 @@ def process(name, obj, mask_png, scale_to_m):
     mid = 0.5 * (verts0[edges0[:, 0]] + verts0[edges0[:, 1]])
     sub = np.concatenate([verts0, mid], 0)
     err = np.abs(sub - v[to_obj] * scale_to_m).max()
+    extra = {}
+    if corr_pkl is not None:
+        # template/arm/smplx_arm_corr.pkl: arm sub-mesh of SMPL-X (hand_models_harp/body_models.py:2100-2127).  Its 'face'
+        # list is the coarse arm mesh in ARM numbering and in SubdivideMeshes input order, so coarse face k pairs with
+        # our recovered face k corner by corner: renumber our coarse verts into the pickle's numbering.
+        import pickle
+        with open(corr_pkl, "rb") as fh:
+            corr = pickle.load(fh)
+        cf = np.asarray(corr["face"], np.int64)
+        assert cf.shape == faces0.shape
+        to_arm = -np.ones(V0, np.int64)
+        to_arm[faces0.reshape(-1)] = cf.reshape(-1)
+        assert (to_arm >= 0).all() and np.unique(to_arm).shape[0] == V0 and np.array_equal(to_arm[faces0], cf)
+        order = np.argsort(to_arm)          # arm id -> our id
+        verts0, faces0 = verts0[order], cf
+        extra = dict(arm_vert=np.asarray(corr["arm_vert"], np.int32),                      # SMPL-X vertex id of each arm vert
+                     mano_vert_from_arm=np.asarray(corr["mano_vert_from_arm"], np.int32),  # the 778 hand verts inside the arm
+                     mano_joint=np.asarray(corr["mano_joint"], np.int32))                  # 22 joint ids (21 hand + elbow)
+        edges0, faces_sub = subdivide_faces(faces0, V0)
+        assert np.array_equal(np.sort(faces_sub.reshape(-1)), np.sort(faces_sub.reshape(-1)))
     from PIL import Image
     m = np.asarray(Image.open(mask_png).convert("L").resize((512, 512))) / 255.0  # optimize_sequence.py:176-178
     out = os.path.join(OUT, f"{name}_template.npz")
@@ -96,6 +116,7 @@ def process(name, obj, mask_png, scale_to_m):
         verts_uvs=vt.astype(np.float32),       # (Vt,2)
         faces_uvs=ft.astype(np.int32),         # (F,3) pairs with subdivided faces
         uv_mask=m.astype(np.float32),          # (512,512)
+        **extra,
     )
     print(f"{name}: V0={V0} F0={F0} E0={E0} V={V0+E0} F={F} Vt={vt.shape[0]} midpoint err={err:.3e} m -> {out}")
 
@@ -103,4 +124,4 @@ def process(name, obj, mask_png, scale_to_m):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     process("hand", f"{REF}/hand/textured_hand.obj", f"{REF}/hand/uv_mask.png", 1e-3)
-    process("arm", f"{REF}/arm/arm_template.obj", f"{REF}/arm/uv_mask.png", 1.0)
+    process("arm", f"{REF}/arm/arm_template.obj", f"{REF}/arm/uv_mask.png", 1.0, corr_pkl=f"{REF}/arm/smplx_arm_corr.pkl")
