@@ -25,13 +25,14 @@ FRAMES, SIZE = 64, 512
 METRIC, UNIT = "optimizer_frames_per_sec_fwd_bwd_512x512_MANO", "frames/s"
 
 
-def config(n_gpus, frames, size):
-    return {"workload": f"{frames}-frame seq @{size}x{size} per GPU, MANO 778->3093 verts / 6152 faces, soft silhouette (K=50) + "
+def config(n_gpus, frames, size, model="hand"):
+    mesh = "MANO 778->3093 verts / 6152 faces" if model == "hand" else "SMPL-X arm 1026->4083 verts / 8128 faces"
+    return {"workload": f"{frames}-frame seq @{size}x{size} per GPU, {mesh}, soft silhouette (K=50) + "
                         "shadowed PBR render + photometric + kps + Laplacian + normal-consistency + ARAP + texture regs, "
                         "fwd+bwd+Adam (VGG term excluded)",
             "frames_per_gpu": frames, "img_size": size, "global_frames": frames * n_gpus,
             "parallelism": f"dp{n_gpus} (static frame sharding, one allreduce of shared-parameter grads per step)",
-            "l2_policy": "per-step image inputs (335 MB/GPU) exceed the 126 MB L2; no explicit flush"}
+            "l2_policy": f"per-step image inputs ({20 * size * size * frames / 1e6:.0f} MB/GPU) exceed the 126 MB L2; no explicit flush"}
 
 
 # ---------------------------------------------------------------------------------------------------- CPU reference arm
@@ -130,6 +131,7 @@ def main():
     ap.add_argument("--impl", default="harp", choices=["harp", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES)
     ap.add_argument("--size", type=int, default=SIZE)
+    ap.add_argument("--model", default="hand", choices=["hand", "arm"], help="arm = SMPL-X arm sub-mesh (BASELINE.json configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
@@ -163,7 +165,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     B, S = args.frames, args.size
-    hc, _, _ = scene.make_context(device=dev)
+    hc, _, _ = scene.make_context(device=dev, model=args.model)
     sc = scene.make_scene(hc, B, S, seed=1, frame_offset=rank * B, total_frames=world * B)
     ft = HarpFitter(hc, sc["params"], sc["frames"], sc["ref_verts"], sc["uv_mask"], S, sc["focal"], world_size=world)
     fid = torch.arange(B, device=dev)
@@ -223,31 +225,14 @@ def main():
     cnt = hc.counters()
     losses = ft.loss_dict()
 
-    # ---- end to end through the public call with HOST image buffers (pinned): every step copies its 64 frames
-    # (y_true, y_sil, y_sil_eroded: 335 MB fp32, the reference's DataLoader dtypes) host->device and reads the loss vector
-    # back device->host.  Copies run on a second stream into double-buffered staging tensors so that step i+1's upload
-    # overlaps step i's kernels; the loss of step i is read (pinned, async) while step i+1 runs.
-    host = {k: ft.frames[k].cpu().pin_memory() for k in ("y_true", "y_sil", "y_sil_eroded")}
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = len(LOSS_NAMES) * 4
-    k_e2e = 0 if args.no_e2e else max(3, min(args.steps, 10))
-    e2e_s = torch.tensor([1e-9], device=dev)
-    if k_e2e:
-        stages, runs = [], []
-        for _ in range(2):
-            stg = {k: torch.empty_like(ft.frames[k]) for k in host}
-            stg["init_joints"] = ft.frames["init_joints"]
-            stages.append(stg)
-            if use_graph:
-                runs.append(ft.capture(fid, oa, on, stage="both", batch=stg, warmup=1))
-            else:
-                runs.append(lambda stg=stg: ft.step(fid, oa, on, stage="both", update=True, batch=stg))
-        copy_stream = torch.cuda.Stream(device=dev)
-        main = torch.cuda.current_stream()
+    def e2e_leg(host, make_stage, make_run, n):
+        """Double-buffered: uploads on a copy stream, step i+1's upload overlaps step i's kernels; the loss vector of
+        step i is read back (pinned, async) while step i+1 runs.  Returns wall seconds for n steps."""
+        stages = [make_stage() for _ in range(2)]
+        runs = [make_run(s) for s in stages]
+        copy_stream, main = torch.cuda.Stream(device=dev), torch.cuda.current_stream()
         loss_host = [torch.empty(len(LOSS_NAMES), pin_memory=True) for _ in range(2)]
-        copied = [torch.cuda.Event() for _ in range(2)]
-        done = [torch.cuda.Event() for _ in range(2)]
-        loss_ready = [torch.cuda.Event() for _ in range(2)]
+        copied, done, ready = ([torch.cuda.Event() for _ in range(2)] for _ in range(3))
 
         def upload(i):
             s = i % 2
@@ -257,35 +242,72 @@ def main():
                     stages[s][k].copy_(v, non_blocking=True)
                 copied[s].record(copy_stream)
 
-        def e2e_loop(n):
+        def loop(k):
             seen = []
             upload(0)
-            for i in range(n):
+            for i in range(k):
                 s = i % 2
-                if i + 1 < n:
+                if i + 1 < k:
                     upload(i + 1)
                 main.wait_event(copied[s])
                 runs[s]()
                 done[s].record(main)
                 loss_host[s].copy_(ft.losses, non_blocking=True)
-                loss_ready[s].record(main)
-                if i > 0:  # read the previous step's losses on the host while this step runs
-                    loss_ready[1 - s].synchronize()
+                ready[s].record(main)
+                if i > 0:
+                    ready[1 - s].synchronize()
                     seen.append(float(loss_host[1 - s][0]))
-            loss_ready[(n - 1) % 2].synchronize()
-            seen.append(float(loss_host[(n - 1) % 2][0]))
+            ready[(k - 1) % 2].synchronize()
+            seen.append(float(loss_host[(k - 1) % 2][0]))
             return seen
 
         for ev in done:
             ev.record(main)
-        e2e_loop(2)
+        loop(2)
         sync()
         t0 = time.perf_counter()
-        e2e_loop(k_e2e)
+        loop(n)
         sync()
-        e2e_s = torch.tensor([max(time.perf_counter() - t0, 1e-9)], device=dev)
+        sec = torch.tensor([max(time.perf_counter() - t0, 1e-9)], device=dev)
         if world > 1:
-            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+            dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+        return float(sec)
+
+    # ---- end to end through the public call with HOST image buffers (pinned): every step copies its frames host->device
+    # and reads the loss vector back.  Leg 1: fp32 y_true / y_sil / y_sil_eroded, the dtypes the reference's DataLoader
+    # yields (20 B/pixel).  Leg 2: the uint8 frames + masks the image files decode to (4 B/pixel), converted and eroded on
+    # the device (harp_ingest_u8) — reported separately as e2e_uint8.
+    host = {k: ft.frames[k].cpu().pin_memory() for k in ("y_true", "y_sil", "y_sil_eroded")}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = len(LOSS_NAMES) * 4
+    k_e2e = 0 if args.no_e2e else max(3, min(args.steps, 10))
+    e2e_s = e2e_u8_s = 1e-9
+    h2d_u8 = 0
+    if k_e2e:
+        def stage_f32():
+            s = {k: torch.empty_like(ft.frames[k]) for k in host}
+            s["init_joints"] = ft.frames["init_joints"]
+            return s
+
+        def run_f32(s):
+            if use_graph:
+                return ft.capture(fid, oa, on, stage="both", batch=s, warmup=1)
+            return lambda: ft.step(fid, oa, on, stage="both", update=True, batch=s)
+
+        e2e_s = e2e_leg(host, stage_f32, run_f32, k_e2e)
+        host_u8 = {"rgb": (ft.frames["y_true"] * 255).round().clamp(0, 255).to(torch.uint8).cpu().pin_memory(),
+                   "mask": (ft.frames["y_sil"] * 255).round().to(torch.uint8).cpu().pin_memory()}
+        h2d_u8 = sum(v.numel() for v in host_u8.values())
+
+        def stage_u8():
+            return {k: torch.empty(v.shape, dtype=torch.uint8, device=dev) for k, v in host_u8.items()}
+
+        def run_u8(s):
+            if use_graph:
+                return ft.capture(fid, oa, on, stage="both", batch_u8=s, warmup=1)
+            return lambda: ft.step(fid, oa, on, stage="both", update=True, batch_u8=s)
+
+        e2e_u8_s = e2e_leg(host_u8, stage_u8, run_u8, k_e2e)
 
     if rank == 0:
         value = world * B * args.steps / (ms_total * 1e-3)
@@ -309,15 +331,18 @@ def main():
         achieved = alg[dom] / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+            if args.model == "hand" and S == SIZE and B == FRAMES:  # the ncu capture is of the default workload
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
         except Exception:
             pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": config(world, B, S),
+                "dtype": "f32", "data": "synthetic", "config": config(world, B, S, args.model),
                 "clocks": clk,
-                "e2e": {"value": world * B * k_e2e / float(e2e_s), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": k_e2e},
+                "e2e": {"value": world * B * k_e2e / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": k_e2e, "host_dtype": "fp32 (the reference DataLoader's tensors)"},
+                "e2e_uint8": {"value": world * B * k_e2e / e2e_u8_s, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
+                              "steps": k_e2e, "host_dtype": "uint8 frames + masks, /255 and 3x3x2 erosion on the device"},
                 "gpu_launches": int(launches), "launch_mode": "cuda_graph_replay" if use_graph else "eager",
                 "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -89,6 +89,31 @@ __global__ void __launch_bounds__(TPB) adam_kernel(float* __restrict__ p, const 
   p[i] -= (lr / bc1) * (mi / denom);
 }
 
+// load_img (utils/data_util.py:11-30): /255 in double then float32 like numpy -> torch.Tensor; two 3x3 erosions = one
+// 5x5 minimum with out-of-image taps ignored (cv2.erode's default border value is +inf)
+__global__ void __launch_bounds__(TPB) ingest_u8_kernel(int B, int S, const uint8_t* __restrict__ rgb, const uint8_t* __restrict__ mask,
+                                                         float* __restrict__ y_true, float* __restrict__ y_sil,
+                                                         float* __restrict__ y_er) {
+  size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (size_t)B * S * S) return;
+  int rem = (int)(pix % ((size_t)S * S)), row = rem / S, col = rem % S;
+  const uint8_t* mb = mask + (pix - rem);
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) y_true[pix * 3 + ch] = (float)((double)rgb[pix * 3 + ch] / 255.0);
+  y_sil[pix] = (float)((double)mask[pix] / 255.0);
+  int mn = 255;
+  for (int dy = -2; dy <= 2; ++dy) {
+    int r = row + dy;
+    if (r < 0 || r >= S) continue;
+    for (int dx = -2; dx <= 2; ++dx) {
+      int cc = col + dx;
+      if (cc < 0 || cc >= S) continue;
+      mn = min(mn, (int)mb[r * S + cc]);
+    }
+  }
+  y_er[pix] = (float)((double)mn / 255.0);
+}
+
 struct AdamState {
   int step;
   float bc1, bc2_sqrt;
@@ -126,6 +151,15 @@ extern "C" int harp_adam_dev(float* param, const float* grad, float* exp_avg, fl
     adam_dev_kernel<<<(int)((n + TPB - 1) / TPB), TPB, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                                 (const AdamState*)state);
   HARP_LAUNCH_CHECK_N(2);
+  return HARP_OK;
+}
+
+extern "C" int harp_ingest_u8(int B, int S, const uint8_t* rgb_u8, const uint8_t* mask_u8, float* y_true, float* y_sil,
+                              float* y_sil_eroded, void* stream) {
+  HARP_REQUIRE(B > 0 && S > 0 && rgb_u8 && mask_u8 && y_true && y_sil && y_sil_eroded, HARP_ERR_INVALID, "harp_ingest_u8: bad argument");
+  size_t n = (size_t)B * S * S;
+  ingest_u8_kernel<<<(int)((n + TPB - 1) / TPB), TPB, 0, (cudaStream_t)stream>>>(B, S, rgb_u8, mask_u8, y_true, y_sil, y_sil_eroded);
+  HARP_LAUNCH_CHECK();
   return HARP_OK;
 }
 

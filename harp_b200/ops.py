@@ -385,3 +385,18 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999
     """In-place fused Adam on flat fp32 CUDA tensors (torch.optim.Adam defaults; optimize_sequence.py:253-310)."""
     check(_lib.lib().harp_adam(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), float(lr), float(beta1),
                                float(beta2), float(eps), int(step), stream()))
+
+
+def ingest_u8(rgb_u8, mask_u8, out=None):
+    """`load_img` (utils/data_util.py:11-30) on the device: uint8 frames (B,S,S,3) and masks (B,S,S) ->
+    dict(y_true, y_sil, y_sil_eroded) fp32, the eroded mask being cv2.erode(3x3, iterations=2)."""
+    if rgb_u8.dtype != torch.uint8 or mask_u8.dtype != torch.uint8:
+        raise _lib.HarpError("ingest_u8 needs uint8 tensors")
+    B, S = mask_u8.shape[0], mask_u8.shape[1]
+    dev = rgb_u8.device
+    if out is None:
+        out = dict(y_true=torch.empty(B, S, S, 3, device=dev), y_sil=torch.empty(B, S, S, device=dev),
+                   y_sil_eroded=torch.empty(B, S, S, device=dev))
+    check(_lib.lib().harp_ingest_u8(B, S, ptr(rgb_u8), ptr(mask_u8), ptr(out["y_true"]), ptr(out["y_sil"]), ptr(out["y_sil_eroded"]),
+                                    stream()))
+    return out

@@ -8,14 +8,21 @@ perturbed parameter set (pose noise, camera shift, different texture seed), mask
 import torch
 
 from . import camera, synth
-from .ops import HarpContext, LbsMano, MeshBuild, Shade, Silhouette
+from .body_models import SMPLXARM
+from .ops import HarpContext, Lbs, LbsMano, MeshBuild, Shade, Silhouette
 
 
-def make_context(device="cuda:0", subdivide=True, seed=0):
-    tmpl = synth.load_template("hand")
-    pack = synth.make_mano_pack(seed=seed, template=tmpl)
-    hc = HarpContext(pack["th_faces"], subdivide=subdivide, faces_uvs=tmpl["faces_uvs"], verts_uvs=tmpl["verts_uvs"],
-                     mano=pack, device=device)
+def make_context(device="cuda:0", subdivide=True, seed=0, model="hand"):
+    """model 'hand': MANO-shaped synthetic pack (778 -> 3093 verts); 'arm': SMPL-X-arm-shaped pack (1026 -> 4083 verts)."""
+    tmpl = synth.load_template(model)
+    if model == "arm":
+        pack = synth.make_smplx_pack(seed=seed, template=tmpl)
+        hc = HarpContext(tmpl["faces0"], subdivide=subdivide, faces_uvs=tmpl["faces_uvs"], verts_uvs=tmpl["verts_uvs"],
+                         lbs=synth.reduce_smplx_arm(pack, tmpl), device=device)
+    else:
+        pack = synth.make_mano_pack(seed=seed, template=tmpl)
+        hc = HarpContext(pack["th_faces"], subdivide=subdivide, faces_uvs=tmpl["faces_uvs"], verts_uvs=tmpl["verts_uvs"],
+                         mano=pack, device=device)
     return hc, pack, tmpl
 
 
@@ -28,8 +35,12 @@ def render_frames(hc, p, S, focal, chunk=16, self_shadow=True):
     for a in range(0, T, chunk):
         sl = slice(a, min(a + chunk, T))
         B = sl.stop - sl.start
-        pose48 = torch.cat((p["rot"][sl], p["pose"][sl]), 1).to(dev)
-        verts0, joints = LbsMano.apply(hc, pose48, p["shape"].to(dev), p["trans"][sl].to(dev))
+        if hc.J == 55:
+            full = SMPLXARM.assemble_full_pose(p["rot"][sl].to(dev), p["pose"][sl].to(dev), p["wrist_pose"][sl].to(dev))
+            verts0, joints = Lbs.apply(hc, full, p["shape"].to(dev), p["trans"][sl].to(dev))
+        else:
+            pose48 = torch.cat((p["rot"][sl], p["pose"][sl]), 1).to(dev)
+            verts0, joints = LbsMano.apply(hc, pose48, p["shape"].to(dev), p["trans"][sl].to(dev))
         verts, normals = MeshBuild.apply(hc, verts0, p["verts_disps"].to(dev))
         cR = camera.flip_xy_R(B, dev)
         cT = camera.cam_to_T(p["cam"][sl].to(dev), focal, S)
@@ -54,6 +65,10 @@ def make_scene(hc, T, S, seed=1, frame_offset=0, total_frames=None):
     params = dict(pose=seq["pose"][sl], rot=seq["rot"][sl], trans=seq["trans"][sl], cam=seq["cam"][sl], shape=seq["shape"],
                   verts_disps=torch.zeros(hc.V, 1), texture=app["texture"], normal_map=app["normal_map"],
                   light_positions=app["light_position"][None].repeat(T, 1), amb_ratio=app["amb_ratio"])
+    arm = hc.J == 55
+    if arm:  # wrist-centred arm lying along -x (body_models.py:2342): smaller weak-perspective scale, shifted into frame
+        params["wrist_pose"] = 0.1 * torch.sin(torch.arange(total)[:, None] * 0.3 + torch.tensor([0.0, 1.0, 2.0]))[sl].float()
+        params["cam"] = params["cam"] * torch.tensor([0.35, 1.0, 1.0]) + torch.tensor([0.0, 0.15, 0.0])
     g = torch.Generator().manual_seed(100 + seed)
     tgt = dict(params)
     noise = 0.05 * torch.randn(total, 45, generator=g)
@@ -64,12 +79,14 @@ def make_scene(hc, T, S, seed=1, frame_offset=0, total_frames=None):
     sil, rgb, _, joints = render_frames(hc, tgt, S, focal)
     y_sil = (sil >= 0.5).float()
     frames = dict(y_true=rgb.clamp(0, 1).contiguous(), y_sil=y_sil, y_sil_eroded=synth.erode_mask(y_sil).contiguous(),
-                  init_joints=(joints * 1000.0).contiguous())
-    first = {k: (v[:1] if k in ("pose", "rot", "trans", "cam", "light_positions") else v) for k, v in params.items()}
+                  init_joints=(joints[:, :21] * 1000.0).contiguous())
+    first = {k: (v[:1] if k in ("pose", "rot", "trans", "cam", "light_positions", "wrist_pose") else v) for k, v in params.items()}
     if frame_offset != 0:  # the ARAP reference is frame 0 of the WHOLE sequence on every rank
-        first.update(pose=seq["pose"][:1], rot=seq["rot"][:1], trans=seq["trans"][:1], cam=seq["cam"][:1])
+        first.update(pose=seq["pose"][:1], rot=seq["rot"][:1], trans=seq["trans"][:1])
+        if arm:
+            first["wrist_pose"] = 0.1 * torch.sin(torch.zeros(1, 1) + torch.tensor([0.0, 1.0, 2.0])).float()
     _, _, ref_verts, _ = render_frames(hc, first, S, focal)
-    tmpl = synth.load_template("hand")
+    tmpl = synth.load_template("arm" if arm else "hand")
     offsets = dict(albedo=synth.make_reg_offsets(seed=3, std=1.0).to(dev).contiguous(),
                    normal=synth.make_reg_offsets(seed=4, std=2.0).to(dev).contiguous())
     return dict(params=params, frames=frames, ref_verts=ref_verts[:1].contiguous(),

@@ -136,10 +136,13 @@ class HarpFitter:
         return t
 
     # -- one minibatch ----------------------------------------------------------------------------------------------------
-    def step(self, fid, off_albedo, off_normal, stage="both", update=True, batch=None, frame_range=None, exchange=True):
+    def step(self, fid, off_albedo, off_normal, stage="both", update=True, batch=None, frame_range=None, exchange=True,
+             batch_u8=None):
         """fid: (B,) long device tensor of frame ids owned by this rank.  stage: 'coarse' | 'both' | 'app'
         (`optimize_sequence.py:507-515`).  batch: optional dict overriding self.frames rows (host->device ingest path).
         frame_range=(a,b): promise that fid == arange(a,b), so image rows are used in place instead of gathered.
+        batch_u8: dict(rgb (B,S,S,3) uint8, mask (B,S,S) uint8) device tensors as decoded from the image files; converted
+        (and the mask eroded) on the device like `load_img` (utils/data_util.py:11-30).
         Returns the device tensor of unweighted losses (LOSS_NAMES order); gradients are in self.coarse.grad / self.app.grad."""
         hc, L, S, focal = self.hc, _lib.lib(), self.S, self.focal
         dev, st = hc.device, stream()
@@ -149,7 +152,13 @@ class HarpFitter:
         hc.reserve(B, S)
         P, A = self.coarse.p, self.app.p
         coarse_on, app_on = stage in ("coarse", "both"), stage in ("both", "app")
-        if batch is not None:
+        if batch_u8 is not None:
+            from .ops import ingest_u8
+            fr = ingest_u8(batch_u8["rgb"], batch_u8["mask"],
+                           out=dict(y_true=self._buf("u8_y_true", (B, S, S, 3), zero=False), y_sil=self._buf("u8_y_sil", (B, S, S), zero=False),
+                                    y_sil_eroded=self._buf("u8_y_er", (B, S, S), zero=False)))
+            fr["init_joints"] = batch_u8["init_joints"] if "init_joints" in batch_u8 else self.frames["init_joints"].index_select(0, fid)
+        elif batch is not None:
             fr = batch
         elif frame_range is not None:
             fr = {k: v[frame_range[0]:frame_range[1]] for k, v in self.frames.items()}
@@ -260,12 +269,13 @@ class HarpFitter:
             self.app.adam(self.lr_app)
 
     # -- CUDA-graph replay ------------------------------------------------------------------------------------------------
-    def capture(self, fid, off_albedo, off_normal, stage="both", frame_range=None, batch=None, warmup=2, keep_profile=False):
+    def capture(self, fid, off_albedo, off_normal, stage="both", frame_range=None, batch=None, warmup=2, keep_profile=False,
+                batch_u8=None):
         """Record one optimiser step (all C-ABI launches + the small torch glue) into a CUDA graph.  The ~120 launches of
         a step then replay back to back; inputs are read from the same device buffers every replay (fid, offsets, the
         resident frames or the staging `batch`).  Returns a callable; each call runs one step (update=True)."""
         multi = self.world_size > 1  # the NCCL allreduce and the two Adam launches stay outside the graph
-        kw = dict(stage=stage, frame_range=frame_range, batch=batch)
+        kw = dict(stage=stage, frame_range=frame_range, batch=batch, batch_u8=batch_u8)
         if not keep_profile:
             self.hc.profile(False)
         side = torch.cuda.Stream(device=self.hc.device)

@@ -217,6 +217,13 @@ HARP_API int harp_render_fused(harp_ctx*, int B, int S, float focal, const harp_
 HARP_API int harp_texture_reg(harp_ctx*, int kind, const float* map, int H, int W, const int32_t* offsets, const float* uv_mask,
                      float weight, float* loss, float* d_map, void* stream);
 
+/* ---- uint8 frame ingest: load_img of utils/data_util.py:11-30 on the device ---------------------------------------------
+ * rgb_u8 (B,S,S,3), mask_u8 (B,S,S) as decoded from the JPEG / PNG files -> y_true = rgb/255 (B,S,S,3) fp32,
+ * y_sil = mask/255 (B,S,S), y_sil_eroded = cv2.erode(mask/255, ones(3,3), iterations=2) (border pixels ignore the outside).
+ * Moves 4 bytes per pixel over PCIe instead of the 20 the reference's fp32 DataLoader tensors need. */
+HARP_API int harp_ingest_u8(int B, int S, const uint8_t* rgb_u8, const uint8_t* mask_u8, float* y_true, float* y_sil,
+                            float* y_sil_eroded, void* stream);
+
 /* ---- Adam (torch.optim.Adam defaults, optimize_sequence.py:253-310,567-573), fused over a flat buffer ----------------*/
 HARP_API int harp_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
               float beta2, float eps, int step, void* stream);
