@@ -40,7 +40,8 @@ class HarpShadeGrads(C.Structure):
 class HarpRenderArgs(C.Structure):
     _fields_ = ([(n, C.c_void_p) for n in ("verts", "normals", "cam_R", "cam_T", "light_R", "light_T", "light_pos", "amb",
                                             "texture", "normal_map")] +
-                [("texH", C.c_int32), ("texW", C.c_int32), ("self_shadow", C.c_int32), ("sigma", C.c_float)] +
+                [("texH", C.c_int32), ("texW", C.c_int32), ("self_shadow", C.c_int32), ("faces_per_pixel", C.c_int32),
+                 ("sigma", C.c_float)] +
                 [(n, C.c_void_p) for n in ("y_sil", "y_true", "y_mask")] + [("w_sil", C.c_float), ("w_photo", C.c_float)] +
                 [(n, C.c_void_p) for n in ("alpha", "rgb", "loss_sil", "loss_photo")] + [("grads", HarpShadeGrads)])
 
@@ -87,7 +88,7 @@ def lib():
         L.harp_vertex_normals_fwd.argtypes = [vp, i, vp, vp, vp]
         L.harp_vertex_normals_bwd.argtypes = [vp, i, vp, vp, vp, vp]
         L.harp_mesh_losses.argtypes = [vp, i, vp, vp, vp, vp, vp, c_float_p, vp, vp, vp, vp, vp]
-        L.harp_silhouette.argtypes = [vp, i, i, i, f, f, vp, vp, vp, vp, vp, f, vp, vp, vp, vp, vp]
+        L.harp_silhouette.argtypes = [vp, i, i, i, f, f, i, vp, vp, vp, vp, vp, f, vp, vp, vp, vp, vp]
         L.harp_shade.argtypes = [vp, i, i, i, f, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, f, vp,
                                  C.POINTER(HarpShadeGrads), vp]
         L.harp_render_fused.argtypes = [vp, i, i, f, C.POINTER(HarpRenderArgs), vp]

@@ -91,7 +91,10 @@ struct harp_ctx {
   float* vN = nullptr;            // (B,V,3) unnormalised vertex normals (mesh build scratch)
   float* vtmp = nullptr;          // (B,V,3) scratch
   float* vtmp2 = nullptr;         // (B,V,3) scratch
-  unsigned long long* counters = nullptr;  // [0] K overflow pixels, [1] bin overflow
+  int32_t* ovf_list = nullptr;    // pixels (b*S*S + row*S + col) deferred to the exact top-K silhouette kernel
+  int32_t* ovf_count = nullptr;   // (1)
+  int ovf_cap = 0;
+  unsigned long long* counters = nullptr;  // [0] top-K pixels that could not be handled exactly, [1] bin overflow
   struct harp_prof* prof = nullptr;        // host-side event lists (harp_ctx_profile)
 };
 

@@ -237,7 +237,8 @@ extern "C" int harp_ctx_create_lbs(harp_ctx** out, const harp_topology* topo, co
 static void free_scratch(harp_ctx* c) {
   void* ptrs[] = {c->ndc_cam, c->ndc_light, c->d_ndc_cam, c->d_ndc_light, c->bin_count, c->bin_start, c->bin_fill,
                   c->bin_list, c->light_zbuf, c->light_face, c->d_light_zbuf, c->vN, c->vtmp, c->vtmp2, c->d_verts4,
-                  c->d_normals4, c->vis_fid, c->hit_list, c->hit_count};
+                  c->d_normals4, c->vis_fid, c->hit_list, c->hit_count, c->ovf_list, c->ovf_count};
+  c->ovf_list = c->ovf_count = nullptr;
   c->d_verts4 = c->d_normals4 = nullptr;
   c->vis_fid = c->hit_list = c->hit_count = nullptr;
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -292,6 +293,9 @@ extern "C" int harp_ctx_reserve(harp_ctx* c, int max_batch, int img_size) {
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->vis_fid, npx * sizeof(int32_t)));
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->hit_list, npx * sizeof(int32_t)));
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->hit_count, (size_t)B * sizeof(int32_t)));
+  c->ovf_cap = (int)std::min<size_t>(npx, (size_t)1 << 22);
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->ovf_list, (size_t)c->ovf_cap * sizeof(int32_t)));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->ovf_count, sizeof(int32_t)));
   c->maxB = B;
   c->S = S;
   c->tiles = tiles;

@@ -13,6 +13,8 @@ int harp_project_bwd(harp_ctx* c, int B, int S, float focal, const float* verts,
 int harp_fold4(size_t n, const float* src4, float* dst3, cudaStream_t st);
 int harp_light_depth(harp_ctx* c, int B, int S, cudaStream_t st);
 int harp_light_depth_bwd(harp_ctx* c, int B, int S, cudaStream_t st);
+int harp_sil_topk(harp_ctx* c, int mode, int S, int K, float sigma, float blur, float radius, float* alpha, const float* gin,
+                  float gscale, float inv_n, float* loss, cudaStream_t st);
 
 namespace {
 
@@ -21,7 +23,7 @@ constexpr int NT = HARP_TILE * HARP_TILE;
 constexpr int QCAP = 512;
 
 struct VisArgs {
-  int S;
+  int S, K;
   float sigma, blur, radius;
   const float* ndc;
   const int32_t *bin_count, *bin_start, *bin_list;
@@ -39,26 +41,6 @@ struct VisArgs {
   float photo_inv_n;
   float* photo_loss;
 };
-
-__device__ __forceinline__ void sil_pair_gradient2(const FaceRec& f, float px, float py, float sd, int edge, float t, float g,
-                                                   float prod, float sigma, float* d_ndc) {
-  float prob = 1.f / (1.f + expf(fdiv(sd, sigma)));
-  float gsd = g * (-prod * prob / sigma);
-  float gd = sd < 0.f ? -gsd : gsd;
-  if (gd == 0.f) return;
-  float ax, ay, bx, by; int va, vb;
-  if (edge == 0) { ax = f.x0; ay = f.y0; bx = f.x1; by = f.y1; va = f.v0; vb = f.v1; }
-  else if (edge == 1) { ax = f.x0; ay = f.y0; bx = f.x2; by = f.y2; va = f.v0; vb = f.v2; }
-  else { ax = f.x1; ay = f.y1; bx = f.x2; by = f.y2; va = f.v1; vb = f.v2; }
-  if (t < 0.f) {
-    atomicAdd(reinterpret_cast<float2*>(d_ndc + (size_t)vb * 4), make_float2(gd * 2.f * (bx - px), gd * 2.f * (by - py)));
-    return;
-  }
-  float qx = ax + t * (bx - ax), qy = ay + t * (by - ay);
-  float dx = 2.f * gd * (qx - px), dy = 2.f * gd * (qy - py);
-  atomicAdd(reinterpret_cast<float2*>(d_ndc + (size_t)va * 4), make_float2((1.f - t) * dx, (1.f - t) * dy));
-  atomicAdd(reinterpret_cast<float2*>(d_ndc + (size_t)vb * 4), make_float2(t * dx, t * dy));
-}
 
 // SIL_BWD: accumulate the silhouette L1 loss and its gradient (COARSE_OPT stages); PHOTO: accumulate the photometric loss
 // of background pixels (APP_OPT stages; hit pixels are handled by the deferred shading kernel).
@@ -84,7 +66,7 @@ __global__ void __launch_bounds__(NT) pixel_vis_kernel(harp_ctx c, VisArgs a) {
   const float sigma = a.sigma, blur = a.blur;
   float px = pix_to_ndc(col, S), py = pix_to_ndc(row, S);
   float prod = 1.f;
-  int nzero = 0, npass = 0;
+  int nzero = 0, npass = 0, ncand = 0;
   int best_fid = -1;
   float best_q = 0.f;
   bool q_overflow = false;
@@ -111,6 +93,7 @@ __global__ void __launch_bounds__(NT) pixel_vis_kernel(harp_ctx c, VisArgs a) {
         q = e.pass ? 1.f / e.pz : 0.f;
       }
       if (inside) vis_update(c, ndc, px, py, f.fid, q, best_fid, best_q);
+      ++ncand;  // upper bound on the faces PyTorch3D would consider (exact top-K decision after the loop)
       if (nzero > 0) continue;
       if (cls == PAIR_SATURATED) { ++npass; ++nzero; continue; }
       int slot = atomicAdd(&q_n, 1);
@@ -176,10 +159,11 @@ __global__ void __launch_bounds__(NT) pixel_vis_kernel(harp_ctx c, VisArgs a) {
   }
   // ---- silhouette value, loss and gradient
   float al = nzero > 0 ? 1.f : 1.f - prod;
-  if (npass > 50) atomicAdd(c.counters, 1ULL);
-  a.alpha[pix] = al;
+  const bool deferred = ncand > a.K;  // more candidates than faces_per_pixel -> exact top-K kernel
+  if (deferred) sil_defer_overflow(c, (int)pix);
+  else a.alpha[pix] = al;
   if (!SIL_BWD) return;
-  float diff = al - a.y_sil[pix];
+  float diff = deferred ? 0.f : al - a.y_sil[pix];
   float g = diff > 0.f ? a.sil_gscale : (diff < 0.f ? -a.sil_gscale : 0.f);
   {
     float s = block_sum(fabsf(diff), red);
@@ -197,7 +181,7 @@ __global__ void __launch_bounds__(NT) pixel_vis_kernel(harp_ctx c, VisArgs a) {
       int p = q_pix[s];
       if (!s_need[p] || q_edge[s] == 255) continue;
       float ppx = pix_to_ndc(blockIdx.x * HARP_TILE + (p % HARP_TILE), S), ppy = pix_to_ndc(blockIdx.y * HARP_TILE + (p / HARP_TILE), S);
-      sil_pair_gradient2(faces[q_face[s]], ppx, ppy, q_sd[s], q_edge[s], q_t[s], s_g[p], s_prod[p], sigma, d_ndc);
+      sil_pair_gradient(faces[q_face[s]], ppx, ppy, q_sd[s], q_edge[s], q_t[s], s_g[p], s_prod[p], sigma, d_ndc);
     }
     return;
   }
@@ -211,7 +195,7 @@ __global__ void __launch_bounds__(NT) pixel_vis_kernel(harp_ctx c, VisArgs a) {
       PairEval e;
       eval_pair<true, true>(faces[i], px, py, blur, sat, e);
       if (!e.pass || e.saturated) continue;
-      sil_pair_gradient2(faces[i], px, py, e.inside ? -e.dist : e.dist, e.edge, e.t, g, prod, sigma, d_ndc);
+      sil_pair_gradient(faces[i], px, py, e.inside ? -e.dist : e.dist, e.edge, e.t, g, prod, sigma, d_ndc);
     }
   }
 }
@@ -300,8 +284,9 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
     }
   }
   HARP_CHECK_CUDA(cudaMemsetAsync(c->hit_count, 0, (size_t)B * sizeof(int32_t), st));
+  HARP_CHECK_CUDA(cudaMemsetAsync(c->ovf_count, 0, sizeof(int32_t), st));
   VisArgs v{};
-  v.S = S; v.sigma = r->sigma; v.blur = blur; v.radius = radius; v.ndc = c->ndc_cam;
+  v.S = S; v.K = r->faces_per_pixel > 0 ? r->faces_per_pixel : 50; v.sigma = r->sigma; v.blur = blur; v.radius = radius; v.ndc = c->ndc_cam;
   v.bin_count = c->bin_count; v.bin_start = c->bin_start; v.bin_list = c->bin_list;
   v.alpha = r->alpha; v.y_sil = r->y_sil; v.sil_inv_n = 1.f / ((float)B * S * S); v.sil_gscale = r->w_sil * v.sil_inv_n;
   v.sil_loss = r->loss_sil; v.d_ndc = c->d_ndc_cam;
@@ -316,6 +301,8 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
   else pixel_vis_kernel<false, false><<<grid, NT, 0, st>>>(*c, v);
   harp_prof_end(c, 0, st);
   HARP_LAUNCH_CHECK();
+  if ((rc = harp_sil_topk(c, sil_bwd ? 2 : 0, S, v.K, r->sigma, blur, radius, r->alpha, r->y_sil, v.sil_gscale, v.sil_inv_n,
+                          r->loss_sil, st)) != HARP_OK) return rc;
   ShadeArgs a{};
   a.B = B; a.S = S; a.self_shadow = r->self_shadow; a.texH = r->texH; a.texW = r->texW; a.focal = focal;
   a.inv_n = v.photo_inv_n; a.gscale = r->w_photo * a.inv_n;

@@ -162,30 +162,8 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(harp_ctx c, int tiles, c
 // convergent classification pass queues them per tile in shared memory and all 64 threads drain the queue.
 constexpr int QCAP = 512;
 
-__device__ __forceinline__ void sil_pair_gradient(const FaceRec& f, float px, float py, float sd, int edge, float t, float g,
-                                                  float prod, float sigma, float* d_ndc) {
-  float prob = 1.f / (1.f + expf(fdiv(sd, sigma)));
-  // alpha = 1 - prod_k(1-p_k):  d alpha / d sd_k = -(prod) * p_k / sigma   (no exact-zero factor on this path)
-  float gsd = g * (-prod * prob / sigma);
-  float gd = sd < 0.f ? -gsd : gsd;  // w.r.t. the unsigned squared distance (inside <=> signed distance negative)
-  if (gd == 0.f) return;
-  float ax, ay, bx, by; int va, vb;
-  if (edge == 0) { ax = f.x0; ay = f.y0; bx = f.x1; by = f.y1; va = f.v0; vb = f.v1; }
-  else if (edge == 1) { ax = f.x0; ay = f.y0; bx = f.x2; by = f.y2; va = f.v0; vb = f.v2; }
-  else { ax = f.x1; ay = f.y1; bx = f.x2; by = f.y2; va = f.v1; vb = f.v2; }
-  if (t < 0.f) {  // degenerate edge: dist = |p - b|^2
-    atomicAdd(reinterpret_cast<float2*>(d_ndc + (size_t)vb * 4), make_float2(gd * 2.f * (bx - px), gd * 2.f * (by - py)));
-    return;
-  }
-  // PointLineDistanceBackward: q = a + t (b - a), d = q - p ; grad_a = g (1-t) 2 d ; grad_b = g t 2 d
-  float qx = ax + t * (bx - ax), qy = ay + t * (by - ay);
-  float dx = 2.f * gd * (qx - px), dy = 2.f * gd * (qy - py);
-  atomicAdd(reinterpret_cast<float2*>(d_ndc + (size_t)va * 4), make_float2((1.f - t) * dx, (1.f - t) * dy));
-  atomicAdd(reinterpret_cast<float2*>(d_ndc + (size_t)vb * 4), make_float2(t * dx, t * dy));
-}
-
 template <int MODE>
-__global__ void __launch_bounds__(HARP_TILE* HARP_TILE) sil_kernel(harp_ctx c, int S, float sigma, float blur, float radius,
+__global__ void __launch_bounds__(HARP_TILE* HARP_TILE) sil_kernel(harp_ctx c, int S, int K, float sigma, float blur, float radius,
                                                                    const float* __restrict__ ndc_all,
                                                                    const int32_t* __restrict__ bin_count,
                                                                    const int32_t* __restrict__ bin_start,
@@ -213,7 +191,7 @@ __global__ void __launch_bounds__(HARP_TILE* HARP_TILE) sil_kernel(harp_ctx c, i
   const float* ndc = ndc_all + (size_t)b * c.V * 3;
   float px = pix_to_ndc(col, S), py = pix_to_ndc(row, S);
   float prod = 1.f;
-  int nzero = 0, npass = 0;
+  int nzero = 0, npass = 0, ncand = 0;
   bool q_overflow = false;
   const float sat = 17.5f * sigma;
   if (tid == 0) { any_bwd = 0; q_n = 0; }
@@ -224,11 +202,13 @@ __global__ void __launch_bounds__(HARP_TILE* HARP_TILE) sil_kernel(harp_ctx c, i
     if (tid == 0) q_n = 0;
     __syncthreads();
     // A: convergent classification; a pixel with one exactly-zero factor is final (alpha = 1, zero gradient)
-    if (nzero == 0) {
+    {
       for (int i = 0; i < m; ++i) {
         int cls = classify_pair<true>(faces[i], px, py, blur, sat);
         if (cls == PAIR_REJECT) continue;
-        if (cls == PAIR_SATURATED) { ++npass; ++nzero; break; }
+        ++ncand;  // upper bound on the faces PyTorch3D would consider for this pixel (exact top-K decision below)
+        if (nzero > 0) continue;
+        if (cls == PAIR_SATURATED) { ++npass; ++nzero; continue; }
         int slot = atomicAdd(&q_n, 1);
         if (slot < QCAP) {
           q_pix[slot] = (unsigned char)tid; q_face[slot] = (unsigned char)i;
@@ -239,8 +219,7 @@ __global__ void __launch_bounds__(HARP_TILE* HARP_TILE) sil_kernel(harp_ctx c, i
           if (!e.pass) continue;
           ++npass;
           float om = 1.f - 1.f / (1.f + expf(fdiv(e.inside ? -e.dist : e.dist, sigma)));
-          if (om == 0.f) { ++nzero; break; }
-          prod *= om;
+          if (om == 0.f) ++nzero; else prod *= om;
         }
       }
     }
@@ -266,18 +245,19 @@ __global__ void __launch_bounds__(HARP_TILE* HARP_TILE) sil_kernel(harp_ctx c, i
         prod *= om;
       }
     }
-    if (__syncthreads_and(nzero > 0)) break;  // whole tile saturated
   }
   float a = nzero > 0 ? 1.f : 1.f - prod;
-  if (npass > 50) atomicAdd(c.counters, 1ULL);
-  if (MODE != 1) alpha[pix] = a;
+  // more candidates than faces_per_pixel: PyTorch3D keeps only the K nearest in depth -> exact per-pixel kernel
+  const bool deferred = ncand > K;
+  if (deferred) sil_defer_overflow(c, (int)pix);
+  if (MODE != 1 && !deferred) alpha[pix] = a;
   if (MODE == 0) return;
   float g;  // dL/d alpha
   if (MODE == 1) {
-    g = gin[pix];
+    g = deferred ? 0.f : gin[pix];
   } else {
     float tgt = gin[pix];
-    float diff = a - tgt;
+    float diff = deferred ? 0.f : a - tgt;
     g = diff > 0.f ? gscale : (diff < 0.f ? -gscale : 0.f);
     float s = block_sum(fabsf(diff), red);
     if (tid == 0 && s != 0.f) atomicAdd(loss, s * inv_n);
@@ -314,6 +294,94 @@ __global__ void __launch_bounds__(HARP_TILE* HARP_TILE) sil_kernel(harp_ctx c, i
   }
 }
 
+// Exact PyTorch3D semantics for pixels with more candidate faces than faces_per_pixel: keep the K nearest in depth
+// (ties to the lower face id), blend only those.  One warp per deferred pixel; entries live in shared memory.
+// Reached only when faces are sub-pixel (tiny images) or very many layers overlap; never at the reference's 448^2.
+constexpr int TOPK_CAP = 512;   // passing faces per pixel handled exactly
+constexpr int TOPK_WARPS = 4;
+
+template <int MODE>
+__global__ void __launch_bounds__(32 * TOPK_WARPS) sil_topk_kernel(harp_ctx c, int S, int K, float sigma, float blur, float radius,
+                                                                    const float* __restrict__ ndc_all,
+                                                                    const int32_t* __restrict__ bin_count,
+                                                                    const int32_t* __restrict__ bin_start,
+                                                                    const int32_t* __restrict__ bin_list, float* __restrict__ alpha,
+                                                                    const float* __restrict__ gin, float gscale, float inv_n,
+                                                                    float* __restrict__ loss, float* __restrict__ d_ndc_all) {
+  __shared__ float e_pz[TOPK_WARPS][TOPK_CAP], e_sd[TOPK_WARPS][TOPK_CAP], e_t[TOPK_WARPS][TOPK_CAP];
+  __shared__ int e_fid[TOPK_WARPS][TOPK_CAP];
+  __shared__ unsigned char e_edge[TOPK_WARPS][TOPK_CAP], e_keep[TOPK_WARPS][TOPK_CAP];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = min(*c.ovf_count, c.ovf_cap);
+  const int tw = S / HARP_TILE;
+  for (int item = blockIdx.x * TOPK_WARPS + w; item < total; item += gridDim.x * TOPK_WARPS) {
+    int pix = c.ovf_list[item];
+    int b = pix / (S * S), rem = pix % (S * S), row = rem / S, col = rem % S;
+    size_t tglob = (size_t)b * tw * tw + (row / HARP_TILE) * tw + (col / HARP_TILE);
+    int n = bin_count[tglob], start = bin_start[tglob];
+    if (start + n > c.bin_cap) n = max(0, (int)c.bin_cap - start);
+    const int32_t* list = bin_list + (size_t)b * c.bin_cap + start;
+    const float* ndc = ndc_all + (size_t)b * c.V * 3;
+    float px = pix_to_ndc(col, S), py = pix_to_ndc(row, S);
+    int ne = 0;
+    for (int base = 0; base < n; base += 32) {
+      int i = base + lane;
+      bool pass = false;
+      PairEval e;
+      FaceRec f;
+      if (i < n) {
+        load_face(c, ndc, list[i], radius, f);
+        if (!(px > f.xmax || px < f.xmin || py > f.ymax || py < f.ymin)) {
+          eval_pair_full<true, true>(f, px, py, blur, e);
+          pass = e.pass;
+        }
+      }
+      unsigned m = __ballot_sync(0xffffffffu, pass);
+      int slot = ne + __popc(m & ((1u << lane) - 1u));
+      if (pass && slot < TOPK_CAP) {
+        e_pz[w][slot] = e.pz; e_sd[w][slot] = e.inside ? -e.dist : e.dist; e_t[w][slot] = e.t;
+        e_fid[w][slot] = f.fid; e_edge[w][slot] = (unsigned char)e.edge;
+      }
+      ne += __popc(m);
+    }
+    if (ne > TOPK_CAP) { if (lane == 0) atomicAdd(c.counters, 1ULL); ne = TOPK_CAP; }
+    __syncwarp();
+    // rank by (depth, face id); keep rank < K
+    for (int i = lane; i < ne; i += 32) {
+      float z = e_pz[w][i]; int fid = e_fid[w][i], rank = 0;
+      for (int j = 0; j < ne; ++j) rank += (e_pz[w][j] < z || (e_pz[w][j] == z && e_fid[w][j] < fid)) ? 1 : 0;
+      e_keep[w][i] = rank < K ? 1 : 0;
+    }
+    __syncwarp();
+    float prod = 1.f; int nzero = 0;
+    for (int i = lane; i < ne; i += 32) {
+      if (!e_keep[w][i]) continue;
+      float om = 1.f - 1.f / (1.f + expf(fdiv(e_sd[w][i], sigma)));
+      if (om == 0.f) ++nzero; else prod *= om;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { prod *= __shfl_xor_sync(0xffffffffu, prod, o); nzero += __shfl_xor_sync(0xffffffffu, nzero, o); }
+    float a = nzero > 0 ? 1.f : 1.f - prod;
+    if (MODE != 1 && lane == 0) alpha[pix] = a;
+    if (MODE == 0) continue;
+    float g;
+    if (MODE == 1) g = gin[pix];
+    else {
+      float diff = a - gin[pix];
+      g = diff > 0.f ? gscale : (diff < 0.f ? -gscale : 0.f);
+      if (lane == 0 && diff != 0.f) atomicAdd(loss, fabsf(diff) * inv_n);
+    }
+    if (g == 0.f || nzero > 0 || !(prod > 0.f)) continue;
+    float* d_ndc = d_ndc_all + (size_t)b * c.V * 4;
+    for (int i = lane; i < ne; i += 32) {
+      if (!e_keep[w][i]) continue;
+      FaceRec f;
+      load_face(c, ndc, e_fid[w][i], radius, f);
+      sil_pair_gradient(f, px, py, e_sd[w][i], e_edge[w][i], e_t[w][i], g, prod, sigma, d_ndc);
+    }
+  }
+}
+
 // dst (n,3) += src (n,4).xyz
 __global__ void __launch_bounds__(TPB) fold4_kernel(size_t n, const float4* __restrict__ src, float* __restrict__ dst) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -327,6 +395,18 @@ __global__ void __launch_bounds__(TPB) fold4_kernel(size_t n, const float4* __re
 inline int nblk(size_t n) { return (int)((n + TPB - 1) / TPB); }
 
 }  // namespace
+
+// Exact top-K pass over the pixels the tile kernels deferred (c->ovf_list); mode as harp_silhouette.
+int harp_sil_topk(harp_ctx* c, int mode, int S, int K, float sigma, float blur, float radius, float* alpha, const float* gin,
+                  float gscale, float inv_n, float* loss, cudaStream_t st) {
+  const int32_t *cnt = c->bin_count, *bst = c->bin_start, *lst = c->bin_list;
+  int grid = 2 * HARP_SM_COUNT;
+  if (mode == 0) sil_topk_kernel<0><<<grid, 32 * TOPK_WARPS, 0, st>>>(*c, S, K, sigma, blur, radius, c->ndc_cam, cnt, bst, lst, alpha, nullptr, 0.f, 0.f, nullptr, nullptr);
+  else if (mode == 1) sil_topk_kernel<1><<<grid, 32 * TOPK_WARPS, 0, st>>>(*c, S, K, sigma, blur, radius, c->ndc_cam, cnt, bst, lst, alpha, gin, 0.f, 0.f, nullptr, c->d_ndc_cam);
+  else sil_topk_kernel<2><<<grid, 32 * TOPK_WARPS, 0, st>>>(*c, S, K, sigma, blur, radius, c->ndc_cam, cnt, bst, lst, alpha, gin, gscale, inv_n, loss, c->d_ndc_cam);
+  HARP_LAUNCH_CHECK();
+  return HARP_OK;
+}
 
 int harp_fold4(size_t n, const float* src4, float* dst3, cudaStream_t st) {
   fold4_kernel<<<nblk(n), TPB, 0, st>>>(n, reinterpret_cast<const float4*>(src4), dst3);
@@ -365,7 +445,7 @@ int harp_project_bwd(harp_ctx* c, int B, int S, float focal, const float* verts,
   return HARP_OK;
 }
 
-extern "C" int harp_silhouette(harp_ctx* c, int mode, int B, int S, float focal, float sigma, const float* verts,
+extern "C" int harp_silhouette(harp_ctx* c, int mode, int B, int S, float focal, float sigma, int faces_per_pixel, const float* verts,
                                const float* R, const float* T, float* alpha, const float* gin, float weight, float* loss,
                                float* d_verts, float* d_R, float* d_T, void* stream) {
   HARP_REQUIRE(c && B > 0 && verts && R && T, HARP_ERR_INVALID, "harp_silhouette: null argument");
@@ -382,19 +462,22 @@ extern "C" int harp_silhouette(harp_ctx* c, int mode, int B, int S, float focal,
   if ((rc = harp_project(c, B, S, focal, verts, R, T, c->ndc_cam, st)) != HARP_OK) return rc;
   if ((rc = harp_build_bins(c, 0, B, S, radius, c->ndc_cam, st)) != HARP_OK) return rc;
   if (mode != 0) HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_cam, 0, (size_t)B * c->V * 4 * sizeof(float), st));
+  HARP_CHECK_CUDA(cudaMemsetAsync(c->ovf_count, 0, sizeof(int32_t), st));
+  const int K = faces_per_pixel > 0 ? faces_per_pixel : 50;
   dim3 grid(S / HARP_TILE, S / HARP_TILE, B);
   float inv_n = 1.f / ((float)B * (float)S * (float)S);
   float gscale = weight * inv_n;
   const int32_t *cnt = c->bin_count, *bst = c->bin_start, *lst = c->bin_list;
   harp_prof_begin(c, 0, st);
   if (mode == 0)
-    sil_kernel<0><<<grid, HARP_TILE * HARP_TILE, 0, st>>>(*c, S, sigma, blur, radius, c->ndc_cam, cnt, bst, lst, alpha, nullptr, 0.f, 0.f, nullptr, nullptr);
+    sil_kernel<0><<<grid, HARP_TILE * HARP_TILE, 0, st>>>(*c, S, K, sigma, blur, radius, c->ndc_cam, cnt, bst, lst, alpha, nullptr, 0.f, 0.f, nullptr, nullptr);
   else if (mode == 1)
-    sil_kernel<1><<<grid, HARP_TILE * HARP_TILE, 0, st>>>(*c, S, sigma, blur, radius, c->ndc_cam, cnt, bst, lst, alpha, gin, 0.f, 0.f, nullptr, c->d_ndc_cam);
+    sil_kernel<1><<<grid, HARP_TILE * HARP_TILE, 0, st>>>(*c, S, K, sigma, blur, radius, c->ndc_cam, cnt, bst, lst, alpha, gin, 0.f, 0.f, nullptr, c->d_ndc_cam);
   else
-    sil_kernel<2><<<grid, HARP_TILE * HARP_TILE, 0, st>>>(*c, S, sigma, blur, radius, c->ndc_cam, cnt, bst, lst, alpha, gin, gscale, inv_n, loss, c->d_ndc_cam);
+    sil_kernel<2><<<grid, HARP_TILE * HARP_TILE, 0, st>>>(*c, S, K, sigma, blur, radius, c->ndc_cam, cnt, bst, lst, alpha, gin, gscale, inv_n, loss, c->d_ndc_cam);
   harp_prof_end(c, 0, st);
   HARP_LAUNCH_CHECK();
+  if ((rc = harp_sil_topk(c, mode, S, K, sigma, blur, radius, alpha, gin, gscale, inv_n, loss, st)) != HARP_OK) return rc;
   if (mode != 0) {
     if ((rc = harp_project_bwd(c, B, S, focal, verts, R, T, c->d_ndc_cam, d_verts, d_R, d_T, st)) != HARP_OK) return rc;
   }

@@ -216,3 +216,33 @@ __device__ __forceinline__ void vis_update(const harp_ctx& c, const float* ndc, 
   float pz_new = exact_pz(c, ndc, fid, px, py), pz_old = exact_pz(c, ndc, best, px, py);
   if (pz_new < pz_old || (pz_new == pz_old && fid < best)) { best = fid; best_q = q; }
 }
+
+// Backward of one silhouette factor: alpha = 1 - prod_k(1 - p_k), p = sigmoid(-sd/sigma)  =>  d alpha / d sd_k = -prod p_k / sigma
+// (only reached when no factor is exactly zero), then PointLineDistanceBackward of the closest edge:
+// q = a + t (b - a), d = q - p ; grad_a = g (1-t) 2 d ; grad_b = g t 2 d.   d_ndc rows are (x, y, z, pad).
+__device__ __forceinline__ void sil_pair_gradient(const FaceRec& f, float px, float py, float sd, int edge, float t, float g,
+                                                  float prod, float sigma, float* d_ndc) {
+  float prob = 1.f / (1.f + expf(fdiv(sd, sigma)));
+  float gsd = g * (-prod * prob / sigma);
+  float gd = sd < 0.f ? -gsd : gsd;  // w.r.t. the unsigned squared distance (inside <=> signed distance negative)
+  if (gd == 0.f) return;
+  float ax, ay, bx, by; int va, vb;
+  if (edge == 0) { ax = f.x0; ay = f.y0; bx = f.x1; by = f.y1; va = f.v0; vb = f.v1; }
+  else if (edge == 1) { ax = f.x0; ay = f.y0; bx = f.x2; by = f.y2; va = f.v0; vb = f.v2; }
+  else { ax = f.x1; ay = f.y1; bx = f.x2; by = f.y2; va = f.v1; vb = f.v2; }
+  if (t < 0.f) {  // degenerate edge: dist = |p - b|^2
+    atomicAdd(reinterpret_cast<float2*>(d_ndc + (size_t)vb * 4), make_float2(gd * 2.f * (bx - px), gd * 2.f * (by - py)));
+    return;
+  }
+  float qx = ax + t * (bx - ax), qy = ay + t * (by - ay);
+  float dx = 2.f * gd * (qx - px), dy = 2.f * gd * (qy - py);
+  atomicAdd(reinterpret_cast<float2*>(d_ndc + (size_t)va * 4), make_float2((1.f - t) * dx, (1.f - t) * dy));
+  atomicAdd(reinterpret_cast<float2*>(d_ndc + (size_t)vb * 4), make_float2(t * dx, t * dy));
+}
+
+// A pixel whose candidate count may exceed faces_per_pixel is deferred to the exact top-K kernel (raster.cu).
+__device__ __forceinline__ void sil_defer_overflow(const harp_ctx& c, int pixel_id) {
+  int slot = atomicAdd(c.ovf_count, 1);
+  if (slot < c.ovf_cap) c.ovf_list[slot] = pixel_id;
+  else atomicAdd(c.counters, 1ULL);  // list full: this pixel keeps the all-faces product (reported by harp_ctx_read_counters)
+}

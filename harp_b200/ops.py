@@ -299,26 +299,26 @@ class Silhouette(torch.autograd.Function):
     """MeshRasterizer(K=50) + SoftSilhouetteShader alpha channel (renderer_helper.py:37-58)."""
 
     @staticmethod
-    def forward(ctx, hc, verts, R, T, focal, S, sigma):
+    def forward(ctx, hc, verts, R, T, focal, S, sigma, faces_per_pixel=50):
         verts, R, T = _c(verts), _c(R), _c(T)
         B = verts.shape[0]
         hc.reserve(B, S)
         alpha = torch.empty(B, S, S, device=verts.device)
-        check(_lib.lib().harp_silhouette(hc.h, 0, B, S, float(focal), float(sigma), ptr(verts), ptr(R), ptr(T), ptr(alpha),
-                                         None, 0.0, None, None, None, None, stream()))
-        ctx.hc, ctx.args = hc, (float(focal), int(S), float(sigma))
+        check(_lib.lib().harp_silhouette(hc.h, 0, B, S, float(focal), float(sigma), int(faces_per_pixel), ptr(verts), ptr(R), ptr(T),
+                                         ptr(alpha), None, 0.0, None, None, None, None, stream()))
+        ctx.hc, ctx.args = hc, (float(focal), int(S), float(sigma), int(faces_per_pixel))
         ctx.save_for_backward(verts, R, T)
         return alpha
 
     @staticmethod
     def backward(ctx, g_alpha):
         verts, R, T = ctx.saved_tensors
-        focal, S, sigma = ctx.args
+        focal, S, sigma, K = ctx.args
         B = verts.shape[0]
         d_verts, d_R, d_T = torch.zeros_like(verts), torch.zeros_like(R), torch.zeros_like(T)
-        check(_lib.lib().harp_silhouette(ctx.hc.h, 1, B, S, focal, sigma, ptr(verts), ptr(R), ptr(T), None, ptr(_c(g_alpha)),
+        check(_lib.lib().harp_silhouette(ctx.hc.h, 1, B, S, focal, sigma, K, ptr(verts), ptr(R), ptr(T), None, ptr(_c(g_alpha)),
                                          0.0, None, ptr(d_verts), ptr(d_R), ptr(d_T), stream()))
-        return None, d_verts, d_R, d_T, None, None, None
+        return None, d_verts, d_R, d_T, None, None, None, None
 
 
 class Shade(torch.autograd.Function):

@@ -36,7 +36,7 @@ class SilhouetteRenderer:
     def __call__(self, meshes, **kwargs):
         _check_camera(kwargs, self.image_size)
         alpha = ops.Silhouette.apply(meshes.hc, meshes.verts_padded(), kwargs["R"], kwargs["T"], _scalar(kwargs["focal_length"]),
-                                     self.image_size, self.sigma)
+                                     self.image_size, self.sigma, self.faces_per_pixel)
         return torch.cat([torch.ones_like(alpha)[..., None].expand(-1, -1, -1, 3), alpha[..., None]], dim=-1)
 
 

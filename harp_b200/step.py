@@ -214,7 +214,7 @@ class HarpFitter:
                             d_texture=ptr(self.app.g["texture"]), d_normal_map=ptr(self.app.g["normal_map"]))
         ra = HarpRenderArgs(verts=ptr(verts), normals=ptr(normals), cam_R=ptr(cR), cam_T=ptr(cTc), light_R=ptr(lRc), light_T=ptr(lTc),
                             light_pos=ptr(light_bc), amb=ptr(ambc), texture=ptr(tex), normal_map=ptr(nm), texH=H, texW=Wd,
-                            self_shadow=int(self.self_shadow), sigma=1e-7, y_sil=ptr(fr["y_sil"]), y_true=ptr(fr["y_true"]),
+                            self_shadow=int(self.self_shadow), faces_per_pixel=50, sigma=1e-7, y_sil=ptr(fr["y_sil"]), y_true=ptr(fr["y_true"]),
                             y_mask=ptr(fr["y_sil_eroded"]), w_sil=W["silhouette"] * fscale if coarse_on else 0.0,
                             w_photo=W["photo"] * fscale if app_on else 0.0, alpha=ptr(alpha), rgb=ptr(rgb),
                             loss_sil=ptr(self.losses[_SLOT["silhouette"]:]), loss_photo=ptr(self.losses[_SLOT["photo"]:]), grads=gs)

@@ -101,8 +101,9 @@ HARP_API int harp_ctx_reserve(harp_ctx* ctx, int max_batch, int img_size);
 HARP_API int harp_ctx_dims(const harp_ctx* ctx, int32_t* V0, int32_t* V, int32_t* F, int32_t* E);
 /* Copy the (F,3) int32 (subdivided) face list to [host] memory, for callers that need Meshes.faces_padded(). */
 HARP_API int harp_ctx_faces(const harp_ctx* ctx, int32_t* faces_out);
-/* counters written by the kernels since the last call: [0] pixels with more than K=50 silhouette candidates
- * (PyTorch3D would have kept only the 50 nearest), [1] bin-list capacity overflows.  [host] out. Synchronises. */
+/* counters written by the kernels since the last call: [0] silhouette pixels whose top-K truncation could not be
+ * evaluated exactly (more than 512 passing faces on one pixel, or more than 4M such pixels), [1] bin-list capacity
+ * overflows.  Both 0 means every result follows PyTorch3D's semantics.  [host] out. Synchronises. */
 HARP_API int harp_ctx_read_counters(harp_ctx* ctx, int64_t out[2], void* stream);
 
 /* Number of CUDA kernels this library has launched in this process (all contexts), for launch accounting. */
@@ -163,8 +164,10 @@ HARP_API int harp_mesh_losses(harp_ctx*, int B, const float* verts, const float*
  * mode 0: forward only.
  * mode 1: backward with upstream gradient g_alpha (B,S,S): d_verts (B,V,3), d_R (B,9), d_T (B,3) accumulated.
  * mode 2: fused L1 loss: target (B,S,S); loss (device scalar, accumulated, unweighted mean|target-alpha|);
- *         gradients of weight*loss accumulated. */
-HARP_API int harp_silhouette(harp_ctx*, int mode, int B, int S, float focal, float sigma, const float* verts, const float* R,
+ *         gradients of weight*loss accumulated.
+ * faces_per_pixel = K of RasterizationSettings (50 in HARP; <= 0 means 50).  Pixels with more candidate faces than K are
+ * re-evaluated by an exact per-pixel top-K-by-depth kernel, so results follow PyTorch3D's fragment truncation. */
+HARP_API int harp_silhouette(harp_ctx*, int mode, int B, int S, float focal, float sigma, int faces_per_pixel, const float* verts, const float* R,
                     const float* T, float* alpha, const float* g_alpha_or_target, float weight, float* loss,
                     float* d_verts, float* d_R, float* d_T, void* stream);
 
@@ -201,6 +204,7 @@ typedef struct {
   const float *light_pos, *amb;                       /* (B,3), (1) post-sigmoid */
   const float *texture, *normal_map;                  /* (H,W,3) shared maps, normal_map raw */
   int32_t texH, texW, self_shadow;
+  int32_t faces_per_pixel;                            /* silhouette K (50; <= 0 means 50) */
   float sigma;                                        /* silhouette blend sigma (1e-7) */
   const float *y_sil, *y_true, *y_mask;               /* targets: (B,S,S), (B,S,S,3), eroded mask (B,S,S) */
   float w_sil, w_photo;
