@@ -201,8 +201,11 @@ __global__ void __launch_bounds__(NT) pixel_vis_kernel(harp_ctx c, VisArgs a) {
 }
 
 // Shade the compacted hit pixels of one frame per blockIdx.y; grid-stride over the frame's hit list.
+#ifndef HARP_SHADE_MIN_CTAS
+#define HARP_SHADE_MIN_CTAS 4
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(128, 4) shade_deferred_kernel(harp_ctx c, ShadeArgs a, const int32_t* __restrict__ vis_fid,
+__global__ void __launch_bounds__(128, HARP_SHADE_MIN_CTAS) shade_deferred_kernel(harp_ctx c, ShadeArgs a, const int32_t* __restrict__ vis_fid,
                                                              const int32_t* __restrict__ hit_list,
                                                              const int32_t* __restrict__ hit_count) {
   const int S = a.S;

@@ -5,6 +5,8 @@
 
 struct ShadeArgs {
   int B, S, self_shadow, texH, texW;
+  int fixed_lights;      // 1: Phong twin with constant light colours ka, kd, ks (renderer_helper.py:70-73); 0: ka = amb, kd = 1 - amb, ks = 0
+  float ka, kd, ks;
   float focal, gscale, inv_n;
   const float *verts, *normals, *ndc_cam, *light_R, *light_T, *light_pos, *amb, *texture, *normal_map;
   const float* light_zbuf;
@@ -196,8 +198,10 @@ __device__ __forceinline__ void shade_pixel(const harp_ctx& c, const ShadeArgs& 
         }
       vis = acc / 9.f;
     }
-    sh = amb + (1.f - amb) * cosang * vis;
+    const float ka = a.fixed_lights ? a.ka : amb, kd = a.fixed_lights ? a.kd : 1.f - amb;
+    sh = ka + kd * cosang * vis;
     rgb = sh * tex;
+    if (a.fixed_lights) rgb = rgb + mk3(a.ks, a.ks, a.ks);  // specular^0 == 1 on every fragment
     // softmax_rgb_blend with K=1: (prob c + delta bg)/(prob + delta), delta = 1e-10 -> equals c to < 1 ulp; kept implicit
   }
   o.rgb = rgb;
@@ -223,9 +227,10 @@ __device__ __forceinline__ void shade_pixel(const harp_ctx& c, const ShadeArgs& 
   if (active) {
     f3 g_tex = sh * g;
     float g_sh = g.x * tex.x + g.y * tex.y + g.z * tex.z;
-    r_amb = g_sh * (1.f - cosang * vis);
-    float g_cos = cosang > 0.f ? g_sh * (1.f - amb) * vis : 0.f;
-    float g_vis = g_sh * (1.f - amb) * cosang;
+    const float kd = a.fixed_lights ? a.kd : 1.f - amb;
+    r_amb = a.fixed_lights ? 0.f : g_sh * (1.f - cosang * vis);
+    float g_cos = cosang > 0.f ? g_sh * kd * vis : 0.f;
+    float g_vis = g_sh * kd * cosang;
     f3 gP = mk3(0.f, 0.f, 0.f), gN = mk3(0.f, 0.f, 0.f);
     // --- lighting ---
     f3 g_n2 = g_cos * dh, g_dh = g_cos * n2;

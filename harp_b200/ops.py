@@ -326,17 +326,18 @@ class Shade(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, hc, verts, normals, cam_R, cam_T, light_R, light_T, light_pos, amb, texture, normal_map, focal, S,
-                self_shadow):
+                self_shadow, fixed_lights=None):
         ts = [_c(t) for t in (verts, normals, cam_R, cam_T, light_R, light_T, light_pos, amb.view(1), texture, normal_map)]
         verts, normals, cam_R, cam_T, light_R, light_T, light_pos, amb1, tex, nm = ts
         B = verts.shape[0]
         hc.reserve(B, S)
         H, W = tex.shape[-3], tex.shape[-2]
         rgb = torch.empty(B, S, S, 3, device=verts.device)
+        fl = (C.c_float * 3)(*[float(x) for x in fixed_lights]) if fixed_lights is not None else None
         check(_lib.lib().harp_shade(hc.h, 0, B, S, float(focal), int(self_shadow), ptr(verts), ptr(normals), ptr(cam_R),
-                                    ptr(cam_T), ptr(light_R), ptr(light_T), ptr(light_pos), ptr(amb1), ptr(tex), ptr(nm), H, W,
+                                    ptr(cam_T), ptr(light_R), ptr(light_T), ptr(light_pos), ptr(amb1), ptr(tex), ptr(nm), H, W, fl,
                                     ptr(rgb), None, None, 0.0, None, None, stream()))
-        ctx.hc, ctx.args = hc, (float(focal), int(S), int(self_shadow), H, W)
+        ctx.hc, ctx.args = hc, (float(focal), int(S), int(self_shadow), H, W, fl)
         ctx.shapes = (amb.shape, texture.shape, normal_map.shape)
         ctx.save_for_backward(*ts)
         return rgb
@@ -344,18 +345,18 @@ class Shade(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_rgb):
         verts, normals, cam_R, cam_T, light_R, light_T, light_pos, amb1, tex, nm = ctx.saved_tensors
-        focal, S, self_shadow, H, W = ctx.args
+        focal, S, self_shadow, H, W, fl = ctx.args
         B = verts.shape[0]
         z = torch.zeros_like
         g = dict(d_verts=z(verts), d_normals=z(normals), d_cam_R=z(cam_R), d_cam_T=z(cam_T), d_light_R=z(light_R),
                  d_light_T=z(light_T), d_light_pos=z(light_pos), d_amb=z(amb1), d_texture=z(tex), d_normal_map=z(nm))
         gs = HarpShadeGrads(**{k: ptr(v) for k, v in g.items()})
         check(_lib.lib().harp_shade(ctx.hc.h, 1, B, S, focal, self_shadow, ptr(verts), ptr(normals), ptr(cam_R), ptr(cam_T),
-                                    ptr(light_R), ptr(light_T), ptr(light_pos), ptr(amb1), ptr(tex), ptr(nm), H, W, None,
+                                    ptr(light_R), ptr(light_T), ptr(light_pos), ptr(amb1), ptr(tex), ptr(nm), H, W, fl, None,
                                     ptr(_c(g_rgb)), None, 0.0, None, C.byref(gs), stream()))
         sa, st, sn = ctx.shapes
         return (None, g["d_verts"], g["d_normals"], g["d_cam_R"], g["d_cam_T"], g["d_light_R"], g["d_light_T"],
-                g["d_light_pos"], g["d_amb"].view(sa), g["d_texture"].view(st), g["d_normal_map"].view(sn), None, None, None)
+                g["d_light_pos"], g["d_amb"].view(sa), g["d_texture"].view(st), g["d_normal_map"].view(sn), None, None, None, None)
 
 
 class TextureReg(torch.autograd.Function):
@@ -400,3 +401,17 @@ def ingest_u8(rgb_u8, mask_u8, out=None):
     check(_lib.lib().harp_ingest_u8(B, S, ptr(rgb_u8), ptr(mask_u8), ptr(out["y_true"]), ptr(out["y_sil"]), ptr(out["y_sil_eroded"]),
                                     stream()))
     return out
+
+
+@torch.no_grad()
+def render_normals(hc, verts, normals, R, T, focal, S, normal_map=None, faces_per_pixel=10):
+    """Evaluation-pass normal render (SoftPhongNormalShader, renderer_helper.py:216-301), forward only -> (B,S,S,3)."""
+    verts, normals, R, T = _c(verts), _c(normals), _c(R), _c(T)
+    B = verts.shape[0]
+    hc.reserve(B, S)
+    nm = _c(normal_map) if normal_map is not None else None
+    H, W = (nm.shape[-3], nm.shape[-2]) if nm is not None else (0, 0)
+    rgb = torch.empty(B, S, S, 3, device=verts.device)
+    check(_lib.lib().harp_render_normals(hc.h, B, S, float(focal), int(faces_per_pixel), ptr(verts), ptr(normals), ptr(R), ptr(T),
+                                         ptr(nm), H, W, ptr(rgb), stream()))
+    return rgb

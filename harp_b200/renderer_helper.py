@@ -65,21 +65,53 @@ class ShadowRenderer:
         return torch.cat([rgb, hit], dim=-1)
 
 
-class _NextRowRenderer:
-    def __init__(self, what):
-        self.what = what
+class PhongRenderer:
+    """MeshRenderer(MeshRasterizer(K=1), SoftPhongShaderPBR) — renderer_helper.py:60-83,106-190: point light at `light_posi`
+    with ambient .5 / diffuse .4 / specular .1, shininess 0 (utils/visualize.py:259-263), no shadow pass."""
+    LIGHTS = (0.5, 0.4, 0.1)
 
-    def __call__(self, *a, **k):
-        raise NotImplementedError(f"{self.what}: evaluation-pass renderer, a SURVEY.md 8(f) 'next' row — not built yet")
+    def __init__(self, image_size, light_posi):
+        self.image_size, self.light_posi = int(image_size), light_posi
+
+    def __call__(self, meshes, **kwargs):
+        _check_camera(kwargs, self.image_size)
+        tex, mat = meshes.textures, kwargs.get("materials")
+        if tex is None or mat is None or not getattr(mat, "use_normal_map", False):
+            raise ValueError("phong renderer needs meshes.textures (TexturesUV) and materials with normal_maps")
+        verts = meshes.verts_padded()
+        B = verts.shape[0]
+        light = torch.as_tensor(self.light_posi, dtype=torch.float32, device=verts.device).reshape(-1, 3).expand(B, 3)
+        amb = verts.new_zeros(1)
+        rgb = ops.Shade.apply(meshes.hc, verts, meshes.verts_normals_padded(), kwargs["R"], kwargs["T"], kwargs["R"], kwargs["T"], light,
+                              amb, tex.maps_padded()[:1], mat.normal_maps.maps_padded()[:1], _scalar(kwargs["focal_length"]),
+                              self.image_size, 0, self.LIGHTS)
+        hit = (rgb.detach() != 1.0).any(-1, keepdim=True).to(rgb.dtype)
+        return torch.cat([rgb, hit], dim=-1)
+
+
+class NormalRenderer:
+    """MeshRenderer(MeshRasterizer(K=10), SoftPhongNormalShader) — renderer_helper.py:85-101,216-301.  Evaluation pass:
+    forward only (the reference never differentiates through it)."""
+
+    def __init__(self, image_size, faces_per_pixel=10):
+        self.image_size, self.faces_per_pixel = int(image_size), int(faces_per_pixel)
+
+    def __call__(self, meshes, **kwargs):
+        _check_camera(kwargs, self.image_size)
+        mat = kwargs.get("materials")
+        nm = mat.normal_maps.maps_padded()[:1] if mat is not None and getattr(mat, "use_normal_map", False) else None
+        verts = meshes.verts_padded()
+        rgb = ops.render_normals(meshes.hc, verts, meshes.verts_normals_padded(), kwargs["R"], kwargs["T"],
+                                 _scalar(kwargs["focal_length"]), self.image_size, nm, self.faces_per_pixel)
+        hit = (rgb != 1.0).any(-1, keepdim=True).to(rgb.dtype)
+        return torch.cat([rgb, hit], dim=-1)
 
 
 def get_renderers(image_size, light_posi=((1.0, 1.0, -5.0),), silh_sigma=1e-7, silh_gamma=1e-1, silh_faces_per_pixel=50,
                   device="cuda"):
-    """-> (phong_renderer, silhouette_renderer, normal_renderer) as renderer_helper.get_renderers (26-103).
-    Only the silhouette renderer is on the optimisation path (optimize_sequence.py:471); the other two are eval-only."""
-    return (_NextRowRenderer("SoftPhongShaderPBR (non-shadow Phong, renderer_helper.py:106-190)"),
-            SilhouetteRenderer(image_size, silh_sigma, silh_faces_per_pixel),
-            _NextRowRenderer("SoftPhongNormalShader (K=10 normal render, renderer_helper.py:216-301)"))
+    """-> (phong_renderer, silhouette_renderer, normal_renderer) as renderer_helper.get_renderers (26-103)."""
+    return (PhongRenderer(image_size, light_posi), SilhouetteRenderer(image_size, silh_sigma, silh_faces_per_pixel),
+            NormalRenderer(image_size, 10))
 
 
 def get_shadow_renderers(image_size, light_posi=((1.0, 1.0, -5.0),), silh_sigma=1e-7, silh_gamma=1e-1, silh_faces_per_pixel=50,

@@ -176,6 +176,8 @@ HARP_API int harp_silhouette(harp_ctx*, int mode, int B, int S, float focal, flo
  * verts, normals (B,V,3); cam R,T and light R,T (B,3,3)/(B,3) (process_info_for_shadow, renderer_helper.py:454-468);
  * light_pos (B,3); amb (1) = sigmoid(amb_ratio) already applied; texture, normal_map (H,W,3) shared maps, normal_map RAW
  * (normalised per texel inside, visualize.py:98).  self_shadow=0 renders with vis=1.  rgb (B,S,S,3).
+ * fixed_lights = {ambient, diffuse, specular} selects the non-shadow Phong twin (SoftPhongShaderPBR, renderer_helper.py:
+ * 60-83,106-190: lights .5/.4/.1, shininess 0 => constant specular); NULL = ambient amb, diffuse 1-amb, no specular.
  * mode as above; for mode 1 g = g_rgb (B,S,S,3); for mode 2 g = y_true (B,S,S,3) and `mask` = eroded mask (B,S,S):
  * loss = mean|y*m - rgb*m| (optimize_sequence.py:543). */
 typedef struct {
@@ -190,8 +192,15 @@ typedef struct {
 HARP_API int harp_shade(harp_ctx*, int mode, int B, int S, float focal, int self_shadow, const float* verts,
                const float* normals, const float* cam_R, const float* cam_T, const float* light_R, const float* light_T,
                const float* light_pos, const float* amb, const float* texture, const float* normal_map, int texH,
-               int texW, float* rgb, const float* g_or_target, const float* mask, float weight, float* loss,
-               const harp_shade_grads* grads, void* stream);
+               int texW, const float* fixed_lights /* [host] nullable */, float* rgb, const float* g_or_target,
+               const float* mask, float weight, float* loss, const harp_shade_grads* grads, void* stream);
+
+/* ---- evaluation-pass normal renderer: MeshRasterizer(K=10) + SoftPhongNormalShader (renderer_helper.py:85-101,216-301):
+ * colours = (n * (1,-1,-1) + 1) / 2 of the normal-mapped interpolated normals, softmax_rgb_blend over the K nearest
+ * faces.  Forward only.  normal_map NULL skips the perturbation.  rgb (B,S,S,3). */
+HARP_API int harp_render_normals(harp_ctx*, int B, int S, float focal, int faces_per_pixel, const float* verts,
+                                 const float* normals, const float* R, const float* T, const float* normal_map, int texH,
+                                 int texW, float* rgb, void* stream);
 
 /* ---- fused pixel pass of the optimiser step --------------------------------------------------------------------------
  * harp_silhouette(mode 2) + harp_shade(mode 2) in one launch sequence that walks every tile's face list ONCE (silhouette

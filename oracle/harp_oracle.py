@@ -309,6 +309,71 @@ def render_rgb_shadow(verts, topo, cam, light_positions, amb_ratio, texture, nor
     return rgb
 
 
+def _shade_common(verts, topo, fr, texture, normal_map, use_normal_map=True):
+    """Per-fragment texels and (normal-mapped) normals for a (B,S,S,K) fragment set."""
+    B = verts.shape[0]
+    faces = topo.faces[None].expand(B, -1, -1)
+    mesh = p3d.Meshes(verts, faces)
+    fp = mesh.faces_packed()
+    vnorm = mesh.verts_normals_padded()
+    interp = lambda attr: p3d.interpolate_face_attributes(fr.pix_to_face, fr.bary_coords, attr)  # (B,S,S,K,D)
+    pix_pos = interp(verts.reshape(-1, 3)[fp])
+    pix_n = interp(vnorm.reshape(-1, 3)[fp])
+    fuv = topo.verts_uvs.to(verts.dtype)[topo.faces_uvs].repeat(B, 1, 1)
+    pix_uv = interp(fuv)
+    K = fr.pix_to_face.shape[-1]
+    S = fr.pix_to_face.shape[1]
+
+    def sample(maps):
+        uv = pix_uv.permute(0, 3, 1, 2, 4).reshape(B * K, S, S, 2)
+        tm = torch.flip(maps.expand(B, -1, -1, -1).permute(0, 3, 1, 2), [2])[:, None].expand(-1, K, -1, -1, -1).reshape(B * K, 3, *maps.shape[1:3])
+        t = F.grid_sample(tm, uv * 2.0 - 1.0, mode="bilinear", align_corners=True, padding_mode="border")
+        return t.reshape(B, K, 3, S, S).permute(0, 3, 4, 1, 2)
+
+    texel = sample(texture) if texture is not None else None
+    if use_normal_map:
+        nm = sample(F.normalize(normal_map, dim=-1))
+        tb = compute_tangent(pix_n)
+        pix_n = F.normalize(-tb[..., 0, :] * nm[..., 0:1] - tb[..., 1, :] * nm[..., 1:2] + pix_n * nm[..., 2:3], dim=-1)
+    return pix_pos, pix_n, texel
+
+
+def _softmax_rgb_blend(colors, fr, sigma=RGB_SIGMA, gamma=RGB_GAMMA, znear=1.0, zfar=100.0):
+    """pytorch3d softmax_rgb_blend, background white."""
+    mask = (fr.pix_to_face >= 0).to(colors.dtype)
+    prob = torch.sigmoid(-fr.dists / sigma) * mask
+    z_inv = (zfar - fr.zbuf) / (zfar - znear) * mask
+    z_inv_max = torch.max(z_inv, dim=-1).values[..., None].clamp(min=1e-10)
+    wnum = prob * torch.exp((z_inv - z_inv_max) / gamma)
+    delta = torch.exp((1e-10 - z_inv_max) / gamma).clamp(min=1e-10)
+    denom = wnum.sum(dim=-1)[..., None] + delta
+    return ((wnum[..., None] * colors).sum(dim=-2) + delta * 1.0) / denom
+
+
+def render_phong(verts, topo, cam, light_positions, texture, normal_map, focal, S):
+    """Non-shadow colour renderer: get_renderers' phong_renderer (renderer_helper.py:60-83) = SoftPhongShaderPBR (106-144) +
+    phong_shading_PBR (147-190): lights ambient .5 / diffuse .4 / specular .1, shininess 0 (visualize.py:259-263)."""
+    B = verts.shape[0]
+    ndc, _ = project_ndc(verts, cam_R(B, verts.dtype), cam_to_T(cam, focal, S), focal, S)
+    fr, _ = _frag(ndc, topo.faces[None].expand(B, -1, -1), S, 0.0, 1, False)
+    pix_pos, pix_n, texel = _shade_common(verts, topo, fr, texture, normal_map, True)
+    direction = light_positions[:, None, None, None, :] - pix_pos
+    ang = F.relu((F.normalize(pix_n, p=2, dim=-1, eps=1e-6) * F.normalize(direction, p=2, dim=-1, eps=1e-6)).sum(-1))
+    colors = (0.5 + 0.4 * ang)[..., None] * texel + 0.1  # pow(alpha, shininess=0) == 1: constant specular
+    return _softmax_rgb_blend(colors, fr)
+
+
+def render_normals(verts, topo, cam, normal_map, focal, S, K=10):
+    """Normal renderer: get_renderers' phong_normal_renderer (renderer_helper.py:85-101) = SoftPhongNormalShader (239-301) +
+    phong_normal_shading (216-236), K=10 faces per pixel blended by softmax_rgb_blend."""
+    B = verts.shape[0]
+    ndc, _ = project_ndc(verts, cam_R(B, verts.dtype), cam_to_T(cam, focal, S), focal, S)
+    fr, _ = _frag(ndc, topo.faces[None].expand(B, -1, -1), S, 0.0, K, False)
+    _, pix_n, _ = _shade_common(verts, topo, fr, None, normal_map, normal_map is not None)
+    colors = (pix_n * torch.tensor([1.0, -1.0, -1.0], dtype=verts.dtype) + 1.0) / 2.0
+    return _softmax_rgb_blend(colors, fr)
+
+
 # ------------------------------------------------------------------------------------------------- losses
 def kps_loss(gt_kps, pred_kps_m):
     """loss/kps_loss.py:4-17 (use_arm=False)."""

@@ -82,7 +82,7 @@ def ref_arm_layer(pack):
     return _ARM_LAYER["layer"]
 
 
-def reference_step(pack, tmpl, p, batch, S, focal, subdivide, stage, seed_albedo, seed_normal, arm=False):
+def reference_step(pack, tmpl, p, batch, S, focal, subdivide, stage, seed_albedo, seed_normal, arm=False, eval_renders=False):
     """optimize_sequence.py:446-569 with the reference's functions, device='cpu'."""
     import renderer.renderer_helper as renderer_helper
     from utils.visualize import prepare_mesh, prepare_materials, render_image, render_image_with_RT
@@ -131,6 +131,13 @@ def reference_step(pack, tmpl, p, batch, S, focal, subdivide, stage, seed_albedo
         amb_ratio=torch.nn.Sigmoid()(params["amb_ratio"]), device=dev)
     y_pred = render_image_with_RT(meshes, light_T, light_R, cam_T, cam_R, B, shadow_renderer, S, focal,
                                   silhouette=False, materials_properties=materials_properties, device=dev)
+    extra = {}
+    if eval_renders:  # the two evaluation-pass renderers of get_renderers (optimize_sequence.py:486-488; visualize.py:145-228)
+        with torch.no_grad():
+            extra["phong"] = render_image(meshes, cam, B, phong_renderer, S, focal, silhouette=False, device=dev,
+                                          materials_properties=materials_properties)
+            extra["normals"] = render_image(meshes, cam, B, normal_renderer, S, focal, silhouette=False, device=dev,
+                                            materials_properties=materials_properties)
     loss = {}
     if stage in ("coarse", "both"):
         loss["silhouette"] = l1_loss(batch["y_sil"], y_sil_pred)
@@ -146,7 +153,7 @@ def reference_step(pack, tmpl, p, batch, S, focal, subdivide, stage, seed_albedo
         loss["albedo"] = albedo_reg(params["texture"], uv_mask=batch["uv_mask"], std=1.0)
         torch.manual_seed(seed_normal)
         loss["normal_reg"] = normal_reg(params["normal_map"], uv_mask=batch["uv_mask"])
-    return loss, dict(sil=y_sil_pred, rgb=y_pred, verts=hand_verts, joints=hand_joints, sil_overflow=sil_overflow)
+    return loss, dict(sil=y_sil_pred, rgb=y_pred, verts=hand_verts, joints=hand_joints, sil_overflow=sil_overflow, **extra)
 
 
 def scenario(name, S, B, subdivide, stage, dtype=torch.float32, trans_amp=0.0, arm=False):
@@ -190,7 +197,7 @@ def scenario(name, S, B, subdivide, stage, dtype=torch.float32, trans_amp=0.0, a
                                              for k, v in P.items()}, d1, S, focal, subdivide, "both", 11, 12, arm=arm)
         ref_verts = im0["verts"][:1].clone()
     batch = dict(y_sil=y_sil, y_sil_eroded=y_er, y_true=y_true, init_joints=init_joints, ref_verts=ref_verts, uv_mask=uv_mask)
-    loss, im = reference_step(pack, tmpl, leaf, batch, S, focal, subdivide, stage, 11, 12, arm=arm)
+    loss, im = reference_step(pack, tmpl, leaf, batch, S, focal, subdivide, stage, 11, 12, arm=arm, eval_renders=(name.startswith("c2")))
     total = sum(v * O.LOSS_WEIGHTS[k] for k, v in loss.items())
     names = list(leaf.keys())
     gs = torch.autograd.grad(total, [leaf[k] for k in names], allow_unused=True)
@@ -211,6 +218,9 @@ def scenario(name, S, B, subdivide, stage, dtype=torch.float32, trans_amp=0.0, a
     out["verts"] = im["verts"].detach().numpy()
     out["joints"] = im["joints"].detach().numpy()
     out["sil_overflow"] = int(im["sil_overflow"])
+    for k in ("phong", "normals"):
+        if k in im:
+            out["img_" + k] = im[k].detach().numpy()
     for k, g_ in zip(names, gs):
         out["grad_" + k] = (g_ if g_ is not None else torch.zeros_like(leaf[k])).detach().numpy()
     path = os.path.join(HERE, name + ".npz")

@@ -9,6 +9,7 @@ pytestmark = pytest.mark.gpu
 
 from util import load_golden, rel_l2, frac_within
 
+_EXTRA = {}
 LOSS_W = {"silhouette": 7.0, "kps_anchor": 10.0, "vert_disp_reg": 2.0, "normal": 0.1, "laplacian": 4.0, "arap": 0.2,
           "photo": 1.0, "albedo": 0.5, "normal_reg": 0.1}
 
@@ -83,6 +84,13 @@ def _loop_body(g, stage):
         loss["normal_reg"] = normal_reg(params["normal_map"], uv_mask=batch["uv_mask"])
     total = sum(v * LOSS_W[k] for k, v in loss.items())
     total.backward()
+    _EXTRA.clear()
+    if "img_phong" in g:  # the two evaluation-pass renderers, called exactly as the reference's eval code does
+        with torch.no_grad():
+            _EXTRA["phong"] = render_image(meshes, cam, B, phong_renderer, S, focal, silhouette=False, device=dev,
+                                           materials_properties=materials_properties)
+            _EXTRA["normals"] = render_image(meshes, cam, B, normal_renderer, S, focal, silhouette=False, device=dev,
+                                             materials_properties=materials_properties)
     return loss, total, leaf, y_sil_pred, y_pred
 
 
@@ -114,3 +122,7 @@ def test_dropin_loop_body_matches_reference_golden(name):
         if float(gg.abs().max()) == 0.0:
             continue
         assert frac_within(leaf[k].grad.cpu().view(gg.shape), gg, 1e-3 * float(gg.abs().max())) >= 0.9995, k
+    for k, img in _EXTRA.items():  # SoftPhongShaderPBR and the K=10 normal renderer vs the reference's own renders
+        d = (img.cpu() - torch.tensor(g["img_" + k])).abs().amax(-1)
+        assert float((d <= 2e-4).double().mean()) >= 0.995, (k, float((d <= 2e-4).double().mean()))
+        assert float((d <= 2e-2).double().mean()) >= 0.999, k

@@ -208,6 +208,44 @@ def test_shade_forward_backward(case, S, shadow):
         assert r < (5e-3 if k in ("verts",) else 2e-3), (k, r)
 
 
+def test_phong_twin_and_normal_renderer(case):
+    """Non-shadow SoftPhongShaderPBR (fixed lights .5/.4/.1, differentiable) and the K=10 normal renderer (forward)."""
+    import pytorch3d._core as p3d
+    from harp_b200.ops import Shade, render_normals
+    from harp_b200 import camera
+    model, topo, params, batch, cfg = case
+    hc = _ctx(model, True)
+    B, S = 2, 128
+    focal = 1000.0 * S / 224.0
+    pose48 = torch.cat((params["rot"], params["pose"]), 1)
+    vm, _ = O.mano_forward(model, pose48, params["shape"].repeat(B, 1), params["trans"])
+    verts = O.build_mesh(vm / 1000.0, topo, params["verts_disps"]).detach()
+    light = params["light_position"][None].repeat(B, 1).clone()
+    base = dict(verts=verts, cam=params["cam"], light=light, tex=params["texture"], nm=params["normal_map"])
+    o = {k: v.clone().requires_grad_(True) for k, v in base.items()}
+    rgb_o = O.render_phong(o["verts"], topo, o["cam"], o["light"], o["tex"], o["nm"], focal, S)
+    torch.manual_seed(6)
+    g = torch.randn_like(rgb_o)
+    (rgb_o * g).sum().backward()
+    c = {k: v.clone().cuda().requires_grad_(True) for k, v in base.items()}
+    faces = topo.faces.cuda()[None].expand(B, -1, -1)
+    normals = p3d.Meshes(c["verts"], faces).verts_normals_padded()
+    cR, cT = camera.flip_xy_R(B, "cuda"), camera.cam_to_T(c["cam"], focal, S)
+    rgb_c = Shade.apply(hc, c["verts"], normals, cR, cT, cR, cT, c["light"], torch.zeros(1, device="cuda"), c["tex"], c["nm"],
+                        focal, S, 0, (0.5, 0.4, 0.1))
+    (rgb_c * g.cuda()).sum().backward()
+    d = (rgb_c.detach().cpu() - rgb_o.detach()).abs().amax(-1)
+    assert float((d <= 1e-4).double().mean()) >= 0.995
+    for k in base:
+        r = rel_l2(c[k].grad.cpu(), o[k].grad)
+        assert r < 5e-3, (k, r)
+    with torch.no_grad():
+        n_o = O.render_normals(verts, topo, params["cam"], params["normal_map"], focal, S, K=10)
+        n_c = render_normals(hc, verts.cuda(), normals.detach(), cR, cT.detach(), focal, S, params["normal_map"].cuda(), 10)
+    d = (n_c.cpu() - n_o).abs().amax(-1)
+    assert float((d <= 2e-4).double().mean()) >= 0.995 and float((d <= 2e-2).double().mean()) >= 0.999
+
+
 def test_texture_reg_and_adam():
     from harp_b200 import synth
     from harp_b200.ops import TextureReg, adam_step
