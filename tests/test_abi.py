@@ -64,3 +64,18 @@ def test_ops_fail_loudly_without_cuda():
     from harp_b200 import _lib
     with pytest.raises(_lib.HarpError):
         _lib.ptr(torch.zeros(3))
+
+
+def test_checkpoint_roundtrip_uses_reference_keys(tmp_path):
+    """saved_params.pkl is a pickle of {key: ndarray} with the reference's key names (utils/file_utils.py:6-26)."""
+    import pickle
+    import torch
+    from harp_b200 import file_utils
+    params = {"pose": torch.randn(4, 45), "cam": torch.randn(4, 3), "shape": torch.randn(10), "amb_ratio": torch.tensor(0.4),
+              "texture": torch.rand(1, 8, 8, 3), "verts_disps": torch.zeros(12, 1), "uv_mask": None}
+    path = file_utils.save_result(params, str(tmp_path))
+    raw = pickle.load(open(path, "rb"))
+    assert set(raw) == set(params) and all(k in file_utils.PARAM_KEYS for k in raw)
+    back = file_utils.load_result(str(tmp_path))
+    for k, v in params.items():
+        assert (back[k] is None) if v is None else torch.equal(back[k], v)
