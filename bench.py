@@ -154,6 +154,10 @@ def main():
         print(json.dumps(line), flush=True)
         return
 
+    # anything a library writes to fd 1 (NCCL prints its version banner there) goes to stderr: stdout carries ONE JSON line
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch.distributed as dist
     from harp_b200 import _lib, scene
     from harp_b200.step import HarpFitter, LOSS_NAMES
@@ -356,7 +360,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference(1, 1, frames=1, size=S)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
