@@ -20,7 +20,7 @@ namespace {
 
 constexpr int CHUNK = 64;
 constexpr int NT = HARP_TILE * HARP_TILE;
-constexpr int QCAP = 512;
+constexpr int QCAP = 432;  // with the 112-byte face records: 13.4 KB per CTA -> 16 CTAs per SM
 
 struct VisArgs {
   int S, K;
@@ -42,13 +42,23 @@ struct VisArgs {
   float* photo_loss;
 };
 
+// Block-wide sum of two values at once (64-thread CTAs: two warps); results valid in thread 0.
+__device__ __forceinline__ void block_sum2(float& u, float& v, float* red) {
+  u = warp_sum(u); v = warp_sum(v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { red[2 * w] = u; red[2 * w + 1] = v; }
+  __syncthreads();
+  if (threadIdx.x == 0) { u = red[0] + red[2]; v = red[1] + red[3]; }
+}
+
 // SIL_BWD: accumulate the silhouette L1 loss and its gradient (COARSE_OPT stages); PHOTO: accumulate the photometric loss
 // of background pixels (APP_OPT stages; hit pixels are handled by the deferred shading kernel).
 template <bool SIL_BWD, bool PHOTO>
-__global__ void __launch_bounds__(NT) pixel_vis_kernel(harp_ctx c, VisArgs a) {
-  __shared__ FaceRec faces[CHUNK];
+__global__ void __launch_bounds__(NT, 16) pixel_vis_kernel(harp_ctx c, VisArgs a) {
+  __shared__ FaceTile faces[CHUNK];
   __shared__ float red[32];
   __shared__ unsigned char q_pix[QCAP], q_face[QCAP], q_edge[QCAP];
+  __shared__ unsigned short q_next[QCAP];  // per-pixel chain through the queue, in face-list order
   __shared__ float q_sd[QCAP], q_t[QCAP];
   __shared__ int q_n, any_bwd;
   __shared__ float s_g[NT], s_prod[NT];
@@ -59,7 +69,27 @@ __global__ void __launch_bounds__(NT) pixel_vis_kernel(harp_ctx c, VisArgs a) {
   int col = blockIdx.x * HARP_TILE + lx, row = blockIdx.y * HARP_TILE + ly;
   size_t pix = ((size_t)b * S + row) * S + col;
   size_t tglob = (size_t)b * tw * tw + blockIdx.y * tw + blockIdx.x;
-  int n = a.bin_count[tglob], start = a.bin_start[tglob];
+  int n = a.bin_count[tglob];
+  if (n == 0) {
+    // ---- empty tile (about 4 of 5 at the reference's framing): nothing but streaming.  All loads are issued before the
+    //      first use so that their latencies overlap.
+    float ys = SIL_BWD ? __ldcs(a.y_sil + pix) : 0.f;
+    float mk = 0.f;
+    f3 y = mk3(0.f, 0.f, 0.f);
+    if (PHOTO) { mk = __ldcs(a.y_mask + pix); y = mk3(__ldcs(a.y_true + pix * 3), __ldcs(a.y_true + pix * 3 + 1), __ldcs(a.y_true + pix * 3 + 2)); }
+    a.vis_fid[pix] = -1;
+    a.alpha[pix] = 0.f;
+    st3(a.rgb + pix * 3, mk3(1.f, 1.f, 1.f));
+    float s_sil = fabsf(ys), s_ph = PHOTO ? fabsf(mk - y.x * mk) + fabsf(mk - y.y * mk) + fabsf(mk - y.z * mk) : 0.f;
+    if (!SIL_BWD && !PHOTO) return;
+    block_sum2(s_sil, s_ph, red);
+    if (tid == 0) {
+      if (SIL_BWD && s_sil != 0.f) atomicAdd(a.sil_loss, s_sil * a.sil_inv_n);
+      if (PHOTO && s_ph != 0.f) atomicAdd(a.photo_loss, s_ph * a.photo_inv_n);
+    }
+    return;
+  }
+  int start = a.bin_start[tglob];
   if (start + n > c.bin_cap) n = max(0, (int)c.bin_cap - start);
   const int32_t* list = a.bin_list + (size_t)b * c.bin_cap + start;
   const float* ndc = a.ndc + (size_t)b * c.V * 3;
@@ -70,27 +100,33 @@ __global__ void __launch_bounds__(NT) pixel_vis_kernel(harp_ctx c, VisArgs a) {
   int best_fid = -1;
   float best_q = 0.f;
   bool q_overflow = false;
-  const float sat = 17.5f * sigma;
+  const float sat = 17.5f * sigma, far = 1.001f * blur;
   if (tid == 0) { any_bwd = 0; q_n = 0; }
   for (int base = 0; base < n; base += CHUNK) {
     int m = min(CHUNK, n - base);
     __syncthreads();
-    if (tid < m) load_face(c, ndc, list[base + tid], a.radius, faces[tid]);
+    if (tid < m) stage_face(c, ndc, list[base + tid], a.radius, faces[tid]);
     if (tid == 0) q_n = 0;
     __syncthreads();
-    // A: convergent classification of every (pixel, face) pair: visibility (nearest inside face by 1/depth) for all
-    //    pixels; silhouette factors until the pixel saturates (one exactly-zero factor => alpha = 1, zero gradient)
+    // A: classification of every (pixel, face) pair, branch-free up to the class: visibility (nearest inside face by
+    //    1/depth) for all pixels; silhouette factors until the pixel saturates (one exactly-zero factor => alpha = 1,
+    //    zero gradient).  Band pairs go to the tile's queue, chained per pixel.
+    int q_first = -1, q_last = -1, q_mine = 0;
     for (int i = 0; i < m; ++i) {
-      const FaceRec& f = faces[i];
-      bool inside, exact;
-      float q;
-      int cls = classify_pair_vis<true>(f, px, py, blur, sat, inside, q, exact);
+      const FaceTile& f = faces[i];
+      bool inside;
+      float e0, e1, e2;
+      int cls = classify_fast<true>(f, px, py, far, sat, inside, e0, e1, e2);
       if (cls == PAIR_REJECT) continue;
-      if (exact) {  // a vertex behind the camera: decide visibility with the exact operation sequence
+      float q;
+      if (cls == PAIR_EXACT) {  // a vertex behind the camera: decide with the exact operation sequence
         PairEval e;
         eval_pair_full<false, false>(f, px, py, 0.f, e);
         inside = e.pass;
         q = e.pass ? 1.f / e.pz : 0.f;
+        cls = PAIR_FULL;
+      } else {
+        q = fast_inv_depth(f, e0, e1, e2);
       }
       if (inside) vis_update(c, ndc, px, py, f.fid, q, best_fid, best_q);
       ++ncand;  // upper bound on the faces PyTorch3D would consider (exact top-K decision after the loop)
@@ -99,6 +135,9 @@ __global__ void __launch_bounds__(NT) pixel_vis_kernel(harp_ctx c, VisArgs a) {
       int slot = atomicAdd(&q_n, 1);
       if (slot < QCAP) {
         q_pix[slot] = (unsigned char)tid; q_face[slot] = (unsigned char)i;
+        if (q_last >= 0) q_next[q_last] = (unsigned short)slot; else q_first = slot;
+        q_last = slot;
+        ++q_mine;
       } else {
         q_overflow = true;
         PairEval e;
@@ -121,10 +160,10 @@ __global__ void __launch_bounds__(NT) pixel_vis_kernel(harp_ctx c, VisArgs a) {
       else q_edge[s] = 255;
     }
     __syncthreads();
-    // C: every pixel folds its own results in face-list order
+    // C: every pixel folds its own chain in face-list order
     if (nzero == 0) {
-      for (int s = 0; s < qn; ++s) {
-        if (q_pix[s] != tid || q_edge[s] == 255) continue;
+      for (int s = q_first; q_mine > 0; --q_mine, s = q_next[s]) {
+        if (q_edge[s] == 255) continue;
         ++npass;
         float om = 1.f - 1.f / (1.f + expf(fdiv(q_sd[s], sigma)));
         if (om == 0.f) { ++nzero; break; }
@@ -153,22 +192,23 @@ __global__ void __launch_bounds__(NT) pixel_vis_kernel(harp_ctx c, VisArgs a) {
       photo_abs = fabsf(mk - y.x * mk) + fabsf(mk - y.y * mk) + fabsf(mk - y.z * mk);
     }
   }
-  if (PHOTO) {
-    float s = block_sum(photo_abs, red);
-    if (tid == 0 && s != 0.f) atomicAdd(a.photo_loss, s * a.photo_inv_n);
-  }
   // ---- silhouette value, loss and gradient
   float al = nzero > 0 ? 1.f : 1.f - prod;
   const bool deferred = ncand > a.K;  // more candidates than faces_per_pixel -> exact top-K kernel
   if (deferred) sil_defer_overflow(c, (int)pix);
   else a.alpha[pix] = al;
-  if (!SIL_BWD) return;
-  float diff = deferred ? 0.f : al - a.y_sil[pix];
-  float g = diff > 0.f ? a.sil_gscale : (diff < 0.f ? -a.sil_gscale : 0.f);
-  {
-    float s = block_sum(fabsf(diff), red);
-    if (tid == 0 && s != 0.f) atomicAdd(a.sil_loss, s * a.sil_inv_n);
+  float diff = (deferred || !SIL_BWD) ? 0.f : al - a.y_sil[pix];
+  if (SIL_BWD || PHOTO) {
+    float s_sil = fabsf(diff), s_ph = photo_abs;
+    __syncthreads();  // red[] is free
+    block_sum2(s_sil, s_ph, red);
+    if (tid == 0) {
+      if (SIL_BWD && s_sil != 0.f) atomicAdd(a.sil_loss, s_sil * a.sil_inv_n);
+      if (PHOTO && s_ph != 0.f) atomicAdd(a.photo_loss, s_ph * a.photo_inv_n);
+    }
   }
+  if (!SIL_BWD) return;
+  float g = diff > 0.f ? a.sil_gscale : (diff < 0.f ? -a.sil_gscale : 0.f);
   bool need = (g != 0.f) && nzero == 0 && prod > 0.f && npass > 0;
   if (need) any_bwd = 1;
   s_g[tid] = g; s_prod[tid] = prod; s_need[tid] = need ? 1 : 0;
@@ -181,21 +221,25 @@ __global__ void __launch_bounds__(NT) pixel_vis_kernel(harp_ctx c, VisArgs a) {
       int p = q_pix[s];
       if (!s_need[p] || q_edge[s] == 255) continue;
       float ppx = pix_to_ndc(blockIdx.x * HARP_TILE + (p % HARP_TILE), S), ppy = pix_to_ndc(blockIdx.y * HARP_TILE + (p / HARP_TILE), S);
-      sil_pair_gradient(faces[q_face[s]], ppx, ppy, q_sd[s], q_edge[s], q_t[s], s_g[p], s_prod[p], sigma, d_ndc);
+      sil_pair_gradient(c, faces[q_face[s]], ppx, ppy, q_sd[s], q_edge[s], q_t[s], s_g[p], s_prod[p], sigma, d_ndc);
     }
     return;
   }
   for (int base = 0; base < n; base += CHUNK) {  // generic path (multi-chunk tiles): re-stage and evaluate per pixel
     int m = min(CHUNK, n - base);
     __syncthreads();
-    if (tid < m) load_face(c, ndc, list[base + tid], a.radius, faces[tid]);
+    if (tid < m) stage_face(c, ndc, list[base + tid], a.radius, faces[tid]);
     __syncthreads();
     if (!need) continue;
     for (int i = 0; i < m; ++i) {
+      bool inside;
+      float e0, e1, e2;
+      int cls = classify_fast<true>(faces[i], px, py, far, sat, inside, e0, e1, e2);
+      if (cls == PAIR_REJECT || cls == PAIR_SATURATED) continue;
       PairEval e;
-      eval_pair<true, true>(faces[i], px, py, blur, sat, e);
-      if (!e.pass || e.saturated) continue;
-      sil_pair_gradient(faces[i], px, py, e.inside ? -e.dist : e.dist, e.edge, e.t, g, prod, sigma, d_ndc);
+      eval_pair_full<true, true>(faces[i], px, py, blur, e);
+      if (!e.pass) continue;
+      sil_pair_gradient(c, faces[i], px, py, e.inside ? -e.dist : e.dist, e.edge, e.t, g, prod, sigma, d_ndc);
     }
   }
 }

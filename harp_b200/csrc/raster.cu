@@ -73,8 +73,15 @@ __global__ void __launch_bounds__(TPB) project_bwd_kernel(int B, int V, const fl
 // ---- binning ---------------------------------------------------------------------------------------------------------
 // Pixel column j has x_ndc = 1 - (2j+1)/S (decreasing); a face with inflated bbox [lo,hi] can touch columns
 // ceil((1-hi) S/2 - 0.5) .. floor((1-lo) S/2 - 0.5); a 0.01 px guard absorbs rounding (the exact test runs per pixel).
-__device__ __forceinline__ bool face_tile_range(const harp_ctx& c, const float* ndc, int f, float radius, int S, int& tx0,
-                                                int& tx1, int& ty0, int& ty1) {
+// Per-face binning record: the tile range of the inflated bbox plus what the per-tile edge test needs.
+struct BinFace {
+  int tx0, tx1, ty0, ty1;
+  bool edge_test;            // all three view depths > 0: inside/outside is decided by the edge functions alone
+  float x0, y0, x1, y1, x2, y2, sgn;
+  float thr12, thr20, thr01;  // squared edge length x (1.05 blur + guard): a tile farther than this outside an edge line is skipped
+};
+
+__device__ __forceinline__ bool face_tile_range(const harp_ctx& c, const float* ndc, int f, float radius, int S, BinFace& r) {
   const int32_t* fv = c.faces + (size_t)f * 3;
   const float *a = ndc + (size_t)fv[0] * 3, *b = ndc + (size_t)fv[1] * 3, *d = ndc + (size_t)fv[2] * 3;
   float zmax = fmaxf(fmaxf(a[2], b[2]), d[2]);
@@ -89,9 +96,40 @@ __device__ __forceinline__ bool face_tile_range(const harp_ctx& c, const float* 
   jlo = fmaxf(jlo, 0.f); ilo = fmaxf(ilo, 0.f);
   jhi = fminf(jhi, (float)(S - 1)); ihi = fminf(ihi, (float)(S - 1));
   if (jlo > jhi || ilo > ihi) return false;
-  tx0 = (int)jlo / HARP_TILE; tx1 = (int)jhi / HARP_TILE;
-  ty0 = (int)ilo / HARP_TILE; ty1 = (int)ihi / HARP_TILE;
+  r.tx0 = (int)jlo / HARP_TILE; r.tx1 = (int)jhi / HARP_TILE;
+  r.ty0 = (int)ilo / HARP_TILE; r.ty1 = (int)ihi / HARP_TILE;
+  // Per-tile edge test (only worth it when the bbox spans several tiles).  Pixel pairs of a skipped tile are exactly those
+  // classify_pair rejects: every pixel centre lies outside one edge LINE by more than sqrt(1.05 blur) (+1e-5 NDC guard, four
+  // orders above the fp32 error of an edge function), and the distance to the triangle is at least the distance to that line.
+  r.edge_test = fminf(fminf(a[2], b[2]), d[2]) > 0.f && (r.tx1 > r.tx0 || r.ty1 > r.ty0);
+  if (r.edge_test) {
+    r.x0 = a[0]; r.y0 = a[1]; r.x1 = b[0]; r.y1 = b[1]; r.x2 = d[0]; r.y2 = d[1];
+    r.sgn = fadd(edge_fn(r.x2, r.y2, r.x0, r.y0, r.x1, r.y1), HARP_K_EPS) > 0.f ? 1.f : -1.f;  // sign of FaceRec::area
+    float m = 1.05f * radius * radius + 1e-10f;
+    r.thr12 = m * ((r.x2 - r.x1) * (r.x2 - r.x1) + (r.y2 - r.y1) * (r.y2 - r.y1));
+    r.thr20 = m * ((r.x0 - r.x2) * (r.x0 - r.x2) + (r.y0 - r.y2) * (r.y0 - r.y2));
+    r.thr01 = m * ((r.x1 - r.x0) * (r.x1 - r.x0) + (r.y1 - r.y0) * (r.y1 - r.y0));
+  }
   return true;
+}
+
+// largest signed edge function over the four corner pixel centres of a tile (the function is affine in the pixel position)
+__device__ __forceinline__ float tile_max_edge(float sgn, float xa, float xb, float ya, float yb, float ax, float ay, float bx,
+                                               float by) {
+  float dx = bx - ax, dy = by - ay;
+  float ea = (xa - ax) * dy, eb = (xb - ax) * dy, fa = (ya - ay) * dx, fb = (yb - ay) * dx;
+  return fmaxf(fmaxf(sgn * (ea - fa), sgn * (ea - fb)), fmaxf(sgn * (eb - fa), sgn * (eb - fb)));
+}
+
+__device__ __forceinline__ bool tile_outside_face(const BinFace& r, int tx, int ty, int S) {
+  float xa = pix_to_ndc(tx * HARP_TILE, S), xb = pix_to_ndc(tx * HARP_TILE + HARP_TILE - 1, S);
+  float ya = pix_to_ndc(ty * HARP_TILE, S), yb = pix_to_ndc(ty * HARP_TILE + HARP_TILE - 1, S);
+  float m0 = tile_max_edge(r.sgn, xa, xb, ya, yb, r.x1, r.y1, r.x2, r.y2);  // e0 = EdgeFunction(p, v1, v2)
+  if (m0 < 0.f && m0 * m0 >= r.thr12) return true;
+  float m1 = tile_max_edge(r.sgn, xa, xb, ya, yb, r.x2, r.y2, r.x0, r.y0);
+  if (m1 < 0.f && m1 * m1 >= r.thr20) return true;
+  float m2 = tile_max_edge(r.sgn, xa, xb, ya, yb, r.x0, r.y0, r.x1, r.y1);
+  return m2 < 0.f && m2 * m2 >= r.thr01;
 }
 
 template <bool FILL>
@@ -101,12 +139,13 @@ __global__ void __launch_bounds__(TPB) bin_kernel(harp_ctx c, int B, int S, floa
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * c.F) return;
   int b = idx / c.F, f = idx % c.F;
-  int tx0, tx1, ty0, ty1;
-  if (!face_tile_range(c, ndc + (size_t)b * c.V * 3, f, radius, S, tx0, tx1, ty0, ty1)) return;
+  BinFace r;
+  if (!face_tile_range(c, ndc + (size_t)b * c.V * 3, f, radius, S, r)) return;
   int tw = S / HARP_TILE;
   size_t tb = (size_t)b * tw * tw;
-  for (int ty = ty0; ty <= ty1; ++ty)
-    for (int tx = tx0; tx <= tx1; ++tx) {
+  for (int ty = r.ty0; ty <= r.ty1; ++ty)
+    for (int tx = r.tx0; tx <= r.tx1; ++tx) {
+      if (r.edge_test && tile_outside_face(r, tx, ty, S)) continue;  // deterministic: count and fill passes agree
       size_t t = tb + (size_t)ty * tw + tx;
       if (!FILL) {
         atomicAdd(count + t, 1);
@@ -275,7 +314,7 @@ __global__ void __launch_bounds__(HARP_TILE* HARP_TILE) sil_kernel(harp_ctx c, i
       int p = q_pix[s];
       if (!s_need[p] || q_edge[s] == 255) continue;
       float ppx = pix_to_ndc(blockIdx.x * HARP_TILE + (p % HARP_TILE), S), ppy = pix_to_ndc(blockIdx.y * HARP_TILE + (p / HARP_TILE), S);
-      sil_pair_gradient(faces[q_face[s]], ppx, ppy, q_sd[s], q_edge[s], q_t[s], s_g[p], s_prod[p], sigma, d_ndc);
+      sil_pair_gradient(c, faces[q_face[s]], ppx, ppy, q_sd[s], q_edge[s], q_t[s], s_g[p], s_prod[p], sigma, d_ndc);
     }
     return;
   }
@@ -289,7 +328,7 @@ __global__ void __launch_bounds__(HARP_TILE* HARP_TILE) sil_kernel(harp_ctx c, i
       PairEval e;
       eval_pair<true, true>(faces[i], px, py, blur, sat, e);
       if (!e.pass || e.saturated) continue;
-      sil_pair_gradient(faces[i], px, py, e.inside ? -e.dist : e.dist, e.edge, e.t, g, prod, sigma, d_ndc);
+      sil_pair_gradient(c, faces[i], px, py, e.inside ? -e.dist : e.dist, e.edge, e.t, g, prod, sigma, d_ndc);
     }
   }
 }
@@ -377,7 +416,7 @@ __global__ void __launch_bounds__(32 * TOPK_WARPS) sil_topk_kernel(harp_ctx c, i
       if (!e_keep[w][i]) continue;
       FaceRec f;
       load_face(c, ndc, e_fid[w][i], radius, f);
-      sil_pair_gradient(f, px, py, e_sd[w][i], e_edge[w][i], e_t[w][i], g, prod, sigma, d_ndc);
+      sil_pair_gradient(c, f, px, py, e_sd[w][i], e_edge[w][i], e_t[w][i], g, prod, sigma, d_ndc);
     }
   }
 }

@@ -124,8 +124,8 @@ __device__ __forceinline__ int classify_pair_vis(const FaceRec& f, float px, flo
 }
 
 // CLIP: clip_barycentric_coords (silhouette); blur: blur_radius (squared NDC).  The bounding-box test is classify_pair's.
-template <bool CLIP, bool NEED_DIST>
-__device__ __forceinline__ void eval_pair_full(const FaceRec& f, float px, float py, float blur, PairEval& r) {
+template <bool CLIP, bool NEED_DIST, typename F>
+__device__ __forceinline__ void eval_pair_full(const F& f, float px, float py, float blur, PairEval& r) {
   r.pass = false;
   r.saturated = false;
   float w0 = fdiv(edge_fn(px, py, f.x1, f.y1, f.x2, f.y2), f.area);
@@ -196,6 +196,83 @@ __device__ __forceinline__ void load_face(const harp_ctx& c, const float* ndc, i
   f.iz0 = 1.f / f.z0; f.iz1 = 1.f / f.z1; f.iz2 = 1.f / f.z2;
 }
 
+// The shared-memory record of the tile kernels' face walk: 16-byte groups (one LDS.128 each, broadcast to the warp),
+// (7 of them) holding per-face constants so that the per-(pixel, face) classification is ~45 branch-free instructions:
+//   * the edge deltas fsub(b, a) of PyTorch3D's EdgeFunctionForward, rounded exactly as edge_fn rounds them, so
+//     e_i = fsub(fmul(fsub(px,ax), dy), fmul(fsub(py,ay), dx)) is bit-identical to edge_fn();
+//   * sgn = sign(area) (0 when a vertex is behind the camera: such a face takes the exact path);
+//   * il_i = 1 / |edge_i|^2, so the squared distance to an edge line is e_i^2 il_i (compared against uniform thresholds
+//     with >= 0.1 % margins; never used for output values);
+//   * iz_i = 1 / z_i for the fast inverse depth that orders visibility candidates.
+struct __align__(16) FaceTile {
+  float x0, y0, x1, y1;
+  float x2, y2, xmin, xmax;
+  float ymin, ymax, sgn, area;
+  float d12x, d12y, d20x, d20y;
+  float d01x, d01y, il12, il20;
+  float il01, iz0, iz1, iz2;
+  float z0, z1, z2;
+  int fid;
+};  // 112 B; the vertex ids (needed by the rare gradient path only) are re-read from the face table
+
+__device__ __forceinline__ void stage_face(const harp_ctx& c, const float* ndc, int fid, float radius, FaceTile& f) {
+  const int32_t* fv = c.faces + (size_t)fid * 3;
+  int v0 = fv[0], v1 = fv[1], v2 = fv[2];
+  const float *a = ndc + (size_t)v0 * 3, *b = ndc + (size_t)v1 * 3, *d = ndc + (size_t)v2 * 3;
+  float x0 = a[0], y0 = a[1], z0 = a[2], x1 = b[0], y1 = b[1], z1 = b[2], x2 = d[0], y2 = d[1], z2 = d[2];
+  f.x0 = x0; f.y0 = y0; f.x1 = x1; f.y1 = y1; f.x2 = x2; f.y2 = y2;
+  f.z0 = z0; f.z1 = z1; f.z2 = z2; f.fid = fid;
+  f.xmin = fsub(fminf(fminf(x0, x1), x2), radius);
+  f.xmax = fadd(fmaxf(fmaxf(x0, x1), x2), radius);
+  f.ymin = fsub(fminf(fminf(y0, y1), y2), radius);
+  f.ymax = fadd(fmaxf(fmaxf(y0, y1), y2), radius);
+  float area = fadd(edge_fn(x2, y2, x0, y0, x1, y1), HARP_K_EPS);
+  f.area = area;
+  bool front = fminf(fminf(z0, z1), z2) > 0.f;
+  f.sgn = front ? (area > 0.f ? 1.f : -1.f) : 0.f;
+  f.d12x = fsub(x2, x1); f.d12y = fsub(y2, y1);  // e0 = EdgeFunction(p, v1, v2)
+  f.d20x = fsub(x0, x2); f.d20y = fsub(y0, y2);  // e1 = EdgeFunction(p, v2, v0)
+  f.d01x = fsub(x1, x0); f.d01y = fsub(y1, y0);  // e2 = EdgeFunction(p, v0, v1)
+  f.il12 = 1.f / (f.d12x * f.d12x + f.d12y * f.d12y);
+  f.il20 = 1.f / (f.d20x * f.d20x + f.d20y * f.d20y);
+  f.il01 = 1.f / (f.d01x * f.d01x + f.d01y * f.d01y);
+  f.iz0 = 1.f / z0; f.iz1 = 1.f / z1; f.iz2 = 1.f / z2;
+}
+
+// Branch-free classification of one (pixel, face) pair against a staged FaceTile; same decisions as classify_pair_vis
+// (the exactness argument is above classify_pair): returns PAIR_REJECT / PAIR_SATURATED / PAIR_FULL, or PAIR_EXACT for a
+// face with a vertex behind the camera.  `inside` = strict inside by the bit-exact edge functions; e[] are returned for
+// the fast inverse depth.  With NEED_DIST = false (visibility only) inside pairs report PAIR_SATURATED, all others REJECT.
+enum { PAIR_EXACT = 3 };
+
+template <bool NEED_DIST>
+__device__ __forceinline__ int classify_fast(const FaceTile& f, float px, float py, float far, float sat, bool& inside,
+                                             float& e0, float& e1, float& e2) {
+  bool inb = !(px > f.xmax || px < f.xmin || py > f.ymax || py < f.ymin);
+  e0 = fsub(fmul(fsub(px, f.x1), f.d12y), fmul(fsub(py, f.y1), f.d12x));
+  e1 = fsub(fmul(fsub(px, f.x2), f.d20y), fmul(fsub(py, f.y2), f.d20x));
+  e2 = fsub(fmul(fsub(px, f.x0), f.d01y), fmul(fsub(py, f.y0), f.d01x));
+  float sg = f.sgn;
+  bool i0 = e0 * sg > 0.f, i1 = e1 * sg > 0.f, i2 = e2 * sg > 0.f;
+  inside = inb & i0 & i1 & i2;
+  int cls;
+  if (NEED_DIST) {
+    float u0 = e0 * e0 * f.il12, u1 = e1 * e1 * f.il20, u2 = e2 * e2 * f.il01;
+    bool sat_all = (u0 >= sat) & (u1 >= sat) & (u2 >= sat);
+    bool far_any = (!i0 & (u0 >= far)) | (!i1 & (u1 >= far)) | (!i2 & (u2 >= far));
+    cls = inside ? (sat_all ? PAIR_SATURATED : PAIR_FULL) : (far_any ? PAIR_REJECT : PAIR_FULL);
+  } else {
+    cls = inside ? PAIR_SATURATED : PAIR_REJECT;
+  }
+  cls = sg == 0.f ? PAIR_EXACT : cls;
+  return inb ? cls : PAIR_REJECT;
+}
+
+// fast inverse depth of an inside pair: sum(w_i / z_i) / sum(w_i) with w_i ~ e_i (independent of the area)
+__device__ __forceinline__ float fast_inv_depth(const FaceTile& f, float e0, float e1, float e2) {
+  return __fdividef(e0 * f.iz0 + e1 * f.iz1 + e2 * f.iz2, e0 + e1 + e2);
+}
+
 // Visibility candidate update.  The fast inverse depth q orders candidates; when two are within 1e-5 relative (touching
 // or interpenetrating surfaces) the decision is taken with the exact perspective-correct depth, ties to the lower face
 // id — the order PyTorch3D's K=1 insertion produces.
@@ -220,16 +297,24 @@ __device__ __forceinline__ void vis_update(const harp_ctx& c, const float* ndc, 
 // Backward of one silhouette factor: alpha = 1 - prod_k(1 - p_k), p = sigmoid(-sd/sigma)  =>  d alpha / d sd_k = -prod p_k / sigma
 // (only reached when no factor is exactly zero), then PointLineDistanceBackward of the closest edge:
 // q = a + t (b - a), d = q - p ; grad_a = g (1-t) 2 d ; grad_b = g t 2 d.   d_ndc rows are (x, y, z, pad).
-__device__ __forceinline__ void sil_pair_gradient(const FaceRec& f, float px, float py, float sd, int edge, float t, float g,
+__device__ __forceinline__ void face_verts(const harp_ctx&, const FaceRec& f, int& v0, int& v1, int& v2) { v0 = f.v0; v1 = f.v1; v2 = f.v2; }
+__device__ __forceinline__ void face_verts(const harp_ctx& c, const FaceTile& f, int& v0, int& v1, int& v2) {
+  const int32_t* fv = c.faces + (size_t)f.fid * 3;
+  v0 = fv[0]; v1 = fv[1]; v2 = fv[2];
+}
+
+template <typename F>
+__device__ __forceinline__ void sil_pair_gradient(const harp_ctx& c, const F& f, float px, float py, float sd, int edge, float t, float g,
                                                   float prod, float sigma, float* d_ndc) {
   float prob = 1.f / (1.f + expf(fdiv(sd, sigma)));
   float gsd = g * (-prod * prob / sigma);
   float gd = sd < 0.f ? -gsd : gsd;  // w.r.t. the unsigned squared distance (inside <=> signed distance negative)
   if (gd == 0.f) return;
-  float ax, ay, bx, by; int va, vb;
-  if (edge == 0) { ax = f.x0; ay = f.y0; bx = f.x1; by = f.y1; va = f.v0; vb = f.v1; }
-  else if (edge == 1) { ax = f.x0; ay = f.y0; bx = f.x2; by = f.y2; va = f.v0; vb = f.v2; }
-  else { ax = f.x1; ay = f.y1; bx = f.x2; by = f.y2; va = f.v1; vb = f.v2; }
+  float ax, ay, bx, by; int va, vb, fv0, fv1, fv2;
+  face_verts(c, f, fv0, fv1, fv2);
+  if (edge == 0) { ax = f.x0; ay = f.y0; bx = f.x1; by = f.y1; va = fv0; vb = fv1; }
+  else if (edge == 1) { ax = f.x0; ay = f.y0; bx = f.x2; by = f.y2; va = fv0; vb = fv2; }
+  else { ax = f.x1; ay = f.y1; bx = f.x2; by = f.y2; va = fv1; vb = fv2; }
   if (t < 0.f) {  // degenerate edge: dist = |p - b|^2
     atomicAdd(reinterpret_cast<float2*>(d_ndc + (size_t)vb * 4), make_float2(gd * 2.f * (bx - px), gd * 2.f * (by - py)));
     return;

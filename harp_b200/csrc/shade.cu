@@ -19,25 +19,28 @@ constexpr int CHUNK = 64;
 constexpr int NT = HARP_TILE * HARP_TILE;
 
 __device__ __forceinline__ void nearest_face(const harp_ctx& c, const float* ndc, const int32_t* list, int n, float px,
-                                             float py, FaceRec* faces, Hit& h) {
-  // ordering by the fast inverse depth q (raster.cuh: classify_pair_vis); the winner is re-evaluated exactly below
+                                             float py, FaceTile* faces, Hit& h) {
+  // ordering by the fast inverse depth q (raster.cuh: classify_fast); the winner is re-evaluated exactly below
   int best = -1;
   float best_q = 0.f;
   for (int base = 0; base < n; base += CHUNK) {
     int m = min(CHUNK, n - base);
     __syncthreads();
-    if (threadIdx.x < m) load_face(c, ndc, list[base + threadIdx.x], 0.f, faces[threadIdx.x]);
+    if (threadIdx.x < m) stage_face(c, ndc, list[base + threadIdx.x], 0.f, faces[threadIdx.x]);
     __syncthreads();
     for (int i = 0; i < m; ++i) {
-      const FaceRec& f = faces[i];
-      bool inside, exact;
-      float q;
-      if (classify_pair_vis<false>(f, px, py, 0.f, 0.f, inside, q, exact) == PAIR_REJECT) continue;
-      if (exact) {
+      const FaceTile& f = faces[i];
+      bool inside;
+      float e0, e1, e2, q;
+      int cls = classify_fast<false>(f, px, py, 0.f, 0.f, inside, e0, e1, e2);
+      if (cls == PAIR_REJECT) continue;
+      if (cls == PAIR_EXACT) {
         PairEval e;
         eval_pair_full<false, false>(f, px, py, 0.f, e);
         inside = e.pass;
         q = e.pass ? 1.f / e.pz : 0.f;
+      } else {
+        q = fast_inv_depth(f, e0, e1, e2);
       }
       if (inside) vis_update(c, ndc, px, py, f.fid, q, best, best_q);
     }
@@ -59,7 +62,7 @@ __global__ void __launch_bounds__(NT) light_depth_kernel(harp_ctx c, int S, cons
                                                          const int32_t* __restrict__ bin_count, const int32_t* __restrict__ bin_start,
                                                          const int32_t* __restrict__ bin_list, float* __restrict__ zbuf,
                                                          int32_t* __restrict__ face) {
-  __shared__ FaceRec faces[CHUNK];
+  __shared__ FaceTile faces[CHUNK];
   int b = blockIdx.z, tw = S / HARP_TILE;
   int lx = threadIdx.x % HARP_TILE, ly = threadIdx.x / HARP_TILE;
   int col = blockIdx.x * HARP_TILE + lx, row = blockIdx.y * HARP_TILE + ly;
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(256) light_depth_bwd_kernel(harp_ctx c, int B,
 // MODE 0 forward; 1 backward with upstream g_rgb; 2 fused photometric L1 on the eroded mask
 template <int MODE>
 __global__ void __launch_bounds__(NT, (MODE == 0 ? 16 : 10)) shade_kernel(harp_ctx c, ShadeArgs a) {
-  __shared__ FaceRec faces[CHUNK];
+  __shared__ FaceTile faces[CHUNK];
   __shared__ float red[32];
   int b = blockIdx.z, S = a.S, tw = S / HARP_TILE;
   int lx = threadIdx.x % HARP_TILE, ly = threadIdx.x / HARP_TILE;
