@@ -77,6 +77,8 @@ struct harp_ctx {
   float* d_verts4 = nullptr;      // (B,V,4) shade-backward accumulators, folded into the caller's (B,V,3) tensors
   float* d_normals4 = nullptr;    // (B,V,4)
   float* d_tex4 = nullptr;        // (2,texcap,4) texture / normal-map gradient accumulators
+  float* tex4 = nullptr;          // (2,texcap,4) packed copies read by the shading taps: albedo (r,g,b,0) and the NORMALISED
+                                  // normal map (n.x, n.y, n.z, 1/|m|; negative when |m| <= 1e-12), one 16-byte load per tap
   int64_t texcap = 0;
   int32_t* bin_count = nullptr;   // (2,B,tiles)  [0]=camera view, [1]=light view
   int32_t* bin_start = nullptr;   // (2,B,tiles)
@@ -85,8 +87,7 @@ struct harp_ctx {
   float* light_zbuf = nullptr;    // (B,S,S)
   int32_t* light_face = nullptr;  // (B,S,S)
   float* d_light_zbuf = nullptr;  // (B,S,S)
-  int32_t* vis_fid = nullptr;     // (B,S,S) nearest camera-view face per pixel (fused pixel pass)
-  int32_t* hit_list = nullptr;    // (B,S*S) compacted row*S+col of hit pixels, per frame
+  int32_t* hit_list = nullptr;    // (B,S*S,2) compacted (row*S+col, nearest camera-view face) of hit pixels, per frame
   int32_t* hit_count = nullptr;   // (B)
   float* vN = nullptr;            // (B,V,3) unnormalised vertex normals (mesh build scratch)
   float* vtmp = nullptr;          // (B,V,3) scratch

@@ -237,10 +237,10 @@ extern "C" int harp_ctx_create_lbs(harp_ctx** out, const harp_topology* topo, co
 static void free_scratch(harp_ctx* c) {
   void* ptrs[] = {c->ndc_cam, c->ndc_light, c->d_ndc_cam, c->d_ndc_light, c->bin_count, c->bin_start, c->bin_fill,
                   c->bin_list, c->light_zbuf, c->light_face, c->d_light_zbuf, c->vN, c->vtmp, c->vtmp2, c->d_verts4,
-                  c->d_normals4, c->vis_fid, c->hit_list, c->hit_count, c->ovf_list, c->ovf_count};
+                  c->d_normals4, c->hit_list, c->hit_count, c->ovf_list, c->ovf_count};
   c->ovf_list = c->ovf_count = nullptr;
   c->d_verts4 = c->d_normals4 = nullptr;
-  c->vis_fid = c->hit_list = c->hit_count = nullptr;
+  c->hit_list = c->hit_count = nullptr;
   for (void* p : ptrs) if (p) cudaFree(p);
   c->ndc_cam = c->ndc_light = c->d_ndc_cam = c->d_ndc_light = c->light_zbuf = c->d_light_zbuf = c->vN = c->vtmp = c->vtmp2 = nullptr;
   c->bin_count = c->bin_start = c->bin_fill = c->bin_list = c->light_face = nullptr;
@@ -252,7 +252,7 @@ extern "C" void harp_ctx_destroy(harp_ctx* c) {
   free_scratch(c);
   void* ptrs[] = {c->faces, c->edges0, c->v0e_off, c->v0e_idx, c->vf_off, c->vf_idx, c->vn_off, c->vn_idx, c->edges,
                   c->nc_pairs, c->face_uvs, c->shapedirs, c->posedirs, c->v_template, c->weights,
-                  c->J_template, c->J_shapedirs, c->tips, c->counters, c->d_tex4, c->weightsT, c->pose_mean, c->parents,
+                  c->J_template, c->J_shapedirs, c->tips, c->counters, c->d_tex4, c->tex4, c->weightsT, c->pose_mean, c->parents,
                   c->joint_out_src};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->prof) {
@@ -290,8 +290,7 @@ extern "C" int harp_ctx_reserve(harp_ctx* c, int max_batch, int img_size) {
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->light_zbuf, npx * sizeof(float)));
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->light_face, npx * sizeof(int32_t)));
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->d_light_zbuf, npx * sizeof(float)));
-  HARP_CHECK_CUDA(cudaMalloc((void**)&c->vis_fid, npx * sizeof(int32_t)));
-  HARP_CHECK_CUDA(cudaMalloc((void**)&c->hit_list, npx * sizeof(int32_t)));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->hit_list, 2 * npx * sizeof(int32_t)));
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->hit_count, (size_t)B * sizeof(int32_t)));
   c->ovf_cap = (int)std::min<size_t>(npx, (size_t)1 << 22);
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->ovf_list, (size_t)c->ovf_cap * sizeof(int32_t)));

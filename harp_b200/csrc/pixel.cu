@@ -11,6 +11,7 @@ int harp_project(harp_ctx* c, int B, int S, float focal, const float* verts, con
 int harp_project_bwd(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R, const float* T,
                      const float* d_ndc, float* d_verts, float* d_R, float* d_T, cudaStream_t st);
 int harp_fold4(size_t n, const float* src4, float* dst3, cudaStream_t st);
+int harp_tex_prepare(harp_ctx* c, const float* texture, const float* normal_map, int texH, int texW, cudaStream_t st);
 int harp_light_depth(harp_ctx* c, int B, int S, cudaStream_t st);
 int harp_light_depth_bwd(harp_ctx* c, int B, int S, cudaStream_t st);
 int harp_sil_topk(harp_ctx* c, int mode, int S, int K, float sigma, float blur, float radius, float* alpha, const float* gin,
@@ -34,7 +35,7 @@ struct VisArgs {
   float* sil_loss;
   float* d_ndc;
   // visibility
-  int32_t *vis_fid, *hit_list, *hit_count;
+  int32_t *hit_list, *hit_count;  // hit_list: (B, S*S) int2 records (row*S+col, face id)
   // background pixels of the colour image
   float* rgb;
   const float *y_true, *y_mask;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(NT, 16) pixel_vis_kernel(harp_ctx c, VisArgs a
   __shared__ int q_n, any_bwd;
   __shared__ float s_g[NT], s_prod[NT];
   __shared__ unsigned char s_need[NT];
+  __shared__ float s_px[HARP_TILE], s_py[HARP_TILE];  // NDC centres of the tile's columns / rows (queue drains look pixels up)
   const int S = a.S;
   int b = blockIdx.z, tw = S / HARP_TILE, tid = threadIdx.x;
   int lx = tid % HARP_TILE, ly = tid / HARP_TILE;
@@ -77,7 +79,6 @@ __global__ void __launch_bounds__(NT, 16) pixel_vis_kernel(harp_ctx c, VisArgs a
     float mk = 0.f;
     f3 y = mk3(0.f, 0.f, 0.f);
     if (PHOTO) { mk = __ldcs(a.y_mask + pix); y = mk3(__ldcs(a.y_true + pix * 3), __ldcs(a.y_true + pix * 3 + 1), __ldcs(a.y_true + pix * 3 + 2)); }
-    a.vis_fid[pix] = -1;
     a.alpha[pix] = 0.f;
     st3(a.rgb + pix * 3, mk3(1.f, 1.f, 1.f));
     float s_sil = fabsf(ys), s_ph = PHOTO ? fabsf(mk - y.x * mk) + fabsf(mk - y.y * mk) + fabsf(mk - y.z * mk) : 0.f;
@@ -95,6 +96,8 @@ __global__ void __launch_bounds__(NT, 16) pixel_vis_kernel(harp_ctx c, VisArgs a
   const float* ndc = a.ndc + (size_t)b * c.V * 3;
   const float sigma = a.sigma, blur = a.blur;
   float px = pix_to_ndc(col, S), py = pix_to_ndc(row, S);
+  if (ly == 0) s_px[lx] = px;
+  if (lx == 0) s_py[ly] = py;
   float prod = 1.f;
   int nzero = 0, npass = 0, ncand = 0;
   int best_fid = -1;
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(NT, 16) pixel_vis_kernel(harp_ctx c, VisArgs a
     int qn = min(q_n, QCAP);
     for (int s = tid; s < qn; s += NT) {
       int p = q_pix[s];
-      float ppx = pix_to_ndc(blockIdx.x * HARP_TILE + (p % HARP_TILE), S), ppy = pix_to_ndc(blockIdx.y * HARP_TILE + (p / HARP_TILE), S);
+      float ppx = s_px[p % HARP_TILE], ppy = s_py[p / HARP_TILE];
       PairEval e;
       eval_pair_full<true, true>(faces[q_face[s]], ppx, ppy, blur, e);
       if (e.pass) { q_sd[s] = e.inside ? -e.dist : e.dist; q_edge[s] = (unsigned char)e.edge; q_t[s] = e.t; }
@@ -172,7 +175,6 @@ __global__ void __launch_bounds__(NT, 16) pixel_vis_kernel(harp_ctx c, VisArgs a
     }
   }
   // ---- visibility outputs: face id image + per-frame compacted hit list (warp-aggregated append)
-  a.vis_fid[pix] = best_fid;
   bool hit = best_fid >= 0;
   {
     unsigned mask = __ballot_sync(0xffffffffu, hit);
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(NT, 16) pixel_vis_kernel(harp_ctx c, VisArgs a
     if (mask) {
       if (lane == 0) base = atomicAdd(a.hit_count + b, __popc(mask));
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (hit) a.hit_list[(size_t)b * S * S + base + __popc(mask & ((1u << lane) - 1u))] = row * S + col;
+      if (hit) reinterpret_cast<int2*>(a.hit_list)[(size_t)b * S * S + base + __popc(mask & ((1u << lane) - 1u))] = make_int2(row * S + col, best_fid);
     }
   }
   float photo_abs = 0.f;
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(NT, 16) pixel_vis_kernel(harp_ctx c, VisArgs a
     for (int s = tid; s < qn; s += NT) {
       int p = q_pix[s];
       if (!s_need[p] || q_edge[s] == 255) continue;
-      float ppx = pix_to_ndc(blockIdx.x * HARP_TILE + (p % HARP_TILE), S), ppy = pix_to_ndc(blockIdx.y * HARP_TILE + (p / HARP_TILE), S);
+      float ppx = s_px[p % HARP_TILE], ppy = s_py[p / HARP_TILE];
       sil_pair_gradient(c, faces[q_face[s]], ppx, ppy, q_sd[s], q_edge[s], q_t[s], s_g[p], s_prod[p], sigma, d_ndc);
     }
     return;
@@ -249,24 +251,24 @@ __global__ void __launch_bounds__(NT, 16) pixel_vis_kernel(harp_ctx c, VisArgs a
 #define HARP_SHADE_MIN_CTAS 4
 #endif
 template <int MODE>
-__global__ void __launch_bounds__(128, HARP_SHADE_MIN_CTAS) shade_deferred_kernel(harp_ctx c, ShadeArgs a, const int32_t* __restrict__ vis_fid,
-                                                             const int32_t* __restrict__ hit_list,
+__global__ void __launch_bounds__(128, HARP_SHADE_MIN_CTAS) shade_deferred_kernel(harp_ctx c, ShadeArgs a, const int2* __restrict__ hit_list,
                                                              const int32_t* __restrict__ hit_count) {
   const int S = a.S;
   int b = blockIdx.y;
   int n = hit_count[b];
   int n_pad = (n + 31) & ~31;  // keep warps whole for the warp reductions
   const float* ndc = a.ndc_cam + (size_t)b * c.V * 3;
-  const int32_t* list = hit_list + (size_t)b * S * S;
+  const int2* list = hit_list + (size_t)b * S * S;
   float loss_acc = 0.f, fr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_pad; idx += gridDim.x * blockDim.x) {
     if (idx >= n) continue;
-    int rc = list[idx];
+    int2 rec = list[idx];
+    int rc = rec.x;
     int row = rc / S, col = rc % S;
     size_t pix = (size_t)b * S * S + rc;
     float px = pix_to_ndc(col, S), py = pix_to_ndc(row, S);
     Hit h;
-    h.fid = vis_fid[pix];
+    h.fid = rec.y;
     FaceRec f;
     load_face(c, ndc, h.fid, 0.f, f);
     PairEval e;
@@ -315,13 +317,8 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
     if ((rc = harp_light_depth(c, B, S, st)) != HARP_OK) return rc;
   }
   if (sil_bwd || photo_bwd) HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_cam, 0, nv4, st));
+  if ((rc = harp_tex_prepare(c, r->texture, r->normal_map, r->texH, r->texW, st)) != HARP_OK) return rc;
   if (photo_bwd) {
-    if ((int64_t)ntex > c->texcap) {
-      if (c->d_tex4) cudaFree(c->d_tex4);
-      c->d_tex4 = nullptr; c->texcap = 0;
-      HARP_CHECK_CUDA(cudaMalloc((void**)&c->d_tex4, 2 * ntex * 4 * sizeof(float)));
-      c->texcap = (int64_t)ntex;
-    }
     HARP_CHECK_CUDA(cudaMemsetAsync(c->d_verts4, 0, nv4, st));
     HARP_CHECK_CUDA(cudaMemsetAsync(c->d_normals4, 0, nv4, st));
     HARP_CHECK_CUDA(cudaMemsetAsync(c->d_tex4, 0, 2 * ntex * 4 * sizeof(float), st));
@@ -337,7 +334,7 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
   v.bin_count = c->bin_count; v.bin_start = c->bin_start; v.bin_list = c->bin_list;
   v.alpha = r->alpha; v.y_sil = r->y_sil; v.sil_inv_n = 1.f / ((float)B * S * S); v.sil_gscale = r->w_sil * v.sil_inv_n;
   v.sil_loss = r->loss_sil; v.d_ndc = c->d_ndc_cam;
-  v.vis_fid = c->vis_fid; v.hit_list = c->hit_list; v.hit_count = c->hit_count;
+  v.hit_list = c->hit_list; v.hit_count = c->hit_count;
   v.rgb = r->rgb; v.y_true = r->y_true; v.y_mask = r->y_mask; v.photo_inv_n = 1.f / ((float)B * S * S * 3.f);
   v.photo_loss = r->loss_photo;
   dim3 grid(S / HARP_TILE, S / HARP_TILE, B);
@@ -355,7 +352,8 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
   a.inv_n = v.photo_inv_n; a.gscale = r->w_photo * a.inv_n;
   a.verts = r->verts; a.normals = r->normals; a.ndc_cam = c->ndc_cam;
   a.light_R = r->light_R ? r->light_R : r->cam_R; a.light_T = r->light_T ? r->light_T : r->cam_T;
-  a.light_pos = r->light_pos; a.amb = r->amb; a.texture = r->texture; a.normal_map = r->normal_map;
+  a.light_pos = r->light_pos; a.amb = r->amb;
+  a.tex4 = reinterpret_cast<const float4*>(c->tex4); a.nm4 = a.tex4 + ntex;
   a.light_zbuf = c->light_zbuf; a.rgb = r->rgb; a.gin = r->y_true; a.mask = r->y_mask; a.loss = r->loss_photo;
   if (photo_bwd) {
     a.d_ndc_cam = c->d_ndc_cam; a.d_verts = c->d_verts4; a.d_normals = c->d_normals4;
@@ -364,8 +362,8 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
   }
   dim3 sgrid(96, B);
   harp_prof_begin(c, 1, st);
-  if (photo_bwd) shade_deferred_kernel<2><<<sgrid, 128, 0, st>>>(*c, a, c->vis_fid, c->hit_list, c->hit_count);
-  else shade_deferred_kernel<0><<<sgrid, 128, 0, st>>>(*c, a, c->vis_fid, c->hit_list, c->hit_count);
+  if (photo_bwd) shade_deferred_kernel<2><<<sgrid, 128, 0, st>>>(*c, a, reinterpret_cast<const int2*>(c->hit_list), c->hit_count);
+  else shade_deferred_kernel<0><<<sgrid, 128, 0, st>>>(*c, a, reinterpret_cast<const int2*>(c->hit_list), c->hit_count);
   harp_prof_end(c, 1, st);
   HARP_LAUNCH_CHECK();
   if (photo_bwd) {

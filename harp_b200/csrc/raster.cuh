@@ -248,7 +248,7 @@ enum { PAIR_EXACT = 3 };
 template <bool NEED_DIST>
 __device__ __forceinline__ int classify_fast(const FaceTile& f, float px, float py, float far, float sat, bool& inside,
                                              float& e0, float& e1, float& e2) {
-  bool inb = !(px > f.xmax || px < f.xmin || py > f.ymax || py < f.ymin);
+  bool inb = !((px > f.xmax) | (px < f.xmin) | (py > f.ymax) | (py < f.ymin));  // bitwise: no short-circuit branches
   e0 = fsub(fmul(fsub(px, f.x1), f.d12y), fmul(fsub(py, f.y1), f.d12x));
   e1 = fsub(fmul(fsub(px, f.x2), f.d20y), fmul(fsub(py, f.y2), f.d20x));
   e2 = fsub(fmul(fsub(px, f.x0), f.d01y), fmul(fsub(py, f.y0), f.d01x));

@@ -13,9 +13,25 @@ int harp_project_bwd(harp_ctx* c, int B, int S, float focal, const float* verts,
                      const float* d_ndc, float* d_verts, float* d_R, float* d_T, cudaStream_t st);
 int harp_fold4(size_t n, const float* src4, float* dst3, cudaStream_t st);
 
+int harp_tex_prepare(harp_ctx* c, const float* texture, const float* normal_map, int texH, int texW, cudaStream_t st);
+
 namespace {
 
 constexpr int CHUNK = 64;
+
+// texture (r,g,b) -> (r,g,b,0); normal map m -> (m / max(|m|, 1e-12), +-1 / max(|m|, 1e-12)): prepare_materials'
+// F.normalize (utils/visualize.py:99) done once per texel instead of once per tap, and one 16-byte load per tap
+__global__ void __launch_bounds__(256) pack_tex_kernel(size_t n, const float* __restrict__ tex, const float* __restrict__ nm,
+                                                        float4* __restrict__ tex4, float4* __restrict__ nm4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  tex4[i] = make_float4(tex[i * 3], tex[i * 3 + 1], tex[i * 3 + 2], 0.f);
+  float x = nm[i * 3], y = nm[i * 3 + 1], z = nm[i * 3 + 2];
+  float l = sqrtf(x * x + y * y + z * z);
+  float inv = 1.f / fmaxf(l, 1e-12f);
+  nm4[i] = make_float4(x * inv, y * inv, z * inv, l > 1e-12f ? inv : -inv);
+}
+
 constexpr int NT = HARP_TILE * HARP_TILE;
 
 __device__ __forceinline__ void nearest_face(const harp_ctx& c, const float* ndc, const int32_t* list, int n, float px,
@@ -68,7 +84,13 @@ __global__ void __launch_bounds__(NT) light_depth_kernel(harp_ctx c, int S, cons
   int col = blockIdx.x * HARP_TILE + lx, row = blockIdx.y * HARP_TILE + ly;
   size_t pix = ((size_t)b * S + row) * S + col;
   size_t tglob = (size_t)b * tw * tw + blockIdx.y * tw + blockIdx.x;
-  int n = bin_count[tglob], start = bin_start[tglob];
+  int n = bin_count[tglob];
+  if (n == 0) {  // empty light tile
+    zbuf[pix] = -1.f;
+    face[pix] = -1;
+    return;
+  }
+  int start = bin_start[tglob];
   if (start + n > c.bin_cap) n = max(0, (int)c.bin_cap - start);
   Hit h;
   nearest_face(c, ndc_all + (size_t)b * c.V * 3, bin_list + (size_t)b * c.bin_cap + start, n, pix_to_ndc(col, S),
@@ -226,6 +248,23 @@ extern "C" int harp_render_normals(harp_ctx* c, int B, int S, float focal, int K
   return HARP_OK;
 }
 
+// (Re)allocate the packed texel buffers for a texH x texW map (one-time) and refresh the packed copies.
+int harp_tex_prepare(harp_ctx* c, const float* texture, const float* normal_map, int texH, int texW, cudaStream_t st) {
+  size_t ntex = (size_t)texH * texW;
+  if ((int64_t)ntex > c->texcap) {
+    if (c->d_tex4) cudaFree(c->d_tex4);
+    if (c->tex4) cudaFree(c->tex4);
+    c->d_tex4 = c->tex4 = nullptr; c->texcap = 0;
+    HARP_CHECK_CUDA(cudaMalloc((void**)&c->d_tex4, 2 * ntex * 4 * sizeof(float)));
+    HARP_CHECK_CUDA(cudaMalloc((void**)&c->tex4, 2 * ntex * 4 * sizeof(float)));
+    c->texcap = (int64_t)ntex;
+  }
+  pack_tex_kernel<<<(int)((ntex + 255) / 256), 256, 0, st>>>(ntex, texture, normal_map, reinterpret_cast<float4*>(c->tex4),
+                                                             reinterpret_cast<float4*>(c->tex4) + ntex);
+  HARP_LAUNCH_CHECK();
+  return HARP_OK;
+}
+
 // light-view depth pass / its backward on the ctx scratch (projected light-view verts and bins must be current)
 int harp_light_depth(harp_ctx* c, int B, int S, cudaStream_t st) {
   dim3 grid(S / HARP_TILE, S / HARP_TILE, B);
@@ -279,17 +318,13 @@ extern "C" int harp_shade(harp_ctx* c, int mode, int B, int S, float focal, int 
   a.inv_n = 1.f / ((float)B * (float)S * (float)S * 3.f);
   a.gscale = weight * a.inv_n;
   a.verts = verts; a.normals = normals; a.ndc_cam = c->ndc_cam; a.light_R = light_R ? light_R : cam_R;
-  a.light_T = light_T ? light_T : cam_T; a.light_pos = light_pos; a.amb = amb; a.texture = texture; a.normal_map = normal_map;
+  a.light_T = light_T ? light_T : cam_T; a.light_pos = light_pos; a.amb = amb;
   a.light_zbuf = c->light_zbuf; a.bin_count = c->bin_count; a.bin_start = c->bin_start; a.bin_list = c->bin_list;
   a.rgb = rgb; a.gin = gin; a.mask = mask; a.loss = loss;
   size_t ntex = (size_t)texH * texW;
+  if ((rc = harp_tex_prepare(c, texture, normal_map, texH, texW, st)) != HARP_OK) return rc;
+  a.tex4 = reinterpret_cast<const float4*>(c->tex4); a.nm4 = a.tex4 + ntex;
   if (mode != 0) {
-    if ((int64_t)ntex > c->texcap) {  // one-time (re)allocation of the padded texel accumulators
-      if (c->d_tex4) cudaFree(c->d_tex4);
-      c->d_tex4 = nullptr; c->texcap = 0;
-      HARP_CHECK_CUDA(cudaMalloc((void**)&c->d_tex4, 2 * ntex * 4 * sizeof(float)));
-      c->texcap = (int64_t)ntex;
-    }
     size_t nv4 = (size_t)B * c->V * 4 * sizeof(float);
     HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_cam, 0, nv4, st));
     HARP_CHECK_CUDA(cudaMemsetAsync(c->d_verts4, 0, nv4, st));

@@ -8,7 +8,8 @@ struct ShadeArgs {
   int fixed_lights;      // 1: Phong twin with constant light colours ka, kd, ks (renderer_helper.py:70-73); 0: ka = amb, kd = 1 - amb, ks = 0
   float ka, kd, ks;
   float focal, gscale, inv_n;
-  const float *verts, *normals, *ndc_cam, *light_R, *light_T, *light_pos, *amb, *texture, *normal_map;
+  const float *verts, *normals, *ndc_cam, *light_R, *light_T, *light_pos, *amb;
+  const float4 *tex4, *nm4;  // packed albedo / normalised normal map (harp_tex_prepare)
   const float* light_zbuf;
   const int32_t *bin_count, *bin_start, *bin_list;
   float* rgb;
@@ -80,8 +81,13 @@ __device__ __forceinline__ void make_taps(float u, float v, int H, int W, Taps& 
 }
 
 __device__ __forceinline__ f3 normalize12(f3 x) {  // F.normalize default eps = 1e-12
-  float l = fmaxf(sqrtf(dot(x, x)), 1e-12f);
-  return mk3(x.x / l, x.y / l, x.z / l);
+  float inv = 1.f / fmaxf(sqrtf(dot(x, x)), 1e-12f);
+  return mk3(x.x * inv, x.y * inv, x.z * inv);
+}
+// backward of F.normalize at a packed normal-map texel (n = m / max(|m|, eps), w = 1 / max(|m|, eps), negative in the eps case)
+__device__ __forceinline__ f3 normalize_bwd_packed(float4 t, f3 gy) {
+  f3 n = mk3(t.x, t.y, t.z);
+  return t.w > 0.f ? t.w * (gy - dot(n, gy) * n) : (-t.w) * gy;
 }
 __device__ __forceinline__ f3 normalize_bwd_eps(f3 x, f3 gy, float eps) {
   float l = sqrtf(dot(x, x));
@@ -129,7 +135,7 @@ __device__ __forceinline__ void shade_pixel(const harp_ctx& c, const ShadeArgs& 
   Taps tp;
   float amb = a.amb[0], cosang = 0.f, vis = 1.f, sh = 0.f, zL = 0.f, s_sign = 1.f, aa = 0.f;
   f3 uvec, vvec;
-  int tapidx[9];
+  int tap_xk = 0, tap_yk = 0;  // centre of the 3x3 PCF window (tap addresses are recomputed in the backward half)
   float tapsig[9];
   const float* lR = a.light_R + (size_t)b * 9;
   const float* lT = a.light_T + (size_t)b * 3;
@@ -153,8 +159,9 @@ __device__ __forceinline__ void shade_pixel(const harp_ctx& c, const ShadeArgs& 
     m = mk3(0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      tex = tex + tp.w[k] * ld3(a.texture + (size_t)tp.idx[k] * 3);
-      m = m + tp.w[k] * normalize12(ld3(a.normal_map + (size_t)tp.idx[k] * 3));
+      float4 t = __ldg(a.tex4 + tp.idx[k]), nm = __ldg(a.nm4 + tp.idx[k]);
+      tex = tex + tp.w[k] * mk3(t.x, t.y, t.z);
+      m = m + tp.w[k] * mk3(nm.x, nm.y, nm.z);
     }
     // PBRMaterials.compute_tangent / apply_normal_map on the (un-normalised) interpolated normal
     s_sign = N.z >= 0.f ? 1.f : -1.f;
@@ -182,6 +189,7 @@ __device__ __forceinline__ void shade_pixel(const harp_ctx& c, const ShadeArgs& 
       float xr = rintf(xs), yr = rintf(ys);
       xr = fminf(fmaxf(xr, -2.f), (float)S + 1.f); yr = fminf(fmaxf(yr, -2.f), (float)S + 1.f);
       int xk = (int)xr, yk = (int)yr;
+      tap_xk = xk; tap_yk = yk;
       const float* zb = a.light_zbuf + (size_t)b * S * S;
       float acc = 0.f;
 #pragma unroll
@@ -190,9 +198,8 @@ __device__ __forceinline__ void shade_pixel(const harp_ctx& c, const ShadeArgs& 
         for (int jj = -1; jj <= 1; ++jj) {
           int ry = min(max(yk + ii, 0), S - 1), rx = min(max(xk + jj, 0), S - 1);
           int t = (ii + 1) * 3 + (jj + 1);
-          tapidx[t] = ry * S + rx;
-          float x = (zb[tapidx[t]] - (zL - 0.008f)) * 1000.f;
-          float sg = 1.f / (1.f + expf(-x));
+          float x = (zb[ry * S + rx] - (zL - 0.008f)) * 1000.f;
+          float sg = __fdividef(1.f, 1.f + __expf(-x));  // sigmoid; 2-ulp exp and division are far inside the 1e-4 image tolerance
           tapsig[t] = sg;
           acc += sg;
         }
@@ -258,7 +265,8 @@ __device__ __forceinline__ void shade_pixel(const harp_ctx& c, const ShadeArgs& 
       for (int t = 0; t < 9; ++t) {
         float ga = g_vis / 9.f * tapsig[t] * (1.f - tapsig[t]) * 1000.f;
         if (ga != 0.f) {
-          atomicAdd(dzb + tapidx[t], ga);
+          int ry = min(max(tap_yk + t / 3 - 1, 0), S - 1), rx = min(max(tap_xk + t % 3 - 1, 0), S - 1);
+          atomicAdd(dzb + ry * S + rx, ga);
           gz -= ga;
         }
       }
@@ -269,14 +277,14 @@ __device__ __forceinline__ void shade_pixel(const harp_ctx& c, const ShadeArgs& 
     // --- textures: value grads to the 4 taps, coordinate grads to uv ---
     float g_u_tex = 0.f, g_v_tex = 0.f;
     {
-      f3 t4[4], m4[4], mraw[4];
+      f3 t4[4], m4[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        t4[k] = ld3(a.texture + (size_t)tp.idx[k] * 3);
-        mraw[k] = ld3(a.normal_map + (size_t)tp.idx[k] * 3);
-        m4[k] = normalize12(mraw[k]);
+        float4 t = __ldg(a.tex4 + tp.idx[k]), nm = __ldg(a.nm4 + tp.idx[k]);
+        t4[k] = mk3(t.x, t.y, t.z);
+        m4[k] = mk3(nm.x, nm.y, nm.z);
         if (tp.w[k] != 0.f) {
-          f3 gt = tp.w[k] * g_tex, gm = normalize_bwd_eps(mraw[k], tp.w[k] * g_m, 1e-12f);
+          f3 gt = tp.w[k] * g_tex, gm = normalize_bwd_packed(nm, tp.w[k] * g_m);
           atomic_add4(a.d_texture + (size_t)tp.idx[k] * 4, gt.x, gt.y, gt.z);
           atomic_add4(a.d_normal_map + (size_t)tp.idx[k] * 4, gm.x, gm.y, gm.z);
         }
