@@ -1,0 +1,145 @@
+// Per-frame camera / light glue of the fused optimiser step, forward and backward, as two launches.
+// Replaces, per minibatch: the weak-perspective camera of render_image (utils/visualize.py:266-270), the shadow pass's light
+// camera (process_info_for_shadow, renderer/renderer_helper.py:454-468; look_at_rotation SURVEY.md A.10), hand_verts.mean(1),
+// sigmoid(amb_ratio) (renderer_helper.py:420-433) and the autograd graph through all of them (about 60 ATen launches).
+// The backward uses forward-mode duals over the six inputs (light position, centroid) of the 12 light-camera outputs.
+#include "common.cuh"
+
+namespace {
+
+constexpr float SHADOW_SPHERE_RADIUS = 1.5f;  // renderer_helper.py:463
+
+// F.normalize(v, eps): v / max(|v|, eps)
+template <typename T>
+__device__ inline void normalize_eps(T v[3], float eps) {
+  T n = dsqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  if (dval(n) > eps) { v[0] = v[0] / n; v[1] = v[1] / n; v[2] = v[2] / n; }
+  else { T k(1.f / eps); v[0] = v[0] * k; v[1] = v[1] * k; v[2] = v[2] * k; }
+}
+
+template <typename T>
+__device__ inline void cross3(const T a[3], const T b[3], T o[3]) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// Light camera on the radius-1.5 sphere around the centroid, looking at it: R (row-major, columns = camera x, y, z axes),
+// T = -R^T eye.
+template <typename T>
+__device__ inline void light_camera(const T L[3], const T c[3], T R[9], T Tt[3]) {
+  T off[3] = {L[0] - c[0], L[1] - c[1], L[2] - c[2]};
+  T s = T(SHADOW_SPHERE_RADIUS) / dsqrt(off[0] * off[0] + off[1] * off[1] + off[2] * off[2]);
+  T eye[3] = {c[0] + off[0] * s, c[1] + off[1] * s, c[2] + off[2] * s};
+  T z[3] = {c[0] - eye[0], c[1] - eye[1], c[2] - eye[2]};
+  normalize_eps(z, 1e-5f);
+  T up[3] = {T(0.f), T(1.f), T(0.f)};
+  T x[3], y[3];
+  cross3(up, z, x);
+  normalize_eps(x, 1e-5f);
+  cross3(z, x, y);
+  normalize_eps(y, 1e-5f);
+  if (fabsf(dval(x[0])) <= 5e-3f && fabsf(dval(x[1])) <= 5e-3f && fabsf(dval(x[2])) <= 5e-3f) {  // light straight above / below
+    cross3(y, z, x);
+    normalize_eps(x, 1e-5f);
+  }
+  for (int i = 0; i < 3; ++i) { R[i * 3 + 0] = x[i]; R[i * 3 + 1] = y[i]; R[i * 3 + 2] = z[i]; }
+  for (int j = 0; j < 3; ++j) Tt[j] = -(R[0 * 3 + j] * eye[0] + R[1 * 3 + j] * eye[1] + R[2 * 3 + j] * eye[2]);
+}
+
+__global__ void __launch_bounds__(256) frame_glue_fwd_kernel(int V, int S, float focal, const float* __restrict__ cam_table,
+                                                             const int64_t* __restrict__ fid, const float* __restrict__ light_pos,
+                                                             const float* __restrict__ amb_ratio, const float* __restrict__ verts,
+                                                             float* __restrict__ cam_T, float* __restrict__ light_b,
+                                                             float* __restrict__ light_R, float* __restrict__ light_T,
+                                                             float* __restrict__ amb, float* __restrict__ centroid) {
+  __shared__ float red[32];
+  int b = blockIdx.x;
+  const float* vb = verts + (size_t)b * V * 3;
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) { sx += vb[v * 3]; sy += vb[v * 3 + 1]; sz += vb[v * 3 + 2]; }
+  sx = block_sum(sx, red); sy = block_sum(sy, red); sz = block_sum(sz, red);
+  if (threadIdx.x != 0) return;
+  float c[3] = {sx / (float)V, sy / (float)V, sz / (float)V};
+  const float* cam = cam_table + (size_t)(fid ? fid[b] : b) * 3;
+  cam_T[b * 3 + 0] = -cam[1];
+  cam_T[b * 3 + 1] = -cam[2];
+  cam_T[b * 3 + 2] = (2.f * focal) / ((float)S * cam[0] + 1e-9f);  // utils/visualize.py:268
+  float L[3] = {light_pos[0], light_pos[1], light_pos[2]}, R[9], T[3];
+  light_camera<float>(L, c, R, T);
+  for (int i = 0; i < 9; ++i) light_R[b * 9 + i] = R[i];
+  for (int i = 0; i < 3; ++i) { light_T[b * 3 + i] = T[i]; light_b[b * 3 + i] = L[i]; centroid[b * 3 + i] = c[i]; }
+  if (b == 0) amb[0] = 1.f / (1.f + expf(-amb_ratio[0]));
+}
+
+__global__ void __launch_bounds__(256) frame_glue_bwd_kernel(int V, int S, float focal, const float* __restrict__ cam_table,
+                                                             const int64_t* __restrict__ fid, const float* __restrict__ light_pos,
+                                                             const float* __restrict__ amb_ratio, const float* __restrict__ centroid,
+                                                             const float* __restrict__ d_cam_T, const float* __restrict__ d_light_R,
+                                                             const float* __restrict__ d_light_T, const float* __restrict__ d_light_pos,
+                                                             const float* __restrict__ d_amb, float* __restrict__ g_cam_table,
+                                                             float* __restrict__ g_light_pos, float* __restrict__ g_amb_ratio,
+                                                             float* __restrict__ d_verts) {
+  __shared__ float gc[3];
+  int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int64_t row = fid ? fid[b] : b;
+    const float* cam = cam_table + (size_t)row * 3;
+    if (g_cam_table) {
+      float den = (float)S * cam[0] + 1e-9f;
+      atomicAdd(g_cam_table + row * 3 + 0, d_cam_T[b * 3 + 2] * (-(2.f * focal) * (float)S / (den * den)));
+      atomicAdd(g_cam_table + row * 3 + 1, -d_cam_T[b * 3 + 0]);
+      atomicAdd(g_cam_table + row * 3 + 2, -d_cam_T[b * 3 + 1]);
+    }
+    Dual<6> L[3], c[3], R[9], T[3];
+    for (int i = 0; i < 3; ++i) { L[i] = Dual<6>::var(light_pos[i], i); c[i] = Dual<6>::var(centroid[b * 3 + i], 3 + i); }
+    light_camera<Dual<6>>(L, c, R, T);
+    float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < 9; ++k) {
+      float u = d_light_R[b * 9 + k];
+      for (int i = 0; i < 6; ++i) g[i] += u * R[k].d[i];
+    }
+    for (int k = 0; k < 3; ++k) {
+      float u = d_light_T[b * 3 + k];
+      for (int i = 0; i < 6; ++i) g[i] += u * T[k].d[i];
+    }
+    if (g_light_pos)
+      for (int i = 0; i < 3; ++i) atomicAdd(g_light_pos + i, g[i] + d_light_pos[b * 3 + i]);  // share_light_position: row 0
+    for (int i = 0; i < 3; ++i) gc[i] = g[3 + i] / (float)V;
+    if (b == 0 && g_amb_ratio) {
+      float s = 1.f / (1.f + expf(-amb_ratio[0]));
+      atomicAdd(g_amb_ratio, d_amb[0] * s * (1.f - s));
+    }
+  }
+  __syncthreads();
+  float gx = gc[0], gy = gc[1], gz = gc[2];
+  if (gx == 0.f && gy == 0.f && gz == 0.f) return;
+  float* dv = d_verts + (size_t)b * V * 3;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) { dv[v * 3] += gx; dv[v * 3 + 1] += gy; dv[v * 3 + 2] += gz; }
+}
+
+}  // namespace
+
+extern "C" int harp_frame_glue_fwd(harp_ctx* c, int B, int S, float focal, const float* cam_table, const int64_t* fid,
+                                   const float* light_pos, const float* amb_ratio, const float* verts, float* cam_T,
+                                   float* light_pos_b, float* light_R, float* light_T, float* amb, float* centroid, void* stream) {
+  HARP_REQUIRE(c && B > 0 && cam_table && light_pos && amb_ratio && verts && cam_T && light_pos_b && light_R && light_T && amb &&
+                   centroid, HARP_ERR_INVALID, "harp_frame_glue_fwd: null argument");
+  frame_glue_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(c->V, S, focal, cam_table, fid, light_pos, amb_ratio, verts, cam_T,
+                                                             light_pos_b, light_R, light_T, amb, centroid);
+  HARP_LAUNCH_CHECK();
+  return HARP_OK;
+}
+
+extern "C" int harp_frame_glue_bwd(harp_ctx* c, int B, int S, float focal, const float* cam_table, const int64_t* fid,
+                                   const float* light_pos, const float* amb_ratio, const float* centroid, const float* d_cam_T,
+                                   const float* d_light_R, const float* d_light_T, const float* d_light_pos, const float* d_amb,
+                                   float* g_cam_table, float* g_light_pos, float* g_amb_ratio, float* d_verts, void* stream) {
+  HARP_REQUIRE(c && B > 0 && cam_table && light_pos && amb_ratio && centroid && d_cam_T && d_light_R && d_light_T && d_light_pos &&
+                   d_amb && d_verts, HARP_ERR_INVALID, "harp_frame_glue_bwd: null argument");
+  frame_glue_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(c->V, S, focal, cam_table, fid, light_pos, amb_ratio, centroid, d_cam_T,
+                                                             d_light_R, d_light_T, d_light_pos, d_amb, g_cam_table, g_light_pos,
+                                                             g_amb_ratio, d_verts);
+  HARP_LAUNCH_CHECK();
+  return HARP_OK;
+}

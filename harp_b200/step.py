@@ -183,24 +183,26 @@ class HarpFitter:
         verts = self._buf("verts", (B, hc.V, 3), zero=False)
         normals = self._buf("normals", (B, hc.V, 3), zero=False)
         check(L.harp_mesh_build_fwd(hc.h, B, ptr(verts0), ptr(disps), ptr(verts), ptr(normals), st))
-        # ---- per-frame camera / light glue (tiny tensors; torch autograd carries their chain)
-        cam_b = P["cam"].index_select(0, fid).requires_grad_(True)
-        light_l = A["light_positions"][0].detach().clone().requires_grad_(True)  # share_light_position (453-454)
-        centroid = verts.mean(1).requires_grad_(True)
-        amb_leaf = A["amb_ratio"].detach().clone().requires_grad_(True)
-        with torch.enable_grad():
-            cT = camera.cam_to_T(cam_b, focal, S)
-            light_b = light_l[None].expand(B, 3)
-            lR, lT = camera.light_camera(light_b, centroid)
-            amb = torch.sigmoid(amb_leaf)
+        # ---- gradient accumulators: one arena, one fill
+        NJ3 = NJ * 3
+        sizes = dict(d_verts=B * hc.V * 3, d_normals=B * hc.V * 3, d_joints=B * NJ3, d_cT=B * 3, d_lR=B * 9, d_lT=B * 3,
+                     d_lpos=B * 3, d_amb=4)
+        arena = self._buf("zero_arena", (sum(sizes.values()),))
+        z, o = {}, 0
+        for k, n in sizes.items():
+            z[k] = arena[o:o + n]
+            o += n
+        d_verts, d_normals = z["d_verts"].view(B, hc.V, 3), z["d_normals"].view(B, hc.V, 3)
+        d_joints, d_cT = z["d_joints"].view(B, NJ, 3), z["d_cT"].view(B, 3)
+        d_lR, d_lT, d_lpos, d_amb = z["d_lR"].view(B, 3, 3), z["d_lT"].view(B, 3), z["d_lpos"].view(B, 3), z["d_amb"][:1]
+        # ---- per-frame camera / light glue: one launch (harp_frame_glue_fwd) instead of ~30 ATen ops
         cR = camera.flip_xy_R(B, dev)
-        cTc, lRc, lTc, light_bc = cT.detach().contiguous(), lR.detach().contiguous(), lT.detach().contiguous(), light_b.detach().contiguous()
-        # ---- gradient accumulators
-        d_verts = self._buf("d_verts", (B, hc.V, 3))
-        d_normals = self._buf("d_normals", (B, hc.V, 3))
-        d_joints = self._buf("d_joints", (B, NJ, 3))
-        d_cT = self._buf("d_cT", (B, 3))
-        d_lR, d_lT, d_lpos, d_amb = self._buf("d_lR", (B, 3, 3)), self._buf("d_lT", (B, 3)), self._buf("d_lpos", (B, 3)), self._buf("d_amb", (1,))
+        cTc, light_bc, lRc, lTc, centroid = (self._buf(n, (B, k), zero=False) for n, k in
+                                             (("cTc", 3), ("light_bc", 3), ("lRc", 9), ("lTc", 3), ("centroid", 3)))
+        ambc = self._buf("ambc", (1,), zero=False)
+        light_shared = A["light_positions"][0]  # share_light_position (optimize_sequence.py:453-454)
+        check(L.harp_frame_glue_fwd(hc.h, B, S, focal, ptr(P["cam"]), ptr(fid), ptr(light_shared), ptr(A["amb_ratio"]), ptr(verts),
+                                    ptr(cTc), ptr(light_bc), ptr(lRc), ptr(lTc), ptr(ambc), ptr(centroid), st))
         W = LOSS_WEIGHTS
         # ---- both renders (silhouette 469-471 and shadowed colour 474-488 run in every stage; their losses are gated by
         #      COARSE_OPT / APP_OPT, 517-519 and 541-543) in one fused pixel pass
@@ -208,7 +210,6 @@ class HarpFitter:
         rgb = self._buf("rgb", (B, S, S, 3), zero=False)
         tex, nm = A["texture"], A["normal_map"]
         H, Wd = tex.shape[-3], tex.shape[-2]
-        ambc = amb.detach().contiguous()
         gs = HarpShadeGrads(d_verts=ptr(d_verts), d_normals=ptr(d_normals), d_cam_R=None, d_cam_T=ptr(d_cT), d_light_R=ptr(d_lR),
                             d_light_T=ptr(d_lT), d_light_pos=ptr(d_lpos), d_amb=ptr(d_amb),
                             d_texture=ptr(self.app.g["texture"]), d_normal_map=ptr(self.app.g["normal_map"]))
@@ -233,10 +234,10 @@ class HarpFitter:
                                      ptr(self.coarse.g["verts_disps"].view(-1)), st))
         # ---- backward through the small per-frame chain, then geometry
         if coarse_on or app_on:
-            g_cam, g_light, g_centroid, g_ambr = torch.autograd.grad(
-                [cT, lR, lT, light_b, amb], [cam_b, light_l, centroid, amb_leaf],
-                grad_outputs=[d_cT, d_lR, d_lT, d_lpos, d_amb.view(amb.shape)], allow_unused=True)
-            d_verts += (g_centroid / hc.V)[:, None, :]
+            check(L.harp_frame_glue_bwd(hc.h, B, S, focal, ptr(P["cam"]), ptr(fid), ptr(light_shared), ptr(A["amb_ratio"]),
+                                        ptr(centroid), ptr(d_cT), ptr(d_lR), ptr(d_lT), ptr(d_lpos), ptr(d_amb),
+                                        ptr(self.coarse.g["cam"]), ptr(self.app.g["light_positions"]), ptr(self.app.g["amb_ratio"]),
+                                        ptr(d_verts), st))
             d_verts0 = self._buf("d_verts0", (B, hc.V0, 3), zero=False)
             check(L.harp_mesh_build_bwd(hc.h, B, ptr(verts0), ptr(disps), ptr(d_verts), ptr(d_normals), ptr(d_verts0),
                                         ptr(self.coarse.g["verts_disps"].view(-1)), st))
@@ -249,10 +250,7 @@ class HarpFitter:
             if self.opt_arm_pose:
                 self.coarse.g["rot"].index_add_(0, fid, d_pose48[:, :3])
                 self.coarse.g["wrist_pose"].index_add_(0, fid, d_pose48[:, 63:66])
-            self.coarse.g["cam"].index_add_(0, fid, g_cam)
             self.coarse.g["shape"] += d_betas.sum(0)
-            self.app.g["light_positions"][0] += g_light
-            self.app.g["amb_ratio"] += g_ambr.view(1)
             self.last = dict(d_rot=d_pose48[:, :3], d_trans=d_trans, alpha=alpha, rgb=rgb, verts=verts, joints=joints,
                              d_wrist=d_pose48[:, 63:66] if self.arm else None)
         # ---- data-parallel exchange: ONE allreduce of the shared-parameter gradients

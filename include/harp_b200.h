@@ -224,6 +224,23 @@ typedef struct {
 
 HARP_API int harp_render_fused(harp_ctx*, int B, int S, float focal, const harp_render_args* args, void* stream);
 
+/* ---- per-frame camera / light glue of the fused step -----------------------------------------------------------------------
+ * Forward: cam_T[b] = (-tx, -ty, 2 f / (S s + 1e-9)) from the weak-perspective row cam_table[fid[b]] = (s, tx, ty)
+ * (utils/visualize.py:266-270; fid NULL = identity); centroid[b] = mean_v verts[b] (renderer_helper.py:455 hand_verts.mean(1));
+ * the shadow pass's light camera on the radius-1.5 sphere about the centroid looking at it, light_R (B,3,3) / light_T (B,3)
+ * (process_info_for_shadow, renderer_helper.py:454-468, with PyTorch3D's look_at_rotation); light_pos_b (B,3) = the shared
+ * light position repeated (optimize_sequence.py:453-454); amb (1) = sigmoid(amb_ratio) (renderer_helper.py:420-433).
+ * Backward: given d_cam_T, d_light_R, d_light_T, d_light_pos (B,..) and d_amb (1) as harp_render_fused accumulates them,
+ * ADDS the gradients to g_cam_table rows fid[b], g_light_pos (3), g_amb_ratio (1) and the centroid's share to d_verts (B,V,3).
+ * Replaces the ~60 ATen launches of these tiny chains and their autograd graph with two launches. */
+HARP_API int harp_frame_glue_fwd(harp_ctx*, int B, int S, float focal, const float* cam_table, const int64_t* fid,
+                        const float* light_pos, const float* amb_ratio, const float* verts, float* cam_T, float* light_pos_b,
+                        float* light_R, float* light_T, float* amb, float* centroid, void* stream);
+HARP_API int harp_frame_glue_bwd(harp_ctx*, int B, int S, float focal, const float* cam_table, const int64_t* fid,
+                        const float* light_pos, const float* amb_ratio, const float* centroid, const float* d_cam_T,
+                        const float* d_light_R, const float* d_light_T, const float* d_light_pos, const float* d_amb,
+                        float* g_cam_table, float* g_light_pos, float* g_amb_ratio, float* d_verts, void* stream);
+
 /* ---- texture regularisers: albedo_reg / normal_reg (loss/texture_reg.py:5-66) ----------------------------------------
  * offsets (H,W,2) int32 = the reference's CPU-RNG neighbour offsets, passed in.  kind 0: albedo_reg; 1: normal_reg
  * (adds 0.2*close_to_z with the reference's dim=2 norm).  loss accumulated (unweighted); d_map accumulated. */
