@@ -97,6 +97,9 @@ struct harp_ctx {
   int ovf_cap = 0;
   unsigned long long* counters = nullptr;  // [0] top-K pixels that could not be handled exactly, [1] bin overflow
   struct harp_prof* prof = nullptr;        // host-side event lists (harp_ctx_profile)
+  // host-side handles for the fused render's light branch (forked from / joined to the caller's stream; capturable)
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 // ---------------------------------------------------------------------------------------------- small vector math

@@ -255,6 +255,9 @@ extern "C" void harp_ctx_destroy(harp_ctx* c) {
                   c->J_template, c->J_shapedirs, c->tips, c->counters, c->d_tex4, c->tex4, c->weightsT, c->pose_mean, c->parents,
                   c->joint_out_src};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->side_stream) cudaStreamDestroy(c->side_stream);
   if (c->prof) {
     for (auto& v : c->prof->ev) for (cudaEvent_t e : v) cudaEventDestroy(e);
     delete c->prof;

@@ -309,13 +309,24 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
   const size_t npx = (size_t)B * S * S, nv4 = (size_t)B * c->V * 4 * sizeof(float), ntex = (size_t)r->texH * r->texW;
   double blur_d = 9.210240366975849 * (double)r->sigma;  // ln(1/1e-4 - 1) sigma (renderer_helper.py:46)
   float blur = (float)blur_d, radius = (float)sqrt(blur_d);
+  if (r->self_shadow) {
+    // light branch (projection, bins, nearest-depth raster of the light view) on the ctx's side stream, concurrent with
+    // the camera branch below; joined before the deferred shading.  Event fork/join is capturable into a CUDA graph.
+    if (!c->side_stream) {
+      HARP_CHECK_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+      HARP_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+      HARP_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
+    cudaStream_t ss = c->side_stream;
+    HARP_CHECK_CUDA(cudaEventRecord(c->ev_fork, st));
+    HARP_CHECK_CUDA(cudaStreamWaitEvent(ss, c->ev_fork, 0));
+    if ((rc = harp_project(c, B, S, focal, r->verts, r->light_R, r->light_T, c->ndc_light, ss)) != HARP_OK) return rc;
+    if ((rc = harp_build_bins(c, 1, B, S, 0.f, c->ndc_light, ss)) != HARP_OK) return rc;
+    if ((rc = harp_light_depth(c, B, S, ss)) != HARP_OK) return rc;
+    HARP_CHECK_CUDA(cudaEventRecord(c->ev_join, ss));
+  }
   if ((rc = harp_project(c, B, S, focal, r->verts, r->cam_R, r->cam_T, c->ndc_cam, st)) != HARP_OK) return rc;
   if ((rc = harp_build_bins(c, 0, B, S, radius, c->ndc_cam, st)) != HARP_OK) return rc;
-  if (r->self_shadow) {
-    if ((rc = harp_project(c, B, S, focal, r->verts, r->light_R, r->light_T, c->ndc_light, st)) != HARP_OK) return rc;
-    if ((rc = harp_build_bins(c, 1, B, S, 0.f, c->ndc_light, st)) != HARP_OK) return rc;
-    if ((rc = harp_light_depth(c, B, S, st)) != HARP_OK) return rc;
-  }
   if (sil_bwd || photo_bwd) HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_cam, 0, nv4, st));
   if ((rc = harp_tex_prepare(c, r->texture, r->normal_map, r->texH, r->texW, st)) != HARP_OK) return rc;
   if (photo_bwd) {
@@ -347,6 +358,7 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
   HARP_LAUNCH_CHECK();
   if ((rc = harp_sil_topk(c, sil_bwd ? 2 : 0, S, v.K, r->sigma, blur, radius, r->alpha, r->y_sil, v.sil_gscale, v.sil_inv_n,
                           r->loss_sil, st)) != HARP_OK) return rc;
+  if (r->self_shadow) HARP_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
   ShadeArgs a{};
   a.B = B; a.S = S; a.self_shadow = r->self_shadow; a.texH = r->texH; a.texW = r->texW; a.focal = focal;
   a.inv_n = v.photo_inv_n; a.gscale = r->w_photo * a.inv_n;

@@ -51,9 +51,9 @@ __global__ void __launch_bounds__(TPB) project_bwd_kernel(int B, int V, const fl
       float gZ = g.z - (g.x * k * X + g.y * k * Y) / (Z * Z);
       if (d_verts) {
         float* dv = d_verts + idx * 3;
-        dv[0] += r[0] * gX + r[1] * gY + r[2] * gZ;
-        dv[1] += r[3] * gX + r[4] * gY + r[5] * gZ;
-        dv[2] += r[6] * gX + r[7] * gY + r[8] * gZ;
+        atomicAdd(dv + 0, r[0] * gX + r[1] * gY + r[2] * gZ);
+        atomicAdd(dv + 1, r[3] * gX + r[4] * gY + r[5] * gZ);
+        atomicAdd(dv + 2, r[6] * gX + r[7] * gY + r[8] * gZ);
       }
       acc[0] = p.x * gX; acc[1] = p.x * gY; acc[2] = p.x * gZ;
       acc[3] = p.y * gX; acc[4] = p.y * gY; acc[5] = p.y * gZ;
@@ -426,8 +426,8 @@ __global__ void __launch_bounds__(TPB) fold4_kernel(size_t n, const float4* __re
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 v = src[i];
-  if (v.x != 0.f || v.y != 0.f || v.z != 0.f) {
-    dst[i * 3] += v.x; dst[i * 3 + 1] += v.y; dst[i * 3 + 2] += v.z;
+  if (v.x != 0.f || v.y != 0.f || v.z != 0.f) {  // atomics: other branches of the step may accumulate into dst concurrently
+    atomicAdd(dst + i * 3, v.x); atomicAdd(dst + i * 3 + 1, v.y); atomicAdd(dst + i * 3 + 2, v.z);
   }
 }
 

@@ -135,6 +135,11 @@ class HarpFitter:
             t.zero_()
         return t
 
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.hc.device)
+        return self._side
+
     # -- one minibatch ----------------------------------------------------------------------------------------------------
     def step(self, fid, off_albedo, off_normal, stage="both", update=True, batch=None, frame_range=None, exchange=True,
              batch_u8=None):
@@ -219,19 +224,25 @@ class HarpFitter:
                             y_mask=ptr(fr["y_sil_eroded"]), w_sil=W["silhouette"] * fscale if coarse_on else 0.0,
                             w_photo=W["photo"] * fscale if app_on else 0.0, alpha=ptr(alpha), rgb=ptr(rgb),
                             loss_sil=ptr(self.losses[_SLOT["silhouette"]:]), loss_photo=ptr(self.losses[_SLOT["photo"]:]), grads=gs)
+        # ---- regulariser branch on a side stream, concurrent with the render: texture regularisers (552-553) and the mesh
+        #      regularisers + keypoint anchor (521-539) depend only on the mesh / textures and accumulate with atomics
+        main, side = torch.cuda.current_stream(), self._side_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ss = stream()
+            if app_on:
+                check(L.harp_texture_reg(hc.h, 0, ptr(tex), H, Wd, ptr(off_albedo), ptr(self.uv_mask), W["albedo"] * fscale,
+                                         ptr(self.losses[_SLOT["albedo"]:]), ptr(self.app.g["texture"]), ss))
+                check(L.harp_texture_reg(hc.h, 1, ptr(nm), H, Wd, ptr(off_normal), ptr(self.uv_mask), W["normal_reg"] * fscale,
+                                         ptr(self.losses[_SLOT["normal_reg"]:]), ptr(self.app.g["normal_map"]), ss))
+            if coarse_on:
+                w5 = (C.c_float * 5)(W["laplacian"] * fscale, W["normal"] * fscale, W["arap"] * fscale, W["kps_anchor"] * fscale,
+                                     W["vert_disp_reg"] * fscale)
+                check(L.harp_mesh_losses(hc.h, B, ptr(verts), ptr(self.ref_verts), ptr(joints), ptr(fr["init_joints"]), ptr(disps), w5,
+                                         ptr(self.losses[_SLOT["laplacian"]:]), ptr(d_verts), ptr(d_joints),
+                                         ptr(self.coarse.g["verts_disps"].view(-1)), ss))
         check(L.harp_render_fused(hc.h, B, S, focal, C.byref(ra), st))
-        if app_on:
-            check(L.harp_texture_reg(hc.h, 0, ptr(tex), H, Wd, ptr(off_albedo), ptr(self.uv_mask), W["albedo"] * fscale,
-                                     ptr(self.losses[_SLOT["albedo"]:]), ptr(self.app.g["texture"]), st))
-            check(L.harp_texture_reg(hc.h, 1, ptr(nm), H, Wd, ptr(off_normal), ptr(self.uv_mask), W["normal_reg"] * fscale,
-                                     ptr(self.losses[_SLOT["normal_reg"]:]), ptr(self.app.g["normal_map"]), st))
-        # ---- mesh regularisers + keypoint anchor (521-539)
-        if coarse_on:
-            w5 = (C.c_float * 5)(W["laplacian"] * fscale, W["normal"] * fscale, W["arap"] * fscale, W["kps_anchor"] * fscale,
-                                 W["vert_disp_reg"] * fscale)
-            check(L.harp_mesh_losses(hc.h, B, ptr(verts), ptr(self.ref_verts), ptr(joints), ptr(fr["init_joints"]), ptr(disps), w5,
-                                     ptr(self.losses[_SLOT["laplacian"]:]), ptr(d_verts), ptr(d_joints),
-                                     ptr(self.coarse.g["verts_disps"].view(-1)), st))
+        main.wait_stream(side)
         # ---- backward through the small per-frame chain, then geometry
         if coarse_on or app_on:
             check(L.harp_frame_glue_bwd(hc.h, B, S, focal, ptr(P["cam"]), ptr(fid), ptr(light_shared), ptr(A["amb_ratio"]),
