@@ -256,12 +256,13 @@ __global__ void __launch_bounds__(128, HARP_SHADE_MIN_CTAS) shade_deferred_kerne
   const int S = a.S;
   int b = blockIdx.y;
   int n = hit_count[b];
-  int n_pad = (n + 31) & ~31;  // keep warps whole for the warp reductions
   const float* ndc = a.ndc_cam + (size_t)b * c.V * 3;
   const int2* list = hit_list + (size_t)b * S * S;
-  float loss_acc = 0.f, fr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_pad; idx += gridDim.x * blockDim.x) {
-    if (idx >= n) continue;
+  // per-thread partial sums of the frame scalars live in shared memory (column per thread: conflict-free), not registers
+  __shared__ float s_fr[9][128];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) s_fr[k][threadIdx.x] = 0.f;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
     int2 rec = list[idx];
     int rc = rec.x;
     int row = rc / S, col = rc % S;
@@ -278,13 +279,18 @@ __global__ void __launch_bounds__(128, HARP_SHADE_MIN_CTAS) shade_deferred_kerne
     ShadeOut o;
     shade_pixel<MODE>(c, a, b, pix, px, py, h, o);
     if (MODE != 1) st3(a.rgb + pix * 3, o.rgb);
-    loss_acc += o.loss_abs;
+    if (MODE != 0) {
+      s_fr[8][threadIdx.x] += o.loss_abs;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) fr[k] += o.frame[k];
+      for (int k = 0; k < 8; ++k) s_fr[k][threadIdx.x] += o.frame[k];
+    }
   }
   if (MODE == 0) return;
+  float fr[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) fr[k] = s_fr[k][threadIdx.x];
   if (MODE == 2) {
-    float s = warp_sum(loss_acc);
+    float s = warp_sum(s_fr[8][threadIdx.x]);
     if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(a.loss, s * a.inv_n);
   }
   shade_flush_frame_scalars(a, b, fr);

@@ -36,14 +36,16 @@ __device__ __forceinline__ void bary_backward(const float* ndc, int v0, int v1, 
   float gw0 = 0.f, gw1 = 0.f, gw2 = 0.f;
   if (den > HARP_K_EPS) {
     float dotgb = gb[0] * h.b0 + gb[1] * h.b1 + gb[2] * h.b2;
-    float gt0 = (gb[0] - dotgb) / den, gt1 = (gb[1] - dotgb) / den, gt2 = (gb[2] - dotgb) / den;
+    float iden = __fdividef(1.f, den);
+    float gt0 = (gb[0] - dotgb) * iden, gt1 = (gb[1] - dotgb) * iden, gt2 = (gb[2] - dotgb) * iden;
     gw0 = gt0 * z1 * z2; gz1 += gt0 * h.w0 * z2; gz2 += gt0 * h.w0 * z1;
     gw1 = gt1 * z0 * z2; gz0 += gt1 * h.w1 * z2; gz2 += gt1 * z0 * h.w1;
     gw2 = gt2 * z0 * z1; gz0 += gt2 * z1 * h.w2; gz1 += gt2 * z0 * h.w2;
   }
   float area = (x2 - x0) * (y1 - y0) - (y2 - y0) * (x1 - x0) + HARP_K_EPS;
-  float ge0 = gw0 / area, ge1 = gw1 / area, ge2 = gw2 / area;
-  float gA = -(gw0 * h.w0 + gw1 * h.w1 + gw2 * h.w2) / area;
+  float iarea = __fdividef(1.f, area);
+  float ge0 = gw0 * iarea, ge1 = gw1 * iarea, ge2 = gw2 * iarea;
+  float gA = -(gw0 * h.w0 + gw1 * h.w1 + gw2 * h.w2) * iarea;
   // E(p,a,b) = (px-ax)(by-ay) - (py-ay)(bx-ax):  dE/da = (py-by, bx-px),  dE/db = (ay-py, px-ax)
   // e0 = E(p,v1,v2), e1 = E(p,v2,v0), e2 = E(p,v0,v1);  A = E(v2,v0,v1) + eps
   float gx0 = ge1 * (y2 - py) + ge2 * (py - y1) + gA * (y2 - y1);
@@ -90,10 +92,11 @@ __device__ __forceinline__ f3 normalize_bwd_packed(float4 t, f3 gy) {
   return t.w > 0.f ? t.w * (gy - dot(n, gy) * n) : (-t.w) * gy;
 }
 __device__ __forceinline__ f3 normalize_bwd_eps(f3 x, f3 gy, float eps) {
-  float l = sqrtf(dot(x, x));
-  if (l > eps) {
-    f3 y = (1.f / l) * x;
-    return (1.f / l) * (gy - dot(y, gy) * y);
+  float l2 = dot(x, x);
+  if (l2 > eps * eps) {
+    float il = rsqrtf(l2);
+    f3 y = il * x;
+    return il * (gy - dot(y, gy) * y);
   }
   return (1.f / eps) * gy;
 }
@@ -130,8 +133,7 @@ __device__ __forceinline__ void shade_pixel(const harp_ctx& c, const ShadeArgs& 
   f3 rgb = mk3(1.f, 1.f, 1.f);  // background (renderer_helper.py:430)
   // forward state kept for the backward half
   int v0 = 0, v1 = 0, v2 = 0;
-  f3 P0, P1, P2, N0, N1, N2, P, N, tex, m, npre, n1, dvec, dh, n2;
-  float uvx[3], uvy[3];
+  f3 P, N, tex, m, npre, n1, dvec, dh, n2;  // per-vertex attributes are re-read in the backward half (L1 hits) to keep registers free
   Taps tp;
   float amb = a.amb[0], cosang = 0.f, vis = 1.f, sh = 0.f, zL = 0.f, s_sign = 1.f, aa = 0.f;
   f3 uvec, vvec;
@@ -146,14 +148,11 @@ __device__ __forceinline__ void shade_pixel(const harp_ctx& c, const ShadeArgs& 
     v0 = fv[0]; v1 = fv[1]; v2 = fv[2];
     const float* vb = a.verts + (size_t)b * c.V * 3;
     const float* nb = a.normals + (size_t)b * c.V * 3;
-    P0 = ld3(vb + (size_t)v0 * 3); P1 = ld3(vb + (size_t)v1 * 3); P2 = ld3(vb + (size_t)v2 * 3);
-    N0 = ld3(nb + (size_t)v0 * 3); N1 = ld3(nb + (size_t)v1 * 3); N2 = ld3(nb + (size_t)v2 * 3);
+    P = h.b0 * ld3(vb + (size_t)v0 * 3) + h.b1 * ld3(vb + (size_t)v1 * 3) + h.b2 * ld3(vb + (size_t)v2 * 3);
+    N = h.b0 * ld3(nb + (size_t)v0 * 3) + h.b1 * ld3(nb + (size_t)v1 * 3) + h.b2 * ld3(nb + (size_t)v2 * 3);
     const float* fu = c.face_uvs + (size_t)h.fid * 6;
-    uvx[0] = fu[0]; uvy[0] = fu[1]; uvx[1] = fu[2]; uvy[1] = fu[3]; uvx[2] = fu[4]; uvy[2] = fu[5];
-    P = h.b0 * P0 + h.b1 * P1 + h.b2 * P2;
-    N = h.b0 * N0 + h.b1 * N1 + h.b2 * N2;
-    float u = h.b0 * uvx[0] + h.b1 * uvx[1] + h.b2 * uvx[2];
-    float v = h.b0 * uvy[0] + h.b1 * uvy[1] + h.b2 * uvy[2];
+    float u = h.b0 * fu[0] + h.b1 * fu[2] + h.b2 * fu[4];
+    float v = h.b0 * fu[1] + h.b1 * fu[3] + h.b2 * fu[5];
     make_taps(u, v, a.texH, a.texW, tp);
     tex = mk3(0.f, 0.f, 0.f);
     m = mk3(0.f, 0.f, 0.f);
@@ -298,9 +297,12 @@ __device__ __forceinline__ void shade_pixel(const harp_ctx& c, const ShadeArgs& 
       g_v_tex = tp.gmy * (dot(g_tex, dty) + dot(g_m, dmy));
     }
     // --- interpolation: P, N, uv = sum_i b_i attr_i ---
-    float gb[3] = {dot(P0, gP) + dot(N0, gN) + uvx[0] * g_u_tex + uvy[0] * g_v_tex,
-                   dot(P1, gP) + dot(N1, gN) + uvx[1] * g_u_tex + uvy[1] * g_v_tex,
-                   dot(P2, gP) + dot(N2, gN) + uvx[2] * g_u_tex + uvy[2] * g_v_tex};
+    const float* vb = a.verts + (size_t)b * c.V * 3;
+    const float* nb = a.normals + (size_t)b * c.V * 3;
+    const float* fu = c.face_uvs + (size_t)h.fid * 6;
+    float gb[3] = {dot(ld3(vb + (size_t)v0 * 3), gP) + dot(ld3(nb + (size_t)v0 * 3), gN) + fu[0] * g_u_tex + fu[1] * g_v_tex,
+                   dot(ld3(vb + (size_t)v1 * 3), gP) + dot(ld3(nb + (size_t)v1 * 3), gN) + fu[2] * g_u_tex + fu[3] * g_v_tex,
+                   dot(ld3(vb + (size_t)v2 * 3), gP) + dot(ld3(nb + (size_t)v2 * 3), gN) + fu[4] * g_u_tex + fu[5] * g_v_tex};
     float* dvb = a.d_verts + (size_t)b * c.V * 4;   // padded (B,V,4) accumulators, folded after the kernel
     float* dnb = a.d_normals + (size_t)b * c.V * 4;
     atomic_add4(dvb + (size_t)v0 * 4, h.b0 * gP.x, h.b0 * gP.y, h.b0 * gP.z);
