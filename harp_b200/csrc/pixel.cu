@@ -71,22 +71,25 @@ __global__ void __launch_bounds__(NT, 16) pixel_vis_kernel(harp_ctx c, VisArgs a
   int col = blockIdx.x * HARP_TILE + lx, row = blockIdx.y * HARP_TILE + ly;
   size_t pix = ((size_t)b * S + row) * S + col;
   size_t tglob = (size_t)b * tw * tw + blockIdx.y * tw + blockIdx.x;
+  // The tile's targets are requested together with its face count so that, for an empty tile (about 4 of 5 at the
+  // reference's framing), one memory latency covers everything it needs; a tile with faces drops them and re-reads at the end.
+  float ys = SIL_BWD ? __ldcs(a.y_sil + pix) : 0.f;
+  float mk = 0.f;
+  f3 y = mk3(0.f, 0.f, 0.f);
+  if (PHOTO) { mk = __ldcs(a.y_mask + pix); y = mk3(__ldcs(a.y_true + pix * 3), __ldcs(a.y_true + pix * 3 + 1), __ldcs(a.y_true + pix * 3 + 2)); }
   int n = a.bin_count[tglob];
   if (n == 0) {
-    // ---- empty tile (about 4 of 5 at the reference's framing): nothing but streaming.  All loads are issued before the
-    //      first use so that their latencies overlap.
-    float ys = SIL_BWD ? __ldcs(a.y_sil + pix) : 0.f;
-    float mk = 0.f;
-    f3 y = mk3(0.f, 0.f, 0.f);
-    if (PHOTO) { mk = __ldcs(a.y_mask + pix); y = mk3(__ldcs(a.y_true + pix * 3), __ldcs(a.y_true + pix * 3 + 1), __ldcs(a.y_true + pix * 3 + 2)); }
+    // ---- empty tile: nothing but streaming
     a.alpha[pix] = 0.f;
     st3(a.rgb + pix * 3, mk3(1.f, 1.f, 1.f));
     float s_sil = fabsf(ys), s_ph = PHOTO ? fabsf(mk - y.x * mk) + fabsf(mk - y.y * mk) + fabsf(mk - y.z * mk) : 0.f;
     if (!SIL_BWD && !PHOTO) return;
-    block_sum2(s_sil, s_ph, red);
-    if (tid == 0) {
-      if (SIL_BWD && s_sil != 0.f) atomicAdd(a.sil_loss, s_sil * a.sil_inv_n);
-      if (PHOTO && s_ph != 0.f) atomicAdd(a.photo_loss, s_ph * a.photo_inv_n);
+    if (__ballot_sync(0xffffffffu, s_sil != 0.f || s_ph != 0.f)) {  // rare: target foreground over an empty tile (per warp, no barrier)
+      s_sil = warp_sum(s_sil); s_ph = warp_sum(s_ph);
+      if ((tid & 31) == 0) {
+        if (SIL_BWD && s_sil != 0.f) atomicAdd(a.sil_loss, s_sil * a.sil_inv_n);
+        if (PHOTO && s_ph != 0.f) atomicAdd(a.photo_loss, s_ph * a.photo_inv_n);
+      }
     }
     return;
   }
@@ -315,35 +318,37 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
   const size_t npx = (size_t)B * S * S, nv4 = (size_t)B * c->V * 4 * sizeof(float), ntex = (size_t)r->texH * r->texW;
   double blur_d = 9.210240366975849 * (double)r->sigma;  // ln(1/1e-4 - 1) sigma (renderer_helper.py:46)
   float blur = (float)blur_d, radius = (float)sqrt(blur_d);
+  // Side branch on the ctx's own stream, concurrent with the camera branch (projection, bins, pixel_vis) below and joined
+  // before the deferred shading: everything only the shading needs — the light view (projection, bins, nearest-depth
+  // raster), the packed texel copies, and the zero fills of the shading's gradient accumulators (92 MB at 64 x 512^2).
+  // Event fork / join is capturable into a CUDA graph.
+  if (!c->side_stream) {
+    HARP_CHECK_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    HARP_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    HARP_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  }
+  cudaStream_t ss = c->side_stream;
+  HARP_CHECK_CUDA(cudaEventRecord(c->ev_fork, st));
+  HARP_CHECK_CUDA(cudaStreamWaitEvent(ss, c->ev_fork, 0));
   if (r->self_shadow) {
-    // light branch (projection, bins, nearest-depth raster of the light view) on the ctx's side stream, concurrent with
-    // the camera branch below; joined before the deferred shading.  Event fork/join is capturable into a CUDA graph.
-    if (!c->side_stream) {
-      HARP_CHECK_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
-      HARP_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-      HARP_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-    }
-    cudaStream_t ss = c->side_stream;
-    HARP_CHECK_CUDA(cudaEventRecord(c->ev_fork, st));
-    HARP_CHECK_CUDA(cudaStreamWaitEvent(ss, c->ev_fork, 0));
     if ((rc = harp_project(c, B, S, focal, r->verts, r->light_R, r->light_T, c->ndc_light, ss)) != HARP_OK) return rc;
     if ((rc = harp_build_bins(c, 1, B, S, 0.f, c->ndc_light, ss)) != HARP_OK) return rc;
     if ((rc = harp_light_depth(c, B, S, ss)) != HARP_OK) return rc;
-    HARP_CHECK_CUDA(cudaEventRecord(c->ev_join, ss));
   }
+  if ((rc = harp_tex_prepare(c, r->texture, r->normal_map, r->texH, r->texW, ss)) != HARP_OK) return rc;
+  if (photo_bwd) {
+    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_verts4, 0, nv4, ss));
+    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_normals4, 0, nv4, ss));
+    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_tex4, 0, 2 * ntex * 4 * sizeof(float), ss));
+    if (r->self_shadow) {
+      HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_light, 0, nv4, ss));
+      HARP_CHECK_CUDA(cudaMemsetAsync(c->d_light_zbuf, 0, npx * sizeof(float), ss));
+    }
+  }
+  HARP_CHECK_CUDA(cudaEventRecord(c->ev_join, ss));
   if ((rc = harp_project(c, B, S, focal, r->verts, r->cam_R, r->cam_T, c->ndc_cam, st)) != HARP_OK) return rc;
   if ((rc = harp_build_bins(c, 0, B, S, radius, c->ndc_cam, st)) != HARP_OK) return rc;
   if (sil_bwd || photo_bwd) HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_cam, 0, nv4, st));
-  if ((rc = harp_tex_prepare(c, r->texture, r->normal_map, r->texH, r->texW, st)) != HARP_OK) return rc;
-  if (photo_bwd) {
-    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_verts4, 0, nv4, st));
-    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_normals4, 0, nv4, st));
-    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_tex4, 0, 2 * ntex * 4 * sizeof(float), st));
-    if (r->self_shadow) {
-      HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_light, 0, nv4, st));
-      HARP_CHECK_CUDA(cudaMemsetAsync(c->d_light_zbuf, 0, npx * sizeof(float), st));
-    }
-  }
   HARP_CHECK_CUDA(cudaMemsetAsync(c->hit_count, 0, (size_t)B * sizeof(int32_t), st));
   HARP_CHECK_CUDA(cudaMemsetAsync(c->ovf_count, 0, sizeof(int32_t), st));
   VisArgs v{};
@@ -364,7 +369,7 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
   HARP_LAUNCH_CHECK();
   if ((rc = harp_sil_topk(c, sil_bwd ? 2 : 0, S, v.K, r->sigma, blur, radius, r->alpha, r->y_sil, v.sil_gscale, v.sil_inv_n,
                           r->loss_sil, st)) != HARP_OK) return rc;
-  if (r->self_shadow) HARP_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
+  HARP_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
   ShadeArgs a{};
   a.B = B; a.S = S; a.self_shadow = r->self_shadow; a.texH = r->texH; a.texW = r->texW; a.focal = focal;
   a.inv_n = v.photo_inv_n; a.gscale = r->w_photo * a.inv_n;
