@@ -122,7 +122,9 @@ __global__ void __launch_bounds__(NT, 16) pixel_vis_kernel(harp_ctx c, VisArgs a
       const FaceTile& f = faces[i];
       bool inside;
       float e0, e1, e2;
-      int cls = classify_fast<true>(f, px, py, far, sat, inside, e0, e1, e2);
+      bool inb = in_face_bbox(f, px, py);
+      if (!__any_sync(0xffffffffu, inb)) continue;  // the face's bbox misses this warp's 8x4 half of the tile
+      int cls = classify_fast<true>(f, px, py, far, sat, inb, inside, e0, e1, e2);
       if (cls == PAIR_REJECT) continue;
       float q;
       if (cls == PAIR_EXACT) {  // a vertex behind the camera: decide with the exact operation sequence
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(NT, 16) pixel_vis_kernel(harp_ctx c, VisArgs a
     for (int i = 0; i < m; ++i) {
       bool inside;
       float e0, e1, e2;
-      int cls = classify_fast<true>(faces[i], px, py, far, sat, inside, e0, e1, e2);
+      int cls = classify_fast<true>(faces[i], px, py, far, sat, in_face_bbox(faces[i], px, py), inside, e0, e1, e2);
       if (cls == PAIR_REJECT || cls == PAIR_SATURATED) continue;
       PairEval e;
       eval_pair_full<true, true>(faces[i], px, py, blur, e);

@@ -245,10 +245,13 @@ __device__ __forceinline__ void stage_face(const harp_ctx& c, const float* ndc, 
 // the fast inverse depth.  With NEED_DIST = false (visibility only) inside pairs report PAIR_SATURATED, all others REJECT.
 enum { PAIR_EXACT = 3 };
 
+__device__ __forceinline__ bool in_face_bbox(const FaceTile& f, float px, float py) {
+  return !((px > f.xmax) | (px < f.xmin) | (py > f.ymax) | (py < f.ymin));  // bitwise: no short-circuit branches
+}
+
 template <bool NEED_DIST>
-__device__ __forceinline__ int classify_fast(const FaceTile& f, float px, float py, float far, float sat, bool& inside,
+__device__ __forceinline__ int classify_fast(const FaceTile& f, float px, float py, float far, float sat, bool inb, bool& inside,
                                              float& e0, float& e1, float& e2) {
-  bool inb = !((px > f.xmax) | (px < f.xmin) | (py > f.ymax) | (py < f.ymin));  // bitwise: no short-circuit branches
   e0 = fsub(fmul(fsub(px, f.x1), f.d12y), fmul(fsub(py, f.y1), f.d12x));
   e1 = fsub(fmul(fsub(px, f.x2), f.d20y), fmul(fsub(py, f.y2), f.d20x));
   e2 = fsub(fmul(fsub(px, f.x0), f.d01y), fmul(fsub(py, f.y0), f.d01x));

@@ -48,7 +48,9 @@ __device__ __forceinline__ void nearest_face(const harp_ctx& c, const float* ndc
       const FaceTile& f = faces[i];
       bool inside;
       float e0, e1, e2, q;
-      int cls = classify_fast<false>(f, px, py, 0.f, 0.f, inside, e0, e1, e2);
+      bool inb = in_face_bbox(f, px, py);
+      if (!__any_sync(0xffffffffu, inb)) continue;  // the face's bbox misses this warp's 8x4 half of the tile
+      int cls = classify_fast<false>(f, px, py, 0.f, 0.f, inb, inside, e0, e1, e2);
       if (cls == PAIR_REJECT) continue;
       if (cls == PAIR_EXACT) {
         PairEval e;
@@ -99,29 +101,50 @@ __global__ void __launch_bounds__(NT) light_depth_kernel(harp_ctx c, int S, cons
   face[pix] = h.fid;
 }
 
-// backward of the light-view depth buffer: zbuf = sum_i b_i z_i at the stored face
-__global__ void __launch_bounds__(256) light_depth_bwd_kernel(harp_ctx c, int B, int S, const float* __restrict__ ndc_all,
-                                                              const int32_t* __restrict__ face, const float* __restrict__ d_zbuf,
-                                                              float* __restrict__ d_ndc_all) {
-  size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= (size_t)B * S * S) return;
-  float g = d_zbuf[pix];
-  int fid = face[pix];
-  if (g == 0.f || fid < 0) return;
-  int b = (int)(pix / ((size_t)S * S));
-  int rem = (int)(pix % ((size_t)S * S));
-  int row = rem / S, col = rem % S;
-  const float* ndc = ndc_all + (size_t)b * c.V * 3;
-  FaceRec f;
-  load_face(c, ndc, fid, 0.f, f);
-  float px = pix_to_ndc(col, S), py = pix_to_ndc(row, S);
-  PairEval e;
-  eval_pair<false, false>(f, px, py, 0.f, 0.f, e);
-  if (!e.pass) return;
-  Hit h; h.fid = fid; h.pz = e.pz; h.b0 = e.b0; h.b1 = e.b1; h.b2 = e.b2; h.w0 = e.w0; h.w1 = e.w1; h.w2 = e.w2;
-  float gb[3] = {g * f.z0, g * f.z1, g * f.z2};
-  float gz[3] = {g * e.b0, g * e.b1, g * e.b2};
-  bary_backward(ndc, f.v0, f.v1, f.v2, px, py, h, gb, gz, d_ndc_all + (size_t)b * c.V * 4);
+// backward of the light-view depth buffer: zbuf = sum_i b_i z_i at the stored face.
+// The gradient image is sparse (only light pixels some PCF tap touched): each CTA scans 1024 pixels with 16-byte loads,
+// compacts the active ones into shared memory and then processes them with full warps.
+constexpr int LDB_THREADS = 256, LDB_PIX = 4 * LDB_THREADS;
+
+__global__ void __launch_bounds__(LDB_THREADS) light_depth_bwd_kernel(harp_ctx c, int B, int S, const float* __restrict__ ndc_all,
+                                                                      const int32_t* __restrict__ face,
+                                                                      const float* __restrict__ d_zbuf,
+                                                                      float* __restrict__ d_ndc_all) {
+  __shared__ unsigned short s_idx[LDB_PIX];
+  __shared__ int s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  const size_t total = (size_t)B * S * S, base = (size_t)blockIdx.x * LDB_PIX;  // S*S is a multiple of 4: whole float4s
+  size_t p0 = base + (size_t)threadIdx.x * 4;
+  if (p0 < total) {
+    float4 g4 = *reinterpret_cast<const float4*>(d_zbuf + p0);
+    float gs[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (gs[k] != 0.f) s_idx[atomicAdd(&s_n, 1)] = (unsigned short)(threadIdx.x * 4 + k);
+  }
+  __syncthreads();
+  const int n = s_n;
+  for (int s = threadIdx.x; s < n; s += LDB_THREADS) {
+    size_t pix = base + s_idx[s];
+    int fid = face[pix];
+    if (fid < 0) continue;
+    float g = d_zbuf[pix];
+    int b = (int)(pix / ((size_t)S * S));
+    int rem = (int)(pix % ((size_t)S * S));
+    int row = rem / S, col = rem % S;
+    const float* ndc = ndc_all + (size_t)b * c.V * 3;
+    FaceRec f;
+    load_face(c, ndc, fid, 0.f, f);
+    float px = pix_to_ndc(col, S), py = pix_to_ndc(row, S);
+    PairEval e;
+    eval_pair<false, false>(f, px, py, 0.f, 0.f, e);
+    if (!e.pass) continue;
+    Hit h; h.fid = fid; h.pz = e.pz; h.b0 = e.b0; h.b1 = e.b1; h.b2 = e.b2; h.w0 = e.w0; h.w1 = e.w1; h.w2 = e.w2;
+    float gb[3] = {g * f.z0, g * f.z1, g * f.z2};
+    float gz[3] = {g * e.b0, g * e.b1, g * e.b2};
+    bary_backward(ndc, f.v0, f.v1, f.v2, px, py, h, gb, gz, d_ndc_all + (size_t)b * c.V * 4);
+  }
 }
 
 // MODE 0 forward; 1 backward with upstream g_rgb; 2 fused photometric L1 on the eroded mask
@@ -277,7 +300,7 @@ int harp_light_depth(harp_ctx* c, int B, int S, cudaStream_t st) {
 
 int harp_light_depth_bwd(harp_ctx* c, int B, int S, cudaStream_t st) {
   size_t npx = (size_t)B * S * S;
-  light_depth_bwd_kernel<<<(int)((npx + 255) / 256), 256, 0, st>>>(*c, B, S, c->ndc_light, c->light_face, c->d_light_zbuf,
+  light_depth_bwd_kernel<<<(int)((npx + LDB_PIX - 1) / LDB_PIX), LDB_THREADS, 0, st>>>(*c, B, S, c->ndc_light, c->light_face, c->d_light_zbuf,
                                                                    c->d_ndc_light);
   HARP_LAUNCH_CHECK();
   return HARP_OK;
@@ -351,7 +374,7 @@ extern "C" int harp_shade(harp_ctx* c, int mode, int B, int S, float focal, int 
     if (grads->d_texture && (rc = harp_fold4(ntex, c->d_tex4, grads->d_texture, st)) != HARP_OK) return rc;
     if (grads->d_normal_map && (rc = harp_fold4(ntex, c->d_tex4 + ntex * 4, grads->d_normal_map, st)) != HARP_OK) return rc;
     if (self_shadow) {
-      light_depth_bwd_kernel<<<(int)((npx + 255) / 256), 256, 0, st>>>(*c, B, S, c->ndc_light, c->light_face, c->d_light_zbuf,
+      light_depth_bwd_kernel<<<(int)((npx + LDB_PIX - 1) / LDB_PIX), LDB_THREADS, 0, st>>>(*c, B, S, c->ndc_light, c->light_face, c->d_light_zbuf,
                                                                        c->d_ndc_light);
       HARP_LAUNCH_CHECK();
       if ((rc = harp_project_bwd(c, B, S, focal, verts, light_R, light_T, c->d_ndc_light, grads->d_verts, grads->d_light_R,
