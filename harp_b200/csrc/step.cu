@@ -114,6 +114,21 @@ __global__ void __launch_bounds__(TPB) ingest_u8_kernel(int B, int S, const uint
   y_er[pix] = (float)((double)mn / 255.0);
 }
 
+// torch.nn.MSELoss()(scale * x, target) and its gradient w.r.t. x, in one pass (metro_modifications/hand_utils.py:64,74,93)
+__global__ void __launch_bounds__(TPB) mse_kernel(int64_t n, const float* __restrict__ x, const float* __restrict__ target,
+                                                   float scale, float* __restrict__ loss, float* __restrict__ d_x) {
+  __shared__ float red[32];
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float val = 0.f;
+  if (i < n) {
+    float d = scale * x[i] - target[i];
+    val = d * d / (float)n;
+    if (d_x) d_x[i] = 2.f * scale * d / (float)n;
+  }
+  float tot = block_sum(val, red);
+  if (threadIdx.x == 0 && tot != 0.f) atomicAdd(loss, tot);
+}
+
 struct AdamState {
   int step;
   float bc1, bc2_sqrt;
@@ -151,6 +166,13 @@ extern "C" int harp_adam_dev(float* param, const float* grad, float* exp_avg, fl
     adam_dev_kernel<<<(int)((n + TPB - 1) / TPB), TPB, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                                 (const AdamState*)state);
   HARP_LAUNCH_CHECK_N(2);
+  return HARP_OK;
+}
+
+extern "C" int harp_mse(int64_t n, const float* x, const float* target, float scale, float* loss, float* d_x, void* stream) {
+  HARP_REQUIRE(n > 0 && x && target && loss, HARP_ERR_INVALID, "harp_mse: bad argument");
+  mse_kernel<<<(int)((n + TPB - 1) / TPB), TPB, 0, (cudaStream_t)stream>>>(n, x, target, scale, loss, d_x);
+  HARP_LAUNCH_CHECK();
   return HARP_OK;
 }
 

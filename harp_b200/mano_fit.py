@@ -1,0 +1,119 @@
+"""Upstream stage: the per-frame MANO fit to METRO's predicted vertices,
+`metro_modifications/hand_utils.py:16-133` (`optimize_for_mano_param`), on the B200 path.
+
+The reference runs, per batch of frames, 500 Adam steps on [rot, trans] (lr 1e-1) and 700 on [rot, pose, shape, trans]
+(lr 1e-2) of `MSELoss(ManoLayer(...)[0], 1000 * pred_vertices)`, re-starting (up to 4 tries) while the final loss exceeds 10.
+Each step there is ~40 ATen launches forward, as many backward, and a CPU-driven optimiser.  Here one step is four
+launches — `harp_lbs_mano_fwd`, `harp_mse`, `harp_lbs_mano_bwd`, `harp_adam_dev` (+ the gradient mask of the coarse stage) —
+captured once per stage as a CUDA graph and replayed; the host reads the loss once per try.
+
+Parameters live in ONE flat fp32 buffer `[pose48 (B,48) = rot|pose | trans (B,3) | shape (B,10)]` with matching grad and
+Adam-moment buffers, so a stage is a single fused Adam over everything; the coarse stage zeroes the pose / shape gradients,
+for which Adam with zero moments yields exactly zero update — bit-identical to an optimiser over [rot, trans] only.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream
+
+
+class _FitState:
+    def __init__(self, hc, target_mm):
+        dev = target_mm.device
+        B = target_mm.shape[0]
+        self.hc, self.B, self.dev = hc, B, dev
+        self.target = target_mm.contiguous()
+        n = B * (48 + 3 + 10)
+        self.data, self.grad = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+        self.m, self.v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+        self.state = torch.zeros(3, dtype=torch.int32, device=dev)
+        o1, o2 = B * 48, B * 51
+        self.pose48, self.trans, self.shape = self.data[:o1].view(B, 48), self.data[o1:o2].view(B, 3), self.data[o2:].view(B, 10)
+        self.d_pose48, self.d_trans, self.d_shape = self.grad[:o1].view(B, 48), self.grad[o1:o2].view(B, 3), self.grad[o2:].view(B, 10)
+        mask = torch.zeros(n, device=dev)
+        mask[:o1].view(B, 48)[:, :3] = 1.0  # rot
+        mask[o1:o2] = 1.0                   # trans
+        self.coarse_mask = mask
+        self.verts0 = torch.empty(B, hc.V0, 3, device=dev)
+        self.joints = torch.empty(B, 21, 3, device=dev)
+        self.d_verts0 = torch.empty(B, hc.V0, 3, device=dev)
+        self.loss = torch.zeros(1, device=dev)
+
+    def reset(self, trans_init):
+        for t in (self.data, self.m, self.v):
+            t.zero_()
+        self.state.zero_()
+        self.trans.copy_(trans_init)
+
+    def new_optimizer(self):
+        self.m.zero_()
+        self.v.zero_()
+        self.state.zero_()
+
+    def forward(self):
+        check(_lib.lib().harp_lbs_mano_fwd(self.hc.h, self.B, ptr(self.pose48), ptr(self.shape), 0, ptr(self.trans), ptr(self.verts0),
+                                           ptr(self.joints), stream()))
+
+    def iteration(self, lr, coarse):
+        L, st = _lib.lib(), stream()
+        self.loss.zero_()
+        self.forward()
+        check(L.harp_mse(self.verts0.numel(), ptr(self.verts0), ptr(self.target), 1000.0, ptr(self.loss), ptr(self.d_verts0), st))
+        check(L.harp_lbs_mano_bwd(self.hc.h, self.B, ptr(self.pose48), ptr(self.shape), 0, ptr(self.trans), ptr(self.d_verts0), None,
+                                  ptr(self.d_pose48), ptr(self.d_shape), ptr(self.d_trans), st))
+        if coarse:
+            self.grad.mul_(self.coarse_mask)
+        check(L.harp_adam_dev(ptr(self.data), ptr(self.grad), ptr(self.m), ptr(self.v), self.data.numel(), float(lr), 0.9, 0.999, 1e-8,
+                              self.state.data_ptr(), st))
+
+    def capture(self, lr, coarse):
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # one eager pass to warm up; its effect is undone by the caller's reset
+            self.iteration(lr, coarse)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.iteration(lr, coarse)
+        return g
+
+
+def optimize_for_mano_param(pred_vertices, mano_layer, idx=0, vert_rgb=None, epoch_coarse=500, epoch_fine=700, max_tries=4,
+                            use_graph=True):
+    """Same call and return value as `metro_modifications/hand_utils.py:16` (epochs exposed as keyword arguments with the
+    reference's values as defaults).  pred_vertices: (B,778,3) metres; mano_layer: `harp_b200.manolayer.ManoLayer`.
+    Returns numpy arrays: joints (B,21,3) mm, verts (B,778,3) mm, rot (B,3), pose (B,45), shape (B,10), trans (B,3)."""
+    hc = mano_layer.hc_coarse
+    dev = hc.device
+    pred = torch.as_tensor(pred_vertices, dtype=torch.float32).to(dev)
+    if pred.dim() != 3 or pred.shape[1:] != (hc.V0, 3):
+        raise ValueError(f"pred_vertices must be (B,{hc.V0},3), got {tuple(pred.shape)}")
+    target = pred.detach() * 1000.0                      # hand_utils.py:39
+    trans_init = target.mean(1) / 1000.0                 # 40, 62
+    fs = _FitState(hc, target)
+    graphs = {}
+    if use_graph:
+        fs.reset(trans_init)
+        graphs["coarse"] = fs.capture(1e-1, True)
+        graphs["fine"] = fs.capture(1e-2, False)
+    final_loss = None
+    for try_num in range(max_tries):                    # 54: restart while the fit error stays above 10
+        fs.reset(trans_init)                            # 57-64 (zeros; trans at the target centroid)
+        for stage, lr, n in (("coarse", 1e-1, epoch_coarse), ("fine", 1e-2, epoch_fine)):
+            fs.new_optimizer()                          # 75 / 98: a fresh torch.optim.Adam per stage
+            for _ in range(n):
+                if use_graph:
+                    graphs[stage].replay()
+                else:
+                    fs.iteration(lr, stage == "coarse")
+        final_loss = float(fs.loss.item())             # loss of the last iteration's forward (107)
+        if final_loss <= 10.0:
+            break
+    fs.forward()                                        # 120
+    out = {"joints": (fs.joints * 1000.0).cpu().numpy(), "verts": (fs.verts0 * 1000.0).cpu().numpy(),
+           "rot": fs.pose48[:, :3].cpu().numpy(), "pose": fs.pose48[:, 3:].cpu().numpy(),
+           "shape": fs.shape.cpu().numpy(), "trans": fs.trans.cpu().numpy()}
+    optimize_for_mano_param.last_loss = final_loss
+    optimize_for_mano_param.last_tries = try_num + 1
+    return {k: np.ascontiguousarray(v) for k, v in out.items()}

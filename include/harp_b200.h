@@ -247,6 +247,12 @@ HARP_API int harp_frame_glue_bwd(harp_ctx*, int B, int S, float focal, const flo
 HARP_API int harp_texture_reg(harp_ctx*, int kind, const float* map, int H, int W, const int32_t* offsets, const float* uv_mask,
                      float weight, float* loss, float* d_map, void* stream);
 
+/* ---- vertex MSE of the upstream per-frame MANO fit (metro_modifications/hand_utils.py:16-133, optimize_for_mano_param) -----
+ * loss += mean_i (scale x_i - target_i)^2 over n elements (torch.nn.MSELoss, 64/74/93); d_x_i = 2 scale (scale x_i - target_i) / n
+ * (overwritten; may be NULL).  With x = harp_lbs_mano_fwd's verts in metres, scale = 1000 and target in millimetres this is
+ * the fit's criterion on ManoLayer's mm output. */
+HARP_API int harp_mse(int64_t n, const float* x, const float* target, float scale, float* loss, float* d_x, void* stream);
+
 /* ---- uint8 frame ingest: load_img of utils/data_util.py:11-30 on the device ---------------------------------------------
  * rgb_u8 (B,S,S,3), mask_u8 (B,S,S) as decoded from the JPEG / PNG files -> y_true = rgb/255 (B,S,S,3) fp32,
  * y_sil = mask/255 (B,S,S), y_sil_eroded = cv2.erode(mask/255, ones(3,3), iterations=2) (border pixels ignore the outside).

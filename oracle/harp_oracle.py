@@ -485,3 +485,35 @@ def step(model, topo, params, batch, cfg):
     losses = {k: v.detach() for k, v in losses.items()}
     losses["total"] = tot.detach()
     return losses, {k: (v.detach() if torch.is_tensor(v) else v) for k, v in img.items()}, grads
+
+
+# ------------------------------------------------------------------------------------------------- upstream MANO fit
+def mano_fit(model, pred_vertices, epoch_coarse=500, epoch_fine=700, max_tries=4):
+    """metro_modifications/hand_utils.py:16-133 (optimize_for_mano_param) on CPU: 500 Adam steps on [rot, trans] at
+    lr 1e-1 (75-91), 700 on [rot, pose, shape, trans] at lr 1e-2 (98-106) of MSELoss(ManoLayer verts mm, 1000 * pred) (74),
+    restarted while the last loss exceeds 10 (54, 108-114).  PINNED: `tests/golden/fit_mano_b2.npz` holds the outputs of the
+    reference's own function run in the build container (`tests/golden/make_golden_fit.py`).
+    Returns (dict of tensors: joints, verts [mm], rot, pose, shape, trans; last loss)."""
+    B = pred_vertices.shape[0]
+    target = pred_vertices.detach() * 1000.0  # 39
+    target_mean = target.mean(1)  # 40
+    mse = torch.nn.MSELoss()
+    loss = None
+    for try_num in range(max_tries):  # 54
+        shape = torch.zeros(B, 10, requires_grad=True)  # 57-58
+        rot = torch.zeros(B, 3, requires_grad=True)  # 59-60
+        pose = torch.zeros(B, 45, requires_grad=True)  # 61-62
+        trans = (torch.zeros(B, 3) + target_mean / 1000.0).requires_grad_()  # 63-64
+        for group, lr, n in (([rot, trans], 1e-1, epoch_coarse), ([rot, pose, shape, trans], 1e-2, epoch_fine)):
+            opt = torch.optim.Adam(group, lr=lr)  # 75 / 98
+            for _ in range(n):
+                verts, _ = mano_forward(model, torch.cat((rot, pose), 1), shape, trans)
+                loss = mse(verts, target)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+        if float(loss) <= 10.0:  # 113
+            break
+    with torch.no_grad():
+        verts, joints = mano_forward(model, torch.cat((rot, pose), 1), shape, trans)  # 120
+    return dict(joints=joints, verts=verts, rot=rot.detach(), pose=pose.detach(), shape=shape.detach(), trans=trans.detach()), float(loss)
