@@ -277,12 +277,14 @@ __global__ void __launch_bounds__(128, HARP_SHADE_MIN_CTAS) shade_deferred_kerne
     h.fid = rec.y;
     FaceRec f;
     load_face(c, ndc, h.fid, 0.f, f);
+    ShadePre pre;  // vertex attributes, uvs and targets: in flight while the barycentrics are evaluated
+    shade_preload<MODE>(c, a, b, pix, h.fid, f.v0, f.v1, f.v2, pre);
     PairEval e;
     eval_pair_full<false, false>(f, px, py, 0.f, e);
     if (e.pass) { h.pz = e.pz; h.b0 = e.b0; h.b1 = e.b1; h.b2 = e.b2; h.w0 = e.w0; h.w1 = e.w1; h.w2 = e.w2; }
     else h.fid = -1;  // the exact test disagrees with the fast classification on a boundary pixel: background
     ShadeOut o;
-    shade_pixel<MODE>(c, a, b, pix, px, py, h, o);
+    shade_pixel<MODE>(c, a, b, pix, px, py, h, o, &pre);
     if (MODE != 1) st3(a.rgb + pix * 3, o.rgb);
     if (MODE != 0) {
       s_fr[8][threadIdx.x] += o.loss_abs;

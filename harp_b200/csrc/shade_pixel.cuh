@@ -101,6 +101,29 @@ __device__ __forceinline__ f3 normalize_bwd_eps(f3 x, f3 gy, float eps) {
   return (1.f / eps) * gy;
 }
 
+// Per-vertex attributes and targets of one hit pixel, requested by the caller as soon as the face id is known so that their
+// latency overlaps the exact barycentric evaluation (the deferred kernel's dependent-load chain is its limiter).
+struct ShadePre {
+  f3 P0, P1, P2, N0, N1, N2;
+  float uv[6];
+  float mk;
+  f3 y;
+};
+
+template <int MODE>
+__device__ __forceinline__ void shade_preload(const harp_ctx& c, const ShadeArgs& a, int b, size_t pix, int fid, int v0, int v1, int v2,
+                                              ShadePre& p) {
+  const float* vb = a.verts + (size_t)b * c.V * 3;
+  const float* nb = a.normals + (size_t)b * c.V * 3;
+  p.P0 = ld3(vb + (size_t)v0 * 3); p.P1 = ld3(vb + (size_t)v1 * 3); p.P2 = ld3(vb + (size_t)v2 * 3);
+  p.N0 = ld3(nb + (size_t)v0 * 3); p.N1 = ld3(nb + (size_t)v1 * 3); p.N2 = ld3(nb + (size_t)v2 * 3);
+  const float* fu = c.face_uvs + (size_t)fid * 6;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) p.uv[k] = fu[k];
+  if (MODE == 2) { p.mk = a.mask[pix]; p.y = ld3(a.gin + pix * 3); }
+  else if (MODE == 1) { p.mk = 0.f; p.y = ld3(a.gin + pix * 3); }
+}
+
 struct ShadeOut {
   f3 rgb;
   float loss_abs;   // sum_c |rgb_c m - y_c m| of this pixel (MODE 2)
@@ -127,7 +150,7 @@ __device__ __forceinline__ void shade_flush_frame_scalars(const ShadeArgs& a, in
 // MODE 0 forward; 1 backward with upstream g_rgb; 2 fused photometric L1 on the eroded mask.
 template <int MODE>
 __device__ __forceinline__ void shade_pixel(const harp_ctx& c, const ShadeArgs& a, int b, size_t pix, float px, float py,
-                                            const Hit& h, ShadeOut& o) {
+                                            const Hit& h, ShadeOut& o, const ShadePre* pre = nullptr) {
   const int S = a.S;
   const float* ndc = a.ndc_cam + (size_t)b * c.V * 3;
   f3 rgb = mk3(1.f, 1.f, 1.f);  // background (renderer_helper.py:430)
@@ -148,11 +171,41 @@ __device__ __forceinline__ void shade_pixel(const harp_ctx& c, const ShadeArgs& 
     v0 = fv[0]; v1 = fv[1]; v2 = fv[2];
     const float* vb = a.verts + (size_t)b * c.V * 3;
     const float* nb = a.normals + (size_t)b * c.V * 3;
-    P = h.b0 * ld3(vb + (size_t)v0 * 3) + h.b1 * ld3(vb + (size_t)v1 * 3) + h.b2 * ld3(vb + (size_t)v2 * 3);
-    N = h.b0 * ld3(nb + (size_t)v0 * 3) + h.b1 * ld3(nb + (size_t)v1 * 3) + h.b2 * ld3(nb + (size_t)v2 * 3);
-    const float* fu = c.face_uvs + (size_t)h.fid * 6;
-    float u = h.b0 * fu[0] + h.b1 * fu[2] + h.b2 * fu[4];
-    float v = h.b0 * fu[1] + h.b1 * fu[3] + h.b2 * fu[5];
+    float u, v;
+    if (pre) {
+      P = h.b0 * pre->P0 + h.b1 * pre->P1 + h.b2 * pre->P2;
+      N = h.b0 * pre->N0 + h.b1 * pre->N1 + h.b2 * pre->N2;
+      u = h.b0 * pre->uv[0] + h.b1 * pre->uv[2] + h.b2 * pre->uv[4];
+      v = h.b0 * pre->uv[1] + h.b1 * pre->uv[3] + h.b2 * pre->uv[5];
+    } else {
+      P = h.b0 * ld3(vb + (size_t)v0 * 3) + h.b1 * ld3(vb + (size_t)v1 * 3) + h.b2 * ld3(vb + (size_t)v2 * 3);
+      N = h.b0 * ld3(nb + (size_t)v0 * 3) + h.b1 * ld3(nb + (size_t)v1 * 3) + h.b2 * ld3(nb + (size_t)v2 * 3);
+      const float* fu = c.face_uvs + (size_t)h.fid * 6;
+      u = h.b0 * fu[0] + h.b1 * fu[2] + h.b2 * fu[4];
+      v = h.b0 * fu[1] + h.b1 * fu[3] + h.b2 * fu[5];
+    }
+    // the 9 PCF taps of the light-view depth buffer depend only on P: request them before the texture taps
+    float ztap[9];
+    if (a.self_shadow) {
+      // hit point in light view space (row-vector: p R + T), its light-screen pixel, 3x3 clamped taps
+      float xl = P.x * lR[0] + P.y * lR[3] + P.z * lR[6] + lT[0];
+      float yl = P.x * lR[1] + P.y * lR[4] + P.z * lR[7] + lT[1];
+      zL = P.x * lR[2] + P.y * lR[5] + P.z * lR[8] + lT[2];
+      float hs = 0.5f * (float)S;
+      float xs = hs - hs * ((a.focal * xl / zL) / hs), ys = hs - hs * ((a.focal * yl / zL) / hs);
+      // .round().long(): round-half-even, then saturate like a float->int64 cast would never need to here
+      float xr = rintf(xs), yr = rintf(ys);
+      xr = fminf(fmaxf(xr, -2.f), (float)S + 1.f); yr = fminf(fmaxf(yr, -2.f), (float)S + 1.f);
+      tap_xk = (int)xr; tap_yk = (int)yr;
+      const float* zb = a.light_zbuf + (size_t)b * S * S;
+#pragma unroll
+      for (int ii = -1; ii <= 1; ++ii)
+#pragma unroll
+        for (int jj = -1; jj <= 1; ++jj) {
+          int ry = min(max(tap_yk + ii, 0), S - 1), rx = min(max(tap_xk + jj, 0), S - 1);
+          ztap[(ii + 1) * 3 + (jj + 1)] = zb[ry * S + rx];
+        }
+    }
     make_taps(u, v, a.texH, a.texW, tp);
     tex = mk3(0.f, 0.f, 0.f);
     m = mk3(0.f, 0.f, 0.f);
@@ -178,30 +231,14 @@ __device__ __forceinline__ void shade_pixel(const harp_ctx& c, const ShadeArgs& 
     dh = (1.f / ld) * dvec;
     cosang = fmaxf(dot(n2, dh), 0.f);
     if (a.self_shadow) {
-      // hit point in light view space (row-vector: p R + T), its light-screen pixel, 3x3 clamped taps
-      float xl = P.x * lR[0] + P.y * lR[3] + P.z * lR[6] + lT[0];
-      float yl = P.x * lR[1] + P.y * lR[4] + P.z * lR[7] + lT[1];
-      zL = P.x * lR[2] + P.y * lR[5] + P.z * lR[8] + lT[2];
-      float hs = 0.5f * (float)S;
-      float xs = hs - hs * ((a.focal * xl / zL) / hs), ys = hs - hs * ((a.focal * yl / zL) / hs);
-      // .round().long(): round-half-even, then saturate like a float->int64 cast would never need to here
-      float xr = rintf(xs), yr = rintf(ys);
-      xr = fminf(fmaxf(xr, -2.f), (float)S + 1.f); yr = fminf(fmaxf(yr, -2.f), (float)S + 1.f);
-      int xk = (int)xr, yk = (int)yr;
-      tap_xk = xk; tap_yk = yk;
-      const float* zb = a.light_zbuf + (size_t)b * S * S;
       float acc = 0.f;
 #pragma unroll
-      for (int ii = -1; ii <= 1; ++ii)
-#pragma unroll
-        for (int jj = -1; jj <= 1; ++jj) {
-          int ry = min(max(yk + ii, 0), S - 1), rx = min(max(xk + jj, 0), S - 1);
-          int t = (ii + 1) * 3 + (jj + 1);
-          float x = (zb[ry * S + rx] - (zL - 0.008f)) * 1000.f;
-          float sg = __fdividef(1.f, 1.f + __expf(-x));  // sigmoid; 2-ulp exp and division are far inside the 1e-4 image tolerance
-          tapsig[t] = sg;
-          acc += sg;
-        }
+      for (int t = 0; t < 9; ++t) {
+        float x = (ztap[t] - (zL - 0.008f)) * 1000.f;
+        float sg = __fdividef(1.f, 1.f + __expf(-x));  // sigmoid; 2-ulp exp and division are far inside the 1e-4 image tolerance
+        tapsig[t] = sg;
+        acc += sg;
+      }
       vis = acc / 9.f;
     }
     const float ka = a.fixed_lights ? a.ka : amb, kd = a.fixed_lights ? a.kd : 1.f - amb;
@@ -219,10 +256,10 @@ __device__ __forceinline__ void shade_pixel(const harp_ctx& c, const ShadeArgs& 
 
   f3 g;  // dL/d rgb
   if (MODE == 1) {
-    g = ld3(a.gin + pix * 3);
+    g = pre ? pre->y : ld3(a.gin + pix * 3);
   } else {
-    float mk = a.mask[pix];
-    f3 y = ld3(a.gin + pix * 3);
+    float mk = pre ? pre->mk : a.mask[pix];
+    f3 y = pre ? pre->y : ld3(a.gin + pix * 3);
     f3 d = mk3(rgb.x * mk - y.x * mk, rgb.y * mk - y.y * mk, rgb.z * mk - y.z * mk);
     o.loss_abs = fabsf(d.x) + fabsf(d.y) + fabsf(d.z);
     auto sgn = [](float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); };
