@@ -91,6 +91,7 @@ class HarpFitter:
         dev = hc.device
         self.hc, self.S, self.focal, self.self_shadow = hc, int(img_size), float(focal_length), bool(self_shadow)
         self.lr_coarse, self.lr_app = lr_coarse, lr_app
+        self.faces_per_pixel = 50  # silhouette rasteriser's K (optimize_sequence.py:427); settable for tests of the top-K path
         self.world_size, self.pg = int(world_size), process_group
         f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
         # optimiser groups (get_optimizers, optimize_sequence.py:253-310, default `harp` branch).  With the SMPL-X arm model
@@ -220,7 +221,7 @@ class HarpFitter:
                             d_texture=ptr(self.app.g["texture"]), d_normal_map=ptr(self.app.g["normal_map"]))
         ra = HarpRenderArgs(verts=ptr(verts), normals=ptr(normals), cam_R=ptr(cR), cam_T=ptr(cTc), light_R=ptr(lRc), light_T=ptr(lTc),
                             light_pos=ptr(light_bc), amb=ptr(ambc), texture=ptr(tex), normal_map=ptr(nm), texH=H, texW=Wd,
-                            self_shadow=int(self.self_shadow), faces_per_pixel=50, sigma=1e-7, y_sil=ptr(fr["y_sil"]), y_true=ptr(fr["y_true"]),
+                            self_shadow=int(self.self_shadow), faces_per_pixel=int(self.faces_per_pixel), sigma=1e-7, y_sil=ptr(fr["y_sil"]), y_true=ptr(fr["y_true"]),
                             y_mask=ptr(fr["y_sil_eroded"]), w_sil=W["silhouette"] * fscale if coarse_on else 0.0,
                             w_photo=W["photo"] * fscale if app_on else 0.0, alpha=ptr(alpha), rgb=ptr(rgb),
                             loss_sil=ptr(self.losses[_SLOT["silhouette"]:]), loss_photo=ptr(self.losses[_SLOT["photo"]:]), grads=gs)

@@ -1,0 +1,103 @@
+"""GPU parity of the fused step (pixel_vis + shade_deferred, the optimised path) on framings the golden cases do not reach:
+a hand partly outside the image, a frame with no hand at all, a hand that crosses the camera plane (vertices with z <= 0:
+the classification's exact path), a tiny hand (many faces per tile: multi-chunk tiles and the top-K deferral), and an odd
+batch size.  The checker is the CPU oracle's whole step (`O.step`) on identical inputs."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import harp_oracle as O
+from util import load_golden, golden_case, rel_l2
+from test_gpu_kernels import _fitter_from_case
+
+
+def _variant(kind):
+    g = load_golden("c2_full_128_sub")
+    model, topo, params, batch, cfg = golden_case(g)
+    params = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in params.items()}
+    batch = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    cam = params["cam"]
+    if kind == "partly_outside":
+        cam[:, 1] += 0.09          # about half of the hand leaves the image on one side
+        cam[1, 2] -= 0.07
+    elif kind == "one_empty_frame":
+        cam[1, 1] += 5.0           # frame 1: nothing in view at all
+    elif kind == "crosses_camera_plane":
+        cam[0, 0] = 160.0          # t_z = 2 f / (S s) ~ 5.6 cm: part of the hand lies behind the camera (z <= 0)
+    elif kind == "tiny_hand":
+        cam[:, 0] = 1.5            # ~15 px wide at 128^2: tens of faces per pixel, hundreds per tile
+    elif kind == "batch_of_three":
+        idx = torch.tensor([0, 1, 0])
+        for k in ("pose", "rot", "trans", "cam"):
+            params[k] = params[k][idx].clone()
+        params["cam"][2, 1] += 0.03
+        for k in ("y_true", "y_sil", "y_sil_eroded", "init_joints"):
+            batch[k] = batch[k][idx].clone()
+    return model, topo, params, batch, cfg
+
+
+@pytest.mark.parametrize("kind", ["partly_outside", "one_empty_frame", "crosses_camera_plane", "tiny_hand", "batch_of_three"])
+def test_fused_step_edge_framing(kind):
+    case = _variant(kind)
+    model, topo, params, batch, cfg = case
+    ref_losses, ref_img, ref_grads = O.step(model, topo, params, batch, cfg)
+    ft, hc = _fitter_from_case(case)
+    B = params["pose"].shape[0]
+    fid = torch.arange(B, device="cuda")
+    ft.step(fid, batch["off_albedo"].cuda().int().contiguous(), batch["off_normal"].cuda().int().contiguous(),
+            stage=cfg["stage"], update=False)
+    ld = ft.loss_dict()
+    cnt = hc.counters()
+    assert cnt["bin_overflow"] == 0 and cnt["sil_k_overflow_pixels"] == 0, cnt
+    assert all(math.isfinite(v) for v in ld.values()), ld
+    assert torch.isfinite(ft.coarse.grad).all() and torch.isfinite(ft.app.grad).all()
+    # images: alpha is exactly 0/1 outside the +-1/3 px edge bands (tolerances as tests/test_gpu_kernels.py)
+    da = (ft.last["alpha"].cpu() - ref_img["sil"]).abs()
+    assert float((da <= 1e-4).double().mean()) >= 0.998, float((da <= 1e-4).double().mean())
+    drgb = (ft.last["rgb"].cpu() - ref_img["rgb"]).abs().amax(-1)
+    assert float((drgb <= 1e-4).double().mean()) >= 0.995, float((drgb <= 1e-4).double().mean())
+    if kind == "one_empty_frame":
+        assert float(ft.last["alpha"][1].abs().max()) == 0.0 and float((ft.last["rgb"][1] - 1.0).abs().max()) == 0.0
+    for k in ("silhouette", "photo", "laplacian", "arap", "kps_anchor"):
+        assert math.isclose(ld[k], float(ref_losses[k]), rel_tol=3e-3, abs_tol=1e-7), (k, ld[k], float(ref_losses[k]))
+    assert math.isclose(ld["total"], float(ref_losses["total"]), rel_tol=2e-3)
+    grads = dict(ft.coarse.g)
+    tol = dict(pose=2e-2, cam=2e-2, shape=2e-2, verts_disps=3e-2)
+    if kind == "tiny_hand":
+        # a handful of sub-pixel faces per pixel: every gradient is a sum over a few hundred band pixels, each of which a
+        # 1-ulp coordinate difference can switch on or off
+        tol = dict(pose=8e-2, cam=8e-2, shape=8e-2, verts_disps=1.5e-1)
+    for k, t in tol.items():
+        r = rel_l2(grads[k].cpu().view(ref_grads[k].shape), ref_grads[k])
+        assert r < t, (k, r)
+
+
+@pytest.mark.parametrize("K", [3, 8])
+def test_fused_step_top_k_deferral_matches_standalone_silhouette(K):
+    """faces_per_pixel smaller than the candidates on a pixel: the fused pixel pass must defer those pixels to the exact
+    top-K kernel exactly as the stand-alone silhouette op does (which tests/test_gpu_kernels.py pins to the oracle at K=3, 8)."""
+    from harp_b200.ops import Silhouette
+    g = load_golden("c2_full_128_sub")
+    case = golden_case(g)
+    model, topo, params, batch, cfg = case
+    ft, hc = _fitter_from_case(case)
+    ft.faces_per_pixel = K
+    B = params["pose"].shape[0]
+    fid = torch.arange(B, device="cuda")
+    ft.step(fid, batch["off_albedo"].cuda().int().contiguous(), batch["off_normal"].cuda().int().contiguous(),
+            stage="both", update=False)
+    alpha_fused = ft.last["alpha"].clone()
+    d_cam_fused = ft.coarse.g["cam"].clone()
+    loss_fused = ft.loss_dict()["silhouette"]
+    S, focal = cfg["img_size"], cfg["focal_length"]
+    verts = ft.last["verts"].detach().clone()
+    cam = params["cam"].cuda().requires_grad_(True)
+    a = Silhouette.apply(hc, verts, O.cam_R(B, torch.float32).cuda(), O.cam_to_T(cam, focal, S), focal, S, 1e-7, K)
+    assert float((a - alpha_fused).abs().max()) <= 1e-6
+    ref50 = Silhouette.apply(hc, verts, O.cam_R(B, torch.float32).cuda(), O.cam_to_T(cam, focal, S), focal, S, 1e-7, 50)
+    assert float((ref50 - a).abs().max()) > 1e-3, "K must change the image for this test to mean anything"
+    loss = (a - batch["y_sil"].cuda()).abs().mean()
+    assert math.isclose(float(loss), loss_fused, rel_tol=1e-5)

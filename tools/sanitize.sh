@@ -18,8 +18,17 @@ for name in ("c2_full_128_sub", "c4_arm_128_sub"):
         ft.step(fid, batch["off_albedo"].cuda().int().contiguous(), batch["off_normal"].cuda().int().contiguous(), stage="both", update=True)
     torch.cuda.synchronize()
     print(name, ft.loss_dict()["total"], hc.counters())
+# upstream per-frame MANO fit (a few eager iterations)
+import numpy as np
+from harp_b200 import mano_fit, synth
+from harp_b200.manolayer import ManoLayer
+tmpl = synth.load_template("hand"); pack = synth.make_mano_pack(seed=0, template=tmpl)
+layer = ManoLayer(pack, tmpl["faces_uvs"], tmpl["verts_uvs"])
+g = load_golden("fit_mano_b2")
+mano_fit.optimize_for_mano_param(torch.tensor(g["pred_vertices"]), layer, epoch_coarse=3, epoch_fine=3, use_graph=False)
+print("mano_fit", mano_fit.optimize_for_mano_param.last_loss)
 PY
 for tool in memcheck racecheck; do
   echo "== compute-sanitizer --tool $tool"
-  compute-sanitizer --tool $tool --print-limit 5 python /tmp/san.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Error:|hazard|c2_full|c4_arm|Invalid|at 0x" | head -20
+  compute-sanitizer --tool $tool --print-limit 5 python /tmp/san.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Error:|hazard|c2_full|c4_arm|mano_fit|Invalid|at 0x" | head -20
 done
