@@ -64,7 +64,9 @@ __global__ void __launch_bounds__(256) frame_glue_fwd_kernel(int V, int S, float
   const float* cam = cam_table + (size_t)(fid ? fid[b] : b) * 3;
   cam_T[b * 3 + 0] = -cam[1];
   cam_T[b * 3 + 1] = -cam[2];
-  cam_T[b * 3 + 2] = (2.f * focal) / ((float)S * cam[0] + 1e-9f);  // utils/visualize.py:268
+  // utils/visualize.py:268 `2 * focal_length / (img_size * cam[:, 0] + 1e-9)`: torch evaluates scalar / tensor as
+  // reciprocal(tensor) * scalar (Tensor.__rtruediv__), two roundings — reproduced so that t_z is bit-identical
+  cam_T[b * 3 + 2] = (1.f / ((float)S * cam[0] + 1e-9f)) * (2.f * focal);
   float L[3] = {light_pos[0], light_pos[1], light_pos[2]}, R[9], T[3];
   light_camera<float>(L, c, R, T);
   for (int i = 0; i < 9; ++i) light_R[b * 9 + i] = R[i];
