@@ -17,12 +17,13 @@ void harp_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_rela
 extern "C" int64_t harp_launch_count(void) { return g_launches.load(); }
 
 struct harp_prof {
-  bool enabled = false;
+  int level = 0;          // 0 off; 1: the two pixel kernels (ids 0, 1; bench roofline timing); 2: also the step's segments (ids 2..7)
   bool in_graph = false;  // events belong to a captured graph: keep them across reads
-  std::vector<cudaEvent_t> ev[2];  // start/stop pairs per kernel id
+  std::vector<cudaEvent_t> ev[8];  // start/stop pairs per id: 0 pixel_vis / silhouette, 1 shade, 2 lbs fwd, 3 lbs bwd,
+                                   // 4 mesh build fwd, 5 mesh build bwd, 6 camera project + bins, 7 render backward tail
 };
 void harp_prof_begin(harp_ctx* c, int id, cudaStream_t st) {
-  if (!c->prof || !c->prof->enabled) return;
+  if (!c->prof || c->prof->level == 0 || (id >= 2 && c->prof->level < 2)) return;
   cudaEvent_t e;
   if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return; }
   // inside a stream capture the record must become an EXTERNAL event node: it is re-recorded on every graph replay and
@@ -39,11 +40,11 @@ void harp_prof_end(harp_ctx* c, int id, cudaStream_t st) { harp_prof_begin(c, id
 extern "C" int harp_ctx_profile(harp_ctx* c, int enable) {
   HARP_REQUIRE(c, HARP_ERR_INVALID, "harp_ctx_profile: null ctx");
   if (!c->prof) c->prof = new harp_prof();
-  c->prof->enabled = enable != 0;
+  c->prof->level = enable;
   return HARP_OK;
 }
 extern "C" int harp_ctx_profile_read(harp_ctx* c, int id, float* total_ms, int* launches) {
-  HARP_REQUIRE(c && id >= 0 && id < 2 && total_ms && launches, HARP_ERR_INVALID, "harp_ctx_profile_read: bad argument");
+  HARP_REQUIRE(c && id >= 0 && id < 8 && total_ms && launches, HARP_ERR_INVALID, "harp_ctx_profile_read: bad argument");
   *total_ms = 0.f; *launches = 0;
   if (!c->prof) return HARP_OK;
   auto& v = c->prof->ev[id];

@@ -236,12 +236,26 @@ __global__ void __launch_bounds__(LBS_THREADS) lbs_bwd_kernel(harp_ctx c, const 
     if (lane == 0) g.dA[j][k] = a;
   }
   // d pose_map and the direct d shape: transposed-table mat-vec, one warp per output
-  for (int o = warp; o < NP + NS; o += nw) {
-    const float* row = o < NP ? c.posedirs + (size_t)o * n3 : c.shapedirs + (size_t)(o - NP) * n3;
-    float a = 0.f;
-    for (int i = lane; i < n3; i += 32) a += row[i] * dvp[i];
-    a = warp_sum(a);
-    if (lane == 0) { if (o < NP) g.dpm[o] = a; else g.dbeta[o - NP] = a; }
+  // (four table rows in flight per warp: the loop is bound by L2 latency, not by arithmetic)
+  for (int o0 = warp * 4; o0 < NP + NS; o0 += nw * 4) {
+    const float* row[4];
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int o = min(o0 + r, NP + NS - 1);
+      row[r] = o < NP ? c.posedirs + (size_t)o * n3 : c.shapedirs + (size_t)(o - NP) * n3;
+    }
+    for (int i = lane; i < n3; i += 32) {
+      float d = dvp[i];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] += row[r][i] * d;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float v = warp_sum(a[r]);
+      int o = o0 + r;
+      if (lane == 0 && o < NP + NS) { if (o < NP) g.dpm[o] = v; else g.dbeta[o - NP] = v; }
+    }
   }
   __syncthreads();
   if (t == 0) {
@@ -323,7 +337,9 @@ extern "C" int harp_lbs_fwd(harp_ctx* c, int B, const float* pose, const float* 
                             float* verts0, float* joints, void* stream) {
   HARP_REQUIRE(c && B > 0 && pose && shape && trans && verts0 && joints, HARP_ERR_INVALID, "harp_lbs_fwd: null argument");
   HARP_REQUIRE(c->has_model, HARP_ERR_NO_MODEL, "harp_lbs_fwd: ctx has no skinning model");
+  harp_prof_begin(c, 2, (cudaStream_t)stream);
   lbs_fwd_kernel<<<B, LBS_THREADS, 0, (cudaStream_t)stream>>>(*c, pose, shape, shape_shared, trans, verts0, joints);
+  harp_prof_end(c, 2, (cudaStream_t)stream);
   HARP_LAUNCH_CHECK();
   return HARP_OK;
 }
@@ -340,8 +356,10 @@ extern "C" int harp_lbs_bwd(harp_ctx* c, int B, const float* pose, const float* 
     HARP_CHECK_CUDA(cudaFuncSetAttribute(lbs_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     configured = dyn;
   }
+  harp_prof_begin(c, 3, (cudaStream_t)stream);
   lbs_bwd_kernel<<<B, LBS_THREADS, dyn, (cudaStream_t)stream>>>(*c, pose, shape, shape_shared, d_verts0, d_joints, d_pose,
                                                                 d_shape, d_trans);
+  harp_prof_end(c, 3, (cudaStream_t)stream);
   HARP_LAUNCH_CHECK();
   return HARP_OK;
 }

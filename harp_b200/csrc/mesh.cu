@@ -304,8 +304,10 @@ extern "C" int harp_mesh_build_fwd(harp_ctx* c, int B, const float* verts0, cons
                                    float* normals, void* stream) {
   HARP_REQUIRE(c && B > 0 && verts0 && verts, HARP_ERR_INVALID, "harp_mesh_build_fwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
+  harp_prof_begin(c, 4, st);
   build_displace_kernel<<<nblk((size_t)B * c->V), TPB, 0, st>>>(*c, B, verts0, disps, verts);
   if (normals) vertex_normals_kernel<<<nblk((size_t)B * c->V), TPB, 0, st>>>(*c, B, verts, normals);
+  harp_prof_end(c, 4, st);
   HARP_LAUNCH_CHECK_N(normals ? 2 : 1);
   return HARP_OK;
 }
@@ -336,6 +338,7 @@ extern "C" int harp_mesh_build_bwd(harp_ctx* c, int B, const float* verts0, cons
   cudaStream_t st = (cudaStream_t)stream;
   int nb = nblk((size_t)B * c->V);
   const float* g = d_verts;  // running gradient w.r.t. the final verts
+  harp_prof_begin(c, 5, st);
   if (d_normals) {
     build_displace_kernel<<<nb, TPB, 0, st>>>(*c, B, verts0, disps, c->vtmp);  // recompute final verts
     normals_bwd_dN_kernel<<<nb, TPB, 0, st>>>(*c, B, c->vtmp, d_normals, c->vtmp2);
@@ -348,6 +351,7 @@ extern "C" int harp_mesh_build_bwd(harp_ctx* c, int B, const float* verts0, cons
     g = c->vtmp;
   }
   subdivide_bwd_kernel<<<nblk((size_t)B * c->V0), TPB, 0, st>>>(*c, B, g, d_verts0);
+  harp_prof_end(c, 5, st);
   HARP_LAUNCH_CHECK_N(1 + (d_normals ? 3 : 0) + (disps ? 2 : 0));
   return HARP_OK;
 }

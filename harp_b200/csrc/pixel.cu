@@ -322,37 +322,22 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
   const size_t npx = (size_t)B * S * S, nv4 = (size_t)B * c->V * 4 * sizeof(float), ntex = (size_t)r->texH * r->texW;
   double blur_d = 9.210240366975849 * (double)r->sigma;  // ln(1/1e-4 - 1) sigma (renderer_helper.py:46)
   float blur = (float)blur_d, radius = (float)sqrt(blur_d);
-  // Side branch on the ctx's own stream, concurrent with the camera branch (projection, bins, pixel_vis) below and joined
-  // before the deferred shading: everything only the shading needs — the light view (projection, bins, nearest-depth
-  // raster), the packed texel copies, and the zero fills of the shading's gradient accumulators (92 MB at 64 x 512^2).
-  // Event fork / join is capturable into a CUDA graph.
+  // Camera branch first (it is the critical path: its kernels are submitted before the side branch's so that they are
+  // dispatched first).
   if (!c->side_stream) {
-    HARP_CHECK_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    int lo = 0, hi = 0;
+    HARP_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = least priority
+    HARP_CHECK_CUDA(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, lo));
     HARP_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     HARP_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   }
   cudaStream_t ss = c->side_stream;
   HARP_CHECK_CUDA(cudaEventRecord(c->ev_fork, st));
-  HARP_CHECK_CUDA(cudaStreamWaitEvent(ss, c->ev_fork, 0));
-  if (r->self_shadow) {
-    if ((rc = harp_project(c, B, S, focal, r->verts, r->light_R, r->light_T, c->ndc_light, ss)) != HARP_OK) return rc;
-    if ((rc = harp_build_bins(c, 1, B, S, 0.f, c->ndc_light, ss)) != HARP_OK) return rc;
-    if ((rc = harp_light_depth(c, B, S, ss)) != HARP_OK) return rc;
-  }
-  if ((rc = harp_tex_prepare(c, r->texture, r->normal_map, r->texH, r->texW, ss)) != HARP_OK) return rc;
-  if (photo_bwd) {
-    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_verts4, 0, nv4, ss));
-    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_normals4, 0, nv4, ss));
-    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_tex4, 0, 2 * ntex * 4 * sizeof(float), ss));
-    if (r->self_shadow) {
-      HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_light, 0, nv4, ss));
-      HARP_CHECK_CUDA(cudaMemsetAsync(c->d_light_zbuf, 0, npx * sizeof(float), ss));
-    }
-  }
-  HARP_CHECK_CUDA(cudaEventRecord(c->ev_join, ss));
+  harp_prof_begin(c, 6, st);
   if ((rc = harp_project(c, B, S, focal, r->verts, r->cam_R, r->cam_T, c->ndc_cam, st)) != HARP_OK) return rc;
   if ((rc = harp_build_bins(c, 0, B, S, radius, c->ndc_cam, st)) != HARP_OK) return rc;
   if (sil_bwd || photo_bwd) HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_cam, 0, nv4, st));
+  harp_prof_end(c, 6, st);
   HARP_CHECK_CUDA(cudaMemsetAsync(c->hit_count, 0, (size_t)B * sizeof(int32_t), st));
   HARP_CHECK_CUDA(cudaMemsetAsync(c->ovf_count, 0, sizeof(int32_t), st));
   VisArgs v{};
@@ -373,6 +358,27 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
   HARP_LAUNCH_CHECK();
   if ((rc = harp_sil_topk(c, sil_bwd ? 2 : 0, S, v.K, r->sigma, blur, radius, r->alpha, r->y_sil, v.sil_gscale, v.sil_inv_n,
                           r->loss_sil, st)) != HARP_OK) return rc;
+  // Side branch on the ctx's own (least-priority) stream, concurrent with the camera branch above and joined before the
+  // deferred shading: everything only the shading needs — the light view (projection, bins, nearest-depth raster), the
+  // packed texel copies, and the zero fills of the shading's gradient accumulators (92 MB at 64 x 512^2).
+  // Event fork / join is capturable into a CUDA graph.
+  HARP_CHECK_CUDA(cudaStreamWaitEvent(ss, c->ev_fork, 0));
+  if (r->self_shadow) {
+    if ((rc = harp_project(c, B, S, focal, r->verts, r->light_R, r->light_T, c->ndc_light, ss)) != HARP_OK) return rc;
+    if ((rc = harp_build_bins(c, 1, B, S, 0.f, c->ndc_light, ss)) != HARP_OK) return rc;
+    if ((rc = harp_light_depth(c, B, S, ss)) != HARP_OK) return rc;
+  }
+  if ((rc = harp_tex_prepare(c, r->texture, r->normal_map, r->texH, r->texW, ss)) != HARP_OK) return rc;
+  if (photo_bwd) {
+    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_verts4, 0, nv4, ss));
+    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_normals4, 0, nv4, ss));
+    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_tex4, 0, 2 * ntex * 4 * sizeof(float), ss));
+    if (r->self_shadow) {
+      HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_light, 0, nv4, ss));
+      HARP_CHECK_CUDA(cudaMemsetAsync(c->d_light_zbuf, 0, npx * sizeof(float), ss));
+    }
+  }
+  HARP_CHECK_CUDA(cudaEventRecord(c->ev_join, ss));
   HARP_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
   ShadeArgs a{};
   a.B = B; a.S = S; a.self_shadow = r->self_shadow; a.texH = r->texH; a.texW = r->texW; a.focal = focal;
@@ -393,6 +399,7 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
   else shade_deferred_kernel<0><<<sgrid, 128, 0, st>>>(*c, a, reinterpret_cast<const int2*>(c->hit_list), c->hit_count);
   harp_prof_end(c, 1, st);
   HARP_LAUNCH_CHECK();
+  harp_prof_begin(c, 7, st);
   if (photo_bwd) {
     if ((rc = harp_fold4((size_t)B * c->V, c->d_verts4, r->grads.d_verts, st)) != HARP_OK) return rc;
     if ((rc = harp_fold4((size_t)B * c->V, c->d_normals4, r->grads.d_normals, st)) != HARP_OK) return rc;
@@ -408,5 +415,6 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
     if ((rc = harp_project_bwd(c, B, S, focal, r->verts, r->cam_R, r->cam_T, c->d_ndc_cam, r->grads.d_verts, r->grads.d_cam_R,
                                r->grads.d_cam_T, st)) != HARP_OK) return rc;
   }
+  harp_prof_end(c, 7, st);
   return HARP_OK;
 }

@@ -117,14 +117,18 @@ class HarpContext:
             self._faces = torch.from_numpy(host).long().to(self.device)
         return self._faces
 
+    PROFILE_SEGMENTS = ("silhouette", "shade", "lbs_fwd", "lbs_bwd", "mesh_build_fwd", "mesh_build_bwd", "camera_project_bins",
+                        "render_backward_tail")
+
     def profile(self, enable=True):
-        """Bracket the silhouette / shade pixel kernels with CUDA events on the launch stream (bench roofline timing)."""
+        """Bracket the silhouette / shade pixel kernels with CUDA events on the launch stream (bench roofline timing);
+        enable=2 also brackets the step's other segments (tools/step_segments.py)."""
         check(_lib.lib().harp_ctx_profile(self.h, int(enable)))
 
-    def profile_read(self):
-        """-> {'silhouette': (total_ms, launches), 'shade': (total_ms, launches)} since the last read; synchronises."""
+    def profile_read(self, detailed=False):
+        """-> {'silhouette': (total_ms, launches), 'shade': (total_ms, launches)[, ...]} since the last read; synchronises."""
         out = {}
-        for i, n in enumerate(("silhouette", "shade")):
+        for i, n in enumerate(self.PROFILE_SEGMENTS if detailed else self.PROFILE_SEGMENTS[:2]):
             ms, k = C.c_float(), C.c_int()
             check(_lib.lib().harp_ctx_profile_read(self.h, i, C.byref(ms), C.byref(k)))
             out[n] = (ms.value, k.value)
