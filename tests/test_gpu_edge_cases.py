@@ -101,3 +101,31 @@ def test_fused_step_top_k_deferral_matches_standalone_silhouette(K):
     assert float((ref50 - a).abs().max()) > 1e-3, "K must change the image for this test to mean anything"
     loss = (a - batch["y_sil"].cuda()).abs().mean()
     assert math.isclose(float(loss), loss_fused, rel_tol=1e-5)
+
+
+@pytest.mark.parametrize("stage", ["coarse", "app"])
+def test_fused_step_stage_gating(stage):
+    """COARSE_OPT-only and APP_OPT-only epochs (optimize_sequence.py:507-515): the other stage's losses and gradients must be
+    absent, the active ones must match the oracle."""
+    g = load_golden("c2_full_128_sub")
+    model, topo, params, batch, cfg = golden_case(g)
+    cfg = dict(cfg, stage=stage)
+    ref_losses, _, ref_grads = O.step(model, topo, params, batch, cfg)
+    ft, hc = _fitter_from_case((model, topo, params, batch, cfg))
+    B = params["pose"].shape[0]
+    ft.step(torch.arange(B, device="cuda"), batch["off_albedo"].cuda().int().contiguous(), batch["off_normal"].cuda().int().contiguous(),
+            stage=stage, update=False)
+    ld = ft.loss_dict()
+    for k in ("silhouette", "photo", "laplacian", "arap", "kps_anchor", "albedo", "normal_reg"):
+        if k in ref_losses:
+            assert math.isclose(ld[k], float(ref_losses[k]), rel_tol=2e-3, abs_tol=1e-7), (k, ld[k], float(ref_losses[k]))
+        else:
+            assert ld[k] == 0.0, (k, ld[k])
+    grads = dict(ft.coarse.g); grads.update(ft.app.g)
+    for k, t in dict(pose=1e-2, cam=1e-2, shape=1e-2, verts_disps=2e-2, texture=6e-2, normal_map=6e-2).items():
+        gg = ref_grads[k]
+        mine = grads[k].cpu().view(gg.shape)
+        if float(gg.abs().max()) == 0.0:
+            assert float(mine.abs().max()) == 0.0, k
+        else:
+            assert rel_l2(mine, gg) < t, (k, rel_l2(mine, gg))
