@@ -21,7 +21,7 @@ namespace {
 
 constexpr int CHUNK = 64;
 constexpr int NT = HARP_TILE * HARP_TILE;
-constexpr int QCAP = 432;  // with the 112-byte face records: 13.4 KB per CTA -> 16 CTAs per SM
+constexpr int QCAP = 352;  // with the 128-byte face records: 13.5 KB per CTA -> 16 CTAs per SM
 
 struct VisArgs {
   int S, K;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(NT, 16) pixel_vis_kernel(harp_ctx c, VisArgs a
   int best_fid = -1;
   float best_q = 0.f;
   bool q_overflow = false;
-  const float sat = 17.5f * sigma, far = 1.001f * blur;
+  const float sat = 17.5f * sigma, far = 1.02f * blur;  // margins of the affine classification (raster.cuh: FaceTile)
   if (tid == 0) { any_bwd = 0; q_n = 0; }
   for (int base = 0; base < n; base += CHUNK) {
     int m = min(CHUNK, n - base);

@@ -196,24 +196,28 @@ __device__ __forceinline__ void load_face(const harp_ctx& c, const float* ndc, i
   f.iz0 = 1.f / f.z0; f.iz1 = 1.f / f.z1; f.iz2 = 1.f / f.z2;
 }
 
-// The shared-memory record of the tile kernels' face walk: 16-byte groups (one LDS.128 each, broadcast to the warp),
-// (7 of them) holding per-face constants so that the per-(pixel, face) classification is ~45 branch-free instructions:
-//   * the edge deltas fsub(b, a) of PyTorch3D's EdgeFunctionForward, rounded exactly as edge_fn rounds them, so
-//     e_i = fsub(fmul(fsub(px,ax), dy), fmul(fsub(py,ay), dx)) is bit-identical to edge_fn();
-//   * sgn = sign(area) (0 when a vertex is behind the camera: such a face takes the exact path);
-//   * il_i = 1 / |edge_i|^2, so the squared distance to an edge line is e_i^2 il_i (compared against uniform thresholds
-//     with >= 0.1 % margins; never used for output values);
-//   * iz_i = 1 / z_i for the fast inverse depth that orders visibility candidates.
+// The shared-memory record of the tile kernels' face walk: eight 16-byte groups (one LDS.128 each, broadcast to the warp)
+// holding per-face constants so that the per-(pixel, face) classification is ~35 branch-free instructions:
+//   * the three edge functions in affine form, already multiplied by sign(area):  t_i(p) = a_i p.x + b_i p.y + c_i  (2 FMAs);
+//     t_i > 0 for all i  <=>  strictly inside.  The affine value differs from PyTorch3D's own EdgeFunctionForward rounding
+//     by at most ~9 ulp of  m_i = |a_i| (1 + |x_anchor|) + |b_i| (1 + |y_anchor|);  eps = 1e-6 max_i m_i (16 ulp) is stored and
+//     every pair with min_i |t_i| < eps is re-classified with the bit-exact edge functions (about 1 pair in 500), so the
+//     strict-inside decision is PyTorch3D's bit for bit.  A face with a vertex behind the camera has eps = +inf;
+//   * il_i = 1 / |edge_i|^2: the squared distance to an edge line is t_i^2 il_i, compared against uniform thresholds with
+//     margins (2 % / 5 %) an order of magnitude above its relative error at those thresholds; never used for output values;
+//   * iz_i = 1 / z_i for the fast inverse depth that orders visibility candidates; the vertices, depths and area for the
+//     exact evaluation of the pairs that need it.
 struct __align__(16) FaceTile {
   float x0, y0, x1, y1;
   float x2, y2, xmin, xmax;
-  float ymin, ymax, sgn, area;
-  float d12x, d12y, d20x, d20y;
-  float d01x, d01y, il12, il20;
-  float il01, iz0, iz1, iz2;
+  float ymin, ymax, eps, area;
+  float a0, b0, c0, il12;   // t0 = sgn * EdgeFunction(p, v1, v2)
+  float a1, b1, c1, il20;   // t1 = sgn * EdgeFunction(p, v2, v0)
+  float a2, b2, c2, il01;   // t2 = sgn * EdgeFunction(p, v0, v1)
+  float iz0, iz1, iz2, sgn;
   float z0, z1, z2;
   int fid;
-};  // 112 B; the vertex ids (needed by the rare gradient path only) are re-read from the face table
+};  // 128 B; the vertex ids (needed by the rare gradient path only) are re-read from the face table
 
 __device__ __forceinline__ void stage_face(const harp_ctx& c, const float* ndc, int fid, float radius, FaceTile& f) {
   const int32_t* fv = c.faces + (size_t)fid * 3;
@@ -229,20 +233,30 @@ __device__ __forceinline__ void stage_face(const harp_ctx& c, const float* ndc, 
   float area = fadd(edge_fn(x2, y2, x0, y0, x1, y1), HARP_K_EPS);
   f.area = area;
   bool front = fminf(fminf(z0, z1), z2) > 0.f;
-  f.sgn = front ? (area > 0.f ? 1.f : -1.f) : 0.f;
-  f.d12x = fsub(x2, x1); f.d12y = fsub(y2, y1);  // e0 = EdgeFunction(p, v1, v2)
-  f.d20x = fsub(x0, x2); f.d20y = fsub(y0, y2);  // e1 = EdgeFunction(p, v2, v0)
-  f.d01x = fsub(x1, x0); f.d01y = fsub(y1, y0);  // e2 = EdgeFunction(p, v0, v1)
-  f.il12 = 1.f / (f.d12x * f.d12x + f.d12y * f.d12y);
-  f.il20 = 1.f / (f.d20x * f.d20x + f.d20y * f.d20y);
-  f.il01 = 1.f / (f.d01x * f.d01x + f.d01y * f.d01y);
+  float sg = front ? (area > 0.f ? 1.f : -1.f) : 0.f;
+  f.sgn = sg;
+  // edge deltas rounded exactly as edge_fn rounds them: EdgeFunction(p, A, B) = (p.x - A.x) dy - (p.y - A.y) dx
+  float d12x = fsub(x2, x1), d12y = fsub(y2, y1);  // anchor v1
+  float d20x = fsub(x0, x2), d20y = fsub(y0, y2);  // anchor v2
+  float d01x = fsub(x1, x0), d01y = fsub(y1, y0);  // anchor v0
+  f.a0 = sg * d12y; f.b0 = -sg * d12x; f.c0 = sg * (y1 * d12x - x1 * d12y);
+  f.a1 = sg * d20y; f.b1 = -sg * d20x; f.c1 = sg * (y2 * d20x - x2 * d20y);
+  f.a2 = sg * d01y; f.b2 = -sg * d01x; f.c2 = sg * (y0 * d01x - x0 * d01y);
+  float m0 = fabsf(d12y) * (1.f + fabsf(x1)) + fabsf(d12x) * (1.f + fabsf(y1));
+  float m1 = fabsf(d20y) * (1.f + fabsf(x2)) + fabsf(d20x) * (1.f + fabsf(y2));
+  float m2 = fabsf(d01y) * (1.f + fabsf(x0)) + fabsf(d01x) * (1.f + fabsf(y0));
+  f.eps = front ? 1e-6f * fmaxf(fmaxf(m0, m1), m2) : __int_as_float(0x7f800000);
+  f.il12 = 1.f / (d12x * d12x + d12y * d12y);
+  f.il20 = 1.f / (d20x * d20x + d20y * d20y);
+  f.il01 = 1.f / (d01x * d01x + d01y * d01y);
   f.iz0 = 1.f / z0; f.iz1 = 1.f / z1; f.iz2 = 1.f / z2;
 }
 
-// Branch-free classification of one (pixel, face) pair against a staged FaceTile; same decisions as classify_pair_vis
-// (the exactness argument is above classify_pair): returns PAIR_REJECT / PAIR_SATURATED / PAIR_FULL, or PAIR_EXACT for a
-// face with a vertex behind the camera.  `inside` = strict inside by the bit-exact edge functions; e[] are returned for
-// the fast inverse depth.  With NEED_DIST = false (visibility only) inside pairs report PAIR_SATURATED, all others REJECT.
+// Classification of one (pixel, face) pair against a staged FaceTile; same decisions as classify_pair_vis (the exactness
+// argument is above classify_pair): returns PAIR_REJECT / PAIR_SATURATED / PAIR_FULL, or PAIR_EXACT for a face with a
+// vertex behind the camera.  `inside` = strict inside as PyTorch3D's bit-exact edge functions decide it; t[] = signed edge
+// functions (for the fast inverse depth).  With NEED_DIST = false (visibility only) inside pairs report PAIR_SATURATED, all
+// others REJECT.  `far` must be >= 1.02 blur and `sat` >= 17.5 sigma (margins, see FaceTile).
 enum { PAIR_EXACT = 3 };
 
 __device__ __forceinline__ bool in_face_bbox(const FaceTile& f, float px, float py) {
@@ -250,25 +264,34 @@ __device__ __forceinline__ bool in_face_bbox(const FaceTile& f, float px, float 
 }
 
 template <bool NEED_DIST>
-__device__ __forceinline__ int classify_fast(const FaceTile& f, float px, float py, float far, float sat, bool inb, bool& inside,
-                                             float& e0, float& e1, float& e2) {
-  e0 = fsub(fmul(fsub(px, f.x1), f.d12y), fmul(fsub(py, f.y1), f.d12x));
-  e1 = fsub(fmul(fsub(px, f.x2), f.d20y), fmul(fsub(py, f.y2), f.d20x));
-  e2 = fsub(fmul(fsub(px, f.x0), f.d01y), fmul(fsub(py, f.y0), f.d01x));
-  float sg = f.sgn;
-  bool i0 = e0 * sg > 0.f, i1 = e1 * sg > 0.f, i2 = e2 * sg > 0.f;
+__device__ __forceinline__ int classify_from_t(const FaceTile& f, float t0, float t1, float t2, float far, float sat, bool inb,
+                                               bool& inside) {
+  bool i0 = t0 > 0.f, i1 = t1 > 0.f, i2 = t2 > 0.f;
   inside = inb & i0 & i1 & i2;
-  int cls;
-  if (NEED_DIST) {
-    float u0 = e0 * e0 * f.il12, u1 = e1 * e1 * f.il20, u2 = e2 * e2 * f.il01;
-    bool sat_all = (u0 >= sat) & (u1 >= sat) & (u2 >= sat);
-    bool far_any = (!i0 & (u0 >= far)) | (!i1 & (u1 >= far)) | (!i2 & (u2 >= far));
-    cls = inside ? (sat_all ? PAIR_SATURATED : PAIR_FULL) : (far_any ? PAIR_REJECT : PAIR_FULL);
-  } else {
-    cls = inside ? PAIR_SATURATED : PAIR_REJECT;
-  }
-  cls = sg == 0.f ? PAIR_EXACT : cls;
+  if (!NEED_DIST) return inside ? PAIR_SATURATED : PAIR_REJECT;
+  float u0 = t0 * t0 * f.il12, u1 = t1 * t1 * f.il20, u2 = t2 * t2 * f.il01;
+  bool sat_all = (u0 >= sat) & (u1 >= sat) & (u2 >= sat);
+  bool far_any = (!i0 & (u0 >= far)) | (!i1 & (u1 >= far)) | (!i2 & (u2 >= far));
+  int cls = inside ? (sat_all ? PAIR_SATURATED : PAIR_FULL) : (far_any ? PAIR_REJECT : PAIR_FULL);
   return inb ? cls : PAIR_REJECT;
+}
+
+template <bool NEED_DIST>
+__device__ __forceinline__ int classify_fast(const FaceTile& f, float px, float py, float far, float sat, bool inb, bool& inside,
+                                             float& t0, float& t1, float& t2) {
+  t0 = fmaf(f.a0, px, fmaf(f.b0, py, f.c0));
+  t1 = fmaf(f.a1, px, fmaf(f.b1, py, f.c1));
+  t2 = fmaf(f.a2, px, fmaf(f.b2, py, f.c2));
+  int cls = classify_from_t<NEED_DIST>(f, t0, t1, t2, far, sat, inb, inside);
+  bool ambiguous = inb & (fminf(fminf(fabsf(t0), fabsf(t1)), fabsf(t2)) < f.eps);
+  if (ambiguous) {  // rare: a sign within rounding distance of zero (or a face crossing the camera plane)
+    if (f.sgn == 0.f) return PAIR_EXACT;
+    t0 = f.sgn * edge_fn(px, py, f.x1, f.y1, f.x2, f.y2);
+    t1 = f.sgn * edge_fn(px, py, f.x2, f.y2, f.x0, f.y0);
+    t2 = f.sgn * edge_fn(px, py, f.x0, f.y0, f.x1, f.y1);
+    cls = classify_from_t<NEED_DIST>(f, t0, t1, t2, far, sat, inb, inside);
+  }
+  return cls;
 }
 
 // fast inverse depth of an inside pair: sum(w_i / z_i) / sum(w_i) with w_i ~ e_i (independent of the area)
