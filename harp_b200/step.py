@@ -27,7 +27,7 @@ class _Flat:
     """Several named parameters as views of one flat fp32 buffer (+ grad, Adam moments) so that one fused Adam launch
     updates the whole optimiser group."""
 
-    def __init__(self, named, device):
+    def __init__(self, named, device, grad_storage=None):
         self.names = [n for n, _ in named]
         sizes = [t.numel() for _, t in named]
         self.offsets = [0]
@@ -35,7 +35,7 @@ class _Flat:
             self.offsets.append(self.offsets[-1] + s)
         n = self.offsets[-1]
         self.data = torch.empty(n, device=device)
-        self.grad = torch.zeros(n, device=device)
+        self.grad = torch.zeros(n, device=device) if grad_storage is None else grad_storage[:n]
         self.m = torch.zeros(n, device=device)
         self.v = torch.zeros(n, device=device)
         self.p, self.g = {}, {}
@@ -68,8 +68,8 @@ def allreduce_shared(coarse, app, losses, world_size, group=None):
     as a single flat fp32 buffer (about 6.3 MB).  Loss values come back averaged over ranks."""
     import torch.distributed as dist
     a0 = coarse.offsets[coarse.names.index("verts_disps")]
-    a1 = app.offsets[app.names.index("amb_ratio")]
-    parts = [coarse.grad[a0:], app.grad[:3], app.grad[a1:], losses]
+    shared_app = [app.g[n].reshape(-1) for n in app.names if n != "light_positions"]
+    parts = [coarse.grad[a0:], app.g["light_positions"].reshape(-1)[:3]] + shared_app + [losses]
     flat = torch.cat([p.reshape(-1) for p in parts])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     o = 0
@@ -78,6 +78,16 @@ def allreduce_shared(coarse, app, losses, world_size, group=None):
         p.copy_(flat[o:o + n].view(p.shape))
         o += n
     losses /= world_size
+
+
+def allreduce_shared_inplace(gbuf, start, stop, loss_slice, world_size, group=None):
+    """The same exchange without staging copies, for gradients laid out in ONE buffer
+    `[coarse: per-frame rows | verts_disps | shape] [losses] [app: amb | texture | normal_map | light (T,3)]`:
+    a single in-place allreduce of `gbuf[start:stop]`, start = offset of verts_disps, stop = end of light row 0 — a span whose
+    length is the same on every rank however the frames are sharded (the rank-local light rows 1..T-1 lie behind it)."""
+    import torch.distributed as dist
+    dist.all_reduce(gbuf[start:stop], op=dist.ReduceOp.SUM, group=group)
+    gbuf[loss_slice] /= world_size
 
 
 class HarpFitter:
@@ -105,9 +115,18 @@ class HarpFitter:
         if self.opt_arm_pose:
             groups += [("wrist_pose", self.wrist), ("rot", f32(params["rot"]))]
         groups += [("verts_disps", f32(params["verts_disps"])), ("shape", f32(params["shape"]))]
-        self.coarse = _Flat(groups, dev)
-        self.app = _Flat([("light_positions", f32(params["light_positions"])), ("amb_ratio", f32(params["amb_ratio"]).view(1)),
-                          ("texture", f32(params["texture"])), ("normal_map", f32(params["normal_map"]))], dev)
+        # the rank-local light rows go last so that everything shared is one contiguous span (see allreduce_shared_inplace)
+        app_groups = [("amb_ratio", f32(params["amb_ratio"]).view(1)), ("texture", f32(params["texture"])),
+                      ("normal_map", f32(params["normal_map"])), ("light_positions", f32(params["light_positions"]))]
+        # all gradients and the loss vector live in one buffer: one fill per step, one in-place allreduce of its shared span
+        nc, na, nl = sum(t.numel() for _, t in groups), sum(t.numel() for _, t in app_groups), len(LOSS_NAMES)
+        self._gbuf = torch.zeros(nc + nl + na, device=dev)
+        self.coarse = _Flat(groups, dev, grad_storage=self._gbuf[:nc])
+        self.app = _Flat(app_groups, dev, grad_storage=self._gbuf[nc + nl:])
+        self.losses = self._gbuf[nc:nc + nl]
+        self._loss_slice = slice(nc, nc + nl)
+        self._shared_start = self.coarse.offsets[self.coarse.names.index("verts_disps")]
+        self._shared_stop = nc + nl + self.app.offsets[self.app.names.index("light_positions")] + 3
         self.rot, self.trans = f32(params["rot"]), f32(params["trans"])
         if self.opt_arm_pose:
             self.rot, self.wrist = self.coarse.p["rot"], self.coarse.p["wrist_pose"]
@@ -115,7 +134,6 @@ class HarpFitter:
         self.ref_verts = f32(ref_verts).view(-1, 3)
         self.uv_mask = f32(uv_mask)
         self.T = self.rot.shape[0]
-        self.losses = torch.zeros(len(LOSS_NAMES), device=dev)
         self._scratch = {}
         self.last = {}
 
@@ -170,9 +188,7 @@ class HarpFitter:
             fr = {k: v[frame_range[0]:frame_range[1]] for k, v in self.frames.items()}
         else:
             fr = {k: v.index_select(0, fid) for k, v in self.frames.items()}
-        self.losses.zero_()
-        self.coarse.grad.zero_()
-        self.app.grad.zero_()
+        self._gbuf.zero_()  # losses, coarse and appearance gradients
         # ---- forward geometry
         rot_b, pose_b = self.rot.index_select(0, fid), P["pose"].index_select(0, fid)
         if self.arm:  # SMPL-X joint order: global | 20 body joints | right wrist (joint 21) | jaw, eyes | left hand | right hand
@@ -311,7 +327,7 @@ class HarpFitter:
         return replay_and_exchange
 
     def _allreduce_shared(self):
-        allreduce_shared(self.coarse, self.app, self.losses, self.world_size, self.pg)
+        allreduce_shared_inplace(self._gbuf, self._shared_start, self._shared_stop, self._loss_slice, self.world_size, self.pg)
 
     def loss_dict(self):
         """One device->host read of the loss vector (the reference does >= 10 `.cpu()` syncs per iteration, 556-561)."""

@@ -38,6 +38,29 @@ def _worker(rank, world, port, T, V):
         assert torch.all(app.g["amb_ratio"] == 10 * tot) and torch.all(app.g["texture"] == 10 * tot)
         assert torch.all(app.g["normal_map"] == 10 * tot)
         assert torch.allclose(losses, torch.full_like(losses, tot / world))
+        # the copy-free variant HarpFitter uses: [coarse grads | losses | app grads with the rank-local light rows last] in
+        # one buffer, one in-place allreduce of the shared span, whose length must not depend on the shard size n
+        from harp_b200.step import allreduce_shared_inplace
+        nc, nl, na = n * 48 + V + 10, len(LOSS_NAMES), 1 + 2 * 8 * 8 * 3 + n * 3
+        gbuf = torch.zeros(nc + nl + na)
+        c2 = _Flat([("pose", torch.zeros(n, 45)), ("cam", torch.zeros(n, 3)), ("verts_disps", torch.zeros(V, 1)),
+                    ("shape", torch.zeros(10))], "cpu", grad_storage=gbuf[:nc])
+        a2 = _Flat([("amb_ratio", torch.zeros(1)), ("texture", torch.zeros(1, 8, 8, 3)), ("normal_map", torch.zeros(1, 8, 8, 3)),
+                    ("light_positions", torch.zeros(n, 3))], "cpu", grad_storage=gbuf[nc + nl:])
+        c2.grad.fill_(float(rank + 1))
+        a2.grad.fill_(float(10 * (rank + 1)))
+        gbuf[nc:nc + nl] = float(rank + 1)
+        start = c2.offsets[c2.names.index("verts_disps")]
+        stop = nc + nl + a2.offsets[a2.names.index("light_positions")] + 3
+        assert stop - start == V + 10 + nl + 1 + 2 * 8 * 8 * 3 + 3
+        allreduce_shared_inplace(gbuf, start, stop, slice(nc, nc + nl), world)
+        assert torch.all(c2.g["pose"] == rank + 1) and torch.all(c2.g["cam"] == rank + 1)
+        assert torch.all(c2.g["verts_disps"] == tot) and torch.all(c2.g["shape"] == tot)
+        assert torch.all(a2.g["light_positions"][0] == 10 * tot)
+        if n > 1:
+            assert torch.all(a2.g["light_positions"][1:] == 10 * (rank + 1))
+        assert torch.all(a2.g["amb_ratio"] == 10 * tot) and torch.all(a2.g["texture"] == 10 * tot) and torch.all(a2.g["normal_map"] == 10 * tot)
+        assert torch.allclose(gbuf[nc:nc + nl], torch.full((nl,), tot / world))
     finally:
         dist.destroy_process_group()
 
