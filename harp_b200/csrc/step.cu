@@ -129,6 +129,40 @@ __global__ void __launch_bounds__(TPB) mse_kernel(int64_t n, const float* __rest
   if (threadIdx.x == 0 && tot != 0.f) atomicAdd(loss, tot);
 }
 
+// Evaluation metrics of utils/eval_util.py:34-49 in one pass: sum |ref - pred| over all channels (l1_diff) and, per frame, the
+// intersection / union pixel counts of the masks thresholded at 0.5 (sil_iou).  One CTA per 1024 pixels of one frame.
+__global__ void __launch_bounds__(TPB) image_metrics_kernel(int S2, const float* __restrict__ ref_img, const float* __restrict__ pred_img,
+                                                             const float* __restrict__ ref_mask, const float* __restrict__ pred_mask,
+                                                             float* __restrict__ l1_sum, int32_t* __restrict__ inter,
+                                                             int32_t* __restrict__ uni) {
+  __shared__ float red[32];
+  __shared__ int cnt[2];
+  int b = blockIdx.y;
+  if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  float acc = 0.f;
+  int ni = 0, nu = 0;
+  for (int k = 0; k < 4; ++k) {
+    int p = (blockIdx.x * 4 + k) * TPB + threadIdx.x;
+    if (p >= S2) break;
+    size_t pix = (size_t)b * S2 + p;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) acc += fabsf(ref_img[pix * 3 + ch] - pred_img[pix * 3 + ch]);
+    bool r = ref_mask[pix] >= 0.5f, q = pred_mask[pix] >= 0.5f;
+    ni += (r && q) ? 1 : 0;
+    nu += (r || q) ? 1 : 0;
+  }
+  float tot = block_sum(acc, red);
+  if (ni) atomicAdd(&cnt[0], ni);
+  if (nu) atomicAdd(&cnt[1], nu);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (tot != 0.f) atomicAdd(l1_sum, tot);
+    if (cnt[0]) atomicAdd(inter + b, cnt[0]);
+    if (cnt[1]) atomicAdd(uni + b, cnt[1]);
+  }
+}
+
 struct AdamState {
   int step;
   float bc1, bc2_sqrt;
@@ -172,6 +206,17 @@ extern "C" int harp_adam_dev(float* param, const float* grad, float* exp_avg, fl
 extern "C" int harp_mse(int64_t n, const float* x, const float* target, float scale, float* loss, float* d_x, void* stream) {
   HARP_REQUIRE(n > 0 && x && target && loss, HARP_ERR_INVALID, "harp_mse: bad argument");
   mse_kernel<<<(int)((n + TPB - 1) / TPB), TPB, 0, (cudaStream_t)stream>>>(n, x, target, scale, loss, d_x);
+  HARP_LAUNCH_CHECK();
+  return HARP_OK;
+}
+
+extern "C" int harp_image_metrics(int B, int S, const float* ref_image, const float* pred_image, const float* ref_mask,
+                                  const float* pred_mask, float* l1_sum, int32_t* inter, int32_t* uni, void* stream) {
+  HARP_REQUIRE(B > 0 && S > 0 && ref_image && pred_image && ref_mask && pred_mask && l1_sum && inter && uni, HARP_ERR_INVALID,
+               "harp_image_metrics: bad argument");
+  int S2 = S * S;
+  dim3 grid((S2 + 4 * TPB - 1) / (4 * TPB), B);
+  image_metrics_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(S2, ref_image, pred_image, ref_mask, pred_mask, l1_sum, inter, uni);
   HARP_LAUNCH_CHECK();
   return HARP_OK;
 }

@@ -253,6 +253,14 @@ HARP_API int harp_texture_reg(harp_ctx*, int kind, const float* map, int H, int 
  * the fit's criterion on ManoLayer's mm output. */
 HARP_API int harp_mse(int64_t n, const float* x, const float* target, float scale, float* loss, float* d_x, void* stream);
 
+/* ---- evaluation-pass image metrics: l1_diff and sil_iou of utils/eval_util.py:34-49 ------------------------------------------
+ * ref_image / pred_image (B,S,S,3) in [0,1], ref_mask / pred_mask (B,S,S).  ACCUMULATES l1_sum += sum |ref - pred| (the caller
+ * divides by 3 B S^2 for torch.mean, 38-39) and, per frame, inter[b] / uni[b] += the pixel counts of (ref >= 0.5) AND / OR
+ * (pred >= 0.5) (42-47); the caller zeroes the three outputs first and forms mean_b inter / uni (48-49).
+ * (LPIPS and MS-SSIM, 51-60, need pretrained networks: out of scope like the VGG term.) */
+HARP_API int harp_image_metrics(int B, int S, const float* ref_image, const float* pred_image, const float* ref_mask,
+                       const float* pred_mask, float* l1_sum, int32_t* inter, int32_t* uni, void* stream);
+
 /* ---- uint8 frame ingest: load_img of utils/data_util.py:11-30 on the device ---------------------------------------------
  * rgb_u8 (B,S,S,3), mask_u8 (B,S,S) as decoded from the JPEG / PNG files -> y_true = rgb/255 (B,S,S,3) fp32,
  * y_sil = mask/255 (B,S,S), y_sil_eroded = cv2.erode(mask/255, ones(3,3), iterations=2) (border pixels ignore the outside).

@@ -517,3 +517,40 @@ def mano_fit(model, pred_vertices, epoch_coarse=500, epoch_fine=700, max_tries=4
     with torch.no_grad():
         verts, joints = mano_forward(model, torch.cat((rot, pose), 1), shape, trans)  # 120
     return dict(joints=joints, verts=verts, rot=rot.detach(), pose=pose.detach(), shape=shape.detach(), trans=trans.detach()), float(loss)
+
+
+# ------------------------------------------------------------------------------------------------- evaluation metrics, resume
+def fill_bg(img, mask):
+    """utils/eval_util.py:28-31."""
+    img = img * mask.unsqueeze(-1)
+    return img + (mask.unsqueeze(-1) - 1) * -1.0
+
+
+def l1_diff(ref_image, ref_mask, pred_image, pred_mask):
+    """utils/eval_util.py:34-39 (the masks are unused by the reference)."""
+    return torch.mean(torch.abs(ref_image - pred_image))
+
+
+def sil_iou(ref_masks, pred_masks):
+    """utils/eval_util.py:41-49.  PINNED with l1_diff / fill_bg: tests/golden/eval_metrics.npz (make_golden_misc.py)."""
+    r, p = ref_masks >= 0.5, pred_masks >= 0.5
+    return torch.mean(torch.logical_and(r, p).sum([1, 2]) / torch.logical_or(r, p).sum([1, 2]))
+
+
+def resume_params(params):
+    """optimize_sequence.py:366-389, statement by statement (inline code of main(); restated, parity unpinned)."""
+    params = dict(params)
+    temp_pose = params["pose"].detach().clone()
+    for i in range(params["pose"].shape[0] // 30 - 1):
+        for j in range(30):
+            temp_pose[i * 30 + j] = ((30 - j) * params["pose"][i * 30] + j * params["pose"][i * 30 + 30]) / 30.0
+    params["pose"] = temp_pose
+    params["trans"] = torch.zeros_like(params["trans"]) + params["trans"].mean(0)
+    params["rot"] = torch.zeros_like(params["rot"]) + params["rot"].mean(0)
+    if "wrist_pose" not in params:
+        params["wrist_pose"] = torch.zeros([params["pose"].shape[0], 3])
+    if "amb_ratio" not in params:
+        params["amb_ratio"] = torch.tensor(0.4)
+    if "normal_map" not in params:
+        params["normal_map"] = torch.tensor([0.0, 0.0, 1.0]).repeat(1, 512, 512, 1)
+    return params
