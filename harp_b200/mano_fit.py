@@ -117,3 +117,79 @@ def optimize_for_mano_param(pred_vertices, mano_layer, idx=0, vert_rgb=None, epo
     optimize_for_mano_param.last_loss = final_loss
     optimize_for_mano_param.last_tries = try_num + 1
     return {k: np.ascontiguousarray(v) for k, v in out.items()}
+
+
+# ---------------------------------------------------------------------------------------------------- sequence smoothing
+def _sum_sq(x):
+    return torch.sum(x ** 2)
+
+
+def _temporal_smoothness(x, n_frames):
+    """LossSmoothPoses(1, nFrames).poses (hand_utils.py:505-513): distance of every interior frame to the 3-frame mean,
+    the mean held constant (detached)."""
+    mean3 = x.detach().clone()
+    mean3[1:-1] = (mean3[1:-1] + mean3[:-2] + mean3[2:]) / 3
+    return _sum_sq(x[1:-1] - mean3[1:-1]) / (n_frames - 2)
+
+
+def _keypoint_distance(est, target, n_frames):
+    """LossKeypoints3D / LossAnchor .loss_func (hand_utils.py:472-496)."""
+    nj = min(est.shape[1], target.shape[1], 21)
+    return _sum_sq(est[:, :nj, :3] - target[:, :nj, :3]) / n_frames
+
+
+def optimize_smooth_seq(params_cpu, mano_layer, use_smplx_arm=False, nimble_hand=False, img_res=224, mano_j_regressor=None,
+                        total_iter_pose=1000, total_iter_cam=1000):
+    """Same call and return value as `metro_modifications/hand_utils.py:540` (MANO branch): temporal smoothing of the per-frame
+    fits.  Stage 1 optimises [rot, pose, shape, cam] with Adam(1e-3) on 1e-2 * (root-relative joints vs the input's) + 1e-1 *
+    (temporal smoothness of the root-relative joints) until the running loss stops falling by 1e-5 — a host decision every
+    iteration, as in the reference (592-595), so the loop is driven from Python: the LBS forward / backward of each iteration
+    are `harp_lbs_mano_fwd/bwd` (through `ManoLayer`'s autograd function), the joint-space losses are a few tiny torch ops on
+    (T,21,3) tensors.  Stage 2 optimises cam alone (Adam 1e-3 + ReduceLROnPlateau) on anchor + smoothness of the
+    camera-relative root; the joints are constant there, so no skinning is needed.  Returns CPU tensors like the reference."""
+    if use_smplx_arm or nimble_hand:
+        raise NotImplementedError("optimize_smooth_seq: only the MANO branch is built (SURVEY.md 8(f) row 4)")
+    dev = mano_layer.hc_coarse.device
+    p = {k: torch.as_tensor(v, dtype=torch.float32).to(dev).clone() for k, v in params_cpu.items()}
+    p["cam"] = p["cam"].unsqueeze(1)                                          # 547
+    T = p["pose"].shape[0]
+    target = p["joints"] - p["joints"][:, 0, :].unsqueeze(1)                  # 463-464
+    free = [p["rot"], p["pose"], p["shape"], p["cam"]]
+    for q in free:
+        q.requires_grad_(True)
+    skin = lambda: mano_layer(torch.cat((p["rot"], p["pose"]), 1), p["shape"], p["trans"])
+    opt = torch.optim.Adam(free, lr=1e-3)                                     # 585
+    running = 999999.0
+    for it in range(total_iter_pose):
+        _, joints = skin()
+        rel = joints - joints[:, 0, :].unsqueeze(1)
+        loss = 1e-2 * _keypoint_distance(rel, target, T) + 1e-1 * _temporal_smoothness(rel, T)   # 566-569 (smooth_body: weight 0)
+        now = loss.item()                                                    # the reference's per-iteration host sync
+        if it > 0 and running - now < 0.00001:
+            break
+        running = (running + now) / 2.0
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    with torch.no_grad():
+        verts, joints = skin()
+    p["joints"], p["verts"] = joints, verts                                  # 616-617
+    focal = 1000.0 * (img_res / 224.0)
+    root = joints[:, 0, :] / 1000.0
+
+    def camera_relative_root(cam):
+        t = torch.stack([cam[:, :, 1], cam[:, :, 2], 2 * focal / (img_res * cam[:, :, 0] + 1e-9)], dim=2)
+        return t + root   # (T,1,3) + (T,3) broadcasts to (T,T,3) exactly as at hand_utils.py:643 / 665
+
+    anchor = camera_relative_root(p["cam"]).detach()
+    opt = torch.optim.Adam([p["cam"]], lr=1e-3)                               # 651
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, patience=10)      # 652
+    for it in range(total_iter_cam):
+        crr = camera_relative_root(p["cam"])
+        loss = 1e-2 * _keypoint_distance(crr, anchor, T) + 1e-2 * _temporal_smoothness(crr, T)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        sched.step(loss)
+    p["cam"] = p["cam"].squeeze(1)
+    return {k: v.detach().cpu() for k, v in p.items()}

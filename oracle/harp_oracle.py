@@ -554,3 +554,71 @@ def resume_params(params):
     if "normal_map" not in params:
         params["normal_map"] = torch.tensor([0.0, 0.0, 1.0]).repeat(1, 512, 512, 1)
     return params
+
+
+# ------------------------------------------------------------------------------------------------- upstream smoothing
+def _smooth_l2(x):  # hand_utils.py:460
+    return torch.sum(x ** 2)
+
+
+def _smooth_poses(x, n_frames):  # LossSmoothPoses(1, nFrames).poses, hand_utils.py:505-513
+    interp = x.clone().detach()
+    interp[1:-1] = (interp[1:-1] + interp[:-2] + interp[2:]) / 3
+    return _smooth_l2(x[1:-1] - interp[1:-1]) / (n_frames - 2)
+
+
+def _kp3d(est, target, n_frames):  # LossKeypoints3D / LossAnchor .loss_func, hand_utils.py:472-496
+    nj = min([est.shape[1], target.shape[1], 21])
+    return _smooth_l2(est[:, :nj, :3] - target[:, :nj, :3]) / n_frames
+
+
+def smooth_seq(model, params_in, img_res=224, total_iter_pose=1000, total_iter_cam=1000, forward=None):
+    """metro_modifications/hand_utils.py:540-688 (optimize_smooth_seq, MANO branch) on CPU.
+    Stage 1 (562-603): Adam(lr 1e-3) over [rot, pose, shape, cam] of 1e-2 * k3d(root-relative joints vs the input's) +
+    1e-1 * temporal smoothness of the root-relative joints, stopped when the running loss stops falling by 1e-5 (592-595).
+    Stage 2 (620-683): Adam(lr 1e-3, ReduceLROnPlateau patience 10) over cam of anchor + smoothness of the camera-relative
+    root (1e-2 each).  Note the reference's broadcast at 643 / 665: camera_t is (T,1,3), the root joints (T,3), so
+    `cam_rel_root` is (T,T,3) — reproduced.  PINNED: tests/golden/smooth_seq_t12.npz (make_golden_smooth.py).
+    `forward(pose48, shape, trans) -> (verts_mm, joints_mm)` defaults to the oracle's mano_forward."""
+    fwd = forward or (lambda p, s, t: mano_forward(model, p, s, t))
+    p = {k: torch.as_tensor(v).float().clone() for k, v in params_in.items()}
+    p["cam"] = p["cam"].unsqueeze(1)  # 547
+    T = p["pose"].shape[0]
+    target = p["joints"] - p["joints"][:, 0, :].unsqueeze(1)  # LossKeypoints3D.__init__, 463-464
+    opt_params = [p["rot"], p["pose"], p["shape"], p["cam"]]
+    for q in opt_params:
+        q.requires_grad = True
+    opt = torch.optim.Adam(opt_params, lr=1e-3)
+    prev_loss = 999999.0
+    for it in range(total_iter_pose):
+        _, joints = fwd(torch.cat((p["rot"], p["pose"]), 1), p["shape"], p["trans"])
+        rel = joints - joints[:, 0, :].unsqueeze(1)
+        loss = _kp3d(rel, target, T) * 1e-2 + _smooth_poses(rel, T) * 1e-1  # smooth_body has weight 0 (568)
+        if it > 0 and prev_loss - loss.item() < 0.00001:
+            break
+        prev_loss = (prev_loss + loss.item()) / 2.0
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    with torch.no_grad():
+        verts, joints = fwd(torch.cat((p["rot"], p["pose"]), 1), p["shape"], p["trans"])
+    p["joints"], p["verts"] = joints, verts
+    focal = 1000.0 * (img_res / 224.0)
+    root = joints[:, 0, :] / 1000.0
+
+    def cam_rel(cam):
+        camera_t = torch.stack([cam[:, :, 1], cam[:, :, 2], 2 * focal / (img_res * cam[:, :, 0] + 1e-9)], dim=2)
+        return camera_t + root  # (T,1,3) + (T,3) -> (T,T,3)
+
+    anchor = cam_rel(p["cam"]).detach()
+    opt = torch.optim.Adam([p["cam"]], lr=1e-3)
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, patience=10)
+    for it in range(total_iter_cam):
+        crr = cam_rel(p["cam"])
+        loss = _kp3d(crr, anchor, T) * 1e-2 + _smooth_poses(crr, T) * 1e-2
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        sched.step(loss)
+    p["cam"] = p["cam"].squeeze(1)
+    return {k: v.detach() for k, v in p.items()}
