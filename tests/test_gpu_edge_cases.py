@@ -129,3 +129,43 @@ def test_fused_step_stage_gating(stage):
             assert float(mine.abs().max()) == 0.0, k
         else:
             assert rel_l2(mine, gg) < t, (k, rel_l2(mine, gg))
+
+
+def test_abi_error_behaviour_on_the_device():
+    """Errors are negative return codes with a message (harp_last_error), never a crash or a silent fallback: missing
+    reservation, an unsupported mode, a null tensor, a CPU tensor, a context without a skinning model / UV tables."""
+    import ctypes as C
+    from harp_b200 import _lib, synth
+    from harp_b200.ops import HarpContext
+    L = _lib.lib()
+    tmpl = synth.load_template("hand")
+    pack = synth.make_mano_pack(seed=0, template=tmpl)
+    hc = HarpContext(pack["th_faces"], subdivide=True, faces_uvs=tmpl["faces_uvs"], verts_uvs=tmpl["verts_uvs"], mano=pack)
+    B, S = 2, 64
+    verts = torch.zeros(B, hc.V, 3, device="cuda")
+    R = torch.eye(3, device="cuda").repeat(B, 1, 1).contiguous()
+    T = torch.tensor([[0.0, 0.0, 1.0]], device="cuda").repeat(B, 1).contiguous()
+    alpha = torch.empty(B, S, S, device="cuda")
+    st = _lib.stream()
+    f = C.c_float
+    args = lambda mode, a: (hc.h, mode, B, S, f(300.0), f(1e-7), 50, _lib.ptr(verts), _lib.ptr(R), _lib.ptr(T), a, None, f(0.0), None,
+                            None, None, None, st)
+    rc = L.harp_silhouette(*args(0, _lib.ptr(alpha)))          # no harp_ctx_reserve(B, S) yet
+    assert rc < 0 and b"reserve" in L.harp_last_error()
+    hc.reserve(B, S)
+    assert L.harp_silhouette(*args(0, _lib.ptr(alpha))) == 0
+    rc = L.harp_silhouette(*args(7, _lib.ptr(alpha)))
+    assert rc < 0 and b"mode" in L.harp_last_error()
+    rc = L.harp_silhouette(*args(0, None))
+    assert rc < 0 and b"alpha" in L.harp_last_error()
+    with pytest.raises(_lib.HarpError):
+        _lib.ptr(torch.zeros(3))                               # CPU tensor: there is no CPU path
+    with pytest.raises(_lib.HarpError):
+        _lib.check(rc)
+    bare = HarpContext(pack["th_faces"], subdivide=False)      # topology only: no skinning model, no UVs
+    out_v, out_j = torch.empty(B, 778, 3, device="cuda"), torch.empty(B, 21, 3, device="cuda")
+    z = torch.zeros(B, 48, device="cuda")
+    rc = L.harp_lbs_mano_fwd(bare.h, B, _lib.ptr(z), _lib.ptr(z[:, :10].contiguous()), 0, _lib.ptr(z[:, :3].contiguous()),
+                             _lib.ptr(out_v), _lib.ptr(out_j), st)
+    assert rc < 0 and b"MANO" in L.harp_last_error()
+    torch.cuda.synchronize()
