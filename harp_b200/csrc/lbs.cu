@@ -10,7 +10,7 @@
 
 namespace {
 
-constexpr int LBS_THREADS = 512;
+constexpr int LBS_THREADS = 1024;  // one vertex per thread for MANO (778); 64 registers x 1024 threads = one SM's register file
 constexpr int MAXJ = HARP_MAX_JOINTS;      // 64
 constexpr int MAXS = HARP_MAX_SHAPE;       // 32
 constexpr int MAXPB = (MAXJ - 1) * 9;      // pose-blendshape basis size
