@@ -63,3 +63,43 @@ def render_image_with_RT(mesh, light_t, light_r, cam_t, cam_r, batch_size, rende
                    T=light_t.to(device), R=light_r.to(device), cam_T=cam_t.to(device), cam_R=cam_r.to(device), materials=materials,
                    image_size=torch.tensor([(img_size, img_size)]))
     return out[:, :, :, 3] if silhouette else out[:, :, :, 0:3]
+
+
+def _rotate_axis_angle(points, degrees, axis):
+    """pytorch3d.transforms.RotateAxisAngle(degrees, axis).transform_points: row vectors times the transposed rotation."""
+    a = torch.tensor(degrees / 180.0 * 3.141592653589793, dtype=points.dtype, device=points.device)
+    c, s, o, z = torch.cos(a), torch.sin(a), torch.ones_like(a), torch.zeros_like(a)
+    R = {"X": [o, z, z, z, c, -s, z, s, c], "Y": [c, z, s, z, o, z, -s, z, c], "Z": [c, -s, z, s, c, z, z, z, o]}[axis]
+    M = torch.stack(R).view(3, 3).t()
+    return points @ M
+
+
+def render_360(params, fid, renderer, img_size, focal_length, mano_layer, configs, render_normal=False, verts_textures=True,
+               mesh_subdivider=None, global_pose=False, global_betas=True, device="cuda", save_img_dir=None, use_arm=False):
+    """Turntable of `utils/visualize.py:145-199`: 36 cumulative 10-degree turns about Y, then 36 about X, of the posed mesh around
+    its centroid, each rendered with `renderer` (the phong or normal renderer of get_renderers).  Returns the 72 frames of the
+    first sample as a uint8 tensor (72,S,S,3) on the device; with `save_img_dir` they are also written as the reference names
+    them (`render_360[_normal]/%04d.jpg`, `h_%04d.jpg`; the animated GIF is left to the caller)."""
+    joints, hand_verts, faces, textures = prepare_mesh(params, fid, mano_layer, verts_textures, mesh_subdivider, global_pose,
+                                                       configs=configs, device=device, use_arm=use_arm)
+    cam = params["cam"][fid.to(params["cam"].device)]
+    B = fid.shape[0]
+    materials_properties = prepare_materials(params, B, device=device)
+    center = torch.mean(hand_verts, dim=1, keepdim=True)
+    hand_verts = hand_verts.detach()
+    frames = []
+    for axis in ("Y", "X"):
+        for _ in range(36):
+            hand_verts = _rotate_axis_angle(hand_verts - center, 10.0, axis) + center
+            img = render_image(Meshes(hand_verts, faces, textures), cam, B, renderer, img_size, focal_length,
+                               materials_properties=materials_properties, device=device)
+            frames.append((img.detach()[0].clip(0, 1) * 255).to(torch.uint8))  # astype(np.uint8): truncation
+    frames = torch.stack(frames)
+    if save_img_dir is not None:
+        import os
+        from PIL import Image
+        out_dir = os.path.join(save_img_dir, "render_360_normal" if render_normal else "render_360")
+        os.makedirs(out_dir, exist_ok=True)
+        for i, f in enumerate(frames.cpu().numpy()):
+            Image.fromarray(f).save(os.path.join(out_dir, ("%04d.jpg" % i) if i < 36 else ("h_%04d.jpg" % (i - 36))))
+    return frames

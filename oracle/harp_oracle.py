@@ -622,3 +622,16 @@ def smooth_seq(model, params_in, img_res=224, total_iter_pose=1000, total_iter_c
         sched.step(loss)
     p["cam"] = p["cam"].squeeze(1)
     return {k: v.detach() for k, v in p.items()}
+
+
+# ------------------------------------------------------------------------------------------------- turntable
+def turntable_verts(verts):
+    """utils/visualize.py:162-196: the 72 vertex sets of render_360 — 36 cumulative 10-degree turns about Y, then 36 about X,
+    around the centroid of the ORIGINAL mesh, with pytorch3d.transforms.RotateAxisAngle (restated in the shim)."""
+    center = torch.mean(verts, dim=1, keepdim=True)  # 160
+    out = []
+    for axis in ("Y", "X"):
+        for _ in range(36):
+            verts = p3d.RotateAxisAngle(10, axis).transform_points(verts - center) + center
+            out.append(verts)
+    return out

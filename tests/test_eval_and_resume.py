@@ -48,3 +48,34 @@ def test_device_metrics_match_reference_golden():
     ma, mb = torch.rand(64, 512, 512, device="cuda", generator=gen), torch.rand(64, 512, 512, device="cuda", generator=gen)
     assert abs(float(eval_util.l1_diff(a, ma, b, mb)) - float((a - b).abs().double().mean())) < 1e-6
     assert abs(float(eval_util.sil_iou(ma, mb)) - float(O.sil_iou(ma.cpu(), mb.cpu()))) < 1e-6
+
+
+@pytest.mark.gpu
+def test_turntable_frames_match_oracle():
+    """render_360 (utils/visualize.py:145-199): the rotated vertex sets and a sample of the 72 frames against the oracle."""
+    from harp_b200 import synth, visualize, renderer_helper
+    from harp_b200.manolayer import ManoLayer
+    from util import golden_case
+    g = load_golden("c2_full_128_sub")
+    model, topo, params, batch, cfg = golden_case(g)
+    tmpl = synth.load_template("hand")
+    pack = synth.make_mano_pack(seed=0, template=tmpl)
+    layer = ManoLayer(pack, tmpl["faces_uvs"], tmpl["verts_uvs"])
+    S, focal = 64, 1000.0 * 64 / 224.0
+    light = params["light_position"][None]
+    p = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in params.items()}
+    p.update(faces_uvs=torch.tensor(tmpl["faces_uvs"]).long()[None].cuda(), verts_uvs=torch.tensor(tmpl["verts_uvs"])[None].cuda(),
+             light_positions=light.cuda())
+    fid = torch.arange(1)
+    phong, _, _ = renderer_helper.get_renderers(image_size=S, light_posi=light.cuda(), device="cuda")
+    configs = {"model_type": "harp", "img_size": S, "focal_length": focal, "use_arm": False}
+    frames = visualize.render_360(p, fid, phong, S, focal, layer, configs, verts_textures=False, mesh_subdivider=object(), device="cuda")
+    assert frames.shape == (72, S, S, 3) and frames.dtype == torch.uint8
+    vm, _ = O.mano_forward(model, torch.cat((params["rot"][:1], params["pose"][:1]), 1), params["shape"][None], params["trans"][:1])
+    verts = O.build_mesh(vm / 1000.0, topo, params["verts_disps"])
+    tv = O.turntable_verts(verts)
+    for i in (0, 17, 35, 36, 53, 71):
+        ref = O.render_phong(tv[i], topo, params["cam"][:1], light, params["texture"], params["normal_map"], focal, S)
+        ref8 = (ref[0, ..., :3].clip(0, 1) * 255).to(torch.uint8)
+        d = (frames[i].cpu().int() - ref8.int()).abs().amax(-1)
+        assert float((d <= 1).double().mean()) >= 0.99, (i, float((d <= 1).double().mean()))   # hard visibility at silhouette pixels
