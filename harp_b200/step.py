@@ -314,7 +314,11 @@ class HarpFitter:
         if keep_profile:
             self.hc.profile_read()  # drop the warm-up event pairs; the captured step re-creates one pair per kernel
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # captured on a high-priority stream: kernel nodes inherit it, so the critical path (camera bins -> pixel pass ->
+        # shading -> geometry backward) is scheduled ahead of the two side branches (default / least priority)
+        if getattr(self, "_capture_stream", None) is None:
+            self._capture_stream = torch.cuda.Stream(device=self.hc.device, priority=-1)
+        with torch.cuda.graph(graph, stream=self._capture_stream):
             self.step(fid, off_albedo, off_normal, update=not multi, exchange=False, **kw)
         self._graph = graph
         if not multi:
