@@ -351,10 +351,12 @@ extern "C" int harp_lbs_bwd(harp_ctx* c, int B, const float* pose, const float* 
   HARP_REQUIRE(c && B > 0 && pose && shape && d_verts0 && d_pose && d_shape, HARP_ERR_INVALID, "harp_lbs_bwd: null argument");
   HARP_REQUIRE(c->has_model, HARP_ERR_NO_MODEL, "harp_lbs_bwd: ctx has no skinning model");
   size_t dyn = lbs_bwd_smem(c);
-  static size_t configured = 0;
-  if (dyn > configured) {
+  static size_t configured[64] = {};  // the attribute is per device
+  int dev = 0;
+  HARP_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || dyn > configured[dev]) {
     HARP_CHECK_CUDA(cudaFuncSetAttribute(lbs_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    configured = dyn;
+    if (dev >= 0 && dev < 64) configured[dev] = dyn;
   }
   harp_prof_begin(c, 3, (cudaStream_t)stream);
   lbs_bwd_kernel<<<B, LBS_THREADS, dyn, (cudaStream_t)stream>>>(*c, pose, shape, shape_shared, d_verts0, d_joints, d_pose,

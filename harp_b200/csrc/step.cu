@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(TPB) image_metrics_kernel(int S2, const float*
 struct AdamState {
   int step;
   float bc1, bc2_sqrt;
+  float lr;  // read only when the call passes lr < 0 (a 3-word state stays valid for lr >= 0)
 };
 
 __global__ void adam_tick_kernel(AdamState* st, float b1, float b2) {
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(TPB) adam_dev_kernel(float* __restrict__ p, co
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float bc1 = st->bc1, bc2s = st->bc2_sqrt;
+  if (lr < 0.f) lr = st->lr;  // learning rate on the device: a scheduler can change it under a captured graph
   float gi = g[i];
   float mi = m[i] + (1.f - b1) * (gi - m[i]);
   float vi = b2 * v[i] + (1.f - b2) * gi * gi;

@@ -44,14 +44,18 @@ class _Flat:
             self.p[name] = self.data[a:b].view(t.shape)
             self.g[name] = self.grad[a:b].view(t.shape)
         # {int32 step, float bias_correction1, float sqrt(bias_correction2)} on the device: the update is graph-capturable
-        self.state = torch.zeros(3, dtype=torch.int32, device=device)
+        # and the learning rate, so a scheduler can change it under a captured graph
+        self.state = torch.zeros(4, dtype=torch.int32, device=device)
 
     @property
     def steps(self):
         return int(self.state[0].item())
 
-    def adam(self, lr):
-        check(_lib.lib().harp_adam_dev(ptr(self.data), ptr(self.grad), ptr(self.m), ptr(self.v), self.data.numel(), float(lr),
+    def set_lr(self, lr):
+        self.state[3:4].view(torch.float32).fill_(float(lr))
+
+    def adam(self):
+        check(_lib.lib().harp_adam_dev(ptr(self.data), ptr(self.grad), ptr(self.m), ptr(self.v), self.data.numel(), -1.0,
                                        0.9, 0.999, 1e-8, self.state.data_ptr(), stream()))
 
 
@@ -100,7 +104,7 @@ class HarpFitter:
                  lr_coarse=1e-3, lr_app=1e-2, world_size=1, process_group=None, opt_arm_pose=False):
         dev = hc.device
         self.hc, self.S, self.focal, self.self_shadow = hc, int(img_size), float(focal_length), bool(self_shadow)
-        self.lr_coarse, self.lr_app = lr_coarse, lr_app
+        self._lr = {"coarse": float(lr_coarse), "app": float(lr_app)}
         self.faces_per_pixel = 50  # silhouette rasteriser's K (optimize_sequence.py:427); settable for tests of the top-K path
         self.world_size, self.pg = int(world_size), process_group
         f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
@@ -127,6 +131,8 @@ class HarpFitter:
         self._loss_slice = slice(nc, nc + nl)
         self._shared_start = self.coarse.offsets[self.coarse.names.index("verts_disps")]
         self._shared_stop = nc + nl + self.app.offsets[self.app.names.index("light_positions")] + 3
+        self.coarse.set_lr(self._lr["coarse"])
+        self.app.set_lr(self._lr["app"])
         self.rot, self.trans = f32(params["rot"]), f32(params["trans"])
         if self.opt_arm_pose:
             self.rot, self.wrist = self.coarse.p["rot"], self.coarse.p["wrist_pose"]
@@ -136,6 +142,26 @@ class HarpFitter:
         self.T = self.rot.shape[0]
         self._scratch = {}
         self.last = {}
+
+    # learning rates live on the device (read by harp_adam_dev), so assigning them also works under a captured graph —
+    # what the reference's two ReduceLROnPlateau schedulers need (optimize_sequence.py:312-321, 601-603)
+    @property
+    def lr_coarse(self):
+        return self._lr["coarse"]
+
+    @lr_coarse.setter
+    def lr_coarse(self, v):
+        self._lr["coarse"] = float(v)
+        self.coarse.set_lr(v)
+
+    @property
+    def lr_app(self):
+        return self._lr["app"]
+
+    @lr_app.setter
+    def lr_app(self, v):
+        self._lr["app"] = float(v)
+        self.app.set_lr(v)
 
     # -- helpers --------------------------------------------------------------------------------------------------------
     def params(self):
@@ -290,9 +316,9 @@ class HarpFitter:
 
     def _update(self, stage):
         if stage in ("coarse", "both"):
-            self.coarse.adam(self.lr_coarse)
+            self.coarse.adam()
         if stage in ("both", "app"):
-            self.app.adam(self.lr_app)
+            self.app.adam()
 
     # -- CUDA-graph replay ------------------------------------------------------------------------------------------------
     def capture(self, fid, off_albedo, off_normal, stage="both", frame_range=None, batch=None, warmup=2, keep_profile=False,

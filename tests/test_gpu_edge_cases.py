@@ -169,3 +169,28 @@ def test_abi_error_behaviour_on_the_device():
                              _lib.ptr(out_v), _lib.ptr(out_j), st)
     assert rc < 0 and b"MANO" in L.harp_last_error()
     torch.cuda.synchronize()
+
+
+def test_learning_rate_change_under_a_captured_graph():
+    """The reference steps two ReduceLROnPlateau schedulers (optimize_sequence.py:312-321, 601-603).  The learning rates live
+    on the device, so assigning `lr_coarse` / `lr_app` changes the update of an already captured step."""
+    g = load_golden("c2_full_128_sub")
+    case = golden_case(g)
+    model, topo, params, batch, cfg = case
+    ft, hc = _fitter_from_case(case)
+    B = params["pose"].shape[0]
+    fid = torch.arange(B, device="cuda")
+    oa, on = batch["off_albedo"].cuda().int().contiguous(), batch["off_normal"].cuda().int().contiguous()
+    replay = ft.capture(fid, oa, on, stage="both", warmup=1)
+    replay()
+    torch.cuda.synchronize()
+    before_c, before_a = ft.coarse.data.clone(), ft.app.data.clone()
+    ft.lr_coarse, ft.lr_app = 0.0, 0.0            # a scheduler driving the rates to zero: parameters must freeze
+    replay()
+    torch.cuda.synchronize()
+    assert torch.equal(ft.coarse.data, before_c) and torch.equal(ft.app.data, before_a)
+    ft.lr_coarse, ft.lr_app = 1e-3, 1e-2
+    replay()
+    torch.cuda.synchronize()
+    assert float((ft.coarse.data - before_c).abs().max()) > 1e-5 and float((ft.app.data - before_a).abs().max()) > 1e-4
+    assert ft.lr_coarse == 1e-3 and ft.lr_app == 1e-2
