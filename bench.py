@@ -188,7 +188,9 @@ def main():
         # replay re-records them and the kernel durations are read from the timed region itself
         hc.profile(True)
         try:
-            replay = ft.capture(fid, oa, on, stage="both", frame_range=(0, B), keep_profile=True)
+            overlapped = world > 1 and os.environ.get("HARP_EXCHANGE", "serial") == "overlap"
+            cap = ft.capture_overlapped if overlapped else ft.capture
+            replay = cap(fid, oa, on, stage="both", frame_range=(0, B), keep_profile=True)
             run_step = replay
         except Exception as e:  # pragma: no cover - falls back to eager launches
             print(f"[bench] CUDA graph capture failed ({e}); timing eager launches", file=sys.stderr)
@@ -296,7 +298,8 @@ def main():
 
         def run_f32(s):
             if use_graph:
-                return ft.capture(fid, oa, on, stage="both", batch=s, warmup=1)
+                return (ft.capture_overlapped if world > 1 and os.environ.get("HARP_EXCHANGE", "serial") == "overlap" else ft.capture)(
+                    fid, oa, on, stage="both", batch=s, warmup=1)
             return lambda: ft.step(fid, oa, on, stage="both", update=True, batch=s)
 
         e2e_s = e2e_leg(host, stage_f32, run_f32, k_e2e)
@@ -309,7 +312,8 @@ def main():
 
         def run_u8(s):
             if use_graph:
-                return ft.capture(fid, oa, on, stage="both", batch_u8=s, warmup=1)
+                return (ft.capture_overlapped if world > 1 and os.environ.get("HARP_EXCHANGE", "serial") == "overlap" else ft.capture)(
+                    fid, oa, on, stage="both", batch_u8=s, warmup=1)
             return lambda: ft.step(fid, oa, on, stage="both", update=True, batch_u8=s)
 
         e2e_u8_s = e2e_leg(host_u8, stage_u8, run_u8, k_e2e)

@@ -187,7 +187,7 @@ class HarpFitter:
 
     # -- one minibatch ----------------------------------------------------------------------------------------------------
     def step(self, fid, off_albedo, off_normal, stage="both", update=True, batch=None, frame_range=None, exchange=True,
-             batch_u8=None):
+             batch_u8=None, after_render=None):
         """fid: (B,) long device tensor of frame ids owned by this rank.  stage: 'coarse' | 'both' | 'app'
         (`optimize_sequence.py:507-515`).  batch: optional dict overriding self.frames rows (host->device ingest path).
         frame_range=(a,b): promise that fid == arange(a,b), so image rows are used in place instead of gathered.
@@ -286,6 +286,8 @@ class HarpFitter:
                                          ptr(self.coarse.g["verts_disps"].view(-1)), ss))
         check(L.harp_render_fused(hc.h, B, S, focal, C.byref(ra), st))
         main.wait_stream(side)
+        if after_render is not None:  # texture / normal-map gradients are final here (capture() splits the step at this point)
+            after_render()
         # ---- backward through the small per-frame chain, then geometry
         if coarse_on or app_on:
             check(L.harp_frame_glue_bwd(hc.h, B, S, focal, ptr(P["cam"]), ptr(fid), ptr(light_shared), ptr(A["amb_ratio"]),
@@ -355,6 +357,81 @@ class HarpFitter:
             self._allreduce_shared()
             self._update(stage)
         return replay_and_exchange
+
+    def capture_overlapped(self, fid, off_albedo, off_normal, stage="both", frame_range=None, batch=None, warmup=2, batch_u8=None,
+                           keep_profile=False):
+        """Multi-GPU variant of capture(): the step is recorded as TWO graphs split where the texture / normal-map gradients
+        (99.8 % of the exchanged bytes) are final, so their allreduce runs on a communication stream underneath the geometry
+        backward (frame glue, mesh build, LBS) of the second graph; the 12 KB of coarse shared gradients, losses, amb and
+        light follow in two small allreduces.  Same result as capture() up to the summation order of the collectives."""
+        import torch.distributed as dist
+        assert self.world_size > 1
+        kw = dict(stage=stage, frame_range=frame_range, batch=batch, batch_u8=batch_u8)
+        if not keep_profile:
+            self.hc.profile(False)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=self.hc.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(fid, off_albedo, off_normal, update=True, **kw)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        if keep_profile:
+            self.hc.profile_read()
+        if getattr(self, "_capture_stream", None) is None:
+            self._capture_stream = torch.cuda.Stream(device=self.hc.device, priority=-1)
+        cap = self._capture_stream
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        cap.wait_stream(cur)
+        state = {"open": None}
+        try:
+            with torch.cuda.stream(cap):
+                g1.capture_begin()
+                state["open"] = g1
+
+                def split():
+                    g1.capture_end()
+                    state["open"] = None
+                    g2.capture_begin(pool=g1.pool())
+                    state["open"] = g2
+                self.step(fid, off_albedo, off_normal, update=False, exchange=False, after_render=split, **kw)
+                g2.capture_end()
+                state["open"] = None
+        except Exception:
+            if state["open"] is not None:
+                try:
+                    with torch.cuda.stream(cap):
+                        state["open"].capture_end()
+                except Exception:
+                    pass
+            torch.cuda.synchronize()
+            raise
+        cur.wait_stream(cap)
+        torch.cuda.synchronize()
+        self._graph = (g1, g2)
+        nc, nl = self.coarse.grad.numel(), len(LOSS_NAMES)
+        app0 = nc + nl
+        o = dict(zip(self.app.names, self.app.offsets))
+        big = self._gbuf[app0 + o["texture"]:app0 + o["light_positions"]]          # texture | normal_map
+        small = self._gbuf[self._shared_start:app0 + o["texture"]]                 # verts_disps | shape | losses | amb
+        light0 = self._gbuf[app0 + o["light_positions"]:app0 + o["light_positions"] + 3]
+        comm = torch.cuda.Stream(device=self.hc.device)
+        R, pg = self.world_size, self.pg
+
+        def replay():
+            main = torch.cuda.current_stream()
+            g1.replay()
+            comm.wait_stream(main)
+            with torch.cuda.stream(comm):
+                dist.all_reduce(big, op=dist.ReduceOp.SUM, group=pg)
+            g2.replay()
+            dist.all_reduce(small, op=dist.ReduceOp.SUM, group=pg)
+            dist.all_reduce(light0, op=dist.ReduceOp.SUM, group=pg)
+            main.wait_stream(comm)
+            self._gbuf[self._loss_slice] /= R
+            self._update(stage)
+        return replay
 
     def _allreduce_shared(self):
         allreduce_shared_inplace(self._gbuf, self._shared_start, self._shared_stop, self._loss_slice, self.world_size, self.pg)
