@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libharpb200.so")
+LIB_PATH = os.environ.get("HARP_LIB") or os.path.join(_HERE, "libharpb200.so")  # HARP_LIB: tuning builds (tools/build_variants.sh)
 
 c_float_p = C.POINTER(C.c_float)
 c_int32_p = C.POINTER(C.c_int32)

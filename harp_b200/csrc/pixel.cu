@@ -19,9 +19,21 @@ int harp_sil_topk(harp_ctx* c, int mode, int S, int K, float sigma, float blur, 
 
 namespace {
 
-constexpr int CHUNK = 64;
+#ifndef HARP_PV_CHUNK
+#define HARP_PV_CHUNK 64
+#endif
+#ifndef HARP_PV_QCAP
+#define HARP_PV_QCAP 352
+#endif
+#ifndef HARP_PV_MINCTAS
+#define HARP_PV_MINCTAS 16
+#endif
+#ifndef HARP_SHADE_GRID
+#define HARP_SHADE_GRID 96
+#endif
+constexpr int CHUNK = HARP_PV_CHUNK;  // faces staged per shared-memory round (tuning knobs: tools/build_variants.sh)
 constexpr int NT = HARP_TILE * HARP_TILE;
-constexpr int QCAP = 352;  // with the 128-byte face records: 13.5 KB per CTA -> 16 CTAs per SM
+constexpr int QCAP = HARP_PV_QCAP;  // 352 with the 128-byte face records: 13.5 KB per CTA -> 16 CTAs per SM
 
 struct VisArgs {
   int S, K;
@@ -55,7 +67,7 @@ __device__ __forceinline__ void block_sum2(float& u, float& v, float* red) {
 // SIL_BWD: accumulate the silhouette L1 loss and its gradient (COARSE_OPT stages); PHOTO: accumulate the photometric loss
 // of background pixels (APP_OPT stages; hit pixels are handled by the deferred shading kernel).
 template <bool SIL_BWD, bool PHOTO>
-__global__ void __launch_bounds__(NT, 16) pixel_vis_kernel(harp_ctx c, VisArgs a) {
+__global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) pixel_vis_kernel(harp_ctx c, VisArgs a) {
   __shared__ FaceTile faces[CHUNK];
   __shared__ float red[32];
   __shared__ unsigned char q_pix[QCAP], q_face[QCAP], q_edge[QCAP];
@@ -393,7 +405,7 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
     a.d_light_R = r->grads.d_light_R; a.d_light_T = r->grads.d_light_T; a.d_light_pos = r->grads.d_light_pos;
     a.d_amb = r->grads.d_amb; a.d_texture = c->d_tex4; a.d_normal_map = c->d_tex4 + ntex * 4; a.d_light_zbuf = c->d_light_zbuf;
   }
-  dim3 sgrid(96, B);
+  dim3 sgrid(HARP_SHADE_GRID, B);
   harp_prof_begin(c, 1, st);
   if (photo_bwd) shade_deferred_kernel<2><<<sgrid, 128, 0, st>>>(*c, a, reinterpret_cast<const int2*>(c->hit_list), c->hit_count);
   else shade_deferred_kernel<0><<<sgrid, 128, 0, st>>>(*c, a, reinterpret_cast<const int2*>(c->hit_list), c->hit_count);
