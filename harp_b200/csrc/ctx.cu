@@ -275,8 +275,12 @@ extern "C" int harp_ctx_reserve(harp_ctx* c, int max_batch, int img_size) {
   int tiles = (S / 8) * (S / 8);
   size_t nv = (size_t)B * c->V * 3 * sizeof(float);
   size_t npx = (size_t)B * S * S;
-  // a face overlaps ~1-4 8x8 tiles at the reference's scales; 24 per face leaves a wide margin (checked: counters[1])
-  c->bin_cap = (int64_t)c->F * 24;
+  // a face overlaps ~1-8 8x8 tiles at the reference's scales (bbox pairs measured on the synthetic hand: 0.2-0.35 x 24 F at
+  // 512^2); the capacity per face grows with the tile count so that a hand zoomed far beyond the image, or crossing the
+  // camera plane (huge projected faces: 3 x 24 F at 512^2, 13 x at 1024^2), still fits: 24 F up to 256^2, 64 F at 512^2,
+  // 256 F from 1024^2 (0.2 / 0.5 GB for both views at 64 x 512^2 / 32 x 1024^2).  Overflow is counted (counters[1]), never silent.
+  int per_face = std::min(256, std::max(24, tiles / 64));
+  c->bin_cap = (int64_t)c->F * per_face;
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->ndc_cam, nv));
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->ndc_light, nv));
   size_t nv4 = (size_t)B * c->V * 4 * sizeof(float);
