@@ -108,9 +108,11 @@ HARP_API int harp_ctx_read_counters(harp_ctx* ctx, int64_t out[2], void* stream)
 
 /* Number of CUDA kernels this library has launched in this process (all contexts), for launch accounting. */
 HARP_API int64_t harp_launch_count(void);
-/* Per-kernel device timing.  enable != 0: the two pixel kernels (id 0 = silhouette, 1 = shade) are bracketed by CUDA
- * events on the launch stream.  harp_ctx_profile_read synchronises, returns the summed elapsed ms and launch count since
- * the last read, and clears. */
+/* Per-kernel device timing.  enable = 1: the two pixel kernels (id 0 = silhouette / pixel_vis, 1 = shade) are bracketed by
+ * CUDA events on the launch stream (inside a stream capture: external event-record nodes, re-recorded on every replay);
+ * enable = 2 also brackets the step's segments: 2 LBS forward, 3 LBS backward, 4 mesh build forward, 5 mesh build backward,
+ * 6 camera projection + binning, 7 the render's backward tail.  harp_ctx_profile_read synchronises, returns the summed
+ * elapsed ms and launch count of one id (0..7) since the last read, and clears (events of a captured graph are kept). */
 HARP_API int harp_ctx_profile(harp_ctx* ctx, int enable);
 HARP_API int harp_ctx_profile_read(harp_ctx* ctx, int kernel_id, float* total_ms, int* launches);
 
@@ -206,7 +208,10 @@ HARP_API int harp_render_normals(harp_ctx*, int B, int S, float focal, int faces
  * harp_silhouette(mode 2) + harp_shade(mode 2) in one launch sequence that walks every tile's face list ONCE (silhouette
  * factors and nearest-face visibility together), compacts hit pixels per frame and shades them with full warps.
  * w_sil / w_photo: loss weights; 0 renders that image forward-only (the reference renders both in every stage,
- * optimize_sequence.py:469-488).  Losses (device scalars) receive the unweighted means; gradients are accumulated. */
+ * optimize_sequence.py:469-488).  Losses (device scalars) receive the unweighted means; gradients are accumulated (with
+ * atomics: other work of the step may add to the same buffers concurrently).  What only the shading needs — the light-view
+ * pass, the packed texel copies, the zero fills of the internal accumulators — runs on a stream owned by the ctx, forked from
+ * and joined to `stream` with events, so the call is still one in-order unit of work on `stream` and can be captured. */
 typedef struct {
   const float *verts, *normals;                       /* (B,V,3) */
   const float *cam_R, *cam_T, *light_R, *light_T;     /* (B,3,3), (B,3) */
