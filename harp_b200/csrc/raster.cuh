@@ -201,7 +201,7 @@ __device__ __forceinline__ void load_face(const harp_ctx& c, const float* ndc, i
 //   * the three edge functions in affine form, already multiplied by sign(area):  t_i(p) = a_i p.x + b_i p.y + c_i  (2 FMAs);
 //     t_i > 0 for all i  <=>  strictly inside.  The affine value differs from PyTorch3D's own EdgeFunctionForward rounding
 //     by at most ~9 ulp of  m_i = |a_i| (1 + |x_anchor|) + |b_i| (1 + |y_anchor|);  eps = 1e-6 max_i m_i (16 ulp) is stored and
-//     every pair with min_i |t_i| < eps is re-classified with the bit-exact edge functions (about 1 pair in 500), so the
+//     every pair with min_i |t_i| < eps is re-classified with the bit-exact edge functions (about 1 in-bbox pair in 1700, tests/test_classification_bounds.py), so the
 //     strict-inside decision is PyTorch3D's bit for bit.  A face with a vertex behind the camera has eps = +inf;
 //   * il_i = 1 / |edge_i|^2: the squared distance to an edge line is t_i^2 il_i, compared against uniform thresholds with
 //     margins (2 % / 5 %) an order of magnitude above its relative error at those thresholds; never used for output values;
