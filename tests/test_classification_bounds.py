@@ -112,3 +112,72 @@ def test_ambiguous_pairs_are_rare_on_a_pixel_grid():
         eps = m if eps is None else np.maximum(eps, m)
     frac = float(((tmin < f32(1e-6) * eps) & inb).sum()) / max(int(inb.sum()), 1)
     assert inb.sum() > 50_000 and frac < 0.02, frac
+
+
+def _pix_to_ndc(idx, S):
+    i = (S - 1 - idx).astype(f32)
+    return f32(-1.0) + (f32(2.0) * i + f32(1.0)) / f32(S)
+
+
+def _point_tri_dist2(p, v):
+    """Exact-enough (float64) squared distance from points p (n,2) to triangles v (n,3,2) and strict inside flags."""
+    p = p.astype(np.float64); v = v.astype(np.float64)
+    d2 = np.full(len(p), np.inf)
+    for i in range(3):
+        a, b = v[:, i], v[:, (i + 1) % 3]
+        ab = b - a
+        t = np.clip(((p - a) * ab).sum(1) / np.maximum((ab * ab).sum(1), 1e-300), 0, 1)
+        q = a + t[:, None] * ab
+        d2 = np.minimum(d2, ((p - q) ** 2).sum(1))
+    def e(a, b):
+        return (p[:, 0] - a[:, 0]) * (b[:, 1] - a[:, 1]) - (p[:, 1] - a[:, 1]) * (b[:, 0] - a[:, 0])
+    e0, e1, e2 = e(v[:, 1], v[:, 2]), e(v[:, 2], v[:, 0]), e(v[:, 0], v[:, 1])
+    inside = ((e0 > 0) & (e1 > 0) & (e2 > 0)) | ((e0 < 0) & (e1 < 0) & (e2 < 0))
+    return d2, inside
+
+
+def test_tile_edge_test_of_the_binning_is_conservative():
+    """csrc/raster.cu: a face is left out of an 8x8 tile's list when all four corner pixel centres lie outside one edge
+    line by more than sqrt(1.05 blur) (+1e-5 guard).  Emulated in float32; for every (face, tile) pair the rule drops, NO
+    pixel centre of the tile may be inside the face or within sqrt(blur) of it (silhouette view), resp. inside it (light view)."""
+    rng = np.random.default_rng(2)
+    S, T = 512, 8
+    n = 60_000
+    c = rng.uniform(-0.95, 0.95, size=(n, 1, 2))
+    size = 10 ** rng.uniform(-2.6, -1.2, size=(n, 1, 1))           # faces of ~1 to ~30 pixels
+    v = (c + size * rng.normal(size=(n, 3, 2))).astype(f32)
+    x = v[..., 0]; y = v[..., 1]
+    for radius in (f32(np.sqrt(float(BLUR))), f32(0.0)):
+        area = _edge_exact(x[:, 2], y[:, 2], x[:, 0], y[:, 0], x[:, 1], y[:, 1]) + f32(1e-8)
+        sgn = np.where(area > 0, f32(1), f32(-1))
+        m = f32(1.05) * radius * radius + f32(1e-10)
+        # tiles of the bbox range (float32 arithmetic as face_tile_range)
+        hs = f32(0.5 * S)
+        xmin, xmax = x.min(1) - radius, x.max(1) + radius
+        ymin, ymax = y.min(1) - radius, y.max(1) + radius
+        jlo = np.clip(np.ceil((1 - xmax) * hs - f32(0.5) - f32(0.01)), 0, S - 1); jhi = np.clip(np.floor((1 - xmin) * hs - f32(0.5) + f32(0.01)), 0, S - 1)
+        ilo = np.clip(np.ceil((1 - ymax) * hs - f32(0.5) - f32(0.01)), 0, S - 1); ihi = np.clip(np.floor((1 - ymin) * hs - f32(0.5) + f32(0.01)), 0, S - 1)
+        valid = (jlo <= jhi) & (ilo <= ihi) & (np.abs(area) > 1e-8)
+        tx = (jlo // T + rng.integers(0, 4, n)).astype(np.int64)    # one random tile of (a superset of) each face's range
+        ty = (ilo // T + rng.integers(0, 4, n)).astype(np.int64)
+        valid &= (tx <= jhi // T) & (ty <= ihi // T)
+        xa, xb = _pix_to_ndc(tx * T, S), _pix_to_ndc(tx * T + T - 1, S)
+        ya, yb = _pix_to_ndc(ty * T, S), _pix_to_ndc(ty * T + T - 1, S)
+        reject = np.zeros(n, bool)
+        for (i0, i1) in ((1, 2), (2, 0), (0, 1)):
+            ax, ay, bx, by = x[:, i0], y[:, i0], x[:, i1], y[:, i1]
+            dx, dy = bx - ax, by - ay
+            ea, eb, fa, fb = (xa - ax) * dy, (xb - ax) * dy, (ya - ay) * dx, (yb - ay) * dx
+            mx = np.maximum(np.maximum(sgn * (ea - fa), sgn * (ea - fb)), np.maximum(sgn * (eb - fa), sgn * (eb - fb)))
+            thr = m * (dx * dx + dy * dy)
+            reject |= (mx < 0) & (mx * mx >= thr)
+        rej = np.nonzero(valid & reject)[0]
+        assert len(rej) > 3000
+        # every pixel centre of every rejected (face, tile) pair
+        jj, ii = np.meshgrid(np.arange(T), np.arange(T))
+        for dj, di in zip(jj.ravel(), ii.ravel()):
+            pxy = np.stack([_pix_to_ndc(tx[rej] * T + dj, S), _pix_to_ndc(ty[rej] * T + di, S)], 1)
+            d2, inside = _point_tri_dist2(pxy, v[rej])
+            assert not inside.any()
+            if radius > 0:
+                assert np.all(d2 >= float(BLUR)), float(d2.min() / float(BLUR))
