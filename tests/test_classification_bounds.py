@@ -181,3 +181,33 @@ def test_tile_edge_test_of_the_binning_is_conservative():
             assert not inside.any()
             if radius > 0:
                 assert np.all(d2 >= float(BLUR)), float(d2.min() / float(BLUR))
+
+
+def test_fast_inverse_depth_orders_faces_like_the_exact_depth():
+    """Visibility candidates are ordered by the fast inverse depth q = sum(t_i / z_i) / sum(t_i) (raster.cuh: fast_inv_depth)
+    and only pairs within 1e-5 relative of each other are re-decided with PyTorch3D's exact perspective-correct depth
+    (vis_update).  Emulated in float32: q must equal 1 / pz_exact to well within that tolerance, so the nearest face chosen
+    outside the tie band is the one PyTorch3D's z-ordering picks."""
+    rng = np.random.default_rng(3)
+    n = 500_000
+    c = rng.uniform(-0.9, 0.9, size=(n, 1, 2))
+    v = (c + 0.02 * rng.normal(size=(n, 3, 2))).astype(f32)
+    z = rng.uniform(0.3, 1.5, size=(n, 1)).astype(f32) + (0.05 * rng.normal(size=(n, 3))).astype(f32)   # metres, hand-sized relief
+    w = rng.dirichlet((1.0, 1.0, 1.0), size=n)                                                           # a point strictly inside
+    p = (w[:, :, None] * v.astype(np.float64)).sum(1).astype(f32)
+    x0, y0, x1, y1, x2, y2 = v[:, 0, 0], v[:, 0, 1], v[:, 1, 0], v[:, 1, 1], v[:, 2, 0], v[:, 2, 1]
+    px, py = p[:, 0], p[:, 1]
+    area = _edge_exact(x2, y2, x0, y0, x1, y1) + f32(1e-8)
+    e0, e1, e2 = _edge_exact(px, py, x1, y1, x2, y2), _edge_exact(px, py, x2, y2, x0, y0), _edge_exact(px, py, x0, y0, x1, y1)
+    w0, w1, w2 = e0 / area, e1 / area, e2 / area
+    inside = (w0 > 0) & (w1 > 0) & (w2 > 0) & (np.abs(area) > 1e-6)
+    z0, z1, z2 = z[:, 0], z[:, 1], z[:, 2]
+    # BarycentricPerspectiveCorrectionForward + the depth interpolation, every operation rounded to float32 (eval_pair_full)
+    t0, t1, t2 = (w0 * z1) * z2, (z0 * w1) * z2, (z0 * z1) * w2
+    den = np.maximum((t0 + t1) + t2, f32(1e-8))
+    b0, b1, b2 = t0 / den, t1 / den, t2 / den
+    pz = (b0 * z0 + b1 * z1) + b2 * z2
+    q = ((e0 * (f32(1) / z0) + e1 * (f32(1) / z1)) + e2 * (f32(1) / z2)) / ((e0 + e1) + e2)
+    rel = np.abs(q.astype(np.float64) * pz.astype(np.float64) - 1.0)[inside]
+    assert inside.sum() > 300_000
+    assert float(rel.max()) < 2.5e-6, float(rel.max())   # 4x inside the 1e-5 tie band
