@@ -53,7 +53,7 @@ class HarpError(RuntimeError):
 _lib = None
 
 # every symbol include/harp_b200.h declares (tests/test_abi.py checks the library exports exactly these)
-SYMBOLS = ["harp_last_error", "harp_version", "harp_launch_count", "harp_ctx_profile", "harp_ctx_profile_read", "harp_ctx_create", "harp_ctx_create_lbs", "harp_ctx_destroy", "harp_lbs_fwd", "harp_lbs_bwd", "harp_ctx_reserve", "harp_ctx_dims",
+SYMBOLS = ["harp_last_error", "harp_version", "harp_launch_count", "harp_ctx_profile", "harp_ctx_profile_read", "harp_ctx_create", "harp_ctx_create_lbs", "harp_ctx_destroy", "harp_lbs_fwd", "harp_lbs_bwd", "harp_ctx_reserve", "harp_ctx_pin", "harp_ctx_dims",
            "harp_ctx_faces", "harp_ctx_read_counters", "harp_lbs_mano_fwd", "harp_lbs_mano_bwd", "harp_mesh_build_fwd",
            "harp_mesh_build_bwd", "harp_vertex_normals_fwd", "harp_vertex_normals_bwd", "harp_mesh_losses", "harp_silhouette", "harp_shade", "harp_render_normals", "harp_render_fused", "harp_frame_glue_fwd", "harp_frame_glue_bwd", "harp_texture_reg", "harp_mse", "harp_image_metrics", "harp_ingest_u8", "harp_adam", "harp_adam_dev"]
 
@@ -78,6 +78,7 @@ def lib():
         L.harp_lbs_fwd.argtypes = [vp, i, vp, vp, i, vp, vp, vp, vp]
         L.harp_lbs_bwd.argtypes = [vp, i, vp, vp, i, vp, vp, vp, vp, vp, vp, vp]
         L.harp_ctx_reserve.argtypes = [vp, i, i]
+        L.harp_ctx_pin.argtypes = [vp, i]
         L.harp_ctx_dims.argtypes = [vp, c_int32_p, c_int32_p, c_int32_p, c_int32_p]
         L.harp_ctx_faces.argtypes = [vp, c_int32_p]
         L.harp_ctx_read_counters.argtypes = [vp, C.POINTER(C.c_int64), vp]
@@ -110,15 +111,34 @@ def check(rc):
         raise HarpError(f"libharpb200 error {rc}: {lib().harp_last_error().decode()}")
 
 
-def ptr(t):
-    """Device pointer of a contiguous CUDA fp32/int32 tensor (None -> NULL)."""
+def ptr(t, dtype=torch.float32):
+    """Device pointer of a contiguous CUDA tensor of the dtype the C ABI reads at that argument (None -> NULL).
+    The kernels trust the layout they are handed (include/harp_b200.h: fp32 everywhere except the int64 frame ids, the int32
+    texel offsets / face tables and the uint8 ingest buffers), so a mismatch is an error here, not a silent misread there."""
     if t is None:
         return None
     if not t.is_cuda:
         raise HarpError("harp_b200 ops need CUDA tensors (there is no CPU path)")
     if not t.is_contiguous():
         raise HarpError("harp_b200 ops need contiguous tensors")
+    if t.dtype != dtype:
+        raise HarpError(f"harp_b200: expected a {dtype} tensor at this argument, got {t.dtype}")
     return t.data_ptr()
+
+
+def iptr(t):
+    """int32 tensor (texel offsets)."""
+    return ptr(t, torch.int32)
+
+
+def lptr(t):
+    """int64 tensor (frame ids)."""
+    return ptr(t, torch.int64)
+
+
+def bptr(t):
+    """uint8 tensor (frames / masks as decoded from the image files)."""
+    return ptr(t, torch.uint8)
 
 
 def stream():

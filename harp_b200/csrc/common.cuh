@@ -69,6 +69,7 @@ struct harp_ctx {
   int32_t *tips = nullptr, *parents = nullptr, *joint_out_src = nullptr;
   // scratch (harp_ctx_reserve)
   int maxB = 0, S = 0, tiles = 0;
+  int pins = 0;                   // captured CUDA graphs that hold the scratch pointers (harp_ctx_pin): no reallocation while > 0
   int64_t bin_cap = 0;            // bin list capacity per frame
   float* ndc_cam = nullptr;       // (B,V,3)
   float* ndc_light = nullptr;     // (B,V,3)
@@ -84,6 +85,11 @@ struct harp_ctx {
   int32_t* bin_start = nullptr;   // (2,B,tiles)
   int32_t* bin_fill = nullptr;    // (2,B,tiles)
   int32_t* bin_list = nullptr;    // (2,B,bin_cap)
+  struct FaceTile* face_rec = nullptr;  // (2,B,F) per-face raster records (144 B), written once per frame and view by the setup
+                                        // kernel (setup.cu) and staged into shared memory by bulk async copies (TMA)
+  int4* work = nullptr;           // (2,B*tiles) non-empty tiles {frame, tile, list start, face count}: heavy tiles from the front,
+                                  // light ones from the back of each view's array (one dynamic queue, heavy first)
+  int32_t* work_ctl = nullptr;    // (2,4) per view: {heavy count, light count, consumer cursor, unused}
   float* light_zbuf = nullptr;    // (B,S,S)
   int32_t* light_face = nullptr;  // (B,S,S)
   float* d_light_zbuf = nullptr;  // (B,S,S)
@@ -99,7 +105,7 @@ struct harp_ctx {
   struct harp_prof* prof = nullptr;        // host-side event lists (harp_ctx_profile)
   // host-side handles for the fused render's light branch (forked from / joined to the caller's stream; capturable)
   cudaStream_t side_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_bins = nullptr;
 };
 
 // ---------------------------------------------------------------------------------------------- small vector math

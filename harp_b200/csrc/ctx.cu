@@ -4,7 +4,7 @@
 #include <map>
 #include <mutex>
 
-#include "common.cuh"
+#include "raster.cuh"
 
 static thread_local std::string g_last_error;
 void harp_set_error(const std::string& msg) { g_last_error = msg; }
@@ -238,8 +238,9 @@ extern "C" int harp_ctx_create_lbs(harp_ctx** out, const harp_topology* topo, co
 static void free_scratch(harp_ctx* c) {
   void* ptrs[] = {c->ndc_cam, c->ndc_light, c->d_ndc_cam, c->d_ndc_light, c->bin_count, c->bin_start, c->bin_fill,
                   c->bin_list, c->light_zbuf, c->light_face, c->d_light_zbuf, c->vN, c->vtmp, c->vtmp2, c->d_verts4,
-                  c->d_normals4, c->hit_list, c->hit_count, c->ovf_list, c->ovf_count};
+                  c->d_normals4, c->hit_list, c->hit_count, c->ovf_list, c->ovf_count, c->face_rec, c->work, c->work_ctl};
   c->ovf_list = c->ovf_count = nullptr;
+  c->face_rec = nullptr; c->work = nullptr; c->work_ctl = nullptr;
   c->d_verts4 = c->d_normals4 = nullptr;
   c->hit_list = c->hit_count = nullptr;
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -258,6 +259,7 @@ extern "C" void harp_ctx_destroy(harp_ctx* c) {
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->ev_bins) cudaEventDestroy(c->ev_bins);
   if (c->side_stream) cudaStreamDestroy(c->side_stream);
   if (c->prof) {
     for (auto& v : c->prof->ev) for (cudaEvent_t e : v) cudaEventDestroy(e);
@@ -270,8 +272,12 @@ extern "C" int harp_ctx_reserve(harp_ctx* c, int max_batch, int img_size) {
   HARP_REQUIRE(c && max_batch > 0 && img_size > 0 && img_size % 8 == 0, HARP_ERR_INVALID,
                "harp_ctx_reserve: need max_batch>0 and img_size a positive multiple of 8");
   if (max_batch <= c->maxB && img_size == c->S) return HARP_OK;
+  // Kernels take the ctx by value, so a captured CUDA graph bakes the scratch pointers in: while any graph is alive
+  // (harp_ctx_pin) the scratch must not move.  The batch capacity never shrinks.
+  HARP_REQUIRE(c->pins == 0, HARP_ERR_CAPACITY,
+               "harp_ctx_reserve: the scratch is pinned by a captured CUDA graph (harp_ctx_pin); release it or use another context");
+  int B = std::max(max_batch, c->maxB), S = img_size;
   free_scratch(c);
-  int B = max_batch, S = img_size;
   int tiles = (S / 8) * (S / 8);
   size_t nv = (size_t)B * c->V * 3 * sizeof(float);
   size_t npx = (size_t)B * S * S;
@@ -303,9 +309,19 @@ extern "C" int harp_ctx_reserve(harp_ctx* c, int max_batch, int img_size) {
   c->ovf_cap = (int)std::min<size_t>(npx, (size_t)1 << 22);
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->ovf_list, (size_t)c->ovf_cap * sizeof(int32_t)));
   HARP_CHECK_CUDA(cudaMalloc((void**)&c->ovf_count, sizeof(int32_t)));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->face_rec, 2 * (size_t)B * c->F * sizeof(FaceTile)));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->work, 2 * (size_t)B * tiles * sizeof(int4)));
+  HARP_CHECK_CUDA(cudaMalloc((void**)&c->work_ctl, 8 * sizeof(int32_t)));
+  HARP_CHECK_CUDA(cudaMemset(c->work_ctl, 0, 8 * sizeof(int32_t)));
   c->maxB = B;
   c->S = S;
   c->tiles = tiles;
+  return HARP_OK;
+}
+
+extern "C" int harp_ctx_pin(harp_ctx* c, int delta) {
+  HARP_REQUIRE(c, HARP_ERR_INVALID, "harp_ctx_pin: null ctx");
+  c->pins = std::max(0, c->pins + delta);
   return HARP_OK;
 }
 

@@ -100,20 +100,26 @@ __device__ void lbs_prologue(const harp_ctx& c, const float* pose, const float* 
 // v_posed for vertex v (template + shape + pose blendshapes); blendshape tables are stored transposed
 // (k, V0*3) so that consecutive threads read consecutive addresses.
 __device__ __forceinline__ f3 lbs_v_posed(const harp_ctx& c, const LbsShared& s, int v) {
+  // The blendshape offsets (|offset| ~ 1e-3 m) are summed on their own, in double, and added to the template once — as the
+  // reference does (v_shaped = template + blend_shapes(...), v_posed = v_shaped + matmul(pose_feature, posedirs):
+  // manolayer.py:181-200, smplx.lbs.lbs).  Accumulating them one by one INTO the coordinate (|x| ~ 0.5 m, ulp 6e-8) loses
+  // ~1e-6 m over the arm's 486 terms, which the sigma = 1e-7 silhouette turns into 5e-3 of gradient error.
   int n3 = c.V0 * 3, i = v * 3, NS = c.n_shape, NP = (c.J - 1) * 9;
-  float x = c.v_template[i], y = c.v_template[i + 1], z = c.v_template[i + 2];
+  double sx = 0.0, sy = 0.0, sz = 0.0;
   for (int b = 0; b < NS; ++b) {
     const float* p = c.shapedirs + (size_t)b * n3 + i;
-    float w = s.beta[b];
-    x += p[0] * w; y += p[1] * w; z += p[2] * w;
+    double w = s.beta[b];
+    sx += p[0] * w; sy += p[1] * w; sz += p[2] * w;
   }
+  float x = c.v_template[i] + (float)sx, y = c.v_template[i + 1] + (float)sy, z = c.v_template[i + 2] + (float)sz;
+  double px = 0.0, py = 0.0, pz = 0.0;
 #pragma unroll 9
   for (int k = 0; k < NP; ++k) {
     const float* p = c.posedirs + (size_t)k * n3 + i;
-    float w = s.pose_map[k];
-    x += p[0] * w; y += p[1] * w; z += p[2] * w;
+    double w = s.pose_map[k];
+    px += p[0] * w; py += p[1] * w; pz += p[2] * w;
   }
-  return mk3(x, y, z);
+  return mk3(x + (float)px, y + (float)py, z + (float)pz);
 }
 
 __device__ __forceinline__ void lbs_blend(const harp_ctx& c, const LbsShared& s, int v, float T[12]) {

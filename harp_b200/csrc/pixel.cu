@@ -5,41 +5,64 @@
 // and blends, both image losses (optimize_sequence.py:519,543) and their autograd.
 #include "shade_pixel.cuh"
 
-int harp_build_bins(harp_ctx* c, int view, int B, int S, float radius, const float* ndc, cudaStream_t st);
-int harp_project(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R, const float* T, float* ndc,
-                 cudaStream_t st);
+int harp_raster_setup(harp_ctx* c, int view, int B, int S, float focal, float radius, const float* verts, const float* R,
+                      const float* T, cudaStream_t st);
 int harp_project_bwd(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R, const float* T,
                      const float* d_ndc, float* d_verts, float* d_R, float* d_T, cudaStream_t st);
 int harp_fold4(size_t n, const float* src4, float* dst3, cudaStream_t st);
 int harp_tex_prepare(harp_ctx* c, const float* texture, const float* normal_map, int texH, int texW, cudaStream_t st);
 int harp_light_depth(harp_ctx* c, int B, int S, cudaStream_t st);
+int harp_light_depth_tiles(harp_ctx* c, int B, int S, cudaStream_t st);
 int harp_light_depth_bwd(harp_ctx* c, int B, int S, cudaStream_t st);
 int harp_sil_topk(harp_ctx* c, int mode, int S, int K, float sigma, float blur, float radius, float* alpha, const float* gin,
                   float gscale, float inv_n, float* loss, cudaStream_t st);
 
 namespace {
 
-#ifndef HARP_PV_CHUNK
-#define HARP_PV_CHUNK 64
-#endif
-#ifndef HARP_PV_QCAP
-#define HARP_PV_QCAP 352
-#endif
 #ifndef HARP_PV_MINCTAS
-#define HARP_PV_MINCTAS 16
+#define HARP_PV_MINCTAS 12
 #endif
 #ifndef HARP_SHADE_GRID
 #define HARP_SHADE_GRID 96
 #endif
-constexpr int CHUNK = HARP_PV_CHUNK;  // faces staged per shared-memory round (tuning knobs: tools/build_variants.sh)
+constexpr int CHUNK = 32;   // faces staged per bulk-copy round (one lane of warp 0 per face)
 constexpr int NT = HARP_TILE * HARP_TILE;
-constexpr int QCAP = HARP_PV_QCAP;  // 352 with the 128-byte face records: 13.5 KB per CTA -> 16 CTAs per SM
+constexpr int QCAP = 320;   // band pairs of one tile (all chunks); a tile that needs more goes to the exact per-pixel kernel
+constexpr int TIECAP = 48;  // visibility candidates within 1e-5 of each other (resolved with the exact depth)
+
+// ---- Blackwell/Hopper async-copy plumbing: mbarrier + bulk global->shared copies (TMA unit; SASS: UBLKCP / SYNCS) ----------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 struct VisArgs {
   int S, K;
   float sigma, blur, radius;
   const float* ndc;
-  const int32_t *bin_count, *bin_start, *bin_list;
+  const FaceTile* rec;       // (B,F) records of this view
+  const int32_t* bin_list;   // (B,bin_cap)
+  const int4* work;          // non-empty tiles: heavy from the front, light from the back
+  int32_t* work_ctl;         // {heavy, light, cursor, -}
+  int work_cap;
   // silhouette
   float* alpha;
   const float* y_sil;
@@ -53,7 +76,21 @@ struct VisArgs {
   const float *y_true, *y_mask;
   float photo_inv_n;
   float* photo_loss;
+  // light view (MODE_LIGHT): nearest depth / face id
+  float* zbuf;
+  int32_t* face;
 };
+
+struct __align__(16) BandEntry {
+  int fid;
+  float sd;              // signed squared distance (inside negative)
+  float t;               // clamped parameter on the closest edge (-1: degenerate edge)
+  short next;            // chain through the pixel's entries (-1 ends)
+  unsigned char pix;
+  unsigned char edge;    // queued: chunk-local face index | 0x40 inside | 0x80 exact path; evaluated: 0..2, or 255 = does not pass
+};
+// s_om[slot] = 1 - sigmoid(-sd / sigma) of an evaluated entry, computed with full warps in the drain
+struct TieEntry { int pix, fid; float q; };
 
 // Block-wide sum of two values at once (64-thread CTAs: two warps); results valid in thread 0.
 __device__ __forceinline__ void block_sum2(float& u, float& v, float* red) {
@@ -64,201 +101,422 @@ __device__ __forceinline__ void block_sum2(float& u, float& v, float* red) {
   if (threadIdx.x == 0) { u = red[0] + red[2]; v = red[1] + red[3]; }
 }
 
-// SIL_BWD: accumulate the silhouette L1 loss and its gradient (COARSE_OPT stages); PHOTO: accumulate the photometric loss
-// of background pixels (APP_OPT stages; hit pixels are handled by the deferred shading kernel).
-template <bool SIL_BWD, bool PHOTO>
-__global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) pixel_vis_kernel(harp_ctx c, VisArgs a) {
-  __shared__ FaceTile faces[CHUNK];
-  __shared__ float red[32];
-  __shared__ unsigned char q_pix[QCAP], q_face[QCAP], q_edge[QCAP];
-  __shared__ unsigned short q_next[QCAP];  // per-pixel chain through the queue, in face-list order
-  __shared__ float q_sd[QCAP], q_t[QCAP];
-  __shared__ int q_n, any_bwd;
-  __shared__ float s_g[NT], s_prod[NT];
-  __shared__ unsigned char s_need[NT];
-  __shared__ float s_px[HARP_TILE], s_py[HARP_TILE];  // NDC centres of the tile's columns / rows (queue drains look pixels up)
-  const int S = a.S;
-  int b = blockIdx.z, tw = S / HARP_TILE, tid = threadIdx.x;
-  int lx = tid % HARP_TILE, ly = tid / HARP_TILE;
-  int col = blockIdx.x * HARP_TILE + lx, row = blockIdx.y * HARP_TILE + ly;
-  size_t pix = ((size_t)b * S + row) * S + col;
-  size_t tglob = (size_t)b * tw * tw + blockIdx.y * tw + blockIdx.x;
-  // The tile's targets are requested together with its face count so that, for an empty tile (about 4 of 5 at the
-  // reference's framing), one memory latency covers everything it needs; a tile with faces drops them and re-reads at the end.
-  float ys = SIL_BWD ? __ldcs(a.y_sil + pix) : 0.f;
-  float mk = 0.f;
-  f3 y = mk3(0.f, 0.f, 0.f);
-  if (PHOTO) { mk = __ldcs(a.y_mask + pix); y = mk3(__ldcs(a.y_true + pix * 3), __ldcs(a.y_true + pix * 3 + 1), __ldcs(a.y_true + pix * 3 + 2)); }
-  int n = a.bin_count[tglob];
-  if (n == 0) {
-    // ---- empty tile: nothing but streaming
-    a.alpha[pix] = 0.f;
-    st3(a.rgb + pix * 3, mk3(1.f, 1.f, 1.f));
-    float s_sil = fabsf(ys), s_ph = PHOTO ? fabsf(mk - y.x * mk) + fabsf(mk - y.y * mk) + fabsf(mk - y.z * mk) : 0.f;
-    if (!SIL_BWD && !PHOTO) return;
-    if (__ballot_sync(0xffffffffu, s_sil != 0.f || s_ph != 0.f)) {  // rare: target foreground over an empty tile (per warp, no barrier)
-      s_sil = warp_sum(s_sil); s_ph = warp_sum(s_ph);
-      if ((tid & 31) == 0) {
-        if (SIL_BWD && s_sil != 0.f) atomicAdd(a.sil_loss, s_sil * a.sil_inv_n);
-        if (PHOTO && s_ph != 0.f) atomicAdd(a.photo_loss, s_ph * a.photo_inv_n);
-      }
-    }
+// Distance part of CheckPixelInsideFace for a face in front of the camera (pz > 0 is implied, strict-inside is known from the
+// bit-exact edge functions): PointTriangleDistanceForward, operation by operation.
+__device__ __forceinline__ void band_dist(const FaceTile& f, float px, float py, float& dist, int& edge, float& t) {
+  float ta, tb, tc;
+  float d01 = point_seg_dist(px, py, f.x0, f.y0, f.x1, f.y1, &ta);
+  float d02 = point_seg_dist(px, py, f.x0, f.y0, f.x2, f.y2, &tb);
+  float d12 = point_seg_dist(px, py, f.x1, f.y1, f.x2, f.y2, &tc);
+  dist = d01; edge = 0; t = ta;
+  if (d02 < dist) { dist = d02; edge = 1; t = tb; }
+  if (d12 < dist) { dist = d12; edge = 2; t = tc; }
+}
+
+// sil_pair_gradient for a face known by id only (the tile's staged records are gone by the time gradients are scattered)
+__device__ __forceinline__ void sil_pair_gradient_fid(const harp_ctx& c, const float* ndc, int fid, float px, float py, float sd, int edge,
+                                                      float t, float g, float prod, float sigma, float* d_ndc) {
+  float prob = 1.f / (1.f + expf(fdiv(sd, sigma)));
+  float gsd = g * (-prod * prob / sigma);
+  float gd = sd < 0.f ? -gsd : gsd;
+  if (gd == 0.f) return;
+  const int32_t* fv = c.faces + (size_t)fid * 3;
+  int va = edge == 2 ? fv[1] : fv[0], vb = edge == 0 ? fv[1] : fv[2];
+  const float *pa = ndc + (size_t)va * 3, *pb = ndc + (size_t)vb * 3;
+  float ax = pa[0], ay = pa[1], bx = pb[0], by = pb[1];
+  if (t < 0.f) {  // degenerate edge: dist = |p - b|^2
+    atomicAdd(reinterpret_cast<float2*>(d_ndc + (size_t)vb * 4), make_float2(gd * 2.f * (bx - px), gd * 2.f * (by - py)));
     return;
   }
-  int start = a.bin_start[tglob];
-  if (start + n > c.bin_cap) n = max(0, (int)c.bin_cap - start);
-  const int32_t* list = a.bin_list + (size_t)b * c.bin_cap + start;
-  const float* ndc = a.ndc + (size_t)b * c.V * 3;
+  float qx = ax + t * (bx - ax), qy = ay + t * (by - ay);
+  float dx = 2.f * gd * (qx - px), dy = 2.f * gd * (qy - py);
+  atomicAdd(reinterpret_cast<float2*>(d_ndc + (size_t)va * 4), make_float2((1.f - t) * dx, (1.f - t) * dy));
+  atomicAdd(reinterpret_cast<float2*>(d_ndc + (size_t)vb * 4), make_float2(t * dx, t * dy));
+}
+
+// exact perspective-correct depth of pixel (px,py) on face `fid`, from the face's record in HBM/L2
+__device__ __forceinline__ float exact_pz_rec(const FaceTile* rec, int fid, float px, float py, PairEval* out = nullptr) {
+  const float4* r = reinterpret_cast<const float4*>(rec + fid);
+  float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r7 = __ldg(r + 7);
+  FaceRec g;
+  g.x0 = r0.x; g.y0 = r0.y; g.x1 = r0.z; g.y1 = r0.w; g.x2 = r1.x; g.y2 = r1.y;
+  g.area = r2.w; g.z0 = r7.x; g.z1 = r7.y; g.z2 = r7.z;
+  PairEval e;
+  eval_pair_full<false, false>(g, px, py, 0.f, e);
+  if (out) *out = e;
+  return e.pass ? e.pz : 3.4e38f;
+}
+
+// The persistent tile rasteriser.  One 64-thread CTA takes non-empty 8x8 tiles from the view's work queue (heavy tiles first).
+// A tile's face records arrive by bulk async copies, 32 faces per round, the NEXT tile's first round being requested before
+// the current tile is processed.  Work is spread over (pixel, face) PAIRS, not pixels: each face contributes only the pixels
+// of its bbox inside the tile (a 5-7 px square for the reference's meshes), the pairs of a round are numbered by a prefix
+// sum and every lane classifies one pair per step, so lanes do useful tests only (the former pixel-major walk tested all 64
+// pixels of the tile against every face).  Visibility is a 64-bit shared-memory atomicMax on (1/depth, ~face id); silhouette
+// band pairs are queued, evaluated with full warps, chained per pixel and folded in ascending face id (deterministic alpha).
+//   SIL     camera view: silhouette + visibility + hit compaction;  !SIL: light view, nearest depth + face id only
+//   SIL_BWD accumulate the silhouette L1 loss and its gradient (COARSE_OPT stages)
+//   PHOTO   accumulate the photometric loss of background pixels (APP_OPT stages)
+template <bool SIL, bool SIL_BWD, bool PHOTO>
+__global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_ctx c, VisArgs a) {
+  __shared__ FaceTile s_rec[2][CHUNK];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ unsigned long long s_vis[NT];
+  __shared__ BandEntry s_q[SIL ? QCAP : 1];
+  __shared__ float s_om[SIL ? QCAP : 1];
+  __shared__ TieEntry s_tie[TIECAP];
+  __shared__ int s_cnt[NT], s_head[NT];
+  __shared__ int s_pre[CHUNK + 1], s_rect[CHUNK];
+  __shared__ float s_rw[CHUNK];
+  __shared__ float s_g[NT], s_prod[NT];
+  __shared__ unsigned char s_need[NT], s_sat[NT];
+  __shared__ float s_px[HARP_TILE], s_py[HARP_TILE];
+  __shared__ float red[4];
+  __shared__ int s_qn, s_tn, s_next, s_ovf;
+  const int S = a.S, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tw = S / HARP_TILE;
   const float sigma = a.sigma, blur = a.blur;
-  float px = pix_to_ndc(col, S), py = pix_to_ndc(row, S);
-  if (ly == 0) s_px[lx] = px;
-  if (lx == 0) s_py[ly] = py;
-  float prod = 1.f;
-  int nzero = 0, npass = 0, ncand = 0;
-  int best_fid = -1;
-  float best_q = 0.f;
-  bool q_overflow = false;
   const float sat = 17.5f * sigma, far = 1.02f * blur;  // margins of the affine classification (raster.cuh: FaceTile)
-  if (tid == 0) { any_bwd = 0; q_n = 0; }
-  for (int base = 0; base < n; base += CHUNK) {
-    int m = min(CHUNK, n - base);
+  const int n_heavy = a.work_ctl[0], total = n_heavy + a.work_ctl[1];
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_next = atomicAdd(a.work_ctl + 2, 1);
+  }
+  __syncthreads();
+  int idx = s_next;
+  if (idx >= total) return;
+  auto load_item = [&](int i) { return a.work[i < n_heavy ? i : a.work_cap - 1 - (i - n_heavy)]; };
+  // one bulk copy per face of the round, issued by warp 0; completion is counted in bytes on the buffer's mbarrier
+  auto issue = [&](const int4& it, int base, int buf) {
+    if (warp == 0) {
+      int m = min(CHUNK, it.w - base);
+      if (lane == 0) mbar_expect_tx(&s_bar[buf], (uint32_t)(m * sizeof(FaceTile)));
+      __syncwarp();
+      if (lane < m) {
+        int f = a.bin_list[(size_t)it.x * c.bin_cap + it.z + base + lane];
+        bulk_g2s(&s_rec[buf][lane], a.rec + (size_t)it.x * c.F + f, (uint32_t)sizeof(FaceTile), &s_bar[buf]);
+      }
+    }
+  };
+  int4 item = load_item(idx);
+  int cur = 0;
+  uint32_t phase0 = 0, phase1 = 0;
+  issue(item, 0, 0);
+  while (true) {
+    // ---- per-tile state; fetch the next work item and request its first round of records
+    s_vis[tid] = 0ULL; s_cnt[tid] = 0; s_head[tid] = -1; s_sat[tid] = 0;
+    const int b = item.x, tile = item.y, n = item.w;
+    const int tx0 = (tile % tw) * HARP_TILE, ty0 = (tile / tw) * HARP_TILE;
+    if (tid < HARP_TILE) s_px[tid] = pix_to_ndc(tx0 + tid, S);
+    else if (tid < 2 * HARP_TILE) s_py[tid - HARP_TILE] = pix_to_ndc(ty0 + tid - HARP_TILE, S);
+    if (tid == 0) { s_qn = 0; s_tn = 0; s_ovf = 0; s_next = atomicAdd(a.work_ctl + 2, 1); }
     __syncthreads();
-    if (tid < m) stage_face(c, ndc, list[base + tid], a.radius, faces[tid]);
-    if (tid == 0) q_n = 0;
+    const int nidx = s_next;
+    const bool have_next = nidx < total;
+    int4 nitem = make_int4(0, 0, 0, 0);
+    if (have_next) { nitem = load_item(nidx); issue(nitem, 0, cur ^ 1); }
+    const float* ndc = a.ndc + (size_t)b * c.V * 3;
+    const bool count_cand = SIL && n > a.K;  // a pixel can have more than K candidates only if the tile has more than K faces
+    int q_lo = 0;
+    for (int base = 0; base < n; base += CHUNK) {
+      const int m = min(CHUNK, n - base);
+      if (base > 0) { __syncthreads(); issue(item, base, cur); }  // the buffer is free: everyone is past the previous round
+      if (cur == 0) { mbar_wait(&s_bar[0], phase0); phase0 ^= 1; } else { mbar_wait(&s_bar[1], phase1); phase1 ^= 1; }
+      const FaceTile* recs = s_rec[cur];
+      // ---- each face's pixel rectangle inside the tile, and the running pair count (warp 0)
+      if (warp == 0) {
+        int cnt = 0, rc = 0;
+        float rw = 1.f;
+        if (lane < m) {
+          int cols = recs[lane].cols, rows = recs[lane].rows;
+          int x0 = max(cols & 0xffff, tx0) - tx0, x1 = min(cols >> 16, tx0 + HARP_TILE - 1) - tx0;
+          int y0 = max(rows & 0xffff, ty0) - ty0, y1 = min(rows >> 16, ty0 + HARP_TILE - 1) - ty0;
+          int w = x1 - x0 + 1, h = y1 - y0 + 1;
+          bool ok = w > 0 && h > 0;
+          cnt = ok ? w * h : 1;  // never zero: pair ends stay distinct (the pair of an empty rectangle is skipped)
+          rc = ok ? (x0 | (y0 << 4) | (w << 8)) : 0;
+          rw = ok ? __frcp_rn((float)w) : 1.f;
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int x = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += x;
+        }
+        s_pre[lane + 1] = incl;
+        if (lane == 0) s_pre[0] = 0;
+        s_rect[lane] = rc;
+        s_rw[lane] = rw;
+      }
+      __syncthreads();
+      // ---- A: one (pixel, face) pair per lane and step
+      {
+        const int P = s_pre[m];
+        const int e_l = lane < m ? s_pre[lane + 1] : 0x7fffffff;  // end of face `lane`'s pairs
+        for (int p0 = warp * 32; p0 < P; p0 += 2 * 32) {
+          // face of pair p = #faces whose pairs end at or before p: faces ended before the window + boundaries inside it
+          int fbase = __popc(__ballot_sync(0xffffffffu, e_l <= p0));
+          unsigned bit = (e_l > p0 && e_l <= p0 + 31) ? (1u << (e_l - p0)) : 0u;
+          unsigned wmask = __reduce_or_sync(0xffffffffu, bit);
+          const int p = p0 + lane;
+          const bool valid = p < P;
+          int fi = valid ? fbase + __popc(wmask & ((2u << lane) - 1u)) : 0;
+          const FaceTile& f = recs[fi];
+          int rc = s_rect[fi], w = rc >> 8;
+          int local = p - s_pre[fi];
+          int ry = __float2int_rz(((float)local + 0.5f) * s_rw[fi]);
+          int lx = (rc & 15) + (local - ry * w), ly = ((rc >> 4) & 15) + ry;
+          if (!valid || w == 0) { lx = 0; ly = 0; }
+          const int pix = ly * HARP_TILE + lx;
+          const float px = s_px[lx], py = s_py[ly];
+          bool inb = valid && w != 0 && in_face_bbox(f, px, py);
+          bool inside;
+          float e0, e1, e2, q = 0.f;
+          int cls = classify_fast<SIL>(f, px, py, far, sat, inb, inside, e0, e1, e2);
+          bool exact = false;
+          if (cls == PAIR_EXACT) {  // a vertex behind the camera: decide with the exact operation sequence
+            PairEval e;
+            eval_pair_full<false, false>(f, px, py, 0.f, e);
+            inside = e.pass;
+            q = e.pass ? 1.f / e.pz : 0.f;
+            cls = SIL ? PAIR_FULL : (inside ? PAIR_SATURATED : PAIR_REJECT);
+            exact = true;
+          } else if (inside) {
+            q = fast_inv_depth(f, e0, e1, e2);
+          }
+          if (cls != PAIR_REJECT && inside) {
+            // nearest face = largest 1/depth; equal depths prefer the lower face id.  Candidates within 1e-5 (relative) of the
+            // running maximum are remembered and settled with the exact depth at the end.
+            unsigned long long key = ((unsigned long long)__float_as_uint(q) << 32) | (unsigned long long)(0xffffffffu - (unsigned)f.fid);
+            unsigned long long old = atomicMax(&s_vis[pix], key);
+            if (old != 0ULL) {
+              float qo = __uint_as_float((unsigned)(old >> 32));
+              if (fabsf(q - qo) <= 1e-5f * fmaxf(q, qo)) {
+                int slot = atomicAdd(&s_tn, 2);
+                if (slot + 1 < TIECAP) {
+                  s_tie[slot] = TieEntry{pix, f.fid, q};
+                  s_tie[slot + 1] = TieEntry{pix, (int)(0xffffffffu - (unsigned)(old & 0xffffffffu)), qo};
+                }
+              }
+            }
+          }
+          if (SIL) {
+            if (cls != PAIR_REJECT && count_cand) atomicAdd(&s_cnt[pix], 1);  // upper bound on PyTorch3D's candidates
+            if (cls == PAIR_SATURATED) s_sat[pix] = 1;  // one exactly-zero factor: alpha = 1, zero gradient
+            bool band = cls == PAIR_FULL && !s_sat[pix];
+            unsigned bm = __ballot_sync(0xffffffffu, band);
+            if (bm) {
+              int qb = 0;
+              if (lane == 0) qb = atomicAdd(&s_qn, __popc(bm));
+              qb = __shfl_sync(0xffffffffu, qb, 0);
+              if (band) {
+                int slot = qb + __popc(bm & ((1u << lane) - 1u));
+                if (slot < QCAP) {
+                  BandEntry e;
+                  e.fid = f.fid; e.sd = 0.f; e.t = 0.f; e.pix = (unsigned char)pix;
+                  e.edge = (unsigned char)(fi | (inside ? 0x40 : 0) | (exact ? 0x80 : 0));
+                  e.next = (short)atomicExch(&s_head[pix], slot);
+                  s_q[slot] = e;
+                } else {
+                  s_ovf = 1;
+                }
+              }
+            }
+          }
+        }
+      }
+      if (SIL) {
+        __syncthreads();
+        // ---- B: evaluate this round's band pairs with every thread busy (pixels already known saturated are skipped)
+        const int qn = min(s_qn, QCAP);
+        for (int s = q_lo + tid; s < qn; s += NT) {
+          BandEntry e = s_q[s];
+          int pix = e.pix;
+          if (s_sat[pix]) { s_q[s].edge = 255; continue; }
+          const FaceTile& f = recs[e.edge & 31];
+          float ppx = s_px[pix % HARP_TILE], ppy = s_py[pix / HARP_TILE];
+          bool inside = (e.edge & 0x40) != 0, pass;
+          float dist, t;
+          int edge;
+          if (e.edge & 0x80) {
+            PairEval r;
+            eval_pair_full<true, true>(f, ppx, ppy, blur, r);
+            pass = r.pass; inside = r.inside; dist = r.dist; edge = r.edge; t = r.t;
+          } else {
+            band_dist(f, ppx, ppy, dist, edge, t);
+            pass = inside || dist < blur;
+          }
+          if (pass) {
+            e.sd = inside ? -dist : dist; e.t = t; e.edge = (unsigned char)edge;
+            float om = 1.f - 1.f / (1.f + expf(fdiv(e.sd, sigma)));  // 1 - sigmoid(-sd / sigma)
+            s_om[s] = om;
+            if (om == 0.f) s_sat[pix] = 1;  // an exactly-zero factor: alpha = 1, zero gradient
+          } else {
+            e.edge = 255;
+          }
+          s_q[s] = e;
+        }
+        q_lo = qn;
+      }
+    }
     __syncthreads();
-    // A: classification of every (pixel, face) pair, branch-free up to the class: visibility (nearest inside face by
-    //    1/depth) for all pixels; silhouette factors until the pixel saturates (one exactly-zero factor => alpha = 1,
-    //    zero gradient).  Band pairs go to the tile's queue, chained per pixel.
-    int q_first = -1, q_last = -1, q_mine = 0;
-    for (int i = 0; i < m; ++i) {
-      const FaceTile& f = faces[i];
-      bool inside;
-      float e0, e1, e2;
-      bool inb = in_face_bbox(f, px, py);
-      if (!__any_sync(0xffffffffu, inb)) continue;  // the face's bbox misses this warp's 8x4 half of the tile
-      int cls = classify_fast<true>(f, px, py, far, sat, inb, inside, e0, e1, e2);
-      if (cls == PAIR_REJECT) continue;
-      float q;
-      if (cls == PAIR_EXACT) {  // a vertex behind the camera: decide with the exact operation sequence
+    // ================================================================== per-pixel epilogue (thread = pixel)
+    const int lx = tid % HARP_TILE, ly = tid / HARP_TILE;
+    const int col = tx0 + lx, row = ty0 + ly;
+    const size_t pix = ((size_t)b * S + row) * S + col;
+    const float px = s_px[lx], py = s_py[ly];
+    // ---- visibility: the running maximum, unless a remembered near-tie has the smaller exact depth
+    unsigned long long key = s_vis[tid];
+    int best_fid = key != 0ULL ? (int)(0xffffffffu - (unsigned)(key & 0xffffffffu)) : -1;
+    {
+      const int nt = min(s_tn, TIECAP);
+      if (s_tn > TIECAP && tid == 0) atomicAdd(c.counters, 1ULL);  // reported by harp_ctx_read_counters (never seen)
+      if (nt > 0 && best_fid >= 0) {
+        float best_q = __uint_as_float((unsigned)(key >> 32)), best_pz = 0.f;
+        bool have_pz = false;
+        for (int i = 0; i < nt; ++i) {
+          TieEntry te = s_tie[i];
+          if (te.pix != tid || te.fid == best_fid || te.q < best_q - 2e-5f * best_q) continue;
+          if (!have_pz) { best_pz = exact_pz_rec(a.rec + (size_t)b * c.F, best_fid, px, py); have_pz = true; }
+          float pz = exact_pz_rec(a.rec + (size_t)b * c.F, te.fid, px, py);
+          if (pz < best_pz || (pz == best_pz && te.fid < best_fid)) { best_fid = te.fid; best_pz = pz; }
+        }
+      }
+    }
+    const bool hit = best_fid >= 0;
+    if (!SIL) {
+      // light view: nearest exact depth + face id (renderer_helper.py:344)
+      float z = -1.f;
+      int fo = -1;
+      if (hit) {
         PairEval e;
-        eval_pair_full<false, false>(f, px, py, 0.f, e);
-        inside = e.pass;
-        q = e.pass ? 1.f / e.pz : 0.f;
-        cls = PAIR_FULL;
+        exact_pz_rec(a.rec + (size_t)b * c.F, best_fid, px, py, &e);
+        if (e.pass) { z = e.pz; fo = best_fid; }
+      }
+      a.zbuf[pix] = z;
+      a.face[pix] = fo;
+    } else {
+      {  // per-frame compacted hit list (warp-aggregated append)
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        int hb = 0;
+        if (mask) {
+          if (lane == 0) hb = atomicAdd(a.hit_count + b, __popc(mask));
+          hb = __shfl_sync(0xffffffffu, hb, 0);
+          if (hit) reinterpret_cast<int2*>(a.hit_list)[(size_t)b * S * S + hb + __popc(mask & ((1u << lane) - 1u))] = make_int2(row * S + col, best_fid);
+        }
+      }
+      float photo_abs = 0.f;
+      if (!hit) {
+        st3(a.rgb + pix * 3, mk3(1.f, 1.f, 1.f));  // background colour (renderer_helper.py:430)
+        if (PHOTO) {
+          float mk = a.y_mask[pix];
+          if (mk != 0.f) {
+            f3 y = ld3(a.y_true + pix * 3);
+            photo_abs = fabsf(mk - y.x * mk) + fabsf(mk - y.y * mk) + fabsf(mk - y.z * mk);
+          }
+        }
+      }
+      // ---- silhouette: the product of the pixel's band factors.  The chain is in arrival order (shared-memory atomics), so
+      // the product is taken in double: re-ordering then changes it by ~1e-16, i.e. the float result is the same however the
+      // pairs were scheduled (alpha is reproducible run to run)
+      const int qn = min(s_qn, QCAP);
+      float prod = 1.f;
+      int nzero = s_sat[tid] ? 1 : 0, npass = nzero;
+      if (nzero == 0) {
+        double dp = 1.0;
+        for (int s = s_head[tid]; s >= 0; s = s_q[s].next) {
+          if (s_q[s].edge == 255) continue;
+          ++npass;
+          dp *= (double)s_om[s];
+        }
+        prod = (float)dp;
+      }
+      float al = nzero > 0 ? 1.f : 1.f - prod;
+      // more candidates than faces_per_pixel (or a band queue that did not fit) -> exact per-pixel top-K kernel
+      const bool deferred = (count_cand && s_cnt[tid] > a.K) || s_ovf != 0;
+      if (deferred) sil_defer_overflow(c, (int)pix);
+      else a.alpha[pix] = al;
+      float diff = (deferred || !SIL_BWD) ? 0.f : al - a.y_sil[pix];
+      if (SIL_BWD || PHOTO) {
+        float s_sil = fabsf(diff), s_ph = photo_abs;
+        block_sum2(s_sil, s_ph, red);
+        if (tid == 0) {
+          if (SIL_BWD && s_sil != 0.f) atomicAdd(a.sil_loss, s_sil * a.sil_inv_n);
+          if (PHOTO && s_ph != 0.f) atomicAdd(a.photo_loss, s_ph * a.photo_inv_n);
+        }
+      }
+      if (SIL_BWD) {
+        float g = diff > 0.f ? a.sil_gscale : (diff < 0.f ? -a.sil_gscale : 0.f);
+        bool need = (g != 0.f) && nzero == 0 && prod > 0.f && npass > 0;
+        s_g[tid] = g; s_prod[tid] = prod; s_need[tid] = need ? 1 : 0;
+        if (__syncthreads_or(need ? 1 : 0)) {
+          float* d_ndc = a.d_ndc + (size_t)b * c.V * 4;
+          for (int s = tid; s < qn; s += NT) {
+            BandEntry e = s_q[s];
+            if (e.edge == 255 || !s_need[e.pix]) continue;
+            sil_pair_gradient_fid(c, ndc, e.fid, s_px[e.pix % HARP_TILE], s_py[e.pix / HARP_TILE], e.sd, e.edge, e.t, s_g[e.pix],
+                                  s_prod[e.pix], sigma, d_ndc);
+          }
+        }
+      }
+    }
+    if (!have_next) break;
+    item = nitem;
+    idx = nidx;
+    cur ^= 1;
+    __syncthreads();  // everyone is done with this tile's shared state
+  }
+}
+
+// Tiles no face touches (4 of 5 at the reference's framing): pure streaming, 16-byte vectors, one thread per 4 pixels of a row.
+//   camera view: alpha = 0, colour = background white, and the two L1 losses of those pixels (the colour target is read only
+//   where the eroded target mask is non-zero);  light view: depth = -1, face = -1.
+template <bool LIGHT, bool SIL_BWD, bool PHOTO>
+__global__ void __launch_bounds__(256) empty_tiles_kernel(int B, int S, const int32_t* __restrict__ bin_count, VisArgs a) {
+  const int q4 = S / 4;  // float4 groups per row; a group never straddles an 8-pixel tile
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)B * S * q4;
+  bool work = gid < total;
+  float s_sil = 0.f, s_ph = 0.f;
+  if (work) {
+    int g4 = (int)(gid % q4);
+    size_t br = gid / q4;
+    int row = (int)(br % S), b = (int)(br / S), tw = S / HARP_TILE;
+    int n = __ldg(bin_count + (size_t)b * tw * tw + (row / HARP_TILE) * tw + (g4 * 4) / HARP_TILE);
+    if (n == 0) {
+      size_t pix = br * S + (size_t)g4 * 4;
+      if (LIGHT) {
+        __stcs(reinterpret_cast<float4*>(a.zbuf + pix), make_float4(-1.f, -1.f, -1.f, -1.f));
+        __stcs(reinterpret_cast<int4*>(a.face + pix), make_int4(-1, -1, -1, -1));
       } else {
-        q = fast_inv_depth(f, e0, e1, e2);
-      }
-      if (inside) vis_update(c, ndc, px, py, f.fid, q, best_fid, best_q);
-      ++ncand;  // upper bound on the faces PyTorch3D would consider (exact top-K decision after the loop)
-      if (nzero > 0) continue;
-      if (cls == PAIR_SATURATED) { ++npass; ++nzero; continue; }
-      int slot = atomicAdd(&q_n, 1);
-      if (slot < QCAP) {
-        q_pix[slot] = (unsigned char)tid; q_face[slot] = (unsigned char)i;
-        if (q_last >= 0) q_next[q_last] = (unsigned short)slot; else q_first = slot;
-        q_last = slot;
-        ++q_mine;
-      } else {
-        q_overflow = true;
-        PairEval e;
-        eval_pair_full<true, true>(f, px, py, blur, e);
-        if (!e.pass) continue;
-        ++npass;
-        float om = 1.f - 1.f / (1.f + expf(fdiv(e.inside ? -e.dist : e.dist, sigma)));
-        if (om == 0.f) ++nzero; else prod *= om;
-      }
-    }
-    __syncthreads();
-    // B: drain the queue of band pairs with every thread busy
-    int qn = min(q_n, QCAP);
-    for (int s = tid; s < qn; s += NT) {
-      int p = q_pix[s];
-      float ppx = s_px[p % HARP_TILE], ppy = s_py[p / HARP_TILE];
-      PairEval e;
-      eval_pair_full<true, true>(faces[q_face[s]], ppx, ppy, blur, e);
-      if (e.pass) { q_sd[s] = e.inside ? -e.dist : e.dist; q_edge[s] = (unsigned char)e.edge; q_t[s] = e.t; }
-      else q_edge[s] = 255;
-    }
-    __syncthreads();
-    // C: every pixel folds its own chain in face-list order
-    if (nzero == 0) {
-      for (int s = q_first; q_mine > 0; --q_mine, s = q_next[s]) {
-        if (q_edge[s] == 255) continue;
-        ++npass;
-        float om = 1.f - 1.f / (1.f + expf(fdiv(q_sd[s], sigma)));
-        if (om == 0.f) { ++nzero; break; }
-        prod *= om;
+        __stcs(reinterpret_cast<float4*>(a.alpha + pix), make_float4(0.f, 0.f, 0.f, 0.f));
+        float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
+        float4* o = reinterpret_cast<float4*>(a.rgb + pix * 3);
+        __stcs(o, one); __stcs(o + 1, one); __stcs(o + 2, one);
+        if (SIL_BWD) {
+          float4 ys = __ldcs(reinterpret_cast<const float4*>(a.y_sil + pix));
+          s_sil = fabsf(ys.x) + fabsf(ys.y) + fabsf(ys.z) + fabsf(ys.w);
+        }
+        if (PHOTO) {
+          float4 mk = __ldcs(reinterpret_cast<const float4*>(a.y_mask + pix));
+          if (mk.x != 0.f || mk.y != 0.f || mk.z != 0.f || mk.w != 0.f) {  // rare: target foreground over an empty tile
+            const float4* yt = reinterpret_cast<const float4*>(a.y_true + pix * 3);
+            float4 y0 = __ldcs(yt), y1 = __ldcs(yt + 1), y2 = __ldcs(yt + 2);
+            s_ph = fabsf(mk.x - y0.x * mk.x) + fabsf(mk.x - y0.y * mk.x) + fabsf(mk.x - y0.z * mk.x) +
+                   fabsf(mk.y - y0.w * mk.y) + fabsf(mk.y - y1.x * mk.y) + fabsf(mk.y - y1.y * mk.y) +
+                   fabsf(mk.z - y1.z * mk.z) + fabsf(mk.z - y1.w * mk.z) + fabsf(mk.z - y2.x * mk.z) +
+                   fabsf(mk.w - y2.y * mk.w) + fabsf(mk.w - y2.z * mk.w) + fabsf(mk.w - y2.w * mk.w);
+          }
+        }
       }
     }
   }
-  // ---- visibility outputs: face id image + per-frame compacted hit list (warp-aggregated append)
-  bool hit = best_fid >= 0;
-  {
-    unsigned mask = __ballot_sync(0xffffffffu, hit);
-    int lane = tid & 31, base = 0;
-    if (mask) {
-      if (lane == 0) base = atomicAdd(a.hit_count + b, __popc(mask));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (hit) reinterpret_cast<int2*>(a.hit_list)[(size_t)b * S * S + base + __popc(mask & ((1u << lane) - 1u))] = make_int2(row * S + col, best_fid);
-    }
-  }
-  float photo_abs = 0.f;
-  if (!hit) {
-    st3(a.rgb + pix * 3, mk3(1.f, 1.f, 1.f));  // background colour (renderer_helper.py:430)
-    if (PHOTO) {
-      float mk = a.y_mask[pix];
-      f3 y = ld3(a.y_true + pix * 3);
-      photo_abs = fabsf(mk - y.x * mk) + fabsf(mk - y.y * mk) + fabsf(mk - y.z * mk);
-    }
-  }
-  // ---- silhouette value, loss and gradient
-  float al = nzero > 0 ? 1.f : 1.f - prod;
-  const bool deferred = ncand > a.K;  // more candidates than faces_per_pixel -> exact top-K kernel
-  if (deferred) sil_defer_overflow(c, (int)pix);
-  else a.alpha[pix] = al;
-  float diff = (deferred || !SIL_BWD) ? 0.f : al - a.y_sil[pix];
-  if (SIL_BWD || PHOTO) {
-    float s_sil = fabsf(diff), s_ph = photo_abs;
-    __syncthreads();  // red[] is free
-    block_sum2(s_sil, s_ph, red);
-    if (tid == 0) {
+  if (LIGHT || (!SIL_BWD && !PHOTO)) return;
+  if (__ballot_sync(0xffffffffu, s_sil != 0.f || s_ph != 0.f)) {
+    s_sil = warp_sum(s_sil); s_ph = warp_sum(s_ph);
+    if ((threadIdx.x & 31) == 0) {
       if (SIL_BWD && s_sil != 0.f) atomicAdd(a.sil_loss, s_sil * a.sil_inv_n);
       if (PHOTO && s_ph != 0.f) atomicAdd(a.photo_loss, s_ph * a.photo_inv_n);
-    }
-  }
-  if (!SIL_BWD) return;
-  float g = diff > 0.f ? a.sil_gscale : (diff < 0.f ? -a.sil_gscale : 0.f);
-  bool need = (g != 0.f) && nzero == 0 && prod > 0.f && npass > 0;
-  if (need) any_bwd = 1;
-  s_g[tid] = g; s_prod[tid] = prod; s_need[tid] = need ? 1 : 0;
-  int any_overflow = __syncthreads_or(q_overflow ? 1 : 0);
-  if (!any_bwd) return;
-  float* d_ndc = a.d_ndc + (size_t)b * c.V * 4;
-  if (n <= CHUNK && !any_overflow) {
-    int qn = min(q_n, QCAP);
-    for (int s = tid; s < qn; s += NT) {
-      int p = q_pix[s];
-      if (!s_need[p] || q_edge[s] == 255) continue;
-      float ppx = s_px[p % HARP_TILE], ppy = s_py[p / HARP_TILE];
-      sil_pair_gradient(c, faces[q_face[s]], ppx, ppy, q_sd[s], q_edge[s], q_t[s], s_g[p], s_prod[p], sigma, d_ndc);
-    }
-    return;
-  }
-  for (int base = 0; base < n; base += CHUNK) {  // generic path (multi-chunk tiles): re-stage and evaluate per pixel
-    int m = min(CHUNK, n - base);
-    __syncthreads();
-    if (tid < m) stage_face(c, ndc, list[base + tid], a.radius, faces[tid]);
-    __syncthreads();
-    if (!need) continue;
-    for (int i = 0; i < m; ++i) {
-      bool inside;
-      float e0, e1, e2;
-      int cls = classify_fast<true>(faces[i], px, py, far, sat, in_face_bbox(faces[i], px, py), inside, e0, e1, e2);
-      if (cls == PAIR_REJECT || cls == PAIR_SATURATED) continue;
-      PairEval e;
-      eval_pair_full<true, true>(faces[i], px, py, blur, e);
-      if (!e.pass) continue;
-      sil_pair_gradient(c, faces[i], px, py, e.inside ? -e.dist : e.dist, e.edge, e.t, g, prod, sigma, d_ndc);
     }
   }
 }
@@ -342,43 +600,43 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
     HARP_CHECK_CUDA(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, lo));
     HARP_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     HARP_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    HARP_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_bins, cudaEventDisableTiming));
   }
   cudaStream_t ss = c->side_stream;
   HARP_CHECK_CUDA(cudaEventRecord(c->ev_fork, st));
   harp_prof_begin(c, 6, st);
-  if ((rc = harp_project(c, B, S, focal, r->verts, r->cam_R, r->cam_T, c->ndc_cam, st)) != HARP_OK) return rc;
-  if ((rc = harp_build_bins(c, 0, B, S, radius, c->ndc_cam, st)) != HARP_OK) return rc;
+  if ((rc = harp_raster_setup(c, 0, B, S, focal, radius, r->verts, r->cam_R, r->cam_T, st)) != HARP_OK) return rc;
+  HARP_CHECK_CUDA(cudaEventRecord(c->ev_bins, st));
   if (sil_bwd || photo_bwd) HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_cam, 0, nv4, st));
   harp_prof_end(c, 6, st);
   HARP_CHECK_CUDA(cudaMemsetAsync(c->hit_count, 0, (size_t)B * sizeof(int32_t), st));
   HARP_CHECK_CUDA(cudaMemsetAsync(c->ovf_count, 0, sizeof(int32_t), st));
   VisArgs v{};
   v.S = S; v.K = r->faces_per_pixel > 0 ? r->faces_per_pixel : 50; v.sigma = r->sigma; v.blur = blur; v.radius = radius; v.ndc = c->ndc_cam;
-  v.bin_count = c->bin_count; v.bin_start = c->bin_start; v.bin_list = c->bin_list;
+  v.rec = c->face_rec; v.bin_list = c->bin_list; v.work = c->work; v.work_ctl = c->work_ctl; v.work_cap = c->maxB * c->tiles;
   v.alpha = r->alpha; v.y_sil = r->y_sil; v.sil_inv_n = 1.f / ((float)B * S * S); v.sil_gscale = r->w_sil * v.sil_inv_n;
   v.sil_loss = r->loss_sil; v.d_ndc = c->d_ndc_cam;
   v.hit_list = c->hit_list; v.hit_count = c->hit_count;
   v.rgb = r->rgb; v.y_true = r->y_true; v.y_mask = r->y_mask; v.photo_inv_n = 1.f / ((float)B * S * S * 3.f);
   v.photo_loss = r->loss_photo;
-  dim3 grid(S / HARP_TILE, S / HARP_TILE, B);
+  const int grid = HARP_SM_COUNT * HARP_PV_MINCTAS;  // persistent: every CTA pulls tiles until the queue is empty
   harp_prof_begin(c, 0, st);
-  if (sil_bwd && photo_bwd) pixel_vis_kernel<true, true><<<grid, NT, 0, st>>>(*c, v);
-  else if (sil_bwd) pixel_vis_kernel<true, false><<<grid, NT, 0, st>>>(*c, v);
-  else if (photo_bwd) pixel_vis_kernel<false, true><<<grid, NT, 0, st>>>(*c, v);
-  else pixel_vis_kernel<false, false><<<grid, NT, 0, st>>>(*c, v);
+  if (sil_bwd && photo_bwd) tile_raster_kernel<true, true, true><<<grid, NT, 0, st>>>(*c, v);
+  else if (sil_bwd) tile_raster_kernel<true, true, false><<<grid, NT, 0, st>>>(*c, v);
+  else if (photo_bwd) tile_raster_kernel<true, false, true><<<grid, NT, 0, st>>>(*c, v);
+  else tile_raster_kernel<true, false, false><<<grid, NT, 0, st>>>(*c, v);
   harp_prof_end(c, 0, st);
   HARP_LAUNCH_CHECK();
   if ((rc = harp_sil_topk(c, sil_bwd ? 2 : 0, S, v.K, r->sigma, blur, radius, r->alpha, r->y_sil, v.sil_gscale, v.sil_inv_n,
                           r->loss_sil, st)) != HARP_OK) return rc;
   // Side branch on the ctx's own (least-priority) stream, concurrent with the camera branch above and joined before the
-  // deferred shading: everything only the shading needs — the light view (projection, bins, nearest-depth raster), the
-  // packed texel copies, and the zero fills of the shading's gradient accumulators (92 MB at 64 x 512^2).
-  // Event fork / join is capturable into a CUDA graph.
+  // deferred shading: everything only the shading needs — the light view (setup, nearest-depth raster), the packed texel
+  // copies, the zero fills of the shading's gradient accumulators — and the HBM-bound streaming pass over the camera view's
+  // empty tiles, which overlaps the issue-bound tile rasteriser.  Event fork / join is capturable into a CUDA graph.
   HARP_CHECK_CUDA(cudaStreamWaitEvent(ss, c->ev_fork, 0));
   if (r->self_shadow) {
-    if ((rc = harp_project(c, B, S, focal, r->verts, r->light_R, r->light_T, c->ndc_light, ss)) != HARP_OK) return rc;
-    if ((rc = harp_build_bins(c, 1, B, S, 0.f, c->ndc_light, ss)) != HARP_OK) return rc;
-    if ((rc = harp_light_depth(c, B, S, ss)) != HARP_OK) return rc;
+    if ((rc = harp_raster_setup(c, 1, B, S, focal, 0.f, r->verts, r->light_R, r->light_T, ss)) != HARP_OK) return rc;
+    if ((rc = harp_light_depth_tiles(c, B, S, ss)) != HARP_OK) return rc;
   }
   if ((rc = harp_tex_prepare(c, r->texture, r->normal_map, r->texH, r->texW, ss)) != HARP_OK) return rc;
   if (photo_bwd) {
@@ -389,6 +647,15 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
       HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_light, 0, nv4, ss));
       HARP_CHECK_CUDA(cudaMemsetAsync(c->d_light_zbuf, 0, npx * sizeof(float), ss));
     }
+  }
+  {
+    HARP_CHECK_CUDA(cudaStreamWaitEvent(ss, c->ev_bins, 0));
+    const int eg = (int)(((size_t)B * S * (S / 4) + 255) / 256);
+    if (sil_bwd && photo_bwd) empty_tiles_kernel<false, true, true><<<eg, 256, 0, ss>>>(B, S, c->bin_count, v);
+    else if (sil_bwd) empty_tiles_kernel<false, true, false><<<eg, 256, 0, ss>>>(B, S, c->bin_count, v);
+    else if (photo_bwd) empty_tiles_kernel<false, false, true><<<eg, 256, 0, ss>>>(B, S, c->bin_count, v);
+    else empty_tiles_kernel<false, false, false><<<eg, 256, 0, ss>>>(B, S, c->bin_count, v);
+    HARP_LAUNCH_CHECK();
   }
   HARP_CHECK_CUDA(cudaEventRecord(c->ev_join, ss));
   HARP_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
@@ -428,5 +695,22 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
                                r->grads.d_cam_T, st)) != HARP_OK) return rc;
   }
   harp_prof_end(c, 7, st);
+  return HARP_OK;
+}
+
+// Light-view nearest depth + face id with the persistent tile rasteriser (setup of view 1 must be current).
+int harp_light_depth_tiles(harp_ctx* c, int B, int S, cudaStream_t st) {
+  VisArgs v{};
+  v.S = S; v.K = 1; v.sigma = 0.f; v.blur = 0.f; v.radius = 0.f; v.ndc = c->ndc_light;
+  v.rec = c->face_rec + (size_t)c->maxB * c->F;
+  v.bin_list = c->bin_list + (size_t)c->maxB * c->bin_cap;
+  v.work_cap = c->maxB * c->tiles;
+  v.work = c->work + v.work_cap;
+  v.work_ctl = c->work_ctl + 4;
+  v.zbuf = c->light_zbuf; v.face = c->light_face;
+  tile_raster_kernel<false, false, false><<<HARP_SM_COUNT * HARP_PV_MINCTAS, NT, 0, st>>>(*c, v);
+  const int eg = (int)(((size_t)B * S * (S / 4) + 255) / 256);
+  empty_tiles_kernel<true, false, false><<<eg, 256, 0, st>>>(B, S, c->bin_count + (size_t)c->maxB * c->tiles, v);
+  HARP_LAUNCH_CHECK_N(2);
   return HARP_OK;
 }

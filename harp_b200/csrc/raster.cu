@@ -4,28 +4,15 @@
 // (367 MB per 512^2 frame); here a pixel's candidate faces live in shared memory and nothing but alpha is written.
 #include "raster.cuh"
 
+int harp_raster_setup(harp_ctx* c, int view, int B, int S, float focal, float radius, const float* verts, const float* R,
+                      const float* T, cudaStream_t st);
+
 namespace {
 
 constexpr int TPB = 256;
 constexpr int CHUNK = 64;  // faces staged per shared-memory round
 
-// ---- projection: X_view = X R + T ; ndc_xy = (f X/Z) / (S/2) ; keep view z   ---------------------------
-__global__ void __launch_bounds__(TPB) project_kernel(int B, int V, const float* __restrict__ verts, const float* __restrict__ R,
-                                                       const float* __restrict__ T, float focal, float half_s,
-                                                       float* __restrict__ ndc) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * V) return;
-  int b = idx / V;
-  const float* r = R + (size_t)b * 9;
-  const float* t = T + (size_t)b * 3;
-  f3 p = ld3(verts + (size_t)idx * 3);
-  float X = p.x * r[0] + p.y * r[3] + p.z * r[6] + t[0];
-  float Y = p.x * r[1] + p.y * r[4] + p.z * r[7] + t[1];
-  float Z = p.x * r[2] + p.y * r[5] + p.z * r[8] + t[2];
-  st3(ndc + (size_t)idx * 3, mk3((focal * X / Z) / half_s, (focal * Y / Z) / half_s, Z));
-}
-
-// backward of project_kernel: d_ndc (B,V,4: xyz + pad) -> d_verts += , d_R += , d_T +=
+// backward of the projection (setup.cu, phase 0): d_ndc (B,V,4: xyz + pad) -> d_verts += , d_R += , d_T +=
 __global__ void __launch_bounds__(TPB) project_bwd_kernel(int B, int V, const float* __restrict__ verts, const float* __restrict__ R,
                                                            const float* __restrict__ T, float focal, float half_s,
                                                            const float* __restrict__ d_ndc, float* __restrict__ d_verts,
@@ -67,130 +54,6 @@ __global__ void __launch_bounds__(TPB) project_bwd_kernel(int B, int V, const fl
     if (i >= 9 && !d_T) continue;
     float s = block_sum(acc[i], red);
     if (threadIdx.x == 0 && s != 0.f) atomicAdd(i < 9 ? d_R + (size_t)b * 9 + i : d_T + (size_t)b * 3 + (i - 9), s);
-  }
-}
-
-// ---- binning ---------------------------------------------------------------------------------------------------------
-// Pixel column j has x_ndc = 1 - (2j+1)/S (decreasing); a face with inflated bbox [lo,hi] can touch columns
-// ceil((1-hi) S/2 - 0.5) .. floor((1-lo) S/2 - 0.5); a 0.01 px guard absorbs rounding (the exact test runs per pixel).
-// Per-face binning record: the tile range of the inflated bbox plus what the per-tile edge test needs.
-struct BinFace {
-  int tx0, tx1, ty0, ty1;
-  bool edge_test;            // all three view depths > 0: inside/outside is decided by the edge functions alone
-  float x0, y0, x1, y1, x2, y2, sgn;
-  float thr12, thr20, thr01;  // squared edge length x (1.05 blur + guard): a tile farther than this outside an edge line is skipped
-};
-
-__device__ __forceinline__ bool face_tile_range(const harp_ctx& c, const float* ndc, int f, float radius, int S, BinFace& r) {
-  const int32_t* fv = c.faces + (size_t)f * 3;
-  const float *a = ndc + (size_t)fv[0] * 3, *b = ndc + (size_t)fv[1] * 3, *d = ndc + (size_t)fv[2] * 3;
-  float zmax = fmaxf(fmaxf(a[2], b[2]), d[2]);
-  float area = edge_fn(a[0], a[1], b[0], b[1], d[0], d[1]);  // EdgeFunctionForward(v0, v1, v2)
-  if (zmax < 0.f || (area <= HARP_K_EPS && area >= -HARP_K_EPS)) return false;
-  if (!(area == area)) return false;  // NaN guard
-  float xmin = fminf(fminf(a[0], b[0]), d[0]) - radius, xmax = fmaxf(fmaxf(a[0], b[0]), d[0]) + radius;
-  float ymin = fminf(fminf(a[1], b[1]), d[1]) - radius, ymax = fmaxf(fmaxf(a[1], b[1]), d[1]) + radius;
-  float hs = 0.5f * (float)S;
-  float jlo = ceilf((1.f - xmax) * hs - 0.5f - 0.01f), jhi = floorf((1.f - xmin) * hs - 0.5f + 0.01f);
-  float ilo = ceilf((1.f - ymax) * hs - 0.5f - 0.01f), ihi = floorf((1.f - ymin) * hs - 0.5f + 0.01f);
-  jlo = fmaxf(jlo, 0.f); ilo = fmaxf(ilo, 0.f);
-  jhi = fminf(jhi, (float)(S - 1)); ihi = fminf(ihi, (float)(S - 1));
-  if (jlo > jhi || ilo > ihi) return false;
-  r.tx0 = (int)jlo / HARP_TILE; r.tx1 = (int)jhi / HARP_TILE;
-  r.ty0 = (int)ilo / HARP_TILE; r.ty1 = (int)ihi / HARP_TILE;
-  // Per-tile edge test (only worth it when the bbox spans several tiles).  Pixel pairs of a skipped tile are exactly those
-  // classify_pair rejects: every pixel centre lies outside one edge LINE by more than sqrt(1.05 blur) (+1e-5 NDC guard, four
-  // orders above the fp32 error of an edge function), and the distance to the triangle is at least the distance to that line.
-  r.edge_test = fminf(fminf(a[2], b[2]), d[2]) > 0.f && (r.tx1 > r.tx0 || r.ty1 > r.ty0);
-  if (r.edge_test) {
-    r.x0 = a[0]; r.y0 = a[1]; r.x1 = b[0]; r.y1 = b[1]; r.x2 = d[0]; r.y2 = d[1];
-    r.sgn = fadd(edge_fn(r.x2, r.y2, r.x0, r.y0, r.x1, r.y1), HARP_K_EPS) > 0.f ? 1.f : -1.f;  // sign of FaceRec::area
-    float m = 1.05f * radius * radius + 1e-10f;
-    r.thr12 = m * ((r.x2 - r.x1) * (r.x2 - r.x1) + (r.y2 - r.y1) * (r.y2 - r.y1));
-    r.thr20 = m * ((r.x0 - r.x2) * (r.x0 - r.x2) + (r.y0 - r.y2) * (r.y0 - r.y2));
-    r.thr01 = m * ((r.x1 - r.x0) * (r.x1 - r.x0) + (r.y1 - r.y0) * (r.y1 - r.y0));
-  }
-  return true;
-}
-
-// largest signed edge function over the four corner pixel centres of a tile (the function is affine in the pixel position)
-__device__ __forceinline__ float tile_max_edge(float sgn, float xa, float xb, float ya, float yb, float ax, float ay, float bx,
-                                               float by) {
-  float dx = bx - ax, dy = by - ay;
-  float ea = (xa - ax) * dy, eb = (xb - ax) * dy, fa = (ya - ay) * dx, fb = (yb - ay) * dx;
-  return fmaxf(fmaxf(sgn * (ea - fa), sgn * (ea - fb)), fmaxf(sgn * (eb - fa), sgn * (eb - fb)));
-}
-
-__device__ __forceinline__ bool tile_outside_face(const BinFace& r, int tx, int ty, int S) {
-  float xa = pix_to_ndc(tx * HARP_TILE, S), xb = pix_to_ndc(tx * HARP_TILE + HARP_TILE - 1, S);
-  float ya = pix_to_ndc(ty * HARP_TILE, S), yb = pix_to_ndc(ty * HARP_TILE + HARP_TILE - 1, S);
-  float m0 = tile_max_edge(r.sgn, xa, xb, ya, yb, r.x1, r.y1, r.x2, r.y2);  // e0 = EdgeFunction(p, v1, v2)
-  if (m0 < 0.f && m0 * m0 >= r.thr12) return true;
-  float m1 = tile_max_edge(r.sgn, xa, xb, ya, yb, r.x2, r.y2, r.x0, r.y0);
-  if (m1 < 0.f && m1 * m1 >= r.thr20) return true;
-  float m2 = tile_max_edge(r.sgn, xa, xb, ya, yb, r.x0, r.y0, r.x1, r.y1);
-  return m2 < 0.f && m2 * m2 >= r.thr01;
-}
-
-template <bool FILL>
-__global__ void __launch_bounds__(TPB) bin_kernel(harp_ctx c, int B, int S, float radius, const float* __restrict__ ndc,
-                                                   int32_t* __restrict__ count, const int32_t* __restrict__ start,
-                                                   int32_t* __restrict__ fill, int32_t* __restrict__ list) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * c.F) return;
-  int b = idx / c.F, f = idx % c.F;
-  BinFace r;
-  if (!face_tile_range(c, ndc + (size_t)b * c.V * 3, f, radius, S, r)) return;
-  int tw = S / HARP_TILE;
-  size_t tb = (size_t)b * tw * tw;
-  for (int ty = r.ty0; ty <= r.ty1; ++ty)
-    for (int tx = r.tx0; tx <= r.tx1; ++tx) {
-      if (r.edge_test && tile_outside_face(r, tx, ty, S)) continue;  // deterministic: count and fill passes agree
-      size_t t = tb + (size_t)ty * tw + tx;
-      if (!FILL) {
-        atomicAdd(count + t, 1);
-      } else {
-        int slot = start[t] + atomicAdd(fill + t, 1);
-        if (slot < c.bin_cap) list[(size_t)b * c.bin_cap + slot] = f;
-      }
-    }
-}
-
-// exclusive scan of one frame's tile counts (one CTA per frame)
-__global__ void __launch_bounds__(1024) bin_scan_kernel(harp_ctx c, int tiles, const int32_t* __restrict__ count,
-                                                         int32_t* __restrict__ start) {
-  __shared__ int wsum[32];
-  int b = blockIdx.x, t = threadIdx.x;
-  int per = (tiles + 1023) / 1024;
-  const int32_t* cnt = count + (size_t)b * tiles;
-  int32_t* st = start + (size_t)b * tiles;
-  int lo = t * per, hi = min(lo + per, tiles);
-  int local = 0;
-  for (int i = lo; i < hi; ++i) local += cnt[i];
-  int lane = t & 31, w = t >> 5;
-  int incl = local;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int n = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += n;
-  }
-  if (lane == 31) wsum[w] = incl;
-  __syncthreads();
-  if (w == 0) {
-    int v = wsum[lane], iv = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int n = __shfl_up_sync(0xffffffffu, iv, o);
-      if (lane >= o) iv += n;
-    }
-    wsum[lane] = iv - v;
-    if (lane == 31 && iv > c.bin_cap) atomicAdd(c.counters + 1, 1ULL);
-  }
-  __syncthreads();
-  int run = wsum[w] + incl - local;
-  for (int i = lo; i < hi; ++i) {
-    st[i] = run;
-    run += cnt[i];
   }
 }
 
@@ -453,29 +316,6 @@ int harp_fold4(size_t n, const float* src4, float* dst3, cudaStream_t st) {
   return HARP_OK;
 }
 
-// Build the bin lists of one view (0 = camera, 1 = light) for B frames from already-projected verts.
-int harp_build_bins(harp_ctx* c, int view, int B, int S, float radius, const float* ndc, cudaStream_t st) {
-  size_t nt = (size_t)B * c->tiles;
-  int32_t* count = c->bin_count + (size_t)view * c->maxB * c->tiles;
-  int32_t* start = c->bin_start + (size_t)view * c->maxB * c->tiles;
-  int32_t* fill = c->bin_fill + (size_t)view * c->maxB * c->tiles;
-  int32_t* list = c->bin_list + (size_t)view * c->maxB * c->bin_cap;
-  HARP_CHECK_CUDA(cudaMemsetAsync(count, 0, nt * sizeof(int32_t), st));
-  HARP_CHECK_CUDA(cudaMemsetAsync(fill, 0, nt * sizeof(int32_t), st));
-  bin_kernel<false><<<nblk((size_t)B * c->F), TPB, 0, st>>>(*c, B, S, radius, ndc, count, start, fill, list);
-  bin_scan_kernel<<<B, 1024, 0, st>>>(*c, c->tiles, count, start);
-  bin_kernel<true><<<nblk((size_t)B * c->F), TPB, 0, st>>>(*c, B, S, radius, ndc, count, start, fill, list);
-  HARP_LAUNCH_CHECK_N(3);
-  return HARP_OK;
-}
-
-int harp_project(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R, const float* T, float* ndc,
-                 cudaStream_t st) {
-  project_kernel<<<nblk((size_t)B * c->V), TPB, 0, st>>>(B, c->V, verts, R, T, focal, 0.5f * (float)S, ndc);
-  HARP_LAUNCH_CHECK();
-  return HARP_OK;
-}
-
 int harp_project_bwd(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R, const float* T,
                      const float* d_ndc, float* d_verts, float* d_R, float* d_T, cudaStream_t st) {
   dim3 grid((c->V + TPB - 1) / TPB, B);
@@ -498,8 +338,7 @@ extern "C" int harp_silhouette(harp_ctx* c, int mode, int B, int S, float focal,
   double blur_d = 9.210240366975849 * (double)sigma;
   float blur = (float)blur_d, radius = (float)sqrt(blur_d);
   int rc;
-  if ((rc = harp_project(c, B, S, focal, verts, R, T, c->ndc_cam, st)) != HARP_OK) return rc;
-  if ((rc = harp_build_bins(c, 0, B, S, radius, c->ndc_cam, st)) != HARP_OK) return rc;
+  if ((rc = harp_raster_setup(c, 0, B, S, focal, radius, verts, R, T, st)) != HARP_OK) return rc;
   if (mode != 0) HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_cam, 0, (size_t)B * c->V * 4 * sizeof(float), st));
   HARP_CHECK_CUDA(cudaMemsetAsync(c->ovf_count, 0, sizeof(int32_t), st));
   const int K = faces_per_pixel > 0 ? faces_per_pixel : 50;

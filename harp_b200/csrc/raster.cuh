@@ -217,13 +217,16 @@ struct __align__(16) FaceTile {
   float iz0, iz1, iz2, sgn;
   float z0, z1, z2;
   int fid;
-};  // 128 B; the vertex ids (needed by the rare gradient path only) are re-read from the face table
+  // pixel rectangle of the inflated bbox (0.01 px guard; the exact float bbox test still runs per pair): columns
+  // jlo | jhi << 16, rows ilo | ihi << 16; jlo > jhi marks a face the rasteriser skips outright (behind the camera, zero area,
+  // off screen).  Written by the per-frame setup kernel (setup.cu), which owns the binning; zero when staged by stage_face.
+  int cols, rows;
+  int pad0, pad1;
+};  // 144 B = 9 x 16 B: consecutive records start 4 banks apart, so the 2-3 records a warp touches per LDS.128 do not collide.
+    // The vertex ids (needed by the rare gradient path only) are re-read from the face table.
 
-__device__ __forceinline__ void stage_face(const harp_ctx& c, const float* ndc, int fid, float radius, FaceTile& f) {
-  const int32_t* fv = c.faces + (size_t)fid * 3;
-  int v0 = fv[0], v1 = fv[1], v2 = fv[2];
-  const float *a = ndc + (size_t)v0 * 3, *b = ndc + (size_t)v1 * 3, *d = ndc + (size_t)v2 * 3;
-  float x0 = a[0], y0 = a[1], z0 = a[2], x1 = b[0], y1 = b[1], z1 = b[2], x2 = d[0], y2 = d[1], z2 = d[2];
+__device__ __forceinline__ void make_face_record(float x0, float y0, float z0, float x1, float y1, float z1, float x2, float y2,
+                                                 float z2, int fid, float radius, FaceTile& f) {
   f.x0 = x0; f.y0 = y0; f.x1 = x1; f.y1 = y1; f.x2 = x2; f.y2 = y2;
   f.z0 = z0; f.z1 = z1; f.z2 = z2; f.fid = fid;
   f.xmin = fsub(fminf(fminf(x0, x1), x2), radius);
@@ -250,6 +253,13 @@ __device__ __forceinline__ void stage_face(const harp_ctx& c, const float* ndc, 
   f.il20 = 1.f / (d20x * d20x + d20y * d20y);
   f.il01 = 1.f / (d01x * d01x + d01y * d01y);
   f.iz0 = 1.f / z0; f.iz1 = 1.f / z1; f.iz2 = 1.f / z2;
+  f.cols = f.rows = f.pad0 = f.pad1 = 0;
+}
+
+__device__ __forceinline__ void stage_face(const harp_ctx& c, const float* ndc, int fid, float radius, FaceTile& f) {
+  const int32_t* fv = c.faces + (size_t)fid * 3;
+  const float *a = ndc + (size_t)fv[0] * 3, *b = ndc + (size_t)fv[1] * 3, *d = ndc + (size_t)fv[2] * 3;
+  make_face_record(a[0], a[1], a[2], b[0], b[1], b[2], d[0], d[1], d[2], fid, radius, f);
 }
 
 // Classification of one (pixel, face) pair against a staged FaceTile; same decisions as classify_pair_vis (the exactness

@@ -6,9 +6,8 @@
 // One pass per pixel, nothing staged in HBM except the light-view depth/face buffers the PCF taps must read.
 #include "shade_pixel.cuh"
 
-int harp_build_bins(harp_ctx* c, int view, int B, int S, float radius, const float* ndc, cudaStream_t st);
-int harp_project(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R, const float* T, float* ndc,
-                 cudaStream_t st);
+int harp_raster_setup(harp_ctx* c, int view, int B, int S, float focal, float radius, const float* verts, const float* R,
+                      const float* T, cudaStream_t st);
 int harp_project_bwd(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R, const float* T,
                      const float* d_ndc, float* d_verts, float* d_R, float* d_T, cudaStream_t st);
 int harp_fold4(size_t n, const float* src4, float* dst3, cudaStream_t st);
@@ -262,8 +261,7 @@ extern "C" int harp_render_normals(harp_ctx* c, int B, int S, float focal, int K
   HARP_REQUIRE(B <= c->maxB && S == c->S, HARP_ERR_CAPACITY, "harp_render_normals: call harp_ctx_reserve(B, S) first");
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  if ((rc = harp_project(c, B, S, focal, verts, R, T, c->ndc_cam, st)) != HARP_OK) return rc;
-  if ((rc = harp_build_bins(c, 0, B, S, 0.f, c->ndc_cam, st)) != HARP_OK) return rc;
+  if ((rc = harp_raster_setup(c, 0, B, S, focal, 0.f, verts, R, T, st)) != HARP_OK) return rc;
   dim3 grid(S / HARP_TILE, S / HARP_TILE, B);
   normal_render_kernel<<<grid, NT, 0, st>>>(*c, S, K, c->ndc_cam, normals, normal_map, texH, texW, c->bin_count, c->bin_start,
                                             c->bin_list, rgb);
@@ -324,12 +322,10 @@ extern "C" int harp_shade(harp_ctx* c, int mode, int B, int S, float focal, int 
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   size_t npx = (size_t)B * S * S;
-  if ((rc = harp_project(c, B, S, focal, verts, cam_R, cam_T, c->ndc_cam, st)) != HARP_OK) return rc;
-  if ((rc = harp_build_bins(c, 0, B, S, 0.f, c->ndc_cam, st)) != HARP_OK) return rc;
+  if ((rc = harp_raster_setup(c, 0, B, S, focal, 0.f, verts, cam_R, cam_T, st)) != HARP_OK) return rc;
   dim3 grid(S / HARP_TILE, S / HARP_TILE, B);
   if (self_shadow) {
-    if ((rc = harp_project(c, B, S, focal, verts, light_R, light_T, c->ndc_light, st)) != HARP_OK) return rc;
-    if ((rc = harp_build_bins(c, 1, B, S, 0.f, c->ndc_light, st)) != HARP_OK) return rc;
+    if ((rc = harp_raster_setup(c, 1, B, S, focal, 0.f, verts, light_R, light_T, st)) != HARP_OK) return rc;
     size_t voff = (size_t)c->maxB * c->tiles;
     light_depth_kernel<<<grid, NT, 0, st>>>(*c, S, c->ndc_light, c->bin_count + voff, c->bin_start + voff,
                                             c->bin_list + (size_t)c->maxB * c->bin_cap, c->light_zbuf, c->light_face);

@@ -22,8 +22,8 @@ def _metrics(ref_image, ref_mask, pred_image, pred_mask):
         raise ValueError("image metrics need (B,S,S,3) images and (B,S,S) masks of one size")
     l1 = torch.zeros(1, device=ref_image.device)
     iu = torch.zeros(2, B, dtype=torch.int32, device=ref_image.device)
-    check(_lib.lib().harp_image_metrics(B, S, ptr(ref_image), ptr(pred_image), ptr(ref_mask), ptr(pred_mask), ptr(l1), ptr(iu[0]),
-                                        ptr(iu[1]), stream()))
+    check(_lib.lib().harp_image_metrics(B, S, ptr(ref_image), ptr(pred_image), ptr(ref_mask), ptr(pred_mask), ptr(l1), _lib.iptr(iu[0]),
+                                        _lib.iptr(iu[1]), stream()))
     return l1 / (3.0 * B * S * S), iu
 
 

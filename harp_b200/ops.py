@@ -101,13 +101,18 @@ class HarpContext:
             pass
 
     def reserve(self, B, S):
-        """Size the ctx scratch for <= B frames of S x S (harp_ctx_reserve); grows monotonically for a fixed S."""
+        """Size the ctx scratch for <= B frames of S x S (harp_ctx_reserve).  The batch capacity never shrinks; a request that
+        would move the scratch while a captured CUDA graph still replays into it (`pin`) raises instead of freeing it."""
         rb, rs = self._reserved
         if B > rb or S != rs:
-            nb = max(B, rb) if S == rs else B
+            nb = max(B, rb)
             with torch.cuda.device(self.device):
                 check(_lib.lib().harp_ctx_reserve(self.h, int(nb), int(S)))
             self._reserved = (nb, S)
+
+    def pin(self, delta=1):
+        """A captured CUDA graph holds this context's scratch pointers: pin(+1) at capture, pin(-1) when the graph dies."""
+        check(_lib.lib().harp_ctx_pin(self.h, int(delta)))
 
     def faces(self):
         """(F,3) int64 face list of the (subdivided) mesh, as `Meshes.faces_padded()[0]`."""
@@ -374,7 +379,7 @@ class TextureReg(torch.autograd.Function):
         m = _c(uv_mask) if uv_mask is not None else None
         loss = torch.zeros(1, device=t.device)
         d = torch.zeros_like(t)
-        check(_lib.lib().harp_texture_reg(hc.h if hc is not None else None, int(kind), ptr(t), H, W, ptr(off), ptr(m), 1.0,
+        check(_lib.lib().harp_texture_reg(hc.h if hc is not None else None, int(kind), ptr(t), H, W, _lib.iptr(off), ptr(m), 1.0,
                                           ptr(loss), ptr(d), stream()))
         ctx.save_for_backward(d)
         ctx.shape = tex.shape
@@ -402,7 +407,7 @@ def ingest_u8(rgb_u8, mask_u8, out=None):
     if out is None:
         out = dict(y_true=torch.empty(B, S, S, 3, device=dev), y_sil=torch.empty(B, S, S, device=dev),
                    y_sil_eroded=torch.empty(B, S, S, device=dev))
-    check(_lib.lib().harp_ingest_u8(B, S, ptr(rgb_u8), ptr(mask_u8), ptr(out["y_true"]), ptr(out["y_sil"]), ptr(out["y_sil_eroded"]),
+    check(_lib.lib().harp_ingest_u8(B, S, _lib.bptr(rgb_u8), _lib.bptr(mask_u8), ptr(out["y_true"]), ptr(out["y_sil"]), ptr(out["y_sil_eroded"]),
                                     stream()))
     return out
 

@@ -14,7 +14,7 @@ import ctypes as C
 import torch
 
 from . import _lib, camera
-from ._lib import HarpRenderArgs, HarpShadeGrads, check, ptr, stream
+from ._lib import HarpRenderArgs, HarpShadeGrads, check, iptr, lptr, ptr, stream
 
 # slots 1..5 are contiguous in harp_mesh_losses' output order
 LOSS_NAMES = ("silhouette", "laplacian", "normal", "arap", "kps_anchor", "vert_disp_reg", "photo", "albedo", "normal_reg")
@@ -249,7 +249,7 @@ class HarpFitter:
                                              (("cTc", 3), ("light_bc", 3), ("lRc", 9), ("lTc", 3), ("centroid", 3)))
         ambc = self._buf("ambc", (1,), zero=False)
         light_shared = A["light_positions"][0]  # share_light_position (optimize_sequence.py:453-454)
-        check(L.harp_frame_glue_fwd(hc.h, B, S, focal, ptr(P["cam"]), ptr(fid), ptr(light_shared), ptr(A["amb_ratio"]), ptr(verts),
+        check(L.harp_frame_glue_fwd(hc.h, B, S, focal, ptr(P["cam"]), lptr(fid), ptr(light_shared), ptr(A["amb_ratio"]), ptr(verts),
                                     ptr(cTc), ptr(light_bc), ptr(lRc), ptr(lTc), ptr(ambc), ptr(centroid), st))
         W = LOSS_WEIGHTS
         # ---- both renders (silhouette 469-471 and shadowed colour 474-488 run in every stage; their losses are gated by
@@ -274,9 +274,9 @@ class HarpFitter:
         with torch.cuda.stream(side):
             ss = stream()
             if app_on:
-                check(L.harp_texture_reg(hc.h, 0, ptr(tex), H, Wd, ptr(off_albedo), ptr(self.uv_mask), W["albedo"] * fscale,
+                check(L.harp_texture_reg(hc.h, 0, ptr(tex), H, Wd, iptr(off_albedo), ptr(self.uv_mask), W["albedo"] * fscale,
                                          ptr(self.losses[_SLOT["albedo"]:]), ptr(self.app.g["texture"]), ss))
-                check(L.harp_texture_reg(hc.h, 1, ptr(nm), H, Wd, ptr(off_normal), ptr(self.uv_mask), W["normal_reg"] * fscale,
+                check(L.harp_texture_reg(hc.h, 1, ptr(nm), H, Wd, iptr(off_normal), ptr(self.uv_mask), W["normal_reg"] * fscale,
                                          ptr(self.losses[_SLOT["normal_reg"]:]), ptr(self.app.g["normal_map"]), ss))
             if coarse_on:
                 w5 = (C.c_float * 5)(W["laplacian"] * fscale, W["normal"] * fscale, W["arap"] * fscale, W["kps_anchor"] * fscale,
@@ -290,7 +290,7 @@ class HarpFitter:
             after_render()
         # ---- backward through the small per-frame chain, then geometry
         if coarse_on or app_on:
-            check(L.harp_frame_glue_bwd(hc.h, B, S, focal, ptr(P["cam"]), ptr(fid), ptr(light_shared), ptr(A["amb_ratio"]),
+            check(L.harp_frame_glue_bwd(hc.h, B, S, focal, ptr(P["cam"]), lptr(fid), ptr(light_shared), ptr(A["amb_ratio"]),
                                         ptr(centroid), ptr(d_cT), ptr(d_lR), ptr(d_lT), ptr(d_lpos), ptr(d_amb),
                                         ptr(self.coarse.g["cam"]), ptr(self.app.g["light_positions"]), ptr(self.app.g["amb_ratio"]),
                                         ptr(d_verts), st))
@@ -348,7 +348,7 @@ class HarpFitter:
             self._capture_stream = torch.cuda.Stream(device=self.hc.device, priority=-1)
         with torch.cuda.graph(graph, stream=self._capture_stream):
             self.step(fid, off_albedo, off_normal, update=not multi, exchange=False, **kw)
-        self._graph = graph
+        self._set_graph(graph)
         if not multi:
             return graph.replay
 
@@ -409,7 +409,7 @@ class HarpFitter:
             raise
         cur.wait_stream(cap)
         torch.cuda.synchronize()
-        self._graph = (g1, g2)
+        self._set_graph((g1, g2))
         nc, nl = self.coarse.grad.numel(), len(LOSS_NAMES)
         app0 = nc + nl
         o = dict(zip(self.app.names, self.app.offsets))
@@ -432,6 +432,28 @@ class HarpFitter:
             self._gbuf[self._loss_slice] /= R
             self._update(stage)
         return replay
+
+    def _set_graph(self, graph):
+        """Keep every captured graph and pin the context's scratch for as long as they live (a later harp_ctx_reserve with
+        a larger batch or another image size must not free memory a graph still replays into)."""
+        if getattr(self, "_graphs", None) is None:
+            self._graphs = []
+        self._graphs.append(graph)
+        self._graph = graph
+        self.hc.pin(+1)
+
+    def release_graph(self):
+        """Drop all captured graphs of this fitter and unpin the context."""
+        n = len(getattr(self, "_graphs", None) or [])
+        self._graphs, self._graph = [], None
+        if n:
+            self.hc.pin(-n)
+
+    def __del__(self):
+        try:
+            self.release_graph()
+        except Exception:
+            pass
 
     def _allreduce_shared(self):
         allreduce_shared_inplace(self._gbuf, self._shared_start, self._shared_stop, self._loss_slice, self.world_size, self.pg)

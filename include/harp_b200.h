@@ -98,6 +98,11 @@ HARP_API void harp_ctx_destroy(harp_ctx* ctx);
 /* Size all scratch (bin lists, projected verts, light depth, per-frame Jacobians) for <= max_batch frames of
  * img_size x img_size.  Allocates; call outside the hot loop. */
 HARP_API int harp_ctx_reserve(harp_ctx* ctx, int max_batch, int img_size);
+/* Kernels receive the ctx by value, so a captured CUDA graph holds the scratch pointers.  A caller that captures calls on this
+ * ctx pins it (delta = +1) for the graph's lifetime and unpins it (-1) when the graph is destroyed; while pinned,
+ * harp_ctx_reserve refuses (HARP_ERR_CAPACITY) any request that would move the scratch instead of freeing memory a graph still
+ * replays into.  The batch capacity never shrinks.  A ctx must not be used from two streams concurrently. */
+HARP_API int harp_ctx_pin(harp_ctx* ctx, int delta);
 HARP_API int harp_ctx_dims(const harp_ctx* ctx, int32_t* V0, int32_t* V, int32_t* F, int32_t* E);
 /* Copy the (F,3) int32 (subdivided) face list to [host] memory, for callers that need Meshes.faces_padded(). */
 HARP_API int harp_ctx_faces(const harp_ctx* ctx, int32_t* faces_out);

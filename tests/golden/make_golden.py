@@ -156,7 +156,7 @@ def reference_step(pack, tmpl, p, batch, S, focal, subdivide, stage, seed_albedo
     return loss, dict(sil=y_sil_pred, rgb=y_pred, verts=hand_verts, joints=hand_joints, sil_overflow=sil_overflow, **extra)
 
 
-def scenario(name, S, B, subdivide, stage, dtype=torch.float32, trans_amp=0.0, arm=False):
+def scenario(name, S, B, subdivide, stage, dtype=torch.float32, trans_amp=0.0, arm=False, eval_renders=None):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import harp_oracle as O
     tmpl = synth.load_template("arm" if arm else "hand")
@@ -197,7 +197,8 @@ def scenario(name, S, B, subdivide, stage, dtype=torch.float32, trans_amp=0.0, a
                                              for k, v in P.items()}, d1, S, focal, subdivide, "both", 11, 12, arm=arm)
         ref_verts = im0["verts"][:1].clone()
     batch = dict(y_sil=y_sil, y_sil_eroded=y_er, y_true=y_true, init_joints=init_joints, ref_verts=ref_verts, uv_mask=uv_mask)
-    loss, im = reference_step(pack, tmpl, leaf, batch, S, focal, subdivide, stage, 11, 12, arm=arm, eval_renders=(name.startswith("c2")))
+    loss, im = reference_step(pack, tmpl, leaf, batch, S, focal, subdivide, stage, 11, 12, arm=arm,
+                              eval_renders=(name == "c2_full_128_sub") if eval_renders is None else eval_renders)
     total = sum(v * O.LOSS_WEIGHTS[k] for k, v in loss.items())
     names = list(leaf.keys())
     gs = torch.autograd.grad(total, [leaf[k] for k in names], allow_unused=True)
@@ -228,9 +229,18 @@ def scenario(name, S, B, subdivide, stage, dtype=torch.float32, trans_amp=0.0, a
     print(name, "->", path, {k: float(v) for k, v in loss.items()}, "overflow", im["sil_overflow"])
 
 
+SCENARIOS = {
+    "c1_sil_256_coarse": dict(S=256, B=1, subdivide=False, stage="coarse"),
+    "c2_full_128_sub": dict(S=128, B=2, subdivide=True, stage="both", trans_amp=0.004),
+    "c4_arm_128_sub": dict(S=128, B=2, subdivide=True, stage="both", trans_amp=0.004, arm=True),
+    # BASELINE.json sizes and the reference's default operating point (utils/config_utils.py:7,11: use_arm, 448 x 448)
+    "c2_full_512_sub": dict(S=512, B=2, subdivide=True, stage="both", trans_amp=0.004),
+    "c4_arm_1024_sub": dict(S=1024, B=1, subdivide=True, stage="both", trans_amp=0.004, arm=True),
+    "arm_448_sub": dict(S=448, B=2, subdivide=True, stage="both", trans_amp=0.004, arm=True),
+}
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     os.chdir(REF)
-    scenario("c1_sil_256_coarse", S=256, B=1, subdivide=False, stage="coarse")
-    scenario("c2_full_128_sub", S=128, B=2, subdivide=True, stage="both", trans_amp=0.004)
-    scenario("c4_arm_128_sub", S=128, B=2, subdivide=True, stage="both", trans_amp=0.004, arm=True)
+    for name in (sys.argv[1:] or list(SCENARIOS)):
+        scenario(name, **SCENARIOS[name])

@@ -7,7 +7,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from util import load_golden, rel_l2, frac_within
+from util import load_golden, rel_l2, frac_within, record
 
 _EXTRA = {}
 LOSS_W = {"silhouette": 7.0, "kps_anchor": 10.0, "vert_disp_reg": 2.0, "normal": 0.1, "laplacian": 4.0, "arap": 0.2,
@@ -94,7 +94,8 @@ def _loop_body(g, stage):
     return loss, total, leaf, y_sil_pred, y_pred
 
 
-@pytest.mark.parametrize("name", ["c2_full_128_sub", "c1_sil_256_coarse", "c4_arm_128_sub"])
+@pytest.mark.parametrize("name", ["c2_full_128_sub", "c1_sil_256_coarse", "c4_arm_128_sub", "c2_full_512_sub", "arm_448_sub",
+                                  "c4_arm_1024_sub"])
 def test_dropin_loop_body_matches_reference_golden(name):
     g = load_golden(name)
     loss, total, leaf, sil, rgb = _loop_body(g, str(g["stage"]))
@@ -106,8 +107,8 @@ def test_dropin_loop_body_matches_reference_golden(name):
     d = (rgb.detach().cpu() - torch.tensor(g["img_rgb"])).abs().amax(-1)
     assert float((d <= 1e-4).double().mean()) >= 0.99
     S_, B_ = int(g["S"]), int(g["B"])
-    if float(g["grad_amb_ratio"]) != 0.0:  # cancelling scalar sum: tolerance = 6 residual-sign flips (see test_gpu_kernels.py)
-        assert abs(float(leaf["amb_ratio"].grad) - float(g["grad_amb_ratio"])) <= 6 * 2.0 / (3 * B_ * S_ * S_) / 4
+    if float(g["grad_amb_ratio"]) != 0.0:  # cancelling scalar sum of per-channel sign quanta (see test_gpu_kernels.py)
+        assert abs(float(leaf["amb_ratio"].grad) - float(g["grad_amb_ratio"])) <= 40 * 2.0 / (3 * B_ * S_ * S_) / 4
     for k in ("pose", "rot", "cam", "shape", "verts_disps", "light_positions", "trans", "wrist_pose"):
         if "grad_" + k not in g:
             continue
@@ -116,6 +117,7 @@ def test_dropin_loop_body_matches_reference_golden(name):
             continue
         assert leaf[k].grad is not None, k
         r = rel_l2(leaf[k].grad.cpu().view(gg.shape), gg)
+        record(f"dropin_vs_golden[{name}]", **{"grad_" + k: r})
         assert r < 2e-2, (k, r)
     for k in ("texture", "normal_map"):
         gg = torch.tensor(g["grad_" + k])

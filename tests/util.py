@@ -60,3 +60,25 @@ def rel_l2(a, b):
 def frac_within(a, b, tol):
     a, b = torch.as_tensor(a), torch.as_tensor(b)
     return float(((a - b).abs() <= tol).double().mean())
+
+
+# ------------------------------------------------------------------------------------------------- measured-error log
+# Every GPU parity test records the errors it MEASURED (not only the bound it asserts); tests/conftest.py writes them to
+# $HARP_PARITY_OUT (default gpurun_out/parity.json) at session end, and the round's copy is committed under profiles/.
+PARITY = {}
+
+
+def record(test, **vals):
+    d = PARITY.setdefault(test, {})
+    for k, v in vals.items():
+        d[k] = float(v) if isinstance(v, (int, float)) or (torch.is_tensor(v) and v.numel() == 1) else v
+
+
+def agree_mask(a, b, tol=1e-4):
+    """Pixels on which two renders of the same scene agree (per-pixel max over channels): the complement is the set of
+    *flip* pixels, where a 1-ulp difference upstream changed a discrete decision (nearest face, band membership, rounded
+    shadow tap) — see DESIGN.md section 2."""
+    d = (torch.as_tensor(a).double() - torch.as_tensor(b).double()).abs()
+    if d.dim() == 4:
+        d = d.amax(-1)
+    return d <= tol

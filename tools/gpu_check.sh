@@ -7,7 +7,7 @@ python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/${TAG}_pytest.l
 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 if [ "$2" = "ncu" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on --nvtx --nvtx-include "harp_timed/" \
-    -k regex:"pixel_vis_kernel|shade_deferred_kernel|light_depth_kernel" -c 3 -f -o gpurun_out/${TAG}_pixel \
+    -k regex:"tile_raster_kernel|shade_deferred_kernel|empty_tiles_kernel|raster_setup_kernel" -c 3 -f -o gpurun_out/${TAG}_pixel \
     python bench.py --steps 1 --warmup 3 --eager --no-e2e --no-cpu-baseline > gpurun_out/${TAG}_ncu.log 2>&1
 fi
 tail -3 gpurun_out/${TAG}_pytest.log
