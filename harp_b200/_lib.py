@@ -55,7 +55,8 @@ _lib = None
 # every symbol include/harp_b200.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = ["harp_last_error", "harp_version", "harp_launch_count", "harp_ctx_profile", "harp_ctx_profile_read", "harp_ctx_create", "harp_ctx_create_lbs", "harp_ctx_destroy", "harp_lbs_fwd", "harp_lbs_bwd", "harp_ctx_reserve", "harp_ctx_pin", "harp_ctx_dims",
            "harp_ctx_faces", "harp_ctx_read_counters", "harp_lbs_mano_fwd", "harp_lbs_mano_bwd", "harp_mesh_build_fwd",
-           "harp_mesh_build_bwd", "harp_vertex_normals_fwd", "harp_vertex_normals_bwd", "harp_mesh_losses", "harp_silhouette", "harp_shade", "harp_render_normals", "harp_render_fused", "harp_frame_glue_fwd", "harp_frame_glue_bwd", "harp_texture_reg", "harp_mse", "harp_image_metrics", "harp_ingest_u8", "harp_adam", "harp_adam_dev"]
+           "harp_mesh_build_bwd", "harp_vertex_normals_fwd", "harp_vertex_normals_bwd", "harp_mesh_losses", "harp_silhouette", "harp_shade", "harp_render_normals", "harp_render_fused", "harp_frame_glue_fwd", "harp_frame_glue_bwd", "harp_texture_reg", "harp_mse", "harp_image_metrics", "harp_ingest_u8", "harp_adam", "harp_adam_dev",
+           "harp_peer_create", "harp_peer_connect", "harp_peer_allreduce", "harp_peer_destroy"]
 
 
 def lib():
@@ -102,6 +103,11 @@ def lib():
         L.harp_ingest_u8.argtypes = [i, i, vp, vp, vp, vp, vp, vp]
         L.harp_adam.argtypes = [vp, vp, vp, vp, C.c_int64, f, f, f, f, i, vp]
         L.harp_adam_dev.argtypes = [vp, vp, vp, vp, C.c_int64, f, f, f, f, vp, vp]
+        L.harp_peer_create.argtypes = [C.POINTER(vp), i, i, C.c_size_t, C.POINTER(vp), vp]
+        L.harp_peer_connect.argtypes = [vp, vp]
+        L.harp_peer_allreduce.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, f, vp]
+        L.harp_peer_destroy.argtypes = [vp]
+        L.harp_peer_destroy.restype = None
         _lib = L
     return _lib
 

@@ -28,7 +28,7 @@ namespace {
 constexpr int CHUNK = 32;   // faces staged per bulk-copy round (one lane of warp 0 per face)
 constexpr int NT = HARP_TILE * HARP_TILE;
 constexpr int QCAP = 320;   // band pairs of one tile (all chunks); a tile that needs more goes to the exact per-pixel kernel
-constexpr int TIECAP = 48;  // visibility candidates within 1e-5 of each other (resolved with the exact depth)
+constexpr int TIECAP = 128; // visibility candidates within 1e-5 of each other (resolved with the exact depth)
 
 // ---- Blackwell/Hopper async-copy plumbing: mbarrier + bulk global->shared copies (TMA unit; SASS: UBLKCP / SYNCS) ----------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,7 +90,7 @@ struct __align__(16) BandEntry {
   unsigned char edge;    // queued: chunk-local face index | 0x40 inside | 0x80 exact path; evaluated: 0..2, or 255 = does not pass
 };
 // s_om[slot] = 1 - sigmoid(-sd / sigma) of an evaluated entry, computed with full warps in the drain
-struct TieEntry { int pix, fid; float q; };
+// a visibility near-tie candidate: pixel (6 bits) | face id << 6
 
 // Block-wide sum of two values at once (64-thread CTAs: two warps); results valid in thread 0.
 __device__ __forceinline__ void block_sum2(float& u, float& v, float* red) {
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
   __shared__ unsigned long long s_vis[NT];
   __shared__ BandEntry s_q[SIL ? QCAP : 1];
   __shared__ float s_om[SIL ? QCAP : 1];
-  __shared__ TieEntry s_tie[TIECAP];
+  __shared__ int s_tie[TIECAP];
   __shared__ int s_cnt[NT], s_head[NT];
   __shared__ int s_pre[CHUNK + 1], s_rect[CHUNK];
   __shared__ float s_rw[CHUNK];
@@ -294,8 +294,8 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
               if (fabsf(q - qo) <= 1e-5f * fmaxf(q, qo)) {
                 int slot = atomicAdd(&s_tn, 2);
                 if (slot + 1 < TIECAP) {
-                  s_tie[slot] = TieEntry{pix, f.fid, q};
-                  s_tie[slot + 1] = TieEntry{pix, (int)(0xffffffffu - (unsigned)(old & 0xffffffffu)), qo};
+                  s_tie[slot] = pix | (f.fid << 6);
+                  s_tie[slot + 1] = pix | ((int)(0xffffffffu - (unsigned)(old & 0xffffffffu)) << 6);
                 }
               }
             }
@@ -372,14 +372,15 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
       const int nt = min(s_tn, TIECAP);
       if (s_tn > TIECAP && tid == 0) atomicAdd(c.counters, 1ULL);  // reported by harp_ctx_read_counters (never seen)
       if (nt > 0 && best_fid >= 0) {
-        float best_q = __uint_as_float((unsigned)(key >> 32)), best_pz = 0.f;
+        // a remembered candidate that has since fallen far behind simply loses the exact comparison
+        float best_pz = 0.f;
         bool have_pz = false;
         for (int i = 0; i < nt; ++i) {
-          TieEntry te = s_tie[i];
-          if (te.pix != tid || te.fid == best_fid || te.q < best_q - 2e-5f * best_q) continue;
+          int te = s_tie[i], tf = te >> 6;
+          if ((te & 63) != tid || tf == best_fid) continue;
           if (!have_pz) { best_pz = exact_pz_rec(a.rec + (size_t)b * c.F, best_fid, px, py); have_pz = true; }
-          float pz = exact_pz_rec(a.rec + (size_t)b * c.F, te.fid, px, py);
-          if (pz < best_pz || (pz == best_pz && te.fid < best_fid)) { best_fid = te.fid; best_pz = pz; }
+          float pz = exact_pz_rec(a.rec + (size_t)b * c.F, tf, px, py);
+          if (pz < best_pz || (pz == best_pz && tf < best_fid)) { best_fid = tf; best_pz = pz; }
         }
       }
     }

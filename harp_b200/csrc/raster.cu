@@ -255,14 +255,17 @@ __global__ void __launch_bounds__(32 * TOPK_WARPS) sil_topk_kernel(harp_ctx c, i
       e_keep[w][i] = rank < K ? 1 : 0;
     }
     __syncwarp();
-    float prod = 1.f; int nzero = 0;
+    // product in double: the float result then does not depend on the order of the factors, so this kernel and the tile
+    // kernels (pixel.cu) give the same alpha for the same set of faces
+    double dprod = 1.0; int nzero = 0;
     for (int i = lane; i < ne; i += 32) {
       if (!e_keep[w][i]) continue;
       float om = 1.f - 1.f / (1.f + expf(fdiv(e_sd[w][i], sigma)));
-      if (om == 0.f) ++nzero; else prod *= om;
+      if (om == 0.f) ++nzero; else dprod *= (double)om;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { prod *= __shfl_xor_sync(0xffffffffu, prod, o); nzero += __shfl_xor_sync(0xffffffffu, nzero, o); }
+    for (int o = 16; o > 0; o >>= 1) { dprod *= __shfl_xor_sync(0xffffffffu, dprod, o); nzero += __shfl_xor_sync(0xffffffffu, nzero, o); }
+    float prod = (float)dprod;
     float a = nzero > 0 ? 1.f : 1.f - prod;
     if (MODE != 1 && lane == 0) alpha[pix] = a;
     if (MODE == 0) continue;

@@ -94,6 +94,42 @@ def allreduce_shared_inplace(gbuf, start, stop, loss_slice, world_size, group=No
     gbuf[loss_slice] /= world_size
 
 
+class _RawCudaBuffer:
+    """A device allocation owned by the C library, exposed through __cuda_array_interface__ so torch can alias it."""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class PeerExchange:
+    """The step's ONE collective as a kernel over NVLink peer memory (csrc/peer.cu, harp_peer_*): every rank's gradient buffer is
+    an IPC-shareable allocation mapped by all ranks of the node; `allreduce` is a CUDA-graph-capturable launch on the current
+    stream.  Handles are exchanged once through torch.distributed (any backend)."""
+
+    def __init__(self, n_floats, rank, world_size, device, group=None):
+        import torch.distributed as dist
+        L = _lib.lib()
+        self.h, data = C.c_void_p(), C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            check(L.harp_peer_create(C.byref(self.h), int(world_size), int(rank), int(n_floats) * 4, C.byref(data), handle))
+            gathered = [None] * world_size
+            dist.all_gather_object(gathered, bytes(handle), group=group)
+            blob = (C.c_ubyte * (64 * world_size)).from_buffer_copy(b"".join(gathered))
+            check(L.harp_peer_connect(self.h, blob))
+        self._owner = _RawCudaBuffer(data.value, n_floats)
+        self.buffer = torch.as_tensor(self._owner, device=device)
+        dist.barrier(group=group)  # nobody launches against a peer that has not mapped everyone yet
+
+    def allreduce(self, start, stop, scale_lo, scale_hi, scale):
+        check(_lib.lib().harp_peer_allreduce(self.h, int(start), int(stop), int(scale_lo), int(scale_hi), float(scale), stream()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            _lib.lib().harp_peer_destroy(self.h)
+            self.h = None
+
+
 class HarpFitter:
     """params: dict with the reference's keys (`optimize_sequence.py:181-250`): pose (T,45), rot (T,3), trans (T,3),
     cam (T,3), shape (10,), verts_disps (V,1), texture / normal_map (1,H,W,3), light_positions (T,3), amb_ratio ().
@@ -101,7 +137,9 @@ class HarpFitter:
     ref_verts: (1,V,3) ARAP reference (`optimize_sequence.py:429-435`); uv_mask (H,W)."""
 
     def __init__(self, hc, params, frames, ref_verts, uv_mask, img_size, focal_length, self_shadow=True,
-                 lr_coarse=1e-3, lr_app=1e-2, world_size=1, process_group=None, opt_arm_pose=False):
+                 lr_coarse=1e-3, lr_app=1e-2, world_size=1, process_group=None, opt_arm_pose=False, exchange="nccl", rank=None):
+        """exchange (world_size > 1): 'nccl' = one in-place NCCL allreduce launched after the step (outside a captured graph);
+        'peer' = the device-side exchange over NVLink peer memory (PeerExchange), part of the captured graph together with Adam."""
         dev = hc.device
         self.hc, self.S, self.focal, self.self_shadow = hc, int(img_size), float(focal_length), bool(self_shadow)
         self._lr = {"coarse": float(lr_coarse), "app": float(lr_app)}
@@ -124,7 +162,15 @@ class HarpFitter:
                       ("normal_map", f32(params["normal_map"])), ("light_positions", f32(params["light_positions"]))]
         # all gradients and the loss vector live in one buffer: one fill per step, one in-place allreduce of its shared span
         nc, na, nl = sum(t.numel() for _, t in groups), sum(t.numel() for _, t in app_groups), len(LOSS_NAMES)
-        self._gbuf = torch.zeros(nc + nl + na, device=dev)
+        self.exchange_mode, self.peer = (exchange if int(world_size) > 1 else "none"), None
+        if self.exchange_mode == "peer":
+            import torch.distributed as dist
+            self.peer = PeerExchange(nc + nl + na, dist.get_rank(process_group) if rank is None else rank, int(world_size), dev,
+                                     group=process_group)
+            self._gbuf = self.peer.buffer
+            self._gbuf.zero_()
+        else:
+            self._gbuf = torch.zeros(nc + nl + na, device=dev)
         self.coarse = _Flat(groups, dev, grad_storage=self._gbuf[:nc])
         self.app = _Flat(app_groups, dev, grad_storage=self._gbuf[nc + nl:])
         self.losses = self._gbuf[nc:nc + nl]
@@ -328,7 +374,8 @@ class HarpFitter:
         """Record one optimiser step (all C-ABI launches + the small torch glue) into a CUDA graph.  The ~120 launches of
         a step then replay back to back; inputs are read from the same device buffers every replay (fid, offsets, the
         resident frames or the staging `batch`).  Returns a callable; each call runs one step (update=True)."""
-        multi = self.world_size > 1  # the NCCL allreduce and the two Adam launches stay outside the graph
+        multi = self.world_size > 1 and self.exchange_mode != "peer"  # NCCL: the allreduce and the two Adam launches stay
+        # outside the graph; the peer-memory exchange is a kernel node like any other
         kw = dict(stage=stage, frame_range=frame_range, batch=batch, batch_u8=batch_u8)
         if not keep_profile:
             self.hc.profile(False)
@@ -347,7 +394,7 @@ class HarpFitter:
         if getattr(self, "_capture_stream", None) is None:
             self._capture_stream = torch.cuda.Stream(device=self.hc.device, priority=-1)
         with torch.cuda.graph(graph, stream=self._capture_stream):
-            self.step(fid, off_albedo, off_normal, update=not multi, exchange=False, **kw)
+            self.step(fid, off_albedo, off_normal, update=not multi, exchange=not multi, **kw)
         self._set_graph(graph)
         if not multi:
             return graph.replay
@@ -455,8 +502,19 @@ class HarpFitter:
         except Exception:
             pass
 
+    def close(self):
+        """Release captured graphs and the peer-memory exchange (all ranks together: peers unmap each other's buffers)."""
+        self.release_graph()
+        if self.peer is not None:
+            torch.cuda.synchronize()
+            self.peer.close()
+            self.peer = None
+
     def _allreduce_shared(self):
-        allreduce_shared_inplace(self._gbuf, self._shared_start, self._shared_stop, self._loss_slice, self.world_size, self.pg)
+        if self.peer is not None:
+            self.peer.allreduce(self._shared_start, self._shared_stop, self._loss_slice.start, self._loss_slice.stop, 1.0 / self.world_size)
+        else:
+            allreduce_shared_inplace(self._gbuf, self._shared_start, self._shared_stop, self._loss_slice, self.world_size, self.pg)
 
     def loss_dict(self):
         """One device->host read of the loss vector (the reference does >= 10 `.cpu()` syncs per iteration, 556-561)."""

@@ -23,6 +23,7 @@
 #define HARP_API
 #endif
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -288,6 +289,22 @@ HARP_API int harp_adam(float* param, const float* grad, float* exp_avg, float* e
  * scheduler (ReduceLROnPlateau, optimize_sequence.py:312-321) can change it without re-capturing the graph. */
 HARP_API int harp_adam_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                            float beta2, float eps, void* state, void* stream);
+
+/* ---- data-parallel exchange over NVLink peer memory (the reference is single-process) -------------------
+ * One process per GPU of ONE node.  Every rank's gradient buffer lives in an IPC-shareable allocation that all ranks map; the
+ * sum of the shared-parameter gradients is a reduce-scatter + all-gather kernel written against the peers' buffers and
+ * synchronised by epoch flags in the same allocations: an ordinary, CUDA-graph-capturable kernel on the caller's stream.
+ *   harp_peer_create   allocates `data_bytes` (+ flags) on the current device; returns the device pointer of the data region
+ *                      (the caller builds its gradient tensors on it) and this rank's 64-byte IPC handle [host]
+ *   harp_peer_connect  `handles`: world x 64 bytes [host], rank-major, gathered by the host layer (torch.distributed)
+ *   harp_peer_allreduce  data[start:stop) (float elements) <- sum over ranks, in place on every rank; elements of
+ *                      [scale_lo, scale_hi) are then multiplied by `scale`.  Every rank launches it once per step. */
+typedef struct harp_peer harp_peer;
+HARP_API int harp_peer_create(harp_peer** out, int world, int rank, size_t data_bytes, void** data_ptr, void* ipc_handle_out);
+HARP_API int harp_peer_connect(harp_peer* peer, const void* handles);
+HARP_API int harp_peer_allreduce(harp_peer* peer, int64_t start, int64_t stop, int64_t scale_lo, int64_t scale_hi, float scale,
+                                 void* stream);
+HARP_API void harp_peer_destroy(harp_peer* peer);
 
 #ifdef __cplusplus
 }

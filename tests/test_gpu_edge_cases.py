@@ -14,9 +14,9 @@ from util import load_golden, golden_case, rel_l2, record
 from test_gpu_kernels import _fitter_from_case
 
 
-def _variant(kind):
+def _variant(kind, dtype=torch.float32):
     g = load_golden("c2_full_128_sub")
-    model, topo, params, batch, cfg = golden_case(g)
+    model, topo, params, batch, cfg = golden_case(g, dtype=dtype)
     params = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in params.items()}
     batch = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
     cam = params["cam"]
@@ -65,16 +65,24 @@ def test_fused_step_edge_framing(kind):
         assert math.isclose(ld[k], float(ref_losses[k]), rel_tol=3e-3, abs_tol=1e-7), (k, ld[k], float(ref_losses[k]))
     assert math.isclose(ld["total"], float(ref_losses["total"]), rel_tol=2e-3)
     grads = dict(ft.coarse.g)
-    tol = dict(pose=2e-2, cam=2e-2, shape=2e-2, verts_disps=3e-2)
-    if kind == "tiny_hand":
-        # a handful of sub-pixel faces per pixel: every gradient is a sum over a few hundred band pixels, each of which a
-        # 1-ulp coordinate difference can switch on or off
-        tol = dict(pose=8e-2, cam=8e-2, shape=8e-2, verts_disps=1.5e-1)
-    errs = {k: rel_l2(grads[k].cpu().view(ref_grads[k].shape), ref_grads[k]) for k in tol}
-    record(f"edge_framing[{kind}]", alpha_frac_1e4=float((da <= 1e-4).double().mean()), rgb_frac_1e4=float((drgb <= 1e-4).double().mean()),
-           grads=errs)
-    for k, t in tol.items():
-        assert errs[k] < t, (k, errs[k])
+    errs = {k: rel_l2(grads[k].cpu().view(ref_grads[k].shape), ref_grads[k]) for k in ("pose", "cam", "shape", "verts_disps")}
+    rec = dict(alpha_frac_1e4=float((da <= 1e-4).double().mean()), rgb_frac_1e4=float((drgb <= 1e-4).double().mean()), grads=errs)
+    if kind == "crosses_camera_plane":
+        # vertices with z ~ 0 project to coordinates of order 1/z: the float32 evaluation of THIS problem is itself only
+        # ~4e-2 accurate (the float32 oracle against the float64 oracle, measured below), so the statement is: the CUDA path
+        # is as close to the float64 value as the reference's float32 arithmetic is
+        _, _, g64 = O.step(*_variant(kind, torch.float64))
+        e_o32 = {k: rel_l2(ref_grads[k], g64[k]) for k in errs}
+        e_cu = {k: rel_l2(grads[k].cpu().view(g64[k].shape), g64[k]) for k in errs}
+        rec.update(o32_vs_o64=e_o32, cuda_vs_o64=e_cu)
+        record(f"edge_framing[{kind}]", **rec)
+        for k in errs:
+            assert e_cu[k] <= 1.5 * e_o32[k] + 1e-3, (k, e_cu[k], e_o32[k])
+        return
+    record(f"edge_framing[{kind}]", **rec)
+    # every framing meets north_star's rtol 1e-3 against the float32 oracle on identical inputs
+    for k, e in errs.items():
+        assert e < 1e-3, (k, e)
 
 
 @pytest.mark.parametrize("K", [3, 8])
