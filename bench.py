@@ -31,20 +31,25 @@ def config(n_gpus, frames, size, model="hand"):
                         "shadowed PBR render + photometric + kps + Laplacian + normal-consistency + ARAP + texture regs, "
                         "fwd+bwd+Adam (VGG term excluded)",
             "frames_per_gpu": frames, "img_size": size, "global_frames": frames * n_gpus,
-            "parallelism": f"dp{n_gpus} (static frame sharding, one allreduce of shared-parameter grads per step)",
+            "parallelism": f"dp{n_gpus} (static round-robin frame sharding, one exchange of shared-parameter grads per step)",
             "l2_policy": f"per-step image inputs ({20 * size * size * frames / 1e6:.0f} MB/GPU) exceed the 126 MB L2; no explicit flush"}
 
 
 # ---------------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference(steps, warmup, frames, size):
+def cpu_reference(steps, warmup, frames, size, device="cpu"):
     """The reference's CPU implementation of the path = the oracle (reference Python on the restated PyTorch3D shim is
-    pinned to it bit-for-bit, tests/test_oracle_golden.py).  Each step is a bounded sample: `frames` frames."""
+    pinned to it bit-for-bit, tests/test_oracle_golden.py).  Each step is a bounded sample: `frames` frames.
+    device='cuda': the same eager PyTorch program with every tensor on the GPU — the stand-in for "the reference's 1-GPU
+    PyTorch3D path" (PyTorch3D's own CUDA rasteriser cannot be installed here), reported as
+    `gpu_eager_standin`, never as the product."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import harp_oracle as O
     from harp_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    dev = torch.device(device)
+    mv = lambda d: {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in d.items()}
     tmpl = synth.load_template("hand")
     pack = synth.make_mano_pack(seed=0, template=tmpl)
     model = {k: torch.tensor(v) for k, v in pack.items()}
@@ -68,15 +73,97 @@ def cpu_reference(steps, warmup, frames, size):
     batch = dict(y_true=y_true, y_sil=y_sil, y_sil_eroded=synth.erode_mask(y_sil), init_joints=joints_mm.detach(),
                  ref_verts=verts[:1].detach(), uv_mask=torch.tensor(tmpl["uv_mask"]),
                  off_albedo=synth.make_reg_offsets(3, 1.0), off_normal=synth.make_reg_offsets(4, 2.0))
+    if dev.type == "cuda":
+        model, params, batch = mv(model), mv(params), mv(batch)
+        for k in ("faces", "faces0", "edges0", "faces_uvs", "verts_uvs"):
+            if torch.is_tensor(getattr(topo, k, None)):
+                setattr(topo, k, getattr(topo, k).to(dev))
+    import contextlib
     times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        O.step(model, topo, params, batch, cfg)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
+    # on the GPU the oracle's own factory calls (torch.zeros / eye / tensor ...) must default to the device too
+    with (torch.device(dev) if dev.type == "cuda" else contextlib.nullcontext()):
+        for i in range(warmup + steps):
+            if dev.type == "cuda":
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            O.step(model, topo, params, batch, cfg)
+            if dev.type == "cuda":
+                torch.cuda.synchronize()
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
     return dict(value=B / sec, ms_per_step=sec * 1e3, cores=cores,
                 sample=f"{B} frame(s) @{S}x{S} per step, full loss set, fwd+bwd via autograd, {steps} steps after {warmup} warm-up")
+
+
+def dropin_leg(sc, hc_model, B, S, steps, warmup):
+    """The reference's loop body (optimize_sequence.py:446-579) written against the Level-1 drop-in modules:
+    prepare_mesh -> silhouette renderer -> shadow renderer -> losses -> autograd backward -> two torch.optim.Adam steps.
+    This is what a HARP maintainer gets by swapping imports; HarpFitter.step is the fused Level-3 path."""
+    from harp_b200 import renderer_helper, synth
+    from harp_b200.manolayer import ManoLayer
+    from harp_b200.structures import Meshes
+    from harp_b200.visualize import prepare_mesh, prepare_materials, render_image, render_image_with_RT
+    from harp_b200.loss import arap_loss, kps_loss, albedo_reg, normal_reg, mesh_laplacian_smoothing, mesh_normal_consistency
+    from harp_b200.step import LOSS_WEIGHTS as W
+    dev = "cuda"
+    tmpl = synth.load_template("hand")
+    layer = ManoLayer(synth.make_mano_pack(seed=0, template=tmpl), faces_uvs=tmpl["faces_uvs"], verts_uvs=tmpl["verts_uvs"], device=dev)
+    P = {k: torch.nn.Parameter(v.clone().to(dev)) for k, v in sc["params"].items()}
+    params = dict(P)
+    params["mesh_faces"] = layer.th_faces
+    params["verts_uvs"] = torch.tensor(tmpl["verts_uvs"])[None]
+    params["faces_uvs"] = torch.tensor(tmpl["faces_uvs"]).long()[None]
+    fr = sc["frames"]
+    focal = sc["focal"]
+    coarse = torch.optim.Adam([P[k] for k in ("pose", "cam", "verts_disps", "shape")], lr=1e-3)
+    app = torch.optim.Adam([P[k] for k in ("amb_ratio", "texture", "normal_map", "light_positions")], lr=1e-2)
+    fid = torch.arange(B)
+    configs = {"model_type": "harp", "img_size": S, "focal_length": focal, "use_arm": False}
+    l1 = torch.nn.L1Loss()
+    ref_mesh = None
+
+    def body():
+        nonlocal ref_mesh
+        light_positions = params["light_positions"][0].repeat(B, 1)
+        _, sil_r, _ = renderer_helper.get_renderers(image_size=S, light_posi=light_positions, silh_sigma=1e-7, silh_gamma=1e-1,
+                                                    silh_faces_per_pixel=50, device=dev)
+        joints, verts, faces, textures = prepare_mesh(params, fid, layer, False, object(), global_pose=False, configs=configs,
+                                                      shared_texture=True, device=dev, use_arm=False)
+        meshes = Meshes(verts, faces, textures)
+        cam = params["cam"][fid]
+        mats = prepare_materials(params, B, device=dev)
+        y_sil_pred = render_image(meshes, cam, B, sil_r, S, focal, silhouette=True, device=dev)
+        lR, lT, cR, cT = renderer_helper.process_info_for_shadow(cam, light_positions, verts.mean(1), image_size=S, focal_length=focal, device=dev)
+        sh_r = renderer_helper.get_shadow_renderers(image_size=S, light_posi=light_positions, amb_ratio=torch.sigmoid(params["amb_ratio"]), device=dev)
+        y_pred = render_image_with_RT(meshes, lT, lR, cT, cR, B, sh_r, S, focal, silhouette=False, materials_properties=mats, device=dev)
+        if ref_mesh is None:
+            ref_mesh = Meshes(sc["ref_verts"].to(dev), faces[:1])
+        me = fr["y_sil_eroded"].unsqueeze(-1)
+        loss = (W["silhouette"] * l1(fr["y_sil"], y_sil_pred) + W["kps_anchor"] * kps_loss(fr["init_joints"], joints, device=dev) +
+                W["vert_disp_reg"] * torch.sum(params["verts_disps"] ** 2.0) + W["laplacian"] * mesh_laplacian_smoothing(meshes) +
+                W["normal"] * mesh_normal_consistency(meshes) + W["arap"] * arap_loss(meshes, ref_mesh) +
+                W["photo"] * l1(fr["y_true"] * me, y_pred * me) +
+                W["albedo"] * albedo_reg(params["texture"], uv_mask=sc["uv_mask"].to(dev), std=1.0) +
+                W["normal_reg"] * normal_reg(params["normal_map"], uv_mask=sc["uv_mask"].to(dev)))
+        coarse.zero_grad(); app.zero_grad()
+        loss.backward()
+        coarse.step(); app.step()
+        return loss
+
+    for _ in range(warmup):
+        body()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = body()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "what": "optimize_sequence.py:446-579 on the Level-1 drop-in modules (separate silhouette / shadow renderer calls, "
+                    "torch.autograd, torch.optim.Adam, eager launches)", "loss": float(loss)}
 
 
 # ---------------------------------------------------------------------------------------------------- clocks
@@ -126,7 +213,7 @@ class ClockSampler:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="harp", choices=["harp", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES)
@@ -135,6 +222,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--exchange", default=os.environ.get("HARP_EXCHANGE", "peer"), choices=["peer", "nccl", "overlap"],
+                    help="N > 1: peer = exchange kernel over NVLink peer memory inside the step graph (default); nccl = one NCCL "
+                         "allreduce after the graph; overlap = NCCL allreduce of the texture gradients under the geometry backward")
+    ap.add_argument("--no-standin", action="store_true", help="skip the GPU-eager stand-in and drop-in legs (N = 1 only)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -149,7 +240,9 @@ def main():
         r = cpu_reference(k, w, frames=4, size=args.size)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": k,
                 "warmup": w, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": config(args.gpus, args.frames, args.size),
+                "dtype": "f32", "data": "synthetic",
+                "config": dict(config(args.gpus, args.frames, args.size), reference_sample_frames_per_step=4,
+                               note="the CPU arm steps a bounded 4-frame sample of the 64-frame workload; value is frames/s"),
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line), flush=True)
@@ -171,8 +264,22 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B, S = args.frames, args.size
     hc, _, _ = scene.make_context(device=dev, model=args.model)
-    sc = scene.make_scene(hc, B, S, seed=1, frame_offset=rank * B, total_frames=world * B)
-    ft = HarpFitter(hc, sc["params"], sc["frames"], sc["ref_verts"], sc["uv_mask"], S, sc["focal"], world_size=world)
+    # static round-robin sharding of the world*B-frame sequence: rank r owns frames r, r + R, ... (every rank sees the whole
+    # motion cycle, so the content-dependent raster work is balanced across ranks)
+    sc = scene.make_scene(hc, B, S, seed=1, frame_offset=rank, total_frames=world * B, frame_stride=world)
+    exchange = args.exchange if world > 1 else "none"
+    if exchange == "peer":  # all ranks must agree: fall back to NCCL together if the IPC mapping fails anywhere
+        ok = torch.ones(1, device=dev)
+        try:
+            ft = HarpFitter(hc, sc["params"], sc["frames"], sc["ref_verts"], sc["uv_mask"], S, sc["focal"], world_size=world, exchange="peer")
+        except Exception as e:  # pragma: no cover
+            print(f"[bench] peer-memory exchange unavailable on rank {rank}: {e}", file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) == 0.0:
+            exchange = "nccl"
+    if exchange != "peer":
+        ft = HarpFitter(hc, sc["params"], sc["frames"], sc["ref_verts"], sc["uv_mask"], S, sc["focal"], world_size=world)
     fid = torch.arange(B, device=dev)
     oa, on = sc["offsets"]["albedo"], sc["offsets"]["normal"]
 
@@ -188,7 +295,7 @@ def main():
         # replay re-records them and the kernel durations are read from the timed region itself
         hc.profile(True)
         try:
-            overlapped = world > 1 and os.environ.get("HARP_EXCHANGE", "serial") == "overlap"
+            overlapped = world > 1 and exchange == "overlap"
             cap = ft.capture_overlapped if overlapped else ft.capture
             replay = cap(fid, oa, on, stage="both", frame_range=(0, B), keep_profile=True)
             run_step = replay
@@ -223,7 +330,11 @@ def main():
     sync()
     launches = launches_per_step * args.steps if use_graph else _lib.lib().harp_launch_count() - n0
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    per_rank_ms = [float(ms) / args.steps]
     if world > 1:
+        allms = [torch.zeros_like(ms) for _ in range(world)]
+        dist.all_gather(allms, ms)
+        per_rank_ms = [float(x) / args.steps for x in allms]
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms)
     clk = clocks.stop() if rank == 0 else None
@@ -298,7 +409,7 @@ def main():
 
         def run_f32(s):
             if use_graph:
-                return (ft.capture_overlapped if world > 1 and os.environ.get("HARP_EXCHANGE", "serial") == "overlap" else ft.capture)(
+                return (ft.capture_overlapped if world > 1 and exchange == "overlap" else ft.capture)(
                     fid, oa, on, stage="both", batch=s, warmup=1)
             return lambda: ft.step(fid, oa, on, stage="both", update=True, batch=s)
 
@@ -312,7 +423,7 @@ def main():
 
         def run_u8(s):
             if use_graph:
-                return (ft.capture_overlapped if world > 1 and os.environ.get("HARP_EXCHANGE", "serial") == "overlap" else ft.capture)(
+                return (ft.capture_overlapped if world > 1 and exchange == "overlap" else ft.capture)(
                     fid, oa, on, stage="both", batch_u8=s, warmup=1)
             return lambda: ft.step(fid, oa, on, stage="both", update=True, batch_u8=s)
 
@@ -353,6 +464,10 @@ def main():
                 "e2e_uint8": {"value": world * B * k_e2e / e2e_u8_s, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
                               "steps": k_e2e, "host_dtype": "uint8 frames + masks, /255 and 3x3x2 erosion on the device"},
                 "gpu_launches": int(launches), "launch_mode": "cuda_graph_replay" if use_graph else "eager",
+                "exchange": {"none": "single GPU", "peer": "reduce-scatter + all-gather kernel over NVLink peer memory inside the step graph",
+                             "nccl": "one in-place NCCL allreduce after the step graph",
+                             "overlap": "NCCL allreduce of texture grads under the geometry backward"}[exchange],
+                "per_rank_ms_per_step": [round(x, 4) for x in per_rank_ms],
                 "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "kernel_ms": dms, "kernel_share_of_step": dms / (ms_total / args.steps),
@@ -365,6 +480,23 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference(4, 1, frames=4, size=S)  # a bounded sample: 5 x 4 frames, about 10 s of host time
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        if world == 1 and not args.no_standin and args.model == "hand":
+            try:  # the same eager PyTorch program on the GPU: stand-in for the reference's 1-GPU PyTorch3D path
+                r = cpu_reference(5, 2, frames=4, size=S, device=f"cuda:{local}")
+                line["gpu_eager_standin"] = {"value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "sample": r["sample"],
+                                             "what": "oracle (reference loop body on the restated PyTorch3D ops) in eager PyTorch on this "
+                                                     "GPU; NOT PyTorch3D's CUDA rasteriser, which cannot be installed offline",
+                                             "ratio_value_over_standin": value / r["value"]}
+            except Exception as e:  # pragma: no cover
+                import traceback
+                traceback.print_exc()
+                line["gpu_eager_standin"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+            try:
+                torch.cuda.empty_cache()
+                line["dropin_level1"] = dropin_leg(sc, hc, B, S, steps=5, warmup=2)
+                line["dropin_level1"]["fused_over_dropin"] = value / line["dropin_level1"]["value"]
+            except Exception as e:  # pragma: no cover
+                line["dropin_level1"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
         print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()

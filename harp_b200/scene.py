@@ -54,13 +54,14 @@ def render_frames(hc, p, S, focal, chunk=16, self_shadow=True):
     return torch.cat(sil), torch.cat(rgb), torch.cat(vs), torch.cat(js)
 
 
-def make_scene(hc, T, S, seed=1, frame_offset=0, total_frames=None):
-    """frame_offset / total_frames: this rank's contiguous shard of a longer sequence (static frame sharding)."""
+def make_scene(hc, T, S, seed=1, frame_offset=0, total_frames=None, frame_stride=1):
+    """frame_offset / total_frames / frame_stride: this rank's shard of a longer sequence under static frame sharding —
+    contiguous (stride 1: frames offset .. offset+T-1) or round-robin (stride R: frames offset, offset+R, ...)."""
     dev = hc.device
     focal = 1000.0 * S / 224.0  # utils/config_utils.py:11-12
     total = total_frames or T
     seq = synth.make_sequence(total, seed=seed, img_size=S)
-    sl = slice(frame_offset, frame_offset + T)
+    sl = slice(frame_offset, frame_offset + T * frame_stride, frame_stride)
     app = synth.make_appearance(seed=2)
     params = dict(pose=seq["pose"][sl], rot=seq["rot"][sl], trans=seq["trans"][sl], cam=seq["cam"][sl], shape=seq["shape"],
                   verts_disps=torch.zeros(hc.V, 1), texture=app["texture"], normal_map=app["normal_map"],
