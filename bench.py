@@ -222,9 +222,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
-    ap.add_argument("--exchange", default=os.environ.get("HARP_EXCHANGE", "peer"), choices=["peer", "nccl", "overlap"],
+    ap.add_argument("--exchange", default=os.environ.get("HARP_EXCHANGE", "peer"), choices=["peer", "nccl"],
                     help="N > 1: peer = exchange kernel over NVLink peer memory inside the step graph (default); nccl = one NCCL "
-                         "allreduce after the graph; overlap = NCCL allreduce of the texture gradients under the geometry backward")
+                         "allreduce after the graph")
     ap.add_argument("--no-standin", action="store_true", help="skip the GPU-eager stand-in and drop-in legs (N = 1 only)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -295,9 +295,7 @@ def main():
         # replay re-records them and the kernel durations are read from the timed region itself
         hc.profile(True)
         try:
-            overlapped = world > 1 and exchange == "overlap"
-            cap = ft.capture_overlapped if overlapped else ft.capture
-            replay = cap(fid, oa, on, stage="both", frame_range=(0, B), keep_profile=True)
+            replay = ft.capture(fid, oa, on, stage="both", frame_range=(0, B), keep_profile=True)
             run_step = replay
         except Exception as e:  # pragma: no cover - falls back to eager launches
             print(f"[bench] CUDA graph capture failed ({e}); timing eager launches", file=sys.stderr)
@@ -409,8 +407,7 @@ def main():
 
         def run_f32(s):
             if use_graph:
-                return (ft.capture_overlapped if world > 1 and exchange == "overlap" else ft.capture)(
-                    fid, oa, on, stage="both", batch=s, warmup=1)
+                return ft.capture(fid, oa, on, stage="both", batch=s, warmup=1)
             return lambda: ft.step(fid, oa, on, stage="both", update=True, batch=s)
 
         e2e_s = e2e_leg(host, stage_f32, run_f32, k_e2e)
@@ -423,8 +420,7 @@ def main():
 
         def run_u8(s):
             if use_graph:
-                return (ft.capture_overlapped if world > 1 and exchange == "overlap" else ft.capture)(
-                    fid, oa, on, stage="both", batch_u8=s, warmup=1)
+                return ft.capture(fid, oa, on, stage="both", batch_u8=s, warmup=1)
             return lambda: ft.step(fid, oa, on, stage="both", update=True, batch_u8=s)
 
         e2e_u8_s = e2e_leg(host_u8, stage_u8, run_u8, k_e2e)
@@ -465,8 +461,7 @@ def main():
                               "steps": k_e2e, "host_dtype": "uint8 frames + masks, /255 and 3x3x2 erosion on the device"},
                 "gpu_launches": int(launches), "launch_mode": "cuda_graph_replay" if use_graph else "eager",
                 "exchange": {"none": "single GPU", "peer": "reduce-scatter + all-gather kernel over NVLink peer memory inside the step graph",
-                             "nccl": "one in-place NCCL allreduce after the step graph",
-                             "overlap": "NCCL allreduce of texture grads under the geometry backward"}[exchange],
+                             "nccl": "one in-place NCCL allreduce after the step graph"}[exchange],
                 "per_rank_ms_per_step": [round(x, 4) for x in per_rank_ms],
                 "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -46,6 +46,17 @@ class HarpRenderArgs(C.Structure):
                 [(n, C.c_void_p) for n in ("alpha", "rgb", "loss_sil", "loss_photo")] + [("grads", HarpShadeGrads)])
 
 
+class HarpStepArgs(C.Structure):
+    """harp_step_args of include/harp_b200.h (field order matters)."""
+    _fields_ = ([(n, C.c_int32) for n in ("B", "S", "stage", "self_shadow", "faces_per_pixel", "texH", "texW")] +
+                [(n, C.c_float) for n in ("focal", "sigma", "frame_scale")] + [("weights", C.c_float * 9)] +
+                [(n, C.c_void_p) for n in ("fid", "pose", "rot", "trans", "cam", "wrist_pose", "shape", "verts_disps", "texture", "normal_map",
+                                           "light_position", "amb_ratio", "y_true", "y_sil", "y_sil_eroded", "init_joints", "ref_verts",
+                                           "uv_mask", "off_albedo", "off_normal", "losses", "alpha", "rgb", "g_pose", "g_cam", "g_rot",
+                                           "g_wrist_pose", "g_shape", "g_verts_disps", "g_texture", "g_normal_map", "g_light_position",
+                                           "g_amb_ratio", "d_rot", "d_trans", "d_wrist", "workspace")])
+
+
 class HarpError(RuntimeError):
     pass
 
@@ -55,7 +66,7 @@ _lib = None
 # every symbol include/harp_b200.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = ["harp_last_error", "harp_version", "harp_launch_count", "harp_ctx_profile", "harp_ctx_profile_read", "harp_ctx_create", "harp_ctx_create_lbs", "harp_ctx_destroy", "harp_lbs_fwd", "harp_lbs_bwd", "harp_ctx_reserve", "harp_ctx_pin", "harp_ctx_dims",
            "harp_ctx_faces", "harp_ctx_read_counters", "harp_lbs_mano_fwd", "harp_lbs_mano_bwd", "harp_mesh_build_fwd",
-           "harp_mesh_build_bwd", "harp_vertex_normals_fwd", "harp_vertex_normals_bwd", "harp_mesh_losses", "harp_silhouette", "harp_shade", "harp_render_normals", "harp_render_fused", "harp_frame_glue_fwd", "harp_frame_glue_bwd", "harp_texture_reg", "harp_mse", "harp_image_metrics", "harp_ingest_u8", "harp_adam", "harp_adam_dev",
+           "harp_mesh_build_bwd", "harp_vertex_normals_fwd", "harp_vertex_normals_bwd", "harp_mesh_losses", "harp_silhouette", "harp_shade", "harp_render_normals", "harp_render_fused", "harp_step_fused", "harp_step_workspace_floats", "harp_step_workspace_views", "harp_frame_glue_fwd", "harp_frame_glue_bwd", "harp_texture_reg", "harp_mse", "harp_image_metrics", "harp_ingest_u8", "harp_adam", "harp_adam_dev",
            "harp_peer_create", "harp_peer_connect", "harp_peer_allreduce", "harp_peer_destroy"]
 
 
@@ -95,6 +106,10 @@ def lib():
                                  C.POINTER(HarpShadeGrads), vp]
         L.harp_render_normals.argtypes = [vp, i, i, f, i, vp, vp, vp, vp, vp, i, i, vp, vp]
         L.harp_render_fused.argtypes = [vp, i, i, f, C.POINTER(HarpRenderArgs), vp]
+        L.harp_step_fused.argtypes = [vp, C.POINTER(HarpStepArgs), vp]
+        L.harp_step_workspace_floats.argtypes = [vp, i]
+        L.harp_step_workspace_floats.restype = C.c_size_t
+        L.harp_step_workspace_views.argtypes = [vp, i, vp] + [C.POINTER(vp)] * 4
         L.harp_frame_glue_fwd.argtypes = [vp, i, i, f] + [vp] * 12
         L.harp_frame_glue_bwd.argtypes = [vp, i, i, f] + [vp] * 15
         L.harp_texture_reg.argtypes = [vp, i, vp, i, i, vp, vp, f, vp, vp, vp]

@@ -55,6 +55,8 @@ struct harp_ctx {
   int32_t* v0e_idx = nullptr;
   int32_t* vf_off = nullptr;     // (V+1) vertex -> incident (face*4 + corner) CSR
   int32_t* vf_idx = nullptr;
+  uint32_t* vf_ring = nullptr;   // per incidence (same order as vf_idx): next | prev << 16, the face's other two vertices in
+                                 // cyclic order after this one, so the corner's cross product is (next - self) x (prev - self)
   int32_t* vn_off = nullptr;     // (V+1) vertex -> neighbour vertex CSR (final mesh edges)
   int32_t* vn_idx = nullptr;
   int32_t* edges = nullptr;      // (E,2) final edges, PyTorch3D edges_packed order
@@ -106,6 +108,8 @@ struct harp_ctx {
   // host-side handles for the fused render's light branch (forked from / joined to the caller's stream; capturable)
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_bins = nullptr;
+  cudaStream_t reg_stream = nullptr;       // harp_step_fused's regulariser branch
+  cudaEvent_t ev_reg_fork = nullptr, ev_reg_join = nullptr;
 };
 
 // ---------------------------------------------------------------------------------------------- small vector math

@@ -179,6 +179,15 @@ extern "C" int harp_ctx_create_lbs(harp_ctx** out, const harp_topology* topo, co
   UP(edges, e.edges);
   UP(nc_pairs, pairs);
   csr_from_lists(vf, off, idx);  UP(vf_off, off);  UP(vf_idx, idx);
+  {
+    HARP_REQUIRE(c->V < 65536, HARP_ERR_INVALID, "harp_ctx_create: meshes up to 65535 vertices");
+    std::vector<uint32_t> ring(idx.size());
+    for (size_t i = 0; i < idx.size(); ++i) {
+      int f = idx[i] >> 2, k = idx[i] & 3;
+      ring[i] = (uint32_t)faces[3 * f + (k + 1) % 3] | ((uint32_t)faces[3 * f + (k + 2) % 3] << 16);
+    }
+    UP(vf_ring, ring);
+  }
   csr_from_lists(vn, off, idx);  UP(vn_off, off);  UP(vn_idx, idx);
   csr_from_lists(v0e, off, idx); UP(v0e_off, off); UP(v0e_idx, idx);
   if (topo->faces_uvs && topo->verts_uvs && topo->Vt > 0) {
@@ -253,13 +262,16 @@ extern "C" void harp_ctx_destroy(harp_ctx* c) {
   if (!c) return;
   free_scratch(c);
   void* ptrs[] = {c->faces, c->edges0, c->v0e_off, c->v0e_idx, c->vf_off, c->vf_idx, c->vn_off, c->vn_idx, c->edges,
-                  c->nc_pairs, c->face_uvs, c->shapedirs, c->posedirs, c->v_template, c->weights,
+                  c->nc_pairs, c->face_uvs, c->vf_ring, c->shapedirs, c->posedirs, c->v_template, c->weights,
                   c->J_template, c->J_shapedirs, c->tips, c->counters, c->d_tex4, c->tex4, c->weightsT, c->pose_mean, c->parents,
                   c->joint_out_src};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->ev_bins) cudaEventDestroy(c->ev_bins);
+  if (c->ev_reg_fork) cudaEventDestroy(c->ev_reg_fork);
+  if (c->ev_reg_join) cudaEventDestroy(c->ev_reg_join);
+  if (c->reg_stream) cudaStreamDestroy(c->reg_stream);
   if (c->side_stream) cudaStreamDestroy(c->side_stream);
   if (c->prof) {
     for (auto& v : c->prof->ev) for (cudaEvent_t e : v) cudaEventDestroy(e);

@@ -1,0 +1,267 @@
+// The per-frame geometry of the optimiser step as TWO kernels (one CTA per frame, the frame's vertices in shared memory):
+//
+//   geo_fwd   gather the frame's rows of the parameter tables -> LBS -> SubdivideMeshes + displacement along vertex normals
+//             -> vertex normals -> centroid, weak-perspective camera, look-at light camera, sigmoid(amb)
+//   geo_bwd   backward of all of the above, down to atomics on the parameter-table gradients
+//
+// Replaces, per minibatch (optimize_sequence.py:446-579): prepare_mesh (utils/visualize.py:16-88: ManoLayer / SMPLXARM forward,
+// SubdivideMeshes, verts_normals, displacement), the camera of render_image (visualize.py:266-270), process_info_for_shadow
+// (renderer_helper.py:454-468), sigmoid(amb_ratio) and their autograd graph — formerly 5 + 9 launches of this package plus
+// a dozen ATen gathers / scatters, each a few microseconds of work behind tens of microseconds of dependent-launch latency.
+#include <algorithm>
+
+#include "glue.cuh"
+#include "lbs.cuh"
+#include "mesh.cuh"
+
+struct GeoArgs {
+  int B, S;
+  float focal;
+  const int64_t* fid;
+  const float *pose, *rot, *trans, *cam, *wrist, *shape, *disps, *light_pos, *amb_ratio;  // parameter tables / shared parameters
+  // forward outputs
+  float *verts0, *joints, *verts, *normals, *vposed;  // vposed: (B,V0,3) blend-shaped rest vertices, kept for the backward
+  float *cam_T, *light_b, *light_R, *light_T, *centroid, *amb;  // (B,3) (B,3) (B,9) (B,3) (B,3) (1)
+  // backward inputs
+  const float *d_verts, *d_normals, *d_joints;
+  const float *d_cam_T, *d_light_pos, *d_light_R, *d_light_T, *d_amb;  // (B,3) (B,3) (B,9) (B,3) (1)
+  // backward outputs (accumulated with atomics; rows of the tables by fid)
+  float *g_pose, *g_cam, *g_rot, *g_wrist, *g_shape, *g_disps, *g_light, *g_amb;
+  float *d_rot, *d_trans, *d_wrist;  // (B,3) per minibatch frame, overwritten (nullable)
+};
+
+namespace {
+
+constexpr int GEO_THREADS = LBS_THREADS;
+constexpr int POSE_PAD = MAXJ * 3;
+
+__host__ __device__ inline size_t words(size_t bytes) { return (bytes + 3) / 4; }
+
+// full axis-angle pose of the model from the frame's table rows: MANO [rot | pose45] (utils/visualize.py:42-44); SMPL-X arm
+// [global_orient | 20 body joints (zero) | right wrist (joint 21) | jaw, eyes, left hand (zero) | right hand] (body_models.py:2278-2296)
+__device__ __forceinline__ float assemble_pose(const harp_ctx& c, const GeoArgs& a, int64_t row, int i) {
+  if (c.J == 16) return i < 3 ? a.rot[row * 3 + i] : a.pose[row * 45 + (i - 3)];
+  if (i < 3) return a.rot[row * 3 + i];
+  if (i >= 63 && i < 66) return a.wrist ? a.wrist[row * 3 + (i - 63)] : 0.f;
+  if (i >= 120) return a.pose[row * 45 + (i - 120)];
+  return 0.f;
+}
+
+__global__ void __launch_bounds__(GEO_THREADS) geo_fwd_kernel(harp_ctx c, GeoArgs a) {
+  extern __shared__ float dyn[];
+  LbsShared& s = *reinterpret_cast<LbsShared*>(dyn);
+  float* s_pose = dyn + words(sizeof(LbsShared));
+  float* v0s = s_pose + POSE_PAD;          // (V0,3) skinned coarse vertices
+  float* vs = v0s + (size_t)c.V0 * 3;      // (V,3) final vertices
+  float* vsub = vs + (size_t)c.V * 3;      // (V,3) subdivided, undisplaced vertices
+  __shared__ float red[32];
+  const int b = blockIdx.x, t = threadIdx.x, J = c.J;
+  const int64_t row = a.fid ? a.fid[b] : b;
+  for (int i = t; i < J * 3; i += GEO_THREADS) s_pose[i] = assemble_pose(c, a, row, i);
+  __syncthreads();
+  lbs_prologue(c, s_pose, a.shape, s);
+  lbs_forward_core(c, s, ld3(a.trans + row * 3), v0s, a.verts0 + (size_t)b * c.V0 * 3, a.joints + (size_t)b * c.n_joints_out * 3,
+                   a.vposed ? a.vposed + (size_t)b * c.V0 * 3 : nullptr);
+  __syncthreads();
+  // SubdivideMeshes (materialised once in shared memory: the gathers below touch every vertex ~12 times) + displacement
+  // along the normals of the undisplaced mesh (utils/visualize.py:48-60)
+  SubdivAccessor sub{v0s, c.edges0, c.V0};
+  for (int v = t; v < c.V; v += GEO_THREADS) st3(vsub + (size_t)v * 3, sub(v));
+  __syncthreads();
+  DirectAccessor und{vsub};
+  float* vg = a.verts + (size_t)b * c.V * 3;
+  for (int v = t; v < c.V; v += GEO_THREADS) {
+    f3 p = und(v);
+    if (a.disps) p = p + a.disps[v] * normalize_eps(vertex_normal_sum(c, und, v), 1e-6f);
+    st3(vs + (size_t)v * 3, p);
+    st3(vg + (size_t)v * 3, p);
+  }
+  __syncthreads();
+  DirectAccessor fin{vs};
+  float* ng = a.normals + (size_t)b * c.V * 3;
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  for (int v = t; v < c.V; v += GEO_THREADS) {
+    st3(ng + (size_t)v * 3, normalize_eps(vertex_normal_sum(c, fin, v), 1e-6f));
+    f3 p = fin(v);
+    sx += p.x; sy += p.y; sz += p.z;
+  }
+  sx = block_sum(sx, red); sy = block_sum(sy, red); sz = block_sum(sz, red);
+  if (t != 0) return;
+  // camera / light glue (as frame_glue_fwd_kernel, glue.cu)
+  float ctr[3] = {sx / (float)c.V, sy / (float)c.V, sz / (float)c.V};
+  const float* cam = a.cam + row * 3;
+  a.cam_T[b * 3 + 0] = -cam[1];
+  a.cam_T[b * 3 + 1] = -cam[2];
+  a.cam_T[b * 3 + 2] = (1.f / ((float)a.S * cam[0] + 1e-9f)) * (2.f * a.focal);  // reciprocal * scalar: torch's scalar / tensor (visualize.py:268)
+  float L[3] = {a.light_pos[0], a.light_pos[1], a.light_pos[2]}, R[9], T[3];
+  light_camera<float>(L, ctr, R, T);
+  for (int i = 0; i < 3; ++i) { a.light_b[b * 3 + i] = L[i]; a.light_T[b * 3 + i] = T[i]; a.centroid[b * 3 + i] = ctr[i]; }
+  for (int i = 0; i < 9; ++i) a.light_R[b * 9 + i] = R[i];
+  if (b == 0) a.amb[0] = 1.f / (1.f + expf(-a.amb_ratio[0]));
+}
+
+__global__ void __launch_bounds__(GEO_THREADS) geo_bwd_kernel(harp_ctx c, GeoArgs a, int scratch_floats) {
+  extern __shared__ float dyn[];
+  LbsShared& s = *reinterpret_cast<LbsShared*>(dyn);
+  LbsBwdShared& g = *reinterpret_cast<LbsBwdShared*>(dyn + words(sizeof(LbsShared)));
+  float* s_pose = dyn + words(sizeof(LbsShared)) + words(sizeof(LbsBwdShared));
+  float* s_out = s_pose + POSE_PAD;        // d_pose (J*3) | d_shape (n_shape) | d_trans (3)
+  float* v0s = s_out + POSE_PAD + MAXS + 4;  // (V0,3)
+  float* dv0 = v0s + (size_t)c.V0 * 3;     // (V0,3) gradient w.r.t. the skinned coarse vertices
+  float* A = dv0 + (size_t)c.V0 * 3;       // three (V,3) arrays, later the LBS backward's scratch
+  float* Bf = A + (size_t)c.V * 3;
+  float* C = Bf + (size_t)c.V * 3;
+  __shared__ float gc[3];
+  const int b = blockIdx.x, t = threadIdx.x, J = c.J, NS = c.n_shape, V = c.V;
+  const int64_t row = a.fid ? a.fid[b] : b;
+  for (int i = t; i < J * 3; i += GEO_THREADS) s_pose[i] = assemble_pose(c, a, row, i);
+  const float* v0g = a.verts0 + (size_t)b * c.V0 * 3;
+  for (int i = t; i < c.V0 * 3; i += GEO_THREADS) v0s[i] = v0g[i];
+  __syncthreads();
+  lbs_prologue(c, s_pose, a.shape, s);
+  // ---- camera / light glue backward (as frame_glue_bwd_kernel, glue.cu)
+  if (t == 0) {
+    const float* cam = a.cam + row * 3;
+    const float* dct = a.d_cam_T + (size_t)b * 3;
+    float den = (float)a.S * cam[0] + 1e-9f;
+    atomicAdd(a.g_cam + row * 3 + 0, dct[2] * (-(2.f * a.focal) * (float)a.S / (den * den)));
+    atomicAdd(a.g_cam + row * 3 + 1, -dct[0]);
+    atomicAdd(a.g_cam + row * 3 + 2, -dct[1]);
+    Dual<6> L[3], ct[3], R[9], T[3];
+    for (int i = 0; i < 3; ++i) { L[i] = Dual<6>::var(a.light_pos[i], i); ct[i] = Dual<6>::var(a.centroid[b * 3 + i], 3 + i); }
+    light_camera<Dual<6>>(L, ct, R, T);
+    float gg[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < 9; ++k) {
+      float u = a.d_light_R[b * 9 + k];
+      for (int i = 0; i < 6; ++i) gg[i] += u * R[k].d[i];
+    }
+    for (int k = 0; k < 3; ++k) {
+      float u = a.d_light_T[b * 3 + k];
+      for (int i = 0; i < 6; ++i) gg[i] += u * T[k].d[i];
+    }
+    if (a.g_light)
+      for (int i = 0; i < 3; ++i) atomicAdd(a.g_light + i, gg[i] + a.d_light_pos[b * 3 + i]);  // share_light_position: row 0
+    for (int i = 0; i < 3; ++i) gc[i] = gg[3 + i] / (float)V;
+    if (b == 0 && a.g_amb) {
+      float sg = 1.f / (1.f + expf(-a.amb_ratio[0]));
+      atomicAdd(a.g_amb, a.d_amb[0] * sg * (1.f - sg));
+    }
+  }
+  // Three (V,3) arrays in shared memory, re-used as the phases go (every gather reads materialised vertices: computing the
+  // edge midpoints on the fly inside the gathers was a third of this kernel's instructions):
+  //   P1  A = subdivided vertices;  Bf = final (displaced) vertices
+  //   P2  C = dN = normalize_bwd(N(final), d_normals)
+  //   P3  A = g1 = d_verts + centroid gradient + gather(dN over final)
+  //   P4  Bf = subdivided vertices again;  C = dNs = normalize_bwd(N(subdivided), disp * g1);  d_disps += n_s . g1
+  //   P5  A += gather(dNs over subdivided)            (in place: a thread rewrites only its own row)
+  //   P6  dv0 = subdivision backward of A
+  SubdivAccessor sub{v0s, c.edges0, c.V0};
+  for (int v = t; v < V; v += GEO_THREADS) st3(A + (size_t)v * 3, sub(v));
+  __syncthreads();
+  DirectAccessor undA{A};
+  for (int v = t; v < V; v += GEO_THREADS) {
+    f3 p = undA(v);
+    if (a.disps) p = p + a.disps[v] * normalize_eps(vertex_normal_sum(c, undA, v), 1e-6f);
+    st3(Bf + (size_t)v * 3, p);
+  }
+  __syncthreads();
+  DirectAccessor fin{Bf};
+  const float* dng = a.d_normals + (size_t)b * V * 3;
+  for (int v = t; v < V; v += GEO_THREADS)
+    st3(C + (size_t)v * 3, normalize_bwd(vertex_normal_sum(c, fin, v), ld3(dng + (size_t)v * 3), 1e-6f));
+  __syncthreads();
+  const float* dvg = a.d_verts + (size_t)b * V * 3;
+  const f3 gcv = mk3(gc[0], gc[1], gc[2]);
+  for (int v = t; v < V; v += GEO_THREADS)
+    st3(A + (size_t)v * 3, ld3(dvg + (size_t)v * 3) + gcv + normal_grad_gather(c, fin, C, v));
+  __syncthreads();
+  if (a.disps) {
+    for (int v = t; v < V; v += GEO_THREADS) st3(Bf + (size_t)v * 3, sub(v));
+    __syncthreads();
+    DirectAccessor undB{Bf};
+    for (int v = t; v < V; v += GEO_THREADS) {
+      f3 N = vertex_normal_sum(c, undB, v);
+      f3 gv = ld3(A + (size_t)v * 3);
+      if (a.g_disps) atomicAdd(a.g_disps + v, dot(normalize_eps(N, 1e-6f), gv));
+      st3(C + (size_t)v * 3, normalize_bwd(N, a.disps[v] * gv, 1e-6f));
+    }
+    __syncthreads();
+    for (int v = t; v < V; v += GEO_THREADS)
+      st3(A + (size_t)v * 3, ld3(A + (size_t)v * 3) + normal_grad_gather(c, undB, C, v));
+    __syncthreads();
+  }
+  const float* g2 = A;
+  // ---- P6: subdivision backward: d verts0[v] = g[v] + 0.5 * sum over incident coarse edges
+  for (int v = t; v < c.V0; v += GEO_THREADS) {
+    f3 acc = ld3(g2 + (size_t)v * 3);
+    if (c.subdivide)
+      for (int i = c.v0e_off[v]; i < c.v0e_off[v + 1]; ++i) acc = acc + 0.5f * ld3(g2 + (size_t)(c.V0 + c.v0e_idx[i]) * 3);
+    st3(dv0 + (size_t)v * 3, acc);
+  }
+  __syncthreads();
+  // ---- LBS backward (scratch: the three vertex arrays are dead)
+  (void)scratch_floats;
+  lbs_backward_core(c, s, g, A, A + (size_t)c.V0 * 3, dv0, a.d_joints ? a.d_joints + (size_t)b * c.n_joints_out * 3 : nullptr, s_out,
+                    s_out + POSE_PAD, s_out + POSE_PAD + MAXS, a.vposed ? a.vposed + (size_t)b * c.V0 * 3 : nullptr);
+  __syncthreads();
+  // ---- scatter into the parameter-table gradients
+  if (J == 16) {
+    if (t < 45) atomicAdd(a.g_pose + row * 45 + t, s_out[3 + t]);
+  } else {
+    if (t < 45) atomicAdd(a.g_pose + row * 45 + t, s_out[120 + t]);
+    if (t >= 64 && t < 67) {
+      float w = s_out[63 + (t - 64)];
+      if (a.g_wrist) atomicAdd(a.g_wrist + row * 3 + (t - 64), w);
+      if (a.d_wrist) a.d_wrist[(size_t)b * 3 + (t - 64)] = w;
+    }
+  }
+  if (t >= 96 && t < 99) {
+    float r = s_out[t - 96];
+    if (a.g_rot) atomicAdd(a.g_rot + row * 3 + (t - 96), r);
+    if (a.d_rot) a.d_rot[(size_t)b * 3 + (t - 96)] = r;
+    if (a.d_trans) a.d_trans[(size_t)b * 3 + (t - 96)] = s_out[POSE_PAD + MAXS + (t - 96)];
+  }
+  if (t >= 128 && t < 128 + NS) atomicAdd(a.g_shape + (t - 128), s_out[POSE_PAD + (t - 128)]);
+}
+
+size_t geo_fwd_smem(const harp_ctx* c) { return (words(sizeof(LbsShared)) + POSE_PAD + (size_t)c->V0 * 3 + (size_t)c->V * 6) * 4; }
+size_t geo_bwd_scratch(const harp_ctx* c) { return std::max((size_t)c->V * 9, (size_t)c->V0 * 3 + lbs_bwd_scratch_floats(c)); }
+size_t geo_bwd_smem(const harp_ctx* c) {
+  return (words(sizeof(LbsShared)) + words(sizeof(LbsBwdShared)) + 2 * POSE_PAD + MAXS + 4 + (size_t)c->V0 * 6 + geo_bwd_scratch(c)) * 4;
+}
+
+int configure(const void* fn, size_t bytes, size_t* configured) {
+  int dev = 0;
+  HARP_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || bytes > configured[dev]) {
+    HARP_REQUIRE(bytes <= 227 * 1024, HARP_ERR_CAPACITY, "fused geometry kernels: mesh too large for one CTA's shared memory");
+    HARP_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (dev >= 0 && dev < 64) configured[dev] = bytes;
+  }
+  return HARP_OK;
+}
+
+}  // namespace
+
+int harp_geo_fwd(harp_ctx* c, const GeoArgs& a, cudaStream_t st) {
+  HARP_REQUIRE(c->has_model && (c->J == 16 || c->J == 55), HARP_ERR_NO_MODEL, "harp_step_fused: ctx needs a MANO or SMPL-X-arm model");
+  static size_t configured[64] = {};
+  int rc = configure((const void*)geo_fwd_kernel, geo_fwd_smem(c), configured);
+  if (rc != HARP_OK) return rc;
+  harp_prof_begin(c, 2, st);
+  geo_fwd_kernel<<<a.B, GEO_THREADS, geo_fwd_smem(c), st>>>(*c, a);
+  harp_prof_end(c, 2, st);
+  HARP_LAUNCH_CHECK();
+  return HARP_OK;
+}
+
+int harp_geo_bwd(harp_ctx* c, const GeoArgs& a, cudaStream_t st) {
+  static size_t configured[64] = {};
+  int rc = configure((const void*)geo_bwd_kernel, geo_bwd_smem(c), configured);
+  if (rc != HARP_OK) return rc;
+  harp_prof_begin(c, 3, st);
+  geo_bwd_kernel<<<a.B, GEO_THREADS, geo_bwd_smem(c), st>>>(*c, a, (int)geo_bwd_scratch(c));
+  harp_prof_end(c, 3, st);
+  HARP_LAUNCH_CHECK();
+  return HARP_OK;
+}

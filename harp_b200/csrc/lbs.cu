@@ -6,134 +6,9 @@
 // each way over exactly the vertices the caller keeps.  FP32 FFMA throughout: the blendshape contractions are
 // [(J-1)*9 x 3V] per frame (135 x 2334 for MANO, 486 x 3078 for the arm) — far too small for tcgen05 tiles and needed
 // at full fp32 accuracy (last bullet).
-#include "common.cuh"
+#include "lbs.cuh"
 
 namespace {
-
-constexpr int LBS_THREADS = 1024;  // one vertex per thread for MANO (778); 64 registers x 1024 threads = one SM's register file
-constexpr int MAXJ = HARP_MAX_JOINTS;      // 64
-constexpr int MAXS = HARP_MAX_SHAPE;       // 32
-constexpr int MAXPB = (MAXJ - 1) * 9;      // pose-blendshape basis size
-
-struct LbsShared {
-  float beta[MAXS];
-  float pose[MAXJ * 3];   // full axis-angle pose (pose_mean added)
-  float R[MAXJ][9];
-  float J[MAXJ][3];
-  float G[MAXJ][12];      // 3x4 [R|t] global transforms
-  float A[MAXJ][12];      // with rest joint removed
-  float pose_map[MAXPB];
-  int parent[MAXJ];
-};
-
-// smplx.lbs.batch_rodrigues: R = I + sin(a) K + (1 - cos(a)) K^2, a = |r + 1e-8|   
-template <typename T>
-__device__ inline void rodrigues_smplx(const T r[3], T R[9]) {
-  T ax = r[0] + T(1e-8f), ay = r[1] + T(1e-8f), az = r[2] + T(1e-8f);
-  T angle = dsqrt(ax * ax + ay * ay + az * az);
-  T x = r[0] / angle, y = r[1] / angle, z = r[2] / angle;
-  T s = dsin(angle), c1 = T(1.f) - dcos(angle);
-  // K = [[0,-z,y],[z,0,-x],[-y,x,0]];  K^2 = [[-(y2+z2), xy, xz],[xy, -(x2+z2), yz],[xz, yz, -(x2+y2)]]
-  T xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
-  R[0] = T(1.f) - c1 * (yy + zz); R[1] = c1 * xy - s * z;          R[2] = c1 * xz + s * y;
-  R[3] = c1 * xy + s * z;          R[4] = T(1.f) - c1 * (xx + zz); R[5] = c1 * yz - s * x;
-  R[6] = c1 * xz - s * y;          R[7] = c1 * yz + s * x;          R[8] = T(1.f) - c1 * (xx + yy);
-}
-
-template <typename T>
-__device__ inline void rodrigues_any(int kind, const T r[3], T R[9]) {
-  if (kind == 0) rodrigues_quat<T>(r, R);
-  else rodrigues_smplx<T>(r, R);
-}
-
-// Everything that depends only on (pose, shape): shared by forward and backward.
-__device__ void lbs_prologue(const harp_ctx& c, const float* pose, const float* beta, LbsShared& s) {
-  int t = threadIdx.x, J = c.J, NS = c.n_shape;
-  if (t < NS) s.beta[t] = beta[t];
-  if (t < J * 3) s.pose[t] = pose[t] + c.pose_mean[t];
-  if (t < J) s.parent[t] = c.parents[t];
-  __syncthreads();
-  if (t < J) rodrigues_any<float>(c.rodrigues_kind, &s.pose[3 * t], s.R[t]);
-  if (t >= 64 && t < 64 + J * 3) {
-    int i = t - 64;
-    float a = c.J_template[i];
-    for (int b = 0; b < NS; ++b) a += c.J_shapedirs[i * NS + b] * s.beta[b];
-    s.J[i / 3][i % 3] = a;
-  }
-  __syncthreads();
-  for (int i = t; i < (J - 1) * 9; i += blockDim.x) {
-    int j = i / 9 + 1, k = i % 9;
-    s.pose_map[i] = s.R[j][k] - ((k == 0 || k == 4 || k == 8) ? 1.f : 0.f);
-  }
-  if (t == 0) {  // kinematic chain, parents precede children (SMPL family ordering)
-    for (int k = 0; k < 9; ++k) s.G[0][(k / 3) * 4 + (k % 3)] = s.R[0][k];
-    for (int k = 0; k < 3; ++k) s.G[0][k * 4 + 3] = s.J[0][k];
-    for (int j = 1; j < J; ++j) {
-      int p = s.parent[j];
-      float rel[3] = {s.J[j][0] - s.J[p][0], s.J[j][1] - s.J[p][1], s.J[j][2] - s.J[p][2]};
-      for (int r = 0; r < 3; ++r) {
-        for (int cc = 0; cc < 3; ++cc) {
-          float a = 0.f;
-          for (int k = 0; k < 3; ++k) a += s.G[p][r * 4 + k] * s.R[j][k * 3 + cc];
-          s.G[j][r * 4 + cc] = a;
-        }
-        float a = s.G[p][r * 4 + 3];
-        for (int k = 0; k < 3; ++k) a += s.G[p][r * 4 + k] * rel[k];
-        s.G[j][r * 4 + 3] = a;
-      }
-    }
-  }
-  __syncthreads();
-  if (t < J) {
-    for (int r = 0; r < 3; ++r) {
-      float tj = 0.f;
-      for (int k = 0; k < 3; ++k) {
-        s.A[t][r * 4 + k] = s.G[t][r * 4 + k];
-        tj += s.G[t][r * 4 + k] * s.J[t][k];
-      }
-      s.A[t][r * 4 + 3] = s.G[t][r * 4 + 3] - tj;
-    }
-  }
-  __syncthreads();
-}
-
-// v_posed for vertex v (template + shape + pose blendshapes); blendshape tables are stored transposed
-// (k, V0*3) so that consecutive threads read consecutive addresses.
-__device__ __forceinline__ f3 lbs_v_posed(const harp_ctx& c, const LbsShared& s, int v) {
-  // The blendshape offsets (|offset| ~ 1e-3 m) are summed on their own, in double, and added to the template once — as the
-  // reference does (v_shaped = template + blend_shapes(...), v_posed = v_shaped + matmul(pose_feature, posedirs):
-  // manolayer.py:181-200, smplx.lbs.lbs).  Accumulating them one by one INTO the coordinate (|x| ~ 0.5 m, ulp 6e-8) loses
-  // ~1e-6 m over the arm's 486 terms, which the sigma = 1e-7 silhouette turns into 5e-3 of gradient error.
-  int n3 = c.V0 * 3, i = v * 3, NS = c.n_shape, NP = (c.J - 1) * 9;
-  double sx = 0.0, sy = 0.0, sz = 0.0;
-  for (int b = 0; b < NS; ++b) {
-    const float* p = c.shapedirs + (size_t)b * n3 + i;
-    double w = s.beta[b];
-    sx += p[0] * w; sy += p[1] * w; sz += p[2] * w;
-  }
-  float x = c.v_template[i] + (float)sx, y = c.v_template[i + 1] + (float)sy, z = c.v_template[i + 2] + (float)sz;
-  double px = 0.0, py = 0.0, pz = 0.0;
-#pragma unroll 9
-  for (int k = 0; k < NP; ++k) {
-    const float* p = c.posedirs + (size_t)k * n3 + i;
-    double w = s.pose_map[k];
-    px += p[0] * w; py += p[1] * w; pz += p[2] * w;
-  }
-  return mk3(x + (float)px, y + (float)py, z + (float)pz);
-}
-
-__device__ __forceinline__ void lbs_blend(const harp_ctx& c, const LbsShared& s, int v, float T[12]) {
-#pragma unroll
-  for (int k = 0; k < 12; ++k) T[k] = 0.f;
-  const float* w = c.weights + (size_t)v * c.J;
-  for (int j = 0; j < c.J; ++j) {
-    float wj = w[j];
-    if (wj != 0.f) {
-#pragma unroll
-      for (int k = 0; k < 12; ++k) T[k] += wj * s.A[j][k];
-    }
-  }
-}
 
 __global__ void __launch_bounds__(LBS_THREADS) lbs_fwd_kernel(harp_ctx c, const float* __restrict__ pose,
                                                                 const float* __restrict__ shape, int shape_shared,
@@ -142,37 +17,8 @@ __global__ void __launch_bounds__(LBS_THREADS) lbs_fwd_kernel(harp_ctx c, const 
   __shared__ LbsShared s;
   int b = blockIdx.x, J = c.J;
   lbs_prologue(c, pose + (size_t)b * J * 3, shape + (shape_shared ? 0 : (size_t)b * c.n_shape), s);
-  f3 off = ld3(trans + (size_t)b * 3);
-  if (c.center_joint >= 0)  // wrist-centring of SMPLXARM (body_models.py:2342-2343)
-    off = off - mk3(s.G[c.center_joint][3], s.G[c.center_joint][7], s.G[c.center_joint][11]);
-  float* vout = verts0 + (size_t)b * c.V0 * 3;
-  for (int v = threadIdx.x; v < c.V0; v += blockDim.x) {
-    f3 vp = lbs_v_posed(c, s, v);
-    float T[12];
-    lbs_blend(c, s, v, T);
-    f3 o = mk3(T[0] * vp.x + T[1] * vp.y + T[2] * vp.z + T[3], T[4] * vp.x + T[5] * vp.y + T[6] * vp.z + T[7],
-               T[8] * vp.x + T[9] * vp.y + T[10] * vp.z + T[11]);
-    st3(vout + (size_t)v * 3, o + off);
-  }
-  __syncthreads();
-  if (threadIdx.x < c.n_joints_out) {
-    int src = c.joint_out_src[threadIdx.x];
-    f3 p;
-    if (src < J) p = mk3(s.G[src][3], s.G[src][7], s.G[src][11]) + off;
-    else p = ld3(vout + (size_t)c.tips[src - J] * 3);  // vertex-joints (fingertips): already offset
-    st3(joints + ((size_t)b * c.n_joints_out + threadIdx.x) * 3, p);
-  }
+  lbs_forward_core(c, s, ld3(trans + (size_t)b * 3), verts0 + (size_t)b * c.V0 * 3, nullptr, joints + (size_t)b * c.n_joints_out * 3);
 }
-
-struct LbsBwdShared {
-  float dA[MAXJ][12];
-  float dR[MAXJ][9];
-  float dJ[MAXJ][3];
-  float djtr[MAXJ][3];
-  float dpm[MAXPB];
-  float dbeta[MAXS];
-  float red[32];
-};
 
 __global__ void __launch_bounds__(LBS_THREADS) lbs_bwd_kernel(harp_ctx c, const float* __restrict__ pose,
                                                                 const float* __restrict__ shape, int shape_shared,
@@ -184,150 +30,10 @@ __global__ void __launch_bounds__(LBS_THREADS) lbs_bwd_kernel(harp_ctx c, const 
   LbsBwdShared& g = *reinterpret_cast<LbsBwdShared*>(dyn + (sizeof(LbsShared) + 3) / 4);
   float* dvp = dyn + (sizeof(LbsShared) + 3) / 4 + (sizeof(LbsBwdShared) + 3) / 4;  // (V0*3) gradient w.r.t. v_posed
   float* dTs = dvp + c.V0 * 3;      // (12, V0) per-vertex dT = g (x) [v_posed;1], k-major (bank-conflict free)
-  int b = blockIdx.x, t = threadIdx.x, J = c.J, NS = c.n_shape, NP = (J - 1) * 9, NJO = c.n_joints_out;
+  int b = blockIdx.x, J = c.J, NS = c.n_shape, NJO = c.n_joints_out;
   lbs_prologue(c, pose + (size_t)b * J * 3, shape + (shape_shared ? 0 : (size_t)b * NS), s);
-  const float* dj = d_joints ? d_joints + (size_t)b * NJO * 3 : nullptr;
-  if (t < J * 3) (&g.djtr[0][0])[t] = 0.f;
-  __syncthreads();
-  if (t < NJO && dj) {
-    int src = c.joint_out_src[t];
-    if (src < J)
-      for (int k = 0; k < 3; ++k) atomicAdd(&g.djtr[src][k], dj[t * 3 + k]);  // (a chain joint may be listed twice)
-  }
-  __syncthreads();
-  const float* gv = d_verts0 + (size_t)b * c.V0 * 3;
-  f3 tsum = mk3(0.f, 0.f, 0.f);
-  for (int v = t; v < c.V0; v += blockDim.x) {
-    f3 gg = ld3(gv + (size_t)v * 3);
-    if (dj) {
-      for (int k = 0; k < c.n_tips; ++k)
-        if (c.tips[k] == v) {
-          for (int o = 0; o < NJO; ++o)
-            if (c.joint_out_src[o] == J + k) gg = gg + ld3(dj + o * 3);
-        }
-    }
-    tsum = tsum + gg;
-    f3 vp = lbs_v_posed(c, s, v);
-    float T[12];
-    lbs_blend(c, s, v, T);
-    // d v_posed = T.R^T g
-    dvp[v * 3 + 0] = T[0] * gg.x + T[4] * gg.y + T[8] * gg.z;
-    dvp[v * 3 + 1] = T[1] * gg.x + T[5] * gg.y + T[9] * gg.z;
-    dvp[v * 3 + 2] = T[2] * gg.x + T[6] * gg.y + T[10] * gg.z;
-    float dT[12] = {gg.x * vp.x, gg.x * vp.y, gg.x * vp.z, gg.x, gg.y * vp.x, gg.y * vp.y, gg.y * vp.z, gg.y,
-                    gg.z * vp.x, gg.z * vp.y, gg.z * vp.z, gg.z};
-#pragma unroll
-    for (int k = 0; k < 12; ++k) dTs[k * c.V0 + v] = dT[k];
-  }
-  // total translation gradient = sum_v g_v + sum of chain-joint grads (vertex-joints were folded into g_v)
-  float tx = block_sum(tsum.x, g.red), ty = block_sum(tsum.y, g.red), tz = block_sum(tsum.z, g.red);
-  __syncthreads();
-  if (t == 0) {
-    for (int j = 0; j < J; ++j) { tx += g.djtr[j][0]; ty += g.djtr[j][1]; tz += g.djtr[j][2]; }
-    if (d_trans) { d_trans[b * 3] = tx; d_trans[b * 3 + 1] = ty; d_trans[b * 3 + 2] = tz; }
-    if (c.center_joint >= 0) {  // every output was shifted by -G[center].t
-      g.djtr[c.center_joint][0] -= tx; g.djtr[c.center_joint][1] -= ty; g.djtr[c.center_joint][2] -= tz;
-    }
-  }
-  int warp = t >> 5, lane = t & 31, nw = blockDim.x >> 5, n3 = c.V0 * 3;
-  // dA (J x 12) = W^T (J x V0) . dT (V0 x 12): one warp per output, lanes over vertices (no shared-memory float atomics
-  // in the hot loop: those compile to CAS spin loops)
-  for (int o = warp; o < J * 12; o += nw) {
-    int j = o / 12, k = o % 12;
-    const float* wrow = c.weightsT + (size_t)j * c.V0;
-    const float* drow = dTs + k * c.V0;
-    float a = 0.f;
-    for (int v = lane; v < c.V0; v += 32) a += wrow[v] * drow[v];
-    a = warp_sum(a);
-    if (lane == 0) g.dA[j][k] = a;
-  }
-  // d pose_map and the direct d shape: transposed-table mat-vec, one warp per output
-  // (four table rows in flight per warp: the loop is bound by L2 latency, not by arithmetic)
-  for (int o0 = warp * 4; o0 < NP + NS; o0 += nw * 4) {
-    const float* row[4];
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      int o = min(o0 + r, NP + NS - 1);
-      row[r] = o < NP ? c.posedirs + (size_t)o * n3 : c.shapedirs + (size_t)(o - NP) * n3;
-    }
-    for (int i = lane; i < n3; i += 32) {
-      float d = dvp[i];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) a[r] += row[r][i] * d;
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      float v = warp_sum(a[r]);
-      int o = o0 + r;
-      if (lane == 0 && o < NP + NS) { if (o < NP) g.dpm[o] = v; else g.dbeta[o - NP] = v; }
-    }
-  }
-  __syncthreads();
-  if (t == 0) {
-    // reverse-mode through A_j = [G.R | G.t - G.R J_j] and the kinematic chain G_j = G_p [R_j | J_j - J_p];
-    // dG accumulators reuse dTs (dead after the contraction above)
-    float(*dGR)[9] = reinterpret_cast<float(*)[9]>(dTs);
-    float(*dGt)[3] = reinterpret_cast<float(*)[3]>(dTs + MAXJ * 9);
-    for (int j = 0; j < J; ++j) {
-      for (int r = 0; r < 3; ++r) {
-        float dat = g.dA[j][r * 4 + 3];
-        dGt[j][r] = dat + g.djtr[j][r];
-        for (int k = 0; k < 3; ++k) dGR[j][r * 3 + k] = g.dA[j][r * 4 + k] - dat * s.J[j][k];
-      }
-      for (int k = 0; k < 3; ++k) {
-        float a = 0.f;
-        for (int r = 0; r < 3; ++r) a += s.G[j][r * 4 + k] * g.dA[j][r * 4 + 3];
-        g.dJ[j][k] = -a;
-      }
-    }
-    for (int j = J - 1; j >= 1; --j) {
-      int p = s.parent[j];
-      float rel[3] = {s.J[j][0] - s.J[p][0], s.J[j][1] - s.J[p][1], s.J[j][2] - s.J[p][2]};
-      for (int r = 0; r < 3; ++r)
-        for (int k = 0; k < 3; ++k) {
-          // dG_p.R[r][k] += sum_c dG_j.R[r][c] R_j[k][c] + dG_j.t[r] rel[k]
-          float a = dGt[j][r] * rel[k];
-          for (int cc = 0; cc < 3; ++cc) a += dGR[j][r * 3 + cc] * s.R[j][k * 3 + cc];
-          dGR[p][r * 3 + k] += a;
-        }
-      for (int k = 0; k < 3; ++k)
-        for (int cc = 0; cc < 3; ++cc) {
-          // dR_j[k][c] = sum_r G_p.R[r][k] dG_j.R[r][c]
-          float a = 0.f;
-          for (int r = 0; r < 3; ++r) a += s.G[p][r * 4 + k] * dGR[j][r * 3 + cc];
-          g.dR[j][k * 3 + cc] = a;
-        }
-      for (int k = 0; k < 3; ++k) {
-        float a = 0.f;
-        for (int r = 0; r < 3; ++r) a += s.G[p][r * 4 + k] * dGt[j][r];
-        g.dJ[j][k] += a;
-        g.dJ[p][k] -= a;
-      }
-      for (int r = 0; r < 3; ++r) dGt[p][r] += dGt[j][r];
-    }
-    for (int k = 0; k < 9; ++k) g.dR[0][k] = dGR[0][k];
-    for (int k = 0; k < 3; ++k) g.dJ[0][k] += dGt[0][k];
-  }
-  __syncthreads();
-  for (int i = t; i < NP; i += blockDim.x) g.dR[i / 9 + 1][i % 9] += g.dpm[i];  // pose_map = R - I
-  __syncthreads();
-  if (t < J) {  // Rodrigues Jacobian by forward-mode duals
-    Dual<3> a[3] = {Dual<3>::var(s.pose[3 * t], 0), Dual<3>::var(s.pose[3 * t + 1], 1), Dual<3>::var(s.pose[3 * t + 2], 2)};
-    Dual<3> R[9];
-    rodrigues_any<Dual<3>>(c.rodrigues_kind, a, R);
-    for (int i = 0; i < 3; ++i) {
-      float acc = 0.f;
-      for (int k = 0; k < 9; ++k) acc += R[k].d[i] * g.dR[t][k];
-      d_pose[(size_t)b * J * 3 + 3 * t + i] = acc;
-    }
-  }
-  if (t >= 64 && t < 64 + NS) {
-    int bi = t - 64;
-    float a = g.dbeta[bi];
-    for (int i = 0; i < J * 3; ++i) a += c.J_shapedirs[i * NS + bi] * (&g.dJ[0][0])[i];
-    d_shape[(size_t)b * NS + bi] = a;
-  }
+  lbs_backward_core(c, s, g, dvp, dTs, d_verts0 + (size_t)b * c.V0 * 3, d_joints ? d_joints + (size_t)b * NJO * 3 : nullptr,
+                    d_pose + (size_t)b * J * 3, d_shape + (size_t)b * NS, d_trans ? d_trans + (size_t)b * 3 : nullptr);
 }
 
 size_t lbs_bwd_smem(const harp_ctx* c) {

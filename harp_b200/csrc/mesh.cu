@@ -3,74 +3,11 @@
 // build; the regularisers use a handful of global atomics per element).
 // Replaces utils/visualize.py:48-64 (SubdivideMeshes, Meshes.verts_normals_padded), optimize_sequence.py:533-539
 // (mesh_laplacian_smoothing, mesh_normal_consistency, arap_loss) and loss/kps_loss.py.
-#include "common.cuh"
+#include "mesh.cuh"
 
 namespace {
 
 constexpr int TPB = 256;
-
-// Vertex accessors ------------------------------------------------------------------------------------------------
-struct SubdivAccessor {  // subdivided vertex v computed on the fly from the coarse verts of one frame
-  const float* v0;
-  const int32_t* edges0;
-  int V0;
-  __device__ __forceinline__ f3 operator()(int v) const {
-    if (v < V0) return ld3(v0 + (size_t)v * 3);
-    int e = v - V0;
-    f3 a = ld3(v0 + (size_t)edges0[2 * e] * 3), b = ld3(v0 + (size_t)edges0[2 * e + 1] * 3);
-    return mk3((a.x + b.x) / 2.f, (a.y + b.y) / 2.f, (a.z + b.z) / 2.f);  // mean(dim=2) of two
-  }
-};
-struct DirectAccessor {
-  const float* v;
-  __device__ __forceinline__ f3 operator()(int i) const { return ld3(v + (size_t)i * 3); }
-};
-
-// Meshes._compute_vertex_normals: sum over incident faces of the corner-specific cross product.
-template <typename Acc>
-__device__ __forceinline__ f3 vertex_normal_sum(const harp_ctx& c, const Acc& acc, int v) {
-  f3 n = mk3(0.f, 0.f, 0.f);
-  for (int i = c.vf_off[v]; i < c.vf_off[v + 1]; ++i) {
-    int fc = c.vf_idx[i], f = fc >> 2, k = fc & 3;
-    const int32_t* fv = c.faces + (size_t)f * 3;
-    f3 a = acc(fv[0]), b = acc(fv[1]), d = acc(fv[2]);
-    f3 cr = k == 0 ? cross(b - a, d - a) : (k == 1 ? cross(d - b, a - b) : cross(a - d, b - d));
-    n = n + cr;
-  }
-  return n;
-}
-
-__device__ __forceinline__ f3 normalize_eps(f3 n, float eps, float* len_out = nullptr) {
-  float l = sqrtf(dot(n, n));
-  float d = fmaxf(l, eps);
-  if (len_out) *len_out = l;
-  return mk3(n.x / d, n.y / d, n.z / d);
-}
-
-// backward of y = x / max(|x|, eps)
-__device__ __forceinline__ f3 normalize_bwd(f3 x, f3 gy, float eps) {
-  float l = sqrtf(dot(x, x));
-  if (l > eps) {
-    f3 y = (1.f / l) * x;
-    return (1.f / l) * (gy - dot(y, gy) * y);
-  }
-  return (1.f / eps) * gy;
-}
-
-// gradient of sum_f (c_f . G_f) w.r.t. vertex u, G_f = dN summed over the three corners of f
-template <typename Acc>
-__device__ __forceinline__ f3 normal_grad_gather(const harp_ctx& c, const Acc& acc, const float* dN, int u) {
-  f3 g = mk3(0.f, 0.f, 0.f);
-  for (int i = c.vf_off[u]; i < c.vf_off[u + 1]; ++i) {
-    int fc = c.vf_idx[i], f = fc >> 2, k = fc & 3;
-    const int32_t* fv = c.faces + (size_t)f * 3;
-    f3 a = acc(fv[0]), b = acc(fv[1]), d = acc(fv[2]);
-    f3 G = ld3(dN + (size_t)fv[0] * 3) + ld3(dN + (size_t)fv[1] * 3) + ld3(dN + (size_t)fv[2] * 3);
-    // c = (b-a) x (d-a):  d/db = (d-a) x G,  d/dd = G x (b-a),  d/da = (b-d) x G
-    g = g + (k == 0 ? cross(b - d, G) : (k == 1 ? cross(d - a, G) : cross(G, b - a)));
-  }
-  return g;
-}
 
 // ---- forward ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) build_displace_kernel(harp_ctx c, int B, const float* __restrict__ verts0,

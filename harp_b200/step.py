@@ -13,7 +13,7 @@ import ctypes as C
 
 import torch
 
-from . import _lib, camera
+from . import _lib
 from ._lib import HarpRenderArgs, HarpShadeGrads, check, iptr, lptr, ptr, stream
 
 # slots 1..5 are contiguous in harp_mesh_losses' output order
@@ -226,14 +226,9 @@ class HarpFitter:
             t.zero_()
         return t
 
-    def _side_stream(self):
-        if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream(device=self.hc.device)
-        return self._side
-
     # -- one minibatch ----------------------------------------------------------------------------------------------------
     def step(self, fid, off_albedo, off_normal, stage="both", update=True, batch=None, frame_range=None, exchange=True,
-             batch_u8=None, after_render=None):
+             batch_u8=None):
         """fid: (B,) long device tensor of frame ids owned by this rank.  stage: 'coarse' | 'both' | 'app'
         (`optimize_sequence.py:507-515`).  batch: optional dict overriding self.frames rows (host->device ingest path).
         frame_range=(a,b): promise that fid == arange(a,b), so image rows are used in place instead of gathered.
@@ -241,13 +236,11 @@ class HarpFitter:
         (and the mask eroded) on the device like `load_img` (utils/data_util.py:11-30).
         Returns the device tensor of unweighted losses (LOSS_NAMES order); gradients are in self.coarse.grad / self.app.grad."""
         hc, L, S, focal = self.hc, _lib.lib(), self.S, self.focal
-        dev, st = hc.device, stream()
+        st = stream()
         B = int(fid.shape[0])
         R = self.world_size
-        fscale = 1.0 / R  # frame losses are means over the GLOBAL batch; frame-independent terms are split over ranks
         hc.reserve(B, S)
         P, A = self.coarse.p, self.app.p
-        coarse_on, app_on = stage in ("coarse", "both"), stage in ("both", "app")
         if batch_u8 is not None:
             from .ops import ingest_u8
             fr = ingest_u8(batch_u8["rgb"], batch_u8["mask"],
@@ -261,101 +254,36 @@ class HarpFitter:
         else:
             fr = {k: v.index_select(0, fid) for k, v in self.frames.items()}
         self._gbuf.zero_()  # losses, coarse and appearance gradients
-        # ---- forward geometry
-        rot_b, pose_b = self.rot.index_select(0, fid), P["pose"].index_select(0, fid)
-        if self.arm:  # SMPL-X joint order: global | 20 body joints | right wrist (joint 21) | jaw, eyes | left hand | right hand
-            z = self._buf("zeros", (B, 60))
-            pose48 = torch.cat((rot_b, z, self.wrist.index_select(0, fid), z[:, :54], pose_b), 1)
-        else:
-            pose48 = torch.cat((rot_b, pose_b), 1)
-        trans = self.trans.index_select(0, fid)
-        NJ = hc.n_joints_out
-        verts0 = self._buf("verts0", (B, hc.V0, 3), zero=False)
-        joints = self._buf("joints", (B, NJ, 3), zero=False)
-        check(L.harp_lbs_fwd(hc.h, B, ptr(pose48), ptr(P["shape"]), 1, ptr(trans), ptr(verts0), ptr(joints), st))
-        disps = P["verts_disps"].view(-1)
-        verts = self._buf("verts", (B, hc.V, 3), zero=False)
-        normals = self._buf("normals", (B, hc.V, 3), zero=False)
-        check(L.harp_mesh_build_fwd(hc.h, B, ptr(verts0), ptr(disps), ptr(verts), ptr(normals), st))
-        # ---- gradient accumulators: one arena, one fill
-        NJ3 = NJ * 3
-        sizes = dict(d_verts=B * hc.V * 3, d_normals=B * hc.V * 3, d_joints=B * NJ3, d_cT=B * 3, d_lR=B * 9, d_lT=B * 3,
-                     d_lpos=B * 3, d_amb=4)
-        arena = self._buf("zero_arena", (sum(sizes.values()),))
-        z, o = {}, 0
-        for k, n in sizes.items():
-            z[k] = arena[o:o + n]
-            o += n
-        d_verts, d_normals = z["d_verts"].view(B, hc.V, 3), z["d_normals"].view(B, hc.V, 3)
-        d_joints, d_cT = z["d_joints"].view(B, NJ, 3), z["d_cT"].view(B, 3)
-        d_lR, d_lT, d_lpos, d_amb = z["d_lR"].view(B, 3, 3), z["d_lT"].view(B, 3), z["d_lpos"].view(B, 3), z["d_amb"][:1]
-        # ---- per-frame camera / light glue: one launch (harp_frame_glue_fwd) instead of ~30 ATen ops
-        cR = camera.flip_xy_R(B, dev)
-        cTc, light_bc, lRc, lTc, centroid = (self._buf(n, (B, k), zero=False) for n, k in
-                                             (("cTc", 3), ("light_bc", 3), ("lRc", 9), ("lTc", 3), ("centroid", 3)))
-        ambc = self._buf("ambc", (1,), zero=False)
-        light_shared = A["light_positions"][0]  # share_light_position (optimize_sequence.py:453-454)
-        check(L.harp_frame_glue_fwd(hc.h, B, S, focal, ptr(P["cam"]), lptr(fid), ptr(light_shared), ptr(A["amb_ratio"]), ptr(verts),
-                                    ptr(cTc), ptr(light_bc), ptr(lRc), ptr(lTc), ptr(ambc), ptr(centroid), st))
-        W = LOSS_WEIGHTS
-        # ---- both renders (silhouette 469-471 and shadowed colour 474-488 run in every stage; their losses are gated by
-        #      COARSE_OPT / APP_OPT, 517-519 and 541-543) in one fused pixel pass
+        ws = self._buf("workspace", (int(L.harp_step_workspace_floats(hc.h, B)),), zero=False)
         alpha = self._buf("alpha", (B, S, S), zero=False)
         rgb = self._buf("rgb", (B, S, S, 3), zero=False)
+        d_rot, d_trans, d_wrist = (self._buf(n, (B, 3), zero=False) for n in ("d_rot", "d_trans", "d_wrist"))
         tex, nm = A["texture"], A["normal_map"]
-        H, Wd = tex.shape[-3], tex.shape[-2]
-        gs = HarpShadeGrads(d_verts=ptr(d_verts), d_normals=ptr(d_normals), d_cam_R=None, d_cam_T=ptr(d_cT), d_light_R=ptr(d_lR),
-                            d_light_T=ptr(d_lT), d_light_pos=ptr(d_lpos), d_amb=ptr(d_amb),
-                            d_texture=ptr(self.app.g["texture"]), d_normal_map=ptr(self.app.g["normal_map"]))
-        ra = HarpRenderArgs(verts=ptr(verts), normals=ptr(normals), cam_R=ptr(cR), cam_T=ptr(cTc), light_R=ptr(lRc), light_T=ptr(lTc),
-                            light_pos=ptr(light_bc), amb=ptr(ambc), texture=ptr(tex), normal_map=ptr(nm), texH=H, texW=Wd,
-                            self_shadow=int(self.self_shadow), faces_per_pixel=int(self.faces_per_pixel), sigma=1e-7, y_sil=ptr(fr["y_sil"]), y_true=ptr(fr["y_true"]),
-                            y_mask=ptr(fr["y_sil_eroded"]), w_sil=W["silhouette"] * fscale if coarse_on else 0.0,
-                            w_photo=W["photo"] * fscale if app_on else 0.0, alpha=ptr(alpha), rgb=ptr(rgb),
-                            loss_sil=ptr(self.losses[_SLOT["silhouette"]:]), loss_photo=ptr(self.losses[_SLOT["photo"]:]), grads=gs)
-        # ---- regulariser branch on a side stream, concurrent with the render: texture regularisers (552-553) and the mesh
-        #      regularisers + keypoint anchor (521-539) depend only on the mesh / textures and accumulate with atomics
-        main, side = torch.cuda.current_stream(), self._side_stream()
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            ss = stream()
-            if app_on:
-                check(L.harp_texture_reg(hc.h, 0, ptr(tex), H, Wd, iptr(off_albedo), ptr(self.uv_mask), W["albedo"] * fscale,
-                                         ptr(self.losses[_SLOT["albedo"]:]), ptr(self.app.g["texture"]), ss))
-                check(L.harp_texture_reg(hc.h, 1, ptr(nm), H, Wd, iptr(off_normal), ptr(self.uv_mask), W["normal_reg"] * fscale,
-                                         ptr(self.losses[_SLOT["normal_reg"]:]), ptr(self.app.g["normal_map"]), ss))
-            if coarse_on:
-                w5 = (C.c_float * 5)(W["laplacian"] * fscale, W["normal"] * fscale, W["arap"] * fscale, W["kps_anchor"] * fscale,
-                                     W["vert_disp_reg"] * fscale)
-                check(L.harp_mesh_losses(hc.h, B, ptr(verts), ptr(self.ref_verts), ptr(joints), ptr(fr["init_joints"]), ptr(disps), w5,
-                                         ptr(self.losses[_SLOT["laplacian"]:]), ptr(d_verts), ptr(d_joints),
-                                         ptr(self.coarse.g["verts_disps"].view(-1)), ss))
-        check(L.harp_render_fused(hc.h, B, S, focal, C.byref(ra), st))
-        main.wait_stream(side)
-        if after_render is not None:  # texture / normal-map gradients are final here (capture() splits the step at this point)
-            after_render()
-        # ---- backward through the small per-frame chain, then geometry
-        if coarse_on or app_on:
-            check(L.harp_frame_glue_bwd(hc.h, B, S, focal, ptr(P["cam"]), lptr(fid), ptr(light_shared), ptr(A["amb_ratio"]),
-                                        ptr(centroid), ptr(d_cT), ptr(d_lR), ptr(d_lT), ptr(d_lpos), ptr(d_amb),
-                                        ptr(self.coarse.g["cam"]), ptr(self.app.g["light_positions"]), ptr(self.app.g["amb_ratio"]),
-                                        ptr(d_verts), st))
-            d_verts0 = self._buf("d_verts0", (B, hc.V0, 3), zero=False)
-            check(L.harp_mesh_build_bwd(hc.h, B, ptr(verts0), ptr(disps), ptr(d_verts), ptr(d_normals), ptr(d_verts0),
-                                        ptr(self.coarse.g["verts_disps"].view(-1)), st))
-            d_pose48 = self._buf("d_pose48", (B, pose48.shape[1]), zero=False)
-            d_betas = self._buf("d_betas", (B, 10), zero=False)
-            d_trans = self._buf("d_trans", (B, 3), zero=False)
-            check(L.harp_lbs_bwd(hc.h, B, ptr(pose48), ptr(P["shape"]), 1, ptr(trans), ptr(d_verts0), ptr(d_joints),
-                                 ptr(d_pose48), ptr(d_betas), ptr(d_trans), st))
-            self.coarse.g["pose"].index_add_(0, fid, d_pose48[:, -45:])
-            if self.opt_arm_pose:
-                self.coarse.g["rot"].index_add_(0, fid, d_pose48[:, :3])
-                self.coarse.g["wrist_pose"].index_add_(0, fid, d_pose48[:, 63:66])
-            self.coarse.g["shape"] += d_betas.sum(0)
-            self.last = dict(d_rot=d_pose48[:, :3], d_trans=d_trans, alpha=alpha, rgb=rgb, verts=verts, joints=joints,
-                             d_wrist=d_pose48[:, 63:66] if self.arm else None)
-        # ---- data-parallel exchange: ONE allreduce of the shared-parameter gradients
+        G, GA = self.coarse.g, self.app.g
+        disps = P["verts_disps"].view(-1)
+        a = _lib.HarpStepArgs(
+            B=B, S=S, stage={"coarse": 1, "app": 2, "both": 3}[stage], self_shadow=int(self.self_shadow),
+            faces_per_pixel=int(self.faces_per_pixel), texH=tex.shape[-3], texW=tex.shape[-2], focal=focal, sigma=1e-7,
+            frame_scale=1.0 / R, weights=(C.c_float * 9)(*[LOSS_WEIGHTS[n] for n in LOSS_NAMES]),
+            fid=lptr(fid), pose=ptr(P["pose"]), rot=ptr(self.rot), trans=ptr(self.trans), cam=ptr(P["cam"]),
+            wrist_pose=ptr(self.wrist) if self.arm else None, shape=ptr(P["shape"]), verts_disps=ptr(disps), texture=ptr(tex),
+            normal_map=ptr(nm), light_position=ptr(A["light_positions"]), amb_ratio=ptr(A["amb_ratio"]),
+            y_true=ptr(fr["y_true"]), y_sil=ptr(fr["y_sil"]), y_sil_eroded=ptr(fr["y_sil_eroded"]), init_joints=ptr(fr["init_joints"]),
+            ref_verts=ptr(self.ref_verts), uv_mask=ptr(self.uv_mask), off_albedo=iptr(off_albedo), off_normal=iptr(off_normal),
+            losses=ptr(self.losses), alpha=ptr(alpha), rgb=ptr(rgb), g_pose=ptr(G["pose"]), g_cam=ptr(G["cam"]),
+            g_rot=ptr(G["rot"]) if self.opt_arm_pose else None, g_wrist_pose=ptr(G["wrist_pose"]) if self.opt_arm_pose else None,
+            g_shape=ptr(G["shape"]), g_verts_disps=ptr(G["verts_disps"].view(-1)), g_texture=ptr(GA["texture"]),
+            g_normal_map=ptr(GA["normal_map"]), g_light_position=ptr(GA["light_positions"]), g_amb_ratio=ptr(GA["amb_ratio"]),
+            d_rot=ptr(d_rot), d_trans=ptr(d_trans), d_wrist=ptr(d_wrist) if self.arm else None, workspace=ptr(ws))
+        check(L.harp_step_fused(hc.h, C.byref(a), st))
+        views = [C.c_void_p() for _ in range(4)]
+        check(L.harp_step_workspace_views(hc.h, B, ptr(ws), *[C.byref(v) for v in views]))
+        off = [(v.value - ws.data_ptr()) // 4 for v in views]
+        NJ = hc.n_joints_out
+        self.last = dict(d_rot=d_rot, d_trans=d_trans, alpha=alpha, rgb=rgb, d_wrist=d_wrist if self.arm else None,
+                         verts0=ws[off[0]:off[0] + B * hc.V0 * 3].view(B, hc.V0, 3), joints=ws[off[1]:off[1] + B * NJ * 3].view(B, NJ, 3),
+                         verts=ws[off[2]:off[2] + B * hc.V * 3].view(B, hc.V, 3), normals=ws[off[3]:off[3] + B * hc.V * 3].view(B, hc.V, 3))
+        # ---- data-parallel exchange: ONE exchange of the shared-parameter gradients
         if R > 1 and exchange:
             self._allreduce_shared()
         if update:
@@ -404,81 +332,6 @@ class HarpFitter:
             self._allreduce_shared()
             self._update(stage)
         return replay_and_exchange
-
-    def capture_overlapped(self, fid, off_albedo, off_normal, stage="both", frame_range=None, batch=None, warmup=2, batch_u8=None,
-                           keep_profile=False):
-        """Multi-GPU variant of capture(): the step is recorded as TWO graphs split where the texture / normal-map gradients
-        (99.8 % of the exchanged bytes) are final, so their allreduce runs on a communication stream underneath the geometry
-        backward (frame glue, mesh build, LBS) of the second graph; the 12 KB of coarse shared gradients, losses, amb and
-        light follow in two small allreduces.  Same result as capture() up to the summation order of the collectives."""
-        import torch.distributed as dist
-        assert self.world_size > 1
-        kw = dict(stage=stage, frame_range=frame_range, batch=batch, batch_u8=batch_u8)
-        if not keep_profile:
-            self.hc.profile(False)
-        cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream(device=self.hc.device)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                self.step(fid, off_albedo, off_normal, update=True, **kw)
-        cur.wait_stream(side)
-        torch.cuda.synchronize()
-        if keep_profile:
-            self.hc.profile_read()
-        if getattr(self, "_capture_stream", None) is None:
-            self._capture_stream = torch.cuda.Stream(device=self.hc.device, priority=-1)
-        cap = self._capture_stream
-        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        cap.wait_stream(cur)
-        state = {"open": None}
-        try:
-            with torch.cuda.stream(cap):
-                g1.capture_begin()
-                state["open"] = g1
-
-                def split():
-                    g1.capture_end()
-                    state["open"] = None
-                    g2.capture_begin(pool=g1.pool())
-                    state["open"] = g2
-                self.step(fid, off_albedo, off_normal, update=False, exchange=False, after_render=split, **kw)
-                g2.capture_end()
-                state["open"] = None
-        except Exception:
-            if state["open"] is not None:
-                try:
-                    with torch.cuda.stream(cap):
-                        state["open"].capture_end()
-                except Exception:
-                    pass
-            torch.cuda.synchronize()
-            raise
-        cur.wait_stream(cap)
-        torch.cuda.synchronize()
-        self._set_graph((g1, g2))
-        nc, nl = self.coarse.grad.numel(), len(LOSS_NAMES)
-        app0 = nc + nl
-        o = dict(zip(self.app.names, self.app.offsets))
-        big = self._gbuf[app0 + o["texture"]:app0 + o["light_positions"]]          # texture | normal_map
-        small = self._gbuf[self._shared_start:app0 + o["texture"]]                 # verts_disps | shape | losses | amb
-        light0 = self._gbuf[app0 + o["light_positions"]:app0 + o["light_positions"] + 3]
-        comm = torch.cuda.Stream(device=self.hc.device)
-        R, pg = self.world_size, self.pg
-
-        def replay():
-            main = torch.cuda.current_stream()
-            g1.replay()
-            comm.wait_stream(main)
-            with torch.cuda.stream(comm):
-                dist.all_reduce(big, op=dist.ReduceOp.SUM, group=pg)
-            g2.replay()
-            dist.all_reduce(small, op=dist.ReduceOp.SUM, group=pg)
-            dist.all_reduce(light0, op=dist.ReduceOp.SUM, group=pg)
-            main.wait_stream(comm)
-            self._gbuf[self._loss_slice] /= R
-            self._update(stage)
-        return replay
 
     def _set_graph(self, graph):
         """Keep every captured graph and pin the context's scratch for as long as they live (a later harp_ctx_reserve with

@@ -290,6 +290,39 @@ HARP_API int harp_adam(float* param, const float* grad, float* exp_avg, float* e
 HARP_API int harp_adam_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                            float beta2, float eps, void* state, void* stream);
 
+/* ---- the whole minibatch step behind one call (optimize_sequence.py:446-579) ----------------------------
+ * prepare_mesh, both renders, every loss of 517-553 except VGG and the complete backward, enqueued on `stream` as a fixed
+ * launch sequence (capturable).  Parameters are the reference's tensors (optimize_sequence.py:181-250) as device tables; the
+ * frame rows a minibatch uses are selected by `fid` INSIDE the kernels, and their gradients are accumulated (+=, atomics) into
+ * the same rows of the g_* tables.  `weights` / `losses` order: silhouette, laplacian, normal, arap, kps_anchor, vert_disp_reg,
+ * photo, albedo, normal_reg (unweighted loss values are ACCUMULATED into `losses`: zero it per step).
+ * stage: 1 = COARSE_OPT, 2 = APP_OPT, 3 = both (optimize_sequence.py:507-515).  frame_scale = 1 / world_size under frame
+ * sharding (frame losses are means over the global batch; frame-independent terms are split over ranks).
+ * MANO ctx (J = 16): pose (T,45), rot (T,3); SMPL-X-arm ctx (J = 55): also wrist_pose (T,3) (utils/visualize.py:36-44). */
+typedef struct {
+  int32_t B, S, stage, self_shadow, faces_per_pixel, texH, texW;
+  float focal, sigma, frame_scale;
+  float weights[9];
+  const int64_t* fid;                                   /* (B) rows of the per-frame tables */
+  const float *pose, *rot, *trans, *cam, *wrist_pose;   /* (T,45) (T,3) (T,3) (T,3) (T,3 | NULL) */
+  const float *shape, *verts_disps;                     /* (10), (V | NULL) */
+  const float *texture, *normal_map;                    /* (texH,texW,3) */
+  const float *light_position, *amb_ratio;              /* (3) shared light (row 0), () pre-sigmoid ambient */
+  const float *y_true, *y_sil, *y_sil_eroded;           /* minibatch frames: (B,S,S,3) (B,S,S) (B,S,S) */
+  const float *init_joints, *ref_verts, *uv_mask;       /* (B,21,3) mm, (V,3) ARAP reference, (texH,texW) */
+  const int32_t *off_albedo, *off_normal;               /* (texH,texW,2) neighbour offsets of the texture regularisers */
+  float *losses, *alpha, *rgb;                          /* (9) accumulated; (B,S,S); (B,S,S,3) */
+  float *g_pose, *g_cam, *g_rot, *g_wrist_pose;         /* table gradients, rows by fid; g_rot / g_wrist_pose nullable */
+  float *g_shape, *g_verts_disps, *g_texture, *g_normal_map, *g_light_position, *g_amb_ratio;
+  float *d_rot, *d_trans, *d_wrist;                     /* (B,3) per minibatch frame, overwritten; nullable */
+  float* workspace;                                     /* harp_step_workspace_floats(ctx, B) floats, caller-allocated */
+} harp_step_args;
+HARP_API size_t harp_step_workspace_floats(const harp_ctx* ctx, int B);
+HARP_API int harp_step_fused(harp_ctx* ctx, const harp_step_args* args, void* stream);
+/* where the step left its intermediate results inside `workspace`: (B,V0,3) (B,n_joints,3) (B,V,3) (B,V,3) */
+HARP_API int harp_step_workspace_views(const harp_ctx* ctx, int B, float* workspace, float** verts0, float** joints, float** verts,
+                                       float** normals);
+
 /* ---- data-parallel exchange over NVLink peer memory (the reference is single-process) -------------------
  * One process per GPU of ONE node.  Every rank's gradient buffer lives in an IPC-shareable allocation that all ranks map; the
  * sum of the shared-parameter gradients is a reduce-scatter + all-gather kernel written against the peers' buffers and

@@ -94,7 +94,7 @@ def test_full_size_fused_pass_matches_standalone_ops(full_scene):
     a2 = Silhouette.apply(hc, verts, cR, cT, sc["focal"], SIZE, 1e-7, 50)
     d = (a2 - alpha).abs()
     assert float((d <= 1e-6).double().mean()) >= 0.99999 and float(d.max()) < 1e-3
-    _, normals = MeshBuild.apply(hc, ft._scratch["verts0"][:B], ft.coarse.p["verts_disps"])
+    _, normals = MeshBuild.apply(hc, ft.last["verts0"][:B], ft.coarse.p["verts_disps"])
     light = ft.app.p["light_positions"][0][None].expand(B, 3).contiguous()
     lR, lT = camera.light_camera(light, verts.mean(1))
     rgb2 = Shade.apply(hc, verts, normals, cR, cT, lR, lT, light, torch.sigmoid(ft.app.p["amb_ratio"]), ft.app.p["texture"],
