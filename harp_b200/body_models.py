@@ -19,6 +19,7 @@ class SMPLXARM(torch.nn.Module):
         t = arm_template if arm_template is not None else synth.load_template("arm")
         red = synth.reduce_smplx_arm(smplx_model, t)
         self.right_arm_faces_tensor = torch.as_tensor(t["faces0"]).long()  # body_models.py:2113-2116
+        self.right_mano_idx = torch.as_tensor(t["mano_vert_from_arm"]).long().to(device)  # MANO's 778 vertices inside the arm mesh
         kw = dict(faces_uvs=t["faces_uvs"], verts_uvs=t["verts_uvs"], lbs=red, device=device)
         self.hc_coarse = structures.register_context(ops.HarpContext(t["faces0"], subdivide=False, **kw))
         self.hc = structures.register_context(ops.HarpContext(t["faces0"], subdivide=True, **kw))
@@ -39,11 +40,13 @@ class SMPLXARM(torch.nn.Module):
                         ("jaw_pose", jaw_pose), ("leye_pose", leye_pose), ("reye_pose", reye_pose)):
             if v is not None:
                 raise NotImplementedError(f"SMPLXARM drop-in: `{name}` stays at the layer default in HARP (utils/visualize.py:37-40)")
-        if return_type != "mano_w_arm":
-            raise NotImplementedError("only return_type='mano_w_arm' is on HARP's path")
+        if return_type not in ("mano_w_arm", "mano"):
+            raise NotImplementedError("return_type must be 'mano_w_arm' (fitting loop) or 'mano' (upstream smoothing)")
         B = global_orient.shape[0]
         transl = transl if transl is not None else global_orient.new_zeros(B, 3)
         right_hand_pose = right_hand_pose if right_hand_pose is not None else global_orient.new_zeros(B, 45)
         full_pose = self.assemble_full_pose(global_orient, right_hand_pose, kwargs.get("right_wrist_pose"))
         verts, joints = ops.Lbs.apply(hc or self.hc, full_pose, betas, transl)
+        if return_type == "mano":  # body_models.py:2387-2388: the hand's 778 vertices in MANO order, the 21 MANO joints
+            return verts[:, self.right_mano_idx] * 1000.0, joints[:, :21] * 1000.0
         return verts * 1000.0, joints * 1000.0  # body_models.py:2383-2385

@@ -226,30 +226,50 @@ __device__ __forceinline__ void lbs_backward_core(const harp_ctx& c, LbsShared& 
     const float* wrow = c.weightsT + (size_t)j * c.V0;
     const float* drow = dTs + k * c.V0;
     float a = 0.f;
-    for (int v = lane; v < c.V0; v += 32) a += wrow[v] * drow[v];
+#pragma unroll 8
+    for (int v = lane; v < c.V0; v += 32) a += __ldg(wrow + v) * drow[v];  // unrolled: eight table loads in flight per lane
     a = warp_sum(a);
     if (lane == 0) g.dA[j][k] = a;
   }
-  // d pose_map and the direct d shape: transposed-table mat-vec, one warp per output
-  // (four table rows in flight per warp: the loop is bound by L2 latency, not by arithmetic)
-  for (int o0 = warp * 4; o0 < NP + NS; o0 += nw * 4) {
-    const float* row[4];
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
+  // d pose_map and the direct d shape: transposed-table mat-vec, one warp per group of five outputs (145 = 29 x 5: one round
+  // for MANO), 8-byte loads, four iterations unrolled: 20 table loads in flight per lane — the loop is bound by the L2
+  // latency of the 1.3 MB blendshape table, not by arithmetic
+  {
+    constexpr int RW = 5;
+    const int n2 = n3 >> 1;
+    const float2* d2 = reinterpret_cast<const float2*>(dvp);
+    for (int o0 = warp * RW; o0 < NP + NS; o0 += nw * RW) {
+      const float* row[RW];
+      float a[RW];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      int o = min(o0 + r, NP + NS - 1);
-      row[r] = o < NP ? c.posedirs + (size_t)o * n3 : c.shapedirs + (size_t)(o - NP) * n3;
-    }
-    for (int i = lane; i < n3; i += 32) {
-      float d = dvp[i];
+      for (int r = 0; r < RW; ++r) {
+        int o = min(o0 + r, NP + NS - 1);
+        row[r] = o < NP ? c.posedirs + (size_t)o * n3 : c.shapedirs + (size_t)(o - NP) * n3;
+        a[r] = 0.f;
+      }
+      if ((n3 & 1) == 0 && (reinterpret_cast<size_t>(dvp) & 7) == 0) {  // rows start 8-byte aligned when 3 V0 is even (MANO 2334, arm 3078)
+#pragma unroll 4
+        for (int i = lane; i < n2; i += 32) {
+          float2 d = d2[i];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) a[r] += row[r][i] * d;
-    }
+          for (int r = 0; r < RW; ++r) {
+            float2 x = __ldg(reinterpret_cast<const float2*>(row[r]) + i);
+            a[r] += x.x * d.x + x.y * d.y;
+          }
+        }
+      } else {
+        for (int i = lane; i < n3; i += 32) {
+          float d = dvp[i];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      float v = warp_sum(a[r]);
-      int o = o0 + r;
-      if (lane == 0 && o < NP + NS) { if (o < NP) g.dpm[o] = v; else g.dbeta[o - NP] = v; }
+          for (int r = 0; r < RW; ++r) a[r] += row[r][i] * d;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RW; ++r) {
+        float v = warp_sum(a[r]);
+        int o = o0 + r;
+        if (lane == 0 && o < NP + NS) { if (o < NP) g.dpm[o] = v; else g.dbeta[o - NP] = v; }
+      }
     }
   }
   __syncthreads();

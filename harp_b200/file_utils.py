@@ -14,8 +14,7 @@ PARAM_KEYS = ("trans", "pose", "rot", "shape", "wrist_pose", "verts_disps", "ver
 def save_result(params, base_output_dir, test=False):
     """utils/file_utils.py:6-16.  `params`: dict of tensors / arrays, or a HarpFitter (its `.params()` are used)."""
     if hasattr(params, "params") and callable(params.params):
-        extra = getattr(params, "extra_params", {})
-        params = dict(params.params(), **extra)
+        params = dict(params.params())  # a HarpFitter: optimised tensors + the keys it was built with (extra_params)
     out = {}
     for k, v in params.items():
         if v is None:

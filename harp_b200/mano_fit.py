@@ -140,15 +140,15 @@ def _keypoint_distance(est, target, n_frames):
 
 def optimize_smooth_seq(params_cpu, mano_layer, use_smplx_arm=False, nimble_hand=False, img_res=224, mano_j_regressor=None,
                         total_iter_pose=1000, total_iter_cam=1000):
-    """Same call and return value as `metro_modifications/hand_utils.py:540` (MANO branch): temporal smoothing of the per-frame
+    """Same call and return value as `metro_modifications/hand_utils.py:540` (MANO and SMPL-X-arm branches): temporal smoothing of the per-frame
     fits.  Stage 1 optimises [rot, pose, shape, cam] with Adam(1e-3) on 1e-2 * (root-relative joints vs the input's) + 1e-1 *
     (temporal smoothness of the root-relative joints) until the running loss stops falling by 1e-5 — a host decision every
     iteration, as in the reference (592-595), so the loop is driven from Python: the LBS forward / backward of each iteration
     are `harp_lbs_mano_fwd/bwd` (through `ManoLayer`'s autograd function), the joint-space losses are a few tiny torch ops on
     (T,21,3) tensors.  Stage 2 optimises cam alone (Adam 1e-3 + ReduceLROnPlateau) on anchor + smoothness of the
     camera-relative root; the joints are constant there, so no skinning is needed.  Returns CPU tensors like the reference."""
-    if use_smplx_arm or nimble_hand:
-        raise NotImplementedError("optimize_smooth_seq: only the MANO branch is built (SURVEY.md 8(f) row 4)")
+    if nimble_hand:
+        raise NotImplementedError("optimize_smooth_seq: the NIMBLE hand model needs third-party code and assets (SURVEY.md section 2)")
     dev = mano_layer.hc_coarse.device
     p = {k: torch.as_tensor(v, dtype=torch.float32).to(dev).clone() for k, v in params_cpu.items()}
     p["cam"] = p["cam"].unsqueeze(1)                                          # 547
@@ -157,7 +157,11 @@ def optimize_smooth_seq(params_cpu, mano_layer, use_smplx_arm=False, nimble_hand
     free = [p["rot"], p["pose"], p["shape"], p["cam"]]
     for q in free:
         q.requires_grad_(True)
-    skin = lambda: mano_layer(torch.cat((p["rot"], p["pose"]), 1), p["shape"], p["trans"])
+    if use_smplx_arm:  # hand_utils.py:586,620,639,663: the reference's default branch (utils/config_utils.py:7)
+        skin = lambda: mano_layer(betas=p["shape"], global_orient=p["rot"], transl=p["trans"], right_hand_pose=p["pose"],
+                                  return_type="mano", hc=mano_layer.hc_coarse)
+    else:
+        skin = lambda: mano_layer(torch.cat((p["rot"], p["pose"]), 1), p["shape"], p["trans"])
     opt = torch.optim.Adam(free, lr=1e-3)                                     # 585
     running = 999999.0
     for it in range(total_iter_pose):

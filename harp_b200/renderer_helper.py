@@ -76,14 +76,19 @@ class PhongRenderer:
     def __call__(self, meshes, **kwargs):
         _check_camera(kwargs, self.image_size)
         tex, mat = meshes.textures, kwargs.get("materials")
-        if tex is None or mat is None or not getattr(mat, "use_normal_map", False):
-            raise ValueError("phong renderer needs meshes.textures (TexturesUV) and materials with normal_maps")
+        if tex is None:
+            raise ValueError("phong renderer needs meshes.textures (TexturesUV)")
         verts = meshes.verts_padded()
         B = verts.shape[0]
+        if mat is not None and getattr(mat, "use_normal_map", False):
+            nm = mat.normal_maps.maps_padded()[:1]
+        else:  # materials without normal maps (render_360_light, utils/visualize.py:220): a constant +z map leaves the normals as they are
+            t = tex.maps_padded()  # the kernel samples both maps on one (H, W) grid
+            nm = verts.new_tensor([0.0, 0.0, 1.0]).expand(1, t.shape[-3], t.shape[-2], 3).contiguous()
         light = torch.as_tensor(self.light_posi, dtype=torch.float32, device=verts.device).reshape(-1, 3).expand(B, 3)
         amb = verts.new_zeros(1)
         rgb = ops.Shade.apply(meshes.hc, verts, meshes.verts_normals_padded(), kwargs["R"], kwargs["T"], kwargs["R"], kwargs["T"], light,
-                              amb, tex.maps_padded()[:1], mat.normal_maps.maps_padded()[:1], _scalar(kwargs["focal_length"]),
+                              amb, tex.maps_padded()[:1], nm, _scalar(kwargs["focal_length"]),
                               self.image_size, 0, self.LIGHTS)
         hit = (rgb.detach() != 1.0).any(-1, keepdim=True).to(rgb.dtype)
         return torch.cat([rgb, hit], dim=-1)

@@ -186,6 +186,11 @@ class HarpFitter:
         self.ref_verts = f32(ref_verts).view(-1, 3)
         self.uv_mask = f32(uv_mask)
         self.T = self.rot.shape[0]
+        # everything of `params` that is not optimised here (mesh_faces, faces_uvs, verts_uvs, uv_mask, init_joints, verts_rgb,
+        # wrist_pose of a frozen arm, ...) is kept so that a checkpoint written from the fitter has every key the reference's
+        # load_result / prepare_mesh / prepare_materials index (utils/visualize.py:48,85-86)
+        own = {n for n, _ in groups} | {n for n, _ in app_groups} | {"amb_ratio", "rot", "trans"}
+        self.extra_params = {k: v for k, v in params.items() if k not in own}
         self._scratch = {}
         self.last = {}
 
@@ -215,6 +220,10 @@ class HarpFitter:
         out.update(self.app.p)
         out["amb_ratio"] = self.app.p["amb_ratio"].view(())
         out["rot"], out["trans"] = self.rot, self.trans
+        if self.arm:
+            out["wrist_pose"] = self.wrist
+        for k, v in self.extra_params.items():
+            out.setdefault(k, v)
         return out
 
     def _buf(self, name, shape, zero=True):

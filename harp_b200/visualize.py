@@ -103,3 +103,32 @@ def render_360(params, fid, renderer, img_size, focal_length, mano_layer, config
         for i, f in enumerate(frames.cpu().numpy()):
             Image.fromarray(f).save(os.path.join(out_dir, ("%04d.jpg" % i) if i < 36 else ("h_%04d.jpg" % (i - 36))))
     return frames
+
+
+def render_360_light(params, fid, hand_verts, faces, textures, img_size, focal_length, save_img_dir=None, device="cuda"):
+    """Light sweep of `utils/visualize.py:199-228`: 40 renders of the posed mesh with the Phong renderer (no normal map: the
+    reference passes no materials_properties here, 220) while the point light moves along z from -5 to 5 at x = y = 1.
+    Returns the first sample's frames as uint8 (40,S,S,3) on the device; with `save_img_dir` they are also written as
+    `render_360_light/%04d.jpg` (the animated GIF is left to the caller)."""
+    from . import renderer_helper
+    cam = params["cam"][fid.to(params["cam"].device)]
+    B = fid.shape[0]
+    mesh = Meshes(hand_verts.detach(), faces, textures)
+    start, end, num = -5.0, 5.0, 40
+    frames = []
+    for idx in range(num):
+        cur_z = start + (end - start) / num * idx
+        light_positions = torch.Tensor((1.0, 1.0, cur_z)).repeat(B, 1)
+        phong_renderer, _, _ = renderer_helper.get_renderers(image_size=img_size, light_posi=light_positions, silh_sigma=1e-7,
+                                                             silh_gamma=1e-1, silh_faces_per_pixel=50, device=device)
+        img = render_image(mesh, cam, B, phong_renderer, img_size, focal_length, device=device)
+        frames.append((img.detach()[0].clip(0, 1) * 255).to(torch.uint8))
+    frames = torch.stack(frames)
+    if save_img_dir is not None:
+        import os
+        from PIL import Image
+        out_dir = os.path.join(save_img_dir, "render_360_light")
+        os.makedirs(out_dir, exist_ok=True)
+        for i, f in enumerate(frames.cpu().numpy()):
+            Image.fromarray(f).save(os.path.join(out_dir, "%04d.jpg" % i))
+    return frames

@@ -42,7 +42,7 @@ class _PlateauCompat(_Plateau):
 torch.optim.lr_scheduler.ReduceLROnPlateau = _PlateauCompat
 
 from harp_b200 import synth  # noqa: E402
-from make_golden import ref_mano_layer  # noqa: E402
+from make_golden import ref_mano_layer, ref_arm_layer  # noqa: E402
 
 
 def main():
@@ -75,5 +75,39 @@ def main():
     print("moved: pose", float((out["pose"] - pose).abs().max()), "cam", float((out["cam"] - cam).abs().max()))
 
 
+def main_arm():
+    """The reference's default branch (utils/config_utils.py:7 use_arm=True): optimize_smooth_seq(use_smplx_arm=True) on the
+    reference's own SMPLXARM layer (hand_models_harp/body_models.py, return_type='mano'), synthetic SMPL-X-format model."""
+    import hand_utils
+    torch.set_num_threads(os.cpu_count() or 1)
+    os.chdir(REF)  # body_models.py:2101 opens the arm correspondence relative to the reference root
+    tmpl = synth.load_template("arm")
+    pack = synth.make_smplx_pack(seed=0, template=tmpl)
+    layer = ref_arm_layer(pack)
+    T = 8
+    seq = synth.make_sequence(T, seed=1)
+    g = torch.Generator().manual_seed(6)
+    rot = seq["rot"] + 0.03 * torch.randn(T, 3, generator=g)
+    pose = seq["pose"] + 0.05 * torch.randn(T, 45, generator=g)
+    shape = seq["shape"][None].repeat(T, 1) + 0.1 * torch.randn(T, 10, generator=g)
+    trans = torch.tensor([[0.0, 0.0, 0.5]]).repeat(T, 1) + 0.002 * torch.randn(T, 3, generator=g)
+    cam = seq["cam"] + torch.tensor([0.3, 0.01, 0.01]) * torch.randn(T, 3, generator=g)
+    with torch.no_grad():
+        verts, joints = layer(betas=shape, global_orient=rot, transl=trans, right_hand_pose=pose, return_type="mano")
+    params_in = dict(rot=rot, pose=pose, shape=shape, trans=trans, cam=cam, joints=joints, verts=verts)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        out = hand_utils.optimize_smooth_seq({k: v.clone() for k, v in params_in.items()}, layer, use_smplx_arm=True, img_res=224,
+                                             total_iter_pose=300)
+    print(buf.getvalue()[-200:])
+    np.savez_compressed(os.path.join(HERE, "smooth_seq_arm_t8.npz"), **{"in_" + k: v.numpy() for k, v in params_in.items()},
+                        **{"out_" + k: v.numpy() for k, v in out.items()})
+    print({k: tuple(v.shape) for k, v in out.items()})
+    print("moved: pose", float((out["pose"] - pose).abs().max()), "cam", float((out["cam"] - cam).abs().max()))
+
+
 if __name__ == "__main__":
-    main()
+    if "arm" in sys.argv[1:]:
+        main_arm()
+    else:
+        main()

@@ -79,3 +79,32 @@ def test_turntable_frames_match_oracle():
         ref8 = (ref[0, ..., :3].clip(0, 1) * 255).to(torch.uint8)
         d = (frames[i].cpu().int() - ref8.int()).abs().amax(-1)
         assert float((d <= 1).double().mean()) >= 0.99, (i, float((d <= 1).double().mean()))   # hard visibility at silhouette pixels
+
+
+@pytest.mark.gpu
+def test_light_sweep_frames_match_oracle():
+    """render_360_light (utils/visualize.py:199-228): 40 Phong renders, no normal map, the light moving along z."""
+    from harp_b200 import synth, visualize
+    from harp_b200.manolayer import ManoLayer
+    from harp_b200.structures import TexturesUV
+    from util import golden_case
+    g = load_golden("c2_full_128_sub")
+    model, topo, params, batch, cfg = golden_case(g)
+    tmpl = synth.load_template("hand")
+    pack = synth.make_mano_pack(seed=0, template=tmpl)
+    layer = ManoLayer(pack, tmpl["faces_uvs"], tmpl["verts_uvs"])
+    S, focal = 64, 1000.0 * 64 / 224.0
+    vm, _ = O.mano_forward(model, torch.cat((params["rot"][:1], params["pose"][:1]), 1), params["shape"][None], params["trans"][:1])
+    verts = O.build_mesh(vm / 1000.0, topo, params["verts_disps"])
+    tex = TexturesUV(maps=params["texture"][:1].cuda(), faces_uvs=torch.tensor(tmpl["faces_uvs"]).long()[None].cuda(),
+                     verts_uvs=torch.tensor(tmpl["verts_uvs"])[None].cuda())
+    p = {"cam": params["cam"].cuda()}
+    frames = visualize.render_360_light(p, torch.arange(1), verts.cuda(), layer.hc.faces()[None], tex, S, focal, device="cuda")
+    assert frames.shape == (40, S, S, 3) and frames.dtype == torch.uint8
+    flat = torch.tensor([0.0, 0.0, 1.0]).view(1, 1, 1, 3)
+    for i in (0, 13, 39):
+        light = torch.tensor([[1.0, 1.0, -5.0 + 10.0 / 40 * i]])
+        ref = O.render_phong(verts, topo, params["cam"][:1], light, params["texture"], flat, focal, S)
+        ref8 = (ref[0, ..., :3].clip(0, 1) * 255).to(torch.uint8)
+        d = (frames[i].cpu().int() - ref8.int()).abs().amax(-1)
+        assert float((d <= 1).double().mean()) >= 0.99, (i, float((d <= 1).double().mean()))

@@ -392,19 +392,3 @@ def test_fused_step_matches_reference_golden(name):
         if k in ("texture", "normal_map"):
             frac = frac_within(mine, gg, 1e-3 * float(gg.abs().max()))
             assert frac >= 0.9995, (k, frac)
-
-
-def test_ingest_u8_matches_load_img():
-    """uint8 -> fp32 frames with the 3x3 x2 erosion of utils/data_util.py:11-30 (numpy /255 in double, cv2 border rule)."""
-    import numpy as np
-    from harp_b200 import synth
-    from harp_b200.ops import ingest_u8
-    rng = np.random.RandomState(0)
-    B, S = 2, 64
-    rgb = rng.randint(0, 256, size=(B, S, S, 3)).astype(np.uint8)
-    mask = (rng.rand(B, S, S) > 0.3).astype(np.uint8) * 255
-    mask[:, 10:20, 10:20] = rng.randint(0, 256, size=(B, 10, 10))  # grey values survive load_img un-thresholded
-    out = ingest_u8(torch.tensor(rgb).cuda(), torch.tensor(mask).cuda())
-    assert torch.equal(out["y_true"].cpu(), torch.Tensor(rgb / 255))
-    assert torch.equal(out["y_sil"].cpu(), torch.Tensor(mask / 255))
-    assert torch.equal(out["y_sil_eroded"].cpu(), synth.erode_mask(torch.Tensor(mask / 255)))

@@ -140,3 +140,47 @@ def test_smoothing_against_reference_golden():
         d = float((out[k] - torch.tensor(g["out_" + k])).abs().max())
         assert d <= t, (k, d)
     assert float((out["pose"] - pin["pose"]).abs().max()) > 0.05   # it did smooth
+
+
+# ---- the reference's default branch: optimize_smooth_seq(use_smplx_arm=True) on SMPLXARM (hand_utils.py:586,620,639,663) ----------
+def _arm_model():
+    from harp_b200 import synth
+    from util import golden_case
+    tmpl = synth.load_template("arm")
+    pack = synth.make_smplx_pack(seed=0, template=tmpl)
+    g = load_golden("c4_arm_128_sub")
+    model = golden_case(g)[0]
+    return pack, tmpl, model
+
+
+def test_oracle_arm_smoothing_matches_reference_golden():
+    g = load_golden("smooth_seq_arm_t8")
+    pin = {k[3:]: torch.tensor(g[k]) for k in g if k.startswith("in_")}
+    _, tmpl, model = _arm_model()
+    mano_idx = torch.tensor(tmpl["mano_vert_from_arm"]).long()
+
+    def fwd(p48, shape, trans):  # SMPLXARM(..., return_type='mano'): body_models.py:2387-2388
+        v, j = O.smplxarm_forward(model, shape, p48[:, :3], p48[:, 3:], torch.zeros_like(trans), trans)
+        return v[:, mano_idx], j[:, :21]
+
+    out = O.smooth_seq(model, pin, total_iter_pose=300, forward=fwd)
+    for k in ("rot", "pose", "shape", "cam", "joints", "verts"):
+        ref = torch.tensor(g["out_" + k])
+        assert float((out[k] - ref).abs().max()) <= 2e-5 * max(float(ref.abs().max()), 1.0), (k, float((out[k] - ref).abs().max()))
+
+
+@pytest.mark.gpu
+def test_arm_smoothing_against_reference_golden():
+    from harp_b200 import mano_fit
+    from harp_b200.body_models import SMPLXARM
+    g = load_golden("smooth_seq_arm_t8")
+    pin = {k[3:]: torch.tensor(g[k]) for k in g if k.startswith("in_")}
+    pack, tmpl, _ = _arm_model()
+    layer = SMPLXARM(pack, tmpl)
+    out = mano_fit.optimize_smooth_seq({k: v.clone() for k, v in pin.items()}, layer, use_smplx_arm=True, img_res=224, total_iter_pose=300)
+    assert out["verts"].shape == (8, 778, 3) and out["joints"].shape == (8, 21, 3)
+    tol = dict(rot=2e-3, pose=5e-3, shape=5e-3, cam=2e-3, trans=0.0, joints=0.15, verts=0.15)
+    for k, t in tol.items():
+        d = float((out[k] - torch.tensor(g["out_" + k])).abs().max())
+        assert d <= t, (k, d)
+    assert float((out["pose"] - pin["pose"]).abs().max()) > 0.05
