@@ -71,6 +71,7 @@ struct harp_ctx {
   int32_t *tips = nullptr, *parents = nullptr, *joint_out_src = nullptr;
   // scratch (harp_ctx_reserve)
   int maxB = 0, S = 0, tiles = 0;
+  bool defer_fold = false;        // host-side: harp_render_fused leaves d_verts4 / d_normals4 unfolded (harp_step_fused)
   int pins = 0;                   // captured CUDA graphs that hold the scratch pointers (harp_ctx_pin): no reallocation while > 0
   int64_t bin_cap = 0;            // bin list capacity per frame
   float* ndc_cam = nullptr;       // (B,V,3)

@@ -10,22 +10,7 @@
 //
 // The exchange of the shared-parameter gradients between GPUs (harp_peer_allreduce) and the optimiser update (harp_adam_dev)
 // follow on the same stream.  Loss weights, stage gating and frame scaling: optimize_sequence.py:411-422, 507-515.
-#include "common.cuh"
-
-struct GeoArgs {
-  int B, S;
-  float focal;
-  const int64_t* fid;
-  const float *pose, *rot, *trans, *cam, *wrist, *shape, *disps, *light_pos, *amb_ratio;
-  float *verts0, *joints, *verts, *normals, *vposed;
-  float *cam_T, *light_b, *light_R, *light_T, *centroid, *amb;
-  const float *d_verts, *d_normals, *d_joints;
-  const float *d_cam_T, *d_light_pos, *d_light_R, *d_light_T, *d_amb;
-  float *g_pose, *g_cam, *g_rot, *g_wrist, *g_shape, *g_disps, *g_light, *g_amb;
-  float *d_rot, *d_trans, *d_wrist;
-};
-int harp_geo_fwd(harp_ctx* c, const GeoArgs& a, cudaStream_t st);
-int harp_geo_bwd(harp_ctx* c, const GeoArgs& a, cudaStream_t st);
+#include "geom.cuh"
 
 namespace {
 
@@ -133,7 +118,11 @@ extern "C" int harp_step_fused(harp_ctx* c, const harp_step_args* p, void* strea
   r.grads.d_verts = w.d_verts; r.grads.d_normals = w.d_normals; r.grads.d_cam_R = nullptr; r.grads.d_cam_T = w.d_cam_T;
   r.grads.d_light_R = w.d_light_R; r.grads.d_light_T = w.d_light_T; r.grads.d_light_pos = w.d_light_pos; r.grads.d_amb = w.d_amb;
   r.grads.d_texture = p->g_texture; r.grads.d_normal_map = p->g_normal_map;
-  if ((rc = harp_render_fused(c, B, S, p->focal, &r, st)) != HARP_OK) return rc;
+  c->defer_fold = true;  // the padded per-vertex accumulators of the shading backward are folded inside geo_bwd
+  rc = harp_render_fused(c, B, S, p->focal, &r, st);
+  c->defer_fold = false;
+  if (rc != HARP_OK) return rc;
+  if (app_on) { g.d_verts4 = c->d_verts4; g.d_normals4 = c->d_normals4; }
   HARP_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_reg_join, 0));
   return harp_geo_bwd(c, g, st);
 }

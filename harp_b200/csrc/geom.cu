@@ -10,25 +10,10 @@
 // a dozen ATen gathers / scatters, each a few microseconds of work behind tens of microseconds of dependent-launch latency.
 #include <algorithm>
 
+#include "geom.cuh"
 #include "glue.cuh"
 #include "lbs.cuh"
 #include "mesh.cuh"
-
-struct GeoArgs {
-  int B, S;
-  float focal;
-  const int64_t* fid;
-  const float *pose, *rot, *trans, *cam, *wrist, *shape, *disps, *light_pos, *amb_ratio;  // parameter tables / shared parameters
-  // forward outputs
-  float *verts0, *joints, *verts, *normals, *vposed;  // vposed: (B,V0,3) blend-shaped rest vertices, kept for the backward
-  float *cam_T, *light_b, *light_R, *light_T, *centroid, *amb;  // (B,3) (B,3) (B,9) (B,3) (B,3) (1)
-  // backward inputs
-  const float *d_verts, *d_normals, *d_joints;
-  const float *d_cam_T, *d_light_pos, *d_light_R, *d_light_T, *d_amb;  // (B,3) (B,3) (B,9) (B,3) (1)
-  // backward outputs (accumulated with atomics; rows of the tables by fid)
-  float *g_pose, *g_cam, *g_rot, *g_wrist, *g_shape, *g_disps, *g_light, *g_amb;
-  float *d_rot, *d_trans, *d_wrist;  // (B,3) per minibatch frame, overwritten (nullable)
-};
 
 namespace {
 
@@ -167,13 +152,21 @@ __global__ void __launch_bounds__(GEO_THREADS) geo_bwd_kernel(harp_ctx c, GeoArg
   __syncthreads();
   DirectAccessor fin{Bf};
   const float* dng = a.d_normals + (size_t)b * V * 3;
-  for (int v = t; v < V; v += GEO_THREADS)
-    st3(C + (size_t)v * 3, normalize_bwd(vertex_normal_sum(c, fin, v), ld3(dng + (size_t)v * 3), 1e-6f));
+  const float4* dn4 = a.d_normals4 ? reinterpret_cast<const float4*>(a.d_normals4) + (size_t)b * V : nullptr;
+  for (int v = t; v < V; v += GEO_THREADS) {
+    f3 dn = ld3(dng + (size_t)v * 3);
+    if (dn4) { float4 q = dn4[v]; dn = dn + mk3(q.x, q.y, q.z); }
+    st3(C + (size_t)v * 3, normalize_bwd(vertex_normal_sum(c, fin, v), dn, 1e-6f));
+  }
   __syncthreads();
   const float* dvg = a.d_verts + (size_t)b * V * 3;
   const f3 gcv = mk3(gc[0], gc[1], gc[2]);
-  for (int v = t; v < V; v += GEO_THREADS)
-    st3(A + (size_t)v * 3, ld3(dvg + (size_t)v * 3) + gcv + normal_grad_gather(c, fin, C, v));
+  const float4* dv4 = a.d_verts4 ? reinterpret_cast<const float4*>(a.d_verts4) + (size_t)b * V : nullptr;
+  for (int v = t; v < V; v += GEO_THREADS) {
+    f3 dv = ld3(dvg + (size_t)v * 3) + gcv;
+    if (dv4) { float4 q = dv4[v]; dv = dv + mk3(q.x, q.y, q.z); }
+    st3(A + (size_t)v * 3, dv + normal_grad_gather(c, fin, C, v));
+  }
   __syncthreads();
   if (a.disps) {
     for (int v = t; v < V; v += GEO_THREADS) st3(Bf + (size_t)v * 3, sub(v));

@@ -6,13 +6,14 @@
 #include "shade_pixel.cuh"
 
 int harp_raster_setup(harp_ctx* c, int view, int B, int S, float focal, float radius, const float* verts, const float* R,
-                      const float* T, cudaStream_t st);
+                      const float* T, cudaStream_t st, bool zero_grads = false);
 int harp_project_bwd(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R, const float* T,
                      const float* d_ndc, float* d_verts, float* d_R, float* d_T, cudaStream_t st);
 int harp_fold4(size_t n, const float* src4, float* dst3, cudaStream_t st);
 int harp_tex_prepare(harp_ctx* c, const float* texture, const float* normal_map, int texH, int texW, cudaStream_t st);
 int harp_light_depth(harp_ctx* c, int B, int S, cudaStream_t st);
-int harp_light_depth_tiles(harp_ctx* c, int B, int S, cudaStream_t st);
+int harp_light_depth_tiles(harp_ctx* c, int B, int S, bool zero_grad, cudaStream_t st);
+int harp_light_depth_bwd_tiles(harp_ctx* c, int B, int S, cudaStream_t st);
 int harp_light_depth_bwd(harp_ctx* c, int B, int S, cudaStream_t st);
 int harp_sil_topk(harp_ctx* c, int mode, int S, int K, float sigma, float blur, float radius, float* alpha, const float* gin,
                   float gscale, float inv_n, float* loss, cudaStream_t st);
@@ -70,15 +71,16 @@ struct VisArgs {
   float* sil_loss;
   float* d_ndc;
   // visibility
-  int32_t *hit_list, *hit_count;  // hit_list: (B, S*S) int2 records (row*S+col, face id)
+  int32_t *hit_list, *hit_count;  // hit_list: (B, S*S) int2 records (row << 16 | col, face id)
   // background pixels of the colour image
   float* rgb;
   const float *y_true, *y_mask;
   float photo_inv_n;
   float* photo_loss;
-  // light view (MODE_LIGHT): nearest depth / face id
+  // light view (MODE_LIGHT): nearest depth / face id, and the zero fill of the depth-gradient image on non-empty tiles
   float* zbuf;
   int32_t* face;
+  float* d_zbuf;
 };
 
 struct __align__(16) BandEntry {
@@ -396,6 +398,7 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
       }
       a.zbuf[pix] = z;
       a.face[pix] = fo;
+      if (a.d_zbuf) a.d_zbuf[pix] = 0.f;  // the gradient image is only ever touched on tiles some face covers
     } else {
       {  // per-frame compacted hit list (warp-aggregated append)
         unsigned mask = __ballot_sync(0xffffffffu, hit);
@@ -403,7 +406,7 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
         if (mask) {
           if (lane == 0) hb = atomicAdd(a.hit_count + b, __popc(mask));
           hb = __shfl_sync(0xffffffffu, hb, 0);
-          if (hit) reinterpret_cast<int2*>(a.hit_list)[(size_t)b * S * S + hb + __popc(mask & ((1u << lane) - 1u))] = make_int2(row * S + col, best_fid);
+          if (hit) reinterpret_cast<int2*>(a.hit_list)[(size_t)b * S * S + hb + __popc(mask & ((1u << lane) - 1u))] = make_int2((row << 16) | col, best_fid);
         }
       }
       float photo_abs = 0.f;
@@ -532,7 +535,7 @@ __global__ void __launch_bounds__(128, HARP_SHADE_MIN_CTAS) shade_deferred_kerne
   const int S = a.S;
   int b = blockIdx.y;
   int n = hit_count[b];
-  const float* ndc = a.ndc_cam + (size_t)b * c.V * 3;
+  const FaceTile* frec = c.face_rec + (size_t)b * c.F;  // camera view
   const int2* list = hit_list + (size_t)b * S * S;
   // per-thread partial sums of the frame scalars live in shared memory (column per thread: conflict-free), not registers
   __shared__ float s_fr[9][128];
@@ -540,22 +543,28 @@ __global__ void __launch_bounds__(128, HARP_SHADE_MIN_CTAS) shade_deferred_kerne
   for (int k = 0; k < 9; ++k) s_fr[k][threadIdx.x] = 0.f;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
     int2 rec = list[idx];
-    int rc = rec.x;
-    int row = rc / S, col = rc % S;
-    size_t pix = (size_t)b * S * S + rc;
+    const int row = rec.x >> 16, col = rec.x & 0xffff;
+    size_t pix = ((size_t)b * S + row) * S + col;
     float px = pix_to_ndc(col, S), py = pix_to_ndc(row, S);
     Hit h;
     h.fid = rec.y;
+    // the face's raster record (one contiguous 144-byte row written by the setup kernel) and its vertex ids are requested
+    // together: one dependent hop less than face table -> three projected vertices
+    const float4* r4 = reinterpret_cast<const float4*>(frec + h.fid);
+    const int32_t* fv = c.faces + (size_t)h.fid * 3;
+    float4 r0 = __ldg(r4), r1 = __ldg(r4 + 1), r2 = __ldg(r4 + 2), r7 = __ldg(r4 + 7);
+    const int v0 = fv[0], v1 = fv[1], v2 = fv[2];
     FaceRec f;
-    load_face(c, ndc, h.fid, 0.f, f);
+    f.x0 = r0.x; f.y0 = r0.y; f.x1 = r0.z; f.y1 = r0.w; f.x2 = r1.x; f.y2 = r1.y; f.area = r2.w; f.z0 = r7.x; f.z1 = r7.y; f.z2 = r7.z;
     ShadePre pre;  // vertex attributes, uvs and targets: in flight while the barycentrics are evaluated
-    shade_preload<MODE>(c, a, b, pix, h.fid, f.v0, f.v1, f.v2, pre);
+    shade_preload<MODE>(c, a, b, pix, h.fid, v0, v1, v2, pre);
     PairEval e;
     eval_pair_full<false, false>(f, px, py, 0.f, e);
     if (e.pass) { h.pz = e.pz; h.b0 = e.b0; h.b1 = e.b1; h.b2 = e.b2; h.w0 = e.w0; h.w1 = e.w1; h.w2 = e.w2; }
     else h.fid = -1;  // the exact test disagrees with the fast classification on a boundary pixel: background
+    const Tri2 tri{f.x0, f.y0, f.z0, f.x1, f.y1, f.z1, f.x2, f.y2, f.z2};
     ShadeOut o;
-    shade_pixel<MODE>(c, a, b, pix, px, py, h, o, &pre);
+    shade_pixel<MODE>(c, a, b, pix, px, py, h, o, &pre, &tri);
     if (MODE != 1) st3(a.rgb + pix * 3, o.rgb);
     if (MODE != 0) {
       s_fr[8][threadIdx.x] += o.loss_abs;
@@ -606,12 +615,10 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
   cudaStream_t ss = c->side_stream;
   HARP_CHECK_CUDA(cudaEventRecord(c->ev_fork, st));
   harp_prof_begin(c, 6, st);
-  if ((rc = harp_raster_setup(c, 0, B, S, focal, radius, r->verts, r->cam_R, r->cam_T, st)) != HARP_OK) return rc;
+  // (the setup kernels also zero the projected-vertex gradient accumulator, the hit counters and the top-K counter)
+  if ((rc = harp_raster_setup(c, 0, B, S, focal, radius, r->verts, r->cam_R, r->cam_T, st, true)) != HARP_OK) return rc;
   HARP_CHECK_CUDA(cudaEventRecord(c->ev_bins, st));
-  if (sil_bwd || photo_bwd) HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_cam, 0, nv4, st));
   harp_prof_end(c, 6, st);
-  HARP_CHECK_CUDA(cudaMemsetAsync(c->hit_count, 0, (size_t)B * sizeof(int32_t), st));
-  HARP_CHECK_CUDA(cudaMemsetAsync(c->ovf_count, 0, sizeof(int32_t), st));
   VisArgs v{};
   v.S = S; v.K = r->faces_per_pixel > 0 ? r->faces_per_pixel : 50; v.sigma = r->sigma; v.blur = blur; v.radius = radius; v.ndc = c->ndc_cam;
   v.rec = c->face_rec; v.bin_list = c->bin_list; v.work = c->work; v.work_ctl = c->work_ctl; v.work_cap = c->maxB * c->tiles;
@@ -636,18 +643,14 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
   // empty tiles, which overlaps the issue-bound tile rasteriser.  Event fork / join is capturable into a CUDA graph.
   HARP_CHECK_CUDA(cudaStreamWaitEvent(ss, c->ev_fork, 0));
   if (r->self_shadow) {
-    if ((rc = harp_raster_setup(c, 1, B, S, focal, 0.f, r->verts, r->light_R, r->light_T, ss)) != HARP_OK) return rc;
-    if ((rc = harp_light_depth_tiles(c, B, S, ss)) != HARP_OK) return rc;
+    if ((rc = harp_raster_setup(c, 1, B, S, focal, 0.f, r->verts, r->light_R, r->light_T, ss, photo_bwd)) != HARP_OK) return rc;
+    if ((rc = harp_light_depth_tiles(c, B, S, photo_bwd, ss)) != HARP_OK) return rc;
   }
   if ((rc = harp_tex_prepare(c, r->texture, r->normal_map, r->texH, r->texW, ss)) != HARP_OK) return rc;
   if (photo_bwd) {
     HARP_CHECK_CUDA(cudaMemsetAsync(c->d_verts4, 0, nv4, ss));
     HARP_CHECK_CUDA(cudaMemsetAsync(c->d_normals4, 0, nv4, ss));
     HARP_CHECK_CUDA(cudaMemsetAsync(c->d_tex4, 0, 2 * ntex * 4 * sizeof(float), ss));
-    if (r->self_shadow) {
-      HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_light, 0, nv4, ss));
-      HARP_CHECK_CUDA(cudaMemsetAsync(c->d_light_zbuf, 0, npx * sizeof(float), ss));
-    }
   }
   {
     HARP_CHECK_CUDA(cudaStreamWaitEvent(ss, c->ev_bins, 0));
@@ -681,12 +684,14 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
   HARP_LAUNCH_CHECK();
   harp_prof_begin(c, 7, st);
   if (photo_bwd) {
-    if ((rc = harp_fold4((size_t)B * c->V, c->d_verts4, r->grads.d_verts, st)) != HARP_OK) return rc;
-    if ((rc = harp_fold4((size_t)B * c->V, c->d_normals4, r->grads.d_normals, st)) != HARP_OK) return rc;
+    if (!c->defer_fold) {  // harp_step_fused folds the padded vertex accumulators inside its geometry backward
+      if ((rc = harp_fold4((size_t)B * c->V, c->d_verts4, r->grads.d_verts, st)) != HARP_OK) return rc;
+      if ((rc = harp_fold4((size_t)B * c->V, c->d_normals4, r->grads.d_normals, st)) != HARP_OK) return rc;
+    }
     if (r->grads.d_texture && (rc = harp_fold4(ntex, c->d_tex4, r->grads.d_texture, st)) != HARP_OK) return rc;
     if (r->grads.d_normal_map && (rc = harp_fold4(ntex, c->d_tex4 + ntex * 4, r->grads.d_normal_map, st)) != HARP_OK) return rc;
     if (r->self_shadow) {
-      if ((rc = harp_light_depth_bwd(c, B, S, st)) != HARP_OK) return rc;
+      if ((rc = harp_light_depth_bwd_tiles(c, B, S, st)) != HARP_OK) return rc;
       if ((rc = harp_project_bwd(c, B, S, focal, r->verts, r->light_R, r->light_T, c->d_ndc_light, r->grads.d_verts,
                                  r->grads.d_light_R, r->grads.d_light_T, st)) != HARP_OK) return rc;
     }
@@ -699,8 +704,69 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
   return HARP_OK;
 }
 
+// backward of the light-view depth buffer (zbuf = sum_i b_i z_i at the stored face) over the non-empty light tiles only: the
+// PCF taps of the shading can only have touched pixels of tiles some face covers.  Four tiles per CTA round; the pixels with a
+// gradient are compacted in shared memory and then processed by full warps.
+__global__ void __launch_bounds__(256) light_depth_bwd_tiles_kernel(harp_ctx c, int S, const int4* __restrict__ work, const int32_t* __restrict__ ctl,
+                                                                    int work_cap, const FaceTile* __restrict__ rec_all,
+                                                                    const int32_t* __restrict__ face, const float* __restrict__ d_zbuf,
+                                                                    float* __restrict__ d_ndc_all) {
+  __shared__ int s_pix[256];
+  __shared__ float s_g[256];
+  __shared__ int s_n;
+  const int n_heavy = ctl[0], total = n_heavy + ctl[1], tw = S / HARP_TILE, t = threadIdx.x;
+  for (int i0 = blockIdx.x * 4; i0 < total; i0 += gridDim.x * 4) {
+    if (t == 0) s_n = 0;
+    __syncthreads();
+    int i = i0 + (t >> 6);
+    if (i < total) {
+      int4 it = work[i < n_heavy ? i : work_cap - 1 - (i - n_heavy)];
+      int lx = t & 7, ly = (t >> 3) & 7;
+      int row = (it.y / tw) * HARP_TILE + ly, col = (it.y % tw) * HARP_TILE + lx;
+      int pix = (it.x * S + row) * S + col;
+      float g = d_zbuf[pix];
+      if (g != 0.f) { int s = atomicAdd(&s_n, 1); s_pix[s] = pix; s_g[s] = g; }
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (t < n) {
+      int pix = s_pix[t];
+      int fid = face[pix];
+      if (fid >= 0) {
+        float g = s_g[t];
+        int b = pix / (S * S), rem = pix % (S * S), row = rem / S, col = rem % S;
+        float px = pix_to_ndc(col, S), py = pix_to_ndc(row, S);
+        const float4* r4 = reinterpret_cast<const float4*>(rec_all + (size_t)b * c.F + fid);
+        float4 r0 = __ldg(r4), r1 = __ldg(r4 + 1), r2 = __ldg(r4 + 2), r7 = __ldg(r4 + 7);
+        FaceRec f;
+        f.x0 = r0.x; f.y0 = r0.y; f.x1 = r0.z; f.y1 = r0.w; f.x2 = r1.x; f.y2 = r1.y; f.area = r2.w; f.z0 = r7.x; f.z1 = r7.y; f.z2 = r7.z;
+        PairEval e;
+        eval_pair_full<false, false>(f, px, py, 0.f, e);
+        if (e.pass) {
+          const int32_t* fv = c.faces + (size_t)fid * 3;
+          Hit h; h.fid = fid; h.pz = e.pz; h.b0 = e.b0; h.b1 = e.b1; h.b2 = e.b2; h.w0 = e.w0; h.w1 = e.w1; h.w2 = e.w2;
+          float gb[3] = {g * f.z0, g * f.z1, g * f.z2};
+          float gz[3] = {g * e.b0, g * e.b1, g * e.b2};
+          bary_backward(Tri2{f.x0, f.y0, f.z0, f.x1, f.y1, f.z1, f.x2, f.y2, f.z2}, fv[0], fv[1], fv[2], px, py, h, gb, gz,
+                        d_ndc_all + (size_t)b * c.V * 4);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int harp_light_depth_bwd_tiles(harp_ctx* c, int B, int S, cudaStream_t st) {
+  (void)B;
+  const int cap = c->maxB * c->tiles;
+  light_depth_bwd_tiles_kernel<<<HARP_SM_COUNT * 4, 256, 0, st>>>(*c, S, c->work + cap, c->work_ctl + 4, cap, c->face_rec + (size_t)c->maxB * c->F,
+                                                               c->light_face, c->d_light_zbuf, c->d_ndc_light);
+  HARP_LAUNCH_CHECK();
+  return HARP_OK;
+}
+
 // Light-view nearest depth + face id with the persistent tile rasteriser (setup of view 1 must be current).
-int harp_light_depth_tiles(harp_ctx* c, int B, int S, cudaStream_t st) {
+int harp_light_depth_tiles(harp_ctx* c, int B, int S, bool zero_grad, cudaStream_t st) {
   VisArgs v{};
   v.S = S; v.K = 1; v.sigma = 0.f; v.blur = 0.f; v.radius = 0.f; v.ndc = c->ndc_light;
   v.rec = c->face_rec + (size_t)c->maxB * c->F;
@@ -708,7 +774,7 @@ int harp_light_depth_tiles(harp_ctx* c, int B, int S, cudaStream_t st) {
   v.work_cap = c->maxB * c->tiles;
   v.work = c->work + v.work_cap;
   v.work_ctl = c->work_ctl + 4;
-  v.zbuf = c->light_zbuf; v.face = c->light_face;
+  v.zbuf = c->light_zbuf; v.face = c->light_face; v.d_zbuf = zero_grad ? c->d_light_zbuf : nullptr;
   tile_raster_kernel<false, false, false><<<HARP_SM_COUNT * HARP_PV_MINCTAS, NT, 0, st>>>(*c, v);
   const int eg = (int)(((size_t)B * S * (S / 4) + 255) / 256);
   empty_tiles_kernel<true, false, false><<<eg, 256, 0, st>>>(B, S, c->bin_count + (size_t)c->maxB * c->tiles, v);

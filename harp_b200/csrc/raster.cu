@@ -5,7 +5,7 @@
 #include "raster.cuh"
 
 int harp_raster_setup(harp_ctx* c, int view, int B, int S, float focal, float radius, const float* verts, const float* R,
-                      const float* T, cudaStream_t st);
+                      const float* T, cudaStream_t st, bool zero_grads = false);
 
 namespace {
 

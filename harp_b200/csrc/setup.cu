@@ -86,6 +86,9 @@ struct SetupArgs {
   int4* work;                   // (B*tiles) out: heavy items from the front, light from the back
   int32_t* work_ctl;            // {heavy, light, cursor, -}
   int work_cap;
+  // optional zero fills folded into these kernels (saves their memset nodes on the step's critical path)
+  float* zero_d_ndc;            // (B,V,4) projected-vertex gradient accumulator of this view
+  int32_t *zero_hit_count, *zero_ovf_count;  // (B), (1)
 };
 
 // approximate NDC of a pixel centre (the conservative tile test has a 1e-5 NDC guard; the exact value is pix_to_ndc)
@@ -115,6 +118,7 @@ __global__ void __launch_bounds__(256) face_setup_kernel(harp_ctx c, SetupArgs a
     float o[3];
     project(f, o);
     st3(a.ndc + ((size_t)b * c.V + f) * 3, mk3(o[0], o[1], o[2]));
+    if (a.zero_d_ndc) reinterpret_cast<float4*>(a.zero_d_ndc)[(size_t)b * c.V + f] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (f >= c.F) return;
   const int32_t* fv = c.faces + (size_t)f * 3;
@@ -162,6 +166,10 @@ __global__ void __launch_bounds__(SETUP_THREADS) bin_scan_kernel(harp_ctx c, Set
   __shared__ int s_wsum[32], s_wne[32], s_whv[32];
   __shared__ int s_base_heavy, s_base_light;
   const int b = blockIdx.x, t = threadIdx.x, tiles = a.tiles, lane = t & 31, w = t >> 5;
+  if (t == 0) {
+    if (a.zero_hit_count) a.zero_hit_count[b] = 0;
+    if (a.zero_ovf_count && b == 0) a.zero_ovf_count[0] = 0;
+  }
   const int32_t* gcount = a.bin_count + (size_t)b * tiles;
   int32_t* gstart = a.bin_start + (size_t)b * tiles;
   int32_t* gcur = a.bin_cursor + (size_t)b * tiles;
@@ -255,7 +263,7 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(harp_ctx c, SetupArgs a) 
 
 // Project `verts` with (R, T) and build everything the tile kernels of one view consume (0 = camera, 1 = light).
 int harp_raster_setup(harp_ctx* c, int view, int B, int S, float focal, float radius, const float* verts, const float* R,
-                      const float* T, cudaStream_t st) {
+                      const float* T, cudaStream_t st, bool zero_grads) {
   HARP_REQUIRE(S / HARP_TILE <= 255, HARP_ERR_CAPACITY, "harp_raster_setup: images up to 2040 x 2040");
   const size_t voff = (size_t)view * c->maxB * c->tiles;
   SetupArgs a{};
@@ -267,8 +275,13 @@ int harp_raster_setup(harp_ctx* c, int view, int B, int S, float focal, float ra
   a.work_cap = c->maxB * c->tiles;
   a.work = c->work + (size_t)view * a.work_cap;
   a.work_ctl = c->work_ctl + view * 4;
-  HARP_CHECK_CUDA(cudaMemsetAsync(a.bin_count, 0, (size_t)B * c->tiles * sizeof(int32_t), st));
+  if (zero_grads) {
+    a.zero_d_ndc = view == 0 ? c->d_ndc_cam : c->d_ndc_light;
+    if (view == 0) { a.zero_hit_count = c->hit_count; a.zero_ovf_count = c->ovf_count; }
+  }
+  // one zero fill for the tile counters and the view's queue control words (allocated back to back: ctx.cu)
   HARP_CHECK_CUDA(cudaMemsetAsync(a.work_ctl, 0, 4 * sizeof(int32_t), st));
+  HARP_CHECK_CUDA(cudaMemsetAsync(a.bin_count, 0, (size_t)B * c->tiles * sizeof(int32_t), st));
   const int n = std::max(c->F, c->V);
   face_setup_kernel<<<(int)(((size_t)B * n + 255) / 256), 256, 0, st>>>(*c, a);
   bin_scan_kernel<<<B, SETUP_THREADS, 0, st>>>(*c, a);

@@ -7,7 +7,7 @@
 #include "shade_pixel.cuh"
 
 int harp_raster_setup(harp_ctx* c, int view, int B, int S, float focal, float radius, const float* verts, const float* R,
-                      const float* T, cudaStream_t st);
+                      const float* T, cudaStream_t st, bool zero_grads = false);
 int harp_project_bwd(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R, const float* T,
                      const float* d_ndc, float* d_verts, float* d_R, float* d_T, cudaStream_t st);
 int harp_fold4(size_t n, const float* src4, float* dst3, cudaStream_t st);
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(LDB_THREADS) light_depth_bwd_kernel(harp_ctx c
     Hit h; h.fid = fid; h.pz = e.pz; h.b0 = e.b0; h.b1 = e.b1; h.b2 = e.b2; h.w0 = e.w0; h.w1 = e.w1; h.w2 = e.w2;
     float gb[3] = {g * f.z0, g * f.z1, g * f.z2};
     float gz[3] = {g * e.b0, g * e.b1, g * e.b2};
-    bary_backward(ndc, f.v0, f.v1, f.v2, px, py, h, gb, gz, d_ndc_all + (size_t)b * c.V * 4);
+    bary_backward(tri_from_ndc(ndc, f.v0, f.v1, f.v2), f.v0, f.v1, f.v2, px, py, h, gb, gz, d_ndc_all + (size_t)b * c.V * 4);
   }
 }
 

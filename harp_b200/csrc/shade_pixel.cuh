@@ -27,10 +27,17 @@ struct Hit {
 
 // ---- barycentric backward: grads of the perspective-correct barycentrics -> NDC xy and view z of the 3 face verts ------
 // b_i = t_i / sum(t), t_0 = w0 z1 z2 ..., w_i = e_i / A  (BarycentricPerspectiveCorrection / BarycentricCoords backward)
-__device__ __forceinline__ void bary_backward(const float* ndc, int v0, int v1, int v2, float px, float py, const Hit& h,
-                                              const float gb[3], float gz_direct[3], float* d_ndc) {
+struct Tri2 {  // projected triangle: NDC xy and view z of the three vertices
+  float x0, y0, z0, x1, y1, z1, x2, y2, z2;
+};
+__device__ __forceinline__ Tri2 tri_from_ndc(const float* ndc, int v0, int v1, int v2) {
   const float *A0 = ndc + (size_t)v0 * 3, *A1 = ndc + (size_t)v1 * 3, *A2 = ndc + (size_t)v2 * 3;
-  float x0 = A0[0], y0 = A0[1], z0 = A0[2], x1 = A1[0], y1 = A1[1], z1 = A1[2], x2 = A2[0], y2 = A2[1], z2 = A2[2];
+  return Tri2{A0[0], A0[1], A0[2], A1[0], A1[1], A1[2], A2[0], A2[1], A2[2]};
+}
+
+__device__ __forceinline__ void bary_backward(const Tri2& t, int v0, int v1, int v2, float px, float py, const Hit& h,
+                                              const float gb[3], float gz_direct[3], float* d_ndc) {
+  float x0 = t.x0, y0 = t.y0, z0 = t.z0, x1 = t.x1, y1 = t.y1, z1 = t.z1, x2 = t.x2, y2 = t.y2, z2 = t.z2;
   float den = h.w0 * z1 * z2 + z0 * h.w1 * z2 + z0 * z1 * h.w2;
   float gz0 = gz_direct[0], gz1 = gz_direct[1], gz2 = gz_direct[2];
   float gw0 = 0.f, gw1 = 0.f, gw2 = 0.f;
@@ -150,7 +157,7 @@ __device__ __forceinline__ void shade_flush_frame_scalars(const ShadeArgs& a, in
 // MODE 0 forward; 1 backward with upstream g_rgb; 2 fused photometric L1 on the eroded mask.
 template <int MODE>
 __device__ __forceinline__ void shade_pixel(const harp_ctx& c, const ShadeArgs& a, int b, size_t pix, float px, float py,
-                                            const Hit& h, ShadeOut& o, const ShadePre* pre = nullptr) {
+                                            const Hit& h, ShadeOut& o, const ShadePre* pre = nullptr, const Tri2* tri = nullptr) {
   const int S = a.S;
   const float* ndc = a.ndc_cam + (size_t)b * c.V * 3;
   f3 rgb = mk3(1.f, 1.f, 1.f);  // background (renderer_helper.py:430)
@@ -349,7 +356,7 @@ __device__ __forceinline__ void shade_pixel(const harp_ctx& c, const ShadeArgs& 
     atomic_add4(dnb + (size_t)v1 * 4, h.b1 * gN.x, h.b1 * gN.y, h.b1 * gN.z);
     atomic_add4(dnb + (size_t)v2 * 4, h.b2 * gN.x, h.b2 * gN.y, h.b2 * gN.z);
     float gz[3] = {0.f, 0.f, 0.f};
-    bary_backward(ndc, v0, v1, v2, px, py, h, gb, gz, a.d_ndc_cam + (size_t)b * c.V * 4);
+    bary_backward(tri ? *tri : tri_from_ndc(ndc, v0, v1, v2), v0, v1, v2, px, py, h, gb, gz, a.d_ndc_cam + (size_t)b * c.V * 4);
   }
   o.active = active;
   o.frame[0] = r_light[0]; o.frame[1] = r_light[1]; o.frame[2] = r_light[2]; o.frame[3] = r_amb;
