@@ -8,6 +8,8 @@
 // SubdivideMeshes, verts_normals, displacement), the camera of render_image (visualize.py:266-270), process_info_for_shadow
 // (renderer_helper.py:454-468), sigmoid(amb_ratio) and their autograd graph — formerly 5 + 9 launches of this package plus
 // a dozen ATen gathers / scatters, each a few microseconds of work behind tens of microseconds of dependent-launch latency.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 
 #include "geom.cuh"
@@ -17,8 +19,11 @@
 
 namespace {
 
+namespace cg = cooperative_groups;
+
 constexpr int GEO_THREADS = LBS_THREADS;
 constexpr int POSE_PAD = MAXJ * 3;
+constexpr int PART_PAD = (MAXJ * 12 + MAXPB + MAXS + 3 + 3) & ~3;  // one CTA's block of partial LBS sums
 
 __host__ __device__ inline size_t words(size_t bytes) { return (bytes + 3) / 4; }
 
@@ -32,6 +37,20 @@ __device__ __forceinline__ float assemble_pose(const harp_ctx& c, const GeoArgs&
   return 0.f;
 }
 
+// A frame is shared by a thread-block CLUSTER of 1, 2 or 4 CTAs (picked so that B x cluster fills the 148 SMs): every CTA keeps
+// complete copies of the frame's vertex arrays in its own shared memory, computes a quarter / half / all of each phase's
+// vertices and writes its results into every CTA's copy through distributed shared memory; a cluster barrier separates the
+// phases.  (One CTA per frame left 84 of 148 SMs idle at 64 frames and made the step's cost constant below that.)
+struct Cluster {
+  cg::cluster_group g;
+  int rank, n;
+  __device__ Cluster() : g(cg::this_cluster()) { rank = (int)g.block_rank(); n = (int)g.num_blocks(); }
+  __device__ __forceinline__ void st3_all(float* local, f3 v) const {
+    for (int r = 0; r < n; ++r) st3(g.map_shared_rank(local, r), v);
+  }
+  __device__ __forceinline__ void sync() const { g.sync(); }
+};
+
 __global__ void __launch_bounds__(GEO_THREADS) geo_fwd_kernel(harp_ctx c, GeoArgs a) {
   extern __shared__ float dyn[];
   LbsShared& s = *reinterpret_cast<LbsShared*>(dyn);
@@ -40,39 +59,66 @@ __global__ void __launch_bounds__(GEO_THREADS) geo_fwd_kernel(harp_ctx c, GeoArg
   float* vs = v0s + (size_t)c.V0 * 3;      // (V,3) final vertices
   float* vsub = vs + (size_t)c.V * 3;      // (V,3) subdivided, undisplaced vertices
   __shared__ float red[32];
-  const int b = blockIdx.x, t = threadIdx.x, J = c.J;
+  __shared__ float s_csum[4][3];           // centroid partial sums of the cluster's CTAs (rank 0's copy is used)
+  const Cluster cl;
+  const int b = blockIdx.x / cl.n, t = threadIdx.x, J = c.J;
   const int64_t row = a.fid ? a.fid[b] : b;
   for (int i = t; i < J * 3; i += GEO_THREADS) s_pose[i] = assemble_pose(c, a, row, i);
   __syncthreads();
-  lbs_prologue(c, s_pose, a.shape, s);
-  lbs_forward_core(c, s, ld3(a.trans + row * 3), v0s, a.verts0 + (size_t)b * c.V0 * 3, a.joints + (size_t)b * c.n_joints_out * 3,
-                   a.vposed ? a.vposed + (size_t)b * c.V0 * 3 : nullptr);
-  __syncthreads();
-  // SubdivideMeshes (materialised once in shared memory: the gathers below touch every vertex ~12 times) + displacement
-  // along the normals of the undisplaced mesh (utils/visualize.py:48-60)
+  lbs_prologue(c, s_pose, a.shape, s);  // (every CTA of the cluster: a few hundred flops)
+  // ---- LBS: vertices rank, rank + n, ... (interleaved by thread block) -> every CTA's v0s, and HBM
+  {
+    f3 off = ld3(a.trans + row * 3);
+    if (c.center_joint >= 0)  // wrist-centring of SMPLXARM (body_models.py:2342-2343)
+      off = off - mk3(s.G[c.center_joint][3], s.G[c.center_joint][7], s.G[c.center_joint][11]);
+    float* v0g = a.verts0 + (size_t)b * c.V0 * 3;
+    float* vpg = a.vposed ? a.vposed + (size_t)b * c.V0 * 3 : nullptr;
+    for (int v = cl.rank * GEO_THREADS + t; v < c.V0; v += GEO_THREADS * cl.n) {
+      f3 vp = lbs_v_posed(c, s, v);
+      if (vpg) st3(vpg + (size_t)v * 3, vp);  // kept for the backward (saves its pass over the pose blendshapes)
+      float T[12];
+      lbs_blend(c, s, v, T);
+      f3 o = mk3(T[0] * vp.x + T[1] * vp.y + T[2] * vp.z + T[3], T[4] * vp.x + T[5] * vp.y + T[6] * vp.z + T[7],
+                 T[8] * vp.x + T[9] * vp.y + T[10] * vp.z + T[11]) + off;
+      cl.st3_all(v0s + (size_t)v * 3, o);
+      st3(v0g + (size_t)v * 3, o);
+    }
+    cl.sync();
+    if (cl.rank == 0 && t < c.n_joints_out) {
+      int src = c.joint_out_src[t];
+      f3 p = src < J ? mk3(s.G[src][3], s.G[src][7], s.G[src][11]) + off : ld3(v0s + (size_t)c.tips[src - J] * 3);
+      st3(a.joints + ((size_t)b * c.n_joints_out + t) * 3, p);
+    }
+  }
+  // ---- SubdivideMeshes (materialised once in shared memory, by every CTA for itself: two smem reads per vertex) +
+  //      displacement along the normals of the undisplaced mesh (utils/visualize.py:48-60)
   SubdivAccessor sub{v0s, c.edges0, c.V0};
   for (int v = t; v < c.V; v += GEO_THREADS) st3(vsub + (size_t)v * 3, sub(v));
   __syncthreads();
   DirectAccessor und{vsub};
   float* vg = a.verts + (size_t)b * c.V * 3;
-  for (int v = t; v < c.V; v += GEO_THREADS) {
+  for (int v = cl.rank * GEO_THREADS + t; v < c.V; v += GEO_THREADS * cl.n) {
     f3 p = und(v);
     if (a.disps) p = p + a.disps[v] * normalize_eps(vertex_normal_sum(c, und, v), 1e-6f);
-    st3(vs + (size_t)v * 3, p);
+    cl.st3_all(vs + (size_t)v * 3, p);
     st3(vg + (size_t)v * 3, p);
   }
-  __syncthreads();
+  cl.sync();
   DirectAccessor fin{vs};
   float* ng = a.normals + (size_t)b * c.V * 3;
   float sx = 0.f, sy = 0.f, sz = 0.f;
-  for (int v = t; v < c.V; v += GEO_THREADS) {
+  for (int v = cl.rank * GEO_THREADS + t; v < c.V; v += GEO_THREADS * cl.n) {
     st3(ng + (size_t)v * 3, normalize_eps(vertex_normal_sum(c, fin, v), 1e-6f));
     f3 p = fin(v);
     sx += p.x; sy += p.y; sz += p.z;
   }
   sx = block_sum(sx, red); sy = block_sum(sy, red); sz = block_sum(sz, red);
-  if (t != 0) return;
+  if (t == 0) st3(cl.g.map_shared_rank(&s_csum[cl.rank][0], 0), mk3(sx, sy, sz));
+  cl.sync();
+  if (cl.rank != 0 || t != 0) return;
   // camera / light glue (as frame_glue_fwd_kernel, glue.cu)
+  sx = sy = sz = 0.f;
+  for (int r = 0; r < cl.n; ++r) { sx += s_csum[r][0]; sy += s_csum[r][1]; sz += s_csum[r][2]; }
   float ctr[3] = {sx / (float)c.V, sy / (float)c.V, sz / (float)c.V};
   const float* cam = a.cam + row * 3;
   a.cam_T[b * 3 + 0] = -cam[1];
@@ -91,21 +137,23 @@ __global__ void __launch_bounds__(GEO_THREADS) geo_bwd_kernel(harp_ctx c, GeoArg
   LbsBwdShared& g = *reinterpret_cast<LbsBwdShared*>(dyn + words(sizeof(LbsShared)));
   float* s_pose = dyn + words(sizeof(LbsShared)) + words(sizeof(LbsBwdShared));
   float* s_out = s_pose + POSE_PAD;        // d_pose (J*3) | d_shape (n_shape) | d_trans (3)
-  float* v0s = s_out + POSE_PAD + MAXS + 4;  // (V0,3)
+  float* s_part = s_out + POSE_PAD + MAXS + 4;  // the cluster's partial LBS sums (rank 0's copy is used): 4 x PART_PAD
+  float* v0s = s_part + 4 * PART_PAD;      // (V0,3)
   float* dv0 = v0s + (size_t)c.V0 * 3;     // (V0,3) gradient w.r.t. the skinned coarse vertices
   float* A = dv0 + (size_t)c.V0 * 3;       // three (V,3) arrays, later the LBS backward's scratch
   float* Bf = A + (size_t)c.V * 3;
   float* C = Bf + (size_t)c.V * 3;
   __shared__ float gc[3];
-  const int b = blockIdx.x, t = threadIdx.x, J = c.J, NS = c.n_shape, V = c.V;
+  const Cluster cl;
+  const int b = blockIdx.x / cl.n, t = threadIdx.x, J = c.J, NS = c.n_shape, V = c.V;
   const int64_t row = a.fid ? a.fid[b] : b;
   for (int i = t; i < J * 3; i += GEO_THREADS) s_pose[i] = assemble_pose(c, a, row, i);
   const float* v0g = a.verts0 + (size_t)b * c.V0 * 3;
   for (int i = t; i < c.V0 * 3; i += GEO_THREADS) v0s[i] = v0g[i];
   __syncthreads();
   lbs_prologue(c, s_pose, a.shape, s);
-  // ---- camera / light glue backward (as frame_glue_bwd_kernel, glue.cu)
-  if (t == 0) {
+  // ---- camera / light glue backward (as frame_glue_bwd_kernel, glue.cu): rank 0, result (the centroid's gradient) to everyone
+  if (cl.rank == 0 && t == 0) {
     const float* cam = a.cam + row * 3;
     const float* dct = a.d_cam_T + (size_t)b * 3;
     float den = (float)a.S * cam[0] + 1e-9f;
@@ -126,65 +174,66 @@ __global__ void __launch_bounds__(GEO_THREADS) geo_bwd_kernel(harp_ctx c, GeoArg
     }
     if (a.g_light)
       for (int i = 0; i < 3; ++i) atomicAdd(a.g_light + i, gg[i] + a.d_light_pos[b * 3 + i]);  // share_light_position: row 0
-    for (int i = 0; i < 3; ++i) gc[i] = gg[3 + i] / (float)V;
+    cl.st3_all(gc, mk3(gg[3] / (float)V, gg[4] / (float)V, gg[5] / (float)V));
     if (b == 0 && a.g_amb) {
       float sg = 1.f / (1.f + expf(-a.amb_ratio[0]));
       atomicAdd(a.g_amb, a.d_amb[0] * sg * (1.f - sg));
     }
   }
   // Three (V,3) arrays in shared memory, re-used as the phases go (every gather reads materialised vertices: computing the
-  // edge midpoints on the fly inside the gathers was a third of this kernel's instructions):
-  //   P1  A = subdivided vertices;  Bf = final (displaced) vertices
-  //   P2  C = dN = normalize_bwd(N(final), d_normals)
-  //   P3  A = g1 = d_verts + centroid gradient + gather(dN over final)
-  //   P4  Bf = subdivided vertices again;  C = dNs = normalize_bwd(N(subdivided), disp * g1);  d_disps += n_s . g1
-  //   P5  A += gather(dNs over subdivided)            (in place: a thread rewrites only its own row)
-  //   P6  dv0 = subdivision backward of A
+  // edge midpoints on the fly inside the gathers was a third of this kernel's instructions).  "split" phases are shared by the
+  // cluster's CTAs (results written to every CTA's copy), "local" ones are cheap enough for every CTA to do for itself:
+  //   P1  local  A = subdivided vertices;   split  Bf = final (displaced) vertices
+  //   P2  split  C = dN = normalize_bwd(N(final), d_normals)
+  //   P3  split  A = g1 = d_verts + centroid gradient + gather(dN over final)
+  //   P4  local  Bf = subdivided vertices again;   split  C = dNs = normalize_bwd(N(subdivided), disp * g1);  d_disps += n_s . g1
+  //   P5  split  A += gather(dNs over subdivided)     (in place: only the owner of a row reads it in this phase)
+  //   P6  local  dv0 = subdivision backward of A
+  const int vfirst = cl.rank * GEO_THREADS + t, vstep = GEO_THREADS * cl.n;
   SubdivAccessor sub{v0s, c.edges0, c.V0};
   for (int v = t; v < V; v += GEO_THREADS) st3(A + (size_t)v * 3, sub(v));
   __syncthreads();
   DirectAccessor undA{A};
-  for (int v = t; v < V; v += GEO_THREADS) {
+  for (int v = vfirst; v < V; v += vstep) {
     f3 p = undA(v);
     if (a.disps) p = p + a.disps[v] * normalize_eps(vertex_normal_sum(c, undA, v), 1e-6f);
-    st3(Bf + (size_t)v * 3, p);
+    cl.st3_all(Bf + (size_t)v * 3, p);
   }
-  __syncthreads();
+  cl.sync();
   DirectAccessor fin{Bf};
   const float* dng = a.d_normals + (size_t)b * V * 3;
   const float4* dn4 = a.d_normals4 ? reinterpret_cast<const float4*>(a.d_normals4) + (size_t)b * V : nullptr;
-  for (int v = t; v < V; v += GEO_THREADS) {
+  for (int v = vfirst; v < V; v += vstep) {
     f3 dn = ld3(dng + (size_t)v * 3);
     if (dn4) { float4 q = dn4[v]; dn = dn + mk3(q.x, q.y, q.z); }
-    st3(C + (size_t)v * 3, normalize_bwd(vertex_normal_sum(c, fin, v), dn, 1e-6f));
+    cl.st3_all(C + (size_t)v * 3, normalize_bwd(vertex_normal_sum(c, fin, v), dn, 1e-6f));
   }
-  __syncthreads();
+  cl.sync();
   const float* dvg = a.d_verts + (size_t)b * V * 3;
   const f3 gcv = mk3(gc[0], gc[1], gc[2]);
   const float4* dv4 = a.d_verts4 ? reinterpret_cast<const float4*>(a.d_verts4) + (size_t)b * V : nullptr;
-  for (int v = t; v < V; v += GEO_THREADS) {
+  for (int v = vfirst; v < V; v += vstep) {
     f3 dv = ld3(dvg + (size_t)v * 3) + gcv;
     if (dv4) { float4 q = dv4[v]; dv = dv + mk3(q.x, q.y, q.z); }
-    st3(A + (size_t)v * 3, dv + normal_grad_gather(c, fin, C, v));
+    cl.st3_all(A + (size_t)v * 3, dv + normal_grad_gather(c, fin, C, v));
   }
-  __syncthreads();
+  cl.sync();
   if (a.disps) {
     for (int v = t; v < V; v += GEO_THREADS) st3(Bf + (size_t)v * 3, sub(v));
     __syncthreads();
     DirectAccessor undB{Bf};
-    for (int v = t; v < V; v += GEO_THREADS) {
+    for (int v = vfirst; v < V; v += vstep) {
       f3 N = vertex_normal_sum(c, undB, v);
       f3 gv = ld3(A + (size_t)v * 3);
       if (a.g_disps) atomicAdd(a.g_disps + v, dot(normalize_eps(N, 1e-6f), gv));
-      st3(C + (size_t)v * 3, normalize_bwd(N, a.disps[v] * gv, 1e-6f));
+      cl.st3_all(C + (size_t)v * 3, normalize_bwd(N, a.disps[v] * gv, 1e-6f));
     }
-    __syncthreads();
-    for (int v = t; v < V; v += GEO_THREADS)
-      st3(A + (size_t)v * 3, ld3(A + (size_t)v * 3) + normal_grad_gather(c, undB, C, v));
-    __syncthreads();
+    cl.sync();
+    for (int v = vfirst; v < V; v += vstep)
+      cl.st3_all(A + (size_t)v * 3, ld3(A + (size_t)v * 3) + normal_grad_gather(c, undB, C, v));
+    cl.sync();
   }
   const float* g2 = A;
-  // ---- P6: subdivision backward: d verts0[v] = g[v] + 0.5 * sum over incident coarse edges
   for (int v = t; v < c.V0; v += GEO_THREADS) {
     f3 acc = ld3(g2 + (size_t)v * 3);
     if (c.subdivide)
@@ -192,10 +241,19 @@ __global__ void __launch_bounds__(GEO_THREADS) geo_bwd_kernel(harp_ctx c, GeoArg
     st3(dv0 + (size_t)v * 3, acc);
   }
   __syncthreads();
-  // ---- LBS backward (scratch: the three vertex arrays are dead)
+  // ---- LBS backward: every CTA accumulates over its contiguous (even-aligned) range of coarse vertices into rank 0's block of
+  //      partial sums; rank 0 finishes.  Scratch: the three vertex arrays are dead.
   (void)scratch_floats;
-  lbs_backward_core(c, s, g, A, A + (size_t)c.V0 * 3, dv0, a.d_joints ? a.d_joints + (size_t)b * c.n_joints_out * 3 : nullptr, s_out,
-                    s_out + POSE_PAD, s_out + POSE_PAD + MAXS, a.vposed ? a.vposed + (size_t)b * c.V0 * 3 : nullptr);
+  const float* dj = a.d_joints ? a.d_joints + (size_t)b * c.n_joints_out * 3 : nullptr;
+  {
+    const int per = ((c.V0 + cl.n - 1) / cl.n + 1) & ~1;
+    const int vb = min(c.V0, cl.rank * per), ve = min(c.V0, vb + per);
+    float* part0 = cl.g.map_shared_rank(s_part, 0) + (size_t)cl.rank * PART_PAD;
+    lbs_backward_accumulate(c, s, g.red, A, A + (size_t)c.V0 * 3, dv0, dj, a.vposed ? a.vposed + (size_t)b * c.V0 * 3 : nullptr, vb, ve, part0);
+  }
+  cl.sync();
+  if (cl.rank != 0) return;
+  lbs_backward_finish(c, s, g, A + (size_t)c.V0 * 3, s_part, cl.n, PART_PAD, dj, s_out, s_out + POSE_PAD, s_out + POSE_PAD + MAXS);
   __syncthreads();
   // ---- scatter into the parameter-table gradients
   if (J == 16) {
@@ -220,7 +278,22 @@ __global__ void __launch_bounds__(GEO_THREADS) geo_bwd_kernel(harp_ctx c, GeoArg
 size_t geo_fwd_smem(const harp_ctx* c) { return (words(sizeof(LbsShared)) + POSE_PAD + (size_t)c->V0 * 3 + (size_t)c->V * 6) * 4; }
 size_t geo_bwd_scratch(const harp_ctx* c) { return std::max((size_t)c->V * 9, (size_t)c->V0 * 3 + lbs_bwd_scratch_floats(c)); }
 size_t geo_bwd_smem(const harp_ctx* c) {
-  return (words(sizeof(LbsShared)) + words(sizeof(LbsBwdShared)) + 2 * POSE_PAD + MAXS + 4 + (size_t)c->V0 * 6 + geo_bwd_scratch(c)) * 4;
+  return (words(sizeof(LbsShared)) + words(sizeof(LbsBwdShared)) + 2 * POSE_PAD + MAXS + 4 + 4 * PART_PAD + (size_t)c->V0 * 6 + geo_bwd_scratch(c)) * 4;
+}
+
+// cluster size: the largest of 4, 2, 1 with B x size <= #SMs
+int geo_cluster(int B) { return B * 4 <= HARP_SM_COUNT ? 4 : (B * 2 <= HARP_SM_COUNT ? 2 : 1); }
+
+template <typename... Args>
+int launch_clustered(void (*kernel)(Args...), int B, int cl, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(B * cl); cfg.blockDim = dim3(GEO_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  HARP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
+  return HARP_OK;
 }
 
 int configure(const void* fn, size_t bytes, size_t* configured) {
@@ -242,7 +315,7 @@ int harp_geo_fwd(harp_ctx* c, const GeoArgs& a, cudaStream_t st) {
   int rc = configure((const void*)geo_fwd_kernel, geo_fwd_smem(c), configured);
   if (rc != HARP_OK) return rc;
   harp_prof_begin(c, 2, st);
-  geo_fwd_kernel<<<a.B, GEO_THREADS, geo_fwd_smem(c), st>>>(*c, a);
+  if ((rc = launch_clustered(geo_fwd_kernel, a.B, geo_cluster(a.B), geo_fwd_smem(c), st, *c, a)) != HARP_OK) return rc;
   harp_prof_end(c, 2, st);
   HARP_LAUNCH_CHECK();
   return HARP_OK;
@@ -253,7 +326,7 @@ int harp_geo_bwd(harp_ctx* c, const GeoArgs& a, cudaStream_t st) {
   int rc = configure((const void*)geo_bwd_kernel, geo_bwd_smem(c), configured);
   if (rc != HARP_OK) return rc;
   harp_prof_begin(c, 3, st);
-  geo_bwd_kernel<<<a.B, GEO_THREADS, geo_bwd_smem(c), st>>>(*c, a, (int)geo_bwd_scratch(c));
+  if ((rc = launch_clustered(geo_bwd_kernel, a.B, geo_cluster(a.B), geo_bwd_smem(c), st, *c, a, (int)geo_bwd_scratch(c))) != HARP_OK) return rc;
   harp_prof_end(c, 3, st);
   HARP_LAUNCH_CHECK();
   return HARP_OK;

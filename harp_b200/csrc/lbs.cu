@@ -37,10 +37,7 @@ __global__ void __launch_bounds__(LBS_THREADS) lbs_bwd_kernel(harp_ctx c, const 
 }
 
 size_t lbs_bwd_smem(const harp_ctx* c) {
-  size_t words = (sizeof(LbsShared) + 3) / 4 + (sizeof(LbsBwdShared) + 3) / 4 + (size_t)c->V0 * 15;
-  size_t need_dg = (size_t)MAXJ * 12;  // dG accumulators alias dTs
-  if ((size_t)c->V0 * 12 < need_dg) words += need_dg;
-  return words * sizeof(float);
+  return ((sizeof(LbsShared) + 3) / 4 + (sizeof(LbsBwdShared) + 3) / 4 + lbs_bwd_scratch_floats(c)) * sizeof(float);
 }
 
 }  // namespace

@@ -170,23 +170,24 @@ struct LbsBwdShared {
   float red[32];
 };
 
-// Backward of one frame's LBS by the whole CTA, after lbs_prologue.  gv: (V0,3) gradient w.r.t. the skinned vertices; dj:
-// (n_joints_out,3) gradient w.r.t. the output joints or null; dvp (V0*3) and dTs (12*V0) are scratch; outputs are this
-// frame's d_pose (J*3), d_shape (n_shape), d_trans (3, optional).  All pointers may be shared or global memory.
-__device__ __forceinline__ void lbs_backward_core(const harp_ctx& c, LbsShared& s, LbsBwdShared& g, float* dvp, float* dTs, const float* gv,
-                                                  const float* dj, float* d_pose, float* d_shape, float* d_trans,
-                                                  const float* vposed = nullptr) {
+// Backward of one frame's LBS, after lbs_prologue, in two parts so that several CTAs (a thread-block cluster) can share a frame:
+//
+//   lbs_backward_accumulate  over the vertices [vb, ve): d v_posed and dT = g (x) [v_posed; 1] per vertex, then the contractions
+//                            against the skinning weights and the blendshape tables restricted to that range ->
+//                            PARTIAL sums  out = [dA (J*12) | d pose_map ((J-1)*9) | d beta (n_shape) | sum of g (3)]
+//   lbs_backward_finish      sums the partial results of all ranges, then the reverse-mode pass through the kinematic chain,
+//                            the Rodrigues Jacobians and the joint regressor -> d_pose (J*3), d_shape (n_shape), d_trans (3)
+//
+// gv: (V0,3) gradient w.r.t. the skinned vertices; dj: (n_joints_out,3) gradient w.r.t. the output joints or null; dvp (V0*3)
+// and dTs (12*V0) are scratch indexed by the global vertex id.  All pointers may be shared or global memory.
+__host__ __device__ inline int lbs_partial_floats(int J, int NS) { return J * 12 + (J - 1) * 9 + NS + 3; }
+
+__device__ __forceinline__ void lbs_backward_accumulate(const harp_ctx& c, const LbsShared& s, float* red, float* dvp, float* dTs,
+                                                        const float* gv, const float* dj, const float* vposed, int vb, int ve,
+                                                        float* out) {
   const int t = threadIdx.x, J = c.J, NS = c.n_shape, NP = (J - 1) * 9, NJO = c.n_joints_out;
-  if (t < J * 3) (&g.djtr[0][0])[t] = 0.f;
-  __syncthreads();
-  if (t < NJO && dj) {
-    int src = c.joint_out_src[t];
-    if (src < J)
-      for (int k = 0; k < 3; ++k) atomicAdd(&g.djtr[src][k], dj[t * 3 + k]);  // (a chain joint may be listed twice)
-  }
-  __syncthreads();
   f3 tsum = mk3(0.f, 0.f, 0.f);
-  for (int v = t; v < c.V0; v += blockDim.x) {
+  for (int v = vb + t; v < ve; v += blockDim.x) {
     f3 gg = ld3(gv + (size_t)v * 3);
     if (dj) {
       for (int k = 0; k < c.n_tips; ++k)
@@ -208,17 +209,10 @@ __device__ __forceinline__ void lbs_backward_core(const harp_ctx& c, LbsShared& 
 #pragma unroll
     for (int k = 0; k < 12; ++k) dTs[k * c.V0 + v] = dT[k];
   }
-  // total translation gradient = sum_v g_v + sum of chain-joint grads (vertex-joints were folded into g_v)
-  float tx = block_sum(tsum.x, g.red), ty = block_sum(tsum.y, g.red), tz = block_sum(tsum.z, g.red);
+  float tx = block_sum(tsum.x, red), ty = block_sum(tsum.y, red), tz = block_sum(tsum.z, red);  // (block_sum synchronises)
   __syncthreads();
-  if (t == 0) {
-    for (int j = 0; j < J; ++j) { tx += g.djtr[j][0]; ty += g.djtr[j][1]; tz += g.djtr[j][2]; }
-    if (d_trans) { d_trans[0] = tx; d_trans[1] = ty; d_trans[2] = tz; }
-    if (c.center_joint >= 0) {  // every output was shifted by -G[center].t
-      g.djtr[c.center_joint][0] -= tx; g.djtr[c.center_joint][1] -= ty; g.djtr[c.center_joint][2] -= tz;
-    }
-  }
-  int warp = t >> 5, lane = t & 31, nw = blockDim.x >> 5, n3 = c.V0 * 3;
+  if (t == 0) { out[J * 12 + NP + NS] = tx; out[J * 12 + NP + NS + 1] = ty; out[J * 12 + NP + NS + 2] = tz; }
+  const int warp = t >> 5, lane = t & 31, nw = blockDim.x >> 5, n3 = c.V0 * 3;
   // dA (J x 12) = W^T (J x V0) . dT (V0 x 12): one warp per output, lanes over vertices (no shared-memory float atomics
   // in the hot loop: those compile to CAS spin loops)
   for (int o = warp; o < J * 12; o += nw) {
@@ -227,16 +221,17 @@ __device__ __forceinline__ void lbs_backward_core(const harp_ctx& c, LbsShared& 
     const float* drow = dTs + k * c.V0;
     float a = 0.f;
 #pragma unroll 8
-    for (int v = lane; v < c.V0; v += 32) a += __ldg(wrow + v) * drow[v];  // unrolled: eight table loads in flight per lane
+    for (int v = vb + lane; v < ve; v += 32) a += __ldg(wrow + v) * drow[v];  // unrolled: eight table loads in flight per lane
     a = warp_sum(a);
-    if (lane == 0) g.dA[j][k] = a;
+    if (lane == 0) out[o] = a;
   }
   // d pose_map and the direct d shape: transposed-table mat-vec, one warp per group of five outputs (145 = 29 x 5: one round
   // for MANO), 8-byte loads, four iterations unrolled: 20 table loads in flight per lane — the loop is bound by the L2
   // latency of the 1.3 MB blendshape table, not by arithmetic
   {
     constexpr int RW = 5;
-    const int n2 = n3 >> 1;
+    const int ib = 3 * vb, ie = 3 * ve;
+    const bool vec2 = ((n3 | ib | ie) & 1) == 0 && (reinterpret_cast<size_t>(dvp) & 7) == 0;  // rows and range 8-byte aligned
     const float2* d2 = reinterpret_cast<const float2*>(dvp);
     for (int o0 = warp * RW; o0 < NP + NS; o0 += nw * RW) {
       const float* row[RW];
@@ -247,9 +242,9 @@ __device__ __forceinline__ void lbs_backward_core(const harp_ctx& c, LbsShared& 
         row[r] = o < NP ? c.posedirs + (size_t)o * n3 : c.shapedirs + (size_t)(o - NP) * n3;
         a[r] = 0.f;
       }
-      if ((n3 & 1) == 0 && (reinterpret_cast<size_t>(dvp) & 7) == 0) {  // rows start 8-byte aligned when 3 V0 is even (MANO 2334, arm 3078)
+      if (vec2) {
 #pragma unroll 4
-        for (int i = lane; i < n2; i += 32) {
+        for (int i = (ib >> 1) + lane; i < (ie >> 1); i += 32) {
           float2 d = d2[i];
 #pragma unroll
           for (int r = 0; r < RW; ++r) {
@@ -258,7 +253,7 @@ __device__ __forceinline__ void lbs_backward_core(const harp_ctx& c, LbsShared& 
           }
         }
       } else {
-        for (int i = lane; i < n3; i += 32) {
+        for (int i = ib + lane; i < ie; i += 32) {
           float d = dvp[i];
 #pragma unroll
           for (int r = 0; r < RW; ++r) a[r] += row[r][i] * d;
@@ -268,8 +263,43 @@ __device__ __forceinline__ void lbs_backward_core(const harp_ctx& c, LbsShared& 
       for (int r = 0; r < RW; ++r) {
         float v = warp_sum(a[r]);
         int o = o0 + r;
-        if (lane == 0 && o < NP + NS) { if (o < NP) g.dpm[o] = v; else g.dbeta[o - NP] = v; }
+        if (lane == 0 && o < NP + NS) out[J * 12 + o] = v;
       }
+    }
+  }
+}
+
+// parts: `nparts` partial-result blocks of `stride` floats each (lbs_backward_accumulate); dTs: scratch of >= MAXJ*12 floats
+__device__ __forceinline__ void lbs_backward_finish(const harp_ctx& c, LbsShared& s, LbsBwdShared& g, float* dTs, const float* parts,
+                                                    int nparts, int stride, const float* dj, float* d_pose, float* d_shape,
+                                                    float* d_trans) {
+  const int t = threadIdx.x, J = c.J, NS = c.n_shape, NP = (J - 1) * 9, NJO = c.n_joints_out;
+  if (t < J * 3) (&g.djtr[0][0])[t] = 0.f;
+  __syncthreads();
+  if (t < NJO && dj) {
+    int src = c.joint_out_src[t];
+    if (src < J)
+      for (int k = 0; k < 3; ++k) atomicAdd(&g.djtr[src][k], dj[t * 3 + k]);  // (a chain joint may be listed twice)
+  }
+  for (int i = t; i < J * 12 + NP + NS; i += blockDim.x) {
+    float a = 0.f;
+    for (int r = 0; r < nparts; ++r) a += parts[(size_t)r * stride + i];
+    if (i < J * 12) g.dA[i / 12][i % 12] = a;
+    else if (i < J * 12 + NP) g.dpm[i - J * 12] = a;
+    else g.dbeta[i - J * 12 - NP] = a;
+  }
+  __syncthreads();
+  if (t == 0) {
+    // total translation gradient = sum_v g_v + sum of chain-joint grads (vertex-joints were folded into g_v)
+    float tx = 0.f, ty = 0.f, tz = 0.f;
+    for (int r = 0; r < nparts; ++r) {
+      const float* q = parts + (size_t)r * stride + J * 12 + NP + NS;
+      tx += q[0]; ty += q[1]; tz += q[2];
+    }
+    for (int j = 0; j < J; ++j) { tx += g.djtr[j][0]; ty += g.djtr[j][1]; tz += g.djtr[j][2]; }
+    if (d_trans) { d_trans[0] = tx; d_trans[1] = ty; d_trans[2] = tz; }
+    if (c.center_joint >= 0) {  // every output was shifted by -G[center].t
+      g.djtr[c.center_joint][0] -= tx; g.djtr[c.center_joint][1] -= ty; g.djtr[c.center_joint][2] -= tz;
     }
   }
   __syncthreads();
@@ -339,11 +369,21 @@ __device__ __forceinline__ void lbs_backward_core(const harp_ctx& c, LbsShared& 
   }
 }
 
+// One CTA, all vertices (the stand-alone kernel): accumulate into the scratch's tail, then finish.
+__device__ __forceinline__ void lbs_backward_core(const harp_ctx& c, LbsShared& s, LbsBwdShared& g, float* dvp, float* dTs, const float* gv,
+                                                  const float* dj, float* d_pose, float* d_shape, float* d_trans,
+                                                  const float* vposed = nullptr) {
+  float* part = dTs + (size_t)12 * c.V0 + (c.V0 * 12 < MAXJ * 12 ? MAXJ * 12 : 0);
+  lbs_backward_accumulate(c, s, g.red, dvp, dTs, gv, dj, vposed, 0, c.V0, part);
+  __syncthreads();
+  lbs_backward_finish(c, s, g, dTs, part, 1, 0, dj, d_pose, d_shape, d_trans);
+}
+
 inline size_t lbs_bwd_scratch_floats(const harp_ctx* c) {
   size_t words = (size_t)c->V0 * 15;
   size_t need_dg = (size_t)MAXJ * 12;  // dG accumulators alias dTs
   if ((size_t)c->V0 * 12 < need_dg) words += need_dg;
-  return words;
+  return words + (size_t)lbs_partial_floats(c->J, c->n_shape);  // + one block of partial sums behind dTs
 }
 
 }  // namespace
