@@ -30,12 +30,12 @@ def arap_loss(meshes, ref_meshes, target_length: float = 0.0):
 def kps_loss(gt_kps, pred_kps, use_arm=False, device="cuda"):
     """loss/kps_loss.py:4-17: gt in mm, pred in m, root-aligned, (mm/100)^2."""
     B, nj = pred_kps.shape[0], pred_kps.shape[1]
-    from .structures import _CONTEXTS
-    # the kps term needs no topology, only a context whose joint count matches the layout of `pred_kps`
+    from .structures import any_context
+    # the kps term needs no topology, only a context on the same device whose joint count matches the layout of `pred_kps`
     # (21 for MANO; 22 for the arm, of which the kernel compares the first 21 — loss/kps_loss.py:7-8)
-    hc = next((c for c in _CONTEXTS.values() if max(c.n_joints_out, 21) == nj), None)
+    hc = any_context(pred_kps.device, nj)
     if hc is None:
-        raise ValueError(f"kps_loss: no registered context produces {nj} joints")
+        raise ValueError(f"kps_loss: no registered context on {pred_kps.device} produces {nj} joints")
     dummy = torch.zeros(B, hc.V, 3, device=pred_kps.device)
     return ops.MeshLosses.apply(hc, dummy, None, pred_kps, gt_kps.to(pred_kps.device), None)[3]
 

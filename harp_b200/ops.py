@@ -413,6 +413,26 @@ def ingest_u8(rgb_u8, mask_u8, out=None):
 
 
 @torch.no_grad()
+def render_forward(hc, verts, normals, cam_R, cam_T, light_R, light_T, light_pos, amb, texture, normal_map, focal, S, self_shadow=1,
+                   faces_per_pixel=50, sigma=1e-7):
+    """Both renders of the loop body, forward only, through the fused pixel pass (`harp_render_fused` with zero loss weights:
+    raster setup, persistent tile rasteriser, light view, deferred shading) -> (alpha (B,S,S), rgb (B,S,S,3)).
+    What `optimize_sequence.py:469-488` computes per minibatch, without the two K-fragment tensors; BASELINE.json configs[4]."""
+    ts = [_c(t) for t in (verts, normals, cam_R, cam_T, light_R, light_T, light_pos, amb.view(1), texture, normal_map)]
+    verts, normals, cam_R, cam_T, light_R, light_T, light_pos, amb1, tex, nm = ts
+    B = verts.shape[0]
+    hc.reserve(B, S)
+    alpha = torch.empty(B, S, S, device=verts.device)
+    rgb = torch.empty(B, S, S, 3, device=verts.device)
+    ra = _lib.HarpRenderArgs(verts=ptr(verts), normals=ptr(normals), cam_R=ptr(cam_R), cam_T=ptr(cam_T), light_R=ptr(light_R),
+                             light_T=ptr(light_T), light_pos=ptr(light_pos), amb=ptr(amb1), texture=ptr(tex), normal_map=ptr(nm),
+                             texH=tex.shape[-3], texW=tex.shape[-2], self_shadow=int(self_shadow), faces_per_pixel=int(faces_per_pixel),
+                             sigma=float(sigma), w_sil=0.0, w_photo=0.0, alpha=ptr(alpha), rgb=ptr(rgb))
+    check(_lib.lib().harp_render_fused(hc.h, B, int(S), float(focal), C.byref(ra), stream()))
+    return alpha, rgb
+
+
+@torch.no_grad()
 def render_normals(hc, verts, normals, R, T, focal, S, normal_map=None, faces_per_pixel=10):
     """Evaluation-pass normal render (SoftPhongNormalShader, renderer_helper.py:216-301), forward only -> (B,S,S,3)."""
     verts, normals, R, T = _c(verts), _c(normals), _c(R), _c(T)

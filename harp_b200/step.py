@@ -381,6 +381,12 @@ class HarpFitter:
     def loss_dict(self):
         """One device->host read of the loss vector (the reference does >= 10 `.cpu()` syncs per iteration, 556-561)."""
         vals = self.losses.detach().cpu().tolist()
+        cnt = self.hc.counters()  # this call already synchronises: check the only two conditions that make results inexact
+        if cnt["bin_overflow"] or cnt["sil_k_overflow_pixels"]:
+            import warnings
+            warnings.warn(f"harp_b200: results are not exact for this framing: {cnt} (a hand zoomed far past the image, or faces "
+                          "crossing the camera plane, overflowed the tile lists / the exact top-K path; see DESIGN.md section 2)")
+        self.last_counters = cnt
         d = dict(zip(LOSS_NAMES, vals))
         d["total"] = sum(LOSS_WEIGHTS[k] * v for k, v in d.items())
         return d

@@ -8,24 +8,45 @@ import torch
 from . import ops
 
 _CONTEXTS = {}
+_VERIFIED = set()
 
 
 def register_context(hc):
     """Make a `HarpContext` discoverable by mesh size, so `Meshes(verts, faces)` built by user code finds its tables."""
-    _CONTEXTS[(hc.V, hc.F, str(hc.device))] = hc
+    _CONTEXTS.setdefault((hc.V, hc.F, str(hc.device)), []).append(hc)
     return hc
 
 
 def context_for(verts, faces, textures=None):
+    """The registered context whose face table EQUALS `faces` (same counts are not enough: another mesh with as many vertices
+    and faces must not get this one's edges and UV tables).  The comparison runs once per (context, faces tensor)."""
     V, F = verts.shape[-2], faces.shape[-2]
-    key = (V, F, str(verts.device))
-    hc = _CONTEXTS.get(key)
-    if hc is None:  # unknown topology: build tables from the faces as given (no subdivision, no skinning model)
-        f = faces[0] if faces.dim() == 3 else faces
-        fu = textures.faces_uvs_first().cpu().numpy() if textures is not None else None
-        vu = textures.verts_uvs_first().cpu().numpy() if textures is not None else None
-        hc = register_context(ops.HarpContext(f.cpu().numpy(), subdivide=False, faces_uvs=fu, verts_uvs=vu, device=verts.device))
-    return hc
+    f = faces[0] if faces.dim() == 3 else faces
+    cands = [hc for (v_, f_, _), lst in _CONTEXTS.items() if (v_, f_) == (V, F) for hc in lst
+             if hc.device.type == verts.device.type and (hc.device.index or 0) == (verts.device.index or 0)]
+    for hc in cands:
+        tag = (id(hc), f.data_ptr(), f._version)
+        if tag in _VERIFIED:
+            return hc
+        if torch.equal(hc.faces(), f.to(hc.faces().device).long()):
+            _VERIFIED.add(tag)
+            return hc
+    # unknown topology: build tables from the faces as given (no subdivision, no skinning model)
+    fu = textures.faces_uvs_first().cpu().numpy() if textures is not None else None
+    vu = textures.verts_uvs_first().cpu().numpy() if textures is not None else None
+    return register_context(ops.HarpContext(f.cpu().numpy(), subdivide=False, faces_uvs=fu, verts_uvs=vu, device=verts.device))
+
+
+def any_context(device, n_joints=None):
+    """A context on `device` for work that needs no topology (the keypoint term): optionally one whose skinning model emits
+    `n_joints` joints."""
+    want = torch.device(device)
+    same = lambda a, b: a.type == b.type and (a.index or 0) == (b.index or 0)  # 'cuda' is 'cuda:0' unless a device was selected
+    for lst in _CONTEXTS.values():
+        for hc in lst:
+            if same(hc.device, want) and (n_joints is None or max(hc.n_joints_out, 21) == n_joints):
+                return hc
+    return None
 
 
 class TexturesUV:

@@ -17,7 +17,9 @@ def prepare_mesh(params, fid, mano_layer, verts_textures, mesh_subdivider, globa
     B = fid.shape[0]
     fid = fid.to(params["pose"].device)
     betas = params["shape"].to(device)
-    hc = mano_layer.hc if mesh_subdivider is not None else mano_layer.hc_coarse
+    disps = params.get("verts_disps")
+    # utils/visualize.py:49-64: the mesh is subdivided only inside the `verts_disps is not None` branch
+    hc = mano_layer.hc if (mesh_subdivider is not None and disps is not None) else mano_layer.hc_coarse
     if use_arm:  # visualize.py:36-40
         full_pose = mano_layer.assemble_full_pose(params["rot"][fid].to(device), params["pose"][fid].to(device),
                                                   params["wrist_pose"][fid].to(device))
@@ -25,7 +27,6 @@ def prepare_mesh(params, fid, mano_layer, verts_textures, mesh_subdivider, globa
     else:
         pose48 = torch.cat((params["rot"][fid], params["pose"][fid]), 1).to(device)
         verts0, joints = ops.LbsMano.apply(hc, pose48, betas, params["trans"][fid].to(device))  # metres (visualize.py:45-46)
-    disps = params.get("verts_disps")
     if disps is not None and disps.shape[1] != 1:
         raise NotImplementedError("free 3-D vertex offsets (VERT_DISPS_NORMALS=False) are not used by HARP's config")
     verts, _ = ops.MeshBuild.apply(hc, verts0, disps.to(device) if disps is not None else None)

@@ -120,3 +120,25 @@ def test_full_size_graph_replay_equals_eager(full_scene):
     assert float((graphed.app.data - eager.app.data).abs().max()) < 2e-2
     le, lg = eager.loss_dict(), graphed.loss_dict()
     assert math.isclose(le["total"], lg["total"], rel_tol=2e-3)
+
+
+def test_forward_only_fused_render_matches_the_step_images(full_scene):
+    """ops.render_forward (harp_render_fused with zero loss weights; BASELINE.json configs[4]) writes the same images as the
+    optimiser step's fused pass on the same mesh."""
+    from harp_b200 import camera
+    from harp_b200.ops import render_forward
+    hc, sc = full_scene
+    ft = _fitter(hc, sc)
+    B = 8
+    fid = torch.arange(B, device="cuda")
+    ft.step(fid, sc["offsets"]["albedo"], sc["offsets"]["normal"], stage="both", update=False)
+    alpha, rgb, verts, normals = ft.last["alpha"].clone(), ft.last["rgb"].clone(), ft.last["verts"].clone(), ft.last["normals"].clone()
+    cR = camera.flip_xy_R(B, "cuda")
+    cT = camera.cam_to_T(ft.coarse.p["cam"][:B], sc["focal"], SIZE)
+    light = ft.app.p["light_positions"][0][None].expand(B, 3).contiguous()
+    lR, lT = camera.light_camera(light, verts.mean(1))
+    a2, r2 = render_forward(hc, verts, normals, cR, cT, lR, lT, light, torch.sigmoid(ft.app.p["amb_ratio"]), ft.app.p["texture"],
+                            ft.app.p["normal_map"], sc["focal"], SIZE, 1)
+    assert float((a2 - alpha).abs().max()) <= 1e-6
+    d = (r2 - rgb).abs().amax(-1)
+    assert float((d <= 1e-4).double().mean()) >= 0.999, float((d <= 1e-4).double().mean())  # (torch light camera vs the in-kernel one)

@@ -12,7 +12,7 @@ import torch
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
 from harp_b200 import camera, scene  # noqa: E402
-from harp_b200.ops import LbsMano, MeshBuild, Shade, Silhouette  # noqa: E402
+from harp_b200.ops import LbsMano, MeshBuild, render_forward  # noqa: E402
 from harp_b200.step import HarpFitter  # noqa: E402
 
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
@@ -64,9 +64,7 @@ def c5():
                 verts, normals = MeshBuild.apply(hc, verts0, p["verts_disps"])
                 cT = camera.cam_to_T(cam, focal, S)
                 lR, lT = camera.light_camera(light, verts.mean(1))
-                a = Silhouette.apply(hc, verts, cR, cT, focal, S, 1e-7)
-                r = Shade.apply(hc, verts, normals, cR, cT, lR, lT, light, amb, p["texture"], p["normal_map"], focal, S, 1)
-                return a, r
+                return render_forward(hc, verts, normals, cR, cT, lR, lT, light, amb, p["texture"], p["normal_map"], focal, S, 1)
             ms = timeit(fwd, 2, 10 if B < 256 else 4)
             gbps = 16.0 * S * S * B / (ms * 1e-3) / 1e9  # algorithmic: write y_pred 12 S^2 + alpha 4 S^2 per frame
             print(json.dumps({"config": f"C5 forward-only raster @512x512, batch {B}", "batch": B, "ms": ms, "frames_per_s": B * 1e3 / ms,
