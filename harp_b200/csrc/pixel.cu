@@ -28,7 +28,7 @@ namespace {
 #endif
 constexpr int CHUNK = 32;   // faces staged per bulk-copy round (one lane of warp 0 per face)
 constexpr int NT = HARP_TILE * HARP_TILE;
-constexpr int QCAP = 320;   // band pairs of one tile (all chunks); a tile that needs more goes to the exact per-pixel kernel
+constexpr int QCAP = 256;   // band pairs of one tile (all chunks); a tile that needs more goes to the exact per-pixel kernel
 constexpr int TIECAP = 128; // visibility candidates within 1e-5 of each other (resolved with the exact depth)
 
 // ---- Blackwell/Hopper async-copy plumbing: mbarrier + bulk global->shared copies (TMA unit; SASS: UBLKCP / SYNCS) ----------
@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
   __shared__ int s_tie[TIECAP];
   __shared__ int s_cnt[NT], s_head[NT];
   __shared__ int s_pre[CHUNK + 1], s_rect[CHUNK];
-  __shared__ float s_rw[CHUNK];
+  __shared__ unsigned short s_span[CHUNK * HARP_TILE], s_upre[CHUNK * HARP_TILE + 2], s_tmp[CHUNK * HARP_TILE];  // (face, row) spans of the round
+  __shared__ int s_scan0, s_nu;
   __shared__ float s_g[NT], s_prod[NT];
   __shared__ unsigned char s_need[NT], s_sat[NT];
   __shared__ float s_px[HARP_TILE], s_py[HARP_TILE];
@@ -225,21 +226,18 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
       if (base > 0) { __syncthreads(); issue(item, base, cur); }  // the buffer is free: everyone is past the previous round
       if (cur == 0) { mbar_wait(&s_bar[0], phase0); phase0 ^= 1; } else { mbar_wait(&s_bar[1], phase1); phase1 ^= 1; }
       const FaceTile* recs = s_rec[cur];
-      // ---- each face's pixel rectangle inside the tile, and the running pair count (warp 0)
+      // ---- (1) each face's pixel rectangle inside the tile: its rows are the UNITS of this round (warp 0, lane = face)
       if (warp == 0) {
-        int cnt = 0, rc = 0;
-        float rw = 1.f;
+        int h = 0, rc = 0;
         if (lane < m) {
           int cols = recs[lane].cols, rows = recs[lane].rows;
           int x0 = max(cols & 0xffff, tx0) - tx0, x1 = min(cols >> 16, tx0 + HARP_TILE - 1) - tx0;
           int y0 = max(rows & 0xffff, ty0) - ty0, y1 = min(rows >> 16, ty0 + HARP_TILE - 1) - ty0;
-          int w = x1 - x0 + 1, h = y1 - y0 + 1;
-          bool ok = w > 0 && h > 0;
-          cnt = ok ? w * h : 1;  // never zero: pair ends stay distinct (the pair of an empty rectangle is skipped)
-          rc = ok ? (x0 | (y0 << 4) | (w << 8)) : 0;
-          rw = ok ? __frcp_rn((float)w) : 1.f;
+          int w = x1 - x0 + 1;
+          h = (w > 0 && y1 >= y0) ? y1 - y0 + 1 : 0;
+          rc = x0 | (y0 << 4) | (max(w, 0) << 8);
         }
-        int incl = cnt;
+        int incl = h;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           int x = __shfl_up_sync(0xffffffffu, incl, o);
@@ -248,27 +246,92 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
         s_pre[lane + 1] = incl;
         if (lane == 0) s_pre[0] = 0;
         s_rect[lane] = rc;
-        s_rw[lane] = rw;
+      }
+      __syncthreads();
+      // ---- (2) per (face, row): the span of columns that can matter — inside every edge line inflated by the band half-width
+      //      (exactly the pairs the classification below would not reject; triangles fill a quarter of their bounding boxes,
+      //      so this removes two thirds of the pair tests).  Each thread owns `per` consecutive units; non-empty spans are
+      //      compacted and their pixel counts prefix-summed in one block scan (pairs in the low, units in the high half-word).
+      {
+        const int U = s_pre[m];
+        const int per = (U + NT - 1) / NT;  // <= 4: at most 32 faces x 8 rows
+        const int u0 = tid * per, u1 = min(U, u0 + per);
+        int packed = 0;
+        if (u0 < u1) {
+          int lo = 0, hi = m;  // face of unit u0: the last face whose unit offset is <= u0
+          while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pre[mid] <= u0) lo = mid; else hi = mid; }
+          int fi = lo;
+          const float hs = 0.5f * (float)S, sq = SIL ? sqrtf(far) * 1.001f : 0.f;
+#pragma unroll 1
+          for (int u = u0; u < u1; ++u) {
+            while (s_pre[fi + 1] <= u) ++fi;  // (faces without rows have equal offsets and are skipped)
+            const FaceTile& f = recs[fi];
+            const int rc = s_rect[fi], rx0 = rc & 15, rw = rc >> 8;
+            const int ry = ((rc >> 4) & 15) + (u - s_pre[fi]);
+            int c0 = rx0, c1 = rx0 + rw - 1;  // tile-local column range, inclusive
+            if (f.sgn != 0.f) {               // (a face crossing the camera plane keeps its whole rectangle)
+              const float py = s_py[ry];
+              float xlo = f.xmin, xhi = f.xmax;
+              bool empty = false;
+#pragma unroll 1
+              for (int e = 0; e < 3; ++e) {
+                // keep x with  a x + (b py + c) > -M,  M = sqrt(far) |edge| (+ the affine form's rounding bound)
+                const float4 ed = reinterpret_cast<const float4*>(&f)[3 + e];  // a, b, c, 1 / |edge|^2
+                float base = fmaf(ed.y, py, ed.z) + sq * rsqrtf(ed.w) + 2.f * f.eps;
+                if (fabsf(ed.x) > 1e-12f) {
+                  float xb = __fdividef(-base, ed.x);
+                  if (ed.x > 0.f) xlo = fmaxf(xlo, xb); else xhi = fminf(xhi, xb);
+                } else if (base <= 0.f) {
+                  empty = true;
+                }
+              }
+              // pixel column j has x = 1 - (2j+1)/S (decreasing): columns ceil((1-xhi) S/2 - 0.5) .. floor((1-xlo) S/2 - 0.5),
+              // widened by 0.01 px (the exact tests run per pair)
+              float fj0 = ceilf((1.f - xhi) * hs - 0.5f - 0.01f), fj1 = floorf((1.f - xlo) * hs - 0.5f + 0.01f);
+              fj0 = fmaxf(fj0, (float)(tx0 + c0)); fj1 = fminf(fj1, (float)(tx0 + c1));
+              if (empty || !(fj0 <= fj1)) { c1 = c0 - 1; } else { c0 = (int)fj0 - tx0; c1 = (int)fj1 - tx0; }
+            }
+            const int len = max(0, c1 - c0 + 1);
+            s_tmp[u] = (unsigned short)(fi | (ry << 5) | (c0 << 8) | (len << 11));
+            packed += len > 0 ? (len | (1 << 16)) : 0;
+          }
+        }
+        int incl = packed;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int x = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += x;
+        }
+        if (tid == 31) s_scan0 = incl;
+        __syncthreads();
+        int excl = incl - packed + (warp == 1 ? s_scan0 : 0);
+        int pp = excl & 0xffff, uu = excl >> 16;
+#pragma unroll 1
+        for (int u = u0; u < u1; ++u) {
+          const int cd = s_tmp[u], len = cd >> 11;
+          if (len > 0) {
+            s_span[uu] = (unsigned short)cd;
+            pp += len;
+            s_upre[++uu] = (unsigned short)pp;
+          }
+        }
+        if (tid == NT - 1) { s_upre[0] = 0; s_nu = uu; }
       }
       __syncthreads();
       // ---- A: one (pixel, face) pair per lane and step
       {
-        const int P = s_pre[m];
-        const int e_l = lane < m ? s_pre[lane + 1] : 0x7fffffff;  // end of face `lane`'s pairs
+        const int NU = s_nu;
+        const int P = NU > 0 ? s_upre[NU] : 0;
         for (int p0 = warp * 32; p0 < P; p0 += 2 * 32) {
-          // face of pair p = #faces whose pairs end at or before p: faces ended before the window + boundaries inside it
-          int fbase = __popc(__ballot_sync(0xffffffffu, e_l <= p0));
-          unsigned bit = (e_l > p0 && e_l <= p0 + 31) ? (1u << (e_l - p0)) : 0u;
-          unsigned wmask = __reduce_or_sync(0xffffffffu, bit);
           const int p = p0 + lane;
           const bool valid = p < P;
-          int fi = valid ? fbase + __popc(wmask & ((2u << lane) - 1u)) : 0;
+          int lo = 0, hi = NU;  // unit of pair p: the last unit whose first pair is <= p
+          const int pq = valid ? p : 0;
+          while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_upre[mid] <= pq) lo = mid; else hi = mid; }
+          const int cd = s_span[lo];
+          const int fi = cd & 31, ly = (cd >> 5) & 7, lx = ((cd >> 8) & 7) + (pq - s_upre[lo]);
           const FaceTile& f = recs[fi];
-          int rc = s_rect[fi], w = rc >> 8;
-          int local = p - s_pre[fi];
-          int ry = __float2int_rz(((float)local + 0.5f) * s_rw[fi]);
-          int lx = (rc & 15) + (local - ry * w), ly = ((rc >> 4) & 15) + ry;
-          if (!valid || w == 0) { lx = 0; ly = 0; }
+          const int w = valid ? 1 : 0;
           const int pix = ly * HARP_TILE + lx;
           const float px = s_px[lx], py = s_py[ly];
           bool inb = valid && w != 0 && in_face_bbox(f, px, py);
@@ -527,7 +590,7 @@ __global__ void __launch_bounds__(256) empty_tiles_kernel(int B, int S, const in
 
 // Shade the compacted hit pixels of one frame per blockIdx.y; grid-stride over the frame's hit list.
 #ifndef HARP_SHADE_MIN_CTAS
-#define HARP_SHADE_MIN_CTAS 4
+#define HARP_SHADE_MIN_CTAS 3  // 168 registers, no spills: the kernel is bound by per-thread instruction latency, so registers beat warps (0.549 -> 0.535 ms)
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(128, HARP_SHADE_MIN_CTAS) shade_deferred_kernel(harp_ctx c, ShadeArgs a, const int2* __restrict__ hit_list,
