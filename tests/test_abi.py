@@ -79,3 +79,33 @@ def test_checkpoint_roundtrip_uses_reference_keys(tmp_path):
     back = file_utils.load_result(str(tmp_path))
     for k, v in params.items():
         assert (back[k] is None) if v is None else torch.equal(back[k], v)
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """The ctypes mirrors in harp_b200/_lib.py (what INTEGRATION.md shows a maintainer) have the size and field offsets a C
+    compiler gives the structs of include/harp_b200.h."""
+    from harp_b200 import _lib
+    probes = {"harp_step_args": ("B", "focal", "weights", "fid", "pose", "y_true", "losses", "g_pose", "d_rot", "workspace"),
+              "harp_render_args": ("verts", "texH", "sigma", "y_sil", "w_sil", "alpha", "grads"),
+              "harp_shade_grads": ("d_verts", "d_normal_map"), "harp_topology": ("V0", "faces0", "verts_uvs"),
+              "harp_lbs_model": ("J", "parents", "rodrigues_kind", "tips")}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "harp_b200.h")}"', "int main(void) {"]
+    for st, fields in probes.items():
+        lines.append(f'  printf("{st} %zu", sizeof({st}));')
+        for f in fields:
+            lines.append(f'  printf(" %zu", offsetof({st}, {f}));')
+        lines.append('  printf("\\n");')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    mirror = {"harp_step_args": _lib.HarpStepArgs, "harp_render_args": _lib.HarpRenderArgs, "harp_shade_grads": _lib.HarpShadeGrads,
+              "harp_topology": _lib.HarpTopology, "harp_lbs_model": _lib.HarpLbsModel}
+    for line in out.strip().splitlines():
+        name, size, *offs = line.split()
+        cls = mirror[name]
+        assert ctypes.sizeof(cls) == int(size), (name, ctypes.sizeof(cls), size)
+        for f, o in zip(probes[name], offs):
+            assert getattr(cls, f).offset == int(o), (name, f, getattr(cls, f).offset, o)
