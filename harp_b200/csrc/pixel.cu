@@ -11,10 +11,8 @@ int harp_project_bwd(harp_ctx* c, int B, int S, float focal, const float* verts,
                      const float* d_ndc, float* d_verts, float* d_R, float* d_T, cudaStream_t st);
 int harp_fold4(size_t n, const float* src4, float* dst3, cudaStream_t st);
 int harp_tex_prepare(harp_ctx* c, const float* texture, const float* normal_map, int texH, int texW, cudaStream_t st);
-int harp_light_depth(harp_ctx* c, int B, int S, cudaStream_t st);
 int harp_light_depth_tiles(harp_ctx* c, int B, int S, bool zero_grad, cudaStream_t st);
 int harp_light_depth_bwd_tiles(harp_ctx* c, int B, int S, cudaStream_t st);
-int harp_light_depth_bwd(harp_ctx* c, int B, int S, cudaStream_t st);
 int harp_sil_topk(harp_ctx* c, int mode, int S, int K, float sigma, float blur, float radius, float* alpha, const float* gin,
                   float gscale, float inv_n, float* loss, cudaStream_t st);
 
@@ -65,14 +63,15 @@ struct VisArgs {
   int32_t* work_ctl;         // {heavy, light, cursor, -}
   int work_cap;
   // silhouette
-  float* alpha;
-  const float* y_sil;
+  float* alpha;          // may be null (gradient-only pass)
+  const float* y_sil;    // target of the fused L1 loss ...
+  const float* g_alpha;  // ... or an upstream dL/dalpha image (then no loss is accumulated)
   float sil_gscale, sil_inv_n;
   float* sil_loss;
   float* d_ndc;
   // visibility
-  int32_t *hit_list, *hit_count;  // hit_list: (B, S*S) int2 records (row << 16 | col, face id)
-  // background pixels of the colour image
+  int32_t *hit_list, *hit_count;  // hit_list: (B, S*S) int2 records (row << 16 | col, face id); null: silhouette only
+  // background pixels of the colour image (null: silhouette only / gradient-only pass)
   float* rgb;
   const float *y_true, *y_mask;
   float photo_inv_n;
@@ -156,10 +155,13 @@ __device__ __forceinline__ float exact_pz_rec(const FaceTile* rec, int fid, floa
 // sum and every lane classifies one pair per step, so lanes do useful tests only (the former pixel-major walk tested all 64
 // pixels of the tile against every face).  Visibility is a 64-bit shared-memory atomicMax on (1/depth, ~face id); silhouette
 // band pairs are queued, evaluated with full warps, chained per pixel and folded in ascending face id (deterministic alpha).
-//   SIL     camera view: silhouette + visibility + hit compaction;  !SIL: light view, nearest depth + face id only
-//   SIL_BWD accumulate the silhouette L1 loss and its gradient (COARSE_OPT stages)
+//   SIL     soft silhouette (band pairs) next to the visibility;  CAM: camera-view outputs (hit compaction, background
+//           colour);  !SIL && !CAM: light view, nearest depth + face id only.  The fitting step runs <SIL, CAM>; the
+//           stand-alone Silhouette op runs the same with no hit list / colour image, the stand-alone Shade op <!SIL, CAM>
+//   SIL_BWD the silhouette gradient: of the fused L1 loss (COARSE_OPT stages) or, when a.g_alpha is set, of an upstream
+//           dL/dalpha image (the autograd drop-in)
 //   PHOTO   accumulate the photometric loss of background pixels (APP_OPT stages)
-template <bool SIL, bool SIL_BWD, bool PHOTO>
+template <bool SIL, bool SIL_BWD, bool PHOTO, bool CAM>
 __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_ctx c, VisArgs a) {
   __shared__ FaceTile s_rec[2][CHUNK];
   __shared__ __align__(8) uint64_t s_bar[2];
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
       }
     }
     const bool hit = best_fid >= 0;
-    if (!SIL) {
+    if (!CAM) {
       // light view: nearest exact depth + face id (renderer_helper.py:344)
       float z = -1.f;
       int fo = -1;
@@ -463,7 +465,7 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
       a.face[pix] = fo;
       if (a.d_zbuf) a.d_zbuf[pix] = 0.f;  // the gradient image is only ever touched on tiles some face covers
     } else {
-      {  // per-frame compacted hit list (warp-aggregated append)
+      if (a.hit_list) {  // per-frame compacted hit list (warp-aggregated append)
         unsigned mask = __ballot_sync(0xffffffffu, hit);
         int hb = 0;
         if (mask) {
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
       }
       float photo_abs = 0.f;
       if (!hit) {
-        st3(a.rgb + pix * 3, mk3(1.f, 1.f, 1.f));  // background colour (renderer_helper.py:430)
+        if (a.rgb) st3(a.rgb + pix * 3, mk3(1.f, 1.f, 1.f));  // background colour (renderer_helper.py:430)
         if (PHOTO) {
           float mk = a.y_mask[pix];
           if (mk != 0.f) {
@@ -487,23 +489,27 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
       // the product is taken in double: re-ordering then changes it by ~1e-16, i.e. the float result is the same however the
       // pairs were scheduled (alpha is reproducible run to run)
       const int qn = min(s_qn, QCAP);
-      float prod = 1.f;
-      int nzero = s_sat[tid] ? 1 : 0, npass = nzero;
-      if (nzero == 0) {
-        double dp = 1.0;
-        for (int s = s_head[tid]; s >= 0; s = s_q[s].next) {
-          if (s_q[s].edge == 255) continue;
-          ++npass;
-          dp *= (double)s_om[s];
+      float prod = 1.f, diff = 0.f;
+      int nzero = 0, npass = 0;
+      bool deferred = false;
+      if (SIL) {
+        nzero = s_sat[tid] ? 1 : 0; npass = nzero;
+        if (nzero == 0) {
+          double dp = 1.0;
+          for (int s = s_head[tid]; s >= 0; s = s_q[s].next) {
+            if (s_q[s].edge == 255) continue;
+            ++npass;
+            dp *= (double)s_om[s];
+          }
+          prod = (float)dp;
         }
-        prod = (float)dp;
+        float al = nzero > 0 ? 1.f : 1.f - prod;
+        // more candidates than faces_per_pixel (or a band queue that did not fit) -> exact per-pixel top-K kernel
+        deferred = (count_cand && s_cnt[tid] > a.K) || s_ovf != 0;
+        if (deferred) sil_defer_overflow(c, (int)pix);
+        else if (a.alpha) a.alpha[pix] = al;
+        if (SIL_BWD && !deferred && !a.g_alpha) diff = al - a.y_sil[pix];
       }
-      float al = nzero > 0 ? 1.f : 1.f - prod;
-      // more candidates than faces_per_pixel (or a band queue that did not fit) -> exact per-pixel top-K kernel
-      const bool deferred = (count_cand && s_cnt[tid] > a.K) || s_ovf != 0;
-      if (deferred) sil_defer_overflow(c, (int)pix);
-      else a.alpha[pix] = al;
-      float diff = (deferred || !SIL_BWD) ? 0.f : al - a.y_sil[pix];
       if (SIL_BWD || PHOTO) {
         float s_sil = fabsf(diff), s_ph = photo_abs;
         block_sum2(s_sil, s_ph, red);
@@ -514,6 +520,7 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
       }
       if (SIL_BWD) {
         float g = diff > 0.f ? a.sil_gscale : (diff < 0.f ? -a.sil_gscale : 0.f);
+        if (a.g_alpha) g = deferred ? 0.f : a.g_alpha[pix];  // an upstream dL/dalpha image instead of the fused loss
         bool need = (g != 0.f) && nzero == 0 && prod > 0.f && npass > 0;
         s_g[tid] = g; s_prod[tid] = prod; s_need[tid] = need ? 1 : 0;
         if (__syncthreads_or(need ? 1 : 0)) {
@@ -556,11 +563,13 @@ __global__ void __launch_bounds__(256) empty_tiles_kernel(int B, int S, const in
         __stcs(reinterpret_cast<float4*>(a.zbuf + pix), make_float4(-1.f, -1.f, -1.f, -1.f));
         __stcs(reinterpret_cast<int4*>(a.face + pix), make_int4(-1, -1, -1, -1));
       } else {
-        __stcs(reinterpret_cast<float4*>(a.alpha + pix), make_float4(0.f, 0.f, 0.f, 0.f));
-        float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
-        float4* o = reinterpret_cast<float4*>(a.rgb + pix * 3);
-        __stcs(o, one); __stcs(o + 1, one); __stcs(o + 2, one);
-        if (SIL_BWD) {
+        if (a.alpha) __stcs(reinterpret_cast<float4*>(a.alpha + pix), make_float4(0.f, 0.f, 0.f, 0.f));
+        if (a.rgb) {
+          float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
+          float4* o = reinterpret_cast<float4*>(a.rgb + pix * 3);
+          __stcs(o, one); __stcs(o + 1, one); __stcs(o + 2, one);
+        }
+        if (SIL_BWD && a.y_sil) {
           float4 ys = __ldcs(reinterpret_cast<const float4*>(a.y_sil + pix));
           s_sil = fabsf(ys.x) + fabsf(ys.y) + fabsf(ys.z) + fabsf(ys.w);
         }
@@ -646,25 +655,25 @@ __global__ void __launch_bounds__(128, HARP_SHADE_MIN_CTAS) shade_deferred_kerne
   shade_flush_frame_scalars(a, b, fr);
 }
 
-}  // namespace
 
-extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const harp_render_args* r, void* stream) {
-  HARP_REQUIRE(c && r && B > 0, HARP_ERR_INVALID, "harp_render_fused: null argument");
-  HARP_REQUIRE(r->verts && r->normals && r->cam_R && r->cam_T && r->light_pos && r->amb && r->texture && r->normal_map &&
-                   r->alpha && r->rgb, HARP_ERR_INVALID, "harp_render_fused: missing input / output tensor");
-  HARP_REQUIRE(c->has_uv, HARP_ERR_INVALID, "harp_render_fused: ctx was created without UV tables");
-  HARP_REQUIRE(B <= c->maxB && S == c->S, HARP_ERR_CAPACITY, "harp_render_fused: call harp_ctx_reserve(B, S) first");
-  HARP_REQUIRE(!r->self_shadow || (r->light_R && r->light_T), HARP_ERR_INVALID, "harp_render_fused: light camera required");
-  const bool sil_bwd = r->w_sil != 0.f, photo_bwd = r->w_photo != 0.f;
-  HARP_REQUIRE(!sil_bwd || (r->y_sil && r->loss_sil && r->grads.d_verts && r->grads.d_cam_T), HARP_ERR_INVALID,
-               "harp_render_fused: silhouette loss needs y_sil, loss_sil, d_verts, d_cam_T");
-  HARP_REQUIRE(!photo_bwd || (r->y_true && r->y_mask && r->loss_photo && r->grads.d_verts && r->grads.d_normals), HARP_ERR_INVALID,
-               "harp_render_fused: photometric loss needs y_true, y_mask, loss_photo, d_verts, d_normals");
-  cudaStream_t st = (cudaStream_t)stream;
+// One render pass over B frames: which branches run and how their gradients are driven.
+struct RenderPlan {
+  bool sil = true, shade = true;   // silhouette branch / colour branch
+  int sil_mode = 0, shade_mode = 0;  // 0 forward; 1 backward of an upstream gradient image; 2 fused L1 loss + its gradient
+  const float* g_alpha = nullptr;  // sil_mode 1: dL/dalpha (B,S,S)
+  const float* fixed_lights = nullptr;  // host {ka, kd, ks}: the Phong twin with constant light colours
+  const char* who = "harp_render";
+};
+
+// The schedule every render entry point shares (harp_render_fused, harp_silhouette, harp_shade).  In shade mode 1 the
+// upstream dL/drgb image travels in r->y_true.
+int render_pass(harp_ctx* c, int B, int S, float focal, const harp_render_args* r, const RenderPlan& p, cudaStream_t st) {
+  const bool sil_bwd = p.sil && p.sil_mode != 0, shade_bwd = p.shade && p.shade_mode != 0, photo = p.shade && p.shade_mode == 2;
+  const bool shadow = p.shade && r->self_shadow;
   int rc;
-  const size_t npx = (size_t)B * S * S, nv4 = (size_t)B * c->V * 4 * sizeof(float), ntex = (size_t)r->texH * r->texW;
-  double blur_d = 9.210240366975849 * (double)r->sigma;  // ln(1/1e-4 - 1) sigma (renderer_helper.py:46)
-  float blur = (float)blur_d, radius = (float)sqrt(blur_d);
+  const size_t nv4 = (size_t)B * c->V * 4 * sizeof(float), ntex = (size_t)r->texH * r->texW;
+  double blur_d = 9.210240366975849 * (double)r->sigma;  // ln(1/1e-4 - 1) sigma (renderer_helper.py:46), in double like numpy
+  float blur = p.sil ? (float)blur_d : 0.f, radius = p.sil ? (float)sqrt(blur_d) : 0.f;
   // Camera branch first (it is the critical path: its kernels are submitted before the side branch's so that they are
   // dispatched first).
   if (!c->side_stream) {
@@ -685,81 +694,98 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
   VisArgs v{};
   v.S = S; v.K = r->faces_per_pixel > 0 ? r->faces_per_pixel : 50; v.sigma = r->sigma; v.blur = blur; v.radius = radius; v.ndc = c->ndc_cam;
   v.rec = c->face_rec; v.bin_list = c->bin_list; v.work = c->work; v.work_ctl = c->work_ctl; v.work_cap = c->maxB * c->tiles;
-  v.alpha = r->alpha; v.y_sil = r->y_sil; v.sil_inv_n = 1.f / ((float)B * S * S); v.sil_gscale = r->w_sil * v.sil_inv_n;
-  v.sil_loss = r->loss_sil; v.d_ndc = c->d_ndc_cam;
-  v.hit_list = c->hit_list; v.hit_count = c->hit_count;
-  v.rgb = r->rgb; v.y_true = r->y_true; v.y_mask = r->y_mask; v.photo_inv_n = 1.f / ((float)B * S * S * 3.f);
-  v.photo_loss = r->loss_photo;
+  v.sil_inv_n = 1.f / ((float)B * S * S); v.sil_gscale = r->w_sil * v.sil_inv_n;
+  if (p.sil) {
+    v.alpha = p.sil_mode == 1 ? nullptr : r->alpha;
+    v.y_sil = p.sil_mode == 2 ? r->y_sil : nullptr; v.g_alpha = p.sil_mode == 1 ? p.g_alpha : nullptr;
+    v.sil_loss = r->loss_sil; v.d_ndc = c->d_ndc_cam;
+  }
+  v.photo_inv_n = 1.f / ((float)B * S * S * 3.f);
+  if (p.shade) {
+    v.hit_list = c->hit_list; v.hit_count = c->hit_count;
+    v.rgb = p.shade_mode == 1 ? nullptr : r->rgb;
+    if (photo) { v.y_true = r->y_true; v.y_mask = r->y_mask; v.photo_loss = r->loss_photo; }
+  }
   const int grid = HARP_SM_COUNT * HARP_PV_MINCTAS;  // persistent: every CTA pulls tiles until the queue is empty
   harp_prof_begin(c, 0, st);
-  if (sil_bwd && photo_bwd) tile_raster_kernel<true, true, true><<<grid, NT, 0, st>>>(*c, v);
-  else if (sil_bwd) tile_raster_kernel<true, true, false><<<grid, NT, 0, st>>>(*c, v);
-  else if (photo_bwd) tile_raster_kernel<true, false, true><<<grid, NT, 0, st>>>(*c, v);
-  else tile_raster_kernel<true, false, false><<<grid, NT, 0, st>>>(*c, v);
+  if (p.sil) {
+    if (sil_bwd && photo) tile_raster_kernel<true, true, true, true><<<grid, NT, 0, st>>>(*c, v);
+    else if (sil_bwd) tile_raster_kernel<true, true, false, true><<<grid, NT, 0, st>>>(*c, v);
+    else if (photo) tile_raster_kernel<true, false, true, true><<<grid, NT, 0, st>>>(*c, v);
+    else tile_raster_kernel<true, false, false, true><<<grid, NT, 0, st>>>(*c, v);
+  } else {
+    if (photo) tile_raster_kernel<false, false, true, true><<<grid, NT, 0, st>>>(*c, v);
+    else tile_raster_kernel<false, false, false, true><<<grid, NT, 0, st>>>(*c, v);
+  }
   harp_prof_end(c, 0, st);
   HARP_LAUNCH_CHECK();
-  if ((rc = harp_sil_topk(c, sil_bwd ? 2 : 0, S, v.K, r->sigma, blur, radius, r->alpha, r->y_sil, v.sil_gscale, v.sil_inv_n,
-                          r->loss_sil, st)) != HARP_OK) return rc;
+  if (p.sil && (rc = harp_sil_topk(c, p.sil_mode, S, v.K, r->sigma, blur, radius, r->alpha, p.sil_mode == 1 ? p.g_alpha : r->y_sil,
+                                   v.sil_gscale, v.sil_inv_n, r->loss_sil, st)) != HARP_OK) return rc;
   // Side branch on the ctx's own (least-priority) stream, concurrent with the camera branch above and joined before the
   // deferred shading: everything only the shading needs — the light view (setup, nearest-depth raster), the packed texel
   // copies, the zero fills of the shading's gradient accumulators — and the HBM-bound streaming pass over the camera view's
   // empty tiles, which overlaps the issue-bound tile rasteriser.  Event fork / join is capturable into a CUDA graph.
   HARP_CHECK_CUDA(cudaStreamWaitEvent(ss, c->ev_fork, 0));
-  if (r->self_shadow) {
-    if ((rc = harp_raster_setup(c, 1, B, S, focal, 0.f, r->verts, r->light_R, r->light_T, ss, photo_bwd)) != HARP_OK) return rc;
-    if ((rc = harp_light_depth_tiles(c, B, S, photo_bwd, ss)) != HARP_OK) return rc;
+  if (shadow) {
+    if ((rc = harp_raster_setup(c, 1, B, S, focal, 0.f, r->verts, r->light_R, r->light_T, ss, shade_bwd)) != HARP_OK) return rc;
+    if ((rc = harp_light_depth_tiles(c, B, S, shade_bwd, ss)) != HARP_OK) return rc;
   }
-  if ((rc = harp_tex_prepare(c, r->texture, r->normal_map, r->texH, r->texW, ss)) != HARP_OK) return rc;
-  if (photo_bwd) {
+  if (p.shade && (rc = harp_tex_prepare(c, r->texture, r->normal_map, r->texH, r->texW, ss)) != HARP_OK) return rc;
+  if (shade_bwd) {
     HARP_CHECK_CUDA(cudaMemsetAsync(c->d_verts4, 0, nv4, ss));
     HARP_CHECK_CUDA(cudaMemsetAsync(c->d_normals4, 0, nv4, ss));
     HARP_CHECK_CUDA(cudaMemsetAsync(c->d_tex4, 0, 2 * ntex * 4 * sizeof(float), ss));
   }
-  {
+  if (v.alpha || v.rgb || sil_bwd || photo) {
     HARP_CHECK_CUDA(cudaStreamWaitEvent(ss, c->ev_bins, 0));
     const int eg = (int)(((size_t)B * S * (S / 4) + 255) / 256);
-    if (sil_bwd && photo_bwd) empty_tiles_kernel<false, true, true><<<eg, 256, 0, ss>>>(B, S, c->bin_count, v);
+    if (sil_bwd && photo) empty_tiles_kernel<false, true, true><<<eg, 256, 0, ss>>>(B, S, c->bin_count, v);
     else if (sil_bwd) empty_tiles_kernel<false, true, false><<<eg, 256, 0, ss>>>(B, S, c->bin_count, v);
-    else if (photo_bwd) empty_tiles_kernel<false, false, true><<<eg, 256, 0, ss>>>(B, S, c->bin_count, v);
+    else if (photo) empty_tiles_kernel<false, false, true><<<eg, 256, 0, ss>>>(B, S, c->bin_count, v);
     else empty_tiles_kernel<false, false, false><<<eg, 256, 0, ss>>>(B, S, c->bin_count, v);
     HARP_LAUNCH_CHECK();
   }
   HARP_CHECK_CUDA(cudaEventRecord(c->ev_join, ss));
   HARP_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
-  ShadeArgs a{};
-  a.B = B; a.S = S; a.self_shadow = r->self_shadow; a.texH = r->texH; a.texW = r->texW; a.focal = focal;
-  a.inv_n = v.photo_inv_n; a.gscale = r->w_photo * a.inv_n;
-  a.verts = r->verts; a.normals = r->normals; a.ndc_cam = c->ndc_cam;
-  a.light_R = r->light_R ? r->light_R : r->cam_R; a.light_T = r->light_T ? r->light_T : r->cam_T;
-  a.light_pos = r->light_pos; a.amb = r->amb;
-  a.tex4 = reinterpret_cast<const float4*>(c->tex4); a.nm4 = a.tex4 + ntex;
-  a.light_zbuf = c->light_zbuf; a.rgb = r->rgb; a.gin = r->y_true; a.mask = r->y_mask; a.loss = r->loss_photo;
-  if (photo_bwd) {
-    a.d_ndc_cam = c->d_ndc_cam; a.d_verts = c->d_verts4; a.d_normals = c->d_normals4;
-    a.d_light_R = r->grads.d_light_R; a.d_light_T = r->grads.d_light_T; a.d_light_pos = r->grads.d_light_pos;
-    a.d_amb = r->grads.d_amb; a.d_texture = c->d_tex4; a.d_normal_map = c->d_tex4 + ntex * 4; a.d_light_zbuf = c->d_light_zbuf;
-  }
-  dim3 sgrid(HARP_SHADE_GRID, B);
   harp_prof_begin(c, 1, st);
-  if (photo_bwd) shade_deferred_kernel<2><<<sgrid, 128, 0, st>>>(*c, a, reinterpret_cast<const int2*>(c->hit_list), c->hit_count);
-  else shade_deferred_kernel<0><<<sgrid, 128, 0, st>>>(*c, a, reinterpret_cast<const int2*>(c->hit_list), c->hit_count);
+  if (p.shade) {
+    ShadeArgs a{};
+    a.B = B; a.S = S; a.self_shadow = r->self_shadow; a.texH = r->texH; a.texW = r->texW; a.focal = focal;
+    if (p.fixed_lights) { a.fixed_lights = 1; a.ka = p.fixed_lights[0]; a.kd = p.fixed_lights[1]; a.ks = p.fixed_lights[2]; }
+    a.inv_n = v.photo_inv_n; a.gscale = r->w_photo * a.inv_n;
+    a.verts = r->verts; a.normals = r->normals; a.ndc_cam = c->ndc_cam;
+    a.light_R = r->light_R ? r->light_R : r->cam_R; a.light_T = r->light_T ? r->light_T : r->cam_T;
+    a.light_pos = r->light_pos; a.amb = r->amb;
+    a.tex4 = reinterpret_cast<const float4*>(c->tex4); a.nm4 = a.tex4 + ntex;
+    a.light_zbuf = c->light_zbuf; a.rgb = r->rgb; a.gin = r->y_true; a.mask = r->y_mask; a.loss = r->loss_photo;
+    if (shade_bwd) {
+      a.d_ndc_cam = c->d_ndc_cam; a.d_verts = c->d_verts4; a.d_normals = c->d_normals4;
+      a.d_light_R = r->grads.d_light_R; a.d_light_T = r->grads.d_light_T; a.d_light_pos = r->grads.d_light_pos;
+      a.d_amb = r->grads.d_amb; a.d_texture = c->d_tex4; a.d_normal_map = c->d_tex4 + ntex * 4; a.d_light_zbuf = c->d_light_zbuf;
+    }
+    dim3 sgrid(HARP_SHADE_GRID, B);
+    const int2* hits = reinterpret_cast<const int2*>(c->hit_list);
+    if (p.shade_mode == 2) shade_deferred_kernel<2><<<sgrid, 128, 0, st>>>(*c, a, hits, c->hit_count);
+    else if (p.shade_mode == 1) shade_deferred_kernel<1><<<sgrid, 128, 0, st>>>(*c, a, hits, c->hit_count);
+    else shade_deferred_kernel<0><<<sgrid, 128, 0, st>>>(*c, a, hits, c->hit_count);
+    HARP_LAUNCH_CHECK();
+  }
   harp_prof_end(c, 1, st);
-  HARP_LAUNCH_CHECK();
   harp_prof_begin(c, 7, st);
-  if (photo_bwd) {
+  if (shade_bwd) {
     if (!c->defer_fold) {  // harp_step_fused folds the padded vertex accumulators inside its geometry backward
       if ((rc = harp_fold4((size_t)B * c->V, c->d_verts4, r->grads.d_verts, st)) != HARP_OK) return rc;
       if ((rc = harp_fold4((size_t)B * c->V, c->d_normals4, r->grads.d_normals, st)) != HARP_OK) return rc;
     }
     if (r->grads.d_texture && (rc = harp_fold4(ntex, c->d_tex4, r->grads.d_texture, st)) != HARP_OK) return rc;
     if (r->grads.d_normal_map && (rc = harp_fold4(ntex, c->d_tex4 + ntex * 4, r->grads.d_normal_map, st)) != HARP_OK) return rc;
-    if (r->self_shadow) {
+    if (shadow) {
       if ((rc = harp_light_depth_bwd_tiles(c, B, S, st)) != HARP_OK) return rc;
       if ((rc = harp_project_bwd(c, B, S, focal, r->verts, r->light_R, r->light_T, c->d_ndc_light, r->grads.d_verts,
                                  r->grads.d_light_R, r->grads.d_light_T, st)) != HARP_OK) return rc;
     }
   }
-  if (sil_bwd || photo_bwd) {
+  if (sil_bwd || shade_bwd) {
     if ((rc = harp_project_bwd(c, B, S, focal, r->verts, r->cam_R, r->cam_T, c->d_ndc_cam, r->grads.d_verts, r->grads.d_cam_R,
                                r->grads.d_cam_T, st)) != HARP_OK) return rc;
   }
@@ -767,6 +793,74 @@ extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const h
   return HARP_OK;
 }
 
+}  // namespace
+
+extern "C" int harp_render_fused(harp_ctx* c, int B, int S, float focal, const harp_render_args* r, void* stream) {
+  HARP_REQUIRE(c && r && B > 0, HARP_ERR_INVALID, "harp_render_fused: null argument");
+  HARP_REQUIRE(r->verts && r->normals && r->cam_R && r->cam_T && r->light_pos && r->amb && r->texture && r->normal_map &&
+                   r->alpha && r->rgb, HARP_ERR_INVALID, "harp_render_fused: missing input / output tensor");
+  HARP_REQUIRE(c->has_uv, HARP_ERR_INVALID, "harp_render_fused: ctx was created without UV tables");
+  HARP_REQUIRE(B <= c->maxB && S == c->S, HARP_ERR_CAPACITY, "harp_render_fused: call harp_ctx_reserve(B, S) first");
+  HARP_REQUIRE(!r->self_shadow || (r->light_R && r->light_T), HARP_ERR_INVALID, "harp_render_fused: light camera required");
+  const bool sil_bwd = r->w_sil != 0.f, photo_bwd = r->w_photo != 0.f;
+  HARP_REQUIRE(!sil_bwd || (r->y_sil && r->loss_sil && r->grads.d_verts && r->grads.d_cam_T), HARP_ERR_INVALID,
+               "harp_render_fused: silhouette loss needs y_sil, loss_sil, d_verts, d_cam_T");
+  HARP_REQUIRE(!photo_bwd || (r->y_true && r->y_mask && r->loss_photo && r->grads.d_verts && r->grads.d_normals), HARP_ERR_INVALID,
+               "harp_render_fused: photometric loss needs y_true, y_mask, loss_photo, d_verts, d_normals");
+  RenderPlan p;
+  p.sil_mode = sil_bwd ? 2 : 0; p.shade_mode = photo_bwd ? 2 : 0;
+  return render_pass(c, B, S, focal, r, p, (cudaStream_t)stream);
+}
+
+// Soft silhouette alone (the drop-in for SoftSilhouetteShader rendering, renderer_helper.py:40-62): the same setup + tile
+// rasteriser + top-K kernels as the fitting step, without hit list or colour image.
+extern "C" int harp_silhouette(harp_ctx* c, int mode, int B, int S, float focal, float sigma, int faces_per_pixel, const float* verts,
+                               const float* R, const float* T, float* alpha, const float* gin, float weight, float* loss,
+                               float* d_verts, float* d_R, float* d_T, void* stream) {
+  HARP_REQUIRE(c && B > 0 && verts && R && T, HARP_ERR_INVALID, "harp_silhouette: null argument");
+  HARP_REQUIRE(mode >= 0 && mode <= 2, HARP_ERR_INVALID, "harp_silhouette: mode must be 0, 1 or 2");
+  HARP_REQUIRE(B <= c->maxB && S == c->S, HARP_ERR_CAPACITY, "harp_silhouette: call harp_ctx_reserve(B, S) first");
+  HARP_REQUIRE(mode == 1 || alpha, HARP_ERR_INVALID, "harp_silhouette: alpha output required");
+  HARP_REQUIRE(mode == 0 || gin, HARP_ERR_INVALID, "harp_silhouette: upstream gradient / target required");
+  HARP_REQUIRE(mode != 2 || loss, HARP_ERR_INVALID, "harp_silhouette: loss output required in fused mode");
+  HARP_REQUIRE(mode == 0 || d_verts, HARP_ERR_INVALID, "harp_silhouette: d_verts required");
+  harp_render_args r{};
+  r.verts = verts; r.cam_R = R; r.cam_T = T; r.sigma = sigma; r.faces_per_pixel = faces_per_pixel;
+  r.alpha = alpha; r.y_sil = gin; r.w_sil = weight; r.loss_sil = loss;
+  r.grads.d_verts = d_verts; r.grads.d_cam_R = d_R; r.grads.d_cam_T = d_T;
+  RenderPlan p;
+  p.shade = false; p.sil_mode = mode; p.g_alpha = gin;
+  return render_pass(c, B, S, focal, &r, p, (cudaStream_t)stream);
+}
+
+// Shadowed, textured colour image alone (the drop-in for the hard-Phong / NeuralShadow renders, renderer_helper.py:64-120,
+// 327-430): setup + visibility-only tile rasteriser + deferred shading, as in the fitting step.
+extern "C" int harp_shade(harp_ctx* c, int mode, int B, int S, float focal, int self_shadow, const float* verts,
+                          const float* normals, const float* cam_R, const float* cam_T, const float* light_R,
+                          const float* light_T, const float* light_pos, const float* amb, const float* texture,
+                          const float* normal_map, int texH, int texW, const float* fixed_lights, float* rgb, const float* gin,
+                          const float* mask, float weight, float* loss, const harp_shade_grads* grads, void* stream) {
+  HARP_REQUIRE(c && B > 0 && verts && normals && cam_R && cam_T && light_pos && amb && texture && normal_map,
+               HARP_ERR_INVALID, "harp_shade: null argument");
+  HARP_REQUIRE(c->has_uv, HARP_ERR_INVALID, "harp_shade: ctx was created without UV tables");
+  HARP_REQUIRE(mode >= 0 && mode <= 2, HARP_ERR_INVALID, "harp_shade: mode must be 0, 1 or 2");
+  HARP_REQUIRE(B <= c->maxB && S == c->S, HARP_ERR_CAPACITY, "harp_shade: call harp_ctx_reserve(B, S) first");
+  HARP_REQUIRE(!self_shadow || (light_R && light_T), HARP_ERR_INVALID, "harp_shade: light_R/light_T required for self_shadow");
+  HARP_REQUIRE(mode == 1 || rgb, HARP_ERR_INVALID, "harp_shade: rgb output required");
+  HARP_REQUIRE(mode == 0 || (gin && grads && grads->d_verts && grads->d_normals), HARP_ERR_INVALID,
+               "harp_shade: upstream gradient / target and d_verts, d_normals required");
+  HARP_REQUIRE(mode != 2 || (mask && loss), HARP_ERR_INVALID, "harp_shade: mask and loss required in fused mode");
+  harp_render_args r{};
+  r.verts = verts; r.normals = normals; r.cam_R = cam_R; r.cam_T = cam_T; r.light_R = light_R; r.light_T = light_T;
+  r.light_pos = light_pos; r.amb = amb; r.texture = texture; r.normal_map = normal_map; r.texH = texH; r.texW = texW;
+  r.self_shadow = self_shadow; r.rgb = rgb; r.y_true = gin; r.y_mask = mask; r.w_photo = weight; r.loss_photo = loss;
+  if (grads) r.grads = *grads;
+  RenderPlan p;
+  p.sil = false; p.shade_mode = mode; p.fixed_lights = fixed_lights;
+  return render_pass(c, B, S, focal, &r, p, (cudaStream_t)stream);
+}
+
+namespace {
 // backward of the light-view depth buffer (zbuf = sum_i b_i z_i at the stored face) over the non-empty light tiles only: the
 // PCF taps of the shading can only have touched pixels of tiles some face covers.  Four tiles per CTA round; the pixels with a
 // gradient are compacted in shared memory and then processed by full warps.
@@ -819,6 +913,8 @@ __global__ void __launch_bounds__(256) light_depth_bwd_tiles_kernel(harp_ctx c, 
   }
 }
 
+}  // namespace
+
 int harp_light_depth_bwd_tiles(harp_ctx* c, int B, int S, cudaStream_t st) {
   (void)B;
   const int cap = c->maxB * c->tiles;
@@ -838,7 +934,7 @@ int harp_light_depth_tiles(harp_ctx* c, int B, int S, bool zero_grad, cudaStream
   v.work = c->work + v.work_cap;
   v.work_ctl = c->work_ctl + 4;
   v.zbuf = c->light_zbuf; v.face = c->light_face; v.d_zbuf = zero_grad ? c->d_light_zbuf : nullptr;
-  tile_raster_kernel<false, false, false><<<HARP_SM_COUNT * HARP_PV_MINCTAS, NT, 0, st>>>(*c, v);
+  tile_raster_kernel<false, false, false, false><<<HARP_SM_COUNT * HARP_PV_MINCTAS, NT, 0, st>>>(*c, v);
   const int eg = (int)(((size_t)B * S * (S / 4) + 255) / 256);
   empty_tiles_kernel<true, false, false><<<eg, 256, 0, st>>>(B, S, c->bin_count + (size_t)c->maxB * c->tiles, v);
   HARP_LAUNCH_CHECK_N(2);

@@ -1,7 +1,6 @@
-// Projection, tile binning and the soft-silhouette render (forward, backward, fused L1 loss).
-// Replaces MeshRasterizer.transform + _C.rasterize_meshes (K=50) + sigmoid_alpha_blend and their autograd
-// (renderer/renderer_helper.py:37-58).  The reference materialises 28 B x 50 fragments per pixel
-// (367 MB per 512^2 frame); here a pixel's candidate faces live in shared memory and nothing but alpha is written.
+// Backward of the projection, the exact top-K silhouette pass for pixels the tile rasteriser (pixel.cu) defers, and the
+// fold of the padded gradient accumulators.  With pixel.cu this replaces MeshRasterizer.transform + _C.rasterize_meshes
+// (K=50) + sigmoid_alpha_blend and their autograd (renderer/renderer_helper.py:37-58).
 #include "raster.cuh"
 
 int harp_raster_setup(harp_ctx* c, int view, int B, int S, float focal, float radius, const float* verts, const float* R,
@@ -54,145 +53,6 @@ __global__ void __launch_bounds__(TPB) project_bwd_kernel(int B, int V, const fl
     if (i >= 9 && !d_T) continue;
     float s = block_sum(acc[i], red);
     if (threadIdx.x == 0 && s != 0.f) atomicAdd(i < 9 ? d_R + (size_t)b * 9 + i : d_T + (size_t)b * 3 + (i - 9), s);
-  }
-}
-
-// ---- soft silhouette -------------------------------------------------------------------------------------------------
-// MODE 0 forward; 1 backward with upstream g_alpha; 2 fused L1(target, alpha) loss (forward + backward in one pass).
-// The +-1/3 px band pairs that need the full distance computation are a few percent of all (pixel, face) candidates but
-// sit in nearly every face a warp visits, so evaluating them in the pixel loop leaves ~6 of 32 lanes active.  Instead the
-// convergent classification pass queues them per tile in shared memory and all 64 threads drain the queue.
-constexpr int QCAP = 512;
-
-template <int MODE>
-__global__ void __launch_bounds__(HARP_TILE* HARP_TILE) sil_kernel(harp_ctx c, int S, int K, float sigma, float blur, float radius,
-                                                                   const float* __restrict__ ndc_all,
-                                                                   const int32_t* __restrict__ bin_count,
-                                                                   const int32_t* __restrict__ bin_start,
-                                                                   const int32_t* __restrict__ bin_list, float* __restrict__ alpha,
-                                                                   const float* __restrict__ gin, float gscale, float inv_n,
-                                                                   float* __restrict__ loss, float* __restrict__ d_ndc_all) {
-  constexpr int NT = HARP_TILE * HARP_TILE;
-  __shared__ FaceRec faces[CHUNK];
-  __shared__ float red[32];
-  __shared__ unsigned char q_pix[QCAP], q_face[QCAP], q_edge[QCAP];  // q_edge == 255: pair did not pass
-  __shared__ float q_sd[QCAP], q_t[QCAP];
-  __shared__ int q_n, any_bwd;
-  __shared__ float s_g[NT], s_prod[NT];
-  __shared__ unsigned char s_need[NT];
-  int b = blockIdx.z, tw = S / HARP_TILE, tid = threadIdx.x;
-  int tile = blockIdx.y * tw + blockIdx.x;
-  int lx = tid % HARP_TILE, ly = tid / HARP_TILE;
-  int col = blockIdx.x * HARP_TILE + lx, row = blockIdx.y * HARP_TILE + ly;
-  size_t pix = ((size_t)b * S + row) * S + col;
-  size_t tglob = (size_t)b * tw * tw + tile;
-  int n = bin_count[tglob];
-  int start = bin_start[tglob];
-  if (start + n > c.bin_cap) n = max(0, (int)c.bin_cap - start);
-  const int32_t* list = bin_list + (size_t)b * c.bin_cap + start;
-  const float* ndc = ndc_all + (size_t)b * c.V * 3;
-  float px = pix_to_ndc(col, S), py = pix_to_ndc(row, S);
-  float prod = 1.f;
-  int nzero = 0, npass = 0, ncand = 0;
-  bool q_overflow = false;
-  const float sat = 17.5f * sigma;
-  if (tid == 0) { any_bwd = 0; q_n = 0; }
-  for (int base = 0; base < n; base += CHUNK) {
-    int m = min(CHUNK, n - base);
-    __syncthreads();
-    if (tid < m) load_face(c, ndc, list[base + tid], radius, faces[tid]);
-    if (tid == 0) q_n = 0;
-    __syncthreads();
-    // A: convergent classification; a pixel with one exactly-zero factor is final (alpha = 1, zero gradient)
-    {
-      for (int i = 0; i < m; ++i) {
-        int cls = classify_pair<true>(faces[i], px, py, blur, sat);
-        if (cls == PAIR_REJECT) continue;
-        ++ncand;  // upper bound on the faces PyTorch3D would consider for this pixel (exact top-K decision below)
-        if (nzero > 0) continue;
-        if (cls == PAIR_SATURATED) { ++npass; ++nzero; continue; }
-        int slot = atomicAdd(&q_n, 1);
-        if (slot < QCAP) {
-          q_pix[slot] = (unsigned char)tid; q_face[slot] = (unsigned char)i;
-        } else {  // queue full (never seen at the reference's scales): evaluate in place
-          q_overflow = true;
-          PairEval e;
-          eval_pair_full<true, true>(faces[i], px, py, blur, e);
-          if (!e.pass) continue;
-          ++npass;
-          float om = 1.f - 1.f / (1.f + expf(fdiv(e.inside ? -e.dist : e.dist, sigma)));
-          if (om == 0.f) ++nzero; else prod *= om;
-        }
-      }
-    }
-    __syncthreads();
-    // B: drain the queue with every thread busy
-    int qn = min(q_n, QCAP);
-    for (int s = tid; s < qn; s += NT) {
-      int p = q_pix[s];
-      float ppx = pix_to_ndc(blockIdx.x * HARP_TILE + (p % HARP_TILE), S), ppy = pix_to_ndc(blockIdx.y * HARP_TILE + (p / HARP_TILE), S);
-      PairEval e;
-      eval_pair_full<true, true>(faces[q_face[s]], ppx, ppy, blur, e);
-      if (e.pass) { q_sd[s] = e.inside ? -e.dist : e.dist; q_edge[s] = (unsigned char)e.edge; q_t[s] = e.t; }
-      else q_edge[s] = 255;
-    }
-    __syncthreads();
-    // C: every pixel folds its own results in queue (= face list) order
-    if (nzero == 0) {
-      for (int s = 0; s < qn; ++s) {
-        if (q_pix[s] != tid || q_edge[s] == 255) continue;
-        ++npass;
-        float om = 1.f - 1.f / (1.f + expf(fdiv(q_sd[s], sigma)));  // 1 - sigmoid(-sd/sigma)
-        if (om == 0.f) { ++nzero; break; }
-        prod *= om;
-      }
-    }
-  }
-  float a = nzero > 0 ? 1.f : 1.f - prod;
-  // more candidates than faces_per_pixel: PyTorch3D keeps only the K nearest in depth -> exact per-pixel kernel
-  const bool deferred = ncand > K;
-  if (deferred) sil_defer_overflow(c, (int)pix);
-  if (MODE != 1 && !deferred) alpha[pix] = a;
-  if (MODE == 0) return;
-  float g;  // dL/d alpha
-  if (MODE == 1) {
-    g = deferred ? 0.f : gin[pix];
-  } else {
-    float tgt = gin[pix];
-    float diff = deferred ? 0.f : a - tgt;
-    g = diff > 0.f ? gscale : (diff < 0.f ? -gscale : 0.f);
-    float s = block_sum(fabsf(diff), red);
-    if (tid == 0 && s != 0.f) atomicAdd(loss, s * inv_n);
-  }
-  bool need = (g != 0.f) && nzero == 0 && prod > 0.f && npass > 0;
-  if (need) any_bwd = 1;
-  s_g[tid] = g; s_prod[tid] = prod; s_need[tid] = need ? 1 : 0;
-  int any_overflow = __syncthreads_or(q_overflow ? 1 : 0);
-  if (!any_bwd) return;
-  float* d_ndc = d_ndc_all + (size_t)b * c.V * 4;
-  if (n <= CHUNK && !any_overflow) {
-    // single-chunk tile (the common case): the queue and the staged faces of pass 1 are still valid
-    int qn = min(q_n, QCAP);
-    for (int s = tid; s < qn; s += NT) {
-      int p = q_pix[s];
-      if (!s_need[p] || q_edge[s] == 255) continue;
-      float ppx = pix_to_ndc(blockIdx.x * HARP_TILE + (p % HARP_TILE), S), ppy = pix_to_ndc(blockIdx.y * HARP_TILE + (p / HARP_TILE), S);
-      sil_pair_gradient(c, faces[q_face[s]], ppx, ppy, q_sd[s], q_edge[s], q_t[s], s_g[p], s_prod[p], sigma, d_ndc);
-    }
-    return;
-  }
-  for (int base = 0; base < n; base += CHUNK) {  // generic path: re-stage every chunk, pixel-parallel
-    int m = min(CHUNK, n - base);
-    __syncthreads();
-    if (tid < m) load_face(c, ndc, list[base + tid], radius, faces[tid]);
-    __syncthreads();
-    if (!need) continue;
-    for (int i = 0; i < m; ++i) {
-      PairEval e;
-      eval_pair<true, true>(faces[i], px, py, blur, sat, e);
-      if (!e.pass || e.saturated) continue;
-      sil_pair_gradient(c, faces[i], px, py, e.inside ? -e.dist : e.dist, e.edge, e.t, g, prod, sigma, d_ndc);
-    }
   }
 }
 
@@ -324,43 +184,5 @@ int harp_project_bwd(harp_ctx* c, int B, int S, float focal, const float* verts,
   dim3 grid((c->V + TPB - 1) / TPB, B);
   project_bwd_kernel<<<grid, TPB, 0, st>>>(B, c->V, verts, R, T, focal, 0.5f * (float)S, d_ndc, d_verts, d_R, d_T);
   HARP_LAUNCH_CHECK();
-  return HARP_OK;
-}
-
-extern "C" int harp_silhouette(harp_ctx* c, int mode, int B, int S, float focal, float sigma, int faces_per_pixel, const float* verts,
-                               const float* R, const float* T, float* alpha, const float* gin, float weight, float* loss,
-                               float* d_verts, float* d_R, float* d_T, void* stream) {
-  HARP_REQUIRE(c && B > 0 && verts && R && T, HARP_ERR_INVALID, "harp_silhouette: null argument");
-  HARP_REQUIRE(mode >= 0 && mode <= 2, HARP_ERR_INVALID, "harp_silhouette: mode must be 0, 1 or 2");
-  HARP_REQUIRE(B <= c->maxB && S == c->S, HARP_ERR_CAPACITY, "harp_silhouette: call harp_ctx_reserve(B, S) first");
-  HARP_REQUIRE(mode == 1 || alpha, HARP_ERR_INVALID, "harp_silhouette: alpha output required");
-  HARP_REQUIRE(mode == 0 || gin, HARP_ERR_INVALID, "harp_silhouette: upstream gradient / target required");
-  HARP_REQUIRE(mode != 2 || loss, HARP_ERR_INVALID, "harp_silhouette: loss output required in fused mode");
-  cudaStream_t st = (cudaStream_t)stream;
-  // blur_radius = ln(1/1e-4 - 1) * sigma (renderer_helper.py:46), evaluated in double like the reference's numpy call
-  double blur_d = 9.210240366975849 * (double)sigma;
-  float blur = (float)blur_d, radius = (float)sqrt(blur_d);
-  int rc;
-  if ((rc = harp_raster_setup(c, 0, B, S, focal, radius, verts, R, T, st)) != HARP_OK) return rc;
-  if (mode != 0) HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_cam, 0, (size_t)B * c->V * 4 * sizeof(float), st));
-  HARP_CHECK_CUDA(cudaMemsetAsync(c->ovf_count, 0, sizeof(int32_t), st));
-  const int K = faces_per_pixel > 0 ? faces_per_pixel : 50;
-  dim3 grid(S / HARP_TILE, S / HARP_TILE, B);
-  float inv_n = 1.f / ((float)B * (float)S * (float)S);
-  float gscale = weight * inv_n;
-  const int32_t *cnt = c->bin_count, *bst = c->bin_start, *lst = c->bin_list;
-  harp_prof_begin(c, 0, st);
-  if (mode == 0)
-    sil_kernel<0><<<grid, HARP_TILE * HARP_TILE, 0, st>>>(*c, S, K, sigma, blur, radius, c->ndc_cam, cnt, bst, lst, alpha, nullptr, 0.f, 0.f, nullptr, nullptr);
-  else if (mode == 1)
-    sil_kernel<1><<<grid, HARP_TILE * HARP_TILE, 0, st>>>(*c, S, K, sigma, blur, radius, c->ndc_cam, cnt, bst, lst, alpha, gin, 0.f, 0.f, nullptr, c->d_ndc_cam);
-  else
-    sil_kernel<2><<<grid, HARP_TILE * HARP_TILE, 0, st>>>(*c, S, K, sigma, blur, radius, c->ndc_cam, cnt, bst, lst, alpha, gin, gscale, inv_n, loss, c->d_ndc_cam);
-  harp_prof_end(c, 0, st);
-  HARP_LAUNCH_CHECK();
-  if ((rc = harp_sil_topk(c, mode, S, K, sigma, blur, radius, alpha, gin, gscale, inv_n, loss, st)) != HARP_OK) return rc;
-  if (mode != 0) {
-    if ((rc = harp_project_bwd(c, B, S, focal, verts, R, T, c->d_ndc_cam, d_verts, d_R, d_T, st)) != HARP_OK) return rc;
-  }
   return HARP_OK;
 }

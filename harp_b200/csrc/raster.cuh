@@ -94,34 +94,10 @@ __device__ __forceinline__ int classify_pair(const FaceRec& f, float px, float p
   return PAIR_FULL;
 }
 
-// Same classification, additionally reporting strict-inside and q = 1 / (perspective-correct depth) for inside pairs:
+// The fast inverse depth q = 1 / (perspective-correct depth) the tile rasteriser orders inside pairs by (fast_inv_depth below):
 // with w_i = e_i / area and b_i ~ w_i / z_i, pz = sum b_i z_i = sum(w_i) / sum(w_i / z_i) = sum(e_i) / sum(e_i / z_i) (the
 // screen-space weights of a sliver face need not sum to 1 in fp32, hence the normalisation).  q orders the faces covering a pixel
 // (nearest = largest q); the winner's barycentrics and depth are then recomputed with the exact operation sequence.
-// `exact_needed` is set for faces with a vertex behind the camera, where the sign argument does not hold.
-template <bool NEED_DIST>
-__device__ __forceinline__ int classify_pair_vis(const FaceRec& f, float px, float py, float blur, float sat, bool& inside,
-                                                 float& q, bool& exact_needed) {
-  inside = false;
-  exact_needed = false;
-  if (px > f.xmax || px < f.xmin || py > f.ymax || py < f.ymin) return PAIR_REJECT;
-  if (!(f.zmin > 0.f)) { exact_needed = true; return PAIR_FULL; }
-  float e0 = edge_fn(px, py, f.x1, f.y1, f.x2, f.y2);
-  float e1 = edge_fn(px, py, f.x2, f.y2, f.x0, f.y0);
-  float e2 = edge_fn(px, py, f.x0, f.y0, f.x1, f.y1);
-  bool pos = f.area > 0.f;
-  bool i0 = pos ? e0 > 0.f : e0 < 0.f, i1 = pos ? e1 > 0.f : e1 < 0.f, i2 = pos ? e2 > 0.f : e2 < 0.f;
-  if (i0 && i1 && i2) {
-    inside = true;
-    q = __fdividef(e0 * f.iz0 + e1 * f.iz1 + e2 * f.iz2, e0 + e1 + e2);  // = sum(w_i/z_i) / sum(w_i): independent of the area
-    if (NEED_DIST && e0 * e0 >= sat * f.l12 && e1 * e1 >= sat * f.l20 && e2 * e2 >= sat * f.l01) return PAIR_SATURATED;
-    return NEED_DIST ? PAIR_FULL : PAIR_SATURATED;
-  }
-  if (!NEED_DIST) return PAIR_REJECT;
-  float far = 1.001f * blur;
-  if ((!i0 && e0 * e0 >= far * f.l12) || (!i1 && e1 * e1 >= far * f.l20) || (!i2 && e2 * e2 >= far * f.l01)) return PAIR_REJECT;
-  return PAIR_FULL;
-}
 
 // CLIP: clip_barycentric_coords (silhouette); blur: blur_radius (squared NDC).  The bounding-box test is classify_pair's.
 template <bool CLIP, bool NEED_DIST, typename F>
@@ -219,7 +195,7 @@ struct __align__(16) FaceTile {
   int fid;
   // pixel rectangle of the inflated bbox (0.01 px guard; the exact float bbox test still runs per pair): columns
   // jlo | jhi << 16, rows ilo | ihi << 16; jlo > jhi marks a face the rasteriser skips outright (behind the camera, zero area,
-  // off screen).  Written by the per-frame setup kernel (setup.cu), which owns the binning; zero when staged by stage_face.
+  // off screen).  Written by the per-frame setup kernel (setup.cu), which owns the binning; 
   int cols, rows;
   int pad0, pad1;
 };  // 144 B = 9 x 16 B: consecutive records start 4 banks apart, so the 2-3 records a warp touches per LDS.128 do not collide.
@@ -256,14 +232,8 @@ __device__ __forceinline__ void make_face_record(float x0, float y0, float z0, f
   f.cols = f.rows = f.pad0 = f.pad1 = 0;
 }
 
-__device__ __forceinline__ void stage_face(const harp_ctx& c, const float* ndc, int fid, float radius, FaceTile& f) {
-  const int32_t* fv = c.faces + (size_t)fid * 3;
-  const float *a = ndc + (size_t)fv[0] * 3, *b = ndc + (size_t)fv[1] * 3, *d = ndc + (size_t)fv[2] * 3;
-  make_face_record(a[0], a[1], a[2], b[0], b[1], b[2], d[0], d[1], d[2], fid, radius, f);
-}
-
-// Classification of one (pixel, face) pair against a staged FaceTile; same decisions as classify_pair_vis (the exactness
-// argument is above classify_pair): returns PAIR_REJECT / PAIR_SATURATED / PAIR_FULL, or PAIR_EXACT for a face with a
+// Classification of one (pixel, face) pair against a staged FaceTile; same decisions as classify_pair (the exactness
+// argument is above it): returns PAIR_REJECT / PAIR_SATURATED / PAIR_FULL, or PAIR_EXACT for a face with a
 // vertex behind the camera.  `inside` = strict inside as PyTorch3D's bit-exact edge functions decide it; t[] = signed edge
 // functions (for the fast inverse depth).  With NEED_DIST = false (visibility only) inside pairs report PAIR_SATURATED, all
 // others REJECT.  `far` must be >= 1.02 blur and `sat` >= 17.5 sigma (margins, see FaceTile).
@@ -307,27 +277,6 @@ __device__ __forceinline__ int classify_fast(const FaceTile& f, float px, float 
 // fast inverse depth of an inside pair: sum(w_i / z_i) / sum(w_i) with w_i ~ e_i (independent of the area)
 __device__ __forceinline__ float fast_inv_depth(const FaceTile& f, float e0, float e1, float e2) {
   return __fdividef(e0 * f.iz0 + e1 * f.iz1 + e2 * f.iz2, e0 + e1 + e2);
-}
-
-// Visibility candidate update.  The fast inverse depth q orders candidates; when two are within 1e-5 relative (touching
-// or interpenetrating surfaces) the decision is taken with the exact perspective-correct depth, ties to the lower face
-// id — the order PyTorch3D's K=1 insertion produces.
-__device__ __forceinline__ float exact_pz(const harp_ctx& c, const float* ndc, int fid, float px, float py) {
-  FaceRec g;
-  load_face(c, ndc, fid, 0.f, g);
-  PairEval e;
-  eval_pair_full<false, false>(g, px, py, 0.f, e);
-  return e.pass ? e.pz : 3.4e38f;
-}
-
-__device__ __forceinline__ void vis_update(const harp_ctx& c, const float* ndc, float px, float py, int fid, float q, int& best,
-                                           float& best_q) {
-  if (best < 0) { best = fid; best_q = q; return; }
-  float tol = 1e-5f * fmaxf(q, best_q);
-  if (q > best_q + tol) { best = fid; best_q = q; return; }
-  if (q < best_q - tol) return;
-  float pz_new = exact_pz(c, ndc, fid, px, py), pz_old = exact_pz(c, ndc, best, px, py);
-  if (pz_new < pz_old || (pz_new == pz_old && fid < best)) { best = fid; best_q = q; }
 }
 
 // Backward of one silhouette factor: alpha = 1 - prod_k(1 - p_k), p = sigmoid(-sd/sigma)  =>  d alpha / d sd_k = -prod p_k / sigma

@@ -33,149 +33,6 @@ __global__ void __launch_bounds__(256) pack_tex_kernel(size_t n, const float* __
 
 constexpr int NT = HARP_TILE * HARP_TILE;
 
-__device__ __forceinline__ void nearest_face(const harp_ctx& c, const float* ndc, const int32_t* list, int n, float px,
-                                             float py, FaceTile* faces, Hit& h) {
-  // ordering by the fast inverse depth q (raster.cuh: classify_fast); the winner is re-evaluated exactly below
-  int best = -1;
-  float best_q = 0.f;
-  for (int base = 0; base < n; base += CHUNK) {
-    int m = min(CHUNK, n - base);
-    __syncthreads();
-    if (threadIdx.x < m) stage_face(c, ndc, list[base + threadIdx.x], 0.f, faces[threadIdx.x]);
-    __syncthreads();
-    for (int i = 0; i < m; ++i) {
-      const FaceTile& f = faces[i];
-      bool inside;
-      float e0, e1, e2, q;
-      bool inb = in_face_bbox(f, px, py);
-      if (!__any_sync(0xffffffffu, inb)) continue;  // the face's bbox misses this warp's 8x4 half of the tile
-      int cls = classify_fast<false>(f, px, py, 0.f, 0.f, inb, inside, e0, e1, e2);
-      if (cls == PAIR_REJECT) continue;
-      if (cls == PAIR_EXACT) {
-        PairEval e;
-        eval_pair_full<false, false>(f, px, py, 0.f, e);
-        inside = e.pass;
-        q = e.pass ? 1.f / e.pz : 0.f;
-      } else {
-        q = fast_inv_depth(f, e0, e1, e2);
-      }
-      if (inside) vis_update(c, ndc, px, py, f.fid, q, best, best_q);
-    }
-  }
-  h.fid = best;
-  h.pz = 3.4e38f;
-  if (best >= 0) {
-    FaceRec f;
-    load_face(c, ndc, best, 0.f, f);
-    PairEval e;
-    eval_pair_full<false, false>(f, px, py, 0.f, e);
-    if (e.pass) { h.pz = e.pz; h.b0 = e.b0; h.b1 = e.b1; h.b2 = e.b2; h.w0 = e.w0; h.w1 = e.w1; h.w2 = e.w2; }
-    else h.fid = -1;
-  }
-}
-
-// ---- light-view depth pass (renderer_helper.py:344): nearest z + face id per light pixel ------------------------------
-__global__ void __launch_bounds__(NT) light_depth_kernel(harp_ctx c, int S, const float* __restrict__ ndc_all,
-                                                         const int32_t* __restrict__ bin_count, const int32_t* __restrict__ bin_start,
-                                                         const int32_t* __restrict__ bin_list, float* __restrict__ zbuf,
-                                                         int32_t* __restrict__ face) {
-  __shared__ FaceTile faces[CHUNK];
-  int b = blockIdx.z, tw = S / HARP_TILE;
-  int lx = threadIdx.x % HARP_TILE, ly = threadIdx.x / HARP_TILE;
-  int col = blockIdx.x * HARP_TILE + lx, row = blockIdx.y * HARP_TILE + ly;
-  size_t pix = ((size_t)b * S + row) * S + col;
-  size_t tglob = (size_t)b * tw * tw + blockIdx.y * tw + blockIdx.x;
-  int n = bin_count[tglob];
-  if (n == 0) {  // empty light tile
-    zbuf[pix] = -1.f;
-    face[pix] = -1;
-    return;
-  }
-  int start = bin_start[tglob];
-  if (start + n > c.bin_cap) n = max(0, (int)c.bin_cap - start);
-  Hit h;
-  nearest_face(c, ndc_all + (size_t)b * c.V * 3, bin_list + (size_t)b * c.bin_cap + start, n, pix_to_ndc(col, S),
-               pix_to_ndc(row, S), faces, h);
-  zbuf[pix] = h.fid >= 0 ? h.pz : -1.f;
-  face[pix] = h.fid;
-}
-
-// backward of the light-view depth buffer: zbuf = sum_i b_i z_i at the stored face.
-// The gradient image is sparse (only light pixels some PCF tap touched): each CTA scans 1024 pixels with 16-byte loads,
-// compacts the active ones into shared memory and then processes them with full warps.
-constexpr int LDB_THREADS = 256, LDB_PIX = 4 * LDB_THREADS;
-
-__global__ void __launch_bounds__(LDB_THREADS) light_depth_bwd_kernel(harp_ctx c, int B, int S, const float* __restrict__ ndc_all,
-                                                                      const int32_t* __restrict__ face,
-                                                                      const float* __restrict__ d_zbuf,
-                                                                      float* __restrict__ d_ndc_all) {
-  __shared__ unsigned short s_idx[LDB_PIX];
-  __shared__ int s_n;
-  if (threadIdx.x == 0) s_n = 0;
-  __syncthreads();
-  const size_t total = (size_t)B * S * S, base = (size_t)blockIdx.x * LDB_PIX;  // S*S is a multiple of 4: whole float4s
-  size_t p0 = base + (size_t)threadIdx.x * 4;
-  if (p0 < total) {
-    float4 g4 = *reinterpret_cast<const float4*>(d_zbuf + p0);
-    float gs[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (gs[k] != 0.f) s_idx[atomicAdd(&s_n, 1)] = (unsigned short)(threadIdx.x * 4 + k);
-  }
-  __syncthreads();
-  const int n = s_n;
-  for (int s = threadIdx.x; s < n; s += LDB_THREADS) {
-    size_t pix = base + s_idx[s];
-    int fid = face[pix];
-    if (fid < 0) continue;
-    float g = d_zbuf[pix];
-    int b = (int)(pix / ((size_t)S * S));
-    int rem = (int)(pix % ((size_t)S * S));
-    int row = rem / S, col = rem % S;
-    const float* ndc = ndc_all + (size_t)b * c.V * 3;
-    FaceRec f;
-    load_face(c, ndc, fid, 0.f, f);
-    float px = pix_to_ndc(col, S), py = pix_to_ndc(row, S);
-    PairEval e;
-    eval_pair<false, false>(f, px, py, 0.f, 0.f, e);
-    if (!e.pass) continue;
-    Hit h; h.fid = fid; h.pz = e.pz; h.b0 = e.b0; h.b1 = e.b1; h.b2 = e.b2; h.w0 = e.w0; h.w1 = e.w1; h.w2 = e.w2;
-    float gb[3] = {g * f.z0, g * f.z1, g * f.z2};
-    float gz[3] = {g * e.b0, g * e.b1, g * e.b2};
-    bary_backward(tri_from_ndc(ndc, f.v0, f.v1, f.v2), f.v0, f.v1, f.v2, px, py, h, gb, gz, d_ndc_all + (size_t)b * c.V * 4);
-  }
-}
-
-// MODE 0 forward; 1 backward with upstream g_rgb; 2 fused photometric L1 on the eroded mask
-template <int MODE>
-__global__ void __launch_bounds__(NT, (MODE == 0 ? 16 : 10)) shade_kernel(harp_ctx c, ShadeArgs a) {
-  __shared__ FaceTile faces[CHUNK];
-  __shared__ float red[32];
-  int b = blockIdx.z, S = a.S, tw = S / HARP_TILE;
-  int lx = threadIdx.x % HARP_TILE, ly = threadIdx.x / HARP_TILE;
-  int col = blockIdx.x * HARP_TILE + lx, row = blockIdx.y * HARP_TILE + ly;
-  size_t pix = ((size_t)b * S + row) * S + col;
-  size_t tglob = (size_t)b * tw * tw + blockIdx.y * tw + blockIdx.x;
-  int n = a.bin_count[tglob], start = a.bin_start[tglob];
-  if (start + n > c.bin_cap) n = max(0, (int)c.bin_cap - start);
-  const float* ndc = a.ndc_cam + (size_t)b * c.V * 3;
-  float px = pix_to_ndc(col, S), py = pix_to_ndc(row, S);
-  Hit h;
-  nearest_face(c, ndc, a.bin_list + (size_t)b * c.bin_cap + start, n, px, py, faces, h);
-
-  ShadeOut o;
-  shade_pixel<MODE>(c, a, b, pix, px, py, h, o);
-  if (MODE != 1) st3(a.rgb + pix * 3, o.rgb);
-  if (MODE == 0) return;
-  if (MODE == 2) {
-    float s = block_sum(o.loss_abs, red);
-    if (threadIdx.x == 0 && s != 0.f) atomicAdd(a.loss, s * a.inv_n);
-  }
-  int any = __syncthreads_or(o.active ? 1 : 0);
-  if (!any) return;
-  shade_flush_frame_scalars(a, b, o.frame);
-}
-
 // ---- normal renderer: K nearest faces per pixel, normal-map-perturbed normals as colours, softmax_rgb_blend ------------
 // (renderer_helper.py:85-101, 216-301; evaluation pass, forward only)
 constexpr int NORMAL_KMAX = 16;
@@ -283,101 +140,5 @@ int harp_tex_prepare(harp_ctx* c, const float* texture, const float* normal_map,
   pack_tex_kernel<<<(int)((ntex + 255) / 256), 256, 0, st>>>(ntex, texture, normal_map, reinterpret_cast<float4*>(c->tex4),
                                                              reinterpret_cast<float4*>(c->tex4) + ntex);
   HARP_LAUNCH_CHECK();
-  return HARP_OK;
-}
-
-// light-view depth pass / its backward on the ctx scratch (projected light-view verts and bins must be current)
-int harp_light_depth(harp_ctx* c, int B, int S, cudaStream_t st) {
-  dim3 grid(S / HARP_TILE, S / HARP_TILE, B);
-  size_t voff = (size_t)c->maxB * c->tiles;
-  light_depth_kernel<<<grid, NT, 0, st>>>(*c, S, c->ndc_light, c->bin_count + voff, c->bin_start + voff,
-                                          c->bin_list + (size_t)c->maxB * c->bin_cap, c->light_zbuf, c->light_face);
-  HARP_LAUNCH_CHECK();
-  return HARP_OK;
-}
-
-int harp_light_depth_bwd(harp_ctx* c, int B, int S, cudaStream_t st) {
-  size_t npx = (size_t)B * S * S;
-  light_depth_bwd_kernel<<<(int)((npx + LDB_PIX - 1) / LDB_PIX), LDB_THREADS, 0, st>>>(*c, B, S, c->ndc_light, c->light_face, c->d_light_zbuf,
-                                                                   c->d_ndc_light);
-  HARP_LAUNCH_CHECK();
-  return HARP_OK;
-}
-
-extern "C" int harp_shade(harp_ctx* c, int mode, int B, int S, float focal, int self_shadow, const float* verts,
-                          const float* normals, const float* cam_R, const float* cam_T, const float* light_R,
-                          const float* light_T, const float* light_pos, const float* amb, const float* texture,
-                          const float* normal_map, int texH, int texW, const float* fixed_lights, float* rgb, const float* gin,
-                          const float* mask, float weight, float* loss, const harp_shade_grads* grads, void* stream) {
-  HARP_REQUIRE(c && B > 0 && verts && normals && cam_R && cam_T && light_pos && amb && texture && normal_map,
-               HARP_ERR_INVALID, "harp_shade: null argument");
-  HARP_REQUIRE(c->has_uv, HARP_ERR_INVALID, "harp_shade: ctx was created without UV tables");
-  HARP_REQUIRE(mode >= 0 && mode <= 2, HARP_ERR_INVALID, "harp_shade: mode must be 0, 1 or 2");
-  HARP_REQUIRE(B <= c->maxB && S == c->S, HARP_ERR_CAPACITY, "harp_shade: call harp_ctx_reserve(B, S) first");
-  HARP_REQUIRE(!self_shadow || (light_R && light_T), HARP_ERR_INVALID, "harp_shade: light_R/light_T required for self_shadow");
-  HARP_REQUIRE(mode == 1 || rgb, HARP_ERR_INVALID, "harp_shade: rgb output required");
-  HARP_REQUIRE(mode == 0 || (gin && grads && grads->d_verts && grads->d_normals), HARP_ERR_INVALID,
-               "harp_shade: upstream gradient / target and d_verts, d_normals required");
-  HARP_REQUIRE(mode != 2 || (mask && loss), HARP_ERR_INVALID, "harp_shade: mask and loss required in fused mode");
-  cudaStream_t st = (cudaStream_t)stream;
-  int rc;
-  size_t npx = (size_t)B * S * S;
-  if ((rc = harp_raster_setup(c, 0, B, S, focal, 0.f, verts, cam_R, cam_T, st)) != HARP_OK) return rc;
-  dim3 grid(S / HARP_TILE, S / HARP_TILE, B);
-  if (self_shadow) {
-    if ((rc = harp_raster_setup(c, 1, B, S, focal, 0.f, verts, light_R, light_T, st)) != HARP_OK) return rc;
-    size_t voff = (size_t)c->maxB * c->tiles;
-    light_depth_kernel<<<grid, NT, 0, st>>>(*c, S, c->ndc_light, c->bin_count + voff, c->bin_start + voff,
-                                            c->bin_list + (size_t)c->maxB * c->bin_cap, c->light_zbuf, c->light_face);
-    HARP_LAUNCH_CHECK();
-  }
-  ShadeArgs a{};
-  a.B = B; a.S = S; a.self_shadow = self_shadow; a.texH = texH; a.texW = texW; a.focal = focal;
-  if (fixed_lights) { a.fixed_lights = 1; a.ka = fixed_lights[0]; a.kd = fixed_lights[1]; a.ks = fixed_lights[2]; }
-  a.inv_n = 1.f / ((float)B * (float)S * (float)S * 3.f);
-  a.gscale = weight * a.inv_n;
-  a.verts = verts; a.normals = normals; a.ndc_cam = c->ndc_cam; a.light_R = light_R ? light_R : cam_R;
-  a.light_T = light_T ? light_T : cam_T; a.light_pos = light_pos; a.amb = amb;
-  a.light_zbuf = c->light_zbuf; a.bin_count = c->bin_count; a.bin_start = c->bin_start; a.bin_list = c->bin_list;
-  a.rgb = rgb; a.gin = gin; a.mask = mask; a.loss = loss;
-  size_t ntex = (size_t)texH * texW;
-  if ((rc = harp_tex_prepare(c, texture, normal_map, texH, texW, st)) != HARP_OK) return rc;
-  a.tex4 = reinterpret_cast<const float4*>(c->tex4); a.nm4 = a.tex4 + ntex;
-  if (mode != 0) {
-    size_t nv4 = (size_t)B * c->V * 4 * sizeof(float);
-    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_cam, 0, nv4, st));
-    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_verts4, 0, nv4, st));
-    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_normals4, 0, nv4, st));
-    HARP_CHECK_CUDA(cudaMemsetAsync(c->d_tex4, 0, 2 * ntex * 4 * sizeof(float), st));
-    if (self_shadow) {
-      HARP_CHECK_CUDA(cudaMemsetAsync(c->d_ndc_light, 0, nv4, st));
-      HARP_CHECK_CUDA(cudaMemsetAsync(c->d_light_zbuf, 0, npx * sizeof(float), st));
-    }
-    a.d_ndc_cam = c->d_ndc_cam; a.d_verts = c->d_verts4; a.d_normals = c->d_normals4;
-    a.d_light_R = grads->d_light_R; a.d_light_T = grads->d_light_T; a.d_light_pos = grads->d_light_pos;
-    a.d_amb = grads->d_amb; a.d_texture = c->d_tex4; a.d_normal_map = c->d_tex4 + ntex * 4;
-    a.d_light_zbuf = c->d_light_zbuf;
-  }
-  harp_prof_begin(c, 1, st);
-  if (mode == 0) shade_kernel<0><<<grid, NT, 0, st>>>(*c, a);
-  else if (mode == 1) shade_kernel<1><<<grid, NT, 0, st>>>(*c, a);
-  else shade_kernel<2><<<grid, NT, 0, st>>>(*c, a);
-  harp_prof_end(c, 1, st);
-  HARP_LAUNCH_CHECK();
-  if (mode != 0) {
-    if ((rc = harp_fold4((size_t)B * c->V, c->d_verts4, grads->d_verts, st)) != HARP_OK) return rc;
-    if ((rc = harp_fold4((size_t)B * c->V, c->d_normals4, grads->d_normals, st)) != HARP_OK) return rc;
-    if (grads->d_texture && (rc = harp_fold4(ntex, c->d_tex4, grads->d_texture, st)) != HARP_OK) return rc;
-    if (grads->d_normal_map && (rc = harp_fold4(ntex, c->d_tex4 + ntex * 4, grads->d_normal_map, st)) != HARP_OK) return rc;
-    if (self_shadow) {
-      light_depth_bwd_kernel<<<(int)((npx + LDB_PIX - 1) / LDB_PIX), LDB_THREADS, 0, st>>>(*c, B, S, c->ndc_light, c->light_face, c->d_light_zbuf,
-                                                                       c->d_ndc_light);
-      HARP_LAUNCH_CHECK();
-      if ((rc = harp_project_bwd(c, B, S, focal, verts, light_R, light_T, c->d_ndc_light, grads->d_verts, grads->d_light_R,
-                                 grads->d_light_T, st)) != HARP_OK) return rc;
-    }
-    if ((rc = harp_project_bwd(c, B, S, focal, verts, cam_R, cam_T, c->d_ndc_cam, grads->d_verts, grads->d_cam_R,
-                               grads->d_cam_T, st)) != HARP_OK) return rc;
-  }
   return HARP_OK;
 }

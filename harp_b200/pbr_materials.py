@@ -1,6 +1,6 @@
 """`renderer/pbr_materials.py:PBRMaterials` at the call boundary: a bag of material constants + the normal-map texture.
 
-The TBN perturbation itself (`compute_tangent` 58-77, `apply_normal_map` 82-124) runs inside `shade_kernel`
+The TBN perturbation itself (`compute_tangent` 58-77, `apply_normal_map` 82-124) runs inside `shade_deferred_kernel`
 (`harp_b200/csrc/shade.cu`); this class only carries what `render_image*` hands to the renderer."""
 import torch
 
