@@ -24,7 +24,11 @@ namespace {
 #ifndef HARP_SHADE_GRID
 #define HARP_SHADE_GRID 96
 #endif
-constexpr int CHUNK = 32;   // faces staged per bulk-copy round (one lane of warp 0 per face)
+#ifndef HARP_PV_CHUNK
+#define HARP_PV_CHUNK 32
+#endif
+constexpr int CHUNK = HARP_PV_CHUNK;   // faces staged per bulk-copy round (one lane of warp 0 per face: at most 32)
+static_assert(CHUNK >= 8 && CHUNK <= 32, "one lane of warp 0 per staged face");
 constexpr int NT = HARP_TILE * HARP_TILE;
 constexpr int QCAP = 256;   // band pairs of one tile (all chunks); a tile that needs more goes to the exact per-pixel kernel
 constexpr int TIECAP = 128; // visibility candidates within 1e-5 of each other (resolved with the exact depth)
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
   __shared__ float s_om[SIL ? QCAP : 1];
   __shared__ int s_tie[TIECAP];
   __shared__ int s_cnt[NT], s_head[NT];
-  __shared__ int s_pre[CHUNK + 1], s_rect[CHUNK];
+  __shared__ int s_pre[33], s_rect[32];
   __shared__ unsigned short s_span[CHUNK * HARP_TILE], s_upre[CHUNK * HARP_TILE + 2], s_tmp[CHUNK * HARP_TILE];  // (face, row) spans of the round
   __shared__ int s_scan0, s_nu;
   __shared__ float s_g[NT], s_prod[NT];
@@ -861,6 +865,17 @@ extern "C" int harp_shade(harp_ctx* c, int mode, int B, int S, float focal, int 
 }
 
 namespace {
+
+__global__ void __launch_bounds__(256) hit_mask_kernel(int S, const int2* __restrict__ hit_list, const int32_t* __restrict__ hit_count,
+                                                       float* __restrict__ mask) {
+  const int b = blockIdx.y, n = hit_count[b];
+  const int2* list = hit_list + (size_t)b * S * S;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int rc = list[i].x;
+    mask[((size_t)b * S + (rc >> 16)) * S + (rc & 0xffff)] = 1.f;
+  }
+}
+
 // backward of the light-view depth buffer (zbuf = sum_i b_i z_i at the stored face) over the non-empty light tiles only: the
 // PCF taps of the shading can only have touched pixels of tiles some face covers.  Four tiles per CTA round; the pixels with a
 // gradient are compacted in shared memory and then processed by full warps.
@@ -914,6 +929,16 @@ __global__ void __launch_bounds__(256) light_depth_bwd_tiles_kernel(harp_ctx c, 
 }
 
 }  // namespace
+
+extern "C" int harp_hit_mask(harp_ctx* c, int B, int S, float* mask, void* stream) {
+  HARP_REQUIRE(c && mask && B > 0, HARP_ERR_INVALID, "harp_hit_mask: null argument");
+  HARP_REQUIRE(B <= c->maxB && S == c->S, HARP_ERR_CAPACITY, "harp_hit_mask: no render pass of this size on the ctx");
+  cudaStream_t st = (cudaStream_t)stream;
+  HARP_CHECK_CUDA(cudaMemsetAsync(mask, 0, (size_t)B * S * S * sizeof(float), st));
+  hit_mask_kernel<<<dim3(32, B), 256, 0, st>>>(S, reinterpret_cast<const int2*>(c->hit_list), c->hit_count, mask);
+  HARP_LAUNCH_CHECK();
+  return HARP_OK;
+}
 
 int harp_light_depth_bwd_tiles(harp_ctx* c, int B, int S, cudaStream_t st) {
   (void)B;

@@ -9,7 +9,6 @@ int harp_raster_setup(harp_ctx* c, int view, int B, int S, float focal, float ra
 namespace {
 
 constexpr int TPB = 256;
-constexpr int CHUNK = 64;  // faces staged per shared-memory round
 
 // backward of the projection (setup.cu, phase 0): d_ndc (B,V,4: xyz + pad) -> d_verts += , d_R += , d_T +=
 __global__ void __launch_bounds__(TPB) project_bwd_kernel(int B, int V, const float* __restrict__ verts, const float* __restrict__ R,

@@ -368,6 +368,14 @@ class Shade(torch.autograd.Function):
                 g["d_light_pos"], g["d_amb"].view(sa), g["d_texture"].view(st), g["d_normal_map"].view(sn), None, None, None, None)
 
 
+def hit_mask(hc, B, S):
+    """(B,S,S,1) coverage of the ctx's last Shade / fused render pass: 1 where a face covers the pixel centre — the alpha channel
+    of the reference's K=1 blends (renderer_helper.py:190,592)."""
+    m = torch.empty(B, S, S, 1, device=hc.device)
+    check(_lib.lib().harp_hit_mask(hc.h, int(B), int(S), ptr(m), stream()))
+    return m
+
+
 class TextureReg(torch.autograd.Function):
     """albedo_reg (kind 0) / normal_reg (kind 1) with explicit neighbour offsets (loss/texture_reg.py:5-66)."""
 

@@ -61,7 +61,7 @@ class ShadowRenderer:
         rgb = ops.Shade.apply(meshes.hc, verts, meshes.verts_normals_padded(), cam_R, cam_T, kwargs["R"], kwargs["T"], light, amb,
                               tex.maps_padded()[:1], mat.normal_maps.maps_padded()[:1], _scalar(kwargs["focal_length"]),
                               self.image_size, int(self.self_shadow))
-        hit = (rgb.detach() != 1.0).any(-1, keepdim=True).to(rgb.dtype)  # alpha of a K=1 blend: 1 on hit pixels
+        hit = ops.hit_mask(meshes.hc, B, self.image_size)  # alpha of a K=1 blend: 1 on covered pixels
         return torch.cat([rgb, hit], dim=-1)
 
 
@@ -90,7 +90,7 @@ class PhongRenderer:
         rgb = ops.Shade.apply(meshes.hc, verts, meshes.verts_normals_padded(), kwargs["R"], kwargs["T"], kwargs["R"], kwargs["T"], light,
                               amb, tex.maps_padded()[:1], nm, _scalar(kwargs["focal_length"]),
                               self.image_size, 0, self.LIGHTS)
-        hit = (rgb.detach() != 1.0).any(-1, keepdim=True).to(rgb.dtype)
+        hit = ops.hit_mask(meshes.hc, B, self.image_size)
         return torch.cat([rgb, hit], dim=-1)
 
 

@@ -203,6 +203,11 @@ HARP_API int harp_shade(harp_ctx*, int mode, int B, int S, float focal, int self
                int texW, const float* fixed_lights /* [host] nullable */, float* rgb, const float* g_or_target,
                const float* mask, float weight, float* loss, const harp_shade_grads* grads, void* stream);
 
+/* Coverage of the last harp_shade / harp_render_fused pass on this ctx: mask (B,S,S) = 1 where a face covers the pixel centre,
+ * else 0 — the alpha channel of the reference's K=1 blends (renderer_helper.py:190,592: softmax_rgb_blend at K=1), which the
+ * reference's callers use as the foreground mask (utils/visualize.py:298). */
+HARP_API int harp_hit_mask(harp_ctx*, int B, int S, float* mask, void* stream);
+
 /* ---- evaluation-pass normal renderer: MeshRasterizer(K=10) + SoftPhongNormalShader (renderer_helper.py:85-101,216-301):
  * colours = (n * (1,-1,-1) + 1) / 2 of the normal-mapped interpolated normals, softmax_rgb_blend over the K nearest
  * faces.  Forward only.  normal_map NULL skips the perturbation.  rgb (B,S,S,3). */

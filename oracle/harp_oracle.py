@@ -201,7 +201,7 @@ def light_camera(cam, light_positions, center, focal, S):
     cT = cam_to_T(cam, focal, S)
     cR = cam_R(cam.shape[0], cam.dtype)
     lp = center + (light_positions - center) * (SHADOW_RADIUS / torch.linalg.norm(light_positions - center, dim=1, keepdim=True))
-    lR = p3d.look_at_rotation(lp, at=center, up=((0, 1, 0),))
+    lR = p3d.look_at_rotation(lp, at=center, up=((0, 1, 0),), device=lp.device)
     lT = -torch.bmm(lR.transpose(1, 2), lp[:, :, None])[:, :, 0]
     return lR, lT, cR, cT
 

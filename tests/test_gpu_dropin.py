@@ -128,3 +128,34 @@ def test_dropin_loop_body_matches_reference_golden(name):
         d = (img.cpu() - torch.tensor(g["img_" + k])).abs().amax(-1)
         assert float((d <= 2e-4).double().mean()) >= 0.995, (k, float((d <= 2e-4).double().mean()))
         assert float((d <= 2e-2).double().mean()) >= 0.999, k
+
+
+def test_alpha_channel_is_the_coverage_not_a_colour_test():
+    """The K=1 renderers' alpha channel (renderer_helper.py:190,592) comes from the rasteriser's hit list: a hand shaded exactly
+    white (white texture, ambient 1) on the white background keeps its alpha, and the mask equals the set of pixels the
+    silhouette's hard interior covers."""
+    from harp_b200 import camera, ops, scene, synth
+    hc, pack, tmpl = scene.make_context("cuda:0")
+    S, B = 128, 2
+    focal = 1000.0 * S / 224.0
+    seq = synth.make_sequence(B, seed=3, img_size=S)
+    dev = hc.device
+    pose48 = torch.cat((seq["rot"], seq["pose"]), 1).to(dev)
+    verts0, _ = ops.LbsMano.apply(hc, pose48, seq["shape"].to(dev), seq["trans"].to(dev))
+    verts, normals = ops.MeshBuild.apply(hc, verts0, torch.zeros(hc.V, 1, device=dev))
+    cR, cT = camera.flip_xy_R(B, dev), camera.cam_to_T(seq["cam"].to(dev), focal, S)
+    light = torch.tensor([[1.0, 1.0, -5.0]], device=dev).expand(B, 3).contiguous()
+    lR, lT = camera.light_camera(light, verts.mean(1))
+    app = synth.make_appearance(seed=2)
+    masks = []
+    for tex, amb in ((app["texture"].to(dev), 0.6), (torch.ones_like(app["texture"]).to(dev), 1.0)):
+        rgb = ops.Shade.apply(hc, verts, normals, cR, cT, lR, lT, light, torch.tensor([amb], device=dev), tex,
+                              app["normal_map"].to(dev), focal, S, 1)
+        masks.append(ops.hit_mask(hc, B, S))
+    assert bool((rgb == 1.0).all())  # the second render is white on white ...
+    assert torch.equal(masks[0], masks[1]) and masks[1].sum() > 500  # ... and still has its alpha
+    assert torch.equal(masks[0][..., 0] > 0, (ops.Shade.apply(hc, verts, normals, cR, cT, lR, lT, light, torch.tensor([0.6], device=dev),
+                                                               app["texture"].to(dev), app["normal_map"].to(dev), focal, S, 1) != 1.0).any(-1))
+    alpha = ops.Silhouette.apply(hc, verts, cR, cT, focal, S, 1e-7)
+    inter = (masks[0][..., 0] > 0) & (alpha < 0.5)
+    assert int(inter.sum()) == 0  # every covered pixel centre is inside the soft silhouette

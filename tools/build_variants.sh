@@ -6,9 +6,8 @@ cd "$(dirname "$0")/.."
 mkdir -p harp_b200/variants
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -shared"
 build() { /usr/local/cuda/bin/nvcc $FLAGS $2 harp_b200/csrc/*.cu -o harp_b200/variants/libharpb200_$1.so; }
-build A "-DHARP_PV_MINCTAS=20 -DHARP_PV_CHUNK=48 -DHARP_PV_QCAP=160" &   # pixel_vis at 20 CTAs / SM
-build B "-DHARP_SHADE_MIN_CTAS=5" &                                        # shade at 5 CTAs / SM (<= 102 registers)
-build C "-DHARP_SHADE_GRID=192" &                                          # shade: 192 CTAs per frame
-build D "-DHARP_PV_CHUNK=32 -DHARP_PV_QCAP=352 -DHARP_PV_MINCTAS=16" &     # pixel_vis: smaller staging chunks
+build c24m12 "-DHARP_PV_CHUNK=24 -DHARP_PV_MINCTAS=12" &   # tile rasteriser: 16.7 KB of shared memory -> 12 resident CTAs (registers) instead of 11
+build c20m14 "-DHARP_PV_CHUNK=20 -DHARP_PV_MINCTAS=14" &   # 15.4 KB, <= 73 registers -> 14 CTAs / SM
+build c16m16 "-DHARP_PV_CHUNK=16 -DHARP_PV_MINCTAS=16" &   # 13.9 KB, <= 64 registers -> 16 CTAs / SM
 wait
 ls -la harp_b200/variants
