@@ -152,7 +152,7 @@ def test_alpha_channel_is_the_coverage_not_a_colour_test():
         rgb = ops.Shade.apply(hc, verts, normals, cR, cT, lR, lT, light, torch.tensor([amb], device=dev), tex,
                               app["normal_map"].to(dev), focal, S, 1)
         masks.append(ops.hit_mask(hc, B, S))
-    assert bool((rgb == 1.0).all())  # the second render is white on white ...
+    assert float((rgb - 1.0).abs().max()) < 1e-6  # the second render is white on white (to the rounding of the bilinear weights) ...
     assert torch.equal(masks[0], masks[1]) and masks[1].sum() > 500  # ... and still has its alpha
     assert torch.equal(masks[0][..., 0] > 0, (ops.Shade.apply(hc, verts, normals, cR, cT, lR, lT, light, torch.tensor([0.6], device=dev),
                                                                app["texture"].to(dev), app["normal_map"].to(dev), focal, S, 1) != 1.0).any(-1))
