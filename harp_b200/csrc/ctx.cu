@@ -19,8 +19,10 @@ extern "C" int64_t harp_launch_count(void) { return g_launches.load(); }
 struct harp_prof {
   int level = 0;          // 0 off; 1: the two pixel kernels (ids 0, 1; bench roofline timing); 2: also the step's segments (ids 2..7)
   bool in_graph = false;  // events belong to a captured graph: keep them across reads
-  std::vector<cudaEvent_t> ev[8];  // start/stop pairs per id: 0 pixel_vis / silhouette, 1 shade, 2 lbs fwd, 3 lbs bwd,
-                                   // 4 mesh build fwd, 5 mesh build bwd, 6 camera project + bins, 7 render backward tail
+  std::vector<cudaEvent_t> ev[12];  // start/stop pairs per id: 0 tile rasteriser, 1 shade, 2 geometry fwd, 3 geometry bwd,
+                                    // 4, 5 stand-alone mesh build fwd / bwd, 6 camera project + bins, 7 render backward tail; timeline only:
+                                    // 8 step prologue, 9 the render's side branch, 10 the regulariser branch
+  std::vector<std::pair<int, cudaEvent_t>> order;  // every event in recording order (harp_ctx_profile_timeline)
 };
 void harp_prof_begin(harp_ctx* c, int id, cudaStream_t st) {
   if (!c->prof || c->prof->level == 0 || (id >= 2 && c->prof->level < 2)) return;
@@ -35,6 +37,7 @@ void harp_prof_begin(harp_ctx* c, int id, cudaStream_t st) {
                                                         : cudaEventRecord(e, st);
   if (rc != cudaSuccess) { cudaGetLastError(); cudaEventDestroy(e); return; }
   c->prof->ev[id].push_back(e);
+  c->prof->order.emplace_back(id, e);
 }
 void harp_prof_end(harp_ctx* c, int id, cudaStream_t st) { harp_prof_begin(c, id, st); }
 extern "C" int harp_ctx_profile(harp_ctx* c, int enable) {
@@ -56,6 +59,24 @@ extern "C" int harp_ctx_profile_read(harp_ctx* c, int id, float* total_ms, int* 
   if (!c->prof->in_graph) {
     for (cudaEvent_t e : v) cudaEventDestroy(e);
     v.clear();
+    auto& o = c->prof->order;
+    for (size_t i = 0; i < o.size();) { if (o[i].first == id) o.erase(o.begin() + i); else ++i; }
+  }
+  return HARP_OK;
+}
+// Every profiling event in recording order as (id, ms since the first event) pairs; even occurrences of an id open its
+// segment, odd ones close it.  For the events of a captured graph these are the times of the last replay.
+extern "C" int harp_ctx_profile_timeline(harp_ctx* c, float* out, int capacity, int* n) {
+  HARP_REQUIRE(c && out && n && capacity >= 0, HARP_ERR_INVALID, "harp_ctx_profile_timeline: bad argument");
+  *n = 0;
+  if (!c->prof || c->prof->order.empty()) return HARP_OK;
+  HARP_CHECK_CUDA(cudaDeviceSynchronize());
+  auto& o = c->prof->order;
+  for (size_t i = 0; i < o.size() && *n < capacity / 2; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, o[0].second, o[i].second) != cudaSuccess) { cudaGetLastError(); continue; }
+    out[2 * *n] = (float)o[i].first; out[2 * *n + 1] = ms;
+    ++*n;
   }
   return HARP_OK;
 }
@@ -268,7 +289,8 @@ extern "C" void harp_ctx_destroy(harp_ctx* c) {
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
-  if (c->ev_bins) cudaEventDestroy(c->ev_bins);
+  if (c->ev_bg) cudaEventDestroy(c->ev_bg);
+  if (c->bg_stream) cudaStreamDestroy(c->bg_stream);
   if (c->ev_reg_fork) cudaEventDestroy(c->ev_reg_fork);
   if (c->ev_reg_join) cudaEventDestroy(c->ev_reg_join);
   if (c->reg_stream) cudaStreamDestroy(c->reg_stream);

@@ -73,6 +73,7 @@ extern "C" int harp_step_fused(harp_ctx* c, const harp_step_args* p, void* strea
   const float* W = p->weights;  // silhouette, laplacian, normal, arap, kps_anchor, vert_disp_reg, photo, albedo, normal_reg
   Workspace w = carve(c, B, p->workspace);
   int rc;
+  harp_prof_begin(c, 8, st);
   HARP_CHECK_CUDA(cudaMemsetAsync(w.zero_begin, 0, w.zero_floats * sizeof(float), st));
   flip_xy_kernel<<<(B * 9 + 127) / 128, 128, 0, st>>>(B, w.cam_R);
   HARP_LAUNCH_CHECK();
@@ -87,6 +88,7 @@ extern "C" int harp_step_fused(harp_ctx* c, const harp_step_args* p, void* strea
   g.g_pose = p->g_pose; g.g_cam = p->g_cam; g.g_rot = p->g_rot; g.g_wrist = p->g_wrist_pose; g.g_shape = p->g_shape;
   g.g_disps = p->g_verts_disps; g.g_light = p->g_light_position; g.g_amb = p->g_amb_ratio;
   g.d_rot = p->d_rot; g.d_trans = p->d_trans; g.d_wrist = p->d_wrist;
+  harp_prof_end(c, 8, st);
   if ((rc = harp_geo_fwd(c, g, st)) != HARP_OK) return rc;
   // ---- regulariser branch: depends only on the mesh / the textures; accumulates with atomics
   if (!c->reg_stream) {
@@ -97,6 +99,7 @@ extern "C" int harp_step_fused(harp_ctx* c, const harp_step_args* p, void* strea
   cudaStream_t rs = c->reg_stream;
   HARP_CHECK_CUDA(cudaEventRecord(c->ev_reg_fork, st));
   HARP_CHECK_CUDA(cudaStreamWaitEvent(rs, c->ev_reg_fork, 0));
+  harp_prof_begin(c, 10, rs);
   if (app_on) {
     if ((rc = harp_texture_reg(c, 0, p->texture, p->texH, p->texW, p->off_albedo, p->uv_mask, W[7] * fs, p->losses + 7, p->g_texture, rs)) != HARP_OK) return rc;
     if ((rc = harp_texture_reg(c, 1, p->normal_map, p->texH, p->texW, p->off_normal, p->uv_mask, W[8] * fs, p->losses + 8, p->g_normal_map, rs)) != HARP_OK) return rc;
@@ -106,6 +109,7 @@ extern "C" int harp_step_fused(harp_ctx* c, const harp_step_args* p, void* strea
     if ((rc = harp_mesh_losses(c, B, w.verts, p->ref_verts, w.joints, p->init_joints, p->verts_disps, w5, p->losses + 1, w.d_verts, w.d_joints,
                                p->g_verts_disps, rs)) != HARP_OK) return rc;
   }
+  harp_prof_end(c, 10, rs);
   HARP_CHECK_CUDA(cudaEventRecord(c->ev_reg_join, rs));
   // ---- both renders (they run in every stage; their losses are gated by COARSE_OPT / APP_OPT) in one fused pixel pass
   harp_render_args r{};

@@ -12,6 +12,8 @@ int harp_project_bwd(harp_ctx* c, int B, int S, float focal, const float* verts,
 int harp_fold4(size_t n, const float* src4, float* dst3, cudaStream_t st);
 int harp_tex_prepare(harp_ctx* c, const float* texture, const float* normal_map, int texH, int texW, cudaStream_t st);
 int harp_light_depth_tiles(harp_ctx* c, int B, int S, bool zero_grad, cudaStream_t st);
+int harp_light_view_setup(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R, const float* T, bool zero_grad,
+                          cudaStream_t st);
 int harp_light_depth_bwd_tiles(harp_ctx* c, int B, int S, cudaStream_t st);
 int harp_sil_topk(harp_ctx* c, int mode, int S, int K, float sigma, float blur, float radius, float* alpha, const float* gin,
                   float gscale, float inv_n, float* loss, cudaStream_t st);
@@ -176,6 +178,7 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
   __shared__ int s_cnt[NT], s_head[NT];
   __shared__ int s_pre[33], s_rect[32];
   __shared__ unsigned short s_span[CHUNK * HARP_TILE], s_upre[CHUNK * HARP_TILE + 2], s_tmp[CHUNK * HARP_TILE];  // (face, row) spans of the round
+  __shared__ unsigned char s_win[CHUNK * 2 + 2];  // unit of the first pair of every 32-pair window
   __shared__ int s_scan0, s_nu;
   __shared__ float s_g[NT], s_prod[NT];
   __shared__ unsigned char s_need[NT], s_sat[NT];
@@ -317,6 +320,8 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
           const int cd = s_tmp[u], len = cd >> 11;
           if (len > 0) {
             s_span[uu] = (unsigned short)cd;
+            const int w = (pp + 31) & ~31;  // a unit has at most 8 pairs: it contains at most one multiple of 32
+            if (w < pp + len) s_win[w >> 5] = (unsigned char)uu;
             pp += len;
             s_upre[++uu] = (unsigned short)pp;
           }
@@ -331,11 +336,15 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
         for (int p0 = warp * 32; p0 < P; p0 += 2 * 32) {
           const int p = p0 + lane;
           const bool valid = p < P;
-          int lo = 0, hi = NU;  // unit of pair p: the last unit whose first pair is <= p
-          const int pq = valid ? p : 0;
-          while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_upre[mid] <= pq) lo = mid; else hi = mid; }
+          // unit of pair p: the unit holding the window's first pair (tabulated during the compaction) plus the number of
+          // units that end at or before p — unit ends inside the window are one bit each of a warp-wide OR
+          const int ua = s_win[p0 >> 5];
+          int e = 64;
+          if (ua + 1 + lane <= NU) e = (int)s_upre[ua + 1 + lane] - p0;
+          const unsigned ends = __reduce_or_sync(0xffffffffu, e < 32 ? (1u << e) : 0u);
+          const int lo = valid ? ua + __popc(ends & ((2u << lane) - 1u)) : 0;
           const int cd = s_span[lo];
-          const int fi = cd & 31, ly = (cd >> 5) & 7, lx = ((cd >> 8) & 7) + (pq - s_upre[lo]);
+          const int fi = cd & 31, ly = (cd >> 5) & 7, lx = ((cd >> 8) & 7) + (valid ? p - (int)s_upre[lo] : 0);
           const FaceTile& f = recs[fi];
           const int w = valid ? 1 : 0;
           const int pix = ly * HARP_TILE + lx;
@@ -678,22 +687,28 @@ int render_pass(harp_ctx* c, int B, int S, float focal, const harp_render_args* 
   const size_t nv4 = (size_t)B * c->V * 4 * sizeof(float), ntex = (size_t)r->texH * r->texW;
   double blur_d = 9.210240366975849 * (double)r->sigma;  // ln(1/1e-4 - 1) sigma (renderer_helper.py:46), in double like numpy
   float blur = p.sil ? (float)blur_d : 0.f, radius = p.sil ? (float)sqrt(blur_d) : 0.f;
-  // Camera branch first (it is the critical path: its kernels are submitted before the side branch's so that they are
-  // dispatched first).
+  // Three concurrent branches, forked from and joined to the caller's stream with events (capturable into a CUDA graph):
+  //   main   camera setup -> tile rasteriser (persistent: it holds every SM until its queue drains) -> top-K -> shading -> tail
+  //   side   (least priority) what only the shading needs: light-view setup, the light view's empty tiles, packed texel copies,
+  //          zero fills of the gradient accumulators, then the light-view rasteriser, whose CTAs move in as the camera
+  //          rasteriser's CTAs retire (they fill its tail); joined before the shading
+  //   bg     (highest priority) the HBM-bound streaming pass over the camera view's EMPTY tiles (background colour, alpha 0
+  //          and their loss terms: 4 of 5 tiles).  Nothing in the step reads its results before the end, so it starts when
+  //          both rasterisers are done and interleaves with the LSU-bound shading CTAs instead of delaying them (before,
+  //          the shading waited for it: 85 us of the step's critical path); joined at the end of the pass
   if (!c->side_stream) {
     int lo = 0, hi = 0;
     HARP_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = least priority
     HARP_CHECK_CUDA(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, lo));
-    HARP_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    HARP_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-    HARP_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_bins, cudaEventDisableTiming));
+    HARP_CHECK_CUDA(cudaStreamCreateWithPriority(&c->bg_stream, cudaStreamNonBlocking, hi));
+    for (cudaEvent_t* e : {&c->ev_fork, &c->ev_join, &c->ev_bg})
+      HARP_CHECK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   }
-  cudaStream_t ss = c->side_stream;
+  cudaStream_t ss = c->side_stream, bs = c->bg_stream;
   HARP_CHECK_CUDA(cudaEventRecord(c->ev_fork, st));
   harp_prof_begin(c, 6, st);
   // (the setup kernels also zero the projected-vertex gradient accumulator, the hit counters and the top-K counter)
   if ((rc = harp_raster_setup(c, 0, B, S, focal, radius, r->verts, r->cam_R, r->cam_T, st, true)) != HARP_OK) return rc;
-  HARP_CHECK_CUDA(cudaEventRecord(c->ev_bins, st));
   harp_prof_end(c, 6, st);
   VisArgs v{};
   v.S = S; v.K = r->faces_per_pixel > 0 ? r->faces_per_pixel : 50; v.sigma = r->sigma; v.blur = blur; v.radius = radius; v.ndc = c->ndc_cam;
@@ -725,31 +740,30 @@ int render_pass(harp_ctx* c, int B, int S, float focal, const harp_render_args* 
   HARP_LAUNCH_CHECK();
   if (p.sil && (rc = harp_sil_topk(c, p.sil_mode, S, v.K, r->sigma, blur, radius, r->alpha, p.sil_mode == 1 ? p.g_alpha : r->y_sil,
                                    v.sil_gscale, v.sil_inv_n, r->loss_sil, st)) != HARP_OK) return rc;
-  // Side branch on the ctx's own (least-priority) stream, concurrent with the camera branch above and joined before the
-  // deferred shading: everything only the shading needs — the light view (setup, nearest-depth raster), the packed texel
-  // copies, the zero fills of the shading's gradient accumulators — and the HBM-bound streaming pass over the camera view's
-  // empty tiles, which overlaps the issue-bound tile rasteriser.  Event fork / join is capturable into a CUDA graph.
+  // ---- side branch
   HARP_CHECK_CUDA(cudaStreamWaitEvent(ss, c->ev_fork, 0));
-  if (shadow) {
-    if ((rc = harp_raster_setup(c, 1, B, S, focal, 0.f, r->verts, r->light_R, r->light_T, ss, shade_bwd)) != HARP_OK) return rc;
-    if ((rc = harp_light_depth_tiles(c, B, S, shade_bwd, ss)) != HARP_OK) return rc;
-  }
+  harp_prof_begin(c, 9, ss);
+  if (shadow && (rc = harp_light_view_setup(c, B, S, focal, r->verts, r->light_R, r->light_T, shade_bwd, ss)) != HARP_OK) return rc;
   if (p.shade && (rc = harp_tex_prepare(c, r->texture, r->normal_map, r->texH, r->texW, ss)) != HARP_OK) return rc;
   if (shade_bwd) {
     HARP_CHECK_CUDA(cudaMemsetAsync(c->d_verts4, 0, nv4, ss));
     HARP_CHECK_CUDA(cudaMemsetAsync(c->d_normals4, 0, nv4, ss));
     HARP_CHECK_CUDA(cudaMemsetAsync(c->d_tex4, 0, 2 * ntex * 4 * sizeof(float), ss));
   }
+  if (shadow && (rc = harp_light_depth_tiles(c, B, S, shade_bwd, ss)) != HARP_OK) return rc;
+  harp_prof_end(c, 9, ss);
+  HARP_CHECK_CUDA(cudaEventRecord(c->ev_join, ss));
+  // ---- background branch
+  HARP_CHECK_CUDA(cudaStreamWaitEvent(bs, c->ev_join, 0));
   if (v.alpha || v.rgb || sil_bwd || photo) {
-    HARP_CHECK_CUDA(cudaStreamWaitEvent(ss, c->ev_bins, 0));
     const int eg = (int)(((size_t)B * S * (S / 4) + 255) / 256);
-    if (sil_bwd && photo) empty_tiles_kernel<false, true, true><<<eg, 256, 0, ss>>>(B, S, c->bin_count, v);
-    else if (sil_bwd) empty_tiles_kernel<false, true, false><<<eg, 256, 0, ss>>>(B, S, c->bin_count, v);
-    else if (photo) empty_tiles_kernel<false, false, true><<<eg, 256, 0, ss>>>(B, S, c->bin_count, v);
-    else empty_tiles_kernel<false, false, false><<<eg, 256, 0, ss>>>(B, S, c->bin_count, v);
+    if (sil_bwd && photo) empty_tiles_kernel<false, true, true><<<eg, 256, 0, bs>>>(B, S, c->bin_count, v);
+    else if (sil_bwd) empty_tiles_kernel<false, true, false><<<eg, 256, 0, bs>>>(B, S, c->bin_count, v);
+    else if (photo) empty_tiles_kernel<false, false, true><<<eg, 256, 0, bs>>>(B, S, c->bin_count, v);
+    else empty_tiles_kernel<false, false, false><<<eg, 256, 0, bs>>>(B, S, c->bin_count, v);
     HARP_LAUNCH_CHECK();
   }
-  HARP_CHECK_CUDA(cudaEventRecord(c->ev_join, ss));
+  HARP_CHECK_CUDA(cudaEventRecord(c->ev_bg, bs));
   HARP_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
   harp_prof_begin(c, 1, st);
   if (p.shade) {
@@ -794,6 +808,7 @@ int render_pass(harp_ctx* c, int B, int S, float focal, const harp_render_args* 
                                r->grads.d_cam_T, st)) != HARP_OK) return rc;
   }
   harp_prof_end(c, 7, st);
+  HARP_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_bg, 0));
   return HARP_OK;
 }
 
@@ -949,8 +964,8 @@ int harp_light_depth_bwd_tiles(harp_ctx* c, int B, int S, cudaStream_t st) {
   return HARP_OK;
 }
 
-// Light-view nearest depth + face id with the persistent tile rasteriser (setup of view 1 must be current).
-int harp_light_depth_tiles(harp_ctx* c, int B, int S, bool zero_grad, cudaStream_t st) {
+// Light view (renderer_helper.py:344), part 1: setup of view 1 and the streaming fill of its empty tiles (depth -1, face -1).
+static VisArgs light_view_args(harp_ctx* c, int S, bool zero_grad) {
   VisArgs v{};
   v.S = S; v.K = 1; v.sigma = 0.f; v.blur = 0.f; v.radius = 0.f; v.ndc = c->ndc_light;
   v.rec = c->face_rec + (size_t)c->maxB * c->F;
@@ -959,9 +974,24 @@ int harp_light_depth_tiles(harp_ctx* c, int B, int S, bool zero_grad, cudaStream
   v.work = c->work + v.work_cap;
   v.work_ctl = c->work_ctl + 4;
   v.zbuf = c->light_zbuf; v.face = c->light_face; v.d_zbuf = zero_grad ? c->d_light_zbuf : nullptr;
-  tile_raster_kernel<false, false, false, false><<<HARP_SM_COUNT * HARP_PV_MINCTAS, NT, 0, st>>>(*c, v);
+  return v;
+}
+
+int harp_light_view_setup(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R, const float* T, bool zero_grad,
+                          cudaStream_t st) {
+  int rc = harp_raster_setup(c, 1, B, S, focal, 0.f, verts, R, T, st, zero_grad);
+  if (rc != HARP_OK) return rc;
   const int eg = (int)(((size_t)B * S * (S / 4) + 255) / 256);
-  empty_tiles_kernel<true, false, false><<<eg, 256, 0, st>>>(B, S, c->bin_count + (size_t)c->maxB * c->tiles, v);
-  HARP_LAUNCH_CHECK_N(2);
+  empty_tiles_kernel<true, false, false><<<eg, 256, 0, st>>>(B, S, c->bin_count + (size_t)c->maxB * c->tiles, light_view_args(c, S, zero_grad));
+  HARP_LAUNCH_CHECK();
+  return HARP_OK;
+}
+
+// Part 2: nearest depth + face id on the covered tiles with the persistent tile rasteriser.
+int harp_light_depth_tiles(harp_ctx* c, int B, int S, bool zero_grad, cudaStream_t st) {
+  (void)B;
+  // (62 registers and 9 KB of shared memory without the silhouette state: 16 CTAs fit an SM)
+  tile_raster_kernel<false, false, false, false><<<HARP_SM_COUNT * 16, NT, 0, st>>>(*c, light_view_args(c, S, zero_grad));
+  HARP_LAUNCH_CHECK();
   return HARP_OK;
 }

@@ -139,6 +139,23 @@ class HarpContext:
             out[n] = (ms.value, k.value)
         return out
 
+    TIMELINE_IDS = ("tile_raster", "shade", "geo_fwd", "geo_bwd", "mesh_fwd", "mesh_bwd", "setup", "render_tail", "prologue",
+                    "side_branch", "regularisers")
+
+    def profile_timeline(self):
+        """[(segment, begin_ms, end_ms)] of every profiled segment in recording order, relative to the first event (for a captured
+        graph: of its last replay).  Shows the gaps and overlaps between segments that the per-segment sums hide."""
+        buf, n = (C.c_float * 512)(), C.c_int()
+        check(_lib.lib().harp_ctx_profile_timeline(self.h, buf, 512, C.byref(n)))
+        open_, out = {}, []
+        for k in range(n.value):
+            i, t = int(buf[2 * k]), float(buf[2 * k + 1])
+            if i in open_:
+                out.append((self.TIMELINE_IDS[i], open_.pop(i), t))
+            else:
+                open_[i] = t
+        return out
+
     def counters(self):
         out = (C.c_int64 * 2)()
         check(_lib.lib().harp_ctx_read_counters(self.h, out, stream()))

@@ -121,6 +121,10 @@ HARP_API int64_t harp_launch_count(void);
  * elapsed ms and launch count of one id (0..7) since the last read, and clears (events of a captured graph are kept). */
 HARP_API int harp_ctx_profile(harp_ctx* ctx, int enable);
 HARP_API int harp_ctx_profile_read(harp_ctx* ctx, int kernel_id, float* total_ms, int* launches);
+/* Every profiling event in recording order: out[2k] = id, out[2k+1] = ms since the first event (even occurrences of an id open
+ * its segment, odd ones close it).  Besides ids 0..7: 8 step prologue, 9 the render's side branch (light view, empty tiles),
+ * 10 the regulariser branch.  Shows the gaps and the overlap that the per-id sums hide.  capacity in floats. */
+HARP_API int harp_ctx_profile_timeline(harp_ctx* ctx, float* out, int capacity, int* n);
 
 /* ---- MANO linear blend skinning: ManoLayer.forward (manopth/manolayer.py:108-296), use_pca=False, axis-angle -------
  * pose48 (B,48) = [rot3 | pose45]; betas (B,10) or one shared row if betas_shared; trans (B,3).

@@ -35,3 +35,6 @@ out = {"frames": B, "size": S, "ms_per_step": e0.elapsed_time(e1) / N,
        "segments_ms_last_replay": {k: round(v[0] / max(v[1], 1), 4) for k, v in seg.items()}}
 out["accounted_ms"] = round(sum(v for k, v in out["segments_ms_last_replay"].items()), 4)
 print(json.dumps(out))
+if os.environ.get("HARP_TIMELINE"):
+    for name, t0, t1 in sorted(hc.profile_timeline(), key=lambda r: r[1]):
+        print(f"  {name:14s} {1e3 * t0:8.1f} -> {1e3 * t1:8.1f} us  ({1e3 * (t1 - t0):6.1f})")
