@@ -396,7 +396,7 @@ def main():
     host = {k: ft.frames[k].cpu().pin_memory() for k in ("y_true", "y_sil", "y_sil_eroded")}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = len(LOSS_NAMES) * 4
-    k_e2e = 0 if args.no_e2e else max(3, min(args.steps, 10))
+    k_e2e = 0 if args.no_e2e else max(3, min(args.steps, 50))  # (the first upload of a leg is not overlapped: amortised)
     e2e_s = e2e_u8_s = 1e-9
     h2d_u8 = 0
     if k_e2e:
@@ -436,11 +436,12 @@ def main():
         # dominant kernel: the longer of the two pixel kernels; algorithmic bytes per launch:
         #   shade fwd+bwd: read y_true 12 S^2 + eroded mask 4 S^2, write rgb 12 S^2  = 28 S^2 B/frame
         #   silhouette fwd+bwd: read y_sil 4 S^2, write alpha 4 S^2                   =  8 S^2 B/frame
-        # with the fused pixel pass, kernel id 0 is pixel_vis (silhouette + visibility; also writes the background pixels of
-        # the colour image and reads their targets) and id 1 is the deferred shading of the compacted hit pixels
+        # with the fused pixel pass, kernel id 0 is the tile rasteriser (silhouette + visibility over the covered tiles; the
+        # background pixels of both images and their loss terms are its and the empty-tile pass's) and id 1 is the deferred
+        # shading of the compacted hit pixels
         hit = float((ft.last["alpha"] > 0.5).float().mean())
         alg = {"shade": 28.0 * S * S * B * hit, "silhouette": (8.0 + 28.0 * (1.0 - hit)) * S * S * B}
-        names = {"silhouette": "pixel_vis_kernel<silhouette fwd+L1+bwd, visibility, hit compaction>",
+        names = {"silhouette": "tile_raster_kernel<silhouette fwd+L1+bwd, visibility, hit compaction>",
                  "shade": "shade_deferred_kernel<shading fwd+L1+bwd over compacted hit pixels>"}
         dom = max(prof, key=lambda n: prof[n][0])
         dms = prof[dom][0] / max(prof[dom][1], 1)

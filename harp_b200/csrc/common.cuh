@@ -108,9 +108,7 @@ struct harp_ctx {
   struct harp_prof* prof = nullptr;        // host-side event lists (harp_ctx_profile)
   // host-side handles for the fused render's light branch (forked from / joined to the caller's stream; capturable)
   cudaStream_t side_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  cudaStream_t bg_stream = nullptr;        // highest priority: the streaming pass over the camera view's empty tiles
-  cudaEvent_t ev_bg = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_setup = nullptr;
   cudaStream_t reg_stream = nullptr;       // harp_step_fused's regulariser branch
   cudaEvent_t ev_reg_fork = nullptr, ev_reg_join = nullptr;
 };

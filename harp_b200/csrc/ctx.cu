@@ -289,8 +289,7 @@ extern "C" void harp_ctx_destroy(harp_ctx* c) {
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
-  if (c->ev_bg) cudaEventDestroy(c->ev_bg);
-  if (c->bg_stream) cudaStreamDestroy(c->bg_stream);
+  if (c->ev_setup) cudaEventDestroy(c->ev_setup);
   if (c->ev_reg_fork) cudaEventDestroy(c->ev_reg_fork);
   if (c->ev_reg_join) cudaEventDestroy(c->ev_reg_join);
   if (c->reg_stream) cudaStreamDestroy(c->reg_stream);

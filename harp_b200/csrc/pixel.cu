@@ -687,28 +687,27 @@ int render_pass(harp_ctx* c, int B, int S, float focal, const harp_render_args* 
   const size_t nv4 = (size_t)B * c->V * 4 * sizeof(float), ntex = (size_t)r->texH * r->texW;
   double blur_d = 9.210240366975849 * (double)r->sigma;  // ln(1/1e-4 - 1) sigma (renderer_helper.py:46), in double like numpy
   float blur = p.sil ? (float)blur_d : 0.f, radius = p.sil ? (float)sqrt(blur_d) : 0.f;
-  // Three concurrent branches, forked from and joined to the caller's stream with events (capturable into a CUDA graph):
+  // Two branches, forked from and joined to the caller's stream with events (capturable into a CUDA graph):
   //   main   camera setup -> tile rasteriser (persistent: it holds every SM until its queue drains) -> top-K -> shading -> tail
-  //   side   (least priority) what only the shading needs: light-view setup, the light view's empty tiles, packed texel copies,
-  //          zero fills of the gradient accumulators, then the light-view rasteriser, whose CTAs move in as the camera
-  //          rasteriser's CTAs retire (they fill its tail); joined before the shading
-  //   bg     (highest priority) the HBM-bound streaming pass over the camera view's EMPTY tiles (background colour, alpha 0
-  //          and their loss terms: 4 of 5 tiles).  Nothing in the step reads its results before the end, so it starts when
-  //          both rasterisers are done and interleaves with the LSU-bound shading CTAs instead of delaying them (before,
-  //          the shading waited for it: 85 us of the step's critical path); joined at the end of the pass
+  //   side   (least priority) what only the shading needs — light-view setup and the light view's empty tiles, packed texel
+  //          copies, zero fills of the gradient accumulators, then the light-view rasteriser, whose CTAs move in as the
+  //          camera rasteriser's CTAs retire (they fill its tail) — and the HBM-bound streaming pass over the camera view's
+  //          empty tiles; joined before the shading.
+  // (Measured with harp_ctx_profile_timeline: the GPU is busy end to end, the branches only fill each other's tails.  Running
+  // the empty-tile pass UNDER the shading instead, on a high-priority stream, lengthened the shading by what the pass takes.)
   if (!c->side_stream) {
     int lo = 0, hi = 0;
     HARP_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = least priority
     HARP_CHECK_CUDA(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, lo));
-    HARP_CHECK_CUDA(cudaStreamCreateWithPriority(&c->bg_stream, cudaStreamNonBlocking, hi));
-    for (cudaEvent_t* e : {&c->ev_fork, &c->ev_join, &c->ev_bg})
+    for (cudaEvent_t* e : {&c->ev_fork, &c->ev_join, &c->ev_setup})
       HARP_CHECK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   }
-  cudaStream_t ss = c->side_stream, bs = c->bg_stream;
+  cudaStream_t ss = c->side_stream;
   HARP_CHECK_CUDA(cudaEventRecord(c->ev_fork, st));
   harp_prof_begin(c, 6, st);
   // (the setup kernels also zero the projected-vertex gradient accumulator, the hit counters and the top-K counter)
   if ((rc = harp_raster_setup(c, 0, B, S, focal, radius, r->verts, r->cam_R, r->cam_T, st, true)) != HARP_OK) return rc;
+  HARP_CHECK_CUDA(cudaEventRecord(c->ev_setup, st));
   harp_prof_end(c, 6, st);
   VisArgs v{};
   v.S = S; v.K = r->faces_per_pixel > 0 ? r->faces_per_pixel : 50; v.sigma = r->sigma; v.blur = blur; v.radius = radius; v.ndc = c->ndc_cam;
@@ -751,19 +750,17 @@ int render_pass(harp_ctx* c, int B, int S, float focal, const harp_render_args* 
     HARP_CHECK_CUDA(cudaMemsetAsync(c->d_tex4, 0, 2 * ntex * 4 * sizeof(float), ss));
   }
   if (shadow && (rc = harp_light_depth_tiles(c, B, S, shade_bwd, ss)) != HARP_OK) return rc;
-  harp_prof_end(c, 9, ss);
-  HARP_CHECK_CUDA(cudaEventRecord(c->ev_join, ss));
-  // ---- background branch
-  HARP_CHECK_CUDA(cudaStreamWaitEvent(bs, c->ev_join, 0));
-  if (v.alpha || v.rgb || sil_bwd || photo) {
+  if (v.alpha || v.rgb || sil_bwd || photo) {  // (in stream order after the camera setup: ev_setup)
+    HARP_CHECK_CUDA(cudaStreamWaitEvent(ss, c->ev_setup, 0));
     const int eg = (int)(((size_t)B * S * (S / 4) + 255) / 256);
-    if (sil_bwd && photo) empty_tiles_kernel<false, true, true><<<eg, 256, 0, bs>>>(B, S, c->bin_count, v);
-    else if (sil_bwd) empty_tiles_kernel<false, true, false><<<eg, 256, 0, bs>>>(B, S, c->bin_count, v);
-    else if (photo) empty_tiles_kernel<false, false, true><<<eg, 256, 0, bs>>>(B, S, c->bin_count, v);
-    else empty_tiles_kernel<false, false, false><<<eg, 256, 0, bs>>>(B, S, c->bin_count, v);
+    if (sil_bwd && photo) empty_tiles_kernel<false, true, true><<<eg, 256, 0, ss>>>(B, S, c->bin_count, v);
+    else if (sil_bwd) empty_tiles_kernel<false, true, false><<<eg, 256, 0, ss>>>(B, S, c->bin_count, v);
+    else if (photo) empty_tiles_kernel<false, false, true><<<eg, 256, 0, ss>>>(B, S, c->bin_count, v);
+    else empty_tiles_kernel<false, false, false><<<eg, 256, 0, ss>>>(B, S, c->bin_count, v);
     HARP_LAUNCH_CHECK();
   }
-  HARP_CHECK_CUDA(cudaEventRecord(c->ev_bg, bs));
+  harp_prof_end(c, 9, ss);
+  HARP_CHECK_CUDA(cudaEventRecord(c->ev_join, ss));
   HARP_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
   harp_prof_begin(c, 1, st);
   if (p.shade) {
@@ -808,7 +805,6 @@ int render_pass(harp_ctx* c, int B, int S, float focal, const harp_render_args* 
                                r->grads.d_cam_T, st)) != HARP_OK) return rc;
   }
   harp_prof_end(c, 7, st);
-  HARP_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_bg, 0));
   return HARP_OK;
 }
 

@@ -12,7 +12,7 @@ if [ "$2" = "ncu" ]; then
     > gpurun_out/${TAG}_launches.log 2>&1
   timeout 700 ncu --set full --clock-control none --import-source on --nvtx --nvtx-include "harp_timed/" \
     -k regex:"tile_raster_kernel|shade_deferred_kernel|empty_tiles_kernel|face_setup_kernel|bin_fill_kernel|geo_fwd_kernel|geo_bwd_kernel|light_depth" \
-    -c 10 -f -o gpurun_out/${TAG}_pixel \
+    -c 12 -f -o gpurun_out/${TAG}_pixel \
     python bench.py --steps 1 --warmup 3 --eager --no-e2e --no-cpu-baseline --no-standin > gpurun_out/${TAG}_ncu.log 2>&1
 fi
 tail -3 gpurun_out/${TAG}_pytest.log
