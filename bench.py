@@ -393,37 +393,39 @@ def main():
     # and reads the loss vector back.  Leg 1: fp32 y_true / y_sil / y_sil_eroded, the dtypes the reference's DataLoader
     # yields (20 B/pixel).  Leg 2: the uint8 frames + masks the image files decode to (4 B/pixel), converted and eroded on
     # the device (harp_ingest_u8) — reported separately as e2e_uint8.
-    host = {k: ft.frames[k].cpu().pin_memory() for k in ("y_true", "y_sil", "y_sil_eroded")}
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = len(LOSS_NAMES) * 4
-    k_e2e = 0 if args.no_e2e else max(3, min(args.steps, 50))  # (the first upload of a leg is not overlapped: amortised)
-    e2e_s = e2e_u8_s = 1e-9
-    h2d_u8 = 0
-    if k_e2e:
-        def stage_f32():
-            s = {k: torch.empty_like(ft.frames[k]) for k in host}
-            s["init_joints"] = ft.frames["init_joints"]
-            return s
+    from harp_b200.hostmem import gpu_numa_affinity
+    with gpu_numa_affinity(dev) as host_affinity:  # pinned staging pages on the GPU's NUMA node
+        host = {k: ft.frames[k].cpu().pin_memory() for k in ("y_true", "y_sil", "y_sil_eroded")}
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        d2h = len(LOSS_NAMES) * 4
+        k_e2e = 0 if args.no_e2e else max(3, min(args.steps, 50))  # (the first upload of a leg is not overlapped: amortised)
+        e2e_s = e2e_u8_s = 1e-9
+        h2d_u8 = 0
+        if k_e2e:
+            def stage_f32():
+                s = {k: torch.empty_like(ft.frames[k]) for k in host}
+                s["init_joints"] = ft.frames["init_joints"]
+                return s
 
-        def run_f32(s):
-            if use_graph:
-                return ft.capture(fid, oa, on, stage="both", batch=s, warmup=1)
-            return lambda: ft.step(fid, oa, on, stage="both", update=True, batch=s)
+            def run_f32(s):
+                if use_graph:
+                    return ft.capture(fid, oa, on, stage="both", batch=s, warmup=1)
+                return lambda: ft.step(fid, oa, on, stage="both", update=True, batch=s)
 
-        e2e_s = e2e_leg(host, stage_f32, run_f32, k_e2e)
-        host_u8 = {"rgb": (ft.frames["y_true"] * 255).round().clamp(0, 255).to(torch.uint8).cpu().pin_memory(),
-                   "mask": (ft.frames["y_sil"] * 255).round().to(torch.uint8).cpu().pin_memory()}
-        h2d_u8 = sum(v.numel() for v in host_u8.values())
+            e2e_s = e2e_leg(host, stage_f32, run_f32, k_e2e)
+            host_u8 = {"rgb": (ft.frames["y_true"] * 255).round().clamp(0, 255).to(torch.uint8).cpu().pin_memory(),
+                       "mask": (ft.frames["y_sil"] * 255).round().to(torch.uint8).cpu().pin_memory()}
+            h2d_u8 = sum(v.numel() for v in host_u8.values())
 
-        def stage_u8():
-            return {k: torch.empty(v.shape, dtype=torch.uint8, device=dev) for k, v in host_u8.items()}
+            def stage_u8():
+                return {k: torch.empty(v.shape, dtype=torch.uint8, device=dev) for k, v in host_u8.items()}
 
-        def run_u8(s):
-            if use_graph:
-                return ft.capture(fid, oa, on, stage="both", batch_u8=s, warmup=1)
-            return lambda: ft.step(fid, oa, on, stage="both", update=True, batch_u8=s)
+            def run_u8(s):
+                if use_graph:
+                    return ft.capture(fid, oa, on, stage="both", batch_u8=s, warmup=1)
+                return lambda: ft.step(fid, oa, on, stage="both", update=True, batch_u8=s)
 
-        e2e_u8_s = e2e_leg(host_u8, stage_u8, run_u8, k_e2e)
+            e2e_u8_s = e2e_leg(host_u8, stage_u8, run_u8, k_e2e)
 
     if rank == 0:
         value = world * B * args.steps / (ms_total * 1e-3)
@@ -457,7 +459,7 @@ def main():
                 "dtype": "f32", "data": "synthetic", "config": config(world, B, S, args.model),
                 "clocks": clk,
                 "e2e": {"value": world * B * k_e2e / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": k_e2e, "host_dtype": "fp32 (the reference DataLoader's tensors)"},
+                        "steps": k_e2e, "host_dtype": "fp32 (the reference DataLoader's tensors)", "host_affinity": host_affinity},
                 "e2e_uint8": {"value": world * B * k_e2e / e2e_u8_s, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
                               "steps": k_e2e, "host_dtype": "uint8 frames + masks, /255 and 3x3x2 erosion on the device"},
                 "gpu_launches": int(launches), "launch_mode": "cuda_graph_replay" if use_graph else "eager",
