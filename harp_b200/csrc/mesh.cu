@@ -298,12 +298,15 @@ extern "C" int harp_mesh_losses(harp_ctx* c, int B, const float* verts, const fl
                                 float* d_verts, float* d_joints, float* d_disps, void* stream) {
   HARP_REQUIRE(c && B > 0 && verts && w && losses, HARP_ERR_INVALID, "harp_mesh_losses: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  laplacian_kernel<<<nblk((size_t)B * c->V), TPB, 0, st>>>(*c, B, verts, w[0], losses + 0, d_verts);
-  if (c->NP > 0) normal_consistency_kernel<<<nblk((size_t)B * c->NP), TPB, 0, st>>>(*c, B, verts, w[1], losses + 1, d_verts);
-  if (ref_verts) arap_kernel<<<nblk((size_t)B * c->E), TPB, 0, st>>>(*c, B, verts, ref_verts, w[2], losses + 2, d_verts);
-  if (joints && init_joints_mm)
+  // a term runs when its inputs are there and its weight is not negative (weight 0: value only)
+  const bool on[5] = {w[0] >= 0.f, c->NP > 0 && w[1] >= 0.f, ref_verts && w[2] >= 0.f, joints && init_joints_mm && w[3] >= 0.f,
+                      disps && w[4] >= 0.f};
+  if (on[0]) laplacian_kernel<<<nblk((size_t)B * c->V), TPB, 0, st>>>(*c, B, verts, w[0], losses + 0, d_verts);
+  if (on[1]) normal_consistency_kernel<<<nblk((size_t)B * c->NP), TPB, 0, st>>>(*c, B, verts, w[1], losses + 1, d_verts);
+  if (on[2]) arap_kernel<<<nblk((size_t)B * c->E), TPB, 0, st>>>(*c, B, verts, ref_verts, w[2], losses + 2, d_verts);
+  if (on[3])
     kps_kernel<<<B, 32, 0, st>>>(B, c->n_joints_out >= 21 ? c->n_joints_out : 21, joints, init_joints_mm, w[3], losses + 3, d_joints);
-  if (disps) disp_reg_kernel<<<nblk(c->V), TPB, 0, st>>>(c->V, disps, w[4], losses + 4, d_disps);
-  HARP_LAUNCH_CHECK_N(1 + (c->NP > 0) + (ref_verts != nullptr) + (joints && init_joints_mm) + (disps != nullptr));
+  if (on[4]) disp_reg_kernel<<<nblk(c->V), TPB, 0, st>>>(c->V, disps, w[4], losses + 4, d_disps);
+  HARP_LAUNCH_CHECK_N(on[0] + on[1] + on[2] + on[3] + on[4]);
   return HARP_OK;
 }

@@ -7,7 +7,7 @@ from . import ops
 
 
 def _mesh_term(meshes, index, ref_verts=None):
-    return ops.MeshLosses.apply(meshes.hc, meshes.verts_padded(), ref_verts, None, None, None)[index]
+    return ops.MeshTerm.apply(meshes.hc, index, meshes.verts_padded(), ref_verts, None, None, None)
 
 
 def mesh_laplacian_smoothing(meshes, method="uniform"):
@@ -37,7 +37,7 @@ def kps_loss(gt_kps, pred_kps, use_arm=False, device="cuda"):
     if hc is None:
         raise ValueError(f"kps_loss: no registered context on {pred_kps.device} produces {nj} joints")
     dummy = torch.zeros(B, hc.V, 3, device=pred_kps.device)
-    return ops.MeshLosses.apply(hc, dummy, None, pred_kps, gt_kps.to(pred_kps.device), None)[3]
+    return ops.MeshTerm.apply(hc, 3, dummy, None, pred_kps, gt_kps.to(pred_kps.device), None)
 
 
 def _draw_offsets(shape_hw, std):

@@ -321,6 +321,39 @@ class MeshLosses(torch.autograd.Function):
         return None, d_verts, None, d_joints, None, d_disps
 
 
+class MeshTerm(torch.autograd.Function):
+    """ONE term of `harp_mesh_losses` (which: 0 laplacian, 1 normal consistency, 2 arap, 3 kps, 4 sum disp^2) as a scalar with
+    its unit-weight gradient precomputed in the same launch — what the drop-in loss functions call one at a time
+    (optimize_sequence.py:524-540); `MeshLosses` is the all-terms variant."""
+
+    @staticmethod
+    def forward(ctx, hc, which, verts, ref_verts, joints, init_joints_mm, disps):
+        verts = _c(verts)
+        B, dev = verts.shape[0], verts.device
+        ref = _c(ref_verts).view(-1, 3) if ref_verts is not None else None
+        joints_c = _c(joints) if joints is not None else None
+        init_c = _c(init_joints_mm) if init_joints_mm is not None else None
+        disps_c = _c(disps).view(-1) if disps is not None else None
+        losses = torch.zeros(5, device=dev)
+        gv = torch.zeros(B, hc.V, 3, device=dev) if which in (0, 1, 2) else None
+        gj = torch.zeros_like(joints_c) if which == 3 else None
+        gd = torch.zeros(hc.V, device=dev) if which == 4 else None
+        w = [-1.0] * 5  # negative weight: the term is not evaluated at all
+        w[which] = 1.0
+        check(_lib.lib().harp_mesh_losses(hc.h, B, ptr(verts), ptr(ref), ptr(joints_c), ptr(init_c), ptr(disps_c), (C.c_float * 5)(*w),
+                                          ptr(losses), ptr(gv), ptr(gj), ptr(gd), stream()))
+        ctx.which, ctx.disps_shape = which, disps.shape if disps is not None else None
+        ctx.save_for_backward(*[t for t in (gv, gj, gd) if t is not None])
+        return losses[which]
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        w = ctx.which
+        return (None, None, g * grad if w < 3 else None, None, g * grad if w == 3 else None, None,
+                (g * grad).view(ctx.disps_shape) if w == 4 else None)
+
+
 class Silhouette(torch.autograd.Function):
     """MeshRasterizer(K=50) + SoftSilhouetteShader alpha channel (renderer_helper.py:37-58)."""
 

@@ -7,6 +7,26 @@ from .pbr_materials import PBRMaterials
 from .structures import Meshes, TexturesUV, TexturesVertex
 
 
+_DEVICE_COPIES = {}
+
+
+def _on_device(t, device):
+    """Static tables (faces_uvs, verts_uvs) that callers keep on the host, as the reference's init_params does
+    (optimize_sequence.py:222-223): one host->device copy per tensor version instead of one per call."""
+    dev = torch.device(device)
+    if t.device.type == dev.type and (dev.index is None or t.device.index == dev.index):
+        return t
+    key = (id(t), t._version, str(dev))
+    hit = _DEVICE_COPIES.get(key)
+    if hit is None or hit[0]() is not t:
+        import weakref
+        if len(_DEVICE_COPIES) > 64:
+            _DEVICE_COPIES.clear()
+        hit = (weakref.ref(t), t.to(dev))
+        _DEVICE_COPIES[key] = hit
+    return hit[1]
+
+
 def prepare_mesh(params, fid, mano_layer, verts_textures, mesh_subdivider, global_pose, configs, device="cuda",
                  vis_normal=False, shared_texture=True, use_arm=False):
     """-> (hand_joints (B,21,3) m, hand_verts (B,V,3) m, faces (B,F,3), textures).
@@ -35,7 +55,7 @@ def prepare_mesh(params, fid, mano_layer, verts_textures, mesh_subdivider, globa
         textures = TexturesVertex(params["verts_rgb"].repeat(B, 1, 1).float().to(device))
     else:
         uv_map = params["texture"][None, 0].to(device) if shared_texture else params["texture"].to(device)
-        textures = TexturesUV(maps=uv_map, faces_uvs=params["faces_uvs"].to(device), verts_uvs=params["verts_uvs"].to(device))
+        textures = TexturesUV(maps=uv_map, faces_uvs=_on_device(params["faces_uvs"], device), verts_uvs=_on_device(params["verts_uvs"], device))
     return joints, verts, faces, textures
 
 
@@ -44,7 +64,8 @@ def prepare_materials(params, batch_size, shared_texture=True, device="cuda"):
     if "normal_map" not in params:
         return {"normal_maps": None}
     nm = params["normal_map"][None, 0].to(device) if shared_texture else params["normal_map"].to(device)
-    return {"normal_maps": TexturesUV(maps=nm, faces_uvs=params["faces_uvs"].to(device), verts_uvs=params["verts_uvs"].to(device))}
+    return {"normal_maps": TexturesUV(maps=nm, faces_uvs=_on_device(params["faces_uvs"], device),
+                                      verts_uvs=_on_device(params["verts_uvs"], device))}
 
 
 def render_image(mesh, cam, batch_size, renderer, img_size, focal_length, silhouette=False, device="cuda",

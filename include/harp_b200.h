@@ -162,7 +162,8 @@ HARP_API int harp_vertex_normals_bwd(harp_ctx*, int B, const float* verts, const
  * mesh_laplacian_smoothing / mesh_normal_consistency (optimize_sequence.py:536-537), arap_loss (loss/arap.py:4-57),
  * kps_loss (loss/kps_loss.py:4-17), sum(disp^2) (optimize_sequence.py:533).
  * w[5] = upstream weights for {laplacian, normal, arap, kps, disp}; losses[5] (device) receives the UNWEIGHTED values
- * (accumulated, zero it first); gradients are weighted.  ref_verts (V,3); joints (B,n_joints_out,3) m of the ctx's model
+ * (accumulated, zero it first); gradients are weighted; a term with weight 0 still reports its value, a term with a NEGATIVE
+ * weight (or without its inputs) is not evaluated.  ref_verts (V,3); joints (B,n_joints_out,3) m of the ctx's model
  * (21 for MANO / no model, 22 for the arm: the first 21 are used); init_joints (B,21,3) mm. */
 HARP_API int harp_mesh_losses(harp_ctx*, int B, const float* verts, const float* ref_verts, const float* joints,
                      const float* init_joints_mm, const float* disps, const float w[5], float* losses,

@@ -18,3 +18,5 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     bench.dropin_leg(sc, hc, B, S, steps=2, warmup=0)
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+print("\n==== by host time (the step is bound by the host: CPU RNG draws of the texture regularisers, pageable host->device copies, ATen launches)")
+print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=25, max_name_column_width=70))
