@@ -400,6 +400,7 @@ def main():
         d2h = len(LOSS_NAMES) * 4
         k_e2e = 0 if args.no_e2e else max(3, min(args.steps, 50))  # (the first upload of a leg is not overlapped: amortised)
         e2e_s = e2e_u8_s = 1e-9
+        e2e_res = None
         h2d_u8 = 0
         if k_e2e:
             def stage_f32():
@@ -426,6 +427,28 @@ def main():
                 return lambda: ft.step(fid, oa, on, stage="both", update=True, batch_u8=s)
 
             e2e_u8_s = e2e_leg(host_u8, stage_u8, run_u8, k_e2e)
+
+        # Epoch-level end to end (how HARP uses the path: hundreds of epochs over the same frames, optimize_sequence.py:
+        # 440-446): the sequence is uploaded ONCE from the pinned host buffers into the fitter's resident frame tensors, then
+        # every step runs on resident frames and returns its loss vector to the host.
+        if k_e2e:
+            k_res = max(k_e2e, min(args.steps, 300))
+            lh = torch.empty(k_res, len(LOSS_NAMES), pin_memory=True)
+            sync()
+            t0 = time.perf_counter()
+            for k, v in host.items():
+                ft.frames[k].copy_(v, non_blocking=True)
+            for i in range(k_res):
+                run_step()
+                lh[i].copy_(ft.losses, non_blocking=True)
+            sync()
+            sec = torch.tensor([max(time.perf_counter() - t0, 1e-9)], device=dev)
+            if world > 1:
+                dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+            e2e_res = {"value": world * B * k_res / float(sec), "unit": UNIT, "steps": k_res, "h2d_bytes_total": h2d,
+                       "d2h_bytes_per_step": d2h,
+                       "what": "frames uploaded once (fp32, pinned host -> device), then every step on resident frames with its loss "
+                               "vector read back: the reference's epoch loop over a fixed sequence"}
 
     if rank == 0:
         value = world * B * args.steps / (ms_total * 1e-3)
@@ -462,6 +485,7 @@ def main():
                         "steps": k_e2e, "host_dtype": "fp32 (the reference DataLoader's tensors)", "host_affinity": host_affinity},
                 "e2e_uint8": {"value": world * B * k_e2e / e2e_u8_s, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
                               "steps": k_e2e, "host_dtype": "uint8 frames + masks, /255 and 3x3x2 erosion on the device"},
+                "e2e_resident_epochs": e2e_res,
                 "gpu_launches": int(launches), "launch_mode": "cuda_graph_replay" if use_graph else "eager",
                 "exchange": {"none": "single GPU", "peer": "reduce-scatter + all-gather kernel over NVLink peer memory inside the step graph",
                              "nccl": "one in-place NCCL allreduce after the step graph"}[exchange],
