@@ -153,31 +153,33 @@ __global__ void __launch_bounds__(GEO_THREADS) geo_bwd_kernel(harp_ctx c, GeoArg
   __syncthreads();
   lbs_prologue(c, s_pose, a.shape, s);
   // ---- camera / light glue backward (as frame_glue_bwd_kernel, glue.cu): rank 0, result (the centroid's gradient) to everyone
-  if (cl.rank == 0 && t == 0) {
-    const float* cam = a.cam + row * 3;
-    const float* dct = a.d_cam_T + (size_t)b * 3;
-    float den = (float)a.S * cam[0] + 1e-9f;
-    atomicAdd(a.g_cam + row * 3 + 0, dct[2] * (-(2.f * a.focal) * (float)a.S / (den * den)));
-    atomicAdd(a.g_cam + row * 3 + 1, -dct[0]);
-    atomicAdd(a.g_cam + row * 3 + 2, -dct[1]);
-    Dual<6> L[3], ct[3], R[9], T[3];
-    for (int i = 0; i < 3; ++i) { L[i] = Dual<6>::var(a.light_pos[i], i); ct[i] = Dual<6>::var(a.centroid[b * 3 + i], 3 + i); }
-    light_camera<Dual<6>>(L, ct, R, T);
-    float gg[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int k = 0; k < 9; ++k) {
-      float u = a.d_light_R[b * 9 + k];
-      for (int i = 0; i < 6; ++i) gg[i] += u * R[k].d[i];
+  if (cl.rank == 0 && t < 6) {
+    // thread i carries the tangent of input i (light position xyz, centroid xyz) through the look-at construction: the same
+    // per-component operations as one thread with six tangents, a third of the dependent chain
+    Dual<1> L[3], ct[3], R[9], T[3];
+    for (int i = 0; i < 3; ++i) {
+      L[i] = Dual<1>(a.light_pos[i]); ct[i] = Dual<1>(a.centroid[b * 3 + i]);
+      if (t == i) L[i].d[0] = 1.f;
+      if (t == 3 + i) ct[i].d[0] = 1.f;
     }
-    for (int k = 0; k < 3; ++k) {
-      float u = a.d_light_T[b * 3 + k];
-      for (int i = 0; i < 6; ++i) gg[i] += u * T[k].d[i];
-    }
-    if (a.g_light)
-      for (int i = 0; i < 3; ++i) atomicAdd(a.g_light + i, gg[i] + a.d_light_pos[b * 3 + i]);  // share_light_position: row 0
-    cl.st3_all(gc, mk3(gg[3] / (float)V, gg[4] / (float)V, gg[5] / (float)V));
-    if (b == 0 && a.g_amb) {
-      float sg = 1.f / (1.f + expf(-a.amb_ratio[0]));
-      atomicAdd(a.g_amb, a.d_amb[0] * sg * (1.f - sg));
+    light_camera<Dual<1>>(L, ct, R, T);
+    float gg = 0.f;
+    for (int k = 0; k < 9; ++k) gg += a.d_light_R[b * 9 + k] * R[k].d[0];
+    for (int k = 0; k < 3; ++k) gg += a.d_light_T[b * 3 + k] * T[k].d[0];
+    if (t < 3 && a.g_light) atomicAdd(a.g_light + t, gg + a.d_light_pos[b * 3 + t]);  // share_light_position: row 0
+    const float g3 = __shfl_sync(0x3fu, gg, 3), g4 = __shfl_sync(0x3fu, gg, 4), g5 = __shfl_sync(0x3fu, gg, 5);
+    if (t == 0) {
+      cl.st3_all(gc, mk3(g3 / (float)V, g4 / (float)V, g5 / (float)V));
+      const float* cam = a.cam + row * 3;
+      const float* dct = a.d_cam_T + (size_t)b * 3;
+      float den = (float)a.S * cam[0] + 1e-9f;
+      atomicAdd(a.g_cam + row * 3 + 0, dct[2] * (-(2.f * a.focal) * (float)a.S / (den * den)));
+      atomicAdd(a.g_cam + row * 3 + 1, -dct[0]);
+      atomicAdd(a.g_cam + row * 3 + 2, -dct[1]);
+      if (b == 0 && a.g_amb) {
+        float sg = 1.f / (1.f + expf(-a.amb_ratio[0]));
+        atomicAdd(a.g_amb, a.d_amb[0] * sg * (1.f - sg));
+      }
     }
   }
   // Three (V,3) arrays in shared memory, re-used as the phases go (every gather reads materialised vertices: computing the
