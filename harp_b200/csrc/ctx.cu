@@ -78,6 +78,11 @@ extern "C" int harp_ctx_profile_timeline(harp_ctx* c, float* out, int capacity, 
     out[2 * *n] = (float)o[i].first; out[2 * *n + 1] = ms;
     ++*n;
   }
+  if (!c->prof->in_graph) {  // eager launches: reading the timeline consumes every event (a captured graph keeps its nodes)
+    for (auto& e : o) cudaEventDestroy(e.second);
+    o.clear();
+    for (auto& v : c->prof->ev) v.clear();
+  }
   return HARP_OK;
 }
 

@@ -123,7 +123,8 @@ HARP_API int harp_ctx_profile(harp_ctx* ctx, int enable);
 HARP_API int harp_ctx_profile_read(harp_ctx* ctx, int kernel_id, float* total_ms, int* launches);
 /* Every profiling event in recording order: out[2k] = id, out[2k+1] = ms since the first event (even occurrences of an id open
  * its segment, odd ones close it).  Besides ids 0..7: 8 step prologue, 9 the render's side branch (light view, empty tiles),
- * 10 the regulariser branch.  Shows the gaps and the overlap that the per-id sums hide.  capacity in floats. */
+ * 10 the regulariser branch.  Shows the gaps and the overlap that the per-id sums hide.  capacity in floats.  Outside a captured graph the
+ * call consumes the events. */
 HARP_API int harp_ctx_profile_timeline(harp_ctx* ctx, float* out, int capacity, int* n);
 
 /* ---- MANO linear blend skinning: ManoLayer.forward (manopth/manolayer.py:108-296), use_pca=False, axis-angle -------

@@ -142,3 +142,38 @@ def test_forward_only_fused_render_matches_the_step_images(full_scene):
     assert float((a2 - alpha).abs().max()) <= 1e-6
     d = (r2 - rgb).abs().amax(-1)
     assert float((d <= 1e-4).double().mean()) >= 0.999, float((d <= 1e-4).double().mean())  # (torch light camera vs the in-kernel one)
+
+
+def test_full_size_alpha_is_reproducible_and_timeline_is_ordered(full_scene):
+    """Two runs of the same step write bit-identical images (the silhouette's factor product is order-independent in double;
+    visibility ties are settled exactly), and the profiling timeline reports the step's segments in dependency order."""
+    hc, sc = full_scene
+    ft = _fitter(hc, sc)
+    fid = torch.arange(FRAMES, device="cuda")
+    oa, on = sc["offsets"]["albedo"], sc["offsets"]["normal"]
+    hc.profile(2)
+    try:
+        ft.step(fid, oa, on, stage="both", update=False, frame_range=(0, FRAMES))
+        a0, r0 = ft.last["alpha"].clone(), ft.last["rgb"].clone()
+        hc.profile_read(detailed=True)  # drop the first run's events
+        ft.step(fid, oa, on, stage="both", update=False, frame_range=(0, FRAMES))
+        tl = {name: (b, e) for name, b, e in hc.profile_timeline()}
+    finally:
+        hc.profile(0)
+        hc.profile_read(detailed=True)
+    assert torch.equal(a0, ft.last["alpha"]) and torch.equal(r0, ft.last["rgb"])
+    for name in ("geo_fwd", "setup", "tile_raster", "shade", "render_tail", "geo_bwd", "side_branch", "regularisers"):
+        assert name in tl and tl[name][1] >= tl[name][0], (name, tl)
+    order = ["geo_fwd", "setup", "tile_raster", "shade", "render_tail", "geo_bwd"]
+    for a, b in zip(order, order[1:]):
+        assert tl[a][1] <= tl[b][0] + 1e-3, (a, b, tl)  # main-stream segments do not overlap
+    assert tl["side_branch"][1] <= tl["shade"][0] + 1e-3  # the shading waits for the light view
+
+
+def test_gpu_numa_lookup_never_raises():
+    from harp_b200 import hostmem
+    node, cpus = hostmem.gpu_numa_node("cuda:0")
+    assert (node is None and cpus is None) or (node >= 0 and len(cpus) > 0)
+    with hostmem.gpu_numa_affinity("cuda:0") as info:
+        pinned = torch.empty(1 << 20, pin_memory=True)
+        assert pinned.is_pinned() and set(info) == {"numa_node", "cpus"}
