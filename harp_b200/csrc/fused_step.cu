@@ -2,8 +2,8 @@
 // every loss of 517-553 except VGG, and the whole backward down to the parameter-table gradients — as ONE C-ABI call that
 // enqueues a fixed launch sequence on the caller's stream (capturable into a CUDA graph):
 //
-//   zero fill of the per-step gradient workspace
-//   geo_fwd                      (geom.cu)   rows of the tables -> LBS -> mesh build -> camera / light glue
+//   geo_fwd                      (geom.cu)   zero fill of the per-frame gradient accumulators; rows of the tables -> LBS -> mesh
+//                                            build -> camera / light glue
 //   |- regulariser branch (ctx stream): texture regularisers, Laplacian / normal consistency / ARAP / keypoints / sum disp^2
 //   harp_render_fused            (pixel.cu)  raster setup, tile rasteriser, light view, deferred shading, their backward
 //   geo_bwd                      (geom.cu)   glue, mesh build and LBS backward -> atomics on the table gradients
@@ -16,7 +16,7 @@ namespace {
 
 struct Workspace {
   float *verts0, *joints, *verts, *normals, *vposed, *cam_T, *light_b, *light_R, *light_T, *centroid, *amb, *cam_R;
-  float* zero_begin;  // everything from here on is zero-filled at the start of the step
+  float* zero_begin;  // everything from here on is zero-filled by geo_fwd at the start of the step
   float *d_verts, *d_normals, *d_joints, *d_cam_T, *d_light_pos, *d_light_R, *d_light_T, *d_amb;
   size_t zero_floats, total_floats;
 };
@@ -39,14 +39,6 @@ Workspace carve(const harp_ctx* c, int B, float* base) {
   w.zero_floats = o - z0;
   w.total_floats = o;
   return w;
-}
-
-// PyTorch3D's view of the reference camera: R = diag(-1, -1, 1) for every frame (utils/visualize.py:269-270)
-__global__ void flip_xy_kernel(int B, float* R) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * 9) return;
-  int k = i % 9;
-  R[i] = k == 0 || k == 4 ? -1.f : (k == 8 ? 1.f : 0.f);
 }
 
 }  // namespace
@@ -73,11 +65,10 @@ extern "C" int harp_step_fused(harp_ctx* c, const harp_step_args* p, void* strea
   const float* W = p->weights;  // silhouette, laplacian, normal, arap, kps_anchor, vert_disp_reg, photo, albedo, normal_reg
   Workspace w = carve(c, B, p->workspace);
   int rc;
-  harp_prof_begin(c, 8, st);
-  HARP_CHECK_CUDA(cudaMemsetAsync(w.zero_begin, 0, w.zero_floats * sizeof(float), st));
-  flip_xy_kernel<<<(B * 9 + 127) / 128, 128, 0, st>>>(B, w.cam_R);
-  HARP_LAUNCH_CHECK();
+  // (the zero fill of the per-frame gradient accumulators and the constant camera rotations are written by geo_fwd: two graph
+  // nodes less at the head of the step)
   GeoArgs g{};
+  g.cam_R = w.cam_R; g.zero_grads = 1;
   g.B = B; g.S = S; g.focal = p->focal; g.fid = p->fid;
   g.pose = p->pose; g.rot = p->rot; g.trans = p->trans; g.cam = p->cam; g.wrist = p->wrist_pose; g.shape = p->shape;
   g.disps = p->verts_disps; g.light_pos = p->light_position; g.amb_ratio = p->amb_ratio;
@@ -88,7 +79,6 @@ extern "C" int harp_step_fused(harp_ctx* c, const harp_step_args* p, void* strea
   g.g_pose = p->g_pose; g.g_cam = p->g_cam; g.g_rot = p->g_rot; g.g_wrist = p->g_wrist_pose; g.g_shape = p->g_shape;
   g.g_disps = p->g_verts_disps; g.g_light = p->g_light_position; g.g_amb = p->g_amb_ratio;
   g.d_rot = p->d_rot; g.d_trans = p->d_trans; g.d_wrist = p->d_wrist;
-  harp_prof_end(c, 8, st);
   if ((rc = harp_geo_fwd(c, g, st)) != HARP_OK) return rc;
   // ---- regulariser branch: depends only on the mesh / the textures; accumulates with atomics
   if (!c->reg_stream) {

@@ -64,6 +64,23 @@ __global__ void __launch_bounds__(GEO_THREADS) geo_fwd_kernel(harp_ctx c, GeoArg
   const int b = blockIdx.x / cl.n, t = threadIdx.x, J = c.J;
   const int64_t row = a.fid ? a.fid[b] : b;
   for (int i = t; i < J * 3; i += GEO_THREADS) s_pose[i] = assemble_pose(c, a, row, i);
+  if (a.zero_grads) {  // this frame's slices of the step's gradient accumulators (was a memset node at the head of the step)
+    const int n = c.V * 3, nj = c.n_joints_out * 3;
+    float* zv = const_cast<float*>(a.d_verts) + (size_t)b * n;
+    float* zn = const_cast<float*>(a.d_normals) + (size_t)b * n;
+    for (int i = cl.rank * GEO_THREADS + t; i < n; i += GEO_THREADS * cl.n) { zv[i] = 0.f; zn[i] = 0.f; }
+    if (cl.rank == 0) {
+      if (t < nj) const_cast<float*>(a.d_joints)[(size_t)b * nj + t] = 0.f;
+      if (t < 9) const_cast<float*>(a.d_light_R)[b * 9 + t] = 0.f;
+      if (t < 3) {
+        const_cast<float*>(a.d_cam_T)[b * 3 + t] = 0.f;
+        const_cast<float*>(a.d_light_pos)[b * 3 + t] = 0.f;
+        const_cast<float*>(a.d_light_T)[b * 3 + t] = 0.f;
+      }
+      if (b == 0 && t == 0) const_cast<float*>(a.d_amb)[0] = 0.f;
+    }
+  }
+  if (a.cam_R && cl.rank == 0 && t < 9) a.cam_R[b * 9 + t] = (t == 0 || t == 4) ? -1.f : (t == 8 ? 1.f : 0.f);
   __syncthreads();
   lbs_prologue(c, s_pose, a.shape, s);  // (every CTA of the cluster: a few hundred flops)
   // ---- LBS: vertices rank, rank + n, ... (interleaved by thread block) -> every CTA's v0s, and HBM

@@ -10,6 +10,8 @@ struct GeoArgs {
   // forward outputs
   float *verts0, *joints, *verts, *normals, *vposed;  // vposed: (B,V0,3) blend-shaped rest vertices, kept for the backward
   float *cam_T, *light_b, *light_R, *light_T, *centroid, *amb;  // (B,3) (B,3) (B,9) (B,3) (B,3) (1)
+  float* cam_R;     // (B,9) PyTorch3D's view of the reference camera, R = diag(-1, -1, 1) per frame (utils/visualize.py:269-270)
+  int zero_grads;   // the forward also zero-fills the "backward inputs" below (the step's per-frame gradient accumulators)
   // backward inputs
   const float *d_verts, *d_normals, *d_joints;
   const float *d_verts4, *d_normals4;  // optional (B,V,4) padded accumulators of the shading backward, added to d_verts / d_normals

@@ -10,6 +10,10 @@ int harp_raster_setup(harp_ctx* c, int view, int B, int S, float focal, float ra
 int harp_project_bwd(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R, const float* T,
                      const float* d_ndc, float* d_verts, float* d_R, float* d_T, cudaStream_t st);
 int harp_fold4(size_t n, const float* src4, float* dst3, cudaStream_t st);
+int harp_fold4_pair(size_t n, const float* src4, float* dst_a, float* dst_b, cudaStream_t st);
+int harp_project_bwd2(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R0, const float* T0, const float* d_ndc0,
+                      float* d_R0, float* d_T0, const float* R1, const float* T1, const float* d_ndc1, float* d_R1, float* d_T1,
+                      float* d_verts, cudaStream_t st);
 int harp_tex_prepare(harp_ctx* c, const float* texture, const float* normal_map, int texH, int texW, cudaStream_t st);
 int harp_light_depth_tiles(harp_ctx* c, int B, int S, bool zero_grad, cudaStream_t st);
 int harp_light_view_setup(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R, const float* T, bool zero_grad,
@@ -792,15 +796,18 @@ int render_pass(harp_ctx* c, int B, int S, float focal, const harp_render_args* 
       if ((rc = harp_fold4((size_t)B * c->V, c->d_verts4, r->grads.d_verts, st)) != HARP_OK) return rc;
       if ((rc = harp_fold4((size_t)B * c->V, c->d_normals4, r->grads.d_normals, st)) != HARP_OK) return rc;
     }
-    if (r->grads.d_texture && (rc = harp_fold4(ntex, c->d_tex4, r->grads.d_texture, st)) != HARP_OK) return rc;
-    if (r->grads.d_normal_map && (rc = harp_fold4(ntex, c->d_tex4 + ntex * 4, r->grads.d_normal_map, st)) != HARP_OK) return rc;
-    if (shadow) {
-      if ((rc = harp_light_depth_bwd_tiles(c, B, S, st)) != HARP_OK) return rc;
-      if ((rc = harp_project_bwd(c, B, S, focal, r->verts, r->light_R, r->light_T, c->d_ndc_light, r->grads.d_verts,
-                                 r->grads.d_light_R, r->grads.d_light_T, st)) != HARP_OK) return rc;
+    if (r->grads.d_texture && r->grads.d_normal_map) {
+      if ((rc = harp_fold4_pair(ntex, c->d_tex4, r->grads.d_texture, r->grads.d_normal_map, st)) != HARP_OK) return rc;
+    } else {
+      if (r->grads.d_texture && (rc = harp_fold4(ntex, c->d_tex4, r->grads.d_texture, st)) != HARP_OK) return rc;
+      if (r->grads.d_normal_map && (rc = harp_fold4(ntex, c->d_tex4 + ntex * 4, r->grads.d_normal_map, st)) != HARP_OK) return rc;
     }
+    if (shadow && (rc = harp_light_depth_bwd_tiles(c, B, S, st)) != HARP_OK) return rc;
   }
-  if (sil_bwd || shade_bwd) {
+  if (shade_bwd && shadow) {  // both views' projection backward in one launch
+    if ((rc = harp_project_bwd2(c, B, S, focal, r->verts, r->cam_R, r->cam_T, c->d_ndc_cam, r->grads.d_cam_R, r->grads.d_cam_T, r->light_R,
+                                r->light_T, c->d_ndc_light, r->grads.d_light_R, r->grads.d_light_T, r->grads.d_verts, st)) != HARP_OK) return rc;
+  } else if (sil_bwd || shade_bwd) {
     if ((rc = harp_project_bwd(c, B, S, focal, r->verts, r->cam_R, r->cam_T, c->d_ndc_cam, r->grads.d_verts, r->grads.d_cam_R,
                                r->grads.d_cam_T, st)) != HARP_OK) return rc;
   }

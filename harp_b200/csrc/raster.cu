@@ -11,15 +11,23 @@ namespace {
 constexpr int TPB = 256;
 
 // backward of the projection (setup.cu, phase 0): d_ndc (B,V,4: xyz + pad) -> d_verts += , d_R += , d_T +=
-__global__ void __launch_bounds__(TPB) project_bwd_kernel(int B, int V, const float* __restrict__ verts, const float* __restrict__ R,
-                                                           const float* __restrict__ T, float focal, float half_s,
-                                                           const float* __restrict__ d_ndc, float* __restrict__ d_verts,
-                                                           float* __restrict__ d_R, float* __restrict__ d_T) {
+struct ProjView {
+  const float *R, *T, *d_ndc;
+  float *d_R, *d_T;
+};
+
+// blockIdx.z selects the view (camera / light): both backward projections of the shading step are one launch
+__global__ void __launch_bounds__(TPB) project_bwd_kernel(int B, int V, const float* __restrict__ verts, ProjView va, ProjView vb,
+                                                           float focal, float half_s, float* __restrict__ d_verts) {
   __shared__ float red[32];
+  const ProjView pv = blockIdx.z == 0 ? va : vb;
+  const float* __restrict__ d_ndc = pv.d_ndc;
+  float* __restrict__ d_R = pv.d_R;
+  float* __restrict__ d_T = pv.d_T;
   int b = blockIdx.y;
   int v = blockIdx.x * blockDim.x + threadIdx.x;
-  const float* r = R + (size_t)b * 9;
-  const float* t = T + (size_t)b * 3;
+  const float* r = pv.R + (size_t)b * 9;
+  const float* t = pv.T + (size_t)b * 3;
   float acc[12];
 #pragma unroll
   for (int i = 0; i < 12; ++i) acc[i] = 0.f;
@@ -146,11 +154,14 @@ __global__ void __launch_bounds__(32 * TOPK_WARPS) sil_topk_kernel(harp_ctx c, i
   }
 }
 
-// dst (n,3) += src (n,4).xyz
-__global__ void __launch_bounds__(TPB) fold4_kernel(size_t n, const float4* __restrict__ src, float* __restrict__ dst) {
+// dst (n,3) += src (n,4).xyz; rows n .. 2n-1 of src go to dst_b (the texture and the normal map fold in one launch)
+__global__ void __launch_bounds__(TPB) fold4_kernel(size_t n, size_t total, const float4* __restrict__ src, float* __restrict__ dst_a,
+                                                    float* __restrict__ dst_b) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= total) return;
   float4 v = src[i];
+  float* dst = dst_a;
+  if (i >= n) { dst = dst_b; i -= n; }
   if (v.x != 0.f || v.y != 0.f || v.z != 0.f) {  // atomics: other branches of the step may accumulate into dst concurrently
     atomicAdd(dst + i * 3, v.x); atomicAdd(dst + i * 3 + 1, v.y); atomicAdd(dst + i * 3 + 2, v.z);
   }
@@ -173,15 +184,34 @@ int harp_sil_topk(harp_ctx* c, int mode, int S, int K, float sigma, float blur, 
 }
 
 int harp_fold4(size_t n, const float* src4, float* dst3, cudaStream_t st) {
-  fold4_kernel<<<nblk(n), TPB, 0, st>>>(n, reinterpret_cast<const float4*>(src4), dst3);
+  fold4_kernel<<<nblk(n), TPB, 0, st>>>(n, n, reinterpret_cast<const float4*>(src4), dst3, nullptr);
+  HARP_LAUNCH_CHECK();
+  return HARP_OK;
+}
+
+// src4 holds two (n,4) blocks back to back: the first folds into dst_a, the second into dst_b
+int harp_fold4_pair(size_t n, const float* src4, float* dst_a, float* dst_b, cudaStream_t st) {
+  fold4_kernel<<<nblk(2 * n), TPB, 0, st>>>(n, 2 * n, reinterpret_cast<const float4*>(src4), dst_a, dst_b);
   HARP_LAUNCH_CHECK();
   return HARP_OK;
 }
 
 int harp_project_bwd(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R, const float* T,
                      const float* d_ndc, float* d_verts, float* d_R, float* d_T, cudaStream_t st) {
-  dim3 grid((c->V + TPB - 1) / TPB, B);
-  project_bwd_kernel<<<grid, TPB, 0, st>>>(B, c->V, verts, R, T, focal, 0.5f * (float)S, d_ndc, d_verts, d_R, d_T);
+  dim3 grid((c->V + TPB - 1) / TPB, B, 1);
+  ProjView v{R, T, d_ndc, d_R, d_T};
+  project_bwd_kernel<<<grid, TPB, 0, st>>>(B, c->V, verts, v, v, focal, 0.5f * (float)S, d_verts);
+  HARP_LAUNCH_CHECK();
+  return HARP_OK;
+}
+
+// camera and light view in one launch (both accumulate into d_verts with atomics)
+int harp_project_bwd2(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R0, const float* T0, const float* d_ndc0,
+                      float* d_R0, float* d_T0, const float* R1, const float* T1, const float* d_ndc1, float* d_R1, float* d_T1,
+                      float* d_verts, cudaStream_t st) {
+  dim3 grid((c->V + TPB - 1) / TPB, B, 2);
+  project_bwd_kernel<<<grid, TPB, 0, st>>>(B, c->V, verts, ProjView{R0, T0, d_ndc0, d_R0, d_T0}, ProjView{R1, T1, d_ndc1, d_R1, d_T1}, focal,
+                                           0.5f * (float)S, d_verts);
   HARP_LAUNCH_CHECK();
   return HARP_OK;
 }

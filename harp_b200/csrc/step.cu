@@ -1,6 +1,8 @@
 // Per-step (not per-frame) pieces: texture regularisers and fused Adam.
 // Replaces loss/texture_reg.py:5-66 and torch.optim.Adam.step on the CPU-resident texture / normal map
 // (optimize_sequence.py:253-310,567-573).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -165,30 +167,37 @@ __global__ void __launch_bounds__(TPB) image_metrics_kernel(int S2, const float*
 
 struct AdamState {
   int step;
-  float bc1, bc2_sqrt;
-  float lr;  // read only when the call passes lr < 0 (a 3-word state stays valid for lr >= 0)
+  unsigned int done;  // CTAs of the running update that have finished (the last one advances `step` and re-arms this)
+  float unused;
+  float lr;           // read only when the call passes lr < 0
 };
 
-__global__ void adam_tick_kernel(AdamState* st, float b1, float b2) {
-  int s = st->step + 1;
-  st->step = s;
-  st->bc1 = 1.f - powf(b1, (float)s);
-  st->bc2_sqrt = sqrtf(1.f - powf(b2, (float)s));
-}
-
+// One launch per parameter group: every thread derives the bias corrections of step + 1 itself (two powf against a 20-byte
+// read-modify-write per element), and the last CTA to finish advances the step counter — the separate one-thread "tick"
+// launch this replaces was a graph node on the step's critical path.
 __global__ void __launch_bounds__(TPB) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
-                                                        const AdamState* __restrict__ st) {
+                                                        AdamState* __restrict__ st) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float bc1 = st->bc1, bc2s = st->bc2_sqrt;
-  if (lr < 0.f) lr = st->lr;  // learning rate on the device: a scheduler can change it under a captured graph
-  float gi = g[i];
-  float mi = m[i] + (1.f - b1) * (gi - m[i]);
-  float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-  m[i] = mi;
-  v[i] = vi;
-  p[i] -= (lr / bc1) * (mi / (sqrtf(vi) / bc2s + eps));
+  const int s = st->step + 1;  // (nobody writes `step` before every CTA has read it: see below)
+  if (i < n) {
+    float bc1 = 1.f - powf(b1, (float)s), bc2s = sqrtf(1.f - powf(b2, (float)s));
+    if (lr < 0.f) lr = st->lr;  // learning rate on the device: a scheduler can change it under a captured graph
+    float gi = g[i];
+    float mi = m[i] + (1.f - b1) * (gi - m[i]);  // lerp, as torch._single_tensor_adam
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= (lr / bc1) * (mi / (sqrtf(vi) / bc2s + eps));
+  }
+  __syncthreads();  // every thread of this CTA has read `step`
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&st->done, 1u) == gridDim.x - 1) {  // the last CTA: all others are past their read of `step`
+      st->done = 0u;
+      st->step = s;
+    }
+  }
 }
 
 }  // namespace
@@ -197,11 +206,9 @@ extern "C" int harp_adam_dev(float* param, const float* grad, float* exp_avg, fl
                              float beta1, float beta2, float eps, void* state, void* stream) {
   HARP_REQUIRE(param && grad && exp_avg && exp_avg_sq && state && n >= 0, HARP_ERR_INVALID, "harp_adam_dev: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  adam_tick_kernel<<<1, 1, 0, st>>>((AdamState*)state, beta1, beta2);
-  if (n > 0)
-    adam_dev_kernel<<<(int)((n + TPB - 1) / TPB), TPB, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                                (const AdamState*)state);
-  HARP_LAUNCH_CHECK_N(2);
+  adam_dev_kernel<<<(int)((std::max<int64_t>(n, 1) + TPB - 1) / TPB), TPB, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                                                   eps, (AdamState*)state);
+  HARP_LAUNCH_CHECK();
   return HARP_OK;
 }
 

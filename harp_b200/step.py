@@ -43,7 +43,7 @@ class _Flat:
             self.data[a:b].copy_(t.detach().reshape(-1).to(device))
             self.p[name] = self.data[a:b].view(t.shape)
             self.g[name] = self.grad[a:b].view(t.shape)
-        # {int32 step, float bias_correction1, float sqrt(bias_correction2)} on the device: the update is graph-capturable
+        # {int32 step, two scratch words, float lr} on the device: the update is graph-capturable
         # and the learning rate, so a scheduler can change it under a captured graph
         self.state = torch.zeros(4, dtype=torch.int32, device=device)
 

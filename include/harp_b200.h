@@ -295,8 +295,9 @@ HARP_API int harp_adam(float* param, const float* grad, float* exp_avg, float* e
               float beta2, float eps, int step, void* stream);
 
 /* Same update with the step counter on the device, so the launch can be captured in a CUDA graph and replayed:
- * state = {int32 step, float bias_correction1, float sqrt(bias_correction2)[, float lr]} (3 or 4 x 4 bytes, zero-initialised
- * by the caller); each call increments state.step first.  lr < 0: the learning rate is read from state[3] on the device, so a
+ * state = {int32 step, uint32 scratch, uint32 scratch[, float lr]} (3 or 4 x 4 bytes, zero-initialised by the caller); each call
+ * updates with the bias corrections of step + 1 and leaves state.step incremented (ONE launch: the last CTA to finish advances
+ * the counter).  lr < 0: the learning rate is read from state[3] on the device, so a
  * scheduler (ReduceLROnPlateau, optimize_sequence.py:312-321) can change it without re-capturing the graph. */
 HARP_API int harp_adam_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                            float beta2, float eps, void* state, void* stream);
