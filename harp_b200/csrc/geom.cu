@@ -49,6 +49,10 @@ struct Cluster {
     for (int r = 0; r < n; ++r) st3(g.map_shared_rank(local, r), v);
   }
   __device__ __forceinline__ void sync() const { g.sync(); }
+  // A peer's shared memory may be written only once that CTA has started: every CTA arrives at kernel entry and waits right
+  // before its first remote store (split barrier: the work in between hides it).
+  __device__ __forceinline__ void entered_arrive() const { g.barrier_arrive(); }
+  __device__ __forceinline__ void entered_wait() const { g.barrier_wait(); }
 };
 
 __global__ void __launch_bounds__(GEO_THREADS) geo_fwd_kernel(harp_ctx c, GeoArgs a) {
@@ -61,6 +65,7 @@ __global__ void __launch_bounds__(GEO_THREADS) geo_fwd_kernel(harp_ctx c, GeoArg
   __shared__ float red[32];
   __shared__ float s_csum[4][3];           // centroid partial sums of the cluster's CTAs (rank 0's copy is used)
   const Cluster cl;
+  cl.entered_arrive();
   const int b = blockIdx.x / cl.n, t = threadIdx.x, J = c.J;
   const int64_t row = a.fid ? a.fid[b] : b;
   for (int i = t; i < J * 3; i += GEO_THREADS) s_pose[i] = assemble_pose(c, a, row, i);
@@ -90,6 +95,7 @@ __global__ void __launch_bounds__(GEO_THREADS) geo_fwd_kernel(harp_ctx c, GeoArg
       off = off - mk3(s.G[c.center_joint][3], s.G[c.center_joint][7], s.G[c.center_joint][11]);
     float* v0g = a.verts0 + (size_t)b * c.V0 * 3;
     float* vpg = a.vposed ? a.vposed + (size_t)b * c.V0 * 3 : nullptr;
+    cl.entered_wait();  // every CTA of the cluster is running: its shared memory may be written from here on
     for (int v = cl.rank * GEO_THREADS + t; v < c.V0; v += GEO_THREADS * cl.n) {
       f3 vp = lbs_v_posed(c, s, v);
       if (vpg) st3(vpg + (size_t)v * 3, vp);  // kept for the backward (saves its pass over the pose blendshapes)
@@ -162,6 +168,7 @@ __global__ void __launch_bounds__(GEO_THREADS) geo_bwd_kernel(harp_ctx c, GeoArg
   float* C = Bf + (size_t)c.V * 3;
   __shared__ float gc[3];
   const Cluster cl;
+  cl.entered_arrive();
   const int b = blockIdx.x / cl.n, t = threadIdx.x, J = c.J, NS = c.n_shape, V = c.V;
   const int64_t row = a.fid ? a.fid[b] : b;
   for (int i = t; i < J * 3; i += GEO_THREADS) s_pose[i] = assemble_pose(c, a, row, i);
@@ -169,6 +176,7 @@ __global__ void __launch_bounds__(GEO_THREADS) geo_bwd_kernel(harp_ctx c, GeoArg
   for (int i = t; i < c.V0 * 3; i += GEO_THREADS) v0s[i] = v0g[i];
   __syncthreads();
   lbs_prologue(c, s_pose, a.shape, s);
+  cl.entered_wait();  // every CTA of the cluster is running: its shared memory may be written from here on
   // ---- camera / light glue backward (as frame_glue_bwd_kernel, glue.cu): rank 0, result (the centroid's gradient) to everyone
   if (cl.rank == 0 && t < 6) {
     // thread i carries the tangent of input i (light position xyz, centroid xyz) through the look-at construction: the same

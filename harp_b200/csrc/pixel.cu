@@ -185,7 +185,13 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
   __shared__ unsigned char s_win[CHUNK * 2 + 2];  // unit of the first pair of every 32-pair window
   __shared__ int s_scan0, s_nu;
   __shared__ float s_g[NT], s_prod[NT];
-  __shared__ unsigned char s_need[NT], s_sat[NT];
+  // a pixel with one exactly-zero factor has alpha = 1 and no gradient.  s_sat is set by the classification (phase A) and read
+  // by the drain (phase B) after a barrier; s_sat2 is set by the drain; the epilogue reads both.  Phase A also PEEKS at s_sat
+  // while other lanes set it, to keep band pairs of already-saturated pixels out of the queue (without it, tiles where fingers
+  // overlap the palm overflow the queue and fall back to the exact top-K kernel: +0.4 ms per step).  That read is a deliberate,
+  // benign race — the flag only moves 0 -> 1 and a stale 0 merely queues an entry the drain then skips — and the only access
+  // compute-sanitizer's racecheck reports in this library (profiles/r02_compute_sanitizer.txt).
+  __shared__ unsigned char s_need[NT], s_sat[NT], s_sat2[NT];
   __shared__ float s_px[HARP_TILE], s_py[HARP_TILE];
   __shared__ float red[4];
   __shared__ int s_qn, s_tn, s_next, s_ovf;
@@ -200,6 +206,7 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
   }
   __syncthreads();
   int idx = s_next;
+  __syncthreads();  // (thread 0 overwrites s_next at the top of the tile loop)
   if (idx >= total) return;
   auto load_item = [&](int i) { return a.work[i < n_heavy ? i : a.work_cap - 1 - (i - n_heavy)]; };
   // one bulk copy per face of the round, issued by warp 0; completion is counted in bytes on the buffer's mbarrier
@@ -220,7 +227,7 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
   issue(item, 0, 0);
   while (true) {
     // ---- per-tile state; fetch the next work item and request its first round of records
-    s_vis[tid] = 0ULL; s_cnt[tid] = 0; s_head[tid] = -1; s_sat[tid] = 0;
+    s_vis[tid] = 0ULL; s_cnt[tid] = 0; s_head[tid] = -1; s_sat[tid] = 0; s_sat2[tid] = 0;
     const int b = item.x, tile = item.y, n = item.w;
     const int tx0 = (tile % tw) * HARP_TILE, ty0 = (tile / tw) * HARP_TILE;
     if (tid < HARP_TILE) s_px[tid] = pix_to_ndc(tx0 + tid, S);
@@ -387,7 +394,7 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
           if (SIL) {
             if (cls != PAIR_REJECT && count_cand) atomicAdd(&s_cnt[pix], 1);  // upper bound on PyTorch3D's candidates
             if (cls == PAIR_SATURATED) s_sat[pix] = 1;  // one exactly-zero factor: alpha = 1, zero gradient
-            bool band = cls == PAIR_FULL && !s_sat[pix];
+            bool band = cls == PAIR_FULL && !s_sat[pix];  // (benign race, see s_sat)
             unsigned bm = __ballot_sync(0xffffffffu, band);
             if (bm) {
               int qb = 0;
@@ -434,7 +441,7 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
             e.sd = inside ? -dist : dist; e.t = t; e.edge = (unsigned char)edge;
             float om = 1.f - 1.f / (1.f + expf(fdiv(e.sd, sigma)));  // 1 - sigmoid(-sd / sigma)
             s_om[s] = om;
-            if (om == 0.f) s_sat[pix] = 1;  // an exactly-zero factor: alpha = 1, zero gradient
+            if (om == 0.f) s_sat2[pix] = 1;  // an exactly-zero factor: alpha = 1, zero gradient
           } else {
             e.edge = 255;
           }
@@ -510,7 +517,7 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
       int nzero = 0, npass = 0;
       bool deferred = false;
       if (SIL) {
-        nzero = s_sat[tid] ? 1 : 0; npass = nzero;
+        nzero = (s_sat[tid] | s_sat2[tid]) ? 1 : 0; npass = nzero;
         if (nzero == 0) {
           double dp = 1.0;
           for (int s = s_head[tid]; s >= 0; s = s_q[s].next) {
