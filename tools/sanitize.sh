@@ -18,6 +18,13 @@ for name in ("c2_full_128_sub", "c4_arm_128_sub"):
         ft.step(fid, batch["off_albedo"].cuda().int().contiguous(), batch["off_normal"].cuda().int().contiguous(), stage="both", update=True)
     torch.cuda.synchronize()
     print(name, ft.loss_dict()["total"], hc.counters())
+# the Level-1 drop-in loop body (stand-alone silhouette / shade ops forward and backward, single-term mesh losses, hit mask,
+# evaluation renderers)
+import test_gpu_dropin as D
+for name in ("c2_full_128_sub", "c4_arm_128_sub"):
+    loss, total, leaf, y_sil_pred, y_pred = D._loop_body(load_golden(name), "both")
+    torch.cuda.synchronize()
+    print("dropin", name, float(total))
 # upstream per-frame MANO fit (a few eager iterations)
 import numpy as np
 from harp_b200 import mano_fit, synth
@@ -30,5 +37,5 @@ print("mano_fit", mano_fit.optimize_for_mano_param.last_loss)
 PY
 for tool in memcheck racecheck; do
   echo "== compute-sanitizer --tool $tool"
-  compute-sanitizer --tool $tool --print-limit 5 python /tmp/san.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Error:|hazard|c2_full|c4_arm|mano_fit|Invalid|at 0x" | head -20
+  compute-sanitizer --tool $tool --print-limit 100 python /tmp/san.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Error:|hazard|c2_full|c4_arm|mano_fit|dropin|Invalid|at 0x" | sort | uniq -c | sort -rn | head -30
 done
