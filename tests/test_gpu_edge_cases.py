@@ -1,4 +1,4 @@
-"""GPU parity of the fused step (pixel_vis + shade_deferred, the optimised path) on framings the golden cases do not reach:
+"""GPU parity of the fused step (tile_raster + shade_deferred, the optimised path) on framings the golden cases do not reach:
 a hand partly outside the image, a frame with no hand at all, a hand that crosses the camera plane (vertices with z <= 0:
 the classification's exact path), a tiny hand (many faces per tile: multi-chunk tiles and the top-K deferral), and an odd
 batch size.  The checker is the CPU oracle's whole step (`O.step`) on identical inputs."""
