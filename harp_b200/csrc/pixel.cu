@@ -1,8 +1,10 @@
 // The fused pixel pass of the optimiser step: ONE walk over each tile's face list yields the soft silhouette (value, L1
 // loss, gradient) AND the nearest covering face of every pixel; hit pixels are compacted per frame and shaded (forward,
 // photometric L1, backward) by a second kernel whose warps are full and barrier-free.
-// Replaces, per minibatch: the K=50 and the K=1 camera-view rasterisations (renderer_helper.py:44-58,353), both shaders
-// and blends, both image losses (optimize_sequence.py:519,543) and their autograd.
+// Replaces, per minibatch: the K=50 and the K=1 camera-view rasterisations (renderer_helper.py:44-58,353), the light-view
+// rasterisation (344), both shaders and blends, both image losses (optimize_sequence.py:519,543) and their autograd.
+// Entry points: harp_render_fused (both images, fused losses), harp_silhouette and harp_shade (one image each; forward,
+// upstream-gradient backward or fused loss) — all three are render_pass with different plans — and harp_hit_mask.
 #include "shade_pixel.cuh"
 
 int harp_raster_setup(harp_ctx* c, int view, int B, int S, float focal, float radius, const float* verts, const float* R,

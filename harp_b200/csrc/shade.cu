@@ -1,17 +1,11 @@
-// Shadowed PBR colour render, forward + analytic backward (+ fused photometric L1 loss).
-// Replaces MeshRendererShadow.forward (renderer/renderer_helper.py:331-412): two K=1 rasterisations, hit-point
-// interpolation, light-space depth, 3x3 PCF taps; SoftPhongShaderShadow / phong_shading_with_shadow (472-592): texture
-// + normal-map bilinear fetches (TexturesUV), PBRMaterials.apply_normal_map (pbr_materials.py:58-124),
-// Lambert lighting (A.7), softmax_rgb_blend at K=1 (A.4); and their autograd graph.
-// One pass per pixel, nothing staged in HBM except the light-view depth/face buffers the PCF taps must read.
+// What the colour renders need besides the per-pixel shading (shade_pixel.cuh, run by shade_deferred_kernel in pixel.cu): the
+// packed texel copies (prepare_materials' per-texel F.normalize, utils/visualize.py:98-99, done once per texel) and the
+// evaluation pass's normal renderer — MeshRasterizer(K=10) + SoftPhongNormalShader + softmax_rgb_blend
+// (renderer/renderer_helper.py:85-101, 216-301; forward only, the reference never differentiates through it).
 #include "shade_pixel.cuh"
 
 int harp_raster_setup(harp_ctx* c, int view, int B, int S, float focal, float radius, const float* verts, const float* R,
                       const float* T, cudaStream_t st, bool zero_grads = false);
-int harp_project_bwd(harp_ctx* c, int B, int S, float focal, const float* verts, const float* R, const float* T,
-                     const float* d_ndc, float* d_verts, float* d_R, float* d_T, cudaStream_t st);
-int harp_fold4(size_t n, const float* src4, float* dst3, cudaStream_t st);
-
 int harp_tex_prepare(harp_ctx* c, const float* texture, const float* normal_map, int texH, int texW, cudaStream_t st);
 
 namespace {
