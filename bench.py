@@ -339,6 +339,7 @@ def main():
     prof = hc.profile_read()
     hc.profile(False)
     cnt = hc.counters()
+    cnt["deferred_pixels_last_step"] = hc.deferred_pixels()  # exact top-K fallback (slower path), of B*S*S pixels
     losses = ft.loss_dict()
 
     def e2e_leg(host, make_stage, make_run, n):

@@ -65,7 +65,7 @@ _lib = None
 
 # every symbol include/harp_b200.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = ["harp_last_error", "harp_version", "harp_launch_count", "harp_ctx_profile", "harp_ctx_profile_read", "harp_ctx_profile_timeline", "harp_ctx_create", "harp_ctx_create_lbs", "harp_ctx_destroy", "harp_lbs_fwd", "harp_lbs_bwd", "harp_ctx_reserve", "harp_ctx_pin", "harp_ctx_dims",
-           "harp_ctx_faces", "harp_ctx_read_counters", "harp_lbs_mano_fwd", "harp_lbs_mano_bwd", "harp_mesh_build_fwd",
+           "harp_ctx_faces", "harp_ctx_read_counters", "harp_ctx_deferred_pixels", "harp_lbs_mano_fwd", "harp_lbs_mano_bwd", "harp_mesh_build_fwd",
            "harp_mesh_build_bwd", "harp_vertex_normals_fwd", "harp_vertex_normals_bwd", "harp_mesh_losses", "harp_silhouette", "harp_shade", "harp_hit_mask", "harp_render_normals", "harp_render_fused", "harp_step_fused", "harp_step_workspace_floats", "harp_step_workspace_views", "harp_frame_glue_fwd", "harp_frame_glue_bwd", "harp_texture_reg", "harp_mse", "harp_image_metrics", "harp_ingest_u8", "harp_adam", "harp_adam_dev",
            "harp_peer_create", "harp_peer_connect", "harp_peer_allreduce", "harp_peer_destroy"]
 
@@ -95,6 +95,7 @@ def lib():
         L.harp_ctx_dims.argtypes = [vp, c_int32_p, c_int32_p, c_int32_p, c_int32_p]
         L.harp_ctx_faces.argtypes = [vp, c_int32_p]
         L.harp_ctx_read_counters.argtypes = [vp, C.POINTER(C.c_int64), vp]
+        L.harp_ctx_deferred_pixels.argtypes = [vp, C.POINTER(C.c_int64), vp]
         L.harp_lbs_mano_fwd.argtypes = [vp, i, vp, vp, i, vp, vp, vp, vp]
         L.harp_lbs_mano_bwd.argtypes = [vp, i, vp, vp, i, vp, vp, vp, vp, vp, vp, vp]
         L.harp_mesh_build_fwd.argtypes = [vp, i, vp, vp, vp, vp, vp]

@@ -390,6 +390,21 @@ extern "C" int harp_ctx_read_counters(harp_ctx* c, int64_t out[2], void* stream)
   return HARP_OK;
 }
 
+// Pixels the LAST silhouette pass on this ctx handed to the exact per-pixel top-K kernel (more candidate faces than
+// faces_per_pixel in a tile with more than K faces, or a tile whose band queue overflowed).  Results are exact either way; the
+// number says how far the content is from the fast path (the fallback costs ~0.1 us per pixel).
+extern "C" int harp_ctx_deferred_pixels(harp_ctx* c, int64_t* out, void* stream) {
+  HARP_REQUIRE(c && out, HARP_ERR_INVALID, "harp_ctx_deferred_pixels: null");
+  int32_t h = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->ovf_count) {
+    HARP_CHECK_CUDA(cudaMemcpyAsync(&h, c->ovf_count, sizeof(h), cudaMemcpyDeviceToHost, st));
+    HARP_CHECK_CUDA(cudaStreamSynchronize(st));
+  }
+  *out = h;
+  return HARP_OK;
+}
+
 // MANO (manopth/manolayer.py:70-97) as an instance of the generic model: fold the joint regressor,
 // J(beta) = Jreg v_template + (Jreg shapedirs) beta (manolayer.py:185-188), kinematic tree of manolayer.py:209-242,
 // 21 output joints = 16 chain joints + 5 fingertip vertices in the order of manolayer.py:279.

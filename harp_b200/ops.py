@@ -161,6 +161,12 @@ class HarpContext:
         check(_lib.lib().harp_ctx_read_counters(self.h, out, stream()))
         return {"sil_k_overflow_pixels": int(out[0]), "bin_overflow": int(out[1])}
 
+    def deferred_pixels(self):
+        """Pixels the last silhouette pass handed to the exact top-K fallback kernel (exact results, slower path)."""
+        out = C.c_int64()
+        check(_lib.lib().harp_ctx_deferred_pixels(self.h, C.byref(out), stream()))
+        return int(out.value)
+
 
 def _c(t):
     return t.contiguous().float()

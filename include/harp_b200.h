@@ -111,6 +111,10 @@ HARP_API int harp_ctx_faces(const harp_ctx* ctx, int32_t* faces_out);
  * evaluated exactly (more than 512 passing faces on one pixel, or more than 4M such pixels), [1] bin-list capacity
  * overflows.  Both 0 means every result follows PyTorch3D's semantics.  [host] out. Synchronises. */
 HARP_API int harp_ctx_read_counters(harp_ctx* ctx, int64_t out[2], void* stream);
+/* Pixels the last silhouette pass on this ctx handed to the exact per-pixel top-K kernel (a pixel with more candidate faces than
+ * faces_per_pixel, or a tile whose 256-entry band queue overflowed).  Results are exact either way; the number tells how far the
+ * content is from the fast path.  [host] out.  Synchronises. */
+HARP_API int harp_ctx_deferred_pixels(harp_ctx* ctx, int64_t* out, void* stream);
 
 /* Number of CUDA kernels this library has launched in this process (all contexts), for launch accounting. */
 HARP_API int64_t harp_launch_count(void);

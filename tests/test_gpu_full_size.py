@@ -170,6 +170,18 @@ def test_full_size_alpha_is_reproducible_and_timeline_is_ordered(full_scene):
     assert tl["side_branch"][1] <= tl["shade"][0] + 1e-3  # the shading waits for the light view
 
 
+def test_deferred_pixel_count_is_reported(full_scene):
+    """The exact top-K fallback is a slower path: the benchmark workload must stay (almost) entirely on the fast one, and the
+    diagnostic that says so must work."""
+    hc, sc = full_scene
+    ft = _fitter(hc, sc)
+    fid = torch.arange(FRAMES, device="cuda")
+    ft.step(fid, sc["offsets"]["albedo"], sc["offsets"]["normal"], stage="both", update=False, frame_range=(0, FRAMES))
+    n = hc.deferred_pixels()
+    assert 0 <= n <= FRAMES * SIZE * SIZE // 1000, n  # under 0.1 % of the pixels
+    assert hc.counters() == {"sil_k_overflow_pixels": 0, "bin_overflow": 0}
+
+
 def test_gpu_numa_lookup_never_raises():
     from harp_b200 import hostmem
     node, cpus = hostmem.gpu_numa_node("cuda:0")
