@@ -38,7 +38,10 @@ namespace {
 constexpr int CHUNK = HARP_PV_CHUNK;   // faces staged per bulk-copy round (one lane of warp 0 per face: at most 32)
 static_assert(CHUNK >= 8 && CHUNK <= 32, "one lane of warp 0 per staged face");
 constexpr int NT = HARP_TILE * HARP_TILE;
-constexpr int QCAP = 256;   // band pairs of one tile (all chunks); a tile that needs more goes to the exact per-pixel kernel
+#ifndef HARP_PV_QCAP
+#define HARP_PV_QCAP 256
+#endif
+constexpr int QCAP = HARP_PV_QCAP;   // band pairs of one tile (all chunks); a tile that needs more goes to the exact per-pixel kernel
 constexpr int TIECAP = 128; // visibility candidates within 1e-5 of each other (resolved with the exact depth)
 
 // ---- Blackwell/Hopper async-copy plumbing: mbarrier + bulk global->shared copies (TMA unit; SASS: UBLKCP / SYNCS) ----------

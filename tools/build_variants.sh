@@ -6,8 +6,7 @@ cd "$(dirname "$0")/.."
 mkdir -p harp_b200/variants
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -shared"
 build() { /usr/local/cuda/bin/nvcc $FLAGS $2 harp_b200/csrc/*.cu -o harp_b200/variants/libharpb200_$1.so; }
-build c24m12 "-DHARP_PV_CHUNK=24 -DHARP_PV_MINCTAS=12" &   # tile rasteriser: 16.7 KB of shared memory -> 12 resident CTAs (registers) instead of 11
-build c20m14 "-DHARP_PV_CHUNK=20 -DHARP_PV_MINCTAS=14" &   # 15.4 KB, <= 73 registers -> 14 CTAs / SM
-build c16m16 "-DHARP_PV_CHUNK=16 -DHARP_PV_MINCTAS=16" &   # 13.9 KB, <= 64 registers -> 16 CTAs / SM
+build q192m15 "-DHARP_PV_QCAP=192 -DHARP_PV_MINCTAS=15" &   # tile rasteriser: 14.3 KB, <= 68 registers -> 15 CTAs / SM
+build q192m16 "-DHARP_PV_QCAP=192 -DHARP_PV_MINCTAS=16 -DHARP_PV_CHUNK=16" &   # 13.6 KB, <= 64 registers -> 16 CTAs / SM
 wait
 ls -la harp_b200/variants
