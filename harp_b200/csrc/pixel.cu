@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
   __shared__ unsigned char s_need[NT], s_sat[NT], s_sat2[NT];
   __shared__ float s_px[HARP_TILE], s_py[HARP_TILE];
   __shared__ float red[4];
-  __shared__ int s_qn, s_tn, s_next, s_ovf;
+  __shared__ int s_qn, s_tn, s_next;
+  __shared__ unsigned char s_ovfp[NT];  // pixels with a band pair that did not fit the queue: only THEY go to the exact top-K kernel
   const int S = a.S, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tw = S / HARP_TILE;
   const float sigma = a.sigma, blur = a.blur;
   const float sat = 17.5f * sigma, far = 1.02f * blur;  // margins of the affine classification (raster.cuh: FaceTile)
@@ -237,7 +238,8 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
     const int tx0 = (tile % tw) * HARP_TILE, ty0 = (tile / tw) * HARP_TILE;
     if (tid < HARP_TILE) s_px[tid] = pix_to_ndc(tx0 + tid, S);
     else if (tid < 2 * HARP_TILE) s_py[tid - HARP_TILE] = pix_to_ndc(ty0 + tid - HARP_TILE, S);
-    if (tid == 0) { s_qn = 0; s_tn = 0; s_ovf = 0; s_next = atomicAdd(a.work_ctl + 2, 1); }
+    s_ovfp[tid] = 0;
+    if (tid == 0) { s_qn = 0; s_tn = 0; s_next = atomicAdd(a.work_ctl + 2, 1); }
     __syncthreads();
     const int nidx = s_next;
     const bool have_next = nidx < total;
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
                   e.next = (short)atomicExch(&s_head[pix], slot);
                   s_q[slot] = e;
                 } else {
-                  s_ovf = 1;
+                  s_ovfp[pix] = 1;
                 }
               }
             }
@@ -533,8 +535,9 @@ __global__ void __launch_bounds__(NT, HARP_PV_MINCTAS) tile_raster_kernel(harp_c
           prod = (float)dp;
         }
         float al = nzero > 0 ? 1.f : 1.f - prod;
-        // more candidates than faces_per_pixel (or a band queue that did not fit) -> exact per-pixel top-K kernel
-        deferred = (count_cand && s_cnt[tid] > a.K) || s_ovf != 0;
+        // more candidates than faces_per_pixel, or one of the pixel's band pairs did not fit the queue -> exact per-pixel top-K
+        // kernel (the other pixels of an overflowing tile have complete chains and stay on this path)
+        deferred = (count_cand && s_cnt[tid] > a.K) || s_ovfp[tid] != 0;
         if (deferred) sil_defer_overflow(c, (int)pix);
         else if (a.alpha) a.alpha[pix] = al;
         if (SIL_BWD && !deferred && !a.g_alpha) diff = al - a.y_sil[pix];
