@@ -130,10 +130,41 @@ class PeerExchange:
             self.h = None
 
 
+class FrameStore:
+    """the sequence's frames decoded ONCE and kept in HBM as uint8 — 4 B per pixel instead of the 20 B of the
+    reference's float32 `y_true` / `y_sil` / `y_sil_eroded` tensors (ImagesDataset + load_img, utils/data_util.py:11-51, decode,
+    divide and erode every frame on the host again in every epoch).  rgb (T,S,S,3) uint8, mask (T,S,S) uint8 (0 / 255),
+    init_joints (T,21,3) mm.  Pass it to `HarpFitter(frames=...)`: every step converts (/255) and erodes its minibatch on the
+    device (`harp_ingest_u8`, bit-identical to `load_img`)."""
+
+    def __init__(self, rgb_u8, mask_u8, init_joints, device="cuda"):
+        self.rgb = torch.as_tensor(rgb_u8).to(device=device, dtype=torch.uint8).contiguous()
+        self.mask = torch.as_tensor(mask_u8).to(device=device, dtype=torch.uint8).contiguous()
+        self.init_joints = torch.as_tensor(init_joints).to(device=device, dtype=torch.float32).contiguous()
+        if self.rgb.dim() != 4 or self.rgb.shape[-1] != 3 or self.mask.shape != self.rgb.shape[:3]:
+            raise ValueError("FrameStore: rgb (T,S,S,3) uint8 and mask (T,S,S) uint8 expected")
+
+    def __len__(self):
+        return self.rgb.shape[0]
+
+    @property
+    def nbytes(self):
+        return self.rgb.numel() + self.mask.numel() + 4 * self.init_joints.numel()
+
+    def batch(self, fid=None, frame_range=None):
+        """-> dict(rgb, mask, init_joints) of a minibatch (views when a contiguous `frame_range` is promised)."""
+        if frame_range is not None:
+            a, b = frame_range
+            return dict(rgb=self.rgb[a:b], mask=self.mask[a:b], init_joints=self.init_joints[a:b])
+        return dict(rgb=self.rgb.index_select(0, fid), mask=self.mask.index_select(0, fid),
+                    init_joints=self.init_joints.index_select(0, fid))
+
+
 class HarpFitter:
     """params: dict with the reference's keys (`optimize_sequence.py:181-250`): pose (T,45), rot (T,3), trans (T,3),
     cam (T,3), shape (10,), verts_disps (V,1), texture / normal_map (1,H,W,3), light_positions (T,3), amb_ratio ().
-    frames: y_true (T,S,S,3), y_sil (T,S,S), y_sil_eroded (T,S,S), init_joints (T,21,3) [mm] — device resident.
+    frames: y_true (T,S,S,3), y_sil (T,S,S), y_sil_eroded (T,S,S), init_joints (T,21,3) [mm] — device resident; or a
+    `FrameStore` (uint8 frames + masks, converted and eroded per minibatch on the device).
     ref_verts: (1,V,3) ARAP reference (`optimize_sequence.py:429-435`); uv_mask (H,W)."""
 
     def __init__(self, hc, params, frames, ref_verts, uv_mask, img_size, focal_length, self_shadow=True,
@@ -182,7 +213,8 @@ class HarpFitter:
         self.rot, self.trans = f32(params["rot"]), f32(params["trans"])
         if self.opt_arm_pose:
             self.rot, self.wrist = self.coarse.p["rot"], self.coarse.p["wrist_pose"]
-        self.frames = {k: f32(v) for k, v in frames.items()}
+        self.store = frames if isinstance(frames, FrameStore) else None
+        self.frames = {"init_joints": self.store.init_joints} if self.store is not None else {k: f32(v) for k, v in frames.items()}
         self.ref_verts = f32(ref_verts).view(-1, 3)
         self.uv_mask = f32(uv_mask)
         self.T = self.rot.shape[0]
@@ -250,6 +282,8 @@ class HarpFitter:
         R = self.world_size
         hc.reserve(B, S)
         P, A = self.coarse.p, self.app.p
+        if batch is None and batch_u8 is None and self.store is not None:
+            batch_u8 = self.store.batch(fid, frame_range)
         if batch_u8 is not None:
             from .ops import ingest_u8
             fr = ingest_u8(batch_u8["rgb"], batch_u8["mask"],

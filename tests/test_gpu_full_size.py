@@ -189,3 +189,36 @@ def test_gpu_numa_lookup_never_raises():
     with hostmem.gpu_numa_affinity("cuda:0") as info:
         pinned = torch.empty(1 << 20, pin_memory=True)
         assert pinned.is_pinned() and set(info) == {"numa_node", "cpus"}
+
+
+def test_uint8_frame_store_equals_float_frames():
+    """a fitter fed from a uint8 FrameStore (4 B/pixel resident, converted and eroded per minibatch on the device)
+    takes the same step as one holding the float32 frames `load_img` would have produced from the same bytes."""
+    from harp_b200 import scene
+    from harp_b200.ops import ingest_u8
+    from harp_b200.step import FrameStore, HarpFitter
+    T, S = 8, 256
+    hc, _, _ = scene.make_context(device="cuda:0", model="hand")
+    sc = scene.make_scene(hc, T, S, seed=3)
+    rgb = (sc["frames"]["y_true"] * 255).round().clamp(0, 255).to(torch.uint8)
+    mask = (sc["frames"]["y_sil"] * 255).round().to(torch.uint8)
+    fl = ingest_u8(rgb, mask)
+    fl = dict(y_true=fl["y_true"].clone(), y_sil=fl["y_sil"].clone(), y_sil_eroded=fl["y_sil_eroded"].clone(),
+              init_joints=sc["frames"]["init_joints"])
+    store = FrameStore(rgb, mask, sc["frames"]["init_joints"])
+    assert len(store) == T and store.nbytes < 0.21 * sum(v.numel() * 4 for v in fl.values())
+    fa = HarpFitter(hc, sc["params"], fl, sc["ref_verts"], sc["uv_mask"], S, sc["focal"])
+    fb = HarpFitter(hc, sc["params"], store, sc["ref_verts"], sc["uv_mask"], S, sc["focal"])
+    oa, on = sc["offsets"]["albedo"], sc["offsets"]["normal"]
+    for fid in (torch.arange(T, device="cuda"), torch.tensor([5, 1, 6, 2], device="cuda")):
+        la = fa.step(fid, oa, on, stage="both", update=False).clone()
+        alpha_a, rgb_a = fa.last["alpha"].clone(), fa.last["rgb"].clone()
+        ga = fa.coarse.grad.clone()
+        lb = fb.step(fid, oa, on, stage="both", update=False).clone()
+        assert torch.equal(alpha_a, fb.last["alpha"]) and torch.equal(rgb_a, fb.last["rgb"])
+        assert torch.allclose(la, lb, rtol=1e-5, atol=1e-8)
+        assert float((ga - fb.coarse.grad).norm() / ga.norm()) < 1e-5
+    replay = fb.capture(torch.arange(T, device="cuda"), oa, on, stage="both", frame_range=(0, T))  # also under a captured graph
+    replay()
+    torch.cuda.synchronize()
+    assert math.isfinite(fb.loss_dict()["total"])
