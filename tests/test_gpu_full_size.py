@@ -222,3 +222,37 @@ def test_uint8_frame_store_equals_float_frames():
     replay()
     torch.cuda.synchronize()
     assert math.isfinite(fb.loss_dict()["total"])
+
+
+@pytest.mark.parametrize("model,size,frames", [("arm", 448, 12), ("arm", 1024, 6)])
+def test_arm_step_equals_two_half_steps(model, size, frames):
+    """The same frame-independence property on the SMPL-X-arm model at the reference's default size (448, utils/config_utils.py:10)
+    and at BASELINE configs[3]'s 1024^2: sizes the CPU oracle cannot reach with more than one or two frames."""
+    from harp_b200 import scene
+    from harp_b200.step import HarpFitter
+    hc, _, _ = scene.make_context(device="cuda:0", model=model)
+    sc = scene.make_scene(hc, frames, size, seed=2)
+    oa, on = sc["offsets"]["albedo"], sc["offsets"]["normal"]
+    per_frame = ("pose", "rot", "trans", "cam", "light_positions", "wrist_pose")
+
+    def fitter(lo, hi):
+        p = {k: (v[lo:hi] if k in per_frame else v) for k, v in sc["params"].items()}
+        fr = {k: v[lo:hi] for k, v in sc["frames"].items()}
+        return HarpFitter(hc, p, fr, sc["ref_verts"], sc["uv_mask"], size, sc["focal"])
+
+    whole = fitter(0, frames)
+    whole.step(torch.arange(frames, device="cuda"), oa, on, stage="both", update=False, frame_range=(0, frames))
+    gw = {k: v.clone() for k, v in whole.coarse.g.items()}
+    lw = whole.loss_dict()
+    assert hc.counters() == {"sil_k_overflow_pixels": 0, "bin_overflow": 0}
+    H, halves = frames // 2, []
+    for lo in (0, H):
+        ft = fitter(lo, lo + H)
+        ft.step(torch.arange(H, device="cuda"), oa, on, stage="both", update=False, frame_range=(0, H))
+        halves.append(({k: v.clone() for k, v in ft.coarse.g.items()}, ft.loss_dict()))
+    for k in ("pose", "cam"):
+        both = torch.cat([h[0][k] for h in halves]) * 0.5
+        assert float((both - gw[k]).norm() / gw[k].norm()) < 1e-3, k
+    for k in ("silhouette", "photo", "kps_anchor", "laplacian", "arap"):
+        avg = 0.5 * (halves[0][1][k] + halves[1][1][k])
+        assert math.isclose(avg, lw[k], rel_tol=2e-4), (k, avg, lw[k])
