@@ -391,9 +391,9 @@ def main():
         return float(sec)
 
     # ---- end to end through the public call with HOST image buffers (pinned): every step copies its frames host->device
-    # and reads the loss vector back.  Leg 1: fp32 y_true / y_sil / y_sil_eroded, the dtypes the reference's DataLoader
-    # yields (20 B/pixel).  Leg 2: the uint8 frames + masks the image files decode to (4 B/pixel), converted and eroded on
-    # the device (harp_ingest_u8) — reported separately as e2e_uint8.
+    # and reads the loss vector back.  Leg 1 (`e2e_float32_host`): fp32 y_true / y_sil / y_sil_eroded, the dtypes the reference's
+    # DataLoader yields (20 B/pixel).  Leg 2 (`e2e`): the uint8 frames + masks the image files decode to (4 B/pixel), converted
+    # and eroded on the device (harp_ingest_u8): the plugin's ingest API.
     from harp_b200.hostmem import gpu_numa_affinity
     with gpu_numa_affinity(dev) as host_affinity:  # pinned staging pages on the GPU's NUMA node
         host = {k: ft.frames[k].cpu().pin_memory() for k in ("y_true", "y_sil", "y_sil_eroded")}
@@ -482,10 +482,15 @@ def main():
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config(world, B, S, args.model),
                 "clocks": clk,
-                "e2e": {"value": world * B * k_e2e / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": k_e2e, "host_dtype": "fp32 (the reference DataLoader's tensors)", "host_affinity": host_affinity},
-                "e2e_uint8": {"value": world * B * k_e2e / e2e_u8_s, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
-                              "steps": k_e2e, "host_dtype": "uint8 frames + masks, /255 and 3x3x2 erosion on the device"},
+                # e2e = the plugin's ingest API (HarpFitter.step(batch_u8=...) -> harp_ingest_u8): host buffers are the decoded uint8
+                # frames + masks as the image files hold them; the float conversion and the mask erosion of the reference's
+                # load_img (utils/data_util.py:11-30) happen on the device, bit-identically (tests/test_io_fixtures.py).
+                # e2e_float32_host = the same step fed the reference DataLoader's float32 tensors (20 B/pixel): PCIe-bound.
+                "e2e": {"value": world * B * k_e2e / e2e_u8_s, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
+                        "steps": k_e2e, "host_dtype": "uint8 frames + masks (what load_img decodes); /255 and 3x3x2 erosion on the device",
+                        "host_affinity": host_affinity},
+                "e2e_float32_host": {"value": world * B * k_e2e / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                     "steps": k_e2e, "host_dtype": "fp32 y_true / y_sil / y_sil_eroded (the reference DataLoader's tensors)"},
                 "e2e_resident_epochs": e2e_res,
                 "gpu_launches": int(launches), "launch_mode": "cuda_graph_replay" if use_graph else "eager",
                 "exchange": {"none": "single GPU", "peer": "reduce-scatter + all-gather kernel over NVLink peer memory inside the step graph",

@@ -20,7 +20,7 @@ python - <<PY
 import json
 d = json.load(open("gpurun_out/${TAG}_bench.json"))
 r = d["roofline"]
-print("value", round(d["value"]), "ms/step", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"]), "u8", round(d["e2e_uint8"]["value"]),
+print("value", round(d["value"]), "ms/step", round(d["ms_per_step"], 3), "e2e(u8)", round(d["e2e"]["value"]), "f32host", round(d["e2e_float32_host"]["value"]),
       "dom", r["kernel"][:20], round(r["kernel_ms"], 3), {k[:14]: round(v, 3) for k, v in r["other_kernel_ms"].items()}, d["counters"])
 print("standin", d.get("gpu_eager_standin"), "dropin", d.get("dropin_level1"))
 PY
