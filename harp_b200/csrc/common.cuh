@@ -57,6 +57,9 @@ struct harp_ctx {
   int32_t* vf_idx = nullptr;
   uint32_t* vf_ring = nullptr;   // per incidence (same order as vf_idx): next | prev << 16, the face's other two vertices in
                                  // cyclic order after this one, so the corner's cross product is (next - self) x (prev - self)
+  uint4* vf_ring8 = nullptr;     // (V,2) the same entries at a fixed stride of eight per vertex, padded with 0xffffffff: one aligned
+                                 // 32-byte load and no offset lookup (a dependent global access less per gather); null when some
+                                 // vertex has more than eight incident faces (the CSR tables above are then used)
   int32_t* vn_off = nullptr;     // (V+1) vertex -> neighbour vertex CSR (final mesh edges)
   int32_t* vn_idx = nullptr;
   int32_t* edges = nullptr;      // (E,2) final edges, PyTorch3D edges_packed order

@@ -213,6 +213,16 @@ extern "C" int harp_ctx_create_lbs(harp_ctx** out, const harp_topology* topo, co
       ring[i] = (uint32_t)faces[3 * f + (k + 1) % 3] | ((uint32_t)faces[3 * f + (k + 2) % 3] << 16);
     }
     UP(vf_ring, ring);
+    int max_valence = 0;
+    for (int v = 0; v < c->V; ++v) max_valence = std::max(max_valence, off[v + 1] - off[v]);
+    if (max_valence <= 8) {  // the MANO / SMPL-X-arm meshes and their subdivisions: at most 8
+      std::vector<uint32_t> ring8((size_t)c->V * 8, 0xffffffffu);
+      for (int v = 0; v < c->V; ++v)
+        for (int i = off[v]; i < off[v + 1]; ++i) ring8[(size_t)v * 8 + (i - off[v])] = ring[i];
+      uint32_t* dev = nullptr;
+      if ((rc = upload(&dev, ring8)) != HARP_OK) { harp_ctx_destroy(c); return rc; }
+      c->vf_ring8 = reinterpret_cast<uint4*>(dev);
+    }
   }
   csr_from_lists(vn, off, idx);  UP(vn_off, off);  UP(vn_idx, idx);
   csr_from_lists(v0e, off, idx); UP(v0e_off, off); UP(v0e_idx, idx);
@@ -288,7 +298,7 @@ extern "C" void harp_ctx_destroy(harp_ctx* c) {
   if (!c) return;
   free_scratch(c);
   void* ptrs[] = {c->faces, c->edges0, c->v0e_off, c->v0e_idx, c->vf_off, c->vf_idx, c->vn_off, c->vn_idx, c->edges,
-                  c->nc_pairs, c->face_uvs, c->vf_ring, c->shapedirs, c->posedirs, c->v_template, c->weights,
+                  c->nc_pairs, c->face_uvs, c->vf_ring, c->vf_ring8, c->shapedirs, c->posedirs, c->v_template, c->weights,
                   c->J_template, c->J_shapedirs, c->tips, c->counters, c->d_tex4, c->tex4, c->weightsT, c->pose_mean, c->parents,
                   c->joint_out_src};
   for (void* p : ptrs) if (p) cudaFree(p);

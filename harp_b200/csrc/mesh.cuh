@@ -30,8 +30,19 @@ struct DirectAccessor {
 template <typename Acc>
 __device__ __forceinline__ f3 vertex_normal_sum(const harp_ctx& c, const Acc& acc, int v) {
   f3 n = mk3(0.f, 0.f, 0.f);
-  const int i0 = c.vf_off[v], i1 = c.vf_off[v + 1];
   const f3 a = acc(v);
+  if (c.vf_ring8) {  // fixed-stride table: one aligned 32-byte load, entries in the same order as the CSR walk below
+    const uint4 r0 = __ldg(c.vf_ring8 + 2 * (size_t)v), r1 = __ldg(c.vf_ring8 + 2 * (size_t)v + 1);
+    const uint32_t ring[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (ring[k] == 0xffffffffu) continue;
+      f3 b = acc((int)(ring[k] & 0xffffu)), d = acc((int)(ring[k] >> 16));
+      n = n + cross(b - a, d - a);
+    }
+    return n;
+  }
+  const int i0 = c.vf_off[v], i1 = c.vf_off[v + 1];
   for (int base = i0; base < i1; base += 8) {
     uint32_t ring[8];
 #pragma unroll
@@ -68,8 +79,20 @@ __device__ __forceinline__ f3 normalize_bwd(f3 x, f3 gy, float eps) {
 template <typename Acc>
 __device__ __forceinline__ f3 normal_grad_gather(const harp_ctx& c, const Acc& acc, const float* dN, int u) {
   f3 g = mk3(0.f, 0.f, 0.f);
-  const int i0 = c.vf_off[u], i1 = c.vf_off[u + 1];
   const f3 Gu = ld3(dN + (size_t)u * 3);
+  if (c.vf_ring8) {
+    const uint4 r0 = __ldg(c.vf_ring8 + 2 * (size_t)u), r1 = __ldg(c.vf_ring8 + 2 * (size_t)u + 1);
+    const uint32_t ring[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (ring[k] == 0xffffffffu) continue;
+      int nx = (int)(ring[k] & 0xffffu), pv = (int)(ring[k] >> 16);
+      f3 G = Gu + ld3(dN + (size_t)nx * 3) + ld3(dN + (size_t)pv * 3);
+      g = g + cross(acc(nx) - acc(pv), G);
+    }
+    return g;
+  }
+  const int i0 = c.vf_off[u], i1 = c.vf_off[u + 1];
   for (int base = i0; base < i1; base += 8) {
     uint32_t ring[8];
 #pragma unroll

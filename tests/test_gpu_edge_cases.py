@@ -204,3 +204,35 @@ def test_learning_rate_change_under_a_captured_graph():
     torch.cuda.synchronize()
     assert float((ft.coarse.data - before_c).abs().max()) > 1e-5 and float((ft.app.data - before_a).abs().max()) > 1e-4
     assert ft.lr_coarse == 1e-3 and ft.lr_app == 1e-2
+
+
+def test_vertex_normals_on_a_high_valence_mesh_use_the_csr_tables():
+    """The hand / arm meshes have at most 8 faces around a vertex, so their gathers read the fixed-stride ring table; a topology with
+    a higher valence falls back to the CSR tables.  Both paths must give PyTorch3D's area-weighted vertex normals and their
+    gradient (Meshes._compute_vertex_normals)."""
+    import numpy as np
+    from harp_b200.ops import HarpContext, VertexNormals
+    for n_fan in (7, 11):  # a closed double fan around an axis: the two poles have valence n_fan
+        ring = [(np.cos(2 * np.pi * k / n_fan), np.sin(2 * np.pi * k / n_fan), 0.1 * np.sin(3.0 * k)) for k in range(n_fan)]
+        verts = np.array([(0.0, 0.0, 0.7), (0.0, 0.0, -0.6)] + ring, np.float32)
+        faces = []
+        for k in range(n_fan):
+            a, b = 2 + k, 2 + (k + 1) % n_fan
+            faces += [(0, a, b), (1, b, a)]
+        faces = np.array(faces, np.int32)
+        hc = HarpContext(faces, subdivide=False, device="cuda:0")
+        v = torch.tensor(verts[None], device="cuda", requires_grad=True)
+        n = VertexNormals.apply(hc, v)
+        w = torch.linspace(0.5, 1.5, n.numel(), device="cuda").view_as(n)
+        (n * w).sum().backward()
+        vr = torch.tensor(verts[None], dtype=torch.float64, requires_grad=True)
+        f = torch.tensor(faces, dtype=torch.long)
+        p0, p1, p2 = vr[0, f[:, 0]], vr[0, f[:, 1]], vr[0, f[:, 2]]
+        acc = torch.zeros(len(verts), 3, dtype=torch.float64)
+        acc = acc.index_add(0, f[:, 0], torch.cross(p1 - p0, p2 - p0, dim=1))
+        acc = acc.index_add(0, f[:, 1], torch.cross(p2 - p1, p0 - p1, dim=1))
+        acc = acc.index_add(0, f[:, 2], torch.cross(p0 - p2, p1 - p2, dim=1))
+        nr = torch.nn.functional.normalize(acc, eps=1e-6, dim=1)[None]
+        (nr * w.double().cpu()).sum().backward()
+        assert float((n.detach().cpu().double() - nr.detach()).abs().max()) < 2e-6, n_fan
+        assert float((v.grad.cpu().double() - vr.grad).norm() / vr.grad.norm()) < 1e-5, n_fan
